@@ -1,0 +1,25 @@
+"""B200-native (sm_100a) inference hot path of optical-flow deep video stabilisation.
+
+Drop-in host mirror of the reference call signatures, backed by libofstab.so (C ABI, include/ofstab.h):
+
+    from coupe.optical_flow_based_deep_video_stabilization_b200 import (
+        flownetS_pyramid, load_and_assign_npz_dict, tf_warp, AffineTransformer, transformImage)
+
+No CPU fallback, no Triton, no backend dispatch: importing is cheap, the first device call loads
+(and if needed builds) the CUDA library and raises if that is impossible.
+"""
+from ._lib import OfstabError, lib_path, load as load_library            # noqa: F401
+from .model import (FlowNetSPyramid, assign_weights, flownetS_pyramid, get_net,                 # noqa: F401
+                    load_and_assign_npz_dict)
+from .ops import (conv2d_nhwc, flow_resize, flow_resize_warp, get_pixel_value, set_warp_variant,  # noqa: F401
+                  tf_warp)
+from .spatial_transformer import AffineTransformer, ProjectiveTransformer, transformer          # noqa: F401
+from .warp import compose, fit, inverse, transformCropImage, transformImage, vec2mtrx           # noqa: F401
+
+__all__ = [
+    "FlowNetSPyramid", "flownetS_pyramid", "load_and_assign_npz_dict", "assign_weights", "get_net",
+    "tf_warp", "get_pixel_value", "flow_resize", "flow_resize_warp", "set_warp_variant", "conv2d_nhwc",
+    "AffineTransformer", "ProjectiveTransformer", "transformer",
+    "vec2mtrx", "transformImage", "transformCropImage", "fit", "compose", "inverse",
+    "OfstabError", "lib_path", "load_library",
+]

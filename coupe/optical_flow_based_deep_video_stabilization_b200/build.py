@@ -1,0 +1,74 @@
+"""In-tree build of libofstab.so (nvcc, sm_100a only).
+
+    python -m coupe.optical_flow_based_deep_video_stabilization_b200.build [--force]
+
+The library is a plain C-ABI shared object (no torch, no pybind): nvcc cross-compiles it on a
+box without a GPU, and the built .so travels with the source tree to the GPU box.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+REPO = os.path.abspath(os.path.join(HERE, "..", ".."))
+LIB_PATH = os.path.join(HERE, "libofstab.so")
+STAMP = os.path.join(HERE, ".libofstab.stamp")
+
+SOURCES = ["ofs_common.cu", "samplers.cu", "conv_gemm.cu", "flownet.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC",
+    "--shared",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: libofstab.so cannot be built (there is no CPU fallback)")
+
+
+def source_digest():
+    h = hashlib.sha256()
+    files = sorted(os.listdir(CSRC)) + ["../../../include/ofstab.h"]
+    for name in files:
+        path = os.path.normpath(os.path.join(CSRC, name))
+        if os.path.isfile(path):
+            h.update(name.encode())
+            with open(path, "rb") as f:
+                h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def is_fresh():
+    if not (os.path.exists(LIB_PATH) and os.path.exists(STAMP)):
+        return False
+    with open(STAMP) as f:
+        return f.read().strip() == source_digest()
+
+
+def build_library(force=False, verbose=False):
+    """Compile csrc/*.cu into libofstab.so when sources changed.  Returns the library path."""
+    if not force and is_fresh():
+        return LIB_PATH
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    with open(STAMP, "w") as f:
+        f.write(source_digest())
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,719 @@
+// Implicit-GEMM convolution and k4-s2 transposed convolution for sm_100a.
+//
+// Replaces, per layer of flownetS_pyramid (reference model.py:807-885):
+//   PadLayer(zeros) + Conv2d(VALID, stride s) + bias [+ BatchNormLayer folded into W'/b'] + lrelu(0.1)
+//   DeConv2dLayer(4,4,s2,SAME) + bias [+ BN folded] + lrelu(0.1)   as 4 sub-pixel phase GEMMs
+//   the N=2 flow heads and the predict2 1x1 product (fp32 output mode)
+//
+// GEMM view:  D[m, n] = sum_{tap, c} A[pixel m shifted by tap, c] * W[n, (tap, c)]
+//   M tile  = 128 output pixels = tileH rows x tileW pixels of the output grid (rows may run over
+//             several images: (b, y) is one "global row" axis)
+//   K block = 64 channels of one tap = one 128-byte row per pixel
+//   A tile  = TMA box {64 ch, tileW, 1, rpl rows, 1} out of a 5-D view of the NHWC activation.
+//             Zero padding, image borders, ragged channel tails and ragged batches are all TMA
+//             out-of-bounds zero fill -- no padded copy of the activation exists.  A stride-2
+//             conv uses a parity view [(xpar, c), x/2, ypar, y/2, b] of the same buffer so that
+//             every tap is still a dense box.
+//   B tile  = TMA box {64, BLOCK_N} of the packed K-major weights.
+//   MMA     = tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16, fp32 accumulators in TMEM
+//             (two accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1).
+//   Roles   = warp 0: TMA producer, warp 1: MMA issuer (+ TMEM alloc), warps 2-5: epilogue
+//             (tcgen05.ld -> +bias -> lrelu -> 16-bit pack -> 128-bit stores into the channel
+//             slice of the consumer's concat buffer).  Persistent: grid = min(tiles, #SM).
+#include "conv_gemm.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "ptx.cuh"
+
+namespace ofs {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kThreads = 192;
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kStages = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+  static constexpr int kBarBytes = 256;
+  static constexpr size_t kSmem = (size_t)kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+};
+
+__device__ __forceinline__ uint32_t pack16(float a, float b, int is_bf16) {
+  if (is_bf16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;                         // [kStages]  TMA -> MMA
+  uint64_t* empty = bars + Cfg::kStages;         // [kStages]  MMA -> TMA
+  uint64_t* tfull = bars + 2 * Cfg::kStages;     // [2]        MMA -> epilogue
+  uint64_t* tempty = bars + 2 * Cfg::kStages + 2;  // [2]      epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&p.tmap_a);
+    ptx::prefetch_tensormap(&p.tmap_w);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull[i], 1);
+      ptx::mbar_init(&tempty[i], 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_kb = p.ntaps * p.nchunks;
+  const int total_tiles = p.tiles_m * p.tiles_n * p.phases;
+  const int tileW = 1 << p.tileW_log2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================================ TMA producer ================================
+      int stage = 0;
+      uint32_t phase = 0;
+      const int npieces = p.tileH / p.rpl;
+      const int piece_bytes = p.rpl * tileW * kBlockK * 2;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_t = tile % p.tiles_n;
+        const int rest = tile / p.tiles_n;
+        const int m_t = rest % p.tiles_m;
+        const int ph = rest / p.tiles_m;
+        const int gy0 = (m_t / p.tiles_x) * p.tileH;
+        const int ox0 = (m_t % p.tiles_x) << p.tileW_log2;
+        const int w_row = ph * p.n_pad + n_t * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / p.nchunks;
+          const int ch = kb - tap * p.nchunks;
+          const int ti = ph * p.ntaps + tap;
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          ptx::mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+          uint8_t* sa = smem + (size_t)stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          const int c = p.tap_c[ti] + ch * kBlockK;
+          const int x = ox0 + p.tap_x[ti];
+          const int pp = p.tap_p[ti];
+          for (int pc = 0; pc < npieces; ++pc) {
+            const int gy = gy0 + pc * p.rpl;
+            const int b = gy / p.Hg;
+            const int y = gy - b * p.Hg + p.tap_y[ti];
+            ptx::tma_load_5d(sa + (size_t)pc * piece_bytes, &p.tmap_a, &full[stage], c, x, pp, y, b);
+          }
+          ptx::tma_load_2d(sb, &p.tmap_w, &full[stage], kb * kBlockK, w_row);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================================ MMA issuer ==================================
+      const uint32_t idesc = ptx::umma_idesc_f16(kBlockM, BLOCK_N, p.is_bf16);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + (size_t)stage * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t da = ptx::umma_desc_sw128(a_addr + k * 32);
+            const uint64_t db = ptx::umma_desc_sw128(b_addr + k * 32);
+            ptx::tc_mma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::tc_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::tc_commit(&tfull[acc]);  // accumulator complete
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ================================== epilogue ====================================
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;    // GEMM row inside the tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_t = tile % p.tiles_n;
+      const int rest = tile / p.tiles_n;
+      const int m_t = rest % p.tiles_m;
+      const int ph = rest / p.tiles_m;
+      const int gy = (m_t / p.tiles_x) * p.tileH + (row >> p.tileW_log2);
+      const int gx = ((m_t % p.tiles_x) << p.tileW_log2) + (row & (tileW - 1));
+      const bool valid = gy < p.rows_total;
+      const int b = gy / p.Hg;
+      const int y = gy - b * p.Hg;
+      const int oy = y * p.out_scale + p.out_oy[ph];
+      const int ox = gx * p.out_scale + p.out_ox[ph];
+      const size_t pix = ((size_t)b * p.out_H + oy) * p.out_W + ox;
+      const int n0 = n_t * BLOCK_N;
+
+      ptx::mbar_wait(&tfull[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      constexpr int kChunk = BLOCK_N >= 32 ? 32 : 16;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += kChunk) {
+        uint32_t v[kChunk];
+        if constexpr (kChunk == 32) ptx::tmem_ld32(t_addr + c0, v); else ptx::tmem_ld16(t_addr + c0, v);
+        ptx::tmem_wait_ld();
+        if (valid) {
+          const float* bias = p.bias + n0 + c0;
+          if (p.out_mode == 0) {
+            uint32_t pk[kChunk / 2];
+#pragma unroll
+            for (int j = 0; j < kChunk / 2; ++j) {
+              float a = __uint_as_float(v[2 * j]) + __ldg(bias + 2 * j);
+              float c = __uint_as_float(v[2 * j + 1]) + __ldg(bias + 2 * j + 1);
+              if (p.lrelu) { a = fmaxf(a, 0.1f * a); c = fmaxf(c, 0.1f * c); }
+              pk[j] = pack16(a, c, p.is_bf16);
+            }
+            uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + pix * p.out_cstride + p.out_coff + n0 + c0;
+            uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+            for (int j = 0; j < kChunk / 8; ++j) o4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          } else {
+            float* o = reinterpret_cast<float*>(p.out) + pix * p.out_cstride + p.out_coff;
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+              const int col = n0 + c0 + j;
+              if (col < p.n_valid) {
+                float a = __uint_as_float(v[j]) + __ldg(bias + j);
+                if (p.lrelu) a = fmaxf(a, 0.1f * a);
+                o[col] = a;
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_act_kernel(const float* __restrict__ in, uint4* __restrict__ out, size_t npix, int cin, int cs,
+                                int is_bf16) {
+  const int groups = cs >> 3;
+  const size_t total = npix * groups;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = i / groups;
+    const int c0 = (int)(i - pix * groups) << 3;
+    const float* src = in + pix * cin;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c0 + j < cin) ? __ldg(src + c0 + j) : 0.0f;
+    out[i] = make_uint4(pack16(v[0], v[1], is_bf16), pack16(v[2], v[3], is_bf16), pack16(v[4], v[5], is_bf16),
+                        pack16(v[6], v[7], is_bf16));
+  }
+}
+
+__global__ void unpack_act_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, size_t npix, int cs,
+                                  int coff, int c, int is_bf16) {
+  const size_t total = npix * c;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = i / c;
+    const int ch = (int)(i - pix * c);
+    const uint16_t raw = in[pix * cs + coff + ch];
+    float f;
+    if (is_bf16) {
+      f = __uint_as_float((uint32_t)raw << 16);
+    } else {
+      __half h = *reinterpret_cast<const __half*>(&raw);
+      f = __half2float(h);
+    }
+    out[i] = f;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+int encode_map(CUtensorMap* map, int is_bf16, int rank, const void* base, const cuuint64_t* dims,
+               const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return OFS_ECUDA;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
+                  const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,%llu,%llu,%llu] box0=%u", (int)r,
+              rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+              (unsigned long long)(rank > 3 ? dims[3] : 0), (unsigned long long)(rank > 4 ? dims[4] : 0), box[0]);
+    return OFS_ECUDA;
+  }
+  return OFS_OK;
+}
+
+template <int BLOCK_N>
+int launch_t(const ConvPlan& plan, cudaStream_t st) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  OFS_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    OFS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)GemmCfg<BLOCK_N>::kSmem));
+    attr_set[dev] = true;
+  }
+  conv_gemm_kernel<BLOCK_N><<<plan.grid, kThreads, GemmCfg<BLOCK_N>::kSmem, st>>>(plan.p);
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
+}
+
+int ilog2(int v) {
+  int l = 0;
+  while ((1 << (l + 1)) <= v) ++l;
+  return l;
+}
+int gcd(int a, int b) { return b == 0 ? a : gcd(b, a % b); }
+
+}  // namespace
+
+uint16_t f32_to_bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+uint16_t f32_to_fp16_rn(float f) {
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  x &= 0x7fffffffu;
+  if (x > 0x7f800000u) return (uint16_t)(sign | 0x7e00u);   // NaN
+  if (x >= 0x47800000u) return (uint16_t)(sign | 0x7c00u);  // >= 65536 or inf
+  if (x < 0x38800000u) {                                    // below 2^-14: subnormal half (or zero)
+    const int e = (int)(x >> 23);
+    if (e < 102) return (uint16_t)sign;                     // < 2^-25 rounds to zero
+    const uint32_t m = (x & 0x7fffffu) | 0x800000u;
+    const int shift = 126 - e;                              // 14..24
+    uint32_t r = m >> shift;
+    const uint32_t rem = m & ((1u << shift) - 1u);
+    const uint32_t halfway = 1u << (shift - 1);
+    if (rem > halfway || (rem == halfway && (r & 1u))) ++r;
+    return (uint16_t)(sign | r);
+  }
+  uint32_t r = x - 0x38000000u;                             // rebias exponent 127 -> 15
+  r += 0xfffu + ((r >> 13) & 1u);                           // round to nearest even on 13 dropped bits
+  r >>= 13;
+  if (r > 0x7c00u) r = 0x7c00u;
+  return (uint16_t)(sign | r);
+}
+
+void conv_act_view(const ConvDesc& d, unsigned long long dims[5], unsigned long long strides_bytes[4]) {
+  const unsigned long long cs = (unsigned long long)d.in_cs, H = (unsigned long long)d.H, W = (unsigned long long)d.W,
+                           B = (unsigned long long)d.B;
+  if (d.kind == kConv && d.stride == 2) {
+    // parity view: [(xpar, c), x/2, ypar, y/2, b]
+    dims[0] = 2 * cs; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = B;
+    strides_bytes[0] = 2 * cs * 2; strides_bytes[1] = W * cs * 2; strides_bytes[2] = 2 * W * cs * 2;
+    strides_bytes[3] = H * W * cs * 2;
+  } else {
+    // [c, x, 1, y, b]; the ragged tail of the last 64-channel chunk is out-of-bounds zero fill
+    dims[0] = cs; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = B;
+    strides_bytes[0] = cs * 2; strides_bytes[1] = W * cs * 2; strides_bytes[2] = W * cs * 2;
+    strides_bytes[3] = H * W * cs * 2;
+  }
+}
+
+int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
+  plan = ConvPlan();
+  plan.d = d;
+  ConvGemmParams& p = plan.p;
+  memset(&p, 0, sizeof(p));
+  OFS_REQUIRE(d.B >= 1 && d.H >= 1 && d.W >= 1 && d.cin >= 1 && d.cout >= 1, "conv plan: bad shape");
+  OFS_REQUIRE(d.in_cs % 8 == 0 && d.in_cs >= d.cin, "conv plan: input channel stride %d must be a multiple of 8 and >= cin %d",
+              d.in_cs, d.cin);
+  OFS_REQUIRE(d.block_n == 16 || d.block_n == 32 || d.block_n == 64 || d.block_n == 128 || d.block_n == 256,
+              "conv plan: block_n %d unsupported", d.block_n);
+  const bool deconv = d.kind == kDeconvK4S2;
+  int Hg, Wg;
+  if (deconv) {
+    OFS_REQUIRE(d.k == 4 && d.stride == 2, "transposed conv supports k=4, stride=2 only");
+    Hg = d.H; Wg = d.W;
+    p.phases = 4; p.out_scale = 2; p.out_H = 2 * d.H; p.out_W = 2 * d.W;
+  } else {
+    OFS_REQUIRE((d.k & 1) == 1 && d.k >= 1 && d.k <= 7, "conv supports odd k <= 7 (got %d)", d.k);
+    OFS_REQUIRE(d.stride == 1 || d.stride == 2, "conv supports stride 1 or 2 (got %d)", d.stride);
+    const int pad = d.k / 2;
+    Hg = (d.H + 2 * pad - d.k) / d.stride + 1;
+    Wg = (d.W + 2 * pad - d.k) / d.stride + 1;
+    if (d.stride == 2) OFS_REQUIRE(d.H % 2 == 0 && d.W % 2 == 0, "stride-2 conv needs even H, W (got %dx%d)", d.H, d.W);
+    p.phases = 1; p.out_scale = 1; p.out_H = Hg; p.out_W = Wg;
+  }
+  // tiling of the M grid
+  int tileW = 1 << ilog2(std::min(Wg, 128));
+  OFS_REQUIRE(tileW >= 8 && Wg % tileW == 0, "conv plan: output grid width %d must be a multiple of a power of two >= 8", Wg);
+  const int tileH = kBlockM / tileW;
+  const int rpl = gcd(tileH, Hg);
+  p.Hg = Hg; p.Wg = Wg; p.rows_total = d.B * Hg;
+  p.tileW_log2 = ilog2(tileW); p.tileH = tileH; p.rpl = rpl;
+  p.tiles_x = Wg / tileW;
+  p.tiles_m = p.tiles_x * ((p.rows_total + tileH - 1) / tileH);
+  // K structure + tap table
+  plan.paired = (!deconv && d.stride == 2 && d.in_cs == 32);
+  if (deconv) {
+    p.ntaps = 4;
+    p.nchunks = (d.cin + 63) / 64;
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        const int ph = py * 2 + px;
+        p.out_oy[ph] = py; p.out_ox[ph] = px;
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 2; ++b) {
+            const int ti = ph * 4 + a * 2 + b;
+            // oy = 2i + ky - 1:  py=0 -> ky in {1 (i=i'), 3 (i=i'-1)};  py=1 -> ky in {0 (i=i'+1), 2 (i=i')}
+            p.tap_y[ti] = (short)(py == 0 ? (a == 0 ? 0 : -1) : (a == 0 ? 1 : 0));
+            p.tap_x[ti] = (short)(px == 0 ? (b == 0 ? 0 : -1) : (b == 0 ? 1 : 0));
+            p.tap_c[ti] = 0; p.tap_p[ti] = 0;
+          }
+      }
+  } else if (d.stride == 1) {
+    p.ntaps = d.k * d.k;
+    p.nchunks = (d.cin + 63) / 64;
+    OFS_REQUIRE(p.ntaps <= kMaxTapEntries, "too many taps");
+    const int pad = d.k / 2;
+    for (int ky = 0; ky < d.k; ++ky)
+      for (int kx = 0; kx < d.k; ++kx) {
+        const int ti = ky * d.k + kx;
+        p.tap_c[ti] = 0; p.tap_p[ti] = 0;
+        p.tap_x[ti] = (short)(kx - pad); p.tap_y[ti] = (short)(ky - pad);
+      }
+  } else if (plan.paired) {
+    // in_cs == 32: the parity view's inner dim (xpar, c) is exactly one 64-element K chunk, so the
+    // taps kx = 2j-1 (xpar 0) and kx = 2j (xpar 1) share one TMA box; kx = -1 carries zero weights.
+    const int pad = d.k / 2;
+    OFS_REQUIRE((pad & 1) == 1, "paired stride-2 conv needs odd padding (k = 3 or 7)");
+    const int nj = (d.k + 1) / 2;
+    p.ntaps = d.k * nj;
+    p.nchunks = 1;
+    OFS_REQUIRE(p.ntaps <= kMaxTapEntries, "too many taps");
+    for (int ky = 0; ky < d.k; ++ky)
+      for (int j = 0; j < nj; ++j) {
+        const int ti = ky * nj + j;
+        const int ty = ky - pad;
+        p.tap_c[ti] = 0;
+        p.tap_x[ti] = (short)((2 * j - 1 - pad) >> 1);  // == (2j - pad) >> 1 for odd pad
+        p.tap_p[ti] = (short)(ty & 1);
+        p.tap_y[ti] = (short)(ty >> 1);
+      }
+  } else {
+    OFS_REQUIRE(d.cin % 64 == 0, "stride-2 conv needs cin %% 64 == 0 (or a 32-channel input buffer); got %d", d.cin);
+    p.ntaps = d.k * d.k;
+    p.nchunks = d.cin / 64;
+    OFS_REQUIRE(p.ntaps <= kMaxTapEntries, "too many taps");
+    const int pad = d.k / 2;
+    for (int ky = 0; ky < d.k; ++ky)
+      for (int kx = 0; kx < d.k; ++kx) {
+        const int ti = ky * d.k + kx;
+        const int tx = kx - pad, ty = ky - pad;
+        p.tap_c[ti] = (short)((tx & 1) * d.in_cs);
+        p.tap_x[ti] = (short)(tx >> 1);
+        p.tap_p[ti] = (short)(ty & 1);
+        p.tap_y[ti] = (short)(ty >> 1);
+      }
+  }
+  plan.block_n = d.block_n;
+  p.n_pad = ((d.cout + d.block_n - 1) / d.block_n) * d.block_n;
+  p.tiles_n = p.n_pad / d.block_n;
+  p.n_valid = d.cout;
+  p.out_mode = d.out_mode; p.lrelu = d.lrelu; p.is_bf16 = d.is_bf16;
+  p.out_cstride = d.out_cstride; p.out_coff = d.out_coff;
+  if (d.out_mode == 0) {
+    OFS_REQUIRE(p.n_pad == d.cout, "16-bit output mode needs cout %% block_n == 0 (cout %d, block_n %d)", d.cout, d.block_n);
+    OFS_REQUIRE(d.out_cstride % 8 == 0 && d.out_coff % 8 == 0, "16-bit output slice must be 16-byte aligned");
+  }
+  plan.k_total = p.ntaps * p.nchunks * kBlockK;
+  plan.w_rows = p.phases * p.n_pad;
+  const int total_tiles = p.tiles_m * p.tiles_n * p.phases;
+  plan.grid = std::max(1, std::min(total_tiles, sm_count()));
+  switch (d.block_n) {
+    case 16: plan.smem = GemmCfg<16>::kSmem; break;
+    case 32: plan.smem = GemmCfg<32>::kSmem; break;
+    case 64: plan.smem = GemmCfg<64>::kSmem; break;
+    case 128: plan.smem = GemmCfg<128>::kSmem; break;
+    default: plan.smem = GemmCfg<256>::kSmem; break;
+  }
+  plan.macs = deconv ? (double)d.B * d.H * d.W * 16.0 * d.cin * d.cout
+                     : (double)d.B * Hg * Wg * (double)d.k * d.k * d.cin * d.cout;
+  return OFS_OK;
+}
+
+void conv_pack_weights(const ConvPlan& plan, const float* w, const float* bias, std::vector<uint16_t>& out,
+                       std::vector<float>& b_padded) {
+  const ConvGemmParams& p = plan.p;
+  const ConvDesc& d = plan.d;
+  const int K = plan.k_total;
+  out.assign((size_t)plan.w_rows * K, 0);
+  b_padded.assign(p.n_pad, 0.0f);
+  for (int n = 0; n < d.cout; ++n) b_padded[n] = bias ? bias[n] : 0.0f;
+  auto cvt = [&](float f) { return d.is_bf16 ? f32_to_bf16_rn(f) : f32_to_fp16_rn(f); };
+  if (d.kind == kDeconvK4S2) {
+    // w: [4,4,cout,cin];  y[2i+ky-1, 2j+kx-1, co] += x[i,j,ci] w[ky,kx,co,ci]
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px)
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 2; ++b) {
+            const int ph = py * 2 + px, t = a * 2 + b;
+            const int ky = py == 0 ? (a == 0 ? 1 : 3) : (a == 0 ? 0 : 2);
+            const int kx = px == 0 ? (b == 0 ? 1 : 3) : (b == 0 ? 0 : 2);
+            for (int n = 0; n < d.cout; ++n) {
+              const float* src = w + (((size_t)ky * 4 + kx) * d.cout + n) * d.cin;
+              uint16_t* dst = out.data() + ((size_t)ph * p.n_pad + n) * K + (size_t)t * p.nchunks * kBlockK;
+              for (int ci = 0; ci < d.cin; ++ci) dst[ci] = cvt(src[ci]);
+            }
+          }
+  } else if (plan.paired) {
+    const int pad = d.k / 2, nj = (d.k + 1) / 2;
+    (void)pad;
+    for (int ky = 0; ky < d.k; ++ky)
+      for (int j = 0; j < nj; ++j)
+        for (int xp = 0; xp < 2; ++xp) {
+          const int kx = 2 * j - 1 + xp;
+          if (kx < 0 || kx >= d.k) continue;
+          for (int ci = 0; ci < d.cin; ++ci) {
+            const float* src = w + (((size_t)ky * d.k + kx) * d.cin + ci) * d.cout;
+            const size_t kidx = (size_t)(ky * nj + j) * kBlockK + xp * 32 + ci;
+            for (int n = 0; n < d.cout; ++n) out[(size_t)n * K + kidx] = cvt(src[n]);
+          }
+        }
+  } else {
+    for (int ky = 0; ky < d.k; ++ky)
+      for (int kx = 0; kx < d.k; ++kx)
+        for (int ci = 0; ci < d.cin; ++ci) {
+          const float* src = w + (((size_t)ky * d.k + kx) * d.cin + ci) * d.cout;
+          const size_t kidx = (size_t)(ky * d.k + kx) * p.nchunks * kBlockK + ci;
+          for (int n = 0; n < d.cout; ++n) out[(size_t)n * K + kidx] = cvt(src[n]);
+        }
+  }
+}
+
+int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const float* bias_dev, void* out) {
+  ConvGemmParams& p = plan.p;
+  const ConvDesc& d = plan.d;
+  OFS_REQUIRE(act_in && w_dev && bias_dev && out, "conv bind: null pointer");
+  OFS_REQUIRE(((uintptr_t)act_in) % 16 == 0 && ((uintptr_t)w_dev) % 16 == 0 && ((uintptr_t)out) % 16 == 0,
+              "conv bind: pointers must be 16-byte aligned");
+  p.out = out;
+  p.bias = bias_dev;
+  const cuuint32_t tileW = 1u << p.tileW_log2;
+  unsigned long long vd[5], vs[4];
+  conv_act_view(d, vd, vs);
+  cuuint64_t dims[5], str[4];
+  for (int i = 0; i < 5; ++i) dims[i] = vd[i];
+  for (int i = 0; i < 4; ++i) str[i] = vs[i];
+  cuuint32_t box[5] = {(cuuint32_t)kBlockK, tileW, 1, (cuuint32_t)p.rpl, 1};
+  int st = encode_map(&p.tmap_a, d.is_bf16, 5, act_in, dims, str, box);
+  if (st != OFS_OK) return st;
+  cuuint64_t wd[2] = {(cuuint64_t)plan.k_total, (cuuint64_t)plan.w_rows};
+  cuuint64_t ws[1] = {(cuuint64_t)plan.k_total * 2};
+  cuuint32_t wb[2] = {(cuuint32_t)kBlockK, (cuuint32_t)plan.block_n};
+  return encode_map(&p.tmap_w, d.is_bf16, 2, w_dev, wd, ws, wb);
+}
+
+int conv_launch(const ConvPlan& plan, cudaStream_t st) {
+  switch (plan.block_n) {
+    case 16: return launch_t<16>(plan, st);
+    case 32: return launch_t<32>(plan, st);
+    case 64: return launch_t<64>(plan, st);
+    case 128: return launch_t<128>(plan, st);
+    case 256: return launch_t<256>(plan, st);
+  }
+  set_error("conv_launch: unsupported block_n %d", plan.block_n);
+  return OFS_EINVAL;
+}
+
+int launch_pack_act(const float* in, void* out, size_t npix, int cin, int cs, int is_bf16, cudaStream_t st) {
+  if (npix == 0) return OFS_OK;
+  const size_t total = npix * (cs / 8);
+  size_t blocks = std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
+  pack_act_kernel<<<(int)blocks, 256, 0, st>>>(in, reinterpret_cast<uint4*>(out), npix, cin, cs, is_bf16);
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
+}
+
+int launch_unpack_act(const void* in, float* out, size_t npix, int cs, int coff, int c, int is_bf16, cudaStream_t st) {
+  if (npix == 0) return OFS_OK;
+  const size_t total = npix * c;
+  size_t blocks = std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
+  unpack_act_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(in), out, npix, cs, coff, c, is_bf16);
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
+}
+
+}  // namespace ofs
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int ofs_conv2d_nhwc(const float* x, const float* w_host, const float* b_host, float* y, int B, int H, int W,
+                               int Cin, int Cout, int k, int stride, int transposed, int lrelu, int precision,
+                               ofs_stream stream) {
+  using namespace ofs;
+  cudaStream_t st = (cudaStream_t)stream;
+  OFS_REQUIRE(x && w_host && y, "ofs_conv2d_nhwc: null pointer");
+  OFS_REQUIRE(precision == OFS_PREC_BF16 || precision == OFS_PREC_FP16, "ofs_conv2d_nhwc: bad precision");
+  int dev = 0;
+  OFS_CUDA(cudaGetDevice(&dev));
+  int rc = require_sm100(dev);
+  if (rc != OFS_OK) return rc;
+  const int is_bf16 = precision == OFS_PREC_BF16;
+  ConvDesc d;
+  d.kind = transposed ? kDeconvK4S2 : kConv;
+  d.B = B; d.H = H; d.W = W; d.cin = Cin; d.cout = Cout; d.k = k; d.stride = stride;
+  // input buffer: stride-2 convs want 64-channel chunks (or exactly 32 channels: the paired conv1 form)
+  if (!transposed && stride == 2) d.in_cs = (Cin <= 32 && ((k / 2) & 1)) ? 32 : ((Cin + 63) / 64) * 64; else d.in_cs = ((Cin + 7) / 8) * 8;
+  const int cin_logical = d.cin;
+  if (!transposed && stride == 2 && d.in_cs != 32) d.cin = d.in_cs;  // zero channels + zero weights
+  d.block_n = Cout >= 128 ? 128 : (Cout >= 64 ? 64 : (Cout >= 32 ? 32 : 16));
+  d.out_mode = 1; d.lrelu = lrelu; d.is_bf16 = is_bf16;
+  d.out_cstride = Cout; d.out_coff = 0;
+  ConvPlan plan;
+  rc = conv_plan_geometry(plan, d);
+  if (rc != OFS_OK) return rc;
+  // weights: expand logical cin to the padded cin the plan was built with
+  std::vector<float> wexp;
+  const float* wsrc = w_host;
+  if (d.cin != cin_logical) {
+    if (transposed) {
+      wexp.assign((size_t)16 * Cout * d.cin, 0.0f);
+      for (size_t r = 0; r < (size_t)16 * Cout; ++r)
+        memcpy(&wexp[r * d.cin], w_host + r * cin_logical, sizeof(float) * cin_logical);
+    } else {
+      wexp.assign((size_t)k * k * d.cin * Cout, 0.0f);
+      for (int t = 0; t < k * k; ++t)
+        memcpy(&wexp[(size_t)t * d.cin * Cout], w_host + (size_t)t * cin_logical * Cout, sizeof(float) * cin_logical * Cout);
+    }
+    wsrc = wexp.data();
+  }
+  std::vector<uint16_t> wp;
+  std::vector<float> bp;
+  conv_pack_weights(plan, wsrc, b_host, wp, bp);
+  void *x16 = nullptr, *w_dev = nullptr;
+  float* b_dev = nullptr;
+  const size_t npix = (size_t)B * H * W;
+  auto cleanup = [&]() {
+    if (x16) cudaFree(x16);
+    if (w_dev) cudaFree(w_dev);
+    if (b_dev) cudaFree(b_dev);
+  };
+  rc = check_cuda(cudaMalloc(&x16, npix * d.in_cs * 2), "cudaMalloc x16", __FILE__, __LINE__);
+  if (rc == OFS_OK) rc = check_cuda(cudaMalloc(&w_dev, wp.size() * 2), "cudaMalloc w", __FILE__, __LINE__);
+  if (rc == OFS_OK) rc = check_cuda(cudaMalloc((void**)&b_dev, bp.size() * 4), "cudaMalloc b", __FILE__, __LINE__);
+  if (rc == OFS_OK) rc = check_cuda(cudaMemcpyAsync(w_dev, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice, st), "H2D w", __FILE__, __LINE__);
+  if (rc == OFS_OK) rc = check_cuda(cudaMemcpyAsync(b_dev, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice, st), "H2D b", __FILE__, __LINE__);
+  if (rc == OFS_OK) rc = launch_pack_act(x, x16, npix, cin_logical, d.in_cs, is_bf16, st);
+  if (rc == OFS_OK) rc = conv_plan_bind(plan, x16, w_dev, b_dev, y);
+  if (rc == OFS_OK) rc = conv_launch(plan, st);
+  if (rc == OFS_OK) rc = check_cuda(cudaStreamSynchronize(st), "conv2d sync", __FILE__, __LINE__);
+  cleanup();
+  return rc;
+}
+
+// Host-only introspection of the plan (geometry, tap table, activation view, packed weights): lets
+// the CPU test-suite emulate the TMA gathers + GEMM in numpy and check the whole index algebra
+// against the oracle convolution without a GPU.  Not part of the product API.
+extern "C" int ofs_debug_conv_plan(int kind, int B, int H, int W, int cin, int in_cs, int cout, int k, int stride,
+                                   int block_n, int is_bf16, const float* w_tf, const float* bias, int* info /*[40]*/,
+                                   short* taps /*[4][64]: c,x,p,y*/, uint16_t* w_packed, long long w_cap,
+                                   float* b_padded /*[n_pad]*/) {
+  using namespace ofs;
+  ConvDesc d;
+  d.kind = kind ? kDeconvK4S2 : kConv;
+  d.B = B; d.H = H; d.W = W; d.cin = cin; d.in_cs = in_cs; d.cout = cout; d.k = k; d.stride = stride;
+  d.block_n = block_n; d.out_mode = 1; d.lrelu = 0; d.is_bf16 = is_bf16; d.out_cstride = cout; d.out_coff = 0;
+  ConvPlan plan;
+  int rc = conv_plan_geometry(plan, d);
+  if (rc != OFS_OK) return rc;
+  const ConvGemmParams& p = plan.p;
+  unsigned long long vd[5], vs[4];
+  conv_act_view(d, vd, vs);
+  const int vals[] = {p.Hg, p.Wg, p.rows_total, p.tileW_log2, p.tileH, p.rpl, p.tiles_x, p.tiles_m, p.tiles_n, p.phases,
+                      p.ntaps, p.nchunks, p.n_pad, plan.k_total, plan.w_rows, plan.paired ? 1 : 0, p.out_scale, p.out_H,
+                      p.out_W, plan.grid, (int)vd[0], (int)vd[1], (int)vd[2], (int)vd[3], (int)vd[4], (int)(vs[0] / 2),
+                      (int)(vs[1] / 2), (int)(vs[2] / 2), (int)(vs[3] / 2), p.out_oy[0], p.out_oy[1], p.out_oy[2],
+                      p.out_oy[3], p.out_ox[0], p.out_ox[1], p.out_ox[2], p.out_ox[3], (int)plan.smem, 0, 0};
+  for (int i = 0; i < 40; ++i) info[i] = vals[i];
+  for (int i = 0; i < kMaxTapEntries; ++i) {
+    taps[0 * kMaxTapEntries + i] = p.tap_c[i];
+    taps[1 * kMaxTapEntries + i] = p.tap_x[i];
+    taps[2 * kMaxTapEntries + i] = p.tap_p[i];
+    taps[3 * kMaxTapEntries + i] = p.tap_y[i];
+  }
+  if (w_tf && w_packed) {
+    std::vector<uint16_t> wp;
+    std::vector<float> bp;
+    conv_pack_weights(plan, w_tf, bias, wp, bp);
+    OFS_REQUIRE((long long)wp.size() <= w_cap, "ofs_debug_conv_plan: w_packed capacity %lld < %zu", w_cap, wp.size());
+    memcpy(w_packed, wp.data(), wp.size() * 2);
+    if (b_padded) memcpy(b_padded, bp.data(), bp.size() * 4);
+  }
+  return OFS_OK;
+}
+
+extern "C" unsigned ofs_debug_cvt16(float f, int is_bf16) { return is_bf16 ? ofs::f32_to_bf16_rn(f) : ofs::f32_to_fp16_rn(f); }

@@ -1,0 +1,92 @@
+// Implicit-GEMM convolution / transposed convolution on tcgen05 (sm_100a): plan + launch API
+// shared by the network (flownet.cu) and the stand-alone op (ofs_conv2d_nhwc).
+#pragma once
+
+#include <vector>
+
+#include "ofs_common.cuh"
+
+namespace ofs {
+
+constexpr int kMaxTapEntries = 64;
+
+// Everything the kernel needs, passed as one __grid_constant__ parameter.
+struct ConvGemmParams {
+  CUtensorMap tmap_a;  // 5-D view of the NHWC 16-bit activation (see conv_gemm.cu)
+  CUtensorMap tmap_w;  // 2-D packed weights [phases * n_pad rows][K_total], K-major
+  // M grid (output pixels; for the transposed conv: input pixels, one GEMM per sub-pixel phase)
+  int Hg, Wg;          // grid height / width per image
+  int rows_total;      // B * Hg
+  int tileW_log2;      // tile = tileH rows x tileW pixels = 128 GEMM rows
+  int tileH;
+  int rpl;             // rows per TMA piece (a piece never straddles two images)
+  int tiles_x;         // Wg / tileW
+  int tiles_m;         // tiles_x * ceil(rows_total / tileH)
+  int tiles_n;         // n_pad / BLOCK_N
+  int phases;          // 1 (conv) or 4 (transposed conv sub-pixel phases)
+  int ntaps, nchunks;  // K_total = ntaps * nchunks * 64
+  int n_pad;           // padded output channels per phase
+  // epilogue
+  void* out;           // 16-bit activations (mode 0) or fp32 (mode 1)
+  const float* bias;   // [n_pad]
+  int out_mode;        // 0: act(v + b) -> 16-bit;  1: v + b -> fp32 (first n_valid columns)
+  int out_H, out_W;    // full output image size
+  int out_cstride;     // channels per output pixel in the destination buffer
+  int out_coff;        // channel offset of this layer's slice in the destination (concat-by-slice)
+  int out_scale;       // 1, or 2 for the transposed conv
+  int n_valid;         // real output channels
+  int lrelu;           // apply max(v, 0.1 v)
+  int is_bf16;         // operand / storage format: 1 bf16, 0 fp16
+  int out_oy[4], out_ox[4];  // per-phase sub-pixel offset
+  // per (phase, tap) TMA coordinate offsets: channel base, x offset, parity plane, y offset
+  short tap_c[kMaxTapEntries], tap_x[kMaxTapEntries], tap_p[kMaxTapEntries], tap_y[kMaxTapEntries];
+};
+
+enum ConvKind { kConv = 0, kDeconvK4S2 = 1 };
+
+struct ConvDesc {
+  ConvKind kind;
+  int B, H, W;         // input image grid
+  int cin;             // logical input channels (K covers ceil(cin/64)*64, extra weights are zero)
+  int in_cs;           // channel stride of the input buffer (elements), multiple of 8
+  int cout;            // logical output channels
+  int k, stride;       // conv: k odd, pad k/2, stride 1|2;  deconv: k=4, stride=2
+  int block_n;         // 16, 32, 64, 128 or 256
+  int out_mode, lrelu, is_bf16;
+  int out_cstride, out_coff;
+};
+
+struct ConvPlan {
+  ConvGemmParams p;
+  ConvDesc d;
+  int block_n = 0;
+  int grid = 0;
+  size_t smem = 0;
+  int k_total = 0;
+  int w_rows = 0;            // phases * n_pad
+  bool paired = false;       // conv1-style stride-2 layer with in_cs == 32: two x-taps per K chunk
+  double macs = 0;           // literal MACs of the layer (roofline numerator)
+};
+
+// Geometry only (no device pointers): tap table, tiling, grid.  OFS_EINVAL on unsupported shapes.
+int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d);
+// Packs float32 weights (TF layout: conv [k,k,cin,cout]; deconv [4,4,cout,cin]) into the 16-bit
+// K-major GEMM layout of `plan` (w_rows x k_total) and the padded bias [n_pad].
+void conv_pack_weights(const ConvPlan& plan, const float* w_tf, const float* bias, std::vector<uint16_t>& w_packed,
+                       std::vector<float>& b_padded);
+// Binds device pointers and encodes the TMA descriptors.
+int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_packed_dev, const float* bias_dev, void* out);
+int conv_launch(const ConvPlan& plan, cudaStream_t st);
+
+// 5-D TMA view of the input activation (dims in elements, strides in bytes; dim 0 is contiguous)
+void conv_act_view(const ConvDesc& d, unsigned long long dims[5], unsigned long long strides_bytes[4]);
+
+uint16_t f32_to_bf16_rn(float f);
+uint16_t f32_to_fp16_rn(float f);
+
+// fp32 NHWC [npix, cin] -> 16-bit [npix, cs] (channels >= cin zero-filled)
+int launch_pack_act(const float* in, void* out, size_t npix, int cin, int cs, int is_bf16, cudaStream_t st);
+// 16-bit [npix, cs] channels [coff, coff+c) -> fp32 [npix, c]
+int launch_unpack_act(const void* in, float* out, size_t npix, int cs, int coff, int c, int is_bf16, cudaStream_t st);
+
+}  // namespace ofs

@@ -1,0 +1,550 @@
+// ofs_net: the FlowNetS-pyramid forward of the stabiliser (reference model.py:786-893) on sm_100a.
+//
+//   feats fp32 [B,384,512,27] --pack--> 16-bit [B,384,512,32]
+//   10 encoder convs + 4 transposed convs + 5 flow heads  -> conv_gemm.cu (tcgen05 implicit GEMM)
+//   BatchNorm (moving stats, no gamma, eps 1e-5) is folded into W'/b' at load time
+//   ConcatLayer            -> never materialised: producers write channel slices of concat buffers
+//   flow pyramid           -> pyr_kernel: f_n = head_n + up(f_{n+1}) + up(f_{n+1})  (TF1 legacy bilinear)
+//                             fused with the 2->2 k4s2 flow up-sampler written into the next concat slice
+//   pad + NN-upsample + predict2 (model.py:882-887) -> 1x1 GEMM on the 96x128 grid (18 columns = 9 taps x 2)
+//                             + predict2_gather_kernel (9-tap gather through the NN index maps, + 8 x up(f3))
+//
+// HBM layout (per batch element, 16-bit): x0 384x512x32 | conv1 192x256x64 | concat2 96x128x200
+// [conv2 0:128 | deconv2 128:192 | up3_2 192:194 | pad] | conv3 48x64x256 | concat3 48x64x392 |
+// conv4 24x32x512 | concat4 24x32x776 | conv5 12x16x512 | concat5 12x16x1032 | conv6, conv6_1 6x8x1024.
+// Pad channels of the concat buffers are zeroed once and never written.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "conv_gemm.cuh"
+
+namespace ofs {
+int flow_resize_warp_impl(const float* img, const float* flow2, float* out, int B, int H, int W, int fh, int fw,
+                          cudaStream_t st);
+}
+
+namespace {
+
+using namespace ofs;
+
+constexpr int kNetH = 384, kNetW = 512, kNetC = 27;
+constexpr float kBnEps = 1e-5f;
+
+__device__ __forceinline__ uint16_t cvt16(float v, int is_bf16) {
+  if (is_bf16) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    return *reinterpret_cast<uint16_t*>(&h);
+  }
+  __half h = __float2half_rn(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+
+// TF-1.10 ResizeBilinear (align_corners=False, legacy): src = dst * (in/out), no half-pixel offset
+__device__ __forceinline__ float2 tf1_bilinear2(const float2* __restrict__ src, int h, int w, float hs, float ws,
+                                                 int oy, int ox) {
+  const float iy = (float)oy * hs, ix = (float)ox * ws;
+  const int y0 = (int)floorf(iy), x0 = (int)floorf(ix);
+  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  const float yl = iy - (float)y0, xl = ix - (float)x0;
+  const float2 tl = src[y0 * w + x0], tr = src[y0 * w + x1], bl = src[y1 * w + x0], br = src[y1 * w + x1];
+  float2 top, bot, v;
+  top.x = tl.x + (tr.x - tl.x) * xl; top.y = tl.y + (tr.y - tl.y) * xl;
+  bot.x = bl.x + (br.x - bl.x) * xl; bot.y = bl.y + (br.y - bl.y) * xl;
+  v.x = top.x + (bot.x - top.x) * yl; v.y = top.y + (bot.y - top.y) * yl;
+  return v;
+}
+
+struct PyrParams {
+  const float2* raw;     // head output at this level [B,h,w]
+  const float2* f_prev;  // summed flow of the coarser level [B,h/2,w/2] or null (level 6)
+  float2* f_out;         // summed flow at this level [B,h,w]
+  const float* up_w;     // [4,4,2,2] (ky,kx,co,ci) then [2] bias
+  uint16_t* concat;      // destination concat buffer [B,2h,2w,cstride]
+  int B, h, w, cstride, coff, is_bf16;
+};
+
+// model.py:857/866/875 (ElementwiseLayer left fold) + model.py:852/861/870/879 (flow up-sampler)
+__device__ __forceinline__ float2 pyr_flow_at(const PyrParams& p, int b, int i, int j) {
+  float2 v = p.raw[((size_t)b * p.h + i) * p.w + j];
+  if (p.f_prev) {
+    const int hp = p.h >> 1, wp = p.w >> 1;
+    const float2 u = tf1_bilinear2(p.f_prev + (size_t)b * hp * wp, hp, wp, (float)hp / (float)p.h,
+                                   (float)wp / (float)p.w, i, j);
+    v.x = (v.x + u.x) + u.x;
+    v.y = (v.y + u.y) + u.y;
+  }
+  return v;
+}
+
+__global__ void pyr_kernel(PyrParams p) {
+  const int H2 = 2 * p.h, W2 = 2 * p.w;
+  const size_t total = (size_t)p.B * H2 * W2;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % W2);
+    const size_t r = idx / W2;
+    const int oy = (int)(r % H2);
+    const int b = (int)(r / H2);
+    if (((oy | ox) & 1) == 0) p.f_out[((size_t)b * p.h + (oy >> 1)) * p.w + (ox >> 1)] = pyr_flow_at(p, b, oy >> 1, ox >> 1);
+    float a0 = __ldg(p.up_w + 64), a1 = __ldg(p.up_w + 65);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int ky = ((oy + 1) & 1) + 2 * s;
+      const int i = (oy + 1 - ky) >> 1;  // 2i + ky - 1 == oy
+      if (i < 0 || i >= p.h) continue;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int kx = ((ox + 1) & 1) + 2 * t;
+        const int j = (ox + 1 - kx) >> 1;
+        if (j < 0 || j >= p.w) continue;
+        const float2 f = pyr_flow_at(p, b, i, j);
+        const float* wk = p.up_w + (ky * 4 + kx) * 4;  // [co][ci]
+        a0 += f.x * __ldg(wk + 0) + f.y * __ldg(wk + 1);
+        a1 += f.x * __ldg(wk + 2) + f.y * __ldg(wk + 3);
+      }
+    }
+    uint16_t* o = p.concat + idx * p.cstride + p.coff;
+    const uint32_t packed = (uint32_t)cvt16(a0, p.is_bf16) | ((uint32_t)cvt16(a1, p.is_bf16) << 16);
+    *reinterpret_cast<uint32_t*>(o) = packed;
+  }
+}
+
+struct Predict2Params {
+  const float* P;     // [B,96,128,18]: column (ky*3+kx)*2 + o
+  const float2* f3;   // [B,48,64]
+  float2* f2;         // [B,382,510]
+  float bias0, bias1;
+  float sy, sx;       // NN align_corners scales (98-1)/(384-1), (130-1)/(512-1) in fp32
+  float hs, ws;       // bilinear scales 48/382, 64/510 in fp32
+  int B;
+};
+
+// model.py:882-887: zero-pad(1) -> nearest(align_corners) to 384x512 -> 3x3 VALID -> + 8 x up(f3)
+__global__ void predict2_gather_kernel(Predict2Params p) {
+  const size_t total = (size_t)p.B * 382 * 510;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % 510);
+    const size_t r = idx / 510;
+    const int oy = (int)(r % 382);
+    const int b = (int)(r / 382);
+    float a0 = p.bias0, a1 = p.bias1;
+    const float* Pb = p.P + (size_t)b * 96 * 128 * 18;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = min((int)roundf((float)(oy + ky) * p.sy), 97) - 1;  // row of the unpadded 96x128 grid
+      if (iy < 0 || iy >= 96) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = min((int)roundf((float)(ox + kx) * p.sx), 129) - 1;
+        if (ix < 0 || ix >= 128) continue;
+        const float2 v = __ldg(reinterpret_cast<const float2*>(Pb + ((size_t)iy * 128 + ix) * 18 + (ky * 3 + kx) * 2));
+        a0 += v.x;
+        a1 += v.y;
+      }
+    }
+    const float2 u = tf1_bilinear2(p.f3 + (size_t)b * 48 * 64, 48, 64, p.hs, p.ws, oy, ox);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a0 += u.x; a1 += u.y; }  // ElementwiseLayer left fold, model.py:887
+    p.f2[idx] = make_float2(a0, a1);
+  }
+}
+
+struct Layer {
+  std::string name;       // checkpoint layer name ("3_1", "deconv5", "predict4", ...)
+  std::string bn;         // BN scope or ""
+  ConvDesc d;             // B filled in at prepare()
+  const void* in = nullptr;
+  void* out = nullptr;
+  ConvPlan plan;
+  void* w_dev = nullptr;
+  float* b_dev = nullptr;
+  size_t w_elems = 0;
+  int n_pad = 0;
+};
+
+struct ActInfo { void* ptr; int H, W, cs, coff, C; };
+
+}  // namespace
+
+struct ofs_net {
+  int device = 0, max_batch = 0, is_bf16 = 1;
+  bool loaded = false;
+  int prepared_B = 0;
+  cudaStream_t stream = nullptr;
+  // 16-bit activations
+  void *x0 = nullptr, *conv1 = nullptr, *concat2 = nullptr, *conv3 = nullptr, *concat3 = nullptr, *conv4 = nullptr,
+       *concat4 = nullptr, *conv5 = nullptr, *concat5 = nullptr, *conv6 = nullptr, *conv6_1 = nullptr;
+  // fp32
+  float *raw[7] = {nullptr}, *f[7] = {nullptr};  // index = pyramid level 3..6; f[2] = flow2
+  float* P2 = nullptr;
+  float* upw = nullptr;  // 4 x (64 + 2) floats: upsample6_5, 5_4, 4_3, 3_2
+  float p2_bias[2] = {0, 0};
+  std::vector<Layer> layers;
+  std::map<std::string, ActInfo> acts;
+  std::vector<void*> allocs;
+  // host-API staging
+  float *st_feats = nullptr, *st_frames = nullptr, *st_out = nullptr;
+  size_t st_frames_cap = 0;
+};
+
+namespace {
+
+int dev_alloc(ofs_net* n, void** p, size_t bytes, bool zero) {
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    return OFS_ENOMEM;
+  }
+  n->allocs.push_back(*p);
+  if (zero) OFS_CUDA(cudaMemset(*p, 0, bytes));
+  return OFS_OK;
+}
+
+Layer make_layer(const char* name, const char* bn, ConvKind kind, int H, int W, int cin, int in_cs, int cout, int k,
+                 int stride, int block_n, int out_mode, int lrelu, int out_cstride, int out_coff, const void* in,
+                 void* out) {
+  Layer L;
+  L.name = name; L.bn = bn;
+  L.d.kind = kind; L.d.B = 1; L.d.H = H; L.d.W = W; L.d.cin = cin; L.d.in_cs = in_cs; L.d.cout = cout; L.d.k = k;
+  L.d.stride = stride; L.d.block_n = block_n; L.d.out_mode = out_mode; L.d.lrelu = lrelu; L.d.is_bf16 = 1;
+  L.d.out_cstride = out_cstride; L.d.out_coff = out_coff;
+  L.in = in; L.out = out;
+  return L;
+}
+
+int prepare(ofs_net* n, int B) {
+  if (n->prepared_B == B) return OFS_OK;
+  for (Layer& L : n->layers) {
+    L.d.B = B;
+    L.d.is_bf16 = n->is_bf16;
+    int rc = conv_plan_geometry(L.plan, L.d);
+    if (rc != OFS_OK) return rc;
+    rc = conv_plan_bind(L.plan, L.in, L.w_dev, L.b_dev, L.out);
+    if (rc != OFS_OK) return rc;
+  }
+  n->prepared_B = B;
+  return OFS_OK;
+}
+
+std::string norm_key(const char* raw) {
+  std::string s(raw);
+  const size_t colon = s.rfind(':');
+  if (colon != std::string::npos && colon + 2 >= s.size()) s = s.substr(0, colon);  // ":0"
+  // keep the last two path components: "<layer>/<var>"
+  const size_t last = s.rfind('/');
+  if (last == std::string::npos) return s;
+  const size_t prev = s.rfind('/', last - 1);
+  return prev == std::string::npos ? s : s.substr(prev + 1);
+}
+
+int launch_pyr(ofs_net* n, int level, int B, cudaStream_t st) {
+  // level in {6,5,4,3}; grid h x w of that level; writes into the concat buffer of level-1
+  static const int hs[7] = {0, 0, 0, 48, 24, 12, 6}, ws[7] = {0, 0, 0, 64, 32, 16, 8};
+  PyrParams p;
+  p.raw = reinterpret_cast<const float2*>(n->raw[level]);
+  p.f_prev = level == 6 ? nullptr : reinterpret_cast<const float2*>(n->f[level + 1]);
+  p.f_out = reinterpret_cast<float2*>(n->f[level]);
+  p.up_w = n->upw + (6 - level) * 66;
+  p.B = B; p.h = hs[level]; p.w = ws[level]; p.is_bf16 = n->is_bf16;
+  switch (level) {
+    case 6: p.concat = (uint16_t*)n->concat5; p.cstride = 1032; p.coff = 1024; break;
+    case 5: p.concat = (uint16_t*)n->concat4; p.cstride = 776; p.coff = 768; break;
+    case 4: p.concat = (uint16_t*)n->concat3; p.cstride = 392; p.coff = 384; break;
+    default: p.concat = (uint16_t*)n->concat2; p.cstride = 200; p.coff = 192; break;
+  }
+  const size_t total = (size_t)B * 4 * p.h * p.w;
+  const int blocks = (int)std::min<size_t>((total + 127) / 128, (size_t)sm_count() * 8);
+  pyr_kernel<<<blocks, 128, 0, st>>>(p);
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
+}
+
+int forward_impl(ofs_net* n, const float* feats, int B, float* f2_target, cudaStream_t st) {
+  OFS_REQUIRE(n && feats, "ofs_net_forward: null pointer");
+  OFS_REQUIRE(B >= 1 && B <= n->max_batch, "ofs_net_forward: batch %d outside [1, %d]", B, n->max_batch);
+  if (!n->loaded) {
+    set_error("ofs_net_forward: weights not loaded (call ofs_net_load_weights first)");
+    return OFS_ESTATE;
+  }
+  OFS_CUDA(cudaSetDevice(n->device));
+  int rc = prepare(n, B);
+  if (rc != OFS_OK) return rc;
+  rc = launch_pack_act(feats, n->x0, (size_t)B * kNetH * kNetW, kNetC, 32, n->is_bf16, st);
+  if (rc != OFS_OK) return rc;
+  for (Layer& L : n->layers) {
+    rc = conv_launch(L.plan, st);
+    if (rc != OFS_OK) return rc;
+    if (L.name == "deconv5") rc = launch_pyr(n, 6, B, st);
+    else if (L.name == "deconv4") rc = launch_pyr(n, 5, B, st);
+    else if (L.name == "deconv3") rc = launch_pyr(n, 4, B, st);
+    else if (L.name == "deconv2") rc = launch_pyr(n, 3, B, st);
+    if (rc != OFS_OK) return rc;
+  }
+  Predict2Params pp;
+  pp.P = n->P2;
+  pp.f3 = reinterpret_cast<const float2*>(n->f[3]);
+  pp.f2 = reinterpret_cast<float2*>(f2_target ? f2_target : n->f[2]);
+  pp.bias0 = n->p2_bias[0]; pp.bias1 = n->p2_bias[1];
+  pp.sy = 97.0f / 383.0f; pp.sx = 129.0f / 511.0f;
+  pp.hs = 48.0f / 382.0f; pp.ws = 64.0f / 510.0f;
+  pp.B = B;
+  const size_t total = (size_t)B * 382 * 510;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
+  predict2_gather_kernel<<<blocks, 256, 0, st>>>(pp);
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
+  OFS_REQUIRE(out, "ofs_net_create: null out pointer");
+  *out = nullptr;
+  OFS_REQUIRE(max_batch >= 1 && max_batch <= 64, "ofs_net_create: max_batch %d outside [1,64]", max_batch);
+  OFS_REQUIRE(precision == OFS_PREC_BF16 || precision == OFS_PREC_FP16, "ofs_net_create: bad precision %d", precision);
+  int rc = require_sm100(device);
+  if (rc != OFS_OK) return rc;
+  OFS_CUDA(cudaSetDevice(device));
+  ofs_net* n = new ofs_net();
+  n->device = device; n->max_batch = max_batch; n->is_bf16 = precision == OFS_PREC_BF16;
+  const size_t B = (size_t)max_batch;
+  struct { void** p; size_t elems; } bufs[] = {
+      {&n->x0, B * 384 * 512 * 32},    {&n->conv1, B * 192 * 256 * 64}, {&n->concat2, B * 96 * 128 * 200},
+      {&n->conv3, B * 48 * 64 * 256},  {&n->concat3, B * 48 * 64 * 392}, {&n->conv4, B * 24 * 32 * 512},
+      {&n->concat4, B * 24 * 32 * 776}, {&n->conv5, B * 12 * 16 * 512},  {&n->concat5, B * 12 * 16 * 1032},
+      {&n->conv6, B * 6 * 8 * 1024},   {&n->conv6_1, B * 6 * 8 * 1024}};
+  for (auto& b : bufs) {
+    rc = dev_alloc(n, b.p, b.elems * 2, true);
+    if (rc != OFS_OK) { ofs_net_destroy(n); return rc; }
+  }
+  static const int hs[7] = {0, 0, 382, 48, 24, 12, 6}, ws[7] = {0, 0, 510, 64, 32, 16, 8};
+  for (int l = 2; l <= 6; ++l) {
+    rc = dev_alloc(n, (void**)&n->f[l], B * hs[l] * ws[l] * 2 * 4, true);
+    if (rc == OFS_OK && l >= 3) rc = dev_alloc(n, (void**)&n->raw[l], B * hs[l] * ws[l] * 2 * 4, true);
+    if (rc != OFS_OK) { ofs_net_destroy(n); return rc; }
+  }
+  rc = dev_alloc(n, (void**)&n->P2, B * 96 * 128 * 18 * 4, true);
+  if (rc == OFS_OK) rc = dev_alloc(n, (void**)&n->upw, 4 * 66 * 4, true);
+  if (rc == OFS_OK) rc = dev_alloc(n, (void**)&n->st_feats, B * kNetH * kNetW * kNetC * 4, false);
+  if (rc != OFS_OK) { ofs_net_destroy(n); return rc; }
+  if (cudaStreamCreateWithFlags(&n->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("cudaStreamCreate failed");
+    ofs_net_destroy(n);
+    return OFS_ECUDA;
+  }
+  // execution order (model.py:807-885).  in_cs / out_cstride are the physical channel strides.
+  auto& Ls = n->layers;
+  Ls.push_back(make_layer("1", "1", kConv, 384, 512, 27, 32, 64, 7, 2, 64, 0, 1, 64, 0, n->x0, n->conv1));
+  Ls.push_back(make_layer("2", "2", kConv, 192, 256, 64, 64, 128, 5, 2, 128, 0, 1, 200, 0, n->conv1, n->concat2));
+  Ls.push_back(make_layer("3", "3", kConv, 96, 128, 128, 200, 256, 5, 2, 128, 0, 1, 256, 0, n->concat2, n->conv3));
+  Ls.push_back(make_layer("3_1", "3_1", kConv, 48, 64, 256, 256, 256, 3, 1, 128, 0, 1, 392, 0, n->conv3, n->concat3));
+  Ls.push_back(make_layer("4", "4", kConv, 48, 64, 256, 392, 512, 3, 2, 128, 0, 1, 512, 0, n->concat3, n->conv4));
+  Ls.push_back(make_layer("4_1", "4_1", kConv, 24, 32, 512, 512, 512, 3, 1, 128, 0, 1, 776, 0, n->conv4, n->concat4));
+  Ls.push_back(make_layer("5", "5", kConv, 24, 32, 512, 776, 512, 3, 2, 128, 0, 1, 512, 0, n->concat4, n->conv5));
+  Ls.push_back(make_layer("5_1", "5_1", kConv, 12, 16, 512, 512, 512, 3, 1, 128, 0, 1, 1032, 0, n->conv5, n->concat5));
+  Ls.push_back(make_layer("6", "6", kConv, 12, 16, 512, 1032, 1024, 3, 2, 128, 0, 1, 1024, 0, n->concat5, n->conv6));
+  Ls.push_back(make_layer("6_1", "6_1", kConv, 6, 8, 1024, 1024, 1024, 3, 1, 128, 0, 1, 1024, 0, n->conv6, n->conv6_1));
+  Ls.push_back(make_layer("predict6", "", kConv, 6, 8, 1024, 1024, 2, 3, 1, 16, 1, 0, 2, 0, n->conv6_1, n->raw[6]));
+  Ls.push_back(make_layer("deconv5", "deconv5_bn", kDeconvK4S2, 6, 8, 1024, 1024, 512, 4, 2, 128, 0, 1, 1032, 512, n->conv6_1, n->concat5));
+  Ls.push_back(make_layer("predict5", "", kConv, 12, 16, 1026, 1032, 2, 3, 1, 16, 1, 0, 2, 0, n->concat5, n->raw[5]));
+  Ls.push_back(make_layer("deconv4", "deconv4_bn", kDeconvK4S2, 12, 16, 1026, 1032, 256, 4, 2, 128, 0, 1, 776, 512, n->concat5, n->concat4));
+  Ls.push_back(make_layer("predict4", "", kConv, 24, 32, 770, 776, 2, 3, 1, 16, 1, 0, 2, 0, n->concat4, n->raw[4]));
+  Ls.push_back(make_layer("deconv3", "deconv3_bn", kDeconvK4S2, 24, 32, 770, 776, 128, 4, 2, 128, 0, 1, 392, 256, n->concat4, n->concat3));
+  Ls.push_back(make_layer("predict3", "", kConv, 48, 64, 386, 392, 2, 3, 1, 16, 1, 0, 2, 0, n->concat3, n->raw[3]));
+  Ls.push_back(make_layer("deconv2", "deconv2_bn", kDeconvK4S2, 48, 64, 386, 392, 64, 4, 2, 64, 0, 1, 200, 128, n->concat3, n->concat2));
+  // predict2 as a 1x1 GEMM with 18 columns on the 96x128 grid
+  Ls.push_back(make_layer("predict2", "", kConv, 96, 128, 194, 200, 18, 1, 1, 32, 1, 0, 18, 0, n->concat2, n->P2));
+  for (Layer& L : Ls) {
+    L.d.is_bf16 = n->is_bf16;
+    rc = conv_plan_geometry(L.plan, L.d);
+    if (rc != OFS_OK) { ofs_net_destroy(n); return rc; }
+    L.w_elems = (size_t)L.plan.w_rows * L.plan.k_total;
+    L.n_pad = L.plan.p.n_pad;
+    rc = dev_alloc(n, &L.w_dev, L.w_elems * 2, true);
+    if (rc == OFS_OK) rc = dev_alloc(n, (void**)&L.b_dev, (size_t)L.n_pad * 4, true);
+    if (rc != OFS_OK) { ofs_net_destroy(n); return rc; }
+  }
+  n->acts = {
+      {"conv1", {n->conv1, 192, 256, 64, 0, 64}},       {"conv2", {n->concat2, 96, 128, 200, 0, 128}},
+      {"conv3", {n->conv3, 48, 64, 256, 0, 256}},       {"conv3_1", {n->concat3, 48, 64, 392, 0, 256}},
+      {"conv4", {n->conv4, 24, 32, 512, 0, 512}},       {"conv4_1", {n->concat4, 24, 32, 776, 0, 512}},
+      {"conv5", {n->conv5, 12, 16, 512, 0, 512}},       {"conv5_1", {n->concat5, 12, 16, 1032, 0, 512}},
+      {"conv6", {n->conv6, 6, 8, 1024, 0, 1024}},       {"conv6_1", {n->conv6_1, 6, 8, 1024, 0, 1024}},
+      {"concat5", {n->concat5, 12, 16, 1032, 0, 1026}}, {"concat4", {n->concat4, 24, 32, 776, 0, 770}},
+      {"concat3", {n->concat3, 48, 64, 392, 0, 386}},   {"concat2", {n->concat2, 96, 128, 200, 0, 194}},
+      {"input", {n->x0, 384, 512, 32, 0, 27}}};
+  *out = n;
+  return OFS_OK;
+}
+
+int ofs_net_destroy(ofs_net* n) {
+  if (!n) return OFS_OK;
+  cudaSetDevice(n->device);
+  if (n->stream) { cudaStreamSynchronize(n->stream); cudaStreamDestroy(n->stream); }
+  for (void* p : n->allocs) cudaFree(p);
+  if (n->st_frames) cudaFree(n->st_frames);
+  if (n->st_out) cudaFree(n->st_out);
+  delete n;
+  return OFS_OK;
+}
+
+int ofs_net_load_weights(ofs_net* n, const ofs_named_array* arrays, int count) {
+  OFS_REQUIRE(n && arrays && count > 0, "ofs_net_load_weights: null / empty input");
+  OFS_CUDA(cudaSetDevice(n->device));
+  std::map<std::string, const ofs_named_array*> by_name;
+  for (int i = 0; i < count; ++i) {
+    OFS_REQUIRE(arrays[i].name && arrays[i].data, "ofs_net_load_weights: entry %d has a null name / data", i);
+    by_name[norm_key(arrays[i].name)] = &arrays[i];
+  }
+  auto find = [&](const std::string& key, int64_t numel, const float** ptr, bool required) -> int {
+    auto it = by_name.find(key);
+    if (it == by_name.end()) {
+      *ptr = nullptr;
+      if (required) { set_error("ofs_net_load_weights: missing array '%s'", key.c_str()); return OFS_EINVAL; }
+      return OFS_OK;
+    }
+    if (it->second->numel != numel) {
+      set_error("ofs_net_load_weights: '%s' has %lld elements, expected %lld", key.c_str(), (long long)it->second->numel,
+                (long long)numel);
+      return OFS_EINVAL;
+    }
+    *ptr = it->second->data;
+    return OFS_OK;
+  };
+  for (Layer& L : n->layers) {
+    const bool deconv = L.d.kind == kDeconvK4S2;
+    const bool is_p2 = L.name == "predict2";
+    const int cin = L.d.cin, cout = is_p2 ? 2 : L.d.cout, k = is_p2 ? 3 : L.d.k;
+    const int64_t wn = (int64_t)k * k * cin * cout;
+    const float *w = nullptr, *b = nullptr, *beta = nullptr, *mean = nullptr, *var = nullptr;
+    int rc = find(L.name + (deconv ? "/W_deconv2d" : "/W_conv2d"), wn, &w, true);
+    if (rc == OFS_OK) rc = find(L.name + (deconv ? "/b_deconv2d" : "/b_conv2d"), cout, &b, false);
+    if (rc == OFS_OK && !L.bn.empty()) {
+      rc = find(L.bn + "/beta", cout, &beta, false);
+      if (rc == OFS_OK) rc = find(L.bn + "/moving_mean", cout, &mean, false);
+      if (rc == OFS_OK) rc = find(L.bn + "/moving_variance", cout, &var, false);
+    }
+    if (rc != OFS_OK) return rc;
+    // fold BN: W' = W r, b' = (b - mu) r + beta, r = 1/sqrt(var + eps)   (double math, fp32 result)
+    std::vector<float> wf((size_t)wn), bf((size_t)cout, 0.0f);
+    std::vector<double> r((size_t)cout, 1.0);
+    for (int c = 0; c < cout; ++c) {
+      if (!L.bn.empty()) r[c] = 1.0 / std::sqrt((double)(var ? var[c] : 1.0f) + (double)kBnEps);
+      const double bb = b ? b[c] : 0.0, mu = mean ? mean[c] : 0.0, be = beta ? beta[c] : 0.0;
+      bf[c] = (float)((bb - mu) * r[c] + be);
+    }
+    if (deconv) {  // [4,4,cout,cin]
+      for (int t = 0; t < 16; ++t)
+        for (int c = 0; c < cout; ++c) {
+          const size_t o = ((size_t)t * cout + c) * cin;
+          for (int ci = 0; ci < cin; ++ci) wf[o + ci] = (float)((double)w[o + ci] * r[c]);
+        }
+    } else {  // [k,k,cin,cout]
+      for (size_t i = 0; i < (size_t)wn; ++i) wf[i] = (float)((double)w[i] * r[i % cout]);
+    }
+    std::vector<uint16_t> wp;
+    std::vector<float> bp;
+    if (is_p2) {
+      // [3,3,194,2] -> 1x1 conv with 18 output columns: column (ky*3+kx)*2 + o; bias applied in the gather
+      std::vector<float> w1((size_t)cin * 18);
+      for (int t = 0; t < 9; ++t)
+        for (int ci = 0; ci < cin; ++ci)
+          for (int o = 0; o < 2; ++o) w1[(size_t)ci * 18 + t * 2 + o] = wf[((size_t)t * cin + ci) * 2 + o];
+      conv_pack_weights(L.plan, w1.data(), nullptr, wp, bp);
+      n->p2_bias[0] = bf[0]; n->p2_bias[1] = bf[1];
+    } else {
+      conv_pack_weights(L.plan, wf.data(), bf.data(), wp, bp);
+    }
+    OFS_REQUIRE(wp.size() == L.w_elems && (int)bp.size() == L.n_pad, "internal: packed size mismatch for %s", L.name.c_str());
+    OFS_CUDA(cudaMemcpy(L.w_dev, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+    OFS_CUDA(cudaMemcpy(L.b_dev, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice));
+  }
+  static const char* ups[4] = {"upsample6_5", "upsample5_4", "upsample4_3", "upsample3_2"};
+  std::vector<float> upw(4 * 66, 0.0f);
+  for (int i = 0; i < 4; ++i) {
+    const float *w = nullptr, *b = nullptr;
+    int rc = find(std::string(ups[i]) + "/W_deconv2d", 64, &w, true);
+    if (rc == OFS_OK) rc = find(std::string(ups[i]) + "/b_deconv2d", 2, &b, false);
+    if (rc != OFS_OK) return rc;
+    memcpy(&upw[i * 66], w, 64 * 4);
+    if (b) { upw[i * 66 + 64] = b[0]; upw[i * 66 + 65] = b[1]; }
+  }
+  OFS_CUDA(cudaMemcpy(n->upw, upw.data(), upw.size() * 4, cudaMemcpyHostToDevice));
+  n->loaded = true;
+  n->prepared_B = 0;
+  return OFS_OK;
+}
+
+int ofs_net_forward(ofs_net* n, const float* feats, int B, float* f6, float* f5, float* f4, float* f3, float* f2,
+                    ofs_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = forward_impl(n, feats, B, f2, st);
+  if (rc != OFS_OK) return rc;
+  static const int hs[7] = {0, 0, 0, 48, 24, 12, 6}, ws[7] = {0, 0, 0, 64, 32, 16, 8};
+  float* outs[7] = {nullptr, nullptr, nullptr, f3, f4, f5, f6};
+  for (int l = 3; l <= 6; ++l)
+    if (outs[l])
+      OFS_CUDA(cudaMemcpyAsync(outs[l], n->f[l], (size_t)B * hs[l] * ws[l] * 2 * 4, cudaMemcpyDeviceToDevice, st));
+  return OFS_OK;
+}
+
+int ofs_net_stabilize(ofs_net* n, const float* feats, const float* frames, float* out, float* flow2_out, int B, int H,
+                      int W, ofs_stream stream) {
+  OFS_REQUIRE(frames && out, "ofs_net_stabilize: null pointer");
+  OFS_REQUIRE(H > 0 && W > 0, "ofs_net_stabilize: bad frame size %dx%d", H, W);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = forward_impl(n, feats, B, flow2_out, st);
+  if (rc != OFS_OK) return rc;
+  return flow_resize_warp_impl(frames, flow2_out ? flow2_out : n->f[2], out, B, H, W, 382, 510, st);
+}
+
+int ofs_net_stabilize_host(ofs_net* n, const float* feats_host, const float* frames_host, float* out_host, int B,
+                           int H, int W) {
+  OFS_REQUIRE(n && feats_host && frames_host && out_host, "ofs_net_stabilize_host: null pointer");
+  OFS_REQUIRE(B >= 1 && B <= n->max_batch && H > 0 && W > 0, "ofs_net_stabilize_host: bad shape");
+  OFS_CUDA(cudaSetDevice(n->device));
+  const size_t frame_bytes = (size_t)B * H * W * 3 * 4;
+  if (frame_bytes > n->st_frames_cap) {  // grow-only staging, sized on first use of a frame size
+    if (n->st_frames) cudaFree(n->st_frames);
+    if (n->st_out) cudaFree(n->st_out);
+    n->st_frames = n->st_out = nullptr;
+    n->st_frames_cap = 0;
+    const size_t cap = (size_t)n->max_batch * H * W * 3 * 4;
+    OFS_CUDA(cudaMalloc((void**)&n->st_frames, cap));
+    OFS_CUDA(cudaMalloc((void**)&n->st_out, cap));
+    n->st_frames_cap = cap;
+  }
+  cudaStream_t st = n->stream;
+  OFS_CUDA(cudaMemcpyAsync(n->st_feats, feats_host, (size_t)B * kNetH * kNetW * kNetC * 4, cudaMemcpyHostToDevice, st));
+  OFS_CUDA(cudaMemcpyAsync(n->st_frames, frames_host, frame_bytes, cudaMemcpyHostToDevice, st));
+  int rc = ofs_net_stabilize(n, n->st_feats, n->st_frames, n->st_out, nullptr, B, H, W, (ofs_stream)st);
+  if (rc != OFS_OK) return rc;
+  OFS_CUDA(cudaMemcpyAsync(out_host, n->st_out, frame_bytes, cudaMemcpyDeviceToHost, st));
+  OFS_CUDA(cudaStreamSynchronize(st));
+  return OFS_OK;
+}
+
+int ofs_net_get_activation(ofs_net* n, const char* name, int B, float* out, int64_t capacity, int* shape4,
+                           ofs_stream stream) {
+  OFS_REQUIRE(n && name && out, "ofs_net_get_activation: null pointer");
+  auto it = n->acts.find(name);
+  OFS_REQUIRE(it != n->acts.end(), "ofs_net_get_activation: unknown activation '%s'", name);
+  const ActInfo& a = it->second;
+  OFS_REQUIRE(B >= 1 && B <= n->max_batch, "ofs_net_get_activation: bad batch");
+  const int64_t need = (int64_t)B * a.H * a.W * a.C;
+  OFS_REQUIRE(capacity >= need, "ofs_net_get_activation: capacity %lld < %lld", (long long)capacity, (long long)need);
+  if (shape4) { shape4[0] = B; shape4[1] = a.H; shape4[2] = a.W; shape4[3] = a.C; }
+  return launch_unpack_act(a.ptr, out, (size_t)B * a.H * a.W, a.cs, a.coff, a.C, n->is_bf16, (cudaStream_t)stream);
+}
+
+int ofs_net_launches_per_forward(const ofs_net* n) {
+  return n ? 1 + (int)n->layers.size() + 4 + 1 : 0;  // pack + GEMM layers + 4 pyramid steps + predict2 gather
+}
+
+}  // extern "C"

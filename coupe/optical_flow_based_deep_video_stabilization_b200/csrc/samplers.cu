@@ -1,0 +1,554 @@
+// Bandwidth-bound gather kernels of the stabiliser hot path (sm_100a):
+//   ofs_tf_warp              <- tf_warp / get_pixel_value        main_dl.py:44-130
+//   ofs_flow_resize(_warp)   <- test-mode flow glue              main_dl.py:497-514
+//   ofs_grid_sample_*        <- Affine/ProjectiveTransformer     spatial_transformer.py:373-452,519-608,755-779,902-964
+//   ofs_vec2mtrx/ofs_lie_warp<- vec2mtrx / transformImage / transformCropImage   warp.py:25-129
+//
+// Design (HBM-bound, 32 B/px for tf_warp at C=3):
+//   * each thread owns 4 consecutive output pixels of one row: flow is read as 2x128-bit loads,
+//     the 4x3 fp32 results leave as 3x128-bit stores (12-byte pixels are not 16-byte aligned
+//     one by one, 4 of them are);
+//   * the "staged" tf_warp variant loads the bounding box of the source pixels a 64x16 output
+//     tile touches into shared memory with fully coalesced loads (bbox found with warp-shuffle
+//     min/max reductions) and gathers the 4 corners from shared memory; tiles whose bbox does
+//     not fit fall back to direct read-only-path gathers;
+//   * grids are sized as a multiple of the SM count and grid-stride over the work.
+// Arithmetic follows the reference operation by operation where that decides an index
+// (truncation vs floor, clip order, fp32 coordinate products); see oracle/samplers.py.
+#include "ofs_common.cuh"
+
+namespace ofs {
+namespace {
+
+struct Taps {
+  int y[4];
+  int x[4];  // source pixel; x < 0 marks "contributes zero"
+  float w[4];
+};
+
+__device__ __forceinline__ int clip_i(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// ---- main_dl.py:83-120 ------------------------------------------------------------------------
+__device__ __forceinline__ Taps taps_tfwarp(float fx, float fy, int ox, int oy, int H, int W) {
+  Taps t;
+  const float x = (float)ox + fx;
+  const float y = (float)oy + fy;
+  const int xi = __float2int_rz(x);  // tf.cast(float->int32): truncation toward zero
+  const int yi = __float2int_rz(y);
+  const int x0 = clip_i(xi, 0, W - 1);
+  const int y0 = clip_i(yi, 0, H - 1);
+  const int x1 = (xi >= W - 1) ? (W - 1) : max(xi + 1, 0);  // clip(xi+1) without int overflow
+  const int y1 = (yi >= H - 1) ? (H - 1) : max(yi + 1, 0);
+  const float x0f = (float)x0, x1f = (float)x1, y0f = (float)y0, y1f = (float)y1;
+  t.y[0] = y0; t.x[0] = x0; t.w[0] = (x1f - x) * (y1f - y);  // Ia
+  t.y[1] = y1; t.x[1] = x0; t.w[1] = (x1f - x) * (y - y0f);  // Ib
+  t.y[2] = y0; t.x[2] = x1; t.w[2] = (x - x0f) * (y1f - y);  // Ic
+  t.y[3] = y1; t.x[3] = x1; t.w[3] = (x - x0f) * (y - y0f);  // Id
+  return t;
+}
+
+// ---- main_dl.py:497-498 (TF1 legacy bilinear of the pre-scaled flow, then per-axis rescale) ----
+struct FlowResize {
+  const float* flow2;  // [B,fh,fw,2]
+  int fh, fw, H, W;
+  float hs, ws;  // fh/H, fw/W in fp32 like CalculateResizeScale
+  __device__ __forceinline__ float2 at(int b, int oy, int ox) const {
+    const float iy = (float)oy * hs;
+    const float ix = (float)ox * ws;
+    const int y0 = (int)floorf(iy), x0 = (int)floorf(ix);
+    const int y1 = min(y0 + 1, fh - 1), x1 = min(x0 + 1, fw - 1);
+    const float yl = iy - (float)y0, xl = ix - (float)x0;
+    const float2* base = reinterpret_cast<const float2*>(flow2) + (size_t)b * fh * fw;
+    float2 tl = __ldg(base + (size_t)y0 * fw + x0), tr = __ldg(base + (size_t)y0 * fw + x1);
+    float2 bl = __ldg(base + (size_t)y1 * fw + x0), br = __ldg(base + (size_t)y1 * fw + x1);
+    const float fhf = (float)fh;
+    // outputs['predict_flow2'] * 384.0 / 382  (multiply, then true division)
+    tl.x = __fdiv_rn(tl.x * 384.0f, fhf); tl.y = __fdiv_rn(tl.y * 384.0f, fhf);
+    tr.x = __fdiv_rn(tr.x * 384.0f, fhf); tr.y = __fdiv_rn(tr.y * 384.0f, fhf);
+    bl.x = __fdiv_rn(bl.x * 384.0f, fhf); bl.y = __fdiv_rn(bl.y * 384.0f, fhf);
+    br.x = __fdiv_rn(br.x * 384.0f, fhf); br.y = __fdiv_rn(br.y * 384.0f, fhf);
+    float2 top, bot, v;
+    top.x = tl.x + (tr.x - tl.x) * xl; top.y = tl.y + (tr.y - tl.y) * xl;
+    bot.x = bl.x + (br.x - bl.x) * xl; bot.y = bl.y + (br.y - bl.y) * xl;
+    v.x = top.x + (bot.x - top.x) * yl;
+    v.y = top.y + (bot.y - top.y) * yl;
+    v.x = __fdiv_rn(v.x * (float)W, 512.0f);  // outflow[...,0:1]*out_w/512
+    v.y = __fdiv_rn(v.y * (float)H, 384.0f);  // outflow[...,1:2]*out_h/384
+    return v;
+  }
+};
+
+// ---- spatial_transformer.py:755-779 + 442-451 / 578-602 + 916-961 -------------------------------
+struct GridSampleCoord {
+  const float* theta;  // [B,6] or [B,8]
+  int projective;
+  int H, W, oH, oW;
+  float step_x, step_y;  // tf.linspace fp32 step
+  __device__ __forceinline__ Taps taps(int b, int oy, int ox) const {
+    const float xt = (oW == 1) ? -1.0f : __fadd_rn(-1.0f, __fmul_rn(step_x, (float)ox));
+    const float yt = (oH == 1) ? -1.0f : __fadd_rn(-1.0f, __fmul_rn(step_y, (float)oy));
+    float xs, ys;
+    if (projective) {
+      const float* t = theta + (size_t)b * 8;
+      xs = __ldg(t + 0) * xt + __ldg(t + 1) * yt + __ldg(t + 2);
+      ys = __ldg(t + 3) * xt + __ldg(t + 4) * yt + __ldg(t + 5);
+      float zs = __ldg(t + 6) * xt + __ldg(t + 7) * yt + 1.0f;
+      if (zs == 0.0f) zs = zs + 1e-8f;
+      xs = __fdiv_rn(xs, zs);
+      ys = __fdiv_rn(ys, zs);
+    } else {
+      const float* t = theta + (size_t)b * 6;
+      xs = __ldg(t + 0) * xt + __ldg(t + 1) * yt + __ldg(t + 2);
+      ys = __ldg(t + 3) * xt + __ldg(t + 4) * yt + __ldg(t + 5);
+    }
+    const float Wf = (float)W, Hf = (float)H;
+    float x = __fmul_rn(__fdiv_rn(__fadd_rn(xs, 1.0f), 2.0f), Wf - 1.0f);
+    float y = __fmul_rn(__fdiv_rn(__fadd_rn(ys, 1.0f), 2.0f), Hf - 1.0f);
+    x = fminf(fmaxf(x, -1.0f), Wf) + 1.0f;  // clip to [-edge, W-1+edge], then += edge
+    y = fminf(fmaxf(y, -1.0f), Hf) + 1.0f;
+    const float x0f = floorf(x), y0f = floorf(y);
+    const float x1f = x0f + 1.0f, y1f = y0f + 1.0f;
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const int x1 = (int)fminf(x1f, Wf + 1.0f), y1 = (int)fminf(y1f, Hf + 1.0f);
+    Taps tp;
+    // coordinates are on the 1-px zero-padded image; map back, outside -> zero tap
+    auto put = [&](int i, int yp, int xp, float w) {
+      const bool in = (yp >= 1) && (yp <= H) && (xp >= 1) && (xp <= W);
+      tp.y[i] = in ? yp - 1 : 0;
+      tp.x[i] = in ? xp - 1 : -1;
+      tp.w[i] = w;
+    };
+    put(0, y0, x0, (x1f - x) * (y1f - y));  // w00 I00
+    put(1, y0, x1, (x - x0f) * (y1f - y));  // w01 I01
+    put(2, y1, x0, (x1f - x) * (y - y0f));  // w10 I10
+    put(3, y1, x1, (x - x0f) * (y - y0f));  // w11 I11
+    return tp;
+  }
+};
+
+// ---- warp.py:46-86 / 89-129 ----------------------------------------------------------------------
+struct LieCoord {
+  const float* pMtrx;    // [B,3,3]
+  const float* refMtrx;  // [3,3]
+  int srcH, srcW, oH, oW;
+  __device__ __forceinline__ Taps taps(int b, int oy, int ox) const {
+    float M[9];
+    const float* P = pMtrx + (size_t)b * 9;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        M[r * 3 + c] = __ldg(refMtrx + r * 3 + 0) * __ldg(P + 0 + c) + __ldg(refMtrx + r * 3 + 1) * __ldg(P + 3 + c) +
+                       __ldg(refMtrx + r * 3 + 2) * __ldg(P + 6 + c);
+    // np.linspace(-1,1,n) evaluated in float64, then astype(float32)
+    const float X = (oW == 1) ? -1.0f : (ox == oW - 1 ? 1.0f : (float)(-1.0 + (double)ox * (2.0 / (double)(oW - 1))));
+    const float Y = (oH == 1) ? -1.0f : (oy == oH - 1 ? 1.0f : (float)(-1.0 + (double)oy * (2.0 / (double)(oH - 1))));
+    const float h0 = M[0] * X + M[1] * Y + M[2];
+    const float h1 = M[3] * X + M[4] * Y + M[5];
+    const float h2 = M[6] * X + M[7] * Y + M[8];
+    const float Xw = __fdiv_rn(h0, h2 + 1e-8f);
+    const float Yw = __fdiv_rn(h1, h2 + 1e-8f);
+    const float xf = floorf(Xw), xc = ceilf(Xw), yf = floorf(Yw), yc = ceilf(Yw);
+    const float xr = Xw - xf, yr = Yw - yf;
+    // clamp before the int conversion (far-outside stays outside; avoids UB on huge values)
+    const int xfi = (int)fminf(fmaxf(xf, -2.0f), (float)srcW + 1.0f);
+    const int xci = (int)fminf(fmaxf(xc, -2.0f), (float)srcW + 1.0f);
+    const int yfi = (int)fminf(fmaxf(yf, -2.0f), (float)srcH + 1.0f);
+    const int yci = (int)fminf(fmaxf(yc, -2.0f), (float)srcH + 1.0f);
+    Taps tp;
+    auto put = [&](int i, int yi, int xi, float w) {
+      const bool in = (xi >= 0) && (xi < srcW) && (yi >= 0) && (yi < srcH);
+      tp.y[i] = in ? yi : 0;
+      tp.x[i] = in ? xi : -1;
+      tp.w[i] = w;
+    };
+    put(0, yfi, xfi, (1.0f - xr) * (1.0f - yr));  // UL
+    put(1, yfi, xci, xr * (1.0f - yr));           // UR
+    put(2, yci, xfi, (1.0f - xr) * yr);           // BL
+    put(3, yci, xci, xr * yr);                    // BR
+    return tp;
+  }
+};
+
+// -------------------------------------------------------------------------------------------------
+// tap providers for the generic kernels
+struct TfWarpProvider {
+  const float* flow;  // [B,H,W,2]
+  int H, W;
+  __device__ __forceinline__ Taps taps(int b, int oy, int ox) const {
+    const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + ((size_t)b * H + oy) * W + ox);
+    return taps_tfwarp(f.x, f.y, ox, oy, H, W);
+  }
+  // 4 consecutive pixels: two 128-bit loads
+  __device__ __forceinline__ void taps4(int b, int oy, int ox, Taps* t) const {
+    const float4* p = reinterpret_cast<const float4*>(flow + (((size_t)b * H + oy) * W + ox) * 2);
+    const float4 a = __ldg(p), c = __ldg(p + 1);
+    t[0] = taps_tfwarp(a.x, a.y, ox + 0, oy, H, W);
+    t[1] = taps_tfwarp(a.z, a.w, ox + 1, oy, H, W);
+    t[2] = taps_tfwarp(c.x, c.y, ox + 2, oy, H, W);
+    t[3] = taps_tfwarp(c.z, c.w, ox + 3, oy, H, W);
+  }
+};
+struct ResizeWarpProvider {
+  FlowResize fr;
+  __device__ __forceinline__ Taps taps(int b, int oy, int ox) const {
+    const float2 f = fr.at(b, oy, ox);
+    return taps_tfwarp(f.x, f.y, ox, oy, fr.H, fr.W);
+  }
+  __device__ __forceinline__ void taps4(int b, int oy, int ox, Taps* t) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = taps(b, oy, ox + j);
+  }
+};
+template <class Coord>
+struct CoordProvider {
+  Coord c;
+  __device__ __forceinline__ Taps taps(int b, int oy, int ox) const { return c.taps(b, oy, ox); }
+  __device__ __forceinline__ void taps4(int b, int oy, int ox, Taps* t) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = c.taps(b, oy, ox + j);
+  }
+};
+
+// 12-byte pixel gather through the read-only path
+__device__ __forceinline__ void gather3(const float* __restrict__ imgb, int srcW, int y, int x, float w, float* acc) {
+  if (x >= 0) {
+    const float* p = imgb + ((size_t)y * srcW + x) * 3;
+    acc[0] += w * __ldg(p + 0);
+    acc[1] += w * __ldg(p + 1);
+    acc[2] += w * __ldg(p + 2);
+  }
+}
+
+// one thread = 4 consecutive output pixels, C == 3, oW % 4 == 0
+template <class Provider>
+__global__ void __launch_bounds__(256) sample_quad3_kernel(Provider prov, const float* __restrict__ img,
+                                                           float* __restrict__ out, int B, int srcH, int srcW, int oH,
+                                                           int oW) {
+  const int qpr = oW >> 2;
+  const size_t total = (size_t)B * oH * qpr;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+    const int qx = (int)(q % qpr);
+    const size_t r = q / qpr;
+    const int oy = (int)(r % oH);
+    const int b = (int)(r / oH);
+    const int ox = qx << 2;
+    Taps t[4];
+    prov.taps4(b, oy, ox, t);
+    const float* imgb = img + (size_t)b * srcH * srcW * 3;
+    float acc[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) acc[i] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) gather3(imgb, srcW, t[j].y[k], t[j].x[k], t[j].w[k], acc + 3 * j);
+    float4* o = reinterpret_cast<float4*>(out + (((size_t)b * oH + oy) * oW + ox) * 3);
+    __stcs(o + 0, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    __stcs(o + 1, make_float4(acc[4], acc[5], acc[6], acc[7]));
+    __stcs(o + 2, make_float4(acc[8], acc[9], acc[10], acc[11]));
+  }
+}
+
+// generic: any C, any width; one thread = one output pixel
+template <class Provider>
+__global__ void __launch_bounds__(256) sample_px_kernel(Provider prov, const float* __restrict__ img,
+                                                        float* __restrict__ out, int B, int srcH, int srcW, int oH,
+                                                        int oW, int C) {
+  const size_t total = (size_t)B * oH * oW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % oW);
+    const size_t r = i / oW;
+    const int oy = (int)(r % oH);
+    const int b = (int)(r / oH);
+    const Taps t = prov.taps(b, oy, ox);
+    const float* imgb = img + (size_t)b * srcH * srcW * C;
+    float* o = out + i * C;
+    for (int c = 0; c < C; ++c) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (t.x[k] >= 0) acc += t.w[k] * __ldg(imgb + ((size_t)t.y[k] * srcW + t.x[k]) * C + c);
+      o[c] = acc;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// staged tf_warp: 64x16 output tile per 256-thread block, source bbox in shared memory
+constexpr int kTileW = 64, kTileH = 16;
+constexpr int kStageMaxPx = 3840;  // 45 KB of fp32 RGB (static shared memory limit is 48 KB)
+
+__device__ __forceinline__ int warp_min(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <class Provider>
+__global__ void __launch_bounds__(256) warp_staged3_kernel(Provider prov, const float* __restrict__ img,
+                                                           float* __restrict__ out, int B, int H, int W) {
+  __shared__ float tile[kStageMaxPx * 3];
+  __shared__ int red[4][8];
+  __shared__ int bbox[4];
+  const int tiles_x = (W + kTileW - 1) / kTileW;
+  const int tiles_y = (H + kTileH - 1) / kTileH;
+  const size_t ntiles = (size_t)B * tiles_y * tiles_x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 quads x 16 rows
+  for (size_t tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
+    const int tix = (int)(tile_id % tiles_x);
+    const size_t r = tile_id / tiles_x;
+    const int tiy = (int)(r % tiles_y);
+    const int b = (int)(r / tiles_y);
+    const int ox = tix * kTileW + tx * 4, oy = tiy * kTileH + ty;
+    const bool active = (ox < W) && (oy < H);  // W % 4 == 0, so a quad is fully in or out
+    Taps t[4];
+    int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
+    if (active) {
+      prov.taps4(b, oy, ox, t);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        xmin = min(xmin, t[j].x[0]); xmax = max(xmax, t[j].x[3]);  // x0 <= x1, y0 <= y1 after clipping
+        ymin = min(ymin, t[j].y[0]); ymax = max(ymax, t[j].y[3]);
+      }
+    }
+    xmin = warp_min(xmin); ymin = warp_min(ymin); xmax = warp_max(xmax); ymax = warp_max(ymax);
+    if (lane == 0) { red[0][wid] = xmin; red[1][wid] = xmax; red[2][wid] = ymin; red[3][wid] = ymax; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int a = (lane < 8) ? red[0][lane] : INT_MAX, c = (lane < 8) ? red[1][lane] : INT_MIN;
+      int d = (lane < 8) ? red[2][lane] : INT_MAX, e = (lane < 8) ? red[3][lane] : INT_MIN;
+      a = warp_min(a); c = warp_max(c); d = warp_min(d); e = warp_max(e);
+      if (lane == 0) { bbox[0] = a; bbox[1] = c; bbox[2] = d; bbox[3] = e; }
+    }
+    __syncthreads();
+    const int bx0 = bbox[0], bx1 = bbox[1], by0 = bbox[2], by1 = bbox[3];
+    const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;
+    const float* imgb = img + (size_t)b * H * W * 3;
+    float acc[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) acc[i] = 0.0f;
+    const bool staged = (bw > 0) && (bh > 0) && ((long long)bw * bh <= kStageMaxPx);
+    if (staged) {
+      const int row_f = bw * 3;
+      for (int rr = wid; rr < bh; rr += 8) {  // one warp per source row: coalesced 128-byte lines
+        const float* src = imgb + ((size_t)(by0 + rr) * W + bx0) * 3;
+        float* dst = tile + rr * row_f;
+        for (int i = lane; i < row_f; i += 32) dst[i] = __ldg(src + i);
+      }
+      __syncthreads();
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float* p = tile + ((t[j].y[k] - by0) * bw + (t[j].x[k] - bx0)) * 3;
+            const float w = t[j].w[k];
+            acc[3 * j + 0] += w * p[0];
+            acc[3 * j + 1] += w * p[1];
+            acc[3 * j + 2] += w * p[2];
+          }
+      }
+    } else if (active) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gather3(imgb, W, t[j].y[k], t[j].x[k], t[j].w[k], acc + 3 * j);
+    }
+    if (active) {
+      float4* o = reinterpret_cast<float4*>(out + (((size_t)b * H + oy) * W + ox) * 3);
+      __stcs(o + 0, make_float4(acc[0], acc[1], acc[2], acc[3]));
+      __stcs(o + 1, make_float4(acc[4], acc[5], acc[6], acc[7]));
+      __stcs(o + 2, make_float4(acc[8], acc[9], acc[10], acc[11]));
+    }
+    __syncthreads();  // tile / bbox reuse
+  }
+}
+
+__global__ void flow_resize_kernel(FlowResize fr, float* __restrict__ out, int B) {
+  const size_t total = (size_t)B * fr.H * fr.W;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % fr.W);
+    const size_t r = i / fr.W;
+    const int oy = (int)(r % fr.H);
+    const int b = (int)(r / fr.H);
+    reinterpret_cast<float2*>(out)[i] = fr.at(b, oy, ox);
+  }
+}
+
+// warp.py:25-43, one thread per batch element
+__global__ void vec2mtrx_kernel(const float* __restrict__ p, float* __restrict__ out, int B, int warp_type,
+                                int warp_approx) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float A[9];
+  if (warp_type == 0) {
+    const float* q = p + (size_t)b * 8;
+    const float p1 = q[0], p2 = q[1], p3 = q[2], p4 = q[3], p5 = q[4], p6 = q[5], p7 = q[6], p8 = q[7];
+    A[0] = p3; A[1] = p2; A[2] = p1;
+    A[3] = p6; A[4] = -p3 - p7; A[5] = p5;
+    A[6] = p4; A[7] = p8; A[8] = p7;
+  } else {
+    const float* q = p + (size_t)b * 6;
+    A[0] = q[0]; A[1] = q[1]; A[2] = q[2];
+    A[3] = q[3]; A[4] = q[4]; A[5] = q[5];
+    A[6] = 0.f; A[7] = 0.f; A[8] = 0.f;
+  }
+  float M[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, N[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  float denom = 1.0f;
+  for (int i = 1; i < warp_approx; ++i) {
+    float T[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) T[r * 3 + c] = N[r * 3 + 0] * A[c] + N[r * 3 + 1] * A[3 + c] + N[r * 3 + 2] * A[6 + c];
+    denom *= (float)i;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      N[k] = T[k];
+      M[k] += __fdiv_rn(T[k], denom);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) out[(size_t)b * 9 + k] = M[k];
+}
+
+int grid_for(size_t work_items, int threads) {
+  const int sms = sm_count();
+  size_t blocks = (work_items + threads - 1) / threads;
+  const size_t cap = (size_t)sms * 8;  // 8 resident 256-thread blocks per SM
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) blocks = 1;
+  return (int)blocks;
+}
+
+int g_warp_variant = 1;  // 0 = direct gathers, 1 = shared-memory staged (default)
+
+template <class Provider>
+int launch_sampler(Provider prov, const float* img, float* out, int B, int srcH, int srcW, int oH, int oW, int C,
+                   bool allow_staged, cudaStream_t st) {
+  if (B == 0 || oH == 0 || oW == 0) return OFS_OK;
+  const bool aligned = (((uintptr_t)out) % 16 == 0);
+  if (C == 3 && (oW % 4) == 0 && aligned) {
+    if (allow_staged && g_warp_variant == 1) {
+      const size_t ntiles = (size_t)B * ((oH + kTileH - 1) / kTileH) * ((oW + kTileW - 1) / kTileW);
+      const int sms = sm_count();
+      size_t blocks = ntiles < (size_t)sms * 4 ? ntiles : (size_t)sms * 4;
+      warp_staged3_kernel<Provider><<<(int)blocks, 256, 0, st>>>(prov, img, out, B, oH, oW);
+    } else {
+      const size_t quads = (size_t)B * oH * (oW / 4);
+      sample_quad3_kernel<Provider><<<grid_for(quads, 256), 256, 0, st>>>(prov, img, out, B, srcH, srcW, oH, oW);
+    }
+  } else {
+    const size_t px = (size_t)B * oH * oW;
+    sample_px_kernel<Provider><<<grid_for(px, 256), 256, 0, st>>>(prov, img, out, B, srcH, srcW, oH, oW, C);
+  }
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
+}
+
+}  // namespace
+
+int tf_warp_impl(const float* img, const float* flow, float* out, int B, int H, int W, int C, cudaStream_t st) {
+  OFS_REQUIRE(img && flow && out, "ofs_tf_warp: null pointer");
+  OFS_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0, "ofs_tf_warp: bad shape B=%d H=%d W=%d C=%d", B, H, W, C);
+  OFS_REQUIRE(((uintptr_t)flow) % 8 == 0, "ofs_tf_warp: flow must be 8-byte aligned");
+  TfWarpProvider prov{flow, H, W};
+  const bool vec_ok = (((uintptr_t)flow) % 16 == 0);
+  if (!vec_ok || (W % 4) != 0 || C != 3) {
+    if (B == 0) return OFS_OK;
+    const size_t px = (size_t)B * H * W;
+    sample_px_kernel<TfWarpProvider><<<grid_for(px, 256), 256, 0, st>>>(prov, img, out, B, H, W, H, W, C);
+    OFS_LAUNCH_CHECK();
+    return OFS_OK;
+  }
+  return launch_sampler(prov, img, out, B, H, W, H, W, C, true, st);
+}
+
+int flow_resize_impl(const float* flow2, float* out, int B, int fh, int fw, int H, int W, cudaStream_t st) {
+  OFS_REQUIRE(flow2 && out, "ofs_flow_resize: null pointer");
+  OFS_REQUIRE(B >= 0 && fh > 0 && fw > 0 && H > 0 && W > 0, "ofs_flow_resize: bad shape");
+  if (B == 0) return OFS_OK;
+  FlowResize fr{flow2, fh, fw, H, W, (float)fh / (float)H, (float)fw / (float)W};
+  flow_resize_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, st>>>(fr, out, B);
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
+}
+
+int flow_resize_warp_impl(const float* img, const float* flow2, float* out, int B, int H, int W, int fh, int fw,
+                          cudaStream_t st) {
+  OFS_REQUIRE(img && flow2 && out, "ofs_flow_resize_warp: null pointer");
+  OFS_REQUIRE(B >= 0 && fh > 0 && fw > 0 && H > 0 && W > 0, "ofs_flow_resize_warp: bad shape");
+  ResizeWarpProvider prov{FlowResize{flow2, fh, fw, H, W, (float)fh / (float)H, (float)fw / (float)W}};
+  return launch_sampler(prov, img, out, B, H, W, H, W, 3, true, st);
+}
+
+}  // namespace ofs
+
+extern "C" {
+
+int ofs_set_warp_variant(int v) {
+  ofs::g_warp_variant = v ? 1 : 0;
+  return OFS_OK;
+}
+
+int ofs_tf_warp(const float* img, const float* flow, float* out, int B, int H, int W, int C, ofs_stream stream) {
+  return ofs::tf_warp_impl(img, flow, out, B, H, W, C, (cudaStream_t)stream);
+}
+
+int ofs_flow_resize(const float* flow2, float* out, int B, int fh, int fw, int H, int W, ofs_stream stream) {
+  return ofs::flow_resize_impl(flow2, out, B, fh, fw, H, W, (cudaStream_t)stream);
+}
+
+int ofs_flow_resize_warp(const float* img, const float* flow2, float* out, int B, int H, int W, int fh, int fw,
+                         ofs_stream stream) {
+  return ofs::flow_resize_warp_impl(img, flow2, out, B, H, W, fh, fw, (cudaStream_t)stream);
+}
+
+static int grid_sample(const float* im, const float* theta, float* out, int B, int H, int W, int C, int oH, int oW,
+                       int projective, ofs_stream stream) {
+  OFS_REQUIRE(im && theta && out, "ofs_grid_sample: null pointer");
+  OFS_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && oH > 0 && oW > 0, "ofs_grid_sample: bad shape");
+  ofs::GridSampleCoord gc;
+  gc.theta = theta; gc.projective = projective; gc.H = H; gc.W = W; gc.oH = oH; gc.oW = oW;
+  gc.step_x = oW > 1 ? 2.0f / (float)(oW - 1) : 0.0f;
+  gc.step_y = oH > 1 ? 2.0f / (float)(oH - 1) : 0.0f;
+  ofs::CoordProvider<ofs::GridSampleCoord> prov{gc};
+  return ofs::launch_sampler(prov, im, out, B, H, W, oH, oW, C, false, (cudaStream_t)stream);
+}
+
+int ofs_grid_sample_affine(const float* im, const float* theta, float* out, int B, int H, int W, int C, int oH,
+                           int oW, ofs_stream stream) {
+  return grid_sample(im, theta, out, B, H, W, C, oH, oW, 0, stream);
+}
+int ofs_grid_sample_projective(const float* im, const float* theta, float* out, int B, int H, int W, int C, int oH,
+                               int oW, ofs_stream stream) {
+  return grid_sample(im, theta, out, B, H, W, C, oH, oW, 1, stream);
+}
+
+int ofs_vec2mtrx(const float* p, float* pMtrx, int B, int warp_type, int warp_approx, ofs_stream stream) {
+  OFS_REQUIRE(p && pMtrx, "ofs_vec2mtrx: null pointer");
+  OFS_REQUIRE(warp_type == 0 || warp_type == 1, "ofs_vec2mtrx: warp_type must be 0 (homography) or 1 (affine)");
+  OFS_REQUIRE(B >= 0 && warp_approx >= 1, "ofs_vec2mtrx: bad B / warp_approx");
+  if (B == 0) return OFS_OK;
+  ofs::vec2mtrx_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p, pMtrx, B, warp_type, warp_approx);
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
+}
+
+int ofs_lie_warp(const float* image, const float* pMtrx, const float* refMtrx, float* out, int B, int srcH, int srcW,
+                 int outH, int outW, ofs_stream stream) {
+  OFS_REQUIRE(image && pMtrx && refMtrx && out, "ofs_lie_warp: null pointer");
+  OFS_REQUIRE(B >= 0 && srcH > 0 && srcW > 0 && outH > 0 && outW > 0, "ofs_lie_warp: bad shape");
+  ofs::LieCoord lc{pMtrx, refMtrx, srcH, srcW, outH, outW};
+  ofs::CoordProvider<ofs::LieCoord> prov{lc};
+  return ofs::launch_sampler(prov, image, out, B, srcH, srcW, outH, outW, 3, false, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,161 @@
+/*
+ * ofstab.h -- C ABI of libofstab.so: the B200 (sm_100a) inference hot path of
+ * posgraph/coupe.optical_flow_based_deep_video_stabilization.
+ *
+ * The reference has no FFI / plugin layer: its "operator API" is a set of Python call
+ * signatures evaluated inside one tf.Session.run per frame.  Each entry point below
+ * replaces the device work behind one of those signatures (reference file:line cited
+ * per function; paths relative to the reference repo, "main_dl.py" =
+ * main_flownetS_pyramid_noprevloss_dataloader.py).  INTEGRATION.md shows the ctypes
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every tensor is a raw pointer + sizes, NHWC, float32 unless
+ *     stated.  "dev" pointers are CUDA device pointers on the net's / current device,
+ *     "host" pointers are CPU memory (pinned memory makes the copies asynchronous).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device-
+ *     pointer entry points are stream-ordered and return without synchronising.
+ *   - every function returns an ofs_status (0 = OK).  On failure a thread-local message
+ *     is available from ofs_last_error().  There is no CPU fallback: a device that is
+ *     not compute capability 10.x yields OFS_ENOTSM100.
+ */
+#ifndef OFSTAB_H_
+#define OFSTAB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFS_VERSION 100 /* 0.1.0 */
+
+typedef enum ofs_status {
+  OFS_OK = 0,
+  OFS_EINVAL = 1,    /* bad shape / null pointer / misaligned pointer                */
+  OFS_ECUDA = 2,     /* a CUDA runtime / driver call failed (message has the detail) */
+  OFS_ENOTSM100 = 3, /* device is not a Blackwell sm_100 part                         */
+  OFS_ENOMEM = 4,
+  OFS_ESTATE = 5     /* call order (e.g. forward before load_weights)                */
+} ofs_status;
+
+typedef void* ofs_stream; /* cudaStream_t */
+
+/* operand format of the tensor-core GEMMs (accumulation is always fp32) */
+typedef enum ofs_precision {
+  OFS_PREC_BF16 = 0, /* bf16 operands (default; the north-star configuration)              */
+  OFS_PREC_FP16 = 1  /* IEEE half operands: same tensor rate, 8x finer mantissa, less range */
+} ofs_precision;
+
+int ofs_version(void);
+/* thread-local message of the last failure on this thread ("" if none) */
+const char* ofs_last_error(void);
+/* OFS_OK iff `device` exists and is compute capability 10.x */
+int ofs_device_check(int device);
+/* number of kernels this library has launched since load (all threads); bench.py's gpu_launches */
+uint64_t ofs_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense backward warp.  Replaces tf_warp(img, flow, H, W) + get_pixel_value
+ * (main_dl.py:44-130): x = col + flow[...,0], y = row + flow[...,1]; corners by truncation
+ * toward zero, clipped to the image; weights from the clipped corners.
+ *   img  [B,H,W,C] dev, flow [B,H,W,2] dev, out [B,H,W,C] dev.
+ */
+int ofs_tf_warp(const float* img, const float* flow, float* out, int B, int H, int W, int C, ofs_stream stream);
+
+/* Tuning knob for ofs_tf_warp / ofs_flow_resize_warp at C=3: 1 (default) = shared-memory staged
+ * source tiles, 0 = direct read-only-path gathers.  Results are identical. */
+int ofs_set_warp_variant(int variant);
+
+/* Test-mode flow glue (main_dl.py:497-498): flow2*(384/fh) -> TF1 legacy bilinear resize to
+ * HxW -> x*W/512, y*H/384.   flow2 [B,fh,fw,2] dev (fh=382, fw=510 for the network),
+ * out [B,H,W,2] dev. */
+int ofs_flow_resize(const float* flow2, float* out, int B, int fh, int fw, int H, int W, ofs_stream stream);
+
+/* Fused main_dl.py:497-514: ofs_flow_resize + ofs_tf_warp without materialising the HxW flow.
+ *   img [B,H,W,3] dev, flow2 [B,fh,fw,2] dev, out [B,H,W,3] dev. */
+int ofs_flow_resize_warp(const float* img, const float* flow2, float* out, int B, int H, int W, int fh, int fw,
+                         ofs_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Spatial transformers.  Replace AffineTransformer(out_size).transform(inp, theta)
+ * (spatial_transformer.py:373-452) and ProjectiveTransformer (:519-608), both through
+ * _meshgrid (:755-779) and bilinear_interp (:902-964: 1-px zero border, clip to [-1, W]).
+ *   im [B,H,W,C] dev, theta [B,6] (affine) or [B,8] (projective) dev, out [B,oH,oW,C] dev.
+ */
+int ofs_grid_sample_affine(const float* im, const float* theta, float* out, int B, int H, int W, int C, int oH,
+                           int oW, ofs_stream stream);
+int ofs_grid_sample_projective(const float* im, const float* theta, float* out, int B, int H, int W, int C, int oH,
+                               int oW, ofs_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Lie-algebra homography / affine warp (warp.py).
+ * ofs_vec2mtrx replaces vec2mtrx(config, p) (warp.py:25-43): warp_type 0 = "homography"
+ * (p [B,8]), 1 = "affine" (p [B,6]); pMtrx [B,3,3] = sum_{i<warp_approx} A^i / i!.
+ * ofs_lie_warp replaces transformImage (warp.py:46-86; srcH==outH, srcW==outW) and
+ * transformCropImage (warp.py:89-129; source dataH x dataW, output height x W):
+ *   image [B,srcH,srcW,3] dev, pMtrx [B,3,3] dev, refMtrx [3,3] dev, out [B,outH,outW,3] dev.
+ */
+int ofs_vec2mtrx(const float* p, float* pMtrx, int B, int warp_type, int warp_approx, ofs_stream stream);
+int ofs_lie_warp(const float* image, const float* pMtrx, const float* refMtrx, float* out, int B, int srcH,
+                 int srcW, int outH, int outW, ofs_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * FlowNetS-pyramid.  Replaces flownetS_pyramid(feats, batch_size, is_train=False)
+ * (model.py:786-893) evaluated under sess.run (main_dl.py:569).
+ */
+typedef struct ofs_net ofs_net;
+
+/* one named float32 host array of a TensorLayer npz checkpoint (main_dl.py:520) */
+typedef struct ofs_named_array {
+  const char* name;  /* e.g. "main_net/flownetS/3_1/W_conv2d:0"; scope prefix and ":0" optional */
+  const float* data; /* host, C-contiguous, TF layout ([kh,kw,cin,cout] conv, [4,4,cout,cin] deconv) */
+  int64_t numel;
+} ofs_named_array;
+
+/* Allocates every device buffer for batches up to max_batch (no allocation afterwards). */
+int ofs_net_create(ofs_net** net, int device, int max_batch, int precision /* ofs_precision */);
+int ofs_net_destroy(ofs_net* net);
+/* BN fold (W' = W/sqrt(var+1e-5), b' = (b-mu)/sqrt(var+1e-5)+beta), 16-bit conversion and
+ * GEMM-K-major packing; copies to the device.  Missing BN statistics default to the
+ * TensorLayer initial values (mu 0, var 1, beta 0); a missing weight is OFS_EINVAL. */
+int ofs_net_load_weights(ofs_net* net, const ofs_named_array* arrays, int n);
+/* feats [B,384,512,27] dev -> the 5 flow maps of the returned dict (model.py:893), dev:
+ * f6 [B,6,8,2] f5 [B,12,16,2] f4 [B,24,32,2] f3 [B,48,64,2] f2 [B,382,510,2]; any may be NULL. */
+int ofs_net_forward(ofs_net* net, const float* feats, int B, float* f6, float* f5, float* f4, float* f3, float* f2,
+                    ofs_stream stream);
+/* The whole sess.run(outputs_warpedimg) of main_dl.py:569: forward + flow glue + warp.
+ * feats [B,384,512,27] dev, frames [B,H,W,3] dev -> out [B,H,W,3] dev.  flow2_out
+ * ([B,382,510,2] dev) may be NULL. */
+int ofs_net_stabilize(ofs_net* net, const float* feats, const float* frames, float* out, float* flow2_out, int B,
+                      int H, int W, ofs_stream stream);
+/* Same call on HOST buffers: H2D of feats+frames, compute, D2H of out, synchronous on return.
+ * (This is the boundary the reference's feed_dict / fetch crosses, main_dl.py:568-569.) */
+int ofs_net_stabilize_host(ofs_net* net, const float* feats_host, const float* frames_host, float* out_host, int B,
+                           int H, int W);
+/* Debug / parity: copy a named activation, widened to float32, into out (dev, capacity in
+ * elements).  shape4 receives [B,H,W,C].  Names: conv1 conv2 conv3 conv3_1 conv4 conv4_1 conv5
+ * conv5_1 conv6 conv6_1 concat5 concat4 concat3 concat2 (logical channels only). */
+int ofs_net_get_activation(ofs_net* net, const char* name, int B, float* out, int64_t capacity, int* shape4,
+                           ofs_stream stream);
+/* per-forward kernel launches (constant for a given B) */
+int ofs_net_launches_per_forward(const ofs_net* net);
+/* device-side time of the last forward's layers is not tracked here; use CUDA events. */
+
+/* ------------------------------------------------------------------------------------------
+ * Stand-alone implicit-GEMM convolution on the same tcgen05 kernel the network uses (unit
+ * tests, micro-benchmarks):  y = act(conv2d(zero_pad(x, k/2), W, stride) + b), NHWC.
+ *   x [B,H,W,Cin] dev f32, w host [k,k,Cin,Cout] f32, b host [Cout] f32 (may be NULL),
+ *   y [B,Ho,Wo,Cout] dev f32, Ho = (H + 2(k/2) - k)/stride + 1.  stride in {1,2}; stride 2
+ *   needs even H, W.  transposed != 0: k must be 4, stride 2, w host [4,4,Cout,Cin] (TF
+ *   conv2d_transpose SAME), y [B,2H,2W,Cout].  lrelu != 0 applies max(v, 0.1 v).
+ * Operands are rounded to `precision` exactly as in the network.  Synchronous.
+ */
+int ofs_conv2d_nhwc(const float* x, const float* w_host, const float* b_host, float* y, int B, int H, int W, int Cin,
+                    int Cout, int k, int stride, int transposed, int lrelu, int precision, ofs_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFSTAB_H_ */

@@ -1,0 +1,124 @@
+"""numpy emulation of conv_gemm.cu's index algebra (test helper, CPU only).
+
+Mirrors the device code path by path -- tile decode, per-tap TMA box coordinates over the 5-D
+activation view with out-of-bounds zero fill, the 128x64 A tile row order, K-block order of the
+packed weights, epilogue row -> output pixel mapping -- using the plan the library itself
+exports through ofs_debug_conv_plan.  What it cannot cover is the hardware side (swizzle, UMMA
+descriptors, barriers): that is the GPU tests' job.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+INFO_KEYS = ["Hg", "Wg", "rows_total", "tileW_log2", "tileH", "rpl", "tiles_x", "tiles_m", "tiles_n", "phases",
+             "ntaps", "nchunks", "n_pad", "k_total", "w_rows", "paired", "out_scale", "out_H", "out_W", "grid",
+             "d0", "d1", "d2", "d3", "d4", "s1", "s2", "s3", "s4", "oy0", "oy1", "oy2", "oy3", "ox0", "ox1", "ox2",
+             "ox3", "smem"]
+
+
+def bf16_round(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def bf16_bits_to_f32(u16):
+    return (u16.astype(np.uint32) << 16).view(np.float32)
+
+
+def get_plan(lib, kind, B, H, W, cin, in_cs, cout, k, stride, block_n, w_tf=None, bias=None):
+    info = (C.c_int * 40)()
+    taps = (C.c_short * 256)()
+    cap = 0
+    wbuf = None
+    bbuf = None
+    if w_tf is not None:
+        cap = 4 * (cout + 256) * (k * k * (cin + 64) + 4096)
+        wbuf = np.zeros(cap, np.uint16)
+        bbuf = np.zeros(cout + 256, np.float32)
+        w_tf = np.ascontiguousarray(w_tf, np.float32)
+        if bias is not None:
+            bias = np.ascontiguousarray(bias, np.float32)
+    rc = lib.ofs_debug_conv_plan(kind, B, H, W, cin, in_cs, cout, k, stride, block_n, 1,
+                                 None if w_tf is None else w_tf.ctypes.data_as(C.c_void_p),
+                                 None if bias is None else bias.ctypes.data_as(C.c_void_p),
+                                 C.cast(info, C.c_void_p), C.cast(taps, C.c_void_p),
+                                 None if wbuf is None else wbuf.ctypes.data_as(C.c_void_p), cap,
+                                 None if bbuf is None else bbuf.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError(lib.ofs_last_error().decode())
+    d = {k_: int(info[i]) for i, k_ in enumerate(INFO_KEYS)}
+    t = np.array(list(taps), np.int64).reshape(4, 64)
+    d["tap_c"], d["tap_x"], d["tap_p"], d["tap_y"] = t[0], t[1], t[2], t[3]
+    if wbuf is not None:
+        d["w"] = bf16_bits_to_f32(wbuf[: d["w_rows"] * d["k_total"]]).reshape(d["w_rows"], d["k_total"])
+        d["b"] = bbuf[: d["n_pad"]].copy()
+    d["block_n"] = block_n
+    return d
+
+
+def tma_box(flat, plan, c, x, pp, y, b, tileW):
+    """Box {64, tileW, 1, rpl, 1} of the 5-D view at signed start coords; OOB elements are zero."""
+    dims = [plan["d0"], plan["d1"], plan["d2"], plan["d3"], plan["d4"]]
+    strides = [1, plan["s1"], plan["s2"], plan["s3"], plan["s4"]]
+    rpl = plan["rpl"]
+    out = np.zeros((rpl, tileW, 64), np.float32)
+    if not (0 <= pp < dims[2] and 0 <= b < dims[4]):
+        return out.reshape(rpl * tileW, 64)
+    ci = c + np.arange(64)
+    xi = x + np.arange(tileW)
+    yi = y + np.arange(rpl)
+    cm = (ci >= 0) & (ci < dims[0])
+    xm = (xi >= 0) & (xi < dims[1])
+    ym = (yi >= 0) & (yi < dims[3])
+    off = (yi[:, None, None] * strides[3] + xi[None, :, None] * strides[1] + ci[None, None, :] * strides[0]
+           + pp * strides[2] + b * strides[4])
+    mask = ym[:, None, None] & xm[None, :, None] & cm[None, None, :]
+    out[mask] = flat[off[mask]]
+    return out.reshape(rpl * tileW, 64)
+
+
+def emulate(plan, act):
+    """act: float32 [B,H,W,in_cs] (already rounded to the 16-bit format).  Returns fp32
+    [B,out_H,out_W,n_pad] = GEMM result + bias, exactly as the epilogue would scatter it."""
+    flat = np.ascontiguousarray(act, np.float32).reshape(-1)
+    tileW = 1 << plan["tileW_log2"]
+    tileH, rpl, Hg = plan["tileH"], plan["rpl"], plan["Hg"]
+    B = act.shape[0]
+    out = np.full((B, plan["out_H"], plan["out_W"], plan["n_pad"]), np.nan, np.float32)
+    num_kb = plan["ntaps"] * plan["nchunks"]
+    BN = plan["block_n"]
+    total = plan["tiles_m"] * plan["tiles_n"] * plan["phases"]
+    oys = [plan["oy0"], plan["oy1"], plan["oy2"], plan["oy3"]]
+    oxs = [plan["ox0"], plan["ox1"], plan["ox2"], plan["ox3"]]
+    for tile in range(total):
+        n_t = tile % plan["tiles_n"]
+        rest = tile // plan["tiles_n"]
+        m_t = rest % plan["tiles_m"]
+        ph = rest // plan["tiles_m"]
+        gy0 = (m_t // plan["tiles_x"]) * tileH
+        ox0 = (m_t % plan["tiles_x"]) << plan["tileW_log2"]
+        w_row = ph * plan["n_pad"] + n_t * BN
+        acc = np.zeros((128, BN), np.float64)
+        for kb in range(num_kb):
+            tap, ch = divmod(kb, plan["nchunks"])
+            ti = ph * plan["ntaps"] + tap
+            A = np.zeros((128, 64), np.float32)
+            for pc in range(tileH // rpl):
+                gy = gy0 + pc * rpl
+                b = gy // Hg
+                y = gy - b * Hg + plan["tap_y"][ti]
+                A[pc * rpl * tileW:(pc + 1) * rpl * tileW] = tma_box(
+                    flat, plan, plan["tap_c"][ti] + ch * 64, ox0 + plan["tap_x"][ti], plan["tap_p"][ti], y, b, tileW)
+            Wt = plan["w"][w_row:w_row + BN, kb * 64:(kb + 1) * 64]
+            acc += A.astype(np.float64) @ Wt.astype(np.float64).T
+        for row in range(128):
+            gy = gy0 + (row >> plan["tileW_log2"])
+            gx = ox0 + (row & (tileW - 1))
+            if gy >= plan["rows_total"]:
+                continue
+            b = gy // Hg
+            y = gy - b * Hg
+            oy = y * plan["out_scale"] + oys[ph]
+            ox = gx * plan["out_scale"] + oxs[ph]
+            out[b, oy, ox, n_t * BN:(n_t + 1) * BN] = acc[row] + plan["b"][n_t * BN:(n_t + 1) * BN]
+    return out

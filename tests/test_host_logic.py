@@ -1,0 +1,148 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, the
+16-bit conversions, and the conv plan (tap tables, TMA view, tiling, weight packing) emulated in
+numpy against the oracle convolution.  No compute call reaches a GPU here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import emu
+from oracle import tf1_ops as T
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from coupe.optical_flow_based_deep_video_stabilization_b200 import _lib
+
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from coupe.optical_flow_based_deep_video_stabilization_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "ofstab.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(ofs_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ofstab.h but not exported"
+    assert declared == set(_lib.PROTOTYPES), "ctypes prototype table and header disagree"
+    assert lib.ofs_version() == 100
+
+
+def test_no_cpu_fallback_without_gpu(lib):
+    import coupe.optical_flow_based_deep_video_stabilization_b200 as ofs
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert lib.ofs_device_check(0) != 0
+    assert b"no CPU fallback" in lib.ofs_last_error() or b"sm_" in lib.ofs_last_error()
+    with pytest.raises(RuntimeError):
+        ofs.tf_warp(torch.zeros(1, 4, 4, 3), torch.zeros(1, 4, 4, 2), 4, 4)
+    with pytest.raises(RuntimeError):
+        ofs.FlowNetSPyramid()
+    with pytest.raises(RuntimeError):
+        ofs.AffineTransformer((4, 4)).transform(torch.zeros(1, 4, 4, 3), torch.zeros(1, 6))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "coupe")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports oracle/"
+
+
+def test_cvt16_matches_torch(lib):
+    rng = np.random.RandomState(0)
+    vals = np.concatenate([rng.randn(2000).astype(np.float32) * s for s in (1e-8, 1e-5, 1e-3, 1.0, 300.0, 7e4)])
+    vals = np.concatenate([vals, np.array([0.0, -0.0, 65504.0, 65519.9, 65520.0, 1e9, -1e9, 6.1e-5, 5.96e-8, 2.98e-8,
+                                           2.9802322e-8, 8.9e-8, np.inf, -np.inf], np.float32)])
+    tv = torch.from_numpy(vals)
+    exp_bf = tv.to(torch.bfloat16).view(torch.int16).numpy().astype(np.uint16)
+    exp_fp = tv.to(torch.float16).view(torch.int16).numpy().astype(np.uint16)
+    got_bf = np.array([lib.ofs_debug_cvt16(float(v), 1) for v in vals], np.uint16)
+    got_fp = np.array([lib.ofs_debug_cvt16(float(v), 0) for v in vals], np.uint16)
+    np.testing.assert_array_equal(got_bf, exp_bf)
+    np.testing.assert_array_equal(got_fp, exp_fp)
+
+
+# kind, B, H, W, cin, in_cs, cout, k, stride, block_n
+CONV_CASES = [
+    pytest.param(0, 2, 6, 8, 70, 72, 16, 3, 1, 16, id="k3s1_ragged_channels_tile_spans_images"),
+    pytest.param(0, 3, 6, 8, 64, 64, 32, 3, 1, 32, id="k3s1_ragged_batch"),
+    pytest.param(0, 1, 12, 16, 64, 72, 32, 3, 2, 32, id="k3s2_slice_of_wider_buffer"),
+    pytest.param(0, 2, 16, 32, 64, 64, 16, 5, 2, 16, id="k5s2"),
+    pytest.param(0, 1, 16, 32, 27, 32, 64, 7, 2, 64, id="k7s2_paired_conv1_form"),
+    pytest.param(0, 1, 12, 16, 20, 32, 16, 3, 2, 16, id="k3s2_paired"),
+    pytest.param(1, 2, 6, 8, 70, 72, 32, 4, 2, 32, id="deconv_k4s2"),
+    pytest.param(1, 1, 12, 16, 130, 136, 64, 4, 2, 64, id="deconv_k4s2_3chunks"),
+    pytest.param(0, 1, 8, 16, 194, 200, 18, 1, 1, 32, id="k1s1_predict2_product"),
+    pytest.param(0, 1, 4, 256, 64, 64, 16, 3, 1, 16, id="wide_rows_two_tiles_per_row"),
+]
+
+
+@pytest.mark.parametrize("kind,B,H,W,cin,in_cs,cout,k,stride,bn", CONV_CASES)
+def test_conv_plan_emulation_matches_oracle(lib, kind, B, H, W, cin, in_cs, cout, k, stride, bn):
+    rng = np.random.RandomState(1234 + k * 7 + stride)
+    x = emu.bf16_round(rng.rand(B, H, W, cin).astype(np.float32))
+    if kind == 0:
+        w = emu.bf16_round(rng.randn(k, k, cin, cout).astype(np.float32) * 0.1)
+    else:
+        w = emu.bf16_round(rng.randn(4, 4, cout, cin).astype(np.float32) * 0.1)
+    b = rng.randn(cout).astype(np.float32)
+    plan = emu.get_plan(lib, kind, B, H, W, cin, in_cs, cout, k, stride, bn, w, b)
+    act = np.zeros((B, H, W, in_cs), np.float32)
+    act[..., :cin] = x
+    act[..., cin:] = 7.0  # other layers' channels in the same buffer must never leak into this GEMM
+    got = emu.emulate(plan, act)[..., :cout]
+    xt, wt, bt = torch.from_numpy(x).double(), torch.from_numpy(w).double(), torch.from_numpy(b).double()
+    if kind == 0:
+        ref = T.conv2d_valid(T.pad_constant(xt, k // 2), wt, bt, stride)
+    else:
+        ref = T.conv2d_transpose_k4s2_same(xt, wt, bt)
+    assert got.shape == tuple(ref.shape)
+    assert not np.isnan(got).any(), "some output pixel was never written"
+    np.testing.assert_allclose(got, ref.numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_network_layer_plans_are_valid(lib):
+    """Geometry of all 19 GEMM layers at B=8: tiles cover the grid, K is whole 64-blocks, smem fits."""
+    layers = [  # kind,H,W,cin,in_cs,cout,k,stride,bn
+        (0, 384, 512, 27, 32, 64, 7, 2, 64), (0, 192, 256, 64, 64, 128, 5, 2, 128), (0, 96, 128, 128, 200, 256, 5, 2, 128),
+        (0, 48, 64, 256, 256, 256, 3, 1, 128), (0, 48, 64, 256, 392, 512, 3, 2, 128), (0, 24, 32, 512, 512, 512, 3, 1, 128),
+        (0, 24, 32, 512, 776, 512, 3, 2, 128), (0, 12, 16, 512, 512, 512, 3, 1, 128), (0, 12, 16, 512, 1032, 1024, 3, 2, 128),
+        (0, 6, 8, 1024, 1024, 1024, 3, 1, 128), (0, 6, 8, 1024, 1024, 2, 3, 1, 16), (1, 6, 8, 1024, 1024, 512, 4, 2, 128),
+        (0, 12, 16, 1026, 1032, 2, 3, 1, 16), (1, 12, 16, 1026, 1032, 256, 4, 2, 128), (0, 24, 32, 770, 776, 2, 3, 1, 16),
+        (1, 24, 32, 770, 776, 128, 4, 2, 128), (0, 48, 64, 386, 392, 2, 3, 1, 16), (1, 48, 64, 386, 392, 64, 4, 2, 64),
+        (0, 96, 128, 194, 200, 18, 1, 1, 32)]
+    for B in (1, 8):
+        for (kind, H, W, cin, in_cs, cout, k, s, bn) in layers:
+            p = emu.get_plan(lib, kind, B, H, W, cin, in_cs, cout, k, s, bn)
+            tileW = 1 << p["tileW_log2"]
+            assert tileW * p["tileH"] == 128 and p["tileH"] % p["rpl"] == 0 and p["Hg"] % p["rpl"] == 0
+            assert (p["rpl"] * tileW) % 8 == 0, "TMA piece must be whole 1024-byte swizzle atoms"
+            assert p["tiles_m"] * 128 >= B * p["Hg"] * p["Wg"]
+            assert p["k_total"] == p["ntaps"] * p["nchunks"] * 64 and p["nchunks"] * 64 >= (cin if not p["paired"] else 64)
+            assert p["smem"] <= 227 * 1024 and 1 <= p["grid"] <= 148 or p["grid"] >= 1
+            assert p["w_rows"] == p["phases"] * p["n_pad"] and p["n_pad"] % bn == 0
+
+
+def test_plan_rejects_unsupported_shapes(lib):
+    info, taps = (C.c_int * 40)(), (C.c_short * 256)()
+
+    def rc(*a):
+        return lib.ofs_debug_conv_plan(*a, 1, None, None, C.cast(info, C.c_void_p), C.cast(taps, C.c_void_p), None, 0, None)
+
+    assert rc(0, 1, 7, 9, 64, 64, 16, 3, 2, 16) != 0     # odd H/W with stride 2
+    assert rc(0, 1, 8, 12, 64, 64, 16, 3, 1, 16) != 0    # grid width 12 is not a multiple of a power of two >= 8
+    assert rc(0, 1, 8, 16, 64, 60, 16, 3, 1, 16) != 0    # channel stride not a multiple of 8
+    assert rc(0, 1, 8, 16, 64, 64, 16, 3, 1, 48) != 0    # block_n
+    assert rc(1, 1, 8, 16, 64, 64, 16, 3, 2, 16) != 0    # transposed conv must be k4 s2
+    assert b"k=4" in lib.ofs_last_error()
