@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- frame-pairs/sec of the stabiliser hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic frame pairs: BASELINE.json configs[1]
+= FlowNetS-pyramid forward + test-mode flow glue + dense warp (the sess.run of
+main_flownetS_pyramid_noprevloss_dataloader.py:569) on 8 independent 720p frame pairs, bf16 operands,
+random-init weights, synthetic frames.  Rank 0 prints ONE JSON line (see the keys below).
+
+    value        whole-job pairs/s, inputs resident in HBM, CUDA-event timed, max over ranks
+    e2e          same metric through the C-ABI host-buffer call (ofs_net_stabilize_host): pinned host
+                 inputs, H2D + compute + D2H inside the timed region
+    roofline     dominant kernel (tcgen05 implicit-GEMM conv): algorithmic FLOPs of the 14 dense layers /
+                 their summed launch time, measured live with CUDA events, vs MEASURED_PEAKS.json
+    roofline_warp  the HBM-bound fused flow-resize + warp kernel
+    cpu_baseline the CPU oracle (a port of the reference arithmetic; TensorFlow 1.10 is not installable)
+                 timed on this box's host cores on a bounded sample
+    --impl reference  times that CPU port alone, on all host threads, same metric / config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "frame-pairs/sec (FlowNetS fwd+warp) @720p"
+UNIT = "pairs/s"
+BATCH, FRAME_H, FRAME_W = 8, 720, 1280
+DENSE_GFLOP_PER_PAIR = 37.89      # 10 encoder convs + 4 transposed convs, literal MACs x 2
+WARP_BYTES_PER_PX = 24.0          # fused flow-resize+warp: image 12 + out 12 (+1.56 MB of flow2 per frame)
+FLOW2_BYTES = 382 * 510 * 2 * 4
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "power_w_max": max(float(s[2]) for s in self.samples), "reasons": reasons, "samples": len(self.samples)}
+
+
+def synth_inputs(torch, seed, batch, h, w, device=None, pinned=False):
+    from oracle import flownet as F  # deterministic generators only (no oracle arithmetic on this path)
+
+    g = torch.Generator().manual_seed(seed)
+    feats = F.make_feats(seed, batch)
+    frames = torch.rand((batch, h, w, 3), generator=g)
+    if device is not None:
+        return feats.to(device), frames.to(device)
+    if pinned:
+        return feats.pin_memory(), frames.pin_memory()
+    return feats, frames
+
+
+def cpu_oracle_rate(torch, n_pairs, h, w, threads):
+    """pairs/s of the CPU port (oracle) of the same step: forward_literal + flow glue + tf_warp."""
+    from oracle import flownet as F
+    from oracle import samplers as S
+
+    torch.set_num_threads(threads)
+    wts = F.make_weights(0, "calibrated", head_scale=0.02)
+    feats, frames = synth_inputs(torch, 7, 1, h, w)
+    out = F.forward_literal(feats, wts)                       # warm-up
+    S.flow_resize_warp(frames, out["predict_flow2"], h, w)
+    t0 = time.perf_counter()
+    for _ in range(n_pairs):
+        out = F.forward_literal(feats, wts)
+        S.flow_resize_warp(frames, out["predict_flow2"], h, w)
+    dt = time.perf_counter() - t0
+    return n_pairs / dt, dt
+
+
+def run_reference(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    pairs_per_step = 2                                        # bounded sample of the 8-pair step
+    rate_w, _ = cpu_oracle_rate(torch, 1, FRAME_H, FRAME_W, threads)
+    del rate_w
+    from oracle import flownet as F
+    from oracle import samplers as S
+
+    wts = F.make_weights(0, "calibrated", head_scale=0.02)
+    feats, frames = synth_inputs(torch, 7, 1, FRAME_H, FRAME_W)
+
+    def step():
+        for _ in range(pairs_per_step):
+            o = F.forward_literal(feats, wts)
+            S.flow_resize_warp(frames, o["predict_flow2"], FRAME_H, FRAME_W)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = pairs_per_step * args.steps / dt
+    sample = f"{pairs_per_step} of the {BATCH} 720p pairs per step, batch 1 each, fp32, {threads} torch threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(), "pairs_per_step_timed": pairs_per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference = CPU port (oracle/) of the TF-1.10 graph; TensorFlow/TensorLayer cannot be installed offline",
+    }), flush=True)
+
+
+def workload_name():
+    return (f"BASELINE configs[1]: FlowNetS-pyramid fwd (384x512x27) + flow glue + tf_warp at {FRAME_H}x{FRAME_W}, "
+            f"batch {BATCH} independent frame pairs per GPU, random-init weights")
+
+
+def run_ours(args):
+    import torch
+
+    import coupe.optical_flow_based_deep_video_stabilization_b200 as ofs
+    from oracle import flownet as F  # weight / input generators only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = ofs.load_library()
+    peaks = load_peaks()
+
+    net = ofs.FlowNetSPyramid(device=dev, max_batch=BATCH, precision=args.precision)
+    net.assign_weights(F.make_weights(0, "calibrated", head_scale=0.02))
+    # two input sets alternate so no step re-reads what the previous one left in the 126 MB L2
+    sets = [synth_inputs(torch, 100 + rank * 2 + i, BATCH, FRAME_H, FRAME_W, device=dev) for i in range(2)]
+    outs = [torch.empty_like(sets[0][1]) for _ in range(2)]
+
+    def step(i):
+        feats, frames = sets[i & 1]
+        ofs._lib.check(lib.ofs_net_stabilize(net._h, ofs._lib.ptr(feats), ofs._lib.ptr(frames), ofs._lib.ptr(outs[i & 1]),
+                                             None, BATCH, FRAME_H, FRAME_W, ofs._lib.current_stream_ptr(dev)))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = lib.ofs_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    launches = int(lib.ofs_launch_count() - l0)
+    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist is not None:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_total = float(ms_total.item())
+    value = world * BATCH * args.steps / (ms_total * 1e-3)
+
+    # ---- per-kernel breakdown, measured live with CUDA events on the launching stream (rank 0)
+    roofline = roofline_warp = breakdown = None
+    if rank == 0:
+        prof = net.profile(sets[0][0], sets[0][1], iters=max(3, min(args.steps, 10)))
+        dense = [(n, ms, m) for (n, ms, m) in prof if n.startswith("gemm:") and not n.startswith("gemm:predict")]
+        gemm_ms = sum(ms for _, ms, _ in dense)
+        flops = 2.0 * sum(m for _, _, m in dense)
+        step_ms = sum(ms for _, ms, _ in prof)
+        ach = flops / (gemm_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                    "kernel": "conv_gemm_kernel<BLOCK_N> (14 dense conv/deconv layers of one step)",
+                    "launches_per_step": len(dense), "ms_per_step_in_kernel": gemm_ms, "share_of_step": gemm_ms / step_ms,
+                    "algorithmic_gflop_per_launch_set": flops / 1e9, "peak_source": peaks["source"] + " (sustained bf16)",
+                    "frac_of_burst_peak": ach / peaks["bf16_tflops"], "frac_of_nominal_2250": ach / 2250.0}
+        wms = [ms for n, ms, _ in prof if n == "flow_resize_warp"][0]
+        wbytes = BATCH * (FRAME_H * FRAME_W * WARP_BYTES_PER_PX + FLOW2_BYTES)
+        wach = wbytes / (wms * 1e-3) / 1e9
+        roofline_warp = {"bound": "hbm", "achieved": wach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": wach / peaks["hbm_gbs"], "traffic": None, "kernel": "warp_staged3_kernel (fused flow-resize + tf_warp)",
+                         "ms_per_launch": wms, "algorithmic_bytes_per_launch": wbytes, "frac_of_nominal_7700": wach / 7700.0,
+                         "peak_source": peaks["source"]}
+        breakdown = [{"kernel": n, "ms": round(ms, 4), "tflops": (2 * m / (ms * 1e-3) / 1e12 if m else None)} for n, ms, m in prof]
+
+    # ---- e2e: the C-ABI host-buffer call, pinned host inputs, H2D + compute + D2H every step
+    hf, hfr = synth_inputs(torch, 300 + rank, BATCH, FRAME_H, FRAME_W, pinned=True)
+    hout = torch.empty_like(hfr).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        net.stabilize_host(hf, hfr, hout)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        net.stabilize_host(hf, hfr, hout)
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if dist is not None:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * BATCH * e2e_steps / float(dt.item())
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            n_pairs = 4
+            rate, secs = cpu_oracle_rate(torch, n_pairs, FRAME_H, FRAME_W, threads)
+            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{n_pairs} 720p frame pairs (batch 1 each) of the same step, fp32 torch-CPU oracle, {secs:.1f} s"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": workload_name(), "pairs_per_step_per_gpu": BATCH, "frame": [FRAME_H, FRAME_W],
+                       "net_input": [384, 512, 27], "l2": "two alternating input sets, 258 MB each (> 126 MB L2)",
+                       "parallelism": f"replicas x{world}, no data-path collective"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hf.numel() * 4 + hfr.numel() * 4),
+                    "d2h_bytes_per_step": int(hout.numel() * 4), "steps": e2e_steps,
+                    "api": "ofs_net_stabilize_host (C ABI, pinned host float32 buffers)"},
+            "gpu_launches": launches, "launches_per_step": launches // max(args.steps, 1),
+            "clocks": clocks, "roofline": roofline, "roofline_warp": roofline_warp, "cpu_baseline": cpu,
+            "breakdown": breakdown, "lib": os.path.relpath(ofs.lib_path(), ROOT),
+        }
+        print(json.dumps(line), flush=True)
+    net.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--precision", choices=["bf16", "fp16"], default="bf16")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

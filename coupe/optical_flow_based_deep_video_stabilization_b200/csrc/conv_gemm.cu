@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_kb = p.ntaps * p.nchunks;
-  const int total_tiles = p.tiles_m * p.tiles_n * p.phases;
+  const int total_tiles = p.tiles_m * p.tiles_n * p.phases * p.ksplit;
   const int tileW = 1 << p.tileW_log2;
 
   if (warp == 0) {
@@ -104,29 +104,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       // ================================ TMA producer ================================
       int stage = 0;
       uint32_t phase = 0;
-      const int npieces = p.tileH / p.rpl;
-      const int piece_bytes = p.rpl * tileW * kBlockK * 2;
+      const int npieces = p.npieces;
+      const int piece_bytes = p.piece_rows * tileW * kBlockK * 2;
+      const uint32_t stage_tx = (uint32_t)(p.a_bytes + Cfg::kBBytes);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_t = tile % p.tiles_n;
         const int rest = tile / p.tiles_n;
         const int m_t = rest % p.tiles_m;
-        const int ph = rest / p.tiles_m;
-        const int gy0 = (m_t / p.tiles_x) * p.tileH;
+        const int rest2 = rest / p.tiles_m;
+        const int ph = rest2 % p.phases;
+        const int ks = rest2 / p.phases;
+        const int gy0 = (m_t / p.tiles_x) * p.tile_rows;
         const int ox0 = (m_t % p.tiles_x) << p.tileW_log2;
         const int w_row = ph * p.n_pad + n_t * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           const int tap = kb / p.nchunks;
           const int ch = kb - tap * p.nchunks;
           const int ti = ph * p.ntaps + tap;
           ptx::mbar_wait(&empty[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+          ptx::mbar_expect_tx(&full[stage], stage_tx);
           uint8_t* sa = smem + (size_t)stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           const int c = p.tap_c[ti] + ch * kBlockK;
           const int x = ox0 + p.tap_x[ti];
           const int pp = p.tap_p[ti];
           for (int pc = 0; pc < npieces; ++pc) {
-            const int gy = gy0 + pc * p.rpl;
+            const int gy = gy0 + pc * p.piece_rows;
             const int b = gy / p.Hg;
             const int y = gy - b * p.Hg + p.tap_y[ti];
             ptx::tma_load_5d(sa + (size_t)pc * piece_bytes, &p.tmap_a, &full[stage], c, x, pp, y, b);
@@ -148,7 +153,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int ks = tile / (p.tiles_n * p.tiles_m * p.phases);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&full[stage], phase);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(smem + (size_t)stage * Cfg::kStageBytes);
@@ -157,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           for (int k = 0; k < kBlockK / 16; ++k) {
             const uint64_t da = ptx::umma_desc_sw128(a_addr + k * 32);
             const uint64_t db = ptx::umma_desc_sw128(b_addr + k * 32);
-            ptx::tc_mma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::tc_mma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           ptx::tc_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -177,10 +185,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       const int n_t = tile % p.tiles_n;
       const int rest = tile / p.tiles_n;
       const int m_t = rest % p.tiles_m;
-      const int ph = rest / p.tiles_m;
-      const int gy = (m_t / p.tiles_x) * p.tileH + (row >> p.tileW_log2);
+      const int rest2 = rest / p.tiles_m;
+      const int ph = rest2 % p.phases;
+      const int ks = rest2 / p.phases;
+      const int ty = row >> p.tileW_log2;
+      const int gy = (m_t / p.tiles_x) * p.tile_rows + ty;
       const int gx = ((m_t % p.tiles_x) << p.tileW_log2) + (row & (tileW - 1));
-      const bool valid = gy < p.rows_total;
+      const bool valid = (ty < p.tile_rows) && (gy < p.rows_total);
       const int b = gy / p.Hg;
       const int y = gy - b * p.Hg;
       const int oy = y * p.out_scale + p.out_oy[ph];
@@ -212,6 +223,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             uint4* o4 = reinterpret_cast<uint4*>(o);
 #pragma unroll
             for (int j = 0; j < kChunk / 8; ++j) o4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          } else if (p.out_mode == 2) {
+            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)ks * p.ws_split_stride +
+                                                   pix * p.n_pad + n0 + c0);
+#pragma unroll
+            for (int j = 0; j < kChunk / 4; ++j)
+              o4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                  __uint_as_float(v[4 * j + 3]));
           } else {
             float* o = reinterpret_cast<float*>(p.out) + pix * p.out_cstride + p.out_coff;
 #pragma unroll
@@ -274,6 +292,34 @@ __global__ void unpack_act_kernel(const uint16_t* __restrict__ in, float* __rest
   }
 }
 
+// split-K: sum the fp32 partials of all splits, + bias, lrelu, 16-bit pack, store into the destination slice
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int ksplit, long long split_stride, size_t npix,
+                                     int n_pad, const float* __restrict__ bias, uint16_t* __restrict__ out,
+                                     int out_cstride, int out_coff, int lrelu, int is_bf16) {
+  const int groups = n_pad >> 3;
+  const size_t total = npix * groups;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = i / groups;
+    const int c0 = (int)(i - pix * groups) << 3;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(bias + c0 + j);
+    for (int s = 0; s < ksplit; ++s) {
+      const float4* src = reinterpret_cast<const float4*>(ws + (size_t)s * split_stride + pix * n_pad + c0);
+      const float4 a = __ldg(src), b = __ldg(src + 1);
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+      v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (lrelu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + pix * out_cstride + out_coff + c0);
+    *o = make_uint4(pack16(v[0], v[1], is_bf16), pack16(v[2], v[3], is_bf16), pack16(v[4], v[5], is_bf16),
+                    pack16(v[6], v[7], is_bf16));
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -322,6 +368,16 @@ int launch_t(const ConvPlan& plan, cudaStream_t st) {
   }
   conv_gemm_kernel<BLOCK_N><<<plan.grid, kThreads, GemmCfg<BLOCK_N>::kSmem, st>>>(plan.p);
   OFS_LAUNCH_CHECK();
+  if (plan.p.ksplit > 1) {
+    const ConvGemmParams& p = plan.p;
+    const size_t npix = (size_t)plan.d.B * p.out_H * p.out_W;
+    const size_t total = npix * (p.n_pad / 8);
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
+    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(plan.ws, p.ksplit, p.ws_split_stride, npix, p.n_pad, plan.bias_dev,
+                                                 reinterpret_cast<uint16_t*>(plan.final_out), plan.d.out_cstride,
+                                                 plan.d.out_coff, plan.d.lrelu, plan.d.is_bf16);
+    OFS_LAUNCH_CHECK();
+  }
   return OFS_OK;
 }
 
@@ -412,11 +468,21 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
   int tileW = 1 << ilog2(std::min(Wg, 128));
   OFS_REQUIRE(tileW >= 8 && Wg % tileW == 0, "conv plan: output grid width %d must be a multiple of a power of two >= 8", Wg);
   const int tileH = kBlockM / tileW;
-  const int rpl = gcd(tileH, Hg);
   p.Hg = Hg; p.Wg = Wg; p.rows_total = d.B * Hg;
-  p.tileW_log2 = ilog2(tileW); p.tileH = tileH; p.rpl = rpl;
+  p.tileW_log2 = ilog2(tileW);
+  if (tileW == Wg && Hg <= tileH) {
+    // small grid (e.g. 6x8): a tile is a whole number of images, fetched by ONE TMA box over (y, b);
+    // GEMM rows past tile_rows * tileW are never stored
+    p.box_y = Hg; p.box_b = tileH / Hg; p.npieces = 1;
+    p.piece_rows = p.box_y * p.box_b; p.tile_rows = p.piece_rows;
+  } else {
+    const int rpl = gcd(tileH, Hg);
+    p.box_y = rpl; p.box_b = 1; p.npieces = tileH / rpl;
+    p.piece_rows = rpl; p.tile_rows = tileH;
+  }
+  p.a_bytes = p.npieces * p.piece_rows * tileW * kBlockK * 2;
   p.tiles_x = Wg / tileW;
-  p.tiles_m = p.tiles_x * ((p.rows_total + tileH - 1) / tileH);
+  p.tiles_m = p.tiles_x * ((p.rows_total + p.tile_rows - 1) / p.tile_rows);
   // K structure + tap table
   plan.paired = (!deconv && d.stride == 2 && d.in_cs == 32);
   if (deconv) {
@@ -492,7 +558,17 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
   }
   plan.k_total = p.ntaps * p.nchunks * kBlockK;
   plan.w_rows = p.phases * p.n_pad;
-  const int total_tiles = p.tiles_m * p.tiles_n * p.phases;
+  {
+    const int num_kb = p.ntaps * p.nchunks;
+    int ks = std::max(1, std::min(d.ksplit, num_kb));
+    OFS_REQUIRE(ks == 1 || d.out_mode == 0, "split-K is implemented for the 16-bit output mode only");
+    p.kb_per_split = (num_kb + ks - 1) / ks;
+    p.ksplit = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
+    p.ws_split_stride = (long long)d.B * p.out_H * p.out_W * p.n_pad;
+    plan.ws_bytes = p.ksplit > 1 ? (size_t)p.ksplit * p.ws_split_stride * 4 : 0;
+    if (p.ksplit > 1) p.out_mode = 2;
+  }
+  const int total_tiles = p.tiles_m * p.tiles_n * p.phases * p.ksplit;
   plan.grid = std::max(1, std::min(total_tiles, sm_count()));
   switch (d.block_n) {
     case 16: plan.smem = GemmCfg<16>::kSmem; break;
@@ -555,13 +631,22 @@ void conv_pack_weights(const ConvPlan& plan, const float* w, const float* bias, 
   }
 }
 
-int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const float* bias_dev, void* out) {
+int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const float* bias_dev, void* out,
+                   float* workspace) {
   ConvGemmParams& p = plan.p;
   const ConvDesc& d = plan.d;
   OFS_REQUIRE(act_in && w_dev && bias_dev && out, "conv bind: null pointer");
   OFS_REQUIRE(((uintptr_t)act_in) % 16 == 0 && ((uintptr_t)w_dev) % 16 == 0 && ((uintptr_t)out) % 16 == 0,
               "conv bind: pointers must be 16-byte aligned");
-  p.out = out;
+  plan.final_out = out;
+  plan.bias_dev = bias_dev;
+  plan.ws = workspace;
+  if (p.ksplit > 1) {
+    OFS_REQUIRE(workspace && ((uintptr_t)workspace) % 16 == 0, "conv bind: split-K needs a 16-byte aligned workspace");
+    p.out = workspace;
+  } else {
+    p.out = out;
+  }
   p.bias = bias_dev;
   const cuuint32_t tileW = 1u << p.tileW_log2;
   unsigned long long vd[5], vs[4];
@@ -569,7 +654,7 @@ int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const 
   cuuint64_t dims[5], str[4];
   for (int i = 0; i < 5; ++i) dims[i] = vd[i];
   for (int i = 0; i < 4; ++i) str[i] = vs[i];
-  cuuint32_t box[5] = {(cuuint32_t)kBlockK, tileW, 1, (cuuint32_t)p.rpl, 1};
+  cuuint32_t box[5] = {(cuuint32_t)kBlockK, tileW, 1, (cuuint32_t)p.box_y, (cuuint32_t)p.box_b};
   int st = encode_map(&p.tmap_a, d.is_bf16, 5, act_in, dims, str, box);
   if (st != OFS_OK) return st;
   cuuint64_t wd[2] = {(cuuint64_t)plan.k_total, (cuuint64_t)plan.w_rows};
@@ -611,9 +696,9 @@ int launch_unpack_act(const void* in, float* out, size_t npix, int cs, int coff,
 }  // namespace ofs
 
 // ------------------------------------------------------------------------------------------------
-extern "C" int ofs_conv2d_nhwc(const float* x, const float* w_host, const float* b_host, float* y, int B, int H, int W,
-                               int Cin, int Cout, int k, int stride, int transposed, int lrelu, int precision,
-                               ofs_stream stream) {
+extern "C" int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const float* b_host, float* y, int B, int H,
+                                  int W, int Cin, int Cout, int k, int stride, int transposed, int lrelu, int precision,
+                                  int block_n, int ksplit, ofs_stream stream) {
   using namespace ofs;
   cudaStream_t st = (cudaStream_t)stream;
   OFS_REQUIRE(x && w_host && y, "ofs_conv2d_nhwc: null pointer");
@@ -630,9 +715,12 @@ extern "C" int ofs_conv2d_nhwc(const float* x, const float* w_host, const float*
   if (!transposed && stride == 2) d.in_cs = (Cin <= 32 && ((k / 2) & 1)) ? 32 : ((Cin + 63) / 64) * 64; else d.in_cs = ((Cin + 7) / 8) * 8;
   const int cin_logical = d.cin;
   if (!transposed && stride == 2 && d.in_cs != 32) d.cin = d.in_cs;  // zero channels + zero weights
-  d.block_n = Cout >= 128 ? 128 : (Cout >= 64 ? 64 : (Cout >= 32 ? 32 : 16));
-  d.out_mode = 1; d.lrelu = lrelu; d.is_bf16 = is_bf16;
-  d.out_cstride = Cout; d.out_coff = 0;
+  d.block_n = block_n > 0 ? block_n : (Cout >= 128 ? 128 : (Cout >= 64 ? 64 : (Cout >= 32 ? 32 : 16)));
+  d.ksplit = ksplit > 1 ? ksplit : 1;
+  const bool via16 = d.ksplit > 1;   // split-K reduces into the 16-bit output format
+  const int cout8 = ((Cout + 7) / 8) * 8;
+  d.out_mode = via16 ? 0 : 1; d.lrelu = lrelu; d.is_bf16 = is_bf16;
+  d.out_cstride = via16 ? cout8 : Cout; d.out_coff = 0;
   ConvPlan plan;
   rc = conv_plan_geometry(plan, d);
   if (rc != OFS_OK) return rc;
@@ -654,51 +742,67 @@ extern "C" int ofs_conv2d_nhwc(const float* x, const float* w_host, const float*
   std::vector<uint16_t> wp;
   std::vector<float> bp;
   conv_pack_weights(plan, wsrc, b_host, wp, bp);
-  void *x16 = nullptr, *w_dev = nullptr;
-  float* b_dev = nullptr;
+  void *x16 = nullptr, *w_dev = nullptr, *y16 = nullptr;
+  float *b_dev = nullptr, *ws = nullptr;
   const size_t npix = (size_t)B * H * W;
+  const size_t npix_out = (size_t)B * plan.p.out_H * plan.p.out_W;
   auto cleanup = [&]() {
     if (x16) cudaFree(x16);
     if (w_dev) cudaFree(w_dev);
     if (b_dev) cudaFree(b_dev);
+    if (y16) cudaFree(y16);
+    if (ws) cudaFree(ws);
   };
   rc = check_cuda(cudaMalloc(&x16, npix * d.in_cs * 2), "cudaMalloc x16", __FILE__, __LINE__);
   if (rc == OFS_OK) rc = check_cuda(cudaMalloc(&w_dev, wp.size() * 2), "cudaMalloc w", __FILE__, __LINE__);
   if (rc == OFS_OK) rc = check_cuda(cudaMalloc((void**)&b_dev, bp.size() * 4), "cudaMalloc b", __FILE__, __LINE__);
+  if (rc == OFS_OK && via16) rc = check_cuda(cudaMalloc(&y16, npix_out * cout8 * 2), "cudaMalloc y16", __FILE__, __LINE__);
+  if (rc == OFS_OK && plan.ws_bytes) rc = check_cuda(cudaMalloc((void**)&ws, plan.ws_bytes), "cudaMalloc ws", __FILE__, __LINE__);
   if (rc == OFS_OK) rc = check_cuda(cudaMemcpyAsync(w_dev, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice, st), "H2D w", __FILE__, __LINE__);
   if (rc == OFS_OK) rc = check_cuda(cudaMemcpyAsync(b_dev, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice, st), "H2D b", __FILE__, __LINE__);
   if (rc == OFS_OK) rc = launch_pack_act(x, x16, npix, cin_logical, d.in_cs, is_bf16, st);
-  if (rc == OFS_OK) rc = conv_plan_bind(plan, x16, w_dev, b_dev, y);
+  if (rc == OFS_OK) rc = conv_plan_bind(plan, x16, w_dev, b_dev, via16 ? y16 : (void*)y, ws);
   if (rc == OFS_OK) rc = conv_launch(plan, st);
+  if (rc == OFS_OK && via16) rc = launch_unpack_act(y16, y, npix_out, cout8, 0, Cout, is_bf16, st);
   if (rc == OFS_OK) rc = check_cuda(cudaStreamSynchronize(st), "conv2d sync", __FILE__, __LINE__);
   cleanup();
   return rc;
+}
+
+extern "C" int ofs_conv2d_nhwc(const float* x, const float* w_host, const float* b_host, float* y, int B, int H, int W,
+                               int Cin, int Cout, int k, int stride, int transposed, int lrelu, int precision,
+                               ofs_stream stream) {
+  return ofs_conv2d_nhwc_ex(x, w_host, b_host, y, B, H, W, Cin, Cout, k, stride, transposed, lrelu, precision, 0, 1, stream);
 }
 
 // Host-only introspection of the plan (geometry, tap table, activation view, packed weights): lets
 // the CPU test-suite emulate the TMA gathers + GEMM in numpy and check the whole index algebra
 // against the oracle convolution without a GPU.  Not part of the product API.
 extern "C" int ofs_debug_conv_plan(int kind, int B, int H, int W, int cin, int in_cs, int cout, int k, int stride,
-                                   int block_n, int is_bf16, const float* w_tf, const float* bias, int* info /*[40]*/,
+                                   int block_n, int is_bf16, const float* w_tf, const float* bias, int* info /*[44]*/,
                                    short* taps /*[4][64]: c,x,p,y*/, uint16_t* w_packed, long long w_cap,
                                    float* b_padded /*[n_pad]*/) {
   using namespace ofs;
   ConvDesc d;
   d.kind = kind ? kDeconvK4S2 : kConv;
   d.B = B; d.H = H; d.W = W; d.cin = cin; d.in_cs = in_cs; d.cout = cout; d.k = k; d.stride = stride;
-  d.block_n = block_n; d.out_mode = 1; d.lrelu = 0; d.is_bf16 = is_bf16; d.out_cstride = cout; d.out_coff = 0;
+  d.block_n = block_n & 0xffff; d.out_mode = 1; d.lrelu = 0; d.is_bf16 = is_bf16; d.out_cstride = cout; d.out_coff = 0;
+  d.ksplit = (block_n >> 16) > 0 ? (block_n >> 16) : 1;  // split-K factor rides in the high half (debug entry only)
+  if (d.ksplit > 1) { d.out_mode = 0; d.out_cstride = ((cout + 7) / 8) * 8; }
   ConvPlan plan;
   int rc = conv_plan_geometry(plan, d);
   if (rc != OFS_OK) return rc;
   const ConvGemmParams& p = plan.p;
   unsigned long long vd[5], vs[4];
   conv_act_view(d, vd, vs);
-  const int vals[] = {p.Hg, p.Wg, p.rows_total, p.tileW_log2, p.tileH, p.rpl, p.tiles_x, p.tiles_m, p.tiles_n, p.phases,
+  const int vals[] = {p.Hg, p.Wg, p.rows_total, p.tileW_log2, p.tile_rows, p.piece_rows, p.tiles_x, p.tiles_m, p.tiles_n, p.phases,
                       p.ntaps, p.nchunks, p.n_pad, plan.k_total, plan.w_rows, plan.paired ? 1 : 0, p.out_scale, p.out_H,
                       p.out_W, plan.grid, (int)vd[0], (int)vd[1], (int)vd[2], (int)vd[3], (int)vd[4], (int)(vs[0] / 2),
                       (int)(vs[1] / 2), (int)(vs[2] / 2), (int)(vs[3] / 2), p.out_oy[0], p.out_oy[1], p.out_oy[2],
-                      p.out_oy[3], p.out_ox[0], p.out_ox[1], p.out_ox[2], p.out_ox[3], (int)plan.smem, 0, 0};
-  for (int i = 0; i < 40; ++i) info[i] = vals[i];
+                      p.out_oy[3], p.out_ox[0], p.out_ox[1], p.out_ox[2], p.out_ox[3], (int)plan.smem, p.npieces, p.box_y,
+                      p.box_b, p.a_bytes, p.ksplit, p.kb_per_split};
+  static_assert(sizeof(vals) / sizeof(int) == 44, "info layout");
+  for (int i = 0; i < 44; ++i) info[i] = vals[i];
   for (int i = 0; i < kMaxTapEntries; ++i) {
     taps[0 * kMaxTapEntries + i] = p.tap_c[i];
     taps[1 * kMaxTapEntries + i] = p.tap_x[i];

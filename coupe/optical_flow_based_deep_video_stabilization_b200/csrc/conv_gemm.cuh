@@ -17,19 +17,27 @@ struct ConvGemmParams {
   // M grid (output pixels; for the transposed conv: input pixels, one GEMM per sub-pixel phase)
   int Hg, Wg;          // grid height / width per image
   int rows_total;      // B * Hg
-  int tileW_log2;      // tile = tileH rows x tileW pixels = 128 GEMM rows
-  int tileH;
-  int rpl;             // rows per TMA piece (a piece never straddles two images)
+  int tileW_log2;      // tile = tile_rows "global rows" (b,y) x tileW pixels <= 128 GEMM rows
+  int tile_rows;       // valid global rows per tile
+  int npieces;         // TMA loads per A stage
+  int piece_rows;      // global rows per piece = box_y * box_b (a piece never straddles an image boundary
+                       // unless it is made of whole images)
+  int box_y, box_b;    // TMA box extent along y and batch: {rpl, 1}, or {Hg, images per tile} for small grids
+  int a_bytes;         // bytes one A stage receives = npieces * piece_rows * tileW * 128
   int tiles_x;         // Wg / tileW
-  int tiles_m;         // tiles_x * ceil(rows_total / tileH)
+  int tiles_m;         // tiles_x * ceil(rows_total / tile_rows)
   int tiles_n;         // n_pad / BLOCK_N
   int phases;          // 1 (conv) or 4 (transposed conv sub-pixel phases)
+  int ksplit;          // split-K factor (partials go to an fp32 workspace, reduced by splitk_reduce_kernel)
+  int kb_per_split;    // K blocks per split
+  long long ws_split_stride;  // workspace elements between two splits = out pixels * n_pad
   int ntaps, nchunks;  // K_total = ntaps * nchunks * 64
   int n_pad;           // padded output channels per phase
   // epilogue
   void* out;           // 16-bit activations (mode 0) or fp32 (mode 1)
   const float* bias;   // [n_pad]
-  int out_mode;        // 0: act(v + b) -> 16-bit;  1: v + b -> fp32 (first n_valid columns)
+  int out_mode;        // 0: act(v + b) -> 16-bit;  1: v + b -> fp32 (first n_valid columns);
+                       // 2: raw fp32 partial sums -> split-K workspace [ks][pixel][n_pad]
   int out_H, out_W;    // full output image size
   int out_cstride;     // channels per output pixel in the destination buffer
   int out_coff;        // channel offset of this layer's slice in the destination (concat-by-slice)
@@ -54,6 +62,7 @@ struct ConvDesc {
   int block_n;         // 16, 32, 64, 128 or 256
   int out_mode, lrelu, is_bf16;
   int out_cstride, out_coff;
+  int ksplit = 1;      // > 1: split the K loop over this many CTAs per tile (16-bit output mode only)
 };
 
 struct ConvPlan {
@@ -66,6 +75,11 @@ struct ConvPlan {
   int w_rows = 0;            // phases * n_pad
   bool paired = false;       // conv1-style stride-2 layer with in_cs == 32: two x-taps per K chunk
   double macs = 0;           // literal MACs of the layer (roofline numerator)
+  size_t ws_bytes = 0;       // split-K workspace this plan needs (0 when ksplit == 1)
+  // split-K reduction (filled by bind)
+  void* final_out = nullptr;
+  const float* bias_dev = nullptr;
+  float* ws = nullptr;
 };
 
 // Geometry only (no device pointers): tap table, tiling, grid.  OFS_EINVAL on unsupported shapes.
@@ -75,7 +89,8 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d);
 void conv_pack_weights(const ConvPlan& plan, const float* w_tf, const float* bias, std::vector<uint16_t>& w_packed,
                        std::vector<float>& b_padded);
 // Binds device pointers and encodes the TMA descriptors.
-int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_packed_dev, const float* bias_dev, void* out);
+int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_packed_dev, const float* bias_dev, void* out,
+                   float* workspace = nullptr);
 int conv_launch(const ConvPlan& plan, cudaStream_t st);
 
 // 5-D TMA view of the input activation (dims in elements, strides in bytes; dim 0 is contiguous)

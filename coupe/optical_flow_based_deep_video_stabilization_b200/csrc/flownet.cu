@@ -16,7 +16,9 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -25,7 +27,7 @@
 
 namespace ofs {
 int flow_resize_warp_impl(const float* img, const float* flow2, float* out, int B, int H, int W, int fh, int fw,
-                          cudaStream_t st);
+                          cudaStream_t st, int prescaled);
 }
 
 namespace {
@@ -117,6 +119,7 @@ struct Predict2Params {
   const float* P;     // [B,96,128,18]: column (ky*3+kx)*2 + o
   const float2* f3;   // [B,48,64]
   float2* f2;         // [B,382,510]
+  float2* f2s;        // [B,382,510]: (f2 * 384.0) / 382, the operand of the test-mode flow glue (main_dl.py:497)
   float bias0, bias1;
   float sy, sx;       // NN align_corners scales (98-1)/(384-1), (130-1)/(512-1) in fp32
   float hs, ws;       // bilinear scales 48/382, 64/510 in fp32
@@ -150,8 +153,75 @@ __global__ void predict2_gather_kernel(Predict2Params p) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { a0 += u.x; a1 += u.y; }  // ElementwiseLayer left fold, model.py:887
     p.f2[idx] = make_float2(a0, a1);
+    p.f2s[idx] = make_float2(__fdiv_rn(a0 * 384.0f, 382.0f), __fdiv_rn(a1 * 384.0f, 382.0f));
   }
 }
+
+// Flow heads predict6..predict3 (model.py:847-848,855-856,864-865,873-874): zero-pad 1 + 3x3 conv to 2
+// channels + bias, no activation.  N = 2 is no tensor-core shape: one warp per output pixel, lanes stride
+// over channels with 128-bit loads of the 16-bit activations and of the [tap][c][2] 16-bit weights, fp32
+// FMA, shuffle reduction.  Neighbouring pixels share taps through L1.
+struct HeadParams {
+  const uint16_t* act;  // [B,h,w,cs]
+  const uint16_t* wgt;  // [9][cs][2]   (zero for c >= cin)
+  float2* out;          // [B,h,w]
+  float b0, b1;
+  int B, h, w, cs, is_bf16;
+};
+
+__device__ __forceinline__ float2 unpack16x2(uint32_t u, int is_bf16) {
+  if (is_bf16) return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+  return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+
+__global__ void __launch_bounds__(256) head3x3_kernel(HeadParams p) {
+  const int lane = threadIdx.x & 31;
+  const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const size_t npix = (size_t)p.B * p.h * p.w;
+  for (size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pix < npix; pix += warps) {
+    const int x = (int)(pix % p.w);
+    const size_t r = pix / p.w;
+    const int y = (int)(r % p.h);
+    const int b = (int)(r / p.h);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll 1
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      if (yy < 0 || yy >= p.h || xx < 0 || xx >= p.w) continue;  // warp-uniform
+      const uint16_t* ap = p.act + (((size_t)b * p.h + yy) * p.w + xx) * p.cs;
+      const uint16_t* wp = p.wgt + (size_t)t * p.cs * 2;
+      for (int c = lane * 8; c < p.cs; c += 256) {
+        const uint4 av = __ldg(reinterpret_cast<const uint4*>(ap + c));
+        const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(wp + 2 * c));
+        const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(wp + 2 * c + 8));
+        const uint32_t au[4] = {av.x, av.y, av.z, av.w};
+        const uint32_t wu[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 a = unpack16x2(au[i], p.is_bf16);      // channels c+2i, c+2i+1
+          const float2 wa = unpack16x2(wu[2 * i], p.is_bf16);     // (o0, o1) of channel c+2i
+          const float2 wb = unpack16x2(wu[2 * i + 1], p.is_bf16); // (o0, o1) of channel c+2i+1
+          a0 = fmaf(a.x, wa.x, a0); a1 = fmaf(a.x, wa.y, a1);
+          a0 = fmaf(a.y, wb.x, a0); a1 = fmaf(a.y, wb.y, a1);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if (lane == 0) p.out[pix] = make_float2(a0 + p.b0, a1 + p.b1);
+  }
+}
+
+struct Head {
+  std::string name;   // "predict6" .. "predict3"
+  int level, h, w, cin, cs;
+  const void* in = nullptr;
+  void* w_dev = nullptr;  // [9][cs][2] 16-bit
+  float bias[2] = {0, 0};
+};
 
 struct Layer {
   std::string name;       // checkpoint layer name ("3_1", "deconv5", "predict4", ...)
@@ -159,7 +229,10 @@ struct Layer {
   ConvDesc d;             // B filled in at prepare()
   const void* in = nullptr;
   void* out = nullptr;
-  ConvPlan plan;
+  int ksplit = 1;         // fixed split-K factor: independent of the batch so results are batch-invariant
+  int block_n_run = 0;    // BLOCK_N used at run time (0 = d.block_n)
+  ConvPlan plan;          // plan of the currently prepared batch size
+  std::map<int, ConvPlan> plans;  // bound plans per batch size (TMA descriptors are per batch)
   void* w_dev = nullptr;
   float* b_dev = nullptr;
   size_t w_elems = 0;
@@ -174,16 +247,21 @@ struct ofs_net {
   int device = 0, max_batch = 0, is_bf16 = 1;
   bool loaded = false;
   int prepared_B = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_h2d[64] = {nullptr}, ev_comp[64] = {nullptr};
   // 16-bit activations
   void *x0 = nullptr, *conv1 = nullptr, *concat2 = nullptr, *conv3 = nullptr, *concat3 = nullptr, *conv4 = nullptr,
        *concat4 = nullptr, *conv5 = nullptr, *concat5 = nullptr, *conv6 = nullptr, *conv6_1 = nullptr;
   // fp32
   float *raw[7] = {nullptr}, *f[7] = {nullptr};  // index = pyramid level 3..6; f[2] = flow2
   float* P2 = nullptr;
+  float* f2s = nullptr;  // pre-scaled flow2 for the fused flow-resize + warp
   float* upw = nullptr;  // 4 x (64 + 2) floats: upsample6_5, 5_4, 4_3, 3_2
   float p2_bias[2] = {0, 0};
   std::vector<Layer> layers;
+  std::vector<Head> heads;   // predict6, predict5, predict4, predict3
+  float* ws = nullptr;       // split-K workspace (grow-only)
+  size_t ws_bytes = 0;
   std::map<std::string, ActInfo> acts;
   std::vector<void*> allocs;
   // host-API staging
@@ -216,17 +294,88 @@ Layer make_layer(const char* name, const char* bn, ConvKind kind, int H, int W, 
   return L;
 }
 
+// OFS_TUNE="layer:block_n:ksplit,..." overrides the tiling of individual layers (experiments only;
+// block_n must keep the packed weight layout valid, i.e. divide the layer's padded N).
+bool tune_lookup(const std::string& name, int* block_n, int* ksplit) {
+  const char* env = getenv("OFS_TUNE");
+  if (!env) return false;
+  std::string s(env);
+  size_t pos = 0;
+  while (pos < s.size()) {
+    size_t end = s.find(',', pos);
+    if (end == std::string::npos) end = s.size();
+    const std::string item = s.substr(pos, end - pos);
+    const size_t c1 = item.find(':'), c2 = item.find(':', c1 == std::string::npos ? 0 : c1 + 1);
+    if (c1 != std::string::npos && c2 != std::string::npos && item.substr(0, c1) == name) {
+      *block_n = atoi(item.substr(c1 + 1, c2 - c1 - 1).c_str());
+      *ksplit = atoi(item.substr(c2 + 1).c_str());
+      return true;
+    }
+    pos = end + 1;
+  }
+  return false;
+}
+
 int prepare(ofs_net* n, int B) {
   if (n->prepared_B == B) return OFS_OK;
+  if (!n->layers.empty() && n->layers[0].plans.count(B)) {  // cached
+    for (Layer& L : n->layers) L.plan = L.plans[B];
+    n->prepared_B = B;
+    return OFS_OK;
+  }
+  size_t ws_need = 0;
   for (Layer& L : n->layers) {
     L.d.B = B;
     L.d.is_bf16 = n->is_bf16;
+    L.d.ksplit = 1;
     int rc = conv_plan_geometry(L.plan, L.d);
     if (rc != OFS_OK) return rc;
-    rc = conv_plan_bind(L.plan, L.in, L.w_dev, L.b_dev, L.out);
+    int bn = L.block_n_run ? L.block_n_run : L.d.block_n, ks = L.ksplit;
+    const bool tuned = tune_lookup(L.name, &bn, &ks);
+    if (tuned && (bn != L.d.block_n) && (L.n_pad % bn != 0)) {
+      set_error("OFS_TUNE: block_n %d does not divide the padded N %d of layer %s", bn, L.n_pad, L.name.c_str());
+      return OFS_EINVAL;
+    }
+    if (ks > 1 || bn != L.d.block_n) {
+      ConvDesc d = L.d;
+      d.block_n = bn;
+      d.ksplit = (L.d.out_mode == 0 && ks > 1) ? ks : 1;
+      rc = conv_plan_geometry(L.plan, d);
+      if (rc != OFS_OK) return rc;
+    }
+    ws_need = std::max(ws_need, L.plan.ws_bytes);
+  }
+  if (ws_need > n->ws_bytes) {
+    // grow-only; sized for max_batch at once so that cached plans of other batch sizes stay valid
+    OFS_CUDA(cudaDeviceSynchronize());
+    if (n->ws) cudaFree(n->ws);
+    n->ws = nullptr;
+    n->ws_bytes = 0;
+    for (Layer& L : n->layers) L.plans.clear();
+    const size_t want = std::max(ws_need, (ws_need / (size_t)B) * (size_t)n->max_batch);
+    OFS_CUDA(cudaMalloc((void**)&n->ws, want));
+    n->ws_bytes = want;
+  }
+  for (Layer& L : n->layers) {
+    int rc = conv_plan_bind(L.plan, L.in, L.w_dev, L.b_dev, L.out, n->ws);
     if (rc != OFS_OK) return rc;
+    L.plans[B] = L.plan;
   }
   n->prepared_B = B;
+  return OFS_OK;
+}
+
+int launch_head(ofs_net* n, const Head& h, int B, cudaStream_t st) {
+  HeadParams p;
+  p.act = reinterpret_cast<const uint16_t*>(h.in);
+  p.wgt = reinterpret_cast<const uint16_t*>(h.w_dev);
+  p.out = reinterpret_cast<float2*>(n->raw[h.level]);
+  p.b0 = h.bias[0]; p.b1 = h.bias[1];
+  p.B = B; p.h = h.h; p.w = h.w; p.cs = h.cs; p.is_bf16 = n->is_bf16;
+  const size_t npix = (size_t)B * h.h * h.w;
+  const int blocks = (int)std::min<size_t>((npix + 7) / 8, (size_t)sm_count() * 8);
+  head3x3_kernel<<<blocks, 256, 0, st>>>(p);
+  OFS_LAUNCH_CHECK();
   return OFS_OK;
 }
 
@@ -263,7 +412,33 @@ int launch_pyr(ofs_net* n, int level, int B, cudaStream_t st) {
   return OFS_OK;
 }
 
-int forward_impl(ofs_net* n, const float* feats, int B, float* f2_target, cudaStream_t st) {
+// `marks` (optional): one event is recorded on `st` after every kernel launch of the forward
+struct Marks {
+  std::vector<cudaEvent_t> ev;
+  std::vector<std::string> names;
+  std::vector<double> macs;
+  size_t used = 0;
+  int mark(cudaStream_t st, const std::string& name, double m) {
+    if (used == ev.size()) {
+      cudaEvent_t e;
+      OFS_CUDA(cudaEventCreate(&e));
+      ev.push_back(e);
+    }
+    OFS_CUDA(cudaEventRecord(ev[used++], st));
+    names.push_back(name);
+    macs.push_back(m);
+    return OFS_OK;
+  }
+};
+#define OFS_MARK(name, m)                                \
+  do {                                                   \
+    if (marks) {                                         \
+      int _rc = marks->mark(st, (name), (m));            \
+      if (_rc != OFS_OK) return _rc;                     \
+    }                                                    \
+  } while (0)
+
+int forward_impl(ofs_net* n, const float* feats, int B, float* f2_target, cudaStream_t st, Marks* marks = nullptr) {
   OFS_REQUIRE(n && feats, "ofs_net_forward: null pointer");
   OFS_REQUIRE(B >= 1 && B <= n->max_batch, "ofs_net_forward: batch %d outside [1, %d]", B, n->max_batch);
   if (!n->loaded) {
@@ -273,21 +448,37 @@ int forward_impl(ofs_net* n, const float* feats, int B, float* f2_target, cudaSt
   OFS_CUDA(cudaSetDevice(n->device));
   int rc = prepare(n, B);
   if (rc != OFS_OK) return rc;
+  OFS_MARK("start", 0.0);
   rc = launch_pack_act(feats, n->x0, (size_t)B * kNetH * kNetW, kNetC, 32, n->is_bf16, st);
   if (rc != OFS_OK) return rc;
+  OFS_MARK("pack_input", 0.0);
   for (Layer& L : n->layers) {
+    int lvl = 0;
+    if (L.name == "deconv5") lvl = 6;
+    else if (L.name == "deconv4") lvl = 5;
+    else if (L.name == "deconv3") lvl = 4;
+    else if (L.name == "deconv2") lvl = 3;
+    if (lvl) {  // the head of this level reads the same input as the transposed conv
+      const Head& h = n->heads[6 - lvl];
+      rc = launch_head(n, h, B, st);
+      if (rc != OFS_OK) return rc;
+      OFS_MARK("head:" + h.name, 0.0);
+    }
     rc = conv_launch(L.plan, st);
     if (rc != OFS_OK) return rc;
-    if (L.name == "deconv5") rc = launch_pyr(n, 6, B, st);
-    else if (L.name == "deconv4") rc = launch_pyr(n, 5, B, st);
-    else if (L.name == "deconv3") rc = launch_pyr(n, 4, B, st);
-    else if (L.name == "deconv2") rc = launch_pyr(n, 3, B, st);
-    if (rc != OFS_OK) return rc;
+    OFS_MARK(L.name == "predict2" ? std::string("gemm:predict2_product") : "gemm:" + L.name,
+             L.name == "predict2" ? (double)B * 96 * 128 * 194 * 18 : L.plan.macs);
+    if (lvl) {
+      rc = launch_pyr(n, lvl, B, st);
+      if (rc != OFS_OK) return rc;
+      OFS_MARK("pyramid:level" + std::to_string(lvl), 0.0);
+    }
   }
   Predict2Params pp;
   pp.P = n->P2;
   pp.f3 = reinterpret_cast<const float2*>(n->f[3]);
   pp.f2 = reinterpret_cast<float2*>(f2_target ? f2_target : n->f[2]);
+  pp.f2s = reinterpret_cast<float2*>(n->f2s);
   pp.bias0 = n->p2_bias[0]; pp.bias1 = n->p2_bias[1];
   pp.sy = 97.0f / 383.0f; pp.sx = 129.0f / 511.0f;
   pp.hs = 48.0f / 382.0f; pp.ws = 64.0f / 510.0f;
@@ -296,6 +487,7 @@ int forward_impl(ofs_net* n, const float* feats, int B, float* f2_target, cudaSt
   const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
   predict2_gather_kernel<<<blocks, 256, 0, st>>>(pp);
   OFS_LAUNCH_CHECK();
+  OFS_MARK("predict2_gather", 0.0);
   return OFS_OK;
 }
 
@@ -330,11 +522,18 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
     if (rc != OFS_OK) { ofs_net_destroy(n); return rc; }
   }
   rc = dev_alloc(n, (void**)&n->P2, B * 96 * 128 * 18 * 4, true);
+  if (rc == OFS_OK) rc = dev_alloc(n, (void**)&n->f2s, B * 382 * 510 * 2 * 4, true);
   if (rc == OFS_OK) rc = dev_alloc(n, (void**)&n->upw, 4 * 66 * 4, true);
   if (rc == OFS_OK) rc = dev_alloc(n, (void**)&n->st_feats, B * kNetH * kNetW * kNetC * 4, false);
   if (rc != OFS_OK) { ofs_net_destroy(n); return rc; }
-  if (cudaStreamCreateWithFlags(&n->stream, cudaStreamNonBlocking) != cudaSuccess) {
-    set_error("cudaStreamCreate failed");
+  bool ok = cudaStreamCreateWithFlags(&n->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&n->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&n->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 64 && ok; ++i)
+    ok = cudaEventCreateWithFlags(&n->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&n->ev_comp[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    set_error("cudaStreamCreate / cudaEventCreate failed");
     ofs_net_destroy(n);
     return OFS_ECUDA;
   }
@@ -350,16 +549,33 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
   Ls.push_back(make_layer("5_1", "5_1", kConv, 12, 16, 512, 512, 512, 3, 1, 128, 0, 1, 1032, 0, n->conv5, n->concat5));
   Ls.push_back(make_layer("6", "6", kConv, 12, 16, 512, 1032, 1024, 3, 2, 128, 0, 1, 1024, 0, n->concat5, n->conv6));
   Ls.push_back(make_layer("6_1", "6_1", kConv, 6, 8, 1024, 1024, 1024, 3, 1, 128, 0, 1, 1024, 0, n->conv6, n->conv6_1));
-  Ls.push_back(make_layer("predict6", "", kConv, 6, 8, 1024, 1024, 2, 3, 1, 16, 1, 0, 2, 0, n->conv6_1, n->raw[6]));
   Ls.push_back(make_layer("deconv5", "deconv5_bn", kDeconvK4S2, 6, 8, 1024, 1024, 512, 4, 2, 128, 0, 1, 1032, 512, n->conv6_1, n->concat5));
-  Ls.push_back(make_layer("predict5", "", kConv, 12, 16, 1026, 1032, 2, 3, 1, 16, 1, 0, 2, 0, n->concat5, n->raw[5]));
   Ls.push_back(make_layer("deconv4", "deconv4_bn", kDeconvK4S2, 12, 16, 1026, 1032, 256, 4, 2, 128, 0, 1, 776, 512, n->concat5, n->concat4));
-  Ls.push_back(make_layer("predict4", "", kConv, 24, 32, 770, 776, 2, 3, 1, 16, 1, 0, 2, 0, n->concat4, n->raw[4]));
   Ls.push_back(make_layer("deconv3", "deconv3_bn", kDeconvK4S2, 24, 32, 770, 776, 128, 4, 2, 128, 0, 1, 392, 256, n->concat4, n->concat3));
-  Ls.push_back(make_layer("predict3", "", kConv, 48, 64, 386, 392, 2, 3, 1, 16, 1, 0, 2, 0, n->concat3, n->raw[3]));
   Ls.push_back(make_layer("deconv2", "deconv2_bn", kDeconvK4S2, 48, 64, 386, 392, 64, 4, 2, 64, 0, 1, 200, 128, n->concat3, n->concat2));
   // predict2 as a 1x1 GEMM with 18 columns on the 96x128 grid
   Ls.push_back(make_layer("predict2", "", kConv, 96, 128, 194, 200, 18, 1, 1, 32, 1, 0, 18, 0, n->concat2, n->P2));
+  {
+    Head h6{"predict6", 6, 6, 8, 1024, 1024, n->conv6_1}, h5{"predict5", 5, 12, 16, 1026, 1032, n->concat5},
+        h4{"predict4", 4, 24, 32, 770, 776, n->concat4}, h3{"predict3", 3, 48, 64, 386, 392, n->concat3};
+    n->heads = {h6, h5, h4, h3};
+    for (Head& h : n->heads) {
+      rc = dev_alloc(n, &h.w_dev, (size_t)9 * h.cs * 2 * 2, true);
+      if (rc != OFS_OK) { ofs_net_destroy(n); return rc; }
+    }
+  }
+  // Deep layers have few output tiles (conv6_1 at B=8: 32) but long K loops: their K loop is split over
+  // several CTAs (fp32 partials in a workspace, summed in a fixed order).  The factors are constants of the
+  // layer -- not of the batch -- so a frame pair's result is bit-identical whatever batch it rides in.
+  // BLOCK_N = 256 where cout allows: the kernel is bound by L2 -> shared-memory delivery, and a wider N
+  // tile halves the A-operand re-fetch per FLOP (measured: profiles/r01_tuning.md).
+  for (Layer& L : Ls) {
+    if (L.name == "3" || L.name == "3_1" || L.name == "4" || L.name == "4_1") { L.block_n_run = 256; }
+    else if (L.name == "5" || L.name == "5_1") { L.block_n_run = 256; L.ksplit = 6; }
+    else if (L.name == "6" || L.name == "6_1") { L.block_n_run = 256; L.ksplit = 8; }
+    else if (L.name == "deconv5") { L.block_n_run = 256; L.ksplit = 4; }
+    else if (L.name == "deconv4") { L.block_n_run = 256; L.ksplit = 3; }
+  }
   for (Layer& L : Ls) {
     L.d.is_bf16 = n->is_bf16;
     rc = conv_plan_geometry(L.plan, L.d);
@@ -386,8 +602,16 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
 int ofs_net_destroy(ofs_net* n) {
   if (!n) return OFS_OK;
   cudaSetDevice(n->device);
-  if (n->stream) { cudaStreamSynchronize(n->stream); cudaStreamDestroy(n->stream); }
+  cudaDeviceSynchronize();
+  if (n->stream) cudaStreamDestroy(n->stream);
+  if (n->s_h2d) cudaStreamDestroy(n->s_h2d);
+  if (n->s_d2h) cudaStreamDestroy(n->s_d2h);
+  for (int i = 0; i < 64; ++i) {
+    if (n->ev_h2d[i]) cudaEventDestroy(n->ev_h2d[i]);
+    if (n->ev_comp[i]) cudaEventDestroy(n->ev_comp[i]);
+  }
   for (void* p : n->allocs) cudaFree(p);
+  if (n->ws) cudaFree(n->ws);
   if (n->st_frames) cudaFree(n->st_frames);
   if (n->st_out) cudaFree(n->st_out);
   delete n;
@@ -465,6 +689,22 @@ int ofs_net_load_weights(ofs_net* n, const ofs_named_array* arrays, int count) {
     OFS_CUDA(cudaMemcpy(L.w_dev, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
     OFS_CUDA(cudaMemcpy(L.b_dev, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice));
   }
+  for (Head& h : n->heads) {
+    const float *w = nullptr, *b = nullptr;
+    int rc = find(h.name + "/W_conv2d", (int64_t)9 * h.cin * 2, &w, true);
+    if (rc == OFS_OK) rc = find(h.name + "/b_conv2d", 2, &b, false);
+    if (rc != OFS_OK) return rc;
+    std::vector<uint16_t> wp((size_t)9 * h.cs * 2, 0);   // [tap][c][o]; TF layout is already [ky,kx,ci,o]
+    for (int t = 0; t < 9; ++t)
+      for (int c = 0; c < h.cin; ++c)
+        for (int o = 0; o < 2; ++o) {
+          const float v = w[((size_t)t * h.cin + c) * 2 + o];
+          wp[((size_t)t * h.cs + c) * 2 + o] = n->is_bf16 ? f32_to_bf16_rn(v) : f32_to_fp16_rn(v);
+        }
+    h.bias[0] = b ? b[0] : 0.f;
+    h.bias[1] = b ? b[1] : 0.f;
+    OFS_CUDA(cudaMemcpy(h.w_dev, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+  }
   static const char* ups[4] = {"upsample6_5", "upsample5_4", "upsample4_3", "upsample3_2"};
   std::vector<float> upw(4 * 66, 0.0f);
   for (int i = 0; i < 4; ++i) {
@@ -478,6 +718,7 @@ int ofs_net_load_weights(ofs_net* n, const ofs_named_array* arrays, int count) {
   OFS_CUDA(cudaMemcpy(n->upw, upw.data(), upw.size() * 4, cudaMemcpyHostToDevice));
   n->loaded = true;
   n->prepared_B = 0;
+  for (Layer& L : n->layers) L.plans.clear();
   return OFS_OK;
 }
 
@@ -501,7 +742,7 @@ int ofs_net_stabilize(ofs_net* n, const float* feats, const float* frames, float
   cudaStream_t st = (cudaStream_t)stream;
   int rc = forward_impl(n, feats, B, flow2_out, st);
   if (rc != OFS_OK) return rc;
-  return flow_resize_warp_impl(frames, flow2_out ? flow2_out : n->f[2], out, B, H, W, 382, 510, st);
+  return flow_resize_warp_impl(frames, n->f2s, out, B, H, W, 382, 510, st, 1);
 }
 
 int ofs_net_stabilize_host(ofs_net* n, const float* feats_host, const float* frames_host, float* out_host, int B,
@@ -509,24 +750,42 @@ int ofs_net_stabilize_host(ofs_net* n, const float* feats_host, const float* fra
   OFS_REQUIRE(n && feats_host && frames_host && out_host, "ofs_net_stabilize_host: null pointer");
   OFS_REQUIRE(B >= 1 && B <= n->max_batch && H > 0 && W > 0, "ofs_net_stabilize_host: bad shape");
   OFS_CUDA(cudaSetDevice(n->device));
-  const size_t frame_bytes = (size_t)B * H * W * 3 * 4;
-  if (frame_bytes > n->st_frames_cap) {  // grow-only staging, sized on first use of a frame size
+  const size_t frame_elems = (size_t)H * W * 3, feat_elems = (size_t)kNetH * kNetW * kNetC;
+  if ((size_t)B * frame_elems * 4 > n->st_frames_cap) {  // grow-only staging, sized on first use of a frame size
+    OFS_CUDA(cudaDeviceSynchronize());
     if (n->st_frames) cudaFree(n->st_frames);
     if (n->st_out) cudaFree(n->st_out);
     n->st_frames = n->st_out = nullptr;
     n->st_frames_cap = 0;
-    const size_t cap = (size_t)n->max_batch * H * W * 3 * 4;
+    const size_t cap = (size_t)n->max_batch * frame_elems * 4;
     OFS_CUDA(cudaMalloc((void**)&n->st_frames, cap));
     OFS_CUDA(cudaMalloc((void**)&n->st_out, cap));
     n->st_frames_cap = cap;
   }
-  cudaStream_t st = n->stream;
-  OFS_CUDA(cudaMemcpyAsync(n->st_feats, feats_host, (size_t)B * kNetH * kNetW * kNetC * 4, cudaMemcpyHostToDevice, st));
-  OFS_CUDA(cudaMemcpyAsync(n->st_frames, frames_host, frame_bytes, cudaMemcpyHostToDevice, st));
-  int rc = ofs_net_stabilize(n, n->st_feats, n->st_frames, n->st_out, nullptr, B, H, W, (ofs_stream)st);
-  if (rc != OFS_OK) return rc;
-  OFS_CUDA(cudaMemcpyAsync(out_host, n->st_out, frame_bytes, cudaMemcpyDeviceToHost, st));
-  OFS_CUDA(cudaStreamSynchronize(st));
+  // The call is PCIe-bound (21 MB of feats + 11 MB of frame in, 11 MB out per 720p pair), so it is
+  // software-pipelined over sub-batches: H2D of chunk k+1, compute of chunk k and D2H of chunk k-1 run on
+  // three streams.  Sub-batching does not change results (fixed split-K factors: batch-invariant).
+  const int chunk = B >= 4 ? 2 : 1;
+  const int nchunks = (B + chunk - 1) / chunk;
+  for (int c = 0; c < nchunks; ++c) {
+    const int b0 = c * chunk, nb = std::min(chunk, B - b0);
+    float* d_feats = n->st_feats + (size_t)b0 * feat_elems;
+    float* d_frames = n->st_frames + (size_t)b0 * frame_elems;
+    float* d_out = n->st_out + (size_t)b0 * frame_elems;
+    OFS_CUDA(cudaMemcpyAsync(d_feats, feats_host + (size_t)b0 * feat_elems, (size_t)nb * feat_elems * 4,
+                             cudaMemcpyHostToDevice, n->s_h2d));
+    OFS_CUDA(cudaMemcpyAsync(d_frames, frames_host + (size_t)b0 * frame_elems, (size_t)nb * frame_elems * 4,
+                             cudaMemcpyHostToDevice, n->s_h2d));
+    OFS_CUDA(cudaEventRecord(n->ev_h2d[c], n->s_h2d));
+    OFS_CUDA(cudaStreamWaitEvent(n->stream, n->ev_h2d[c], 0));
+    int rc = ofs_net_stabilize(n, d_feats, d_frames, d_out, nullptr, nb, H, W, (ofs_stream)n->stream);
+    if (rc != OFS_OK) return rc;
+    OFS_CUDA(cudaEventRecord(n->ev_comp[c], n->stream));
+    OFS_CUDA(cudaStreamWaitEvent(n->s_d2h, n->ev_comp[c], 0));
+    OFS_CUDA(cudaMemcpyAsync(out_host + (size_t)b0 * frame_elems, d_out, (size_t)nb * frame_elems * 4,
+                             cudaMemcpyDeviceToHost, n->s_d2h));
+  }
+  OFS_CUDA(cudaStreamSynchronize(n->s_d2h));
   return OFS_OK;
 }
 
@@ -543,8 +802,51 @@ int ofs_net_get_activation(ofs_net* n, const char* name, int B, float* out, int6
   return launch_unpack_act(a.ptr, out, (size_t)B * a.H * a.W, a.cs, a.coff, a.C, n->is_bf16, (cudaStream_t)stream);
 }
 
+int ofs_net_profile(ofs_net* n, const float* feats, const float* frames, float* out, int B, int H, int W, int iters,
+                    float* ms, double* macs, char* names, int cap, int* count, ofs_stream stream) {
+  OFS_REQUIRE(n && feats && ms && macs && names && count && iters >= 1, "ofs_net_profile: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  Marks marks;
+  std::vector<double> acc;
+  int rc = OFS_OK;
+  for (int it = 0; it < iters && rc == OFS_OK; ++it) {
+    marks.used = 0;
+    marks.names.clear();
+    marks.macs.clear();
+    rc = forward_impl(n, feats, B, nullptr, st, &marks);
+    if (rc == OFS_OK && frames && out) {
+      rc = flow_resize_warp_impl(frames, n->f2s, out, B, H, W, 382, 510, st, 1);
+      if (rc == OFS_OK) rc = marks.mark(st, "flow_resize_warp", 0.0);
+    }
+    if (rc != OFS_OK) break;
+    rc = check_cuda(cudaStreamSynchronize(st), "profile sync", __FILE__, __LINE__);
+    if (rc != OFS_OK) break;
+    if (acc.empty()) acc.assign(marks.used, 0.0);
+    for (size_t i = 1; i < marks.used; ++i) {
+      float t = 0;
+      cudaEventElapsedTime(&t, marks.ev[i - 1], marks.ev[i]);
+      acc[i] += t;
+    }
+  }
+  const int nmarks = (int)marks.used - 1;
+  if (rc == OFS_OK && nmarks > cap) { set_error("ofs_net_profile: capacity %d < %d", cap, nmarks); rc = OFS_EINVAL; }
+  if (rc == OFS_OK) {
+    for (int i = 0; i < nmarks; ++i) {
+      ms[i] = (float)(acc[i + 1] / iters);
+      macs[i] = marks.macs[i + 1];
+      snprintf(names + (size_t)i * 32, 32, "%s", marks.names[i + 1].c_str());
+    }
+    *count = nmarks;
+  }
+  for (cudaEvent_t e : marks.ev) cudaEventDestroy(e);
+  return rc;
+}
+
 int ofs_net_launches_per_forward(const ofs_net* n) {
-  return n ? 1 + (int)n->layers.size() + 4 + 1 : 0;  // pack + GEMM layers + 4 pyramid steps + predict2 gather
+  if (!n) return 0;
+  int k = 1 + (int)n->layers.size() + (int)n->heads.size() + 4 + 1;  // pack + GEMMs + heads + pyramid steps + gather
+  for (const Layer& L : n->layers) k += L.plan.p.ksplit > 1 ? 1 : 0;  // split-K reductions (after prepare())
+  return k;
 }
 
 }  // extern "C"

@@ -52,6 +52,7 @@ struct FlowResize {
   const float* flow2;  // [B,fh,fw,2]
   int fh, fw, H, W;
   float hs, ws;  // fh/H, fw/W in fp32 like CalculateResizeScale
+  int prescaled; // flow2 already holds (flow2 * 384.0) / fh (the network writes that copy itself)
   __device__ __forceinline__ float2 at(int b, int oy, int ox) const {
     const float iy = (float)oy * hs;
     const float ix = (float)ox * ws;
@@ -61,18 +62,20 @@ struct FlowResize {
     const float2* base = reinterpret_cast<const float2*>(flow2) + (size_t)b * fh * fw;
     float2 tl = __ldg(base + (size_t)y0 * fw + x0), tr = __ldg(base + (size_t)y0 * fw + x1);
     float2 bl = __ldg(base + (size_t)y1 * fw + x0), br = __ldg(base + (size_t)y1 * fw + x1);
-    const float fhf = (float)fh;
-    // outputs['predict_flow2'] * 384.0 / 382  (multiply, then true division)
-    tl.x = __fdiv_rn(tl.x * 384.0f, fhf); tl.y = __fdiv_rn(tl.y * 384.0f, fhf);
-    tr.x = __fdiv_rn(tr.x * 384.0f, fhf); tr.y = __fdiv_rn(tr.y * 384.0f, fhf);
-    bl.x = __fdiv_rn(bl.x * 384.0f, fhf); bl.y = __fdiv_rn(bl.y * 384.0f, fhf);
-    br.x = __fdiv_rn(br.x * 384.0f, fhf); br.y = __fdiv_rn(br.y * 384.0f, fhf);
+    if (!prescaled) {
+      const float fhf = (float)fh;
+      // outputs['predict_flow2'] * 384.0 / 382  (multiply, then true division)
+      tl.x = __fdiv_rn(tl.x * 384.0f, fhf); tl.y = __fdiv_rn(tl.y * 384.0f, fhf);
+      tr.x = __fdiv_rn(tr.x * 384.0f, fhf); tr.y = __fdiv_rn(tr.y * 384.0f, fhf);
+      bl.x = __fdiv_rn(bl.x * 384.0f, fhf); bl.y = __fdiv_rn(bl.y * 384.0f, fhf);
+      br.x = __fdiv_rn(br.x * 384.0f, fhf); br.y = __fdiv_rn(br.y * 384.0f, fhf);
+    }
     float2 top, bot, v;
     top.x = tl.x + (tr.x - tl.x) * xl; top.y = tl.y + (tr.y - tl.y) * xl;
     bot.x = bl.x + (br.x - bl.x) * xl; bot.y = bl.y + (br.y - bl.y) * xl;
     v.x = top.x + (bot.x - top.x) * yl;
     v.y = top.y + (bot.y - top.y) * yl;
-    v.x = __fdiv_rn(v.x * (float)W, 512.0f);  // outflow[...,0:1]*out_w/512
+    v.x = (v.x * (float)W) * 0.001953125f;    // outflow[...,0:1]*out_w/512 (power of two: exact)
     v.y = __fdiv_rn(v.y * (float)H, 384.0f);  // outflow[...,1:2]*out_h/384
     return v;
   }
@@ -210,13 +213,18 @@ struct CoordProvider {
   }
 };
 
+// acc + w*v as two separately rounded fp32 operations (no FMA contraction): the reference sums
+// already-rounded products (tf.add_n([wa*Ia, ...])), which makes clipped corner pairs such as
+// (-0.5*I) + (0.5*I) cancel to exactly zero.
+__device__ __forceinline__ float mul_add_rn(float acc, float w, float v) { return __fadd_rn(acc, __fmul_rn(w, v)); }
+
 // 12-byte pixel gather through the read-only path
 __device__ __forceinline__ void gather3(const float* __restrict__ imgb, int srcW, int y, int x, float w, float* acc) {
   if (x >= 0) {
     const float* p = imgb + ((size_t)y * srcW + x) * 3;
-    acc[0] += w * __ldg(p + 0);
-    acc[1] += w * __ldg(p + 1);
-    acc[2] += w * __ldg(p + 2);
+    acc[0] = mul_add_rn(acc[0], w, __ldg(p + 0));
+    acc[1] = mul_add_rn(acc[1], w, __ldg(p + 1));
+    acc[2] = mul_add_rn(acc[2], w, __ldg(p + 2));
   }
 }
 
@@ -268,7 +276,7 @@ __global__ void __launch_bounds__(256) sample_px_kernel(Provider prov, const flo
       float acc = 0.0f;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (t.x[k] >= 0) acc += t.w[k] * __ldg(imgb + ((size_t)t.y[k] * srcW + t.x[k]) * C + c);
+        if (t.x[k] >= 0) acc = mul_add_rn(acc, t.w[k], __ldg(imgb + ((size_t)t.y[k] * srcW + t.x[k]) * C + c));
       o[c] = acc;
     }
   }
@@ -350,9 +358,9 @@ __global__ void __launch_bounds__(256) warp_staged3_kernel(Provider prov, const 
           for (int k = 0; k < 4; ++k) {
             const float* p = tile + ((t[j].y[k] - by0) * bw + (t[j].x[k] - bx0)) * 3;
             const float w = t[j].w[k];
-            acc[3 * j + 0] += w * p[0];
-            acc[3 * j + 1] += w * p[1];
-            acc[3 * j + 2] += w * p[2];
+            acc[3 * j + 0] = mul_add_rn(acc[3 * j + 0], w, p[0]);
+            acc[3 * j + 1] = mul_add_rn(acc[3 * j + 1], w, p[1]);
+            acc[3 * j + 2] = mul_add_rn(acc[3 * j + 2], w, p[2]);
           }
       }
     } else if (active) {
@@ -456,8 +464,9 @@ int launch_sampler(Provider prov, const float* img, float* out, int B, int srcH,
 }  // namespace
 
 int tf_warp_impl(const float* img, const float* flow, float* out, int B, int H, int W, int C, cudaStream_t st) {
-  OFS_REQUIRE(img && flow && out, "ofs_tf_warp: null pointer");
   OFS_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0, "ofs_tf_warp: bad shape B=%d H=%d W=%d C=%d", B, H, W, C);
+  if (B == 0) return OFS_OK;  // empty batch: nothing to do (pointers may be null)
+  OFS_REQUIRE(img && flow && out, "ofs_tf_warp: null pointer");
   OFS_REQUIRE(((uintptr_t)flow) % 8 == 0, "ofs_tf_warp: flow must be 8-byte aligned");
   TfWarpProvider prov{flow, H, W};
   const bool vec_ok = (((uintptr_t)flow) % 16 == 0);
@@ -472,20 +481,21 @@ int tf_warp_impl(const float* img, const float* flow, float* out, int B, int H, 
 }
 
 int flow_resize_impl(const float* flow2, float* out, int B, int fh, int fw, int H, int W, cudaStream_t st) {
-  OFS_REQUIRE(flow2 && out, "ofs_flow_resize: null pointer");
   OFS_REQUIRE(B >= 0 && fh > 0 && fw > 0 && H > 0 && W > 0, "ofs_flow_resize: bad shape");
   if (B == 0) return OFS_OK;
-  FlowResize fr{flow2, fh, fw, H, W, (float)fh / (float)H, (float)fw / (float)W};
+  OFS_REQUIRE(flow2 && out, "ofs_flow_resize: null pointer");
+  FlowResize fr{flow2, fh, fw, H, W, (float)fh / (float)H, (float)fw / (float)W, 0};
   flow_resize_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, st>>>(fr, out, B);
   OFS_LAUNCH_CHECK();
   return OFS_OK;
 }
 
 int flow_resize_warp_impl(const float* img, const float* flow2, float* out, int B, int H, int W, int fh, int fw,
-                          cudaStream_t st) {
-  OFS_REQUIRE(img && flow2 && out, "ofs_flow_resize_warp: null pointer");
+                          cudaStream_t st, int prescaled) {
   OFS_REQUIRE(B >= 0 && fh > 0 && fw > 0 && H > 0 && W > 0, "ofs_flow_resize_warp: bad shape");
-  ResizeWarpProvider prov{FlowResize{flow2, fh, fw, H, W, (float)fh / (float)H, (float)fw / (float)W}};
+  if (B == 0) return OFS_OK;
+  OFS_REQUIRE(img && flow2 && out, "ofs_flow_resize_warp: null pointer");
+  ResizeWarpProvider prov{FlowResize{flow2, fh, fw, H, W, (float)fh / (float)H, (float)fw / (float)W, prescaled}};
   return launch_sampler(prov, img, out, B, H, W, H, W, 3, true, st);
 }
 
@@ -508,13 +518,14 @@ int ofs_flow_resize(const float* flow2, float* out, int B, int fh, int fw, int H
 
 int ofs_flow_resize_warp(const float* img, const float* flow2, float* out, int B, int H, int W, int fh, int fw,
                          ofs_stream stream) {
-  return ofs::flow_resize_warp_impl(img, flow2, out, B, H, W, fh, fw, (cudaStream_t)stream);
+  return ofs::flow_resize_warp_impl(img, flow2, out, B, H, W, fh, fw, (cudaStream_t)stream, 0);
 }
 
 static int grid_sample(const float* im, const float* theta, float* out, int B, int H, int W, int C, int oH, int oW,
                        int projective, ofs_stream stream) {
-  OFS_REQUIRE(im && theta && out, "ofs_grid_sample: null pointer");
   OFS_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0 && oH > 0 && oW > 0, "ofs_grid_sample: bad shape");
+  if (B == 0) return OFS_OK;
+  OFS_REQUIRE(im && theta && out, "ofs_grid_sample: null pointer");
   ofs::GridSampleCoord gc;
   gc.theta = theta; gc.projective = projective; gc.H = H; gc.W = W; gc.oH = oH; gc.oW = oW;
   gc.step_x = oW > 1 ? 2.0f / (float)(oW - 1) : 0.0f;
@@ -533,10 +544,10 @@ int ofs_grid_sample_projective(const float* im, const float* theta, float* out, 
 }
 
 int ofs_vec2mtrx(const float* p, float* pMtrx, int B, int warp_type, int warp_approx, ofs_stream stream) {
-  OFS_REQUIRE(p && pMtrx, "ofs_vec2mtrx: null pointer");
   OFS_REQUIRE(warp_type == 0 || warp_type == 1, "ofs_vec2mtrx: warp_type must be 0 (homography) or 1 (affine)");
   OFS_REQUIRE(B >= 0 && warp_approx >= 1, "ofs_vec2mtrx: bad B / warp_approx");
   if (B == 0) return OFS_OK;
+  OFS_REQUIRE(p && pMtrx, "ofs_vec2mtrx: null pointer");
   ofs::vec2mtrx_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p, pMtrx, B, warp_type, warp_approx);
   OFS_LAUNCH_CHECK();
   return OFS_OK;
@@ -544,8 +555,9 @@ int ofs_vec2mtrx(const float* p, float* pMtrx, int B, int warp_type, int warp_ap
 
 int ofs_lie_warp(const float* image, const float* pMtrx, const float* refMtrx, float* out, int B, int srcH, int srcW,
                  int outH, int outW, ofs_stream stream) {
-  OFS_REQUIRE(image && pMtrx && refMtrx && out, "ofs_lie_warp: null pointer");
   OFS_REQUIRE(B >= 0 && srcH > 0 && srcW > 0 && outH > 0 && outW > 0, "ofs_lie_warp: bad shape");
+  if (B == 0) return OFS_OK;
+  OFS_REQUIRE(image && pMtrx && refMtrx && out, "ofs_lie_warp: null pointer");
   ofs::LieCoord lc{pMtrx, refMtrx, srcH, srcW, outH, outW};
   ofs::CoordProvider<ofs::LieCoord> prov{lc};
   return ofs::launch_sampler(prov, image, out, B, srcH, srcW, outH, outW, 3, false, (cudaStream_t)stream);

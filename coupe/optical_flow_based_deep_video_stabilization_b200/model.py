@@ -126,6 +126,32 @@ class FlowNetSPyramid:
         n = shape[0] * shape[1] * shape[2] * shape[3]
         return buf[:n].view(*list(shape)).clone()
 
+    def profile(self, feats, frames=None, iters=5):
+        """Mean device time of every kernel launch of one step: list of (name, ms, macs)."""
+        feats = _cuda_f32(feats, "feats")
+        B = feats.shape[0]
+        H = W = 0
+        out = None
+        if frames is not None:
+            frames = _cuda_f32(frames, "frames")
+            _, H, W, _ = frames.shape
+            out = torch.empty_like(frames)
+        cap = 64
+        ms = (C.c_float * cap)()
+        macs = (C.c_double * cap)()
+        names = C.create_string_buffer(cap * 32)
+        count = C.c_int(0)
+        with torch.cuda.device(feats.device):
+            _lib.check(self._lib.ofs_net_profile(self._h, _lib.ptr(feats), _lib.ptr(frames), _lib.ptr(out), B, H, W,
+                                                 int(iters), C.cast(ms, C.c_void_p), C.cast(macs, C.c_void_p),
+                                                 C.cast(names, C.c_void_p), cap, C.byref(count),
+                                                 _lib.current_stream_ptr(feats.device)))
+        res = []
+        for i in range(count.value):
+            nm = names.raw[i * 32:(i + 1) * 32].split(b"\0", 1)[0].decode()
+            res.append((nm, float(ms[i]), float(macs[i])))
+        return res
+
     @property
     def launches_per_forward(self):
         return int(self._lib.ofs_net_launches_per_forward(self._h))

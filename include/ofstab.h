@@ -139,9 +139,14 @@ int ofs_net_stabilize_host(ofs_net* net, const float* feats_host, const float* f
  * conv5_1 conv6 conv6_1 concat5 concat4 concat3 concat2 (logical channels only). */
 int ofs_net_get_activation(ofs_net* net, const char* name, int B, float* out, int64_t capacity, int* shape4,
                            ofs_stream stream);
+/* Measurement aid (bench.py): runs `iters` forwards (+ the fused flow-resize/warp when frames and out
+ * are non-NULL) with a CUDA event recorded on `stream` after every kernel launch, and returns the
+ * mean duration of each launch in launch order.  ms[cap], macs[cap] (literal multiply-accumulates of
+ * the layer, 0 for non-GEMM kernels), names[cap*32] (NUL-terminated, 32 bytes each).  Synchronous. */
+int ofs_net_profile(ofs_net* net, const float* feats, const float* frames, float* out, int B, int H, int W, int iters,
+                    float* ms, double* macs, char* names, int cap, int* count, ofs_stream stream);
 /* per-forward kernel launches (constant for a given B) */
 int ofs_net_launches_per_forward(const ofs_net* net);
-/* device-side time of the last forward's layers is not tracked here; use CUDA events. */
 
 /* ------------------------------------------------------------------------------------------
  * Stand-alone implicit-GEMM convolution on the same tcgen05 kernel the network uses (unit
@@ -154,6 +159,13 @@ int ofs_net_launches_per_forward(const ofs_net* net);
  */
 int ofs_conv2d_nhwc(const float* x, const float* w_host, const float* b_host, float* y, int B, int H, int W, int Cin,
                     int Cout, int k, int stride, int transposed, int lrelu, int precision, ofs_stream stream);
+
+/* Same with explicit tiling: block_n in {16,32,64,128,256} (0 = automatic) and a split-K factor
+ * (ksplit > 1 reduces fp32 partials from a workspace into the 16-bit activation format, so the result
+ * carries one 16-bit rounding, exactly as the network's split-K layers do). */
+int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const float* b_host, float* y, int B, int H, int W,
+                       int Cin, int Cout, int k, int stride, int transposed, int lrelu, int precision, int block_n,
+                       int ksplit, ofs_stream stream);
 
 #ifdef __cplusplus
 }

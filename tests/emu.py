@@ -11,10 +11,10 @@ import ctypes as C
 import numpy as np
 import torch
 
-INFO_KEYS = ["Hg", "Wg", "rows_total", "tileW_log2", "tileH", "rpl", "tiles_x", "tiles_m", "tiles_n", "phases",
+INFO_KEYS = ["Hg", "Wg", "rows_total", "tileW_log2", "tile_rows", "piece_rows", "tiles_x", "tiles_m", "tiles_n", "phases",
              "ntaps", "nchunks", "n_pad", "k_total", "w_rows", "paired", "out_scale", "out_H", "out_W", "grid",
              "d0", "d1", "d2", "d3", "d4", "s1", "s2", "s3", "s4", "oy0", "oy1", "oy2", "oy3", "ox0", "ox1", "ox2",
-             "ox3", "smem"]
+             "ox3", "smem", "npieces", "box_y", "box_b", "a_bytes", "ksplit", "kb_per_split"]
 
 
 def bf16_round(a):
@@ -25,8 +25,8 @@ def bf16_bits_to_f32(u16):
     return (u16.astype(np.uint32) << 16).view(np.float32)
 
 
-def get_plan(lib, kind, B, H, W, cin, in_cs, cout, k, stride, block_n, w_tf=None, bias=None):
-    info = (C.c_int * 40)()
+def get_plan(lib, kind, B, H, W, cin, in_cs, cout, k, stride, block_n, w_tf=None, bias=None, ksplit=1):
+    info = (C.c_int * 44)()
     taps = (C.c_short * 256)()
     cap = 0
     wbuf = None
@@ -38,7 +38,7 @@ def get_plan(lib, kind, B, H, W, cin, in_cs, cout, k, stride, block_n, w_tf=None
         w_tf = np.ascontiguousarray(w_tf, np.float32)
         if bias is not None:
             bias = np.ascontiguousarray(bias, np.float32)
-    rc = lib.ofs_debug_conv_plan(kind, B, H, W, cin, in_cs, cout, k, stride, block_n, 1,
+    rc = lib.ofs_debug_conv_plan(kind, B, H, W, cin, in_cs, cout, k, stride, block_n | (ksplit << 16), 1,
                                  None if w_tf is None else w_tf.ctypes.data_as(C.c_void_p),
                                  None if bias is None else bias.ctypes.data_as(C.c_void_p),
                                  C.cast(info, C.c_void_p), C.cast(taps, C.c_void_p),
@@ -57,24 +57,27 @@ def get_plan(lib, kind, B, H, W, cin, in_cs, cout, k, stride, block_n, w_tf=None
 
 
 def tma_box(flat, plan, c, x, pp, y, b, tileW):
-    """Box {64, tileW, 1, rpl, 1} of the 5-D view at signed start coords; OOB elements are zero."""
+    """Box {64, tileW, 1, box_y, box_b} of the 5-D view at signed start coords; OOB elements are zero.
+    Rows of the result are in TMA order: batch-major, then y, then x."""
     dims = [plan["d0"], plan["d1"], plan["d2"], plan["d3"], plan["d4"]]
     strides = [1, plan["s1"], plan["s2"], plan["s3"], plan["s4"]]
-    rpl = plan["rpl"]
-    out = np.zeros((rpl, tileW, 64), np.float32)
-    if not (0 <= pp < dims[2] and 0 <= b < dims[4]):
-        return out.reshape(rpl * tileW, 64)
+    by, bb = plan["box_y"], plan["box_b"]
+    out = np.zeros((bb, by, tileW, 64), np.float32)
+    if not (0 <= pp < dims[2]):
+        return out.reshape(bb * by * tileW, 64)
     ci = c + np.arange(64)
     xi = x + np.arange(tileW)
-    yi = y + np.arange(rpl)
+    yi = y + np.arange(by)
+    bi = b + np.arange(bb)
     cm = (ci >= 0) & (ci < dims[0])
     xm = (xi >= 0) & (xi < dims[1])
     ym = (yi >= 0) & (yi < dims[3])
-    off = (yi[:, None, None] * strides[3] + xi[None, :, None] * strides[1] + ci[None, None, :] * strides[0]
-           + pp * strides[2] + b * strides[4])
-    mask = ym[:, None, None] & xm[None, :, None] & cm[None, None, :]
+    bm = (bi >= 0) & (bi < dims[4])
+    off = (bi[:, None, None, None] * strides[4] + yi[None, :, None, None] * strides[3]
+           + xi[None, None, :, None] * strides[1] + ci[None, None, None, :] * strides[0] + pp * strides[2])
+    mask = bm[:, None, None, None] & ym[None, :, None, None] & xm[None, None, :, None] & cm[None, None, None, :]
     out[mask] = flat[off[mask]]
-    return out.reshape(rpl * tileW, 64)
+    return out.reshape(bb * by * tileW, 64)
 
 
 def emulate(plan, act):
@@ -82,43 +85,103 @@ def emulate(plan, act):
     [B,out_H,out_W,n_pad] = GEMM result + bias, exactly as the epilogue would scatter it."""
     flat = np.ascontiguousarray(act, np.float32).reshape(-1)
     tileW = 1 << plan["tileW_log2"]
-    tileH, rpl, Hg = plan["tileH"], plan["rpl"], plan["Hg"]
+    tile_rows, piece_rows, Hg = plan["tile_rows"], plan["piece_rows"], plan["Hg"]
     B = act.shape[0]
-    out = np.full((B, plan["out_H"], plan["out_W"], plan["n_pad"]), np.nan, np.float32)
+    out = np.full((B, plan["out_H"], plan["out_W"], plan["n_pad"]), np.nan, np.float64)
+    written = np.zeros((B, plan["out_H"], plan["out_W"], plan["n_pad"]), np.int32)
     num_kb = plan["ntaps"] * plan["nchunks"]
     BN = plan["block_n"]
-    total = plan["tiles_m"] * plan["tiles_n"] * plan["phases"]
+    assert plan["a_bytes"] == plan["npieces"] * piece_rows * tileW * 128
+    total = plan["tiles_m"] * plan["tiles_n"] * plan["phases"] * plan["ksplit"]
     oys = [plan["oy0"], plan["oy1"], plan["oy2"], plan["oy3"]]
     oxs = [plan["ox0"], plan["ox1"], plan["ox2"], plan["ox3"]]
     for tile in range(total):
         n_t = tile % plan["tiles_n"]
         rest = tile // plan["tiles_n"]
         m_t = rest % plan["tiles_m"]
-        ph = rest // plan["tiles_m"]
-        gy0 = (m_t // plan["tiles_x"]) * tileH
+        rest2 = rest // plan["tiles_m"]
+        ph = rest2 % plan["phases"]
+        ks = rest2 // plan["phases"]
+        gy0 = (m_t // plan["tiles_x"]) * tile_rows
         ox0 = (m_t % plan["tiles_x"]) << plan["tileW_log2"]
         w_row = ph * plan["n_pad"] + n_t * BN
         acc = np.zeros((128, BN), np.float64)
-        for kb in range(num_kb):
+        kb0 = ks * plan["kb_per_split"]
+        kb1 = min(num_kb, kb0 + plan["kb_per_split"])
+        assert kb1 > kb0, "empty split"
+        for kb in range(kb0, kb1):
             tap, ch = divmod(kb, plan["nchunks"])
             ti = ph * plan["ntaps"] + tap
-            A = np.zeros((128, 64), np.float32)
-            for pc in range(tileH // rpl):
-                gy = gy0 + pc * rpl
+            A = np.full((128, 64), 1e30, np.float32)     # rows no TMA box writes hold garbage on the device
+            for pc in range(plan["npieces"]):
+                gy = gy0 + pc * piece_rows
                 b = gy // Hg
                 y = gy - b * Hg + plan["tap_y"][ti]
-                A[pc * rpl * tileW:(pc + 1) * rpl * tileW] = tma_box(
+                A[pc * piece_rows * tileW:(pc + 1) * piece_rows * tileW] = tma_box(
                     flat, plan, plan["tap_c"][ti] + ch * 64, ox0 + plan["tap_x"][ti], plan["tap_p"][ti], y, b, tileW)
             Wt = plan["w"][w_row:w_row + BN, kb * 64:(kb + 1) * 64]
             acc += A.astype(np.float64) @ Wt.astype(np.float64).T
         for row in range(128):
-            gy = gy0 + (row >> plan["tileW_log2"])
+            ty = row >> plan["tileW_log2"]
+            gy = gy0 + ty
             gx = ox0 + (row & (tileW - 1))
-            if gy >= plan["rows_total"]:
+            if ty >= tile_rows or gy >= plan["rows_total"]:
                 continue
             b = gy // Hg
             y = gy - b * Hg
             oy = y * plan["out_scale"] + oys[ph]
             ox = gx * plan["out_scale"] + oxs[ph]
-            out[b, oy, ox, n_t * BN:(n_t + 1) * BN] = acc[row] + plan["b"][n_t * BN:(n_t + 1) * BN]
-    return out
+            sl = (b, oy, ox, slice(n_t * BN, (n_t + 1) * BN))
+            if ks == 0:
+                out[sl] = plan["b"][n_t * BN:(n_t + 1) * BN]      # the reduction adds the bias once
+            written[sl] += 1
+    # second pass so that split order does not matter: accumulate partials
+    return _accumulate(plan, act, out, written)
+
+
+def _accumulate(plan, act, out, written):
+    """Adds the partial sums of every (tile, split) onto the bias-initialised output."""
+    flat = np.ascontiguousarray(act, np.float32).reshape(-1)
+    tileW = 1 << plan["tileW_log2"]
+    tile_rows, piece_rows, Hg = plan["tile_rows"], plan["piece_rows"], plan["Hg"]
+    num_kb = plan["ntaps"] * plan["nchunks"]
+    BN = plan["block_n"]
+    total = plan["tiles_m"] * plan["tiles_n"] * plan["phases"] * plan["ksplit"]
+    oys = [plan["oy0"], plan["oy1"], plan["oy2"], plan["oy3"]]
+    oxs = [plan["ox0"], plan["ox1"], plan["ox2"], plan["ox3"]]
+    assert (written[~np.isnan(out)] == plan["ksplit"]).all(), "every output must receive exactly ksplit partials"
+    for tile in range(total):
+        n_t = tile % plan["tiles_n"]
+        rest = tile // plan["tiles_n"]
+        m_t = rest % plan["tiles_m"]
+        rest2 = rest // plan["tiles_m"]
+        ph = rest2 % plan["phases"]
+        ks = rest2 // plan["phases"]
+        gy0 = (m_t // plan["tiles_x"]) * tile_rows
+        ox0 = (m_t % plan["tiles_x"]) << plan["tileW_log2"]
+        w_row = ph * plan["n_pad"] + n_t * BN
+        acc = np.zeros((128, BN), np.float64)
+        kb0 = ks * plan["kb_per_split"]
+        kb1 = min(num_kb, kb0 + plan["kb_per_split"])
+        for kb in range(kb0, kb1):
+            tap, ch = divmod(kb, plan["nchunks"])
+            ti = ph * plan["ntaps"] + tap
+            A = np.zeros((128, 64), np.float32)
+            for pc in range(plan["npieces"]):
+                gy = gy0 + pc * piece_rows
+                b = gy // Hg
+                y = gy - b * Hg + plan["tap_y"][ti]
+                A[pc * piece_rows * tileW:(pc + 1) * piece_rows * tileW] = tma_box(
+                    flat, plan, plan["tap_c"][ti] + ch * 64, ox0 + plan["tap_x"][ti], plan["tap_p"][ti], y, b, tileW)
+            Wt = plan["w"][w_row:w_row + BN, kb * 64:(kb + 1) * 64]
+            acc += A.astype(np.float64) @ Wt.astype(np.float64).T
+        for row in range(128):
+            ty = row >> plan["tileW_log2"]
+            gy = gy0 + ty
+            gx = ox0 + (row & (tileW - 1))
+            if ty >= tile_rows or gy >= plan["rows_total"]:
+                continue
+            b = gy // Hg
+            y = gy - b * Hg
+            out[b, y * plan["out_scale"] + oys[ph], gx * plan["out_scale"] + oxs[ph], n_t * BN:(n_t + 1) * BN] += acc[row]
+    return out.astype(np.float32)

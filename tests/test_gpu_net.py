@@ -1,0 +1,231 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution and of the whole FlowNetS-pyramid forward
+(through the C ABI) against the CPU oracle.
+
+Tolerances
+  * single conv layer, operands pre-rounded to the 16-bit format: the only differences are the fp32
+    accumulation order of the tensor core -> |err| <= 2e-3 * (1 + |ref|).
+  * whole network vs the bf16-emulating oracle (same rounding points, fp64 accumulate): per-layer mean
+    relative error <= 1e-2 (a wrong tap / channel / swizzle gives O(1)).
+  * whole network vs the fp32 oracle (BASELINE.json north star): mean EPE(predict_flow2) <= 2e-2 px on the
+    calibrated weight set (head_scale 0.02, mean |flow2| ~ 1.7 px; EPE/|flow| is reported too).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import flownet as F
+from oracle import tf1_ops as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ofs(cuda_dev):
+    import coupe.optical_flow_based_deep_video_stabilization_b200 as m
+
+    m.load_library()
+    return m
+
+
+def _round(x, prec):
+    return x.to(torch.bfloat16 if prec == "bf16" else torch.float16).to(torch.float32)
+
+
+CONV_CASES = [
+    # B, H, W, cin, cout, k, stride, transposed
+    pytest.param(2, 6, 8, 64, 16, 3, 1, False, id="tiny_k3s1"),
+    pytest.param(2, 6, 8, 70, 32, 3, 1, False, id="ragged_channels"),
+    pytest.param(3, 6, 8, 128, 128, 3, 1, False, id="ragged_batch_n128"),
+    pytest.param(1, 48, 64, 256, 256, 3, 1, False, id="conv3_1_shape"),
+    pytest.param(1, 24, 32, 128, 64, 3, 2, False, id="k3s2"),
+    pytest.param(2, 32, 64, 64, 128, 5, 2, False, id="k5s2"),
+    pytest.param(1, 64, 128, 27, 64, 7, 2, False, id="conv1_form_paired"),
+    pytest.param(2, 6, 8, 128, 64, 4, 2, True, id="deconv"),
+    pytest.param(1, 12, 16, 130, 128, 4, 2, True, id="deconv_ragged_channels"),
+    pytest.param(1, 16, 32, 194, 18, 1, 1, False, id="predict2_product"),
+    pytest.param(1, 12, 16, 1026, 2, 3, 1, False, id="flow_head"),
+    pytest.param(1, 8, 256, 64, 64, 3, 1, False, id="two_tiles_per_row"),
+]
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("B,H,W,cin,cout,k,stride,transposed", CONV_CASES)
+def test_conv_gemm_vs_oracle(ofs, cuda_dev, prec, B, H, W, cin, cout, k, stride, transposed):
+    gen = torch.Generator().manual_seed(B * 1000 + H * 10 + k)
+    x = _round(torch.rand((B, H, W, cin), generator=gen), prec)
+    if transposed:
+        w = _round(torch.randn((4, 4, cout, cin), generator=gen) * (1.0 / np.sqrt(4 * cin)), prec)
+    else:
+        w = _round(torch.randn((k, k, cin, cout), generator=gen) * (1.0 / np.sqrt(k * k * cin)), prec)
+    b = torch.randn(cout, generator=gen) * 0.1
+    for lrelu in (False, True):
+        got = ofs.conv2d_nhwc(x.to(cuda_dev), w, b, stride=stride, transposed=transposed, lrelu=lrelu, precision=prec).cpu()
+        if transposed:
+            ref = T.conv2d_transpose_k4s2_same(x.double(), w.double(), b.double())
+        else:
+            ref = T.conv2d_valid(T.pad_constant(x.double(), k // 2), w.double(), b.double(), stride)
+        if lrelu:
+            ref = T.lrelu(ref, 0.1)
+        ref = ref.float()
+        assert got.shape == ref.shape
+        err = (got - ref).abs()
+        assert float((err / (1 + ref.abs())).max()) <= 2e-3, float(err.max())
+
+
+TILING_CASES = [
+    # B, H, W, cin, cout, k, stride, transposed, block_n, ksplit
+    pytest.param(4, 6, 8, 512, 256, 3, 1, False, 128, 4, id="splitk4_whole_image_tiles"),
+    pytest.param(3, 6, 8, 256, 128, 3, 1, False, 128, 1, id="whole_image_tiles_ragged_batch"),
+    pytest.param(2, 12, 16, 256, 128, 3, 2, False, 128, 3, id="splitk3_k3s2"),
+    pytest.param(2, 6, 8, 256, 128, 4, 2, True, 128, 5, id="splitk5_deconv_uneven"),
+    pytest.param(1, 48, 64, 256, 256, 3, 1, False, 256, 1, id="block_n256"),
+    pytest.param(2, 24, 32, 128, 512, 3, 1, False, 256, 2, id="block_n256_splitk2"),
+    pytest.param(1, 24, 32, 128, 64, 3, 1, False, 32, 1, id="block_n32_two_n_tiles"),
+]
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,k,stride,transposed,block_n,ksplit", TILING_CASES)
+def test_conv_gemm_tilings(ofs, cuda_dev, B, H, W, cin, cout, k, stride, transposed, block_n, ksplit):
+    """Explicit block_n / split-K variants of the same kernel (split-K output carries one bf16 rounding)."""
+    gen = torch.Generator().manual_seed(77 + block_n + ksplit)
+    x = _round(torch.rand((B, H, W, cin), generator=gen), "bf16")
+    shape = (4, 4, cout, cin) if transposed else (k, k, cin, cout)
+    w = _round(torch.randn(shape, generator=gen) * (1.0 / np.sqrt(k * k * cin)), "bf16")
+    b = torch.randn(cout, generator=gen) * 0.1
+    got = ofs.conv2d_nhwc(x.to(cuda_dev), w, b, stride=stride, transposed=transposed, lrelu=True, precision="bf16",
+                          block_n=block_n, ksplit=ksplit).cpu()
+    if transposed:
+        ref = T.conv2d_transpose_k4s2_same(x.double(), w.double(), b.double())
+    else:
+        ref = T.conv2d_valid(T.pad_constant(x.double(), k // 2), w.double(), b.double(), stride)
+    ref = T.lrelu(ref, 0.1).float()
+    tol = 6e-3 if ksplit > 1 else 2e-3
+    assert float(((got - ref).abs() / (1 + ref.abs())).max()) <= tol
+
+
+@pytest.fixture(scope="module")
+def net_case(ofs, cuda_dev):
+    w = F.make_weights(0, "calibrated", head_scale=0.02)
+    x = F.make_feats(2, 2)
+    net = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=2, precision="bf16")
+    net.assign_weights(w)
+    out = net.forward(x.to(cuda_dev))
+    torch.cuda.synchronize()
+    return w, x, net, out
+
+
+ACTS = ["conv1", "conv2", "conv3", "conv3_1", "conv4", "conv4_1", "conv5", "conv5_1", "conv6", "conv6_1",
+        "concat5", "concat4", "concat3", "concat2"]
+
+
+def test_network_per_layer_vs_bf16_emulating_oracle(net_case):
+    w, x, net, out = net_case
+    ref = F.forward_folded(x, F.fold_bn(w), emulate_bf16=True, keep=True)
+    report = []
+    for name in ["input"] + ACTS:
+        got = net.activation(name, 2).cpu()
+        exp = (F.round_bf16(x) if name == "input" else ref["_acts"][name]).float()
+        assert got.shape == exp.shape, name
+        rel = float((got - exp).abs().mean() / (exp.abs().mean() + 1e-12))
+        report.append((name, rel))
+        assert rel <= 1e-2, (name, rel, report)
+    for lvl in (6, 5, 4, 3, 2):
+        k = f"predict_flow{lvl}"
+        e = F.epe(out[k].cpu(), ref[k])
+        mag = float(torch.sqrt((ref[k] ** 2).sum(-1)).mean())
+        assert e <= 1e-2 * max(mag, 0.1) + 1e-3, (k, e, mag)
+
+
+def test_network_epe_vs_fp32_oracle_bf16(net_case):
+    w, x, net, out = net_case
+    ref = F.forward_literal(x, w)
+    mag = float(torch.sqrt((ref["predict_flow2"] ** 2).sum(-1)).mean())
+    e = F.epe(out["predict_flow2"].cpu(), ref["predict_flow2"])
+    print(f"bf16: mean EPE(predict_flow2) = {e:.5f} px, mean |flow2| = {mag:.3f} px, EPE/|flow| = {e / mag:.4%}")
+    assert e <= 2e-2, (e, mag)
+    assert out["flow"].data_ptr() == out["predict_flow2"].data_ptr()
+    for lvl, hw in {6: (6, 8), 5: (12, 16), 4: (24, 32), 3: (48, 64), 2: (382, 510)}.items():
+        assert tuple(out[f"predict_flow{lvl}"].shape) == (2,) + hw + (2,)
+
+
+def test_network_epe_fp16_operands_larger_flows(ofs, cuda_dev):
+    """fp16 operands (same tensor rate) hold the 2e-2 px bound at 4x larger flows (|flow2| ~ 7 px)."""
+    w = F.make_weights(0, "calibrated", head_scale=0.08)
+    x = F.make_feats(4, 1)
+    net = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=1, precision="fp16")
+    net.assign_weights(w)
+    out = net.forward(x.to(cuda_dev))
+    ref = F.forward_literal(x, w)
+    mag = float(torch.sqrt((ref["predict_flow2"] ** 2).sum(-1)).mean())
+    e = F.epe(out["predict_flow2"].cpu(), ref["predict_flow2"])
+    print(f"fp16: mean EPE(predict_flow2) = {e:.5f} px, mean |flow2| = {mag:.3f} px, EPE/|flow| = {e / mag:.4%}")
+    assert e <= 2e-2, (e, mag)
+    net.close()
+
+
+def test_network_he_init_relative_epe(ofs, cuda_dev):
+    """Reference initialisers (stress case, |flow2| tens of pixels): report and bound EPE/|flow|."""
+    w = F.make_weights(0, "he")
+    x = F.make_feats(6, 1)
+    net = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=1, precision="bf16")
+    net.assign_weights(w)
+    out = net.forward(x.to(cuda_dev))
+    ref = F.forward_literal(x, w)
+    mag = float(torch.sqrt((ref["predict_flow2"] ** 2).sum(-1)).mean())
+    e = F.epe(out["predict_flow2"].cpu(), ref["predict_flow2"])
+    print(f"he-init bf16: EPE = {e:.4f} px, |flow2| = {mag:.2f} px, EPE/|flow| = {e / mag:.4%}")
+    assert e / mag <= 1.5e-2
+    net.close()
+
+
+def test_batch_independence_and_determinism(net_case, cuda_dev):
+    """Frame pairs are independent units: a pair's result must not depend on its batch neighbours."""
+    w, x, net, out = net_case
+    o1 = net.forward(x[1:2].to(cuda_dev))
+    assert torch.equal(o1["predict_flow2"], net.forward(x[1:2].to(cuda_dev))["predict_flow2"])
+    torch.testing.assert_close(o1["predict_flow2"][0], out["predict_flow2"][1], rtol=0, atol=0)
+    with pytest.raises(RuntimeError):
+        net.forward(torch.zeros(3, 384, 512, 27, device=cuda_dev))                   # > max_batch
+    with pytest.raises(ValueError):
+        net.forward(torch.zeros(1, 256, 256, 27, device=cuda_dev))                   # model.py:850 hard-wires 384x512
+
+
+def test_reference_signature_and_stabilize(ofs, cuda_dev, net_case):
+    """flownetS_pyramid(feats, batch_size, is_train=False) + tf_warp == fused stabilize == host-buffer call."""
+    from oracle import samplers as S
+
+    w, x, net, out = net_case
+    with pytest.raises(RuntimeError):
+        ofs.flownetS_pyramid(x.to(cuda_dev), 2, scope="never_loaded")
+    ofs.assign_weights(w, scope="flownetS", device=cuda_dev, max_batch=2)
+    o = ofs.flownetS_pyramid(x.to(cuda_dev), 2, is_train=False)
+    assert set(o) == {"predict_flow6", "predict_flow5", "predict_flow4", "predict_flow3", "predict_flow2", "flow"}
+    torch.testing.assert_close(o["predict_flow2"], out["predict_flow2"], rtol=0, atol=0)
+    with pytest.raises(NotImplementedError):
+        ofs.flownetS_pyramid(x.to(cuda_dev), 2, is_train=True)
+    H, W = 256, 256                                                                  # BASELINE configs[0] frame size
+    gen = torch.Generator().manual_seed(1)
+    frames = torch.rand((2, H, W, 3), generator=gen)
+    outflow = ofs.flow_resize(o["predict_flow2"], H, W)
+    two_step = ofs.tf_warp(frames.to(cuda_dev), outflow, H, W)
+    fused, f2 = net.stabilize(x.to(cuda_dev), frames.to(cuda_dev), return_flow=True)
+    torch.testing.assert_close(f2, out["predict_flow2"], rtol=0, atol=0)
+    assert float(((fused - two_step).abs() > 1e-5).float().mean()) < 1e-4
+    host = net.stabilize_host(x.pin_memory(), frames.pin_memory())
+    torch.testing.assert_close(host, fused.cpu(), rtol=0, atol=0)
+    ref = S.flow_resize_warp(frames, out["predict_flow2"].cpu(), H, W)               # oracle warp on the GPU's flow
+    assert float(((fused.cpu() - ref).abs() > 1e-3).float().mean()) < 1e-4
+
+
+def test_missing_weight_is_an_error(ofs, cuda_dev):
+    w = F.make_weights(0, "he")
+    del w["4_1/W_conv2d"]
+    net = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=1)
+    with pytest.raises(ofs.OfstabError):
+        net.assign_weights(w)
+    with pytest.raises(ofs.OfstabError):
+        net.forward(torch.zeros(1, 384, 512, 27, device=cuda_dev))                   # forward before weights
+    # names with the checkpoint's scope prefix and ':0' suffix are accepted
+    w = {f"main_net/flownetS/{k}:0": v for k, v in F.make_weights(0, "he").items()}
+    net.assign_weights(w)
+    net.close()

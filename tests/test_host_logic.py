@@ -88,8 +88,20 @@ CONV_CASES = [
 ]
 
 
+SPLITK_CASES = [
+    pytest.param(0, 3, 6, 8, 256, 256, 32, 3, 1, 32, 4, id="splitk4_whole_image_tiles"),
+    pytest.param(0, 2, 12, 16, 128, 136, 16, 3, 2, 16, 3, id="splitk3_k3s2"),
+    pytest.param(1, 2, 6, 8, 130, 136, 32, 4, 2, 32, 5, id="splitk5_deconv_uneven"),
+]
+
+
+@pytest.mark.parametrize("kind,B,H,W,cin,in_cs,cout,k,stride,bn,ks", SPLITK_CASES)
+def test_conv_plan_splitk_emulation(lib, kind, B, H, W, cin, in_cs, cout, k, stride, bn, ks):
+    test_conv_plan_emulation_matches_oracle(lib, kind, B, H, W, cin, in_cs, cout, k, stride, bn, ks)
+
+
 @pytest.mark.parametrize("kind,B,H,W,cin,in_cs,cout,k,stride,bn", CONV_CASES)
-def test_conv_plan_emulation_matches_oracle(lib, kind, B, H, W, cin, in_cs, cout, k, stride, bn):
+def test_conv_plan_emulation_matches_oracle(lib, kind, B, H, W, cin, in_cs, cout, k, stride, bn, ks=1):
     rng = np.random.RandomState(1234 + k * 7 + stride)
     x = emu.bf16_round(rng.rand(B, H, W, cin).astype(np.float32))
     if kind == 0:
@@ -97,7 +109,9 @@ def test_conv_plan_emulation_matches_oracle(lib, kind, B, H, W, cin, in_cs, cout
     else:
         w = emu.bf16_round(rng.randn(4, 4, cout, cin).astype(np.float32) * 0.1)
     b = rng.randn(cout).astype(np.float32)
-    plan = emu.get_plan(lib, kind, B, H, W, cin, in_cs, cout, k, stride, bn, w, b)
+    plan = emu.get_plan(lib, kind, B, H, W, cin, in_cs, cout, k, stride, bn, w, b, ksplit=ks)
+    if ks > 1:
+        assert 1 < plan["ksplit"] <= ks
     act = np.zeros((B, H, W, in_cs), np.float32)
     act[..., :cin] = x
     act[..., cin:] = 7.0  # other layers' channels in the same buffer must never leak into this GEMM
@@ -126,16 +140,18 @@ def test_network_layer_plans_are_valid(lib):
         for (kind, H, W, cin, in_cs, cout, k, s, bn) in layers:
             p = emu.get_plan(lib, kind, B, H, W, cin, in_cs, cout, k, s, bn)
             tileW = 1 << p["tileW_log2"]
-            assert tileW * p["tileH"] == 128 and p["tileH"] % p["rpl"] == 0 and p["Hg"] % p["rpl"] == 0
-            assert (p["rpl"] * tileW) % 8 == 0, "TMA piece must be whole 1024-byte swizzle atoms"
-            assert p["tiles_m"] * 128 >= B * p["Hg"] * p["Wg"]
+            assert tileW * p["tile_rows"] <= 128 and p["npieces"] * p["piece_rows"] == p["tile_rows"]
+            assert p["piece_rows"] == p["box_y"] * p["box_b"]
+            assert p["box_b"] > 1 or p["Hg"] % p["box_y"] == 0, "a piece must not straddle two images"
+            assert (p["piece_rows"] * tileW) % 8 == 0, "TMA piece must be whole 1024-byte swizzle atoms"
+            assert p["tiles_m"] * p["tile_rows"] * tileW >= B * p["Hg"] * p["Wg"]
             assert p["k_total"] == p["ntaps"] * p["nchunks"] * 64 and p["nchunks"] * 64 >= (cin if not p["paired"] else 64)
             assert p["smem"] <= 227 * 1024 and 1 <= p["grid"] <= 148 or p["grid"] >= 1
             assert p["w_rows"] == p["phases"] * p["n_pad"] and p["n_pad"] % bn == 0
 
 
 def test_plan_rejects_unsupported_shapes(lib):
-    info, taps = (C.c_int * 40)(), (C.c_short * 256)()
+    info, taps = (C.c_int * 44)(), (C.c_short * 256)()
 
     def rc(*a):
         return lib.ofs_debug_conv_plan(*a, 1, None, None, C.cast(info, C.c_void_p), C.cast(taps, C.c_void_p), None, 0, None)
