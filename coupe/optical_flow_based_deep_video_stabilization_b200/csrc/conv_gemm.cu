@@ -38,17 +38,6 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kThreads = 192;
 
-template <int BLOCK_N>
-struct GemmCfg {
-  static constexpr int kStages = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8);
-  static constexpr int kABytes = kBlockM * kBlockK * 2;
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
-  static constexpr int kBarBytes = 256;
-  static constexpr size_t kSmem = (size_t)kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
-};
-
 __device__ __forceinline__ uint32_t pack16(float a, float b, int is_bf16) {
   if (is_bf16) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -58,140 +47,298 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int is_bf16) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+// One epilogue chunk of one GEMM row: kChunk accumulator columns starting at column `col0` of the layer.
+template <int kChunk>
+__device__ __forceinline__ void epilogue_store(const ConvGemmParams& p, const uint32_t* v, size_t pix, int col0,
+                                               int ks) {
+  const float* bias = p.bias + col0;
+  if (p.out_mode == 0) {
+    uint32_t pk[kChunk / 2];
+#pragma unroll
+    for (int j = 0; j < kChunk / 2; ++j) {
+      float a = __uint_as_float(v[2 * j]) + __ldg(bias + 2 * j);
+      float c = __uint_as_float(v[2 * j + 1]) + __ldg(bias + 2 * j + 1);
+      if (p.lrelu) { a = fmaxf(a, 0.1f * a); c = fmaxf(c, 0.1f * c); }
+      pk[j] = pack16(a, c, p.is_bf16);
+    }
+    uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + pix * p.out_cstride + p.out_coff + col0;
+    uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+    for (int j = 0; j < kChunk / 8; ++j) o4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  } else if (p.out_mode == 2) {
+    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)ks * p.ws_split_stride +
+                                           pix * p.n_pad + col0);
+#pragma unroll
+    for (int j = 0; j < kChunk / 4; ++j)
+      o4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                          __uint_as_float(v[4 * j + 3]));
+  } else {
+    float* o = reinterpret_cast<float*>(p.out) + pix * p.out_cstride + p.out_coff;
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) {
+      const int col = col0 + j;
+      if (col < p.n_valid) {
+        float a = __uint_as_float(v[j]) + __ldg(bias + j);
+        if (p.lrelu) a = fmaxf(a, 0.1f * a);
+        o[col] = a;
+      }
+    }
+  }
+}
+
+// Tile configuration.  kPair = CTA pairs (tcgen05 cta_group::2): a pair computes 256 GEMM rows x BLOCK_N, each
+// CTA TMA-loads the A tile of its own 128 rows and HALF of the B tile; the leader (cluster rank 0) issues one
+// M=256 MMA reading both CTAs' shared memory; D rows 0-127 land in the leader's TMEM, rows 128-255 in the peer's.
+template <int BLOCK_N, bool kPair>
+struct GemmCfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = (BLOCK_N / (kPair ? 2 : 1)) * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+  static constexpr int kBarBytes = 256;
+  static constexpr size_t kSmem = (size_t)kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+};
+
+// The TMA-producer and MMA-issuer roles are single threads running dependent-issue code (~4-5 cycles per
+// instruction): every instruction in their per-K-block loops costs.  These wrappers work on 32-bit shared
+// addresses kept in registers (no generic->shared conversion per call), and the loops below only add constants
+// to running addresses / descriptors.
+namespace lean {
+__device__ __forceinline__ void wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  if (ok) return;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) __trap();  // protocol bug -> launch error, never a hung GPU
+  }
+}
+__device__ __forceinline__ void expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+template <bool kPair>
+__device__ __forceinline__ void tma5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3,
+                                      int c4) {
+  if constexpr (kPair)
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+        "%5, %6, %7}], [%2];" ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+        "[%2];" ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+template <bool kPair>
+__device__ __forceinline__ void tma2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  if constexpr (kPair)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1) : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(m), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+template <bool kPair>
+__device__ __forceinline__ void commit(uint32_t bar) {
+  if constexpr (kPair)
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <bool kPair>
+__device__ __forceinline__ void mma(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kPair)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+                 "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+                 "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+}  // namespace lean
+
+//   barriers  full[s]   TMA -> MMA.  Pair: leader only; both producers' TMA bytes land on it (one
+//                       arrive.expect_tx by the leader's producer).
+//             empty[s]  MMA -> TMA, one per CTA; pair: released in both CTAs by the leader's multicast commit.
+//             tfull[a]  MMA -> epilogue, one per CTA (multicast commit after the last K block).
+//             tempty[a] epilogue -> MMA: 4 arrivals (1 CTA) / 8 (pair: the peer's warps arrive remotely).
+template <int BLOCK_N, bool kPair>
+__device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
+  using Cfg = GemmCfg<BLOCK_N, kPair>;
+  constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* full = bars;                         // [kStages]  TMA -> MMA
-  uint64_t* empty = bars + Cfg::kStages;         // [kStages]  MMA -> TMA
-  uint64_t* tfull = bars + 2 * Cfg::kStages;     // [2]        MMA -> epilogue
-  uint64_t* tempty = bars + 2 * Cfg::kStages + 2;  // [2]      epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * Cfg::kStageBytes);
+  uint64_t* full = bars;             // [S]
+  uint64_t* empty = bars + S;        // [S]
+  uint64_t* tfull = bars + 2 * S;    // [2]
+  uint64_t* tempty = bars + 2 * S + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = kPair ? ptx::cluster_ctarank() : 0u;
+  const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // scheduling unit: CTA or CTA pair
+  const int nunits = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&p.tmap_a);
     ptx::prefetch_tensormap(&p.tmap_w);
-    for (int i = 0; i < Cfg::kStages; ++i) {
+    for (int i = 0; i < S; ++i) {
       ptx::mbar_init(&full[i], 1);
       ptx::mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull[i], 1);
-      ptx::mbar_init(&tempty[i], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&tempty[i], kPair ? 8 : 4);  // one arrive per epilogue warp (of both CTAs)
     }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    ptx::tmem_relinquish();
+    if constexpr (kPair) { ptx::tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols); ptx::tmem_relinquish_2sm(); }
+    else { ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) ptx::cluster_sync();  // the peer's barriers exist before anything signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_kb = p.ntaps * p.nchunks;
-  const int total_tiles = p.tiles_m * p.tiles_n * p.phases * p.ksplit;
+  const int total_tiles = p.tiles_mp * p.tiles_n * p.phases * p.ksplit;
   const int tileW = 1 << p.tileW_log2;
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const uint32_t full0 = ptx::smem_u32(full), empty0 = ptx::smem_u32(empty);
 
   if (warp == 0) {
     if (lane == 0) {
-      // ================================ TMA producer ================================
+      // ===================================== TMA producer =====================================
+      const bool do_a = !(p.debug & 2), do_b = !(p.debug & 4);
+      const uint32_t stage_tx = (kPair ? 2u : 1u) * (uint32_t)((do_a ? p.a_bytes : 0) + (do_b ? Cfg::kBBytes : 0));
+      const uint32_t full_tgt0 = kPair ? ptx::mapa_u32(full0, 0) : full0;   // where TMA bytes are posted
+      const int piece_bytes = p.piece_rows * tileW * kBlockK * 2;
+      const int npieces = p.npieces;
       int stage = 0;
       uint32_t phase = 0;
-      const int npieces = p.npieces;
-      const int piece_bytes = p.piece_rows * tileW * kBlockK * 2;
-      const uint32_t stage_tx = (uint32_t)(p.a_bytes + Cfg::kBBytes);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      uint32_t sa = smem_base, full_s = full0, empty_s = empty0, full_t = full_tgt0;
+      for (int tile = unit; tile < total_tiles; tile += nunits) {
         const int n_t = tile % p.tiles_n;
         const int rest = tile / p.tiles_n;
-        const int m_t = rest % p.tiles_m;
-        const int rest2 = rest / p.tiles_m;
+        const int m_t = kPair ? (rest % p.tiles_mp) * 2 + (int)rank : rest % p.tiles_mp;
+        const int rest2 = rest / p.tiles_mp;
         const int ph = rest2 % p.phases;
         const int ks = rest2 / p.phases;
         const int gy0 = (m_t / p.tiles_x) * p.tile_rows;
         const int ox0 = (m_t % p.tiles_x) << p.tileW_log2;
-        const int w_row = ph * p.n_pad + n_t * BLOCK_N;
-        const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(num_kb, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          const int tap = kb / p.nchunks;
-          const int ch = kb - tap * p.nchunks;
+        const int w_row = ph * p.n_pad + n_t * BLOCK_N + (kPair ? (int)rank * (BLOCK_N / 2) : 0);
+        const int b0 = gy0 / p.Hg;
+        const int y0 = gy0 - b0 * p.Hg;
+        int kb = ks * p.kb_per_split;
+        const int kb1 = min(num_kb, kb + p.kb_per_split);
+        int tap = kb / p.nchunks;
+        int ch = kb - tap * p.nchunks;
+        int kcol = kb * kBlockK;
+        while (kb < kb1) {
+          // per tap: everything but the channel offset is fixed
           const int ti = ph * p.ntaps + tap;
-          ptx::mbar_wait(&empty[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full[stage], stage_tx);
-          uint8_t* sa = smem + (size_t)stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
-          const int c = p.tap_c[ti] + ch * kBlockK;
+          int c = p.tap_c[ti] + ch * kBlockK;
           const int x = ox0 + p.tap_x[ti];
           const int pp = p.tap_p[ti];
-          for (int pc = 0; pc < npieces; ++pc) {
-            const int gy = gy0 + pc * p.piece_rows;
-            const int b = gy / p.Hg;
-            const int y = gy - b * p.Hg + p.tap_y[ti];
-            ptx::tma_load_5d(sa + (size_t)pc * piece_bytes, &p.tmap_a, &full[stage], c, x, pp, y, b);
+          const int yy = y0 + p.tap_y[ti];
+          const int ch_end = min(p.nchunks, ch + (kb1 - kb));
+          for (; ch < ch_end; ++ch, ++kb) {
+            lean::wait(empty_s, phase ^ 1);
+            if (!kPair || rank == 0) lean::expect_tx(full_s, stage_tx);
+            if (do_a) {
+              if (npieces == 1) {
+                lean::tma5d<kPair>(sa, &p.tmap_a, full_t, c, x, pp, yy, b0);
+              } else {
+                int b = b0, y = yy;
+                const int ylim = p.Hg + p.tap_y[ti];
+                uint32_t dst = sa;
+                for (int pc = 0; pc < npieces; ++pc) {
+                  lean::tma5d<kPair>(dst, &p.tmap_a, full_t, c, x, pp, y, b);
+                  dst += piece_bytes;
+                  y += p.piece_rows;
+                  if (y >= ylim) { y -= p.Hg; ++b; }
+                }
+              }
+            }
+            if (do_b) lean::tma2d<kPair>(sa + Cfg::kABytes, &p.tmap_w, full_t, kcol, w_row);
+            c += kBlockK;
+            kcol += kBlockK;
+            sa += Cfg::kStageBytes; full_s += 8; empty_s += 8; full_t += 8;
+            if (++stage == S) { stage = 0; phase ^= 1; sa = smem_base; full_s = full0; empty_s = empty0; full_t = full_tgt0; }
           }
-          ptx::tma_load_2d(sb, &p.tmap_w, &full[stage], kb * kBlockK, w_row);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          ch = 0;
+          ++tap;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================================ MMA issuer ==================================
-      const uint32_t idesc = ptx::umma_idesc_f16(kBlockM, BLOCK_N, p.is_bf16);
+    if (lane == 0 && rank == 0) {
+      // ====================================== MMA issuer ======================================
+      const uint32_t idesc = ptx::umma_idesc_f16(kPair ? 2 * kBlockM : kBlockM, BLOCK_N, p.is_bf16);
+      const uint64_t da0 = ptx::umma_desc_sw128(smem_base), db0 = ptx::umma_desc_sw128(smem_base + Cfg::kABytes);
+      constexpr uint64_t kStep = (uint64_t)(Cfg::kStageBytes >> 4);   // descriptor address field is in 16-byte units
+      const bool do_mma = !(p.debug & 1);
+      const uint32_t tfull0 = ptx::smem_u32(tfull), tempty0 = ptx::smem_u32(tempty);
       int stage = 0;
       uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+      uint64_t da = da0, db = db0;
+      uint32_t full_s = full0, empty_s = empty0;
+      uint32_t acc = 0, acc_phase = 0;
+      for (int tile = unit; tile < total_tiles; tile += nunits) {
+        lean::wait(tempty0 + 8 * acc, acc_phase ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-        const int ks = tile / (p.tiles_n * p.tiles_m * p.phases);
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        const int ks = tile / (p.tiles_n * p.tiles_mp * p.phases);
         const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(num_kb, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          ptx::mbar_wait(&full[stage], phase);
+        const int nkb = min(num_kb, kb0 + p.kb_per_split) - kb0;
+        for (int i = 0; i < nkb; ++i) {
+          lean::wait(full_s, phase);
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(smem + (size_t)stage * Cfg::kStageBytes);
-          const uint32_t b_addr = a_addr + Cfg::kABytes;
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t da = ptx::umma_desc_sw128(a_addr + k * 32);
-            const uint64_t db = ptx::umma_desc_sw128(b_addr + k * 32);
-            ptx::tc_mma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          if (do_mma) {
+            lean::mma<kPair>(d_tmem, da, db, idesc, i > 0 ? 1u : 0u);   // 4 x K=16 inside the 128-byte swizzle row
+            lean::mma<kPair>(d_tmem, da + 2, db + 2, idesc, 1u);
+            lean::mma<kPair>(d_tmem, da + 4, db + 4, idesc, 1u);
+            lean::mma<kPair>(d_tmem, da + 6, db + 6, idesc, 1u);
           }
-          ptx::tc_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          lean::commit<kPair>(empty_s);   // the stage is reusable (in both CTAs) once these MMAs have read it
+          da += kStep; db += kStep; full_s += 8; empty_s += 8;
+          if (++stage == S) { stage = 0; phase ^= 1; da = da0; db = db0; full_s = full0; empty_s = empty0; }
         }
-        ptx::tc_commit(&tfull[acc]);  // accumulator complete
+        lean::commit<kPair>(tfull0 + 8 * acc);   // accumulator complete
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     }
   } else {
-    // ================================== epilogue ====================================
+    // ============================== epilogue (own 128 rows of every tile) =====================
     const int quad = warp & 3;           // TMEM lane quadrant this warp may read
-    const int row = quad * 32 + lane;    // GEMM row inside the tile
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int row = quad * 32 + lane;    // GEMM row inside this CTA's tile
+    uint32_t acc = 0, acc_phase = 0;
+    const uint32_t tfull0 = ptx::smem_u32(tfull);
+    const uint32_t tempty_tgt0 = kPair ? ptx::mapa_u32(ptx::smem_u32(tempty), 0) : ptx::smem_u32(tempty);
+    for (int tile = unit; tile < total_tiles; tile += nunits) {
       const int n_t = tile % p.tiles_n;
       const int rest = tile / p.tiles_n;
-      const int m_t = rest % p.tiles_m;
-      const int rest2 = rest / p.tiles_m;
+      const int m_t = kPair ? (rest % p.tiles_mp) * 2 + (int)rank : rest % p.tiles_mp;
+      const int rest2 = rest / p.tiles_mp;
       const int ph = rest2 % p.phases;
       const int ks = rest2 / p.phases;
       const int ty = row >> p.tileW_log2;
       const int gy = (m_t / p.tiles_x) * p.tile_rows + ty;
       const int gx = ((m_t % p.tiles_x) << p.tileW_log2) + (row & (tileW - 1));
-      const bool valid = (ty < p.tile_rows) && (gy < p.rows_total);
+      const bool valid = (m_t < p.tiles_m) && (ty < p.tile_rows) && (gy < p.rows_total) && !(p.debug & 8);
       const int b = gy / p.Hg;
       const int y = gy - b * p.Hg;
       const int oy = y * p.out_scale + p.out_oy[ph];
@@ -199,54 +346,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       const size_t pix = ((size_t)b * p.out_H + oy) * p.out_W + ox;
       const int n0 = n_t * BLOCK_N;
 
-      ptx::mbar_wait(&tfull[acc], acc_phase);
+      lean::wait(tfull0 + 8 * acc, acc_phase);
       ptx::tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
       constexpr int kChunk = BLOCK_N >= 32 ? 32 : 16;
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += kChunk) {
         uint32_t v[kChunk];
         if constexpr (kChunk == 32) ptx::tmem_ld32(t_addr + c0, v); else ptx::tmem_ld16(t_addr + c0, v);
         ptx::tmem_wait_ld();
-        if (valid) {
-          const float* bias = p.bias + n0 + c0;
-          if (p.out_mode == 0) {
-            uint32_t pk[kChunk / 2];
-#pragma unroll
-            for (int j = 0; j < kChunk / 2; ++j) {
-              float a = __uint_as_float(v[2 * j]) + __ldg(bias + 2 * j);
-              float c = __uint_as_float(v[2 * j + 1]) + __ldg(bias + 2 * j + 1);
-              if (p.lrelu) { a = fmaxf(a, 0.1f * a); c = fmaxf(c, 0.1f * c); }
-              pk[j] = pack16(a, c, p.is_bf16);
-            }
-            uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + pix * p.out_cstride + p.out_coff + n0 + c0;
-            uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-            for (int j = 0; j < kChunk / 8; ++j) o4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          } else if (p.out_mode == 2) {
-            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)ks * p.ws_split_stride +
-                                                   pix * p.n_pad + n0 + c0);
-#pragma unroll
-            for (int j = 0; j < kChunk / 4; ++j)
-              o4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                  __uint_as_float(v[4 * j + 3]));
-          } else {
-            float* o = reinterpret_cast<float*>(p.out) + pix * p.out_cstride + p.out_coff;
-#pragma unroll
-            for (int j = 0; j < kChunk; ++j) {
-              const int col = n0 + c0 + j;
-              if (col < p.n_valid) {
-                float a = __uint_as_float(v[j]) + __ldg(bias + j);
-                if (p.lrelu) a = fmaxf(a, 0.1f * a);
-                o[col] = a;
-              }
-            }
-          }
-        }
+        if (valid) epilogue_store<kChunk>(p, v, pix, n0 + c0, ks);
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if constexpr (kPair) ptx::mbar_arrive_cluster(tempty_tgt0 + 8 * acc);
+        else ptx::mbar_arrive(&tempty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -254,7 +370,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if constexpr (kPair) ptx::cluster_sync();  // no CTA frees TMEM or exits while the pair still references it
+  if (warp == 1) {
+    if constexpr (kPair) ptx::tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  conv_gemm_body<BLOCK_N, false>(p);
+}
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
+  conv_gemm_body<BLOCK_N, true>(p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -363,21 +493,38 @@ int launch_t(const ConvPlan& plan, cudaStream_t st) {
   OFS_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
     OFS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)GemmCfg<BLOCK_N>::kSmem));
+                                  (int)GemmCfg<BLOCK_N, false>::kSmem));
     attr_set[dev] = true;
   }
-  conv_gemm_kernel<BLOCK_N><<<plan.grid, kThreads, GemmCfg<BLOCK_N>::kSmem, st>>>(plan.p);
+  conv_gemm_kernel<BLOCK_N><<<plan.grid, kThreads, GemmCfg<BLOCK_N, false>::kSmem, st>>>(plan.p);
   OFS_LAUNCH_CHECK();
-  if (plan.p.ksplit > 1) {
-    const ConvGemmParams& p = plan.p;
-    const size_t npix = (size_t)plan.d.B * p.out_H * p.out_W;
-    const size_t total = npix * (p.n_pad / 8);
-    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
-    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(plan.ws, p.ksplit, p.ws_split_stride, npix, p.n_pad, plan.bias_dev,
-                                                 reinterpret_cast<uint16_t*>(plan.final_out), plan.d.out_cstride,
-                                                 plan.d.out_coff, plan.d.lrelu, plan.d.is_bf16);
-    OFS_LAUNCH_CHECK();
+  return OFS_OK;
+}
+
+template <int BLOCK_N>
+int launch_t2(const ConvPlan& plan, cudaStream_t st) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  OFS_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    OFS_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)GemmCfg<BLOCK_N, true>::kSmem));
+    attr_set[dev] = true;
   }
+  conv_gemm2_kernel<BLOCK_N><<<plan.grid, kThreads, GemmCfg<BLOCK_N, true>::kSmem, st>>>(plan.p);
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
+}
+
+int launch_reduce(const ConvPlan& plan, cudaStream_t st) {
+  const ConvGemmParams& p = plan.p;
+  const size_t npix = (size_t)plan.d.B * p.out_H * p.out_W;
+  const size_t total = npix * (p.n_pad / 8);
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
+  splitk_reduce_kernel<<<blocks, 256, 0, st>>>(plan.ws, p.ksplit, p.ws_split_stride, npix, p.n_pad, plan.bias_dev,
+                                               reinterpret_cast<uint16_t*>(plan.final_out), plan.d.out_cstride,
+                                               plan.d.out_coff, plan.d.lrelu, plan.d.is_bf16);
+  OFS_LAUNCH_CHECK();
   return OFS_OK;
 }
 
@@ -449,6 +596,8 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
               d.in_cs, d.cin);
   OFS_REQUIRE(d.block_n == 16 || d.block_n == 32 || d.block_n == 64 || d.block_n == 128 || d.block_n == 256,
               "conv plan: block_n %d unsupported", d.block_n);
+  OFS_REQUIRE(d.cta_group == 1 || (d.cta_group == 2 && d.block_n >= 32),
+              "conv plan: cta_group must be 1, or 2 with block_n >= 32 (got %d / %d)", d.cta_group, d.block_n);
   const bool deconv = d.kind == kDeconvK4S2;
   int Hg, Wg;
   if (deconv) {
@@ -550,7 +699,7 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
   p.n_pad = ((d.cout + d.block_n - 1) / d.block_n) * d.block_n;
   p.tiles_n = p.n_pad / d.block_n;
   p.n_valid = d.cout;
-  p.out_mode = d.out_mode; p.lrelu = d.lrelu; p.is_bf16 = d.is_bf16;
+  p.out_mode = d.out_mode; p.lrelu = d.lrelu; p.is_bf16 = d.is_bf16; p.debug = d.debug;
   p.out_cstride = d.out_cstride; p.out_coff = d.out_coff;
   if (d.out_mode == 0) {
     OFS_REQUIRE(p.n_pad == d.cout, "16-bit output mode needs cout %% block_n == 0 (cout %d, block_n %d)", d.cout, d.block_n);
@@ -568,14 +717,25 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
     plan.ws_bytes = p.ksplit > 1 ? (size_t)p.ksplit * p.ws_split_stride * 4 : 0;
     if (p.ksplit > 1) p.out_mode = 2;
   }
-  const int total_tiles = p.tiles_m * p.tiles_n * p.phases * p.ksplit;
-  plan.grid = std::max(1, std::min(total_tiles, sm_count()));
-  switch (d.block_n) {
-    case 16: plan.smem = GemmCfg<16>::kSmem; break;
-    case 32: plan.smem = GemmCfg<32>::kSmem; break;
-    case 64: plan.smem = GemmCfg<64>::kSmem; break;
-    case 128: plan.smem = GemmCfg<128>::kSmem; break;
-    default: plan.smem = GemmCfg<256>::kSmem; break;
+  p.tiles_mp = d.cta_group == 2 ? (p.tiles_m + 1) / 2 : p.tiles_m;
+  const int total_tiles = p.tiles_mp * p.tiles_n * p.phases * p.ksplit;
+  if (d.cta_group == 2) {
+    plan.grid = 2 * std::max(1, std::min(total_tiles, sm_count() / 2));
+    switch (d.block_n) {
+      case 32: plan.smem = GemmCfg<32, true>::kSmem; break;
+      case 64: plan.smem = GemmCfg<64, true>::kSmem; break;
+      case 128: plan.smem = GemmCfg<128, true>::kSmem; break;
+      default: plan.smem = GemmCfg<256, true>::kSmem; break;
+    }
+  } else {
+    plan.grid = std::max(1, std::min(total_tiles, sm_count()));
+    switch (d.block_n) {
+      case 16: plan.smem = GemmCfg<16, false>::kSmem; break;
+      case 32: plan.smem = GemmCfg<32, false>::kSmem; break;
+      case 64: plan.smem = GemmCfg<64, false>::kSmem; break;
+      case 128: plan.smem = GemmCfg<128, false>::kSmem; break;
+      default: plan.smem = GemmCfg<256, false>::kSmem; break;
+    }
   }
   plan.macs = deconv ? (double)d.B * d.H * d.W * 16.0 * d.cin * d.cout
                      : (double)d.B * Hg * Wg * (double)d.k * d.k * d.cin * d.cout;
@@ -659,20 +819,32 @@ int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const 
   if (st != OFS_OK) return st;
   cuuint64_t wd[2] = {(cuuint64_t)plan.k_total, (cuuint64_t)plan.w_rows};
   cuuint64_t ws[1] = {(cuuint64_t)plan.k_total * 2};
-  cuuint32_t wb[2] = {(cuuint32_t)kBlockK, (cuuint32_t)plan.block_n};
+  cuuint32_t wb[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(plan.block_n / d.cta_group)};
   return encode_map(&p.tmap_w, d.is_bf16, 2, w_dev, wd, ws, wb);
 }
 
 int conv_launch(const ConvPlan& plan, cudaStream_t st) {
-  switch (plan.block_n) {
-    case 16: return launch_t<16>(plan, st);
-    case 32: return launch_t<32>(plan, st);
-    case 64: return launch_t<64>(plan, st);
-    case 128: return launch_t<128>(plan, st);
-    case 256: return launch_t<256>(plan, st);
+  int rc = OFS_EINVAL;
+  if (plan.d.cta_group == 2) {
+    switch (plan.block_n) {
+      case 32: rc = launch_t2<32>(plan, st); break;
+      case 64: rc = launch_t2<64>(plan, st); break;
+      case 128: rc = launch_t2<128>(plan, st); break;
+      case 256: rc = launch_t2<256>(plan, st); break;
+      default: set_error("conv_launch: unsupported block_n %d for CTA pairs", plan.block_n); return OFS_EINVAL;
+    }
+  } else {
+    switch (plan.block_n) {
+      case 16: rc = launch_t<16>(plan, st); break;
+      case 32: rc = launch_t<32>(plan, st); break;
+      case 64: rc = launch_t<64>(plan, st); break;
+      case 128: rc = launch_t<128>(plan, st); break;
+      case 256: rc = launch_t<256>(plan, st); break;
+      default: set_error("conv_launch: unsupported block_n %d", plan.block_n); return OFS_EINVAL;
+    }
   }
-  set_error("conv_launch: unsupported block_n %d", plan.block_n);
-  return OFS_EINVAL;
+  if (rc != OFS_OK) return rc;
+  return plan.p.ksplit > 1 ? launch_reduce(plan, st) : OFS_OK;
 }
 
 int launch_pack_act(const float* in, void* out, size_t npix, int cin, int cs, int is_bf16, cudaStream_t st) {
@@ -698,7 +870,7 @@ int launch_unpack_act(const void* in, float* out, size_t npix, int cs, int coff,
 // ------------------------------------------------------------------------------------------------
 extern "C" int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const float* b_host, float* y, int B, int H,
                                   int W, int Cin, int Cout, int k, int stride, int transposed, int lrelu, int precision,
-                                  int block_n, int ksplit, ofs_stream stream) {
+                                  int block_n, int ksplit, int cta_group, ofs_stream stream) {
   using namespace ofs;
   cudaStream_t st = (cudaStream_t)stream;
   OFS_REQUIRE(x && w_host && y, "ofs_conv2d_nhwc: null pointer");
@@ -717,6 +889,7 @@ extern "C" int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const flo
   if (!transposed && stride == 2 && d.in_cs != 32) d.cin = d.in_cs;  // zero channels + zero weights
   d.block_n = block_n > 0 ? block_n : (Cout >= 128 ? 128 : (Cout >= 64 ? 64 : (Cout >= 32 ? 32 : 16)));
   d.ksplit = ksplit > 1 ? ksplit : 1;
+  d.cta_group = cta_group == 2 ? 2 : 1;
   const bool via16 = d.ksplit > 1;   // split-K reduces into the 16-bit output format
   const int cout8 = ((Cout + 7) / 8) * 8;
   d.out_mode = via16 ? 0 : 1; d.lrelu = lrelu; d.is_bf16 = is_bf16;
@@ -772,7 +945,8 @@ extern "C" int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const flo
 extern "C" int ofs_conv2d_nhwc(const float* x, const float* w_host, const float* b_host, float* y, int B, int H, int W,
                                int Cin, int Cout, int k, int stride, int transposed, int lrelu, int precision,
                                ofs_stream stream) {
-  return ofs_conv2d_nhwc_ex(x, w_host, b_host, y, B, H, W, Cin, Cout, k, stride, transposed, lrelu, precision, 0, 1, stream);
+  return ofs_conv2d_nhwc_ex(x, w_host, b_host, y, B, H, W, Cin, Cout, k, stride, transposed, lrelu, precision, 0, 1, 1,
+                            stream);
 }
 
 // Host-only introspection of the plan (geometry, tap table, activation view, packed weights): lets

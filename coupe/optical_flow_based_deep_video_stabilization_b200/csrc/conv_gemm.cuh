@@ -13,7 +13,7 @@ constexpr int kMaxTapEntries = 64;
 // Everything the kernel needs, passed as one __grid_constant__ parameter.
 struct ConvGemmParams {
   CUtensorMap tmap_a;  // 5-D view of the NHWC 16-bit activation (see conv_gemm.cu)
-  CUtensorMap tmap_w;  // 2-D packed weights [phases * n_pad rows][K_total], K-major
+  CUtensorMap tmap_w;  // 2-D packed weights [phases * n_pad rows][K_total], K-major (box rows: BLOCK_N / cta_group)
   // M grid (output pixels; for the transposed conv: input pixels, one GEMM per sub-pixel phase)
   int Hg, Wg;          // grid height / width per image
   int rows_total;      // B * Hg
@@ -26,6 +26,7 @@ struct ConvGemmParams {
   int a_bytes;         // bytes one A stage receives = npieces * piece_rows * tileW * 128
   int tiles_x;         // Wg / tileW
   int tiles_m;         // tiles_x * ceil(rows_total / tile_rows)
+  int tiles_mp;        // M tiles per scheduling unit: tiles_m (1 CTA) or ceil(tiles_m / 2) (CTA pairs)
   int tiles_n;         // n_pad / BLOCK_N
   int phases;          // 1 (conv) or 4 (transposed conv sub-pixel phases)
   int ksplit;          // split-K factor (partials go to an fp32 workspace, reduced by splitk_reduce_kernel)
@@ -45,6 +46,7 @@ struct ConvGemmParams {
   int n_valid;         // real output channels
   int lrelu;           // apply max(v, 0.1 v)
   int is_bf16;         // operand / storage format: 1 bf16, 0 fp16
+  int debug;           // measurement only: bit0 skip MMAs, bit1 skip A loads, bit2 skip B loads (results garbage)
   int out_oy[4], out_ox[4];  // per-phase sub-pixel offset
   // per (phase, tap) TMA coordinate offsets: channel base, x offset, parity plane, y offset
   short tap_c[kMaxTapEntries], tap_x[kMaxTapEntries], tap_p[kMaxTapEntries], tap_y[kMaxTapEntries];
@@ -63,6 +65,8 @@ struct ConvDesc {
   int out_mode, lrelu, is_bf16;
   int out_cstride, out_coff;
   int ksplit = 1;      // > 1: split the K loop over this many CTAs per tile (16-bit output mode only)
+  int cta_group = 1;   // 2: CTA pairs (tcgen05 cta_group::2): tile = 256 GEMM rows x BLOCK_N, B split over the pair
+  int debug = 0;       // see ConvGemmParams::debug
 };
 
 struct ConvPlan {

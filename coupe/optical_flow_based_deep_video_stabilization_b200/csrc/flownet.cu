@@ -136,13 +136,16 @@ __global__ void predict2_gather_kernel(Predict2Params p) {
     const int b = (int)(r / 382);
     float a0 = p.bias0, a1 = p.bias1;
     const float* Pb = p.P + (size_t)b * 96 * 128 * 18;
+    int ixs[3];
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) ixs[kx] = min((int)roundf((float)(ox + kx) * p.sx), 129) - 1;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = min((int)roundf((float)(oy + ky) * p.sy), 97) - 1;  // row of the unpadded 96x128 grid
       if (iy < 0 || iy >= 96) continue;
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const int ix = min((int)roundf((float)(ox + kx) * p.sx), 129) - 1;
+        const int ix = ixs[kx];
         if (ix < 0 || ix >= 128) continue;
         const float2 v = __ldg(reinterpret_cast<const float2*>(Pb + ((size_t)iy * 128 + ix) * 18 + (ky * 3 + kx) * 2));
         a0 += v.x;
@@ -158,60 +161,78 @@ __global__ void predict2_gather_kernel(Predict2Params p) {
 }
 
 // Flow heads predict6..predict3 (model.py:847-848,855-856,864-865,873-874): zero-pad 1 + 3x3 conv to 2
-// channels + bias, no activation.  N = 2 is no tensor-core shape: one warp per output pixel, lanes stride
-// over channels with 128-bit loads of the 16-bit activations and of the [tap][c][2] 16-bit weights, fp32
-// FMA, shuffle reduction.  Neighbouring pixels share taps through L1.
+// channels + bias, no activation.  N = 2 is far below a tcgen05 tile (the N=16 GEMM form spent 0.39 ms on
+// the four heads), so this is a warp-level mma.sync kernel: a block of 9 warps owns 16 consecutive output
+// pixels, warp k = tap k.  Per 32 input channels a lane issues two 128-bit activation loads (rows g, g+8)
+// and, on lanes 0-7, one 128-bit weight load, feeding two m16n8k16 MMAs (columns 0,1 of N are real).
+// The K index is only summed over, so the 8 channels a lane loads are mapped onto the fragment's k slots
+// in load order -- identically for A and B.  The 9 per-tap partials are summed in a fixed order.
 struct HeadParams {
   const uint16_t* act;  // [B,h,w,cs]
-  const uint16_t* wgt;  // [9][cs][2]   (zero for c >= cin)
+  const uint16_t* wgt;  // [9][2][cs]   (zero for c >= cin)
   float2* out;          // [B,h,w]
   float b0, b1;
   int B, h, w, cs, is_bf16;
 };
 
-__device__ __forceinline__ float2 unpack16x2(uint32_t u, int is_bf16) {
-  if (is_bf16) return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
-  return __half22float2(*reinterpret_cast<const __half2*>(&u));
+__device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1, int is_bf16) {
+  if (is_bf16) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  } else {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
 }
 
-__global__ void __launch_bounds__(256) head3x3_kernel(HeadParams p) {
-  const int lane = threadIdx.x & 31;
-  const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
-  const size_t npix = (size_t)p.B * p.h * p.w;
-  for (size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pix < npix; pix += warps) {
-    const int x = (int)(pix % p.w);
-    const size_t r = pix / p.w;
-    const int y = (int)(r % p.h);
-    const int b = (int)(r / p.h);
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll 1
-    for (int t = 0; t < 9; ++t) {
-      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-      if (yy < 0 || yy >= p.h || xx < 0 || xx >= p.w) continue;  // warp-uniform
-      const uint16_t* ap = p.act + (((size_t)b * p.h + yy) * p.w + xx) * p.cs;
-      const uint16_t* wp = p.wgt + (size_t)t * p.cs * 2;
-      for (int c = lane * 8; c < p.cs; c += 256) {
-        const uint4 av = __ldg(reinterpret_cast<const uint4*>(ap + c));
-        const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(wp + 2 * c));
-        const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(wp + 2 * c + 8));
-        const uint32_t au[4] = {av.x, av.y, av.z, av.w};
-        const uint32_t wu[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+__global__ void __launch_bounds__(288) head3x3_kernel(HeadParams p) {
+  __shared__ float part[9][32];
+  const int lane = threadIdx.x & 31, tap = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+  const int npix = p.B * p.h * p.w;
+  const int ngroups = (npix + 15) >> 4;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const uint16_t* ap[2];
+    bool ok[2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 a = unpack16x2(au[i], p.is_bf16);      // channels c+2i, c+2i+1
-          const float2 wa = unpack16x2(wu[2 * i], p.is_bf16);     // (o0, o1) of channel c+2i
-          const float2 wb = unpack16x2(wu[2 * i + 1], p.is_bf16); // (o0, o1) of channel c+2i+1
-          a0 = fmaf(a.x, wa.x, a0); a1 = fmaf(a.x, wa.y, a1);
-          a0 = fmaf(a.y, wb.x, a0); a1 = fmaf(a.y, wb.y, a1);
-        }
-      }
+    for (int r = 0; r < 2; ++r) {
+      const int pix = grp * 16 + g + 8 * r;
+      const int x = pix % p.w, rest = pix / p.w;
+      const int y = rest % p.h, b = rest / p.h;
+      const int yy = y + dy, xx = x + dx;
+      ok[r] = (pix < npix) && yy >= 0 && yy < p.h && xx >= 0 && xx < p.w;
+      ap[r] = p.act + (((size_t)b * p.h + (ok[r] ? yy : 0)) * p.w + (ok[r] ? xx : 0)) * p.cs;
     }
+    const uint16_t* wp = p.wgt + (size_t)(tap * 2 + (g < 2 ? g : 0)) * p.cs;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int c0 = 0; c0 < p.cs; c0 += 32) {
+      const int ch = c0 + 8 * t;
+      const bool in = ch < p.cs;
+      const uint4 A0 = (ok[0] && in) ? __ldg(reinterpret_cast<const uint4*>(ap[0] + ch)) : zero4;
+      const uint4 A1 = (ok[1] && in) ? __ldg(reinterpret_cast<const uint4*>(ap[1] + ch)) : zero4;
+      const uint4 Bv = (g < 2 && in) ? __ldg(reinterpret_cast<const uint4*>(wp + ch)) : zero4;
+      mma16816(c, A0.x, A1.x, A0.y, A1.y, Bv.x, Bv.y, p.is_bf16);
+      mma16816(c, A0.z, A1.z, A0.w, A1.w, Bv.z, Bv.w, p.is_bf16);
+    }
+    if (t == 0) {  // columns 0,1 of the 16x8 tile: rows g and g+8
+      part[tap][g * 2 + 0] = c[0]; part[tap][g * 2 + 1] = c[1];
+      part[tap][(g + 8) * 2 + 0] = c[2]; part[tap][(g + 8) * 2 + 1] = c[3];
+    }
+    __syncthreads();
+    if (tap == 0) {
+      float s = (lane & 1) ? p.b1 : p.b0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      for (int k = 0; k < 9; ++k) s += part[k][lane];
+      const int pix = grp * 16 + (lane >> 1);
+      if (pix < npix) reinterpret_cast<float*>(p.out)[(size_t)pix * 2 + (lane & 1)] = s;
     }
-    if (lane == 0) p.out[pix] = make_float2(a0 + p.b0, a1 + p.b1);
+    __syncthreads();
   }
 }
 
@@ -219,7 +240,7 @@ struct Head {
   std::string name;   // "predict6" .. "predict3"
   int level, h, w, cin, cs;
   const void* in = nullptr;
-  void* w_dev = nullptr;  // [9][cs][2] 16-bit
+  void* w_dev = nullptr;  // [9][2][cs] 16-bit
   float bias[2] = {0, 0};
 };
 
@@ -231,6 +252,7 @@ struct Layer {
   void* out = nullptr;
   int ksplit = 1;         // fixed split-K factor: independent of the batch so results are batch-invariant
   int block_n_run = 0;    // BLOCK_N used at run time (0 = d.block_n)
+  int cta_group = 1;      // 2 = CTA pairs (conv_gemm2_kernel)
   ConvPlan plan;          // plan of the currently prepared batch size
   std::map<int, ConvPlan> plans;  // bound plans per batch size (TMA descriptors are per batch)
   void* w_dev = nullptr;
@@ -294,9 +316,9 @@ Layer make_layer(const char* name, const char* bn, ConvKind kind, int H, int W, 
   return L;
 }
 
-// OFS_TUNE="layer:block_n:ksplit,..." overrides the tiling of individual layers (experiments only;
+// OFS_TUNE="layer:block_n:ksplit[:cta_group],..." overrides the tiling of individual layers (experiments only;
 // block_n must keep the packed weight layout valid, i.e. divide the layer's padded N).
-bool tune_lookup(const std::string& name, int* block_n, int* ksplit) {
+bool tune_lookup(const std::string& name, int* block_n, int* ksplit, int* cta_group, int* debug) {
   const char* env = getenv("OFS_TUNE");
   if (!env) return false;
   std::string s(env);
@@ -309,6 +331,12 @@ bool tune_lookup(const std::string& name, int* block_n, int* ksplit) {
     if (c1 != std::string::npos && c2 != std::string::npos && item.substr(0, c1) == name) {
       *block_n = atoi(item.substr(c1 + 1, c2 - c1 - 1).c_str());
       *ksplit = atoi(item.substr(c2 + 1).c_str());
+      const size_t c3 = item.find(':', c2 + 1);
+      if (c3 != std::string::npos) {
+        *cta_group = atoi(item.substr(c3 + 1).c_str());
+        const size_t c4 = item.find(':', c3 + 1);
+        if (c4 != std::string::npos) *debug = atoi(item.substr(c4 + 1).c_str());
+      }
       return true;
     }
     pos = end + 1;
@@ -330,15 +358,17 @@ int prepare(ofs_net* n, int B) {
     L.d.ksplit = 1;
     int rc = conv_plan_geometry(L.plan, L.d);
     if (rc != OFS_OK) return rc;
-    int bn = L.block_n_run ? L.block_n_run : L.d.block_n, ks = L.ksplit;
-    const bool tuned = tune_lookup(L.name, &bn, &ks);
+    int bn = L.block_n_run ? L.block_n_run : L.d.block_n, ks = L.ksplit, cg = L.cta_group, dbg = 0;
+    const bool tuned = tune_lookup(L.name, &bn, &ks, &cg, &dbg);
     if (tuned && (bn != L.d.block_n) && (L.n_pad % bn != 0)) {
       set_error("OFS_TUNE: block_n %d does not divide the padded N %d of layer %s", bn, L.n_pad, L.name.c_str());
       return OFS_EINVAL;
     }
-    if (ks > 1 || bn != L.d.block_n) {
+    if (ks > 1 || bn != L.d.block_n || cg == 2 || dbg) {
       ConvDesc d = L.d;
       d.block_n = bn;
+      d.cta_group = cg == 2 ? 2 : 1;
+      d.debug = dbg;
       d.ksplit = (L.d.out_mode == 0 && ks > 1) ? ks : 1;
       rc = conv_plan_geometry(L.plan, d);
       if (rc != OFS_OK) return rc;
@@ -373,8 +403,8 @@ int launch_head(ofs_net* n, const Head& h, int B, cudaStream_t st) {
   p.b0 = h.bias[0]; p.b1 = h.bias[1];
   p.B = B; p.h = h.h; p.w = h.w; p.cs = h.cs; p.is_bf16 = n->is_bf16;
   const size_t npix = (size_t)B * h.h * h.w;
-  const int blocks = (int)std::min<size_t>((npix + 7) / 8, (size_t)sm_count() * 8);
-  head3x3_kernel<<<blocks, 256, 0, st>>>(p);
+  const int blocks = (int)std::min<size_t>((npix + 15) / 16, (size_t)sm_count() * 6);
+  head3x3_kernel<<<blocks, 288, 0, st>>>(p);
   OFS_LAUNCH_CHECK();
   return OFS_OK;
 }
@@ -694,12 +724,12 @@ int ofs_net_load_weights(ofs_net* n, const ofs_named_array* arrays, int count) {
     int rc = find(h.name + "/W_conv2d", (int64_t)9 * h.cin * 2, &w, true);
     if (rc == OFS_OK) rc = find(h.name + "/b_conv2d", 2, &b, false);
     if (rc != OFS_OK) return rc;
-    std::vector<uint16_t> wp((size_t)9 * h.cs * 2, 0);   // [tap][c][o]; TF layout is already [ky,kx,ci,o]
+    std::vector<uint16_t> wp((size_t)9 * 2 * h.cs, 0);   // [tap][o][c]; TF layout is [ky,kx,ci,o]
     for (int t = 0; t < 9; ++t)
       for (int c = 0; c < h.cin; ++c)
         for (int o = 0; o < 2; ++o) {
           const float v = w[((size_t)t * h.cin + c) * 2 + o];
-          wp[((size_t)t * h.cs + c) * 2 + o] = n->is_bf16 ? f32_to_bf16_rn(v) : f32_to_fp16_rn(v);
+          wp[((size_t)t * 2 + o) * h.cs + c] = n->is_bf16 ? f32_to_bf16_rn(v) : f32_to_fp16_rn(v);
         }
     h.bias[0] = b ? b[0] : 0.f;
     h.bias[1] = b ? b[1] : 0.f;

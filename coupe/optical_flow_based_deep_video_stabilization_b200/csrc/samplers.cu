@@ -5,16 +5,21 @@
 //   ofs_vec2mtrx/ofs_lie_warp<- vec2mtrx / transformImage / transformCropImage   warp.py:25-129
 //
 // Design (HBM-bound, 32 B/px for tf_warp at C=3):
-//   * each thread owns 4 consecutive output pixels of one row: flow is read as 2x128-bit loads,
-//     the 4x3 fp32 results leave as 3x128-bit stores (12-byte pixels are not 16-byte aligned
-//     one by one, 4 of them are);
-//   * the "staged" tf_warp variant loads the bounding box of the source pixels a 64x16 output
-//     tile touches into shared memory with fully coalesced loads (bbox found with warp-shuffle
-//     min/max reductions) and gathers the 4 corners from shared memory; tiles whose bbox does
-//     not fit fall back to direct read-only-path gathers;
-//   * grids are sized as a multiple of the SM count and grid-stride over the work.
+//   * a 256-thread block owns a 64x16 output tile; warp w owns rows 2w, 2w+1 and lane l the pixels
+//     l and l+32 of a row, so neighbouring lanes always touch neighbouring pixels: flow loads are
+//     coalesced, gathers of 12-byte pixels are bank-conflict free in shared memory (stride 3 words)
+//     and sector-efficient in L1;
+//   * results leave through a per-warp shared-memory transpose as 128-bit stores of whole rows
+//     (12-byte pixels are not 16-byte aligned one by one, a row segment is);
+//   * the "staged" tf_warp variant loads the bounding box of the source pixels the tile touches into
+//     shared memory with fully coalesced loads (bbox found with warp-shuffle min/max reductions) and
+//     gathers the 4 corners from there; tiles whose bbox does not fit fall back to read-only-path gathers;
+//   * grids are a multiple of the SM count and grid-stride over the tiles.
 // Arithmetic follows the reference operation by operation where that decides an index
 // (truncation vs floor, clip order, fp32 coordinate products); see oracle/samplers.py.
+#include <algorithm>
+#include <climits>
+
 #include "ofs_common.cuh"
 
 namespace ofs {
@@ -182,14 +187,8 @@ struct TfWarpProvider {
     const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + ((size_t)b * H + oy) * W + ox);
     return taps_tfwarp(f.x, f.y, ox, oy, H, W);
   }
-  // 4 consecutive pixels: two 128-bit loads
-  __device__ __forceinline__ void taps4(int b, int oy, int ox, Taps* t) const {
-    const float4* p = reinterpret_cast<const float4*>(flow + (((size_t)b * H + oy) * W + ox) * 2);
-    const float4 a = __ldg(p), c = __ldg(p + 1);
-    t[0] = taps_tfwarp(a.x, a.y, ox + 0, oy, H, W);
-    t[1] = taps_tfwarp(a.z, a.w, ox + 1, oy, H, W);
-    t[2] = taps_tfwarp(c.x, c.y, ox + 2, oy, H, W);
-    t[3] = taps_tfwarp(c.z, c.w, ox + 3, oy, H, W);
+  __device__ __forceinline__ float2 flow_at(int b, int oy, int ox) const {
+    return __ldg(reinterpret_cast<const float2*>(flow) + ((size_t)b * H + oy) * W + ox);
   }
 };
 struct ResizeWarpProvider {
@@ -198,19 +197,12 @@ struct ResizeWarpProvider {
     const float2 f = fr.at(b, oy, ox);
     return taps_tfwarp(f.x, f.y, ox, oy, fr.H, fr.W);
   }
-  __device__ __forceinline__ void taps4(int b, int oy, int ox, Taps* t) const {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) t[j] = taps(b, oy, ox + j);
-  }
+  __device__ __forceinline__ float2 flow_at(int b, int oy, int ox) const { return fr.at(b, oy, ox); }
 };
 template <class Coord>
 struct CoordProvider {
   Coord c;
   __device__ __forceinline__ Taps taps(int b, int oy, int ox) const { return c.taps(b, oy, ox); }
-  __device__ __forceinline__ void taps4(int b, int oy, int ox, Taps* t) const {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) t[j] = c.taps(b, oy, ox + j);
-  }
 };
 
 // acc + w*v as two separately rounded fp32 operations (no FMA contraction): the reference sums
@@ -225,36 +217,6 @@ __device__ __forceinline__ void gather3(const float* __restrict__ imgb, int srcW
     acc[0] = mul_add_rn(acc[0], w, __ldg(p + 0));
     acc[1] = mul_add_rn(acc[1], w, __ldg(p + 1));
     acc[2] = mul_add_rn(acc[2], w, __ldg(p + 2));
-  }
-}
-
-// one thread = 4 consecutive output pixels, C == 3, oW % 4 == 0
-template <class Provider>
-__global__ void __launch_bounds__(256) sample_quad3_kernel(Provider prov, const float* __restrict__ img,
-                                                           float* __restrict__ out, int B, int srcH, int srcW, int oH,
-                                                           int oW) {
-  const int qpr = oW >> 2;
-  const size_t total = (size_t)B * oH * qpr;
-  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
-    const int qx = (int)(q % qpr);
-    const size_t r = q / qpr;
-    const int oy = (int)(r % oH);
-    const int b = (int)(r / oH);
-    const int ox = qx << 2;
-    Taps t[4];
-    prov.taps4(b, oy, ox, t);
-    const float* imgb = img + (size_t)b * srcH * srcW * 3;
-    float acc[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) acc[i] = 0.0f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) gather3(imgb, srcW, t[j].y[k], t[j].x[k], t[j].w[k], acc + 3 * j);
-    float4* o = reinterpret_cast<float4*>(out + (((size_t)b * oH + oy) * oW + ox) * 3);
-    __stcs(o + 0, make_float4(acc[0], acc[1], acc[2], acc[3]));
-    __stcs(o + 1, make_float4(acc[4], acc[5], acc[6], acc[7]));
-    __stcs(o + 2, make_float4(acc[8], acc[9], acc[10], acc[11]));
   }
 }
 
@@ -283,9 +245,9 @@ __global__ void __launch_bounds__(256) sample_px_kernel(Provider prov, const flo
 }
 
 // -------------------------------------------------------------------------------------------------
-// staged tf_warp: 64x16 output tile per 256-thread block, source bbox in shared memory
+// C == 3 tile kernels: 64x16 output tile per 256-thread block (see the design note at the top)
 constexpr int kTileW = 64, kTileH = 16;
-constexpr int kStageMaxPx = 3840;  // 45 KB of fp32 RGB (static shared memory limit is 48 KB)
+constexpr int kStageMaxPx = 2560;  // 30 KB of fp32 RGB source pixels per block
 
 __device__ __forceinline__ int warp_min(int v) {
 #pragma unroll
@@ -298,84 +260,154 @@ __device__ __forceinline__ int warp_max(int v) {
   return v;
 }
 
+// One output row segment (<= 64 px, a multiple of 4) of a warp: lane holds pixels lane and lane+32 as
+// 2 x 3 floats; transposed through `obuf` (192 floats, this warp's) into whole-row 128-bit stores.
+__device__ __forceinline__ void store_row3(float* obuf, float* __restrict__ grow, int lane, int valid_px,
+                                           const float* v0, const float* v1) {
+  obuf[lane * 3 + 0] = v0[0]; obuf[lane * 3 + 1] = v0[1]; obuf[lane * 3 + 2] = v0[2];
+  obuf[(lane + 32) * 3 + 0] = v1[0]; obuf[(lane + 32) * 3 + 1] = v1[1]; obuf[(lane + 32) * 3 + 2] = v1[2];
+  __syncwarp();
+  const int nvec = (valid_px * 3) >> 2;
+  const float4* o4 = reinterpret_cast<const float4*>(obuf);
+  float4* g4 = reinterpret_cast<float4*>(grow);
+  if (lane < nvec) __stcs(g4 + lane, o4[lane]);
+  if (lane + 32 < nvec) __stcs(g4 + lane + 32, o4[lane + 32]);
+  __syncwarp();
+}
+
+struct TileId { int b, ox0, oy0; };
+__device__ __forceinline__ TileId decode_tile(size_t tile_id, int tiles_x, int tiles_y) {
+  TileId t;
+  t.ox0 = (int)(tile_id % tiles_x) * kTileW;
+  const size_t r = tile_id / tiles_x;
+  t.oy0 = (int)(r % tiles_y) * kTileH;
+  t.b = (int)(r / tiles_y);
+  return t;
+}
+
+// generic 4-tap sampler (grid_sample / Lie warp): direct read-only-path gathers
 template <class Provider>
-__global__ void __launch_bounds__(256) warp_staged3_kernel(Provider prov, const float* __restrict__ img,
-                                                           float* __restrict__ out, int B, int H, int W) {
-  __shared__ float tile[kStageMaxPx * 3];
-  __shared__ int red[4][8];
-  __shared__ int bbox[4];
-  const int tiles_x = (W + kTileW - 1) / kTileW;
-  const int tiles_y = (H + kTileH - 1) / kTileH;
+__global__ void __launch_bounds__(256) sample3_kernel(Provider prov, const float* __restrict__ img,
+                                                      float* __restrict__ out, int B, int srcH, int srcW, int oH,
+                                                      int oW) {
+  __shared__ __align__(16) float obuf[8][192];
+  const int tiles_x = (oW + kTileW - 1) / kTileW, tiles_y = (oH + kTileH - 1) / kTileH;
   const size_t ntiles = (size_t)B * tiles_y * tiles_x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 quads x 16 rows
   for (size_t tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
-    const int tix = (int)(tile_id % tiles_x);
-    const size_t r = tile_id / tiles_x;
-    const int tiy = (int)(r % tiles_y);
-    const int b = (int)(r / tiles_y);
-    const int ox = tix * kTileW + tx * 4, oy = tiy * kTileH + ty;
-    const bool active = (ox < W) && (oy < H);  // W % 4 == 0, so a quad is fully in or out
-    Taps t[4];
-    int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
-    if (active) {
-      prov.taps4(b, oy, ox, t);
+    const TileId t = decode_tile(tile_id, tiles_x, tiles_y);
+    const float* imgb = img + (size_t)t.b * srcH * srcW * 3;
+    const int valid_px = min(kTileW, oW - t.ox0);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        xmin = min(xmin, t[j].x[0]); xmax = max(xmax, t[j].x[3]);  // x0 <= x1, y0 <= y1 after clipping
-        ymin = min(ymin, t[j].y[0]); ymax = max(ymax, t[j].y[3]);
+    for (int rr = 0; rr < 2; ++rr) {
+      const int oy = t.oy0 + wid * 2 + rr;
+      if (oy >= oH) break;  // warp-uniform
+      float v[2][3];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ox = t.ox0 + lane + 32 * h;
+        v[h][0] = v[h][1] = v[h][2] = 0.0f;
+        if (ox < oW) {
+          const Taps tp = prov.taps(t.b, oy, ox);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) gather3(imgb, srcW, tp.y[k], tp.x[k], tp.w[k], v[h]);
+        }
       }
+      store_row3(obuf[wid], out + (((size_t)t.b * oH + oy) * oW + t.ox0) * 3, lane, valid_px, v[0], v[1]);
     }
-    xmin = warp_min(xmin); ymin = warp_min(ymin); xmax = warp_max(xmax); ymax = warp_max(ymax);
-    if (lane == 0) { red[0][wid] = xmin; red[1][wid] = xmax; red[2][wid] = ymin; red[3][wid] = ymax; }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      int a = (lane < 8) ? red[0][lane] : INT_MAX, c = (lane < 8) ? red[1][lane] : INT_MIN;
-      int d = (lane < 8) ? red[2][lane] : INT_MAX, e = (lane < 8) ? red[3][lane] : INT_MIN;
-      a = warp_min(a); c = warp_max(c); d = warp_min(d); e = warp_max(e);
-      if (lane == 0) { bbox[0] = a; bbox[1] = c; bbox[2] = d; bbox[3] = e; }
-    }
-    __syncthreads();
-    const int bx0 = bbox[0], bx1 = bbox[1], by0 = bbox[2], by1 = bbox[3];
-    const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;
-    const float* imgb = img + (size_t)b * H * W * 3;
-    float acc[12];
+  }
+}
+
+// tf_warp / fused flow-resize + tf_warp; kStaged: source bounding box of the tile staged in shared memory
+template <class Provider, bool kStaged>
+__global__ void __launch_bounds__(256) warp3_kernel(Provider prov, const float* __restrict__ img,
+                                                    float* __restrict__ out, int B, int H, int W) {
+  __shared__ __align__(16) float obuf[8][192];
+  __shared__ float tile[kStaged ? kStageMaxPx * 3 : 1];
+  __shared__ int red[4][8];
+  __shared__ int bbox[4];
+  const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
+  const size_t ntiles = (size_t)B * tiles_y * tiles_x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (size_t tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
+    const TileId t = decode_tile(tile_id, tiles_x, tiles_y);
+    const float* imgb = img + (size_t)t.b * H * W * 3;
+    const int valid_px = min(kTileW, W - t.ox0);
+    // this thread's 4 pixels: rows 2w, 2w+1 x columns lane, lane+32; keep only their flow
+    float2 fl[2][2];
+    bool on[2][2];
+    int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
 #pragma unroll
-    for (int i = 0; i < 12; ++i) acc[i] = 0.0f;
-    const bool staged = (bw > 0) && (bh > 0) && ((long long)bw * bh <= kStageMaxPx);
-    if (staged) {
-      const int row_f = bw * 3;
-      for (int rr = wid; rr < bh; rr += 8) {  // one warp per source row: coalesced 128-byte lines
-        const float* src = imgb + ((size_t)(by0 + rr) * W + bx0) * 3;
-        float* dst = tile + rr * row_f;
-        for (int i = lane; i < row_f; i += 32) dst[i] = __ldg(src + i);
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int oy = t.oy0 + wid * 2 + rr, ox = t.ox0 + lane + 32 * h;
+        on[rr][h] = (oy < H) && (ox < W);
+        fl[rr][h] = make_float2(0.f, 0.f);
+        if (on[rr][h]) {
+          fl[rr][h] = prov.flow_at(t.b, oy, ox);
+          if (kStaged) {
+            const Taps tp = taps_tfwarp(fl[rr][h].x, fl[rr][h].y, ox, oy, H, W);
+            xmin = min(xmin, tp.x[0]); xmax = max(xmax, tp.x[3]);  // x0 <= x1, y0 <= y1 after clipping
+            ymin = min(ymin, tp.y[0]); ymax = max(ymax, tp.y[3]);
+          }
+        }
+      }
+    bool staged = false;
+    int bx0 = 0, by0 = 0, bw = 0;
+    if (kStaged) {
+      xmin = warp_min(xmin); ymin = warp_min(ymin); xmax = warp_max(xmax); ymax = warp_max(ymax);
+      if (lane == 0) { red[0][wid] = xmin; red[1][wid] = xmax; red[2][wid] = ymin; red[3][wid] = ymax; }
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        int a = (lane < 8) ? red[0][lane] : INT_MAX, c = (lane < 8) ? red[1][lane] : INT_MIN;
+        int d = (lane < 8) ? red[2][lane] : INT_MAX, e = (lane < 8) ? red[3][lane] : INT_MIN;
+        a = warp_min(a); c = warp_max(c); d = warp_min(d); e = warp_max(e);
+        if (lane == 0) { bbox[0] = a; bbox[1] = c; bbox[2] = d; bbox[3] = e; }
       }
       __syncthreads();
-      if (active) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float* p = tile + ((t[j].y[k] - by0) * bw + (t[j].x[k] - bx0)) * 3;
-            const float w = t[j].w[k];
-            acc[3 * j + 0] = mul_add_rn(acc[3 * j + 0], w, p[0]);
-            acc[3 * j + 1] = mul_add_rn(acc[3 * j + 1], w, p[1]);
-            acc[3 * j + 2] = mul_add_rn(acc[3 * j + 2], w, p[2]);
-          }
+      bx0 = bbox[0]; by0 = bbox[2];
+      bw = bbox[1] - bx0 + 1;
+      const int bh = bbox[3] - by0 + 1;
+      staged = (bw > 0) && (bh > 0) && ((long long)bw * bh <= kStageMaxPx);
+      if (staged) {
+        const int row_f = bw * 3;
+        for (int r = wid; r < bh; r += 8) {  // one warp per source row: coalesced 128-byte lines
+          const float* src = imgb + ((size_t)(by0 + r) * W + bx0) * 3;
+          float* dst = tile + r * row_f;
+          for (int i = lane; i < row_f; i += 32) dst[i] = __ldg(src + i);
+        }
+        __syncthreads();
       }
-    } else if (active) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) gather3(imgb, W, t[j].y[k], t[j].x[k], t[j].w[k], acc + 3 * j);
     }
-    if (active) {
-      float4* o = reinterpret_cast<float4*>(out + (((size_t)b * H + oy) * W + ox) * 3);
-      __stcs(o + 0, make_float4(acc[0], acc[1], acc[2], acc[3]));
-      __stcs(o + 1, make_float4(acc[4], acc[5], acc[6], acc[7]));
-      __stcs(o + 2, make_float4(acc[8], acc[9], acc[10], acc[11]));
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int oy = t.oy0 + wid * 2 + rr;
+      if (oy < H) {  // warp-uniform
+        float v[2][3];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          v[h][0] = v[h][1] = v[h][2] = 0.0f;
+          if (on[rr][h]) {
+            const Taps tp = taps_tfwarp(fl[rr][h].x, fl[rr][h].y, t.ox0 + lane + 32 * h, oy, H, W);
+            if (kStaged && staged) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float* p = tile + ((tp.y[k] - by0) * bw + (tp.x[k] - bx0)) * 3;
+                v[h][0] = mul_add_rn(v[h][0], tp.w[k], p[0]);
+                v[h][1] = mul_add_rn(v[h][1], tp.w[k], p[1]);
+                v[h][2] = mul_add_rn(v[h][2], tp.w[k], p[2]);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) gather3(imgb, W, tp.y[k], tp.x[k], tp.w[k], v[h]);
+            }
+          }
+        }
+        store_row3(obuf[wid], out + (((size_t)t.b * H + oy) * W + t.ox0) * 3, lane, valid_px, v[0], v[1]);
+      }
     }
-    __syncthreads();  // tile / bbox reuse
+    if (kStaged) __syncthreads();  // tile / bbox reuse
   }
 }
 
@@ -438,25 +470,38 @@ int grid_for(size_t work_items, int threads) {
 
 int g_warp_variant = 1;  // 0 = direct gathers, 1 = shared-memory staged (default)
 
+size_t tile_count(int B, int oH, int oW) {
+  return (size_t)B * ((oH + kTileH - 1) / kTileH) * ((oW + kTileW - 1) / kTileW);
+}
+int tile_grid(size_t ntiles, int blocks_per_sm) {
+  const size_t cap = (size_t)sm_count() * blocks_per_sm;
+  return (int)std::max<size_t>(1, std::min(ntiles, cap));
+}
+
+// generic 4-tap samplers (grid_sample, Lie warp)
 template <class Provider>
 int launch_sampler(Provider prov, const float* img, float* out, int B, int srcH, int srcW, int oH, int oW, int C,
-                   bool allow_staged, cudaStream_t st) {
+                   cudaStream_t st) {
   if (B == 0 || oH == 0 || oW == 0) return OFS_OK;
-  const bool aligned = (((uintptr_t)out) % 16 == 0);
-  if (C == 3 && (oW % 4) == 0 && aligned) {
-    if (allow_staged && g_warp_variant == 1) {
-      const size_t ntiles = (size_t)B * ((oH + kTileH - 1) / kTileH) * ((oW + kTileW - 1) / kTileW);
-      const int sms = sm_count();
-      size_t blocks = ntiles < (size_t)sms * 4 ? ntiles : (size_t)sms * 4;
-      warp_staged3_kernel<Provider><<<(int)blocks, 256, 0, st>>>(prov, img, out, B, oH, oW);
-    } else {
-      const size_t quads = (size_t)B * oH * (oW / 4);
-      sample_quad3_kernel<Provider><<<grid_for(quads, 256), 256, 0, st>>>(prov, img, out, B, srcH, srcW, oH, oW);
-    }
+  if (C == 3 && (oW % 4) == 0 && (((uintptr_t)out) % 16 == 0)) {
+    const size_t nt = tile_count(B, oH, oW);
+    sample3_kernel<Provider><<<tile_grid(nt, 8), 256, 0, st>>>(prov, img, out, B, srcH, srcW, oH, oW);
   } else {
     const size_t px = (size_t)B * oH * oW;
     sample_px_kernel<Provider><<<grid_for(px, 256), 256, 0, st>>>(prov, img, out, B, srcH, srcW, oH, oW, C);
   }
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
+}
+
+// tf_warp family: flow providers, C == 3 fast path
+template <class Provider>
+int launch_warp3(Provider prov, const float* img, float* out, int B, int H, int W, cudaStream_t st) {
+  const size_t nt = tile_count(B, H, W);
+  if (g_warp_variant == 1)
+    warp3_kernel<Provider, true><<<tile_grid(nt, 5), 256, 0, st>>>(prov, img, out, B, H, W);
+  else
+    warp3_kernel<Provider, false><<<tile_grid(nt, 8), 256, 0, st>>>(prov, img, out, B, H, W);
   OFS_LAUNCH_CHECK();
   return OFS_OK;
 }
@@ -469,15 +514,11 @@ int tf_warp_impl(const float* img, const float* flow, float* out, int B, int H, 
   OFS_REQUIRE(img && flow && out, "ofs_tf_warp: null pointer");
   OFS_REQUIRE(((uintptr_t)flow) % 8 == 0, "ofs_tf_warp: flow must be 8-byte aligned");
   TfWarpProvider prov{flow, H, W};
-  const bool vec_ok = (((uintptr_t)flow) % 16 == 0);
-  if (!vec_ok || (W % 4) != 0 || C != 3) {
-    if (B == 0) return OFS_OK;
-    const size_t px = (size_t)B * H * W;
-    sample_px_kernel<TfWarpProvider><<<grid_for(px, 256), 256, 0, st>>>(prov, img, out, B, H, W, H, W, C);
-    OFS_LAUNCH_CHECK();
-    return OFS_OK;
-  }
-  return launch_sampler(prov, img, out, B, H, W, H, W, C, true, st);
+  if (C == 3 && (W % 4) == 0 && (((uintptr_t)out) % 16 == 0)) return launch_warp3(prov, img, out, B, H, W, st);
+  const size_t px = (size_t)B * H * W;
+  sample_px_kernel<TfWarpProvider><<<grid_for(px, 256), 256, 0, st>>>(prov, img, out, B, H, W, H, W, C);
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
 }
 
 int flow_resize_impl(const float* flow2, float* out, int B, int fh, int fw, int H, int W, cudaStream_t st) {
@@ -496,7 +537,11 @@ int flow_resize_warp_impl(const float* img, const float* flow2, float* out, int 
   if (B == 0) return OFS_OK;
   OFS_REQUIRE(img && flow2 && out, "ofs_flow_resize_warp: null pointer");
   ResizeWarpProvider prov{FlowResize{flow2, fh, fw, H, W, (float)fh / (float)H, (float)fw / (float)W, prescaled}};
-  return launch_sampler(prov, img, out, B, H, W, H, W, 3, true, st);
+  if ((W % 4) == 0 && (((uintptr_t)out) % 16 == 0)) return launch_warp3(prov, img, out, B, H, W, st);
+  const size_t px = (size_t)B * H * W;
+  sample_px_kernel<ResizeWarpProvider><<<grid_for(px, 256), 256, 0, st>>>(prov, img, out, B, H, W, H, W, 3);
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
 }
 
 }  // namespace ofs
@@ -531,7 +576,7 @@ static int grid_sample(const float* im, const float* theta, float* out, int B, i
   gc.step_x = oW > 1 ? 2.0f / (float)(oW - 1) : 0.0f;
   gc.step_y = oH > 1 ? 2.0f / (float)(oH - 1) : 0.0f;
   ofs::CoordProvider<ofs::GridSampleCoord> prov{gc};
-  return ofs::launch_sampler(prov, im, out, B, H, W, oH, oW, C, false, (cudaStream_t)stream);
+  return ofs::launch_sampler(prov, im, out, B, H, W, oH, oW, C, (cudaStream_t)stream);
 }
 
 int ofs_grid_sample_affine(const float* im, const float* theta, float* out, int B, int H, int W, int C, int oH,
@@ -560,7 +605,7 @@ int ofs_lie_warp(const float* image, const float* pMtrx, const float* refMtrx, f
   OFS_REQUIRE(image && pMtrx && refMtrx && out, "ofs_lie_warp: null pointer");
   ofs::LieCoord lc{pMtrx, refMtrx, srcH, srcW, outH, outW};
   ofs::CoordProvider<ofs::LieCoord> prov{lc};
-  return ofs::launch_sampler(prov, image, out, B, srcH, srcW, outH, outW, 3, false, (cudaStream_t)stream);
+  return ofs::launch_sampler(prov, image, out, B, srcH, srcW, outH, outW, 3, (cudaStream_t)stream);
 }
 
 }  // extern "C"

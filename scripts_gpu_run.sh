@@ -27,3 +27,6 @@ if [ "$1" == "ncu" ]; then
   tail -3 gpurun_out/ncu_launches.log gpurun_out/ncu_conv.log gpurun_out/ncu_misc.log
   ls -la gpurun_out
 fi
+if [ "$1" == "sweep" ] || [ "$2" == "sweep" ]; then
+  timeout 1200 python benchmarks/sampler_sweep.py --quick > gpurun_out/sweep.log 2>&1; tail -60 gpurun_out/sweep.log
+fi

@@ -73,27 +73,35 @@ def test_conv_gemm_vs_oracle(ofs, cuda_dev, prec, B, H, W, cin, cout, k, stride,
 
 
 TILING_CASES = [
-    # B, H, W, cin, cout, k, stride, transposed, block_n, ksplit
-    pytest.param(4, 6, 8, 512, 256, 3, 1, False, 128, 4, id="splitk4_whole_image_tiles"),
-    pytest.param(3, 6, 8, 256, 128, 3, 1, False, 128, 1, id="whole_image_tiles_ragged_batch"),
-    pytest.param(2, 12, 16, 256, 128, 3, 2, False, 128, 3, id="splitk3_k3s2"),
-    pytest.param(2, 6, 8, 256, 128, 4, 2, True, 128, 5, id="splitk5_deconv_uneven"),
-    pytest.param(1, 48, 64, 256, 256, 3, 1, False, 256, 1, id="block_n256"),
-    pytest.param(2, 24, 32, 128, 512, 3, 1, False, 256, 2, id="block_n256_splitk2"),
-    pytest.param(1, 24, 32, 128, 64, 3, 1, False, 32, 1, id="block_n32_two_n_tiles"),
+    # B, H, W, cin, cout, k, stride, transposed, block_n, ksplit, cta_group
+    pytest.param(4, 6, 8, 512, 256, 3, 1, False, 128, 4, 1, id="splitk4_whole_image_tiles"),
+    pytest.param(3, 6, 8, 256, 128, 3, 1, False, 128, 1, 1, id="whole_image_tiles_ragged_batch"),
+    pytest.param(2, 12, 16, 256, 128, 3, 2, False, 128, 3, 1, id="splitk3_k3s2"),
+    pytest.param(2, 6, 8, 256, 128, 4, 2, True, 128, 5, 1, id="splitk5_deconv_uneven"),
+    pytest.param(1, 48, 64, 256, 256, 3, 1, False, 256, 1, 1, id="block_n256"),
+    pytest.param(2, 24, 32, 128, 512, 3, 1, False, 256, 2, 1, id="block_n256_splitk2"),
+    pytest.param(1, 24, 32, 128, 64, 3, 1, False, 32, 1, 1, id="block_n32_two_n_tiles"),
+    pytest.param(1, 48, 64, 128, 128, 3, 1, False, 128, 1, 2, id="pair_n128"),
+    pytest.param(1, 48, 64, 256, 256, 3, 1, False, 256, 1, 2, id="pair_n256_conv3_1_shape"),
+    pytest.param(2, 32, 64, 64, 128, 5, 2, False, 128, 1, 2, id="pair_k5s2"),
+    pytest.param(1, 64, 128, 27, 64, 7, 2, False, 64, 1, 2, id="pair_conv1_form"),
+    pytest.param(3, 6, 8, 256, 256, 3, 1, False, 256, 1, 2, id="pair_odd_tile_count_whole_images"),
+    pytest.param(1, 12, 16, 130, 128, 4, 2, True, 64, 1, 2, id="pair_deconv_two_n_tiles"),
+    pytest.param(2, 24, 32, 256, 512, 3, 1, False, 256, 3, 2, id="pair_n256_splitk3"),
+    pytest.param(1, 16, 32, 194, 18, 1, 1, False, 32, 1, 2, id="pair_fp32_out_mode"),
 ]
 
 
-@pytest.mark.parametrize("B,H,W,cin,cout,k,stride,transposed,block_n,ksplit", TILING_CASES)
-def test_conv_gemm_tilings(ofs, cuda_dev, B, H, W, cin, cout, k, stride, transposed, block_n, ksplit):
-    """Explicit block_n / split-K variants of the same kernel (split-K output carries one bf16 rounding)."""
+@pytest.mark.parametrize("B,H,W,cin,cout,k,stride,transposed,block_n,ksplit,cta_group", TILING_CASES)
+def test_conv_gemm_tilings(ofs, cuda_dev, B, H, W, cin, cout, k, stride, transposed, block_n, ksplit, cta_group):
+    """Explicit block_n / split-K / CTA-pair variants (split-K output carries one bf16 rounding)."""
     gen = torch.Generator().manual_seed(77 + block_n + ksplit)
     x = _round(torch.rand((B, H, W, cin), generator=gen), "bf16")
     shape = (4, 4, cout, cin) if transposed else (k, k, cin, cout)
     w = _round(torch.randn(shape, generator=gen) * (1.0 / np.sqrt(k * k * cin)), "bf16")
     b = torch.randn(cout, generator=gen) * 0.1
     got = ofs.conv2d_nhwc(x.to(cuda_dev), w, b, stride=stride, transposed=transposed, lrelu=True, precision="bf16",
-                          block_n=block_n, ksplit=ksplit).cpu()
+                          block_n=block_n, ksplit=ksplit, cta_group=cta_group).cpu()
     if transposed:
         ref = T.conv2d_transpose_k4s2_same(x.double(), w.double(), b.double())
     else:
