@@ -1,0 +1,134 @@
+#!/usr/bin/env python
+"""Per-layer microbenchmark of the tcgen05 implicit-GEMM conv kernel (needs a B200).
+
+    python benchmarks/conv_bench.py [--batch 8] [--layers 3_1,4_1] [--variants "256:1:1,256:1:2"] [--trace]
+
+Each layer of flownetS_pyramid (reference model.py:807-880) is run stand-alone exactly as the network runs it
+(16-bit NHWC activations with the network's channel strides, packed weights, fused bias+lrelu epilogue) on
+device-resident pseudo-random operands through the measurement entry ofs_conv2d_bench.  A variant is
+block_n:ksplit:cta_group[:debug].  Prints us per launch, TFLOP/s on the LITERAL MACs of the layer, and with
+--trace the per-CTA role timeline (SM cycles) of one extra launch.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+# name: (H, W, cin, in_cs, cout, out_cs, k, stride, transposed, default variant)
+LAYERS = {
+    "1": (384, 512, 27, 32, 64, 64, 7, 2, 0),
+    "2": (192, 256, 64, 64, 128, 200, 5, 2, 0),
+    "3": (96, 128, 128, 200, 256, 256, 5, 2, 0),
+    "3_1": (48, 64, 256, 256, 256, 392, 3, 1, 0),
+    "4": (48, 64, 256, 392, 512, 512, 3, 2, 0),
+    "4_1": (24, 32, 512, 512, 512, 776, 3, 1, 0),
+    "5": (24, 32, 512, 776, 512, 512, 3, 2, 0),
+    "5_1": (12, 16, 512, 512, 512, 1032, 3, 1, 0),
+    "6": (12, 16, 512, 1032, 1024, 1024, 3, 2, 0),
+    "6_1": (6, 8, 1024, 1024, 1024, 1024, 3, 1, 0),
+    "deconv5": (6, 8, 1024, 1024, 512, 1032, 4, 2, 1),
+    "deconv4": (12, 16, 1026, 1032, 256, 776, 4, 2, 1),
+    "deconv3": (24, 32, 770, 776, 128, 392, 4, 2, 1),
+    "deconv2": (48, 64, 386, 392, 64, 200, 4, 2, 1),
+}
+DEFAULTS = {"1": "64:1:1", "2": "128:1:1", "3": "256:1:1", "3_1": "256:1:1", "4": "256:1:1", "4_1": "256:1:1",
+            "5": "256:6:1", "5_1": "256:6:1", "6": "256:8:1", "6_1": "256:8:1", "deconv5": "256:4:1",
+            "deconv4": "256:3:1", "deconv3": "128:1:1", "deconv2": "64:1:1"}
+
+
+def macs(name, B):
+    H, W, cin, _, cout, _, k, s, tr = LAYERS[name]
+    if tr:
+        return B * H * W * 16 * cin * cout
+    p = k // 2
+    return B * ((H + 2 * p - k) // s + 1) * ((W + 2 * p - k) // s + 1) * k * k * cin * cout
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--layers", default=",".join(LAYERS))
+    ap.add_argument("--variants", default="", help="comma list of block_n:ksplit:cta_group[:debug]; empty = network default")
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--flush-mb", type=int, default=0)
+    ap.add_argument("--trace", action="store_true")
+    ap.add_argument("--json", default="")
+    args = ap.parse_args()
+
+    import torch
+
+    import coupe.optical_flow_based_deep_video_stabilization_b200 as ofs
+    from coupe.optical_flow_based_deep_video_stabilization_b200 import _lib
+
+    lib = ofs.load_library()
+    fn = lib.ofs_conv2d_bench
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int] * 16 + [C.POINTER(C.c_float), C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p]
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    results = []
+    for name in args.layers.split(","):
+        H, W, cin, in_cs, cout, out_cs, k, s, tr = LAYERS[name]
+        variants = args.variants.split(",") if args.variants else [DEFAULTS[name]]
+        for v in variants:
+            parts = [int(x) for x in v.split(":")]
+            bn, ks, cg = parts[0], parts[1], parts[2]
+            dbg = parts[3] if len(parts) > 3 else 0
+            if cout % bn != 0:
+                continue
+            ms = C.c_float(0)
+            grid = C.c_int(0)
+            cap = 1024 * 16
+            trace = (C.c_longlong * cap)()
+            rc = fn(args.batch, H, W, cin, in_cs, cout, out_cs, k, s, tr, bn, ks, cg, dbg, args.iters, args.flush_mb,
+                    C.byref(ms), C.cast(trace, C.c_void_p) if args.trace else None, cap, C.byref(grid),
+                    _lib.current_stream_ptr(dev))
+            _lib.check(rc)
+            us = ms.value * 1e3
+            tf = 2 * macs(name, args.batch) / (ms.value * 1e-3) / 1e12
+            line = f"{name:8s} bn={bn:3d} ks={ks} cg={cg} dbg={dbg} grid={grid.value:3d}  {us:8.1f} us  {tf:7.1f} TF/s"
+            rec = {"layer": name, "block_n": bn, "ksplit": ks, "cta_group": cg, "debug": dbg, "grid": grid.value,
+                   "us": us, "tflops": tf}
+            if args.trace:
+                g = grid.value
+                rows = [[trace[i * 16 + j] for j in range(16)] for i in range(g)]
+                t0 = min(r[0] for r in rows)
+                span_ns = max(r[7] for r in rows) - t0
+                import statistics as st
+
+                def med(f):
+                    vals = [f(r) for r in rows if f(r) is not None]
+                    return st.median(vals) if vals else float("nan")
+
+                def mx(f):
+                    vals = [f(r) for r in rows if f(r) is not None]
+                    return max(vals) if vals else float("nan")
+                start_skew = mx(lambda r: r[0] - t0)
+                total = med(lambda r: r[9] - r[1])
+                tmax = mx(lambda r: r[9] - r[1])
+                prod = med(lambda r: r[2] - r[1] if r[2] else None)
+                first_full = med(lambda r: r[3] - r[1] if r[3] else None)
+                mma_done = med(lambda r: r[4] - r[1] if r[4] else None)
+                epi_first = med(lambda r: r[5] - r[1] if r[5] else None)
+                epi_done = med(lambda r: r[6] - r[1] if r[6] else None)
+                line += (f"\n           trace: span {span_ns / 1e3:.1f} us, start skew {start_skew / 1e3:.1f} us; cycles (median CTA): "
+                         f"total {total:.0f} (max {tmax:.0f}) | producer done {prod:.0f} | first full {first_full:.0f} | "
+                         f"mma issued {mma_done:.0f} | epi first {epi_first:.0f} | epi done {epi_done:.0f}")
+                rec["trace"] = {"span_us": span_ns / 1e3, "start_skew_us": start_skew / 1e3, "total": total, "total_max": tmax,
+                                "producer_done": prod, "first_full": first_full, "mma_issued": mma_done,
+                                "epi_first": epi_first, "epi_done": epi_done}
+            print(line, flush=True)
+            results.append(rec)
+    if args.json:
+        with open(args.json, "w") as f:
+            json.dump(results, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

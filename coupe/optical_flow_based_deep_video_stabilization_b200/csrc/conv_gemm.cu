@@ -154,14 +154,20 @@ __device__ __forceinline__ void commit(uint32_t bar) {
   else
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// desc = {lo, hi}: lo = (start address >> 4) | LBO field, hi = SBO | version | swizzle (constant)
 template <bool kPair>
-__device__ __forceinline__ void mma(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void mma(uint32_t d, uint32_t da_lo, uint32_t db_lo, uint32_t desc_hi, uint32_t idesc,
+                                    uint32_t accumulate) {
   if constexpr (kPair)
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
-                 "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d), "r"(da_lo), "r"(db_lo), "r"(desc_hi),
+        "r"(idesc), "r"(accumulate) : "memory");
   else
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
-                 "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d), "r"(da_lo), "r"(db_lo), "r"(desc_hi),
+        "r"(idesc), "r"(accumulate) : "memory");
 }
 }  // namespace lean
 
@@ -170,22 +176,32 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t da, uint64_t db, uint32
 //             empty[s]  MMA -> TMA, one per CTA; pair: released in both CTAs by the leader's multicast commit.
 //             tfull[a]  MMA -> epilogue, one per CTA (multicast commit after the last K block).
 //             tempty[a] epilogue -> MMA: 4 arrivals (1 CTA) / 8 (pair: the peer's warps arrive remotely).
+//
+// The producer and MMA-issuer loops run in ALL 32 lanes of their warp with warp-uniform control flow and
+// warp-uniform operands (kernel parameters, blockIdx, loop counters, values broadcast with __shfl_sync); only
+// the TMA / MMA / commit instructions themselves sit under an elected-lane predicate.  That lets ptxas keep
+// shared-memory addresses, TMA coordinates and UMMA descriptors in uniform registers.  A loop entered by
+// lane 0 alone (`if (lane == 0)`) makes every operand "possibly divergent" and each UTMALDG / UTCHMMA is then
+// wrapped in an ELECT + R2UR waterfall loop: ~2x the cycles per K block (see profiles/r01_tuning.md).
 template <int BLOCK_N, bool kPair>
 __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
   using Cfg = GemmCfg<BLOCK_N, kPair>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * Cfg::kStageBytes);
   uint64_t* full = bars;             // [S]
   uint64_t* empty = bars + S;        // [S]
   uint64_t* tfull = bars + 2 * S;    // [2]
   uint64_t* tempty = bars + 2 * S + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  const uint32_t full0 = smem_base + (uint32_t)S * Cfg::kStageBytes, empty0 = full0 + 8 * S;
+  const uint32_t tfull0 = full0 + 16 * S, tempty0 = tfull0 + 16;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = kPair ? ptx::cluster_ctarank() : 0u;
+  const uint32_t rank = kPair ? __shfl_sync(0xffffffffu, ptx::cluster_ctarank(), 0) : 0u;
   const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // scheduling unit: CTA or CTA pair
   const int nunits = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
@@ -210,59 +226,59 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
   __syncthreads();
   if constexpr (kPair) ptx::cluster_sync();  // the peer's barriers exist before anything signals them
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
 
   const int num_kb = p.ntaps * p.nchunks;
   const int total_tiles = p.tiles_mp * p.tiles_n * p.phases * p.ksplit;
   const int tileW = 1 << p.tileW_log2;
-  const uint32_t smem_base = ptx::smem_u32(smem);
-  const uint32_t full0 = ptx::smem_u32(full), empty0 = ptx::smem_u32(empty);
+  long long* trace = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;
+  if (trace && threadIdx.x == 0) { trace[0] = (long long)ptx::globaltimer(); trace[1] = clock64(); }
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================================== TMA producer =====================================
-      const bool do_a = !(p.debug & 2), do_b = !(p.debug & 4);
-      const uint32_t stage_tx = (kPair ? 2u : 1u) * (uint32_t)((do_a ? p.a_bytes : 0) + (do_b ? Cfg::kBBytes : 0));
-      const uint32_t full_tgt0 = kPair ? ptx::mapa_u32(full0, 0) : full0;   // where TMA bytes are posted
-      const int piece_bytes = p.piece_rows * tileW * kBlockK * 2;
-      const int npieces = p.npieces;
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t sa = smem_base, full_s = full0, empty_s = empty0, full_t = full_tgt0;
-      for (int tile = unit; tile < total_tiles; tile += nunits) {
-        const int n_t = tile % p.tiles_n;
-        const int rest = tile / p.tiles_n;
-        const int m_t = kPair ? (rest % p.tiles_mp) * 2 + (int)rank : rest % p.tiles_mp;
-        const int rest2 = rest / p.tiles_mp;
-        const int ph = rest2 % p.phases;
-        const int ks = rest2 / p.phases;
-        const int gy0 = (m_t / p.tiles_x) * p.tile_rows;
-        const int ox0 = (m_t % p.tiles_x) << p.tileW_log2;
-        const int w_row = ph * p.n_pad + n_t * BLOCK_N + (kPair ? (int)rank * (BLOCK_N / 2) : 0);
-        const int b0 = gy0 / p.Hg;
-        const int y0 = gy0 - b0 * p.Hg;
-        int kb = ks * p.kb_per_split;
-        const int kb1 = min(num_kb, kb + p.kb_per_split);
-        int tap = kb / p.nchunks;
-        int ch = kb - tap * p.nchunks;
-        int kcol = kb * kBlockK;
-        while (kb < kb1) {
-          // per tap: everything but the channel offset is fixed
-          const int ti = ph * p.ntaps + tap;
-          int c = p.tap_c[ti] + ch * kBlockK;
-          const int x = ox0 + p.tap_x[ti];
-          const int pp = p.tap_p[ti];
-          const int yy = y0 + p.tap_y[ti];
-          const int ch_end = min(p.nchunks, ch + (kb1 - kb));
-          for (; ch < ch_end; ++ch, ++kb) {
-            lean::wait(empty_s, phase ^ 1);
+    // ===================================== TMA producer =====================================
+    const bool leader = ptx::elect_one();
+    const bool do_a = !(p.debug & 2), do_b = !(p.debug & 4);
+    const uint32_t stage_tx = (kPair ? 2u : 1u) * (uint32_t)((do_a ? p.a_bytes : 0) + (do_b ? Cfg::kBBytes : 0));
+    const uint32_t full_tgt0 = kPair ? ptx::mapa_u32(full0, 0) : full0;   // where TMA bytes are posted
+    const int piece_bytes = p.piece_rows * tileW * kBlockK * 2;
+    const int npieces = p.npieces;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t sa = smem_base, full_s = full0, empty_s = empty0, full_t = full_tgt0;
+    for (int tile = unit; tile < total_tiles; tile += nunits) {
+      const int n_t = tile % p.tiles_n;
+      const int rest = tile / p.tiles_n;
+      const int m_t = kPair ? (rest % p.tiles_mp) * 2 + (int)rank : rest % p.tiles_mp;
+      const int rest2 = rest / p.tiles_mp;
+      const int ph = rest2 % p.phases;
+      const int ks = rest2 / p.phases;
+      const int gy0 = (m_t / p.tiles_x) * p.tile_rows;
+      const int ox0 = (m_t % p.tiles_x) << p.tileW_log2;
+      const int w_row = ph * p.n_pad + n_t * BLOCK_N + (kPair ? (int)rank * (BLOCK_N / 2) : 0);
+      const int b0 = gy0 / p.Hg;
+      const int y0 = gy0 - b0 * p.Hg;
+      int kb = ks * p.kb_per_split;
+      const int kb1 = min(num_kb, kb + p.kb_per_split);
+      int tap = kb / p.nchunks;
+      int ch = kb - tap * p.nchunks;
+      int kcol = kb * kBlockK;
+      while (kb < kb1) {
+        // per tap: everything but the channel offset is fixed
+        const int ti = ph * p.ntaps + tap;
+        int c = p.tap_c[ti] + ch * kBlockK;
+        const int x = ox0 + p.tap_x[ti];
+        const int pp = p.tap_p[ti];
+        const int yy = y0 + p.tap_y[ti];
+        const int ylim = p.Hg + p.tap_y[ti];
+        const int ch_end = min(p.nchunks, ch + (kb1 - kb));
+        for (; ch < ch_end; ++ch, ++kb) {
+          lean::wait(empty_s, phase ^ 1);
+          if (leader) {
             if (!kPair || rank == 0) lean::expect_tx(full_s, stage_tx);
             if (do_a) {
               if (npieces == 1) {
                 lean::tma5d<kPair>(sa, &p.tmap_a, full_t, c, x, pp, yy, b0);
               } else {
                 int b = b0, y = yy;
-                const int ylim = p.Hg + p.tap_y[ti];
                 uint32_t dst = sa;
                 for (int pc = 0; pc < npieces; ++pc) {
                   lean::tma5d<kPair>(dst, &p.tmap_a, full_t, c, x, pp, y, b);
@@ -273,27 +289,32 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
               }
             }
             if (do_b) lean::tma2d<kPair>(sa + Cfg::kABytes, &p.tmap_w, full_t, kcol, w_row);
-            c += kBlockK;
-            kcol += kBlockK;
-            sa += Cfg::kStageBytes; full_s += 8; empty_s += 8; full_t += 8;
-            if (++stage == S) { stage = 0; phase ^= 1; sa = smem_base; full_s = full0; empty_s = empty0; full_t = full_tgt0; }
           }
-          ch = 0;
-          ++tap;
+          c += kBlockK;
+          kcol += kBlockK;
+          sa += Cfg::kStageBytes; full_s += 8; empty_s += 8; full_t += 8;
+          if (++stage == S) { stage = 0; phase ^= 1; sa = smem_base; full_s = full0; empty_s = empty0; full_t = full_tgt0; }
         }
+        ch = 0;
+        ++tap;
       }
     }
+    if (trace && leader) trace[2] = clock64();
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       // ====================================== MMA issuer ======================================
+      const bool leader = ptx::elect_one();
+      const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
       const uint32_t idesc = ptx::umma_idesc_f16(kPair ? 2 * kBlockM : kBlockM, BLOCK_N, p.is_bf16);
-      const uint64_t da0 = ptx::umma_desc_sw128(smem_base), db0 = ptx::umma_desc_sw128(smem_base + Cfg::kABytes);
-      constexpr uint64_t kStep = (uint64_t)(Cfg::kStageBytes >> 4);   // descriptor address field is in 16-byte units
+      // descriptors: only the low word (start address >> 4) changes; the high word is a constant
+      constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t da0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t db0 = (((smem_base + Cfg::kABytes) & 0x3FFFFu) >> 4) | (1u << 16);
+      constexpr uint32_t kStep = (uint32_t)(Cfg::kStageBytes >> 4);   // descriptor address field is in 16-byte units
       const bool do_mma = !(p.debug & 1);
-      const uint32_t tfull0 = ptx::smem_u32(tfull), tempty0 = ptx::smem_u32(tempty);
       int stage = 0;
       uint32_t phase = 0;
-      uint64_t da = da0, db = db0;
+      uint32_t da = da0, db = db0;
       uint32_t full_s = full0, empty_s = empty0;
       uint32_t acc = 0, acc_phase = 0;
       for (int tile = unit; tile < total_tiles; tile += nunits) {
@@ -306,28 +327,32 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
         for (int i = 0; i < nkb; ++i) {
           lean::wait(full_s, phase);
           ptx::tc_fence_after();
-          if (do_mma) {
-            lean::mma<kPair>(d_tmem, da, db, idesc, i > 0 ? 1u : 0u);   // 4 x K=16 inside the 128-byte swizzle row
-            lean::mma<kPair>(d_tmem, da + 2, db + 2, idesc, 1u);
-            lean::mma<kPair>(d_tmem, da + 4, db + 4, idesc, 1u);
-            lean::mma<kPair>(d_tmem, da + 6, db + 6, idesc, 1u);
+          if (trace && leader && tile == unit && i == 0) trace[3] = clock64();
+          if (leader) {
+            if (do_mma) {
+              lean::mma<kPair>(d_tmem, da, db, kDescHi, idesc, i > 0 ? 1u : 0u);   // 4 x K=16 inside the 128-byte swizzle row
+              lean::mma<kPair>(d_tmem, da + 2, db + 2, kDescHi, idesc, 1u);
+              lean::mma<kPair>(d_tmem, da + 4, db + 4, kDescHi, idesc, 1u);
+              lean::mma<kPair>(d_tmem, da + 6, db + 6, kDescHi, idesc, 1u);
+            }
+            lean::commit<kPair>(empty_s);   // the stage is reusable (in both CTAs) once these MMAs have read it
           }
-          lean::commit<kPair>(empty_s);   // the stage is reusable (in both CTAs) once these MMAs have read it
           da += kStep; db += kStep; full_s += 8; empty_s += 8;
           if (++stage == S) { stage = 0; phase ^= 1; da = da0; db = db0; full_s = full0; empty_s = empty0; }
         }
-        lean::commit<kPair>(tfull0 + 8 * acc);   // accumulator complete
+        if (leader) lean::commit<kPair>(tfull0 + 8 * acc);   // accumulator complete
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
+      if (trace && leader) trace[4] = clock64();
     }
   } else {
     // ============================== epilogue (own 128 rows of every tile) =====================
+    const uint32_t tmem_base = *tmem_slot;
     const int quad = warp & 3;           // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;    // GEMM row inside this CTA's tile
     uint32_t acc = 0, acc_phase = 0;
-    const uint32_t tfull0 = ptx::smem_u32(tfull);
-    const uint32_t tempty_tgt0 = kPair ? ptx::mapa_u32(ptx::smem_u32(tempty), 0) : ptx::smem_u32(tempty);
+    const uint32_t tempty_tgt0 = kPair ? ptx::mapa_u32(tempty0, 0) : tempty0;
     for (int tile = unit; tile < total_tiles; tile += nunits) {
       const int n_t = tile % p.tiles_n;
       const int rest = tile / p.tiles_n;
@@ -348,6 +373,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
 
       lean::wait(tfull0 + 8 * acc, acc_phase);
       ptx::tc_fence_after();
+      if (trace && threadIdx.x == 64) { if (tile == unit) trace[5] = clock64(); trace[8] = clock64(); }
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
       constexpr int kChunk = BLOCK_N >= 32 ? 32 : 16;
 #pragma unroll 1
@@ -366,12 +392,15 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (trace && threadIdx.x == 64) trace[6] = clock64();
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (trace && threadIdx.x == 0) { trace[7] = (long long)ptx::globaltimer(); trace[9] = clock64(); }
   if constexpr (kPair) ptx::cluster_sync();  // no CTA frees TMEM or exits while the pair still references it
   if (warp == 1) {
+    const uint32_t tmem_base = *tmem_slot;
     if constexpr (kPair) ptx::tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
     else ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
@@ -699,7 +728,7 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
   p.n_pad = ((d.cout + d.block_n - 1) / d.block_n) * d.block_n;
   p.tiles_n = p.n_pad / d.block_n;
   p.n_valid = d.cout;
-  p.out_mode = d.out_mode; p.lrelu = d.lrelu; p.is_bf16 = d.is_bf16; p.debug = d.debug;
+  p.out_mode = d.out_mode; p.lrelu = d.lrelu; p.is_bf16 = d.is_bf16; p.debug = d.debug; p.trace = d.trace;
   p.out_cstride = d.out_cstride; p.out_coff = d.out_coff;
   if (d.out_mode == 0) {
     OFS_REQUIRE(p.n_pad == d.cout, "16-bit output mode needs cout %% block_n == 0 (cout %d, block_n %d)", d.cout, d.block_n);
@@ -947,6 +976,98 @@ extern "C" int ofs_conv2d_nhwc(const float* x, const float* w_host, const float*
                                ofs_stream stream) {
   return ofs_conv2d_nhwc_ex(x, w_host, b_host, y, B, H, W, Cin, Cout, k, stride, transposed, lrelu, precision, 0, 1, 1,
                             stream);
+}
+
+// Measurement entry (benchmarks/conv_bench.py; not part of the product API): one conv layer exactly as the
+// network runs it (16-bit activations in, 16-bit slice out), device-resident pseudo-random operands, `iters`
+// launches between two CUDA events on `stream`.  flush_mb > 0 writes a buffer of that many MB between
+// launches (outside no timed span: each launch is then timed by its own event pair and averaged).
+// trace (optional, host): [grid][16] per-CTA timestamps of one extra launch, see ConvGemmParams::trace.
+namespace ofs {
+namespace {
+__global__ void fill16_kernel(uint16_t* p, size_t n, uint32_t seed, int is_bf16, float scale) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u + seed;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    const float v = ((float)(h & 0xffff) / 32768.0f - 1.0f) * scale;
+    if (is_bf16) { __nv_bfloat16 b = __float2bfloat16_rn(v); p[i] = *reinterpret_cast<uint16_t*>(&b); }
+    else { __half b = __float2half_rn(v); p[i] = *reinterpret_cast<uint16_t*>(&b); }
+  }
+}
+__global__ void flush_kernel(uint4* p, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = make_uint4((uint32_t)i, 0, 0, 0);
+}
+}  // namespace
+}  // namespace ofs
+
+extern "C" int ofs_conv2d_bench(int B, int H, int W, int Cin, int in_cs, int Cout, int out_cs, int k, int stride,
+                                int transposed, int block_n, int ksplit, int cta_group, int debug, int iters,
+                                int flush_mb, float* ms_avg, long long* trace_host, int trace_cap, int* grid_out,
+                                ofs_stream stream) {
+  using namespace ofs;
+  cudaStream_t st = (cudaStream_t)stream;
+  OFS_REQUIRE(ms_avg && iters >= 1, "ofs_conv2d_bench: bad arguments");
+  int dev = 0;
+  OFS_CUDA(cudaGetDevice(&dev));
+  int rc = require_sm100(dev);
+  if (rc != OFS_OK) return rc;
+  ConvDesc d;
+  d.kind = transposed ? kDeconvK4S2 : kConv;
+  d.B = B; d.H = H; d.W = W; d.cin = Cin; d.in_cs = in_cs; d.cout = Cout; d.k = k; d.stride = stride;
+  d.block_n = block_n; d.ksplit = ksplit > 1 ? ksplit : 1; d.cta_group = cta_group == 2 ? 2 : 1; d.debug = debug;
+  const bool out16 = (Cout % block_n) == 0;
+  d.out_mode = out16 ? 0 : 1; d.lrelu = 1; d.is_bf16 = 1; d.out_cstride = out_cs; d.out_coff = 0;
+  ConvPlan plan;
+  rc = conv_plan_geometry(plan, d);
+  if (rc != OFS_OK) return rc;
+  const size_t npix = (size_t)B * H * W, npix_out = (size_t)B * plan.p.out_H * plan.p.out_W;
+  const size_t w_elems = (size_t)plan.w_rows * plan.k_total;
+  void *x16 = nullptr, *w_dev = nullptr, *y = nullptr, *fl = nullptr;
+  float *b_dev = nullptr, *ws = nullptr;
+  long long* tr = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  auto cleanup = [&]() {
+    for (void* q : {x16, w_dev, y, fl, (void*)b_dev, (void*)ws, (void*)tr}) if (q) cudaFree(q);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  };
+  const size_t flush_bytes = (size_t)flush_mb << 20;
+  bool ok = cudaMalloc(&x16, npix * in_cs * 2) == cudaSuccess && cudaMalloc(&w_dev, w_elems * 2) == cudaSuccess &&
+            cudaMalloc(&y, npix_out * out_cs * (out16 ? 2 : 4)) == cudaSuccess &&
+            cudaMalloc((void**)&b_dev, (size_t)plan.p.n_pad * 4) == cudaSuccess &&
+            (plan.ws_bytes == 0 || cudaMalloc((void**)&ws, plan.ws_bytes) == cudaSuccess) &&
+            (flush_bytes == 0 || cudaMalloc(&fl, flush_bytes) == cudaSuccess) &&
+            cudaMalloc((void**)&tr, (size_t)plan.grid * 16 * 8) == cudaSuccess &&
+            cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess;
+  if (!ok) { cleanup(); set_error("ofs_conv2d_bench: allocation failed"); return OFS_ENOMEM; }
+  fill16_kernel<<<sm_count() * 4, 256, 0, st>>>((uint16_t*)x16, npix * in_cs, 1u, 1, 1.0f);
+  fill16_kernel<<<sm_count() * 4, 256, 0, st>>>((uint16_t*)w_dev, w_elems, 2u, 1, 0.05f);
+  cudaMemsetAsync(b_dev, 0, (size_t)plan.p.n_pad * 4, st);
+  cudaMemsetAsync(tr, 0, (size_t)plan.grid * 16 * 8, st);
+  rc = conv_plan_bind(plan, x16, w_dev, b_dev, y, ws);
+  double total_ms = 0.0;
+  for (int it = -3; it < iters && rc == OFS_OK; ++it) {   // 3 warm-up launches
+    if (fl) flush_kernel<<<sm_count() * 8, 256, 0, st>>>((uint4*)fl, flush_bytes / 16);
+    cudaEventRecord(e0, st);
+    rc = conv_launch(plan, st);
+    cudaEventRecord(e1, st);
+    if (rc == OFS_OK) rc = check_cuda(cudaStreamSynchronize(st), "conv bench sync", __FILE__, __LINE__);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (it >= 0) total_ms += ms;
+  }
+  if (rc == OFS_OK) *ms_avg = (float)(total_ms / iters);
+  if (rc == OFS_OK && trace_host && trace_cap >= plan.grid * 16) {
+    plan.p.trace = tr;
+    if (fl) flush_kernel<<<sm_count() * 8, 256, 0, st>>>((uint4*)fl, flush_bytes / 16);
+    rc = conv_launch(plan, st);
+    if (rc == OFS_OK) rc = check_cuda(cudaStreamSynchronize(st), "conv bench trace sync", __FILE__, __LINE__);
+    if (rc == OFS_OK) cudaMemcpy(trace_host, tr, (size_t)plan.grid * 16 * 8, cudaMemcpyDeviceToHost);
+  }
+  if (grid_out) *grid_out = plan.grid;
+  cleanup();
+  return rc;
 }
 
 // Host-only introspection of the plan (geometry, tap table, activation view, packed weights): lets

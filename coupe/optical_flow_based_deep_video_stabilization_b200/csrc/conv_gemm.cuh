@@ -47,6 +47,7 @@ struct ConvGemmParams {
   int lrelu;           // apply max(v, 0.1 v)
   int is_bf16;         // operand / storage format: 1 bf16, 0 fp16
   int debug;           // measurement only: bit0 skip MMAs, bit1 skip A loads, bit2 skip B loads (results garbage)
+  long long* trace;    // measurement only: per-CTA timestamps [grid][16] (null in production)
   int out_oy[4], out_ox[4];  // per-phase sub-pixel offset
   // per (phase, tap) TMA coordinate offsets: channel base, x offset, parity plane, y offset
   short tap_c[kMaxTapEntries], tap_x[kMaxTapEntries], tap_p[kMaxTapEntries], tap_y[kMaxTapEntries];
@@ -67,6 +68,7 @@ struct ConvDesc {
   int ksplit = 1;      // > 1: split the K loop over this many CTAs per tile (16-bit output mode only)
   int cta_group = 1;   // 2: CTA pairs (tcgen05 cta_group::2): tile = 256 GEMM rows x BLOCK_N, B split over the pair
   int debug = 0;       // see ConvGemmParams::debug
+  long long* trace = nullptr;  // see ConvGemmParams::trace
 };
 
 struct ConvPlan {
