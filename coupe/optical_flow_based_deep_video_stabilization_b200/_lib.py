@@ -53,7 +53,7 @@ PROTOTYPES = {
     "ofs_net_profile": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, C.POINTER(_i), _p]),
     "ofs_net_launches_per_forward": (_i, [_p]),
     "ofs_conv2d_nhwc": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
-    "ofs_conv2d_nhwc_ex": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "ofs_conv2d_nhwc_ex": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
 }
 # host-only introspection used by the CPU test-suite (not part of the product API)
 DEBUG_PROTOTYPES = {

@@ -97,7 +97,9 @@ struct GemmCfg {
   static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
   static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
   static constexpr int kBarBytes = 256;
-  static constexpr size_t kSmem = (size_t)kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+  static constexpr int kStgBytes = kBlockM * 128;        // one 64-channel chunk of the 16-bit output tile (SW128 rows)
+  static constexpr int kStgTotal = BLOCK_N >= 64 ? 2 * kStgBytes : 0;   // double buffered; narrow tiles store directly
+  static constexpr size_t kSmem = (size_t)kStages * kStageBytes + kStgTotal + kBarBytes + 1024;  // + alignment slack
 };
 
 // The TMA-producer and MMA-issuer roles are single threads running dependent-issue code (~4-5 cycles per
@@ -190,13 +192,14 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * Cfg::kStageBytes + Cfg::kStgTotal);
   uint64_t* full = bars;             // [S]
   uint64_t* empty = bars + S;        // [S]
   uint64_t* tfull = bars + 2 * S;    // [2]
   uint64_t* tempty = bars + 2 * S + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
-  const uint32_t full0 = smem_base + (uint32_t)S * Cfg::kStageBytes, empty0 = full0 + 8 * S;
+  const uint32_t stg0 = smem_base + (uint32_t)S * Cfg::kStageBytes;   // 1024-byte aligned
+  const uint32_t full0 = stg0 + Cfg::kStgTotal, empty0 = full0 + 8 * S;
   const uint32_t tfull0 = full0 + 16 * S, tempty0 = tfull0 + 16;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
@@ -208,6 +211,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&p.tmap_a);
     ptx::prefetch_tensormap(&p.tmap_w);
+    if (p.tma_store) for (int i = 0; i < p.phases; ++i) ptx::prefetch_tensormap(&p.tmap_o[i]);
     for (int i = 0; i < S; ++i) {
       ptx::mbar_init(&full[i], 1);
       ptx::mbar_init(&empty[i], 1);
@@ -351,7 +355,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
     const uint32_t tmem_base = *tmem_slot;
     const int quad = warp & 3;           // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;    // GEMM row inside this CTA's tile
-    uint32_t acc = 0, acc_phase = 0;
+    uint32_t acc = 0, acc_phase = 0, stg_parity = 0;
     const uint32_t tempty_tgt0 = kPair ? ptx::mapa_u32(tempty0, 0) : tempty0;
     for (int tile = unit; tile < total_tiles; tile += nunits) {
       const int n_t = tile % p.tiles_n;
@@ -375,23 +379,86 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
       ptx::tc_fence_after();
       if (trace && threadIdx.x == 64) { if (tile == unit) trace[5] = clock64(); trace[8] = clock64(); }
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
-      constexpr int kChunk = BLOCK_N >= 32 ? 32 : 16;
+      bool stored = false;
+      if constexpr (BLOCK_N >= 64) {
+        if (p.tma_store) {
+          // 16-bit epilogue: TMEM -> registers -> (+bias, lrelu, pack) -> SW128-swizzled staging rows ->
+          // one TMA store per 64-channel chunk and A-style piece.  The staging buffer of chunk c is reused
+          // by chunk c+2: thread 64 waits for its previous store to finish reading before the chunk barrier.
+          stored = true;
+          const uint32_t sw = (uint32_t)(row & 7);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += kChunk) {
-        uint32_t v[kChunk];
-        if constexpr (kChunk == 32) ptx::tmem_ld32(t_addr + c0, v); else ptx::tmem_ld16(t_addr + c0, v);
-        ptx::tmem_wait_ld();
-        if (valid) epilogue_store<kChunk>(p, v, pix, n0 + c0, ks);
+          for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {
+            const uint32_t buf = stg0 + (stg_parity ? Cfg::kStgBytes : 0);
+            const uint32_t rowaddr = buf + (uint32_t)row * 128u;
+            const float* bias = p.bias + n0 + c0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t v[32];
+              ptx::tmem_ld32(t_addr + c0 + 32 * h, v);
+              ptx::tmem_wait_ld();
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float a = __uint_as_float(v[2 * j]) + __ldg(bias + 32 * h + 2 * j);
+                float b2 = __uint_as_float(v[2 * j + 1]) + __ldg(bias + 32 * h + 2 * j + 1);
+                if (p.lrelu) { a = fmaxf(a, 0.1f * a); b2 = fmaxf(b2, 0.1f * b2); }
+                pk[j] = pack16(a, b2, p.is_bf16);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                ptx::st_shared_v4(rowaddr + ((((uint32_t)(4 * h + j)) ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2],
+                                  pk[4 * j + 3]);
+            }
+            if (c0 + 64 >= BLOCK_N) {   // every accumulator column of this tile has been read: release the TMEM stage
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if constexpr (kPair) ptx::mbar_arrive_cluster(tempty_tgt0 + 8 * acc);
+                else ptx::mbar_arrive(&tempty[acc]);
+              }
+            }
+            ptx::fence_proxy_async_smem();
+            if (threadIdx.x == 64) ptx::bulk_wait_read0();   // the other buffer is free again after this barrier
+            ptx::named_bar_sync(1, 128);
+            if (threadIdx.x == 64 && m_t < p.tiles_m && !(p.debug & 8)) {
+              const int gy0 = (m_t / p.tiles_x) * p.tile_rows;
+              const int ox0 = (m_t % p.tiles_x) << p.tileW_log2;
+              int bb = gy0 / p.Hg, yy = gy0 - bb * p.Hg;
+              uint32_t src = buf;
+              const uint32_t piece_bytes = (uint32_t)(p.piece_rows << p.tileW_log2) * 128u;
+              for (int pc = 0; pc < p.npieces; ++pc) {
+                ptx::tma_store_4d(&p.tmap_o[ph], src, n0 + c0, ox0, yy, bb);
+                src += piece_bytes;
+                yy += p.piece_rows;
+                if (yy >= p.Hg) { yy -= p.Hg; ++bb; }
+              }
+              ptx::bulk_commit_group();
+            }
+            stg_parity ^= 1u;
+          }
+        }
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (kPair) ptx::mbar_arrive_cluster(tempty_tgt0 + 8 * acc);
-        else ptx::mbar_arrive(&tempty[acc]);
+      if (!stored) {
+        constexpr int kChunk = BLOCK_N >= 32 ? 32 : 16;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += kChunk) {
+          uint32_t v[kChunk];
+          if constexpr (kChunk == 32) ptx::tmem_ld32(t_addr + c0, v); else ptx::tmem_ld16(t_addr + c0, v);
+          ptx::tmem_wait_ld();
+          if (valid) epilogue_store<kChunk>(p, v, pix, n0 + c0, ks);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kPair) ptx::mbar_arrive_cluster(tempty_tgt0 + 8 * acc);
+          else ptx::mbar_arrive(&tempty[acc]);
+        }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (threadIdx.x == 64) ptx::bulk_wait_all();   // outstanding TMA stores complete before the CTA retires
     if (trace && threadIdx.x == 64) trace[6] = clock64();
   }
 
@@ -746,6 +813,7 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
     plan.ws_bytes = p.ksplit > 1 ? (size_t)p.ksplit * p.ws_split_stride * 4 : 0;
     if (p.ksplit > 1) p.out_mode = 2;
   }
+  p.tma_store = (p.out_mode == 0 && d.block_n >= 64) ? 1 : 0;
   p.tiles_mp = d.cta_group == 2 ? (p.tiles_m + 1) / 2 : p.tiles_m;
   const int total_tiles = p.tiles_mp * p.tiles_n * p.phases * p.ksplit;
   if (d.cta_group == 2) {
@@ -846,6 +914,17 @@ int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const 
   cuuint32_t box[5] = {(cuuint32_t)kBlockK, tileW, 1, (cuuint32_t)p.box_y, (cuuint32_t)p.box_b};
   int st = encode_map(&p.tmap_a, d.is_bf16, 5, act_in, dims, str, box);
   if (st != OFS_OK) return st;
+  if (p.tma_store) {
+    const cuuint64_t cs = (cuuint64_t)d.out_cstride, sc = (cuuint64_t)p.out_scale;
+    for (int ph = 0; ph < p.phases; ++ph) {
+      const size_t off = ((size_t)p.out_oy[ph] * p.out_W + p.out_ox[ph]) * cs + (size_t)d.out_coff;
+      cuuint64_t od[4] = {(cuuint64_t)d.cout, (cuuint64_t)p.Wg, (cuuint64_t)p.Hg, (cuuint64_t)d.B};
+      cuuint64_t os[3] = {sc * cs * 2, sc * (cuuint64_t)p.out_W * cs * 2, (cuuint64_t)p.out_H * p.out_W * cs * 2};
+      cuuint32_t ob[4] = {(cuuint32_t)kBlockK, tileW, (cuuint32_t)p.box_y, (cuuint32_t)p.box_b};
+      st = encode_map(&p.tmap_o[ph], d.is_bf16, 4, reinterpret_cast<uint16_t*>(out) + off, od, os, ob);
+      if (st != OFS_OK) return st;
+    }
+  }
   cuuint64_t wd[2] = {(cuuint64_t)plan.k_total, (cuuint64_t)plan.w_rows};
   cuuint64_t ws[1] = {(cuuint64_t)plan.k_total * 2};
   cuuint32_t wb[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(plan.block_n / d.cta_group)};
@@ -899,7 +978,7 @@ int launch_unpack_act(const void* in, float* out, size_t npix, int cs, int coff,
 // ------------------------------------------------------------------------------------------------
 extern "C" int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const float* b_host, float* y, int B, int H,
                                   int W, int Cin, int Cout, int k, int stride, int transposed, int lrelu, int precision,
-                                  int block_n, int ksplit, int cta_group, ofs_stream stream) {
+                                  int block_n, int ksplit, int cta_group, int out16, ofs_stream stream) {
   using namespace ofs;
   cudaStream_t st = (cudaStream_t)stream;
   OFS_REQUIRE(x && w_host && y, "ofs_conv2d_nhwc: null pointer");
@@ -919,7 +998,7 @@ extern "C" int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const flo
   d.block_n = block_n > 0 ? block_n : (Cout >= 128 ? 128 : (Cout >= 64 ? 64 : (Cout >= 32 ? 32 : 16)));
   d.ksplit = ksplit > 1 ? ksplit : 1;
   d.cta_group = cta_group == 2 ? 2 : 1;
-  const bool via16 = d.ksplit > 1;   // split-K reduces into the 16-bit output format
+  const bool via16 = d.ksplit > 1 || out16;   // the network's 16-bit activation epilogue (split-K always reduces into it)
   const int cout8 = ((Cout + 7) / 8) * 8;
   d.out_mode = via16 ? 0 : 1; d.lrelu = lrelu; d.is_bf16 = is_bf16;
   d.out_cstride = via16 ? cout8 : Cout; d.out_coff = 0;
@@ -975,7 +1054,7 @@ extern "C" int ofs_conv2d_nhwc(const float* x, const float* w_host, const float*
                                int Cin, int Cout, int k, int stride, int transposed, int lrelu, int precision,
                                ofs_stream stream) {
   return ofs_conv2d_nhwc_ex(x, w_host, b_host, y, B, H, W, Cin, Cout, k, stride, transposed, lrelu, precision, 0, 1, 1,
-                            stream);
+                            0, stream);
 }
 
 // Measurement entry (benchmarks/conv_bench.py; not part of the product API): one conv layer exactly as the

@@ -14,6 +14,8 @@ constexpr int kMaxTapEntries = 64;
 struct ConvGemmParams {
   CUtensorMap tmap_a;  // 5-D view of the NHWC 16-bit activation (see conv_gemm.cu)
   CUtensorMap tmap_w;  // 2-D packed weights [phases * n_pad rows][K_total], K-major (box rows: BLOCK_N / cta_group)
+  CUtensorMap tmap_o[4];  // per phase: 4-D view [c, x, y, b] of this layer's 16-bit output slice (TMA-store epilogue)
+  int tma_store;       // 1: 16-bit epilogue goes through swizzled shared-memory staging + cp.async.bulk.tensor stores
   // M grid (output pixels; for the transposed conv: input pixels, one GEMM per sub-pixel phase)
   int Hg, Wg;          // grid height / width per image
   int rows_total;      // B * Hg

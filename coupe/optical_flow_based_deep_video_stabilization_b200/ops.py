@@ -90,7 +90,8 @@ def set_warp_variant(variant):
     _lib.check(_lib.load().ofs_set_warp_variant(int(variant)))
 
 
-def conv2d_nhwc(x, w, b=None, stride=1, transposed=False, lrelu=False, precision="bf16", block_n=0, ksplit=1, cta_group=1):
+def conv2d_nhwc(x, w, b=None, stride=1, transposed=False, lrelu=False, precision="bf16", block_n=0, ksplit=1, cta_group=1,
+                out16=False):
     """Stand-alone run of the network's tcgen05 implicit-GEMM conv kernel (tests / microbench).
 
     x [B,H,W,Cin] CUDA f32; w CPU f32 TF layout ([k,k,Cin,Cout], or [4,4,Cout,Cin] when transposed);
@@ -114,5 +115,5 @@ def conv2d_nhwc(x, w, b=None, stride=1, transposed=False, lrelu=False, precision
     with torch.cuda.device(x.device):
         _lib.check(lib.ofs_conv2d_nhwc_ex(_lib.ptr(x), _lib.ptr(w), _lib.ptr(bb), _lib.ptr(y), B, H, W, Cin, Cout, k,
                                           int(stride), int(bool(transposed)), int(bool(lrelu)), prec, int(block_n),
-                                          int(ksplit), int(cta_group), _lib.current_stream_ptr(x.device)))
+                                          int(ksplit), int(cta_group), int(bool(out16)), _lib.current_stream_ptr(x.device)))
     return y
