@@ -230,6 +230,9 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
   __syncthreads();
   if constexpr (kPair) ptx::cluster_sync();  // the peer's barriers exist before anything signals them
   ptx::tc_fence_after();
+  // everything above overlapped the previous kernel's tail; from here on its results are needed
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int num_kb = p.ntaps * p.nchunks;
   const int total_tiles = p.tiles_mp * p.tiles_n * p.phases * p.ksplit;
@@ -486,6 +489,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_act_kernel(const float* __restrict__ in, uint4* __restrict__ out, size_t npix, int cin, int cs,
                                 int is_bf16) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int groups = cs >> 3;
   const size_t total = npix * groups;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -502,6 +507,8 @@ __global__ void pack_act_kernel(const float* __restrict__ in, uint4* __restrict_
 
 __global__ void unpack_act_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, size_t npix, int cs,
                                   int coff, int c, int is_bf16) {
+  pdl_wait();
+  pdl_launch_dependents();
   const size_t total = npix * c;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t pix = i / c;
@@ -522,6 +529,8 @@ __global__ void unpack_act_kernel(const uint16_t* __restrict__ in, float* __rest
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int ksplit, long long split_stride, size_t npix,
                                      int n_pad, const float* __restrict__ bias, uint16_t* __restrict__ out,
                                      int out_cstride, int out_coff, int lrelu, int is_bf16) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int groups = n_pad >> 3;
   const size_t total = npix * groups;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -592,7 +601,7 @@ int launch_t(const ConvPlan& plan, cudaStream_t st) {
                                   (int)GemmCfg<BLOCK_N, false>::kSmem));
     attr_set[dev] = true;
   }
-  conv_gemm_kernel<BLOCK_N><<<plan.grid, kThreads, GemmCfg<BLOCK_N, false>::kSmem, st>>>(plan.p);
+  OFS_CUDA(launch_pdl(conv_gemm_kernel<BLOCK_N>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, false>::kSmem, st, plan.p));
   OFS_LAUNCH_CHECK();
   return OFS_OK;
 }
@@ -607,7 +616,7 @@ int launch_t2(const ConvPlan& plan, cudaStream_t st) {
                                   (int)GemmCfg<BLOCK_N, true>::kSmem));
     attr_set[dev] = true;
   }
-  conv_gemm2_kernel<BLOCK_N><<<plan.grid, kThreads, GemmCfg<BLOCK_N, true>::kSmem, st>>>(plan.p);
+  OFS_CUDA(launch_pdl(conv_gemm2_kernel<BLOCK_N>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, true>::kSmem, st, plan.p));
   OFS_LAUNCH_CHECK();
   return OFS_OK;
 }
@@ -617,9 +626,9 @@ int launch_reduce(const ConvPlan& plan, cudaStream_t st) {
   const size_t npix = (size_t)plan.d.B * p.out_H * p.out_W;
   const size_t total = npix * (p.n_pad / 8);
   const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
-  splitk_reduce_kernel<<<blocks, 256, 0, st>>>(plan.ws, p.ksplit, p.ws_split_stride, npix, p.n_pad, plan.bias_dev,
-                                               reinterpret_cast<uint16_t*>(plan.final_out), plan.d.out_cstride,
-                                               plan.d.out_coff, plan.d.lrelu, plan.d.is_bf16);
+  OFS_CUDA(launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, st, (const float*)plan.ws, p.ksplit,
+                      p.ws_split_stride, npix, p.n_pad, plan.bias_dev, reinterpret_cast<uint16_t*>(plan.final_out),
+                      plan.d.out_cstride, plan.d.out_coff, plan.d.lrelu, plan.d.is_bf16));
   OFS_LAUNCH_CHECK();
   return OFS_OK;
 }
@@ -959,7 +968,8 @@ int launch_pack_act(const float* in, void* out, size_t npix, int cin, int cs, in
   if (npix == 0) return OFS_OK;
   const size_t total = npix * (cs / 8);
   size_t blocks = std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
-  pack_act_kernel<<<(int)blocks, 256, 0, st>>>(in, reinterpret_cast<uint4*>(out), npix, cin, cs, is_bf16);
+  OFS_CUDA(launch_pdl(pack_act_kernel, dim3((unsigned)blocks), dim3(256), 0, st, in, reinterpret_cast<uint4*>(out), npix, cin,
+                      cs, is_bf16));
   OFS_LAUNCH_CHECK();
   return OFS_OK;
 }
@@ -968,7 +978,8 @@ int launch_unpack_act(const void* in, float* out, size_t npix, int cs, int coff,
   if (npix == 0) return OFS_OK;
   const size_t total = npix * c;
   size_t blocks = std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
-  unpack_act_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(in), out, npix, cs, coff, c, is_bf16);
+  OFS_CUDA(launch_pdl(unpack_act_kernel, dim3((unsigned)blocks), dim3(256), 0, st, reinterpret_cast<const uint16_t*>(in), out,
+                      npix, cs, coff, c, is_bf16));
   OFS_LAUNCH_CHECK();
   return OFS_OK;
 }

@@ -84,6 +84,8 @@ __device__ __forceinline__ float2 pyr_flow_at(const PyrParams& p, int b, int i, 
 }
 
 __global__ void pyr_kernel(PyrParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int H2 = 2 * p.h, W2 = 2 * p.w;
   const size_t total = (size_t)p.B * H2 * W2;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -128,6 +130,8 @@ struct Predict2Params {
 
 // model.py:882-887: zero-pad(1) -> nearest(align_corners) to 384x512 -> 3x3 VALID -> + 8 x up(f3)
 __global__ void predict2_gather_kernel(Predict2Params p) {
+  pdl_wait();
+  pdl_launch_dependents();
   const size_t total = (size_t)p.B * 382 * 510;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int ox = (int)(idx % 510);
@@ -190,6 +194,8 @@ __device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uin
 
 __global__ void __launch_bounds__(288) head3x3_kernel(HeadParams p) {
   __shared__ float part[9][32];
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31, tap = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -289,6 +295,18 @@ struct ofs_net {
   // host-API staging
   float *st_feats = nullptr, *st_frames = nullptr, *st_out = nullptr;
   size_t st_frames_cap = 0;
+  // CUDA graphs of whole stabilize() steps, keyed by the call's pointers and shape (see ofs_net_stabilize)
+  struct StepGraph {
+    const float *feats, *frames;
+    float *out, *flow2;
+    int B, H, W;
+    cudaGraphExec_t exec;
+    int launches;
+    uint64_t last_use;
+  };
+  std::vector<StepGraph> graphs;
+  uint64_t graph_clock = 0;
+  int use_graphs = 1;
 };
 
 namespace {
@@ -382,6 +400,8 @@ int prepare(ofs_net* n, int B) {
     n->ws = nullptr;
     n->ws_bytes = 0;
     for (Layer& L : n->layers) L.plans.clear();
+    for (auto& g : n->graphs) cudaGraphExecDestroy(g.exec);   // they hold the old workspace pointer
+    n->graphs.clear();
     const size_t want = std::max(ws_need, (ws_need / (size_t)B) * (size_t)n->max_batch);
     OFS_CUDA(cudaMalloc((void**)&n->ws, want));
     n->ws_bytes = want;
@@ -404,7 +424,7 @@ int launch_head(ofs_net* n, const Head& h, int B, cudaStream_t st) {
   p.B = B; p.h = h.h; p.w = h.w; p.cs = h.cs; p.is_bf16 = n->is_bf16;
   const size_t npix = (size_t)B * h.h * h.w;
   const int blocks = (int)std::min<size_t>((npix + 15) / 16, (size_t)sm_count() * 6);
-  head3x3_kernel<<<blocks, 288, 0, st>>>(p);
+  OFS_CUDA(launch_pdl(head3x3_kernel, dim3(blocks), dim3(288), 0, st, p));
   OFS_LAUNCH_CHECK();
   return OFS_OK;
 }
@@ -437,7 +457,7 @@ int launch_pyr(ofs_net* n, int level, int B, cudaStream_t st) {
   }
   const size_t total = (size_t)B * 4 * p.h * p.w;
   const int blocks = (int)std::min<size_t>((total + 127) / 128, (size_t)sm_count() * 8);
-  pyr_kernel<<<blocks, 128, 0, st>>>(p);
+  OFS_CUDA(launch_pdl(pyr_kernel, dim3(blocks), dim3(128), 0, st, p));
   OFS_LAUNCH_CHECK();
   return OFS_OK;
 }
@@ -515,7 +535,7 @@ int forward_impl(ofs_net* n, const float* feats, int B, float* f2_target, cudaSt
   pp.B = B;
   const size_t total = (size_t)B * 382 * 510;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
-  predict2_gather_kernel<<<blocks, 256, 0, st>>>(pp);
+  OFS_CUDA(launch_pdl(predict2_gather_kernel, dim3(blocks), dim3(256), 0, st, pp));
   OFS_LAUNCH_CHECK();
   OFS_MARK("predict2_gather", 0.0);
   return OFS_OK;
@@ -535,6 +555,7 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
   OFS_CUDA(cudaSetDevice(device));
   ofs_net* n = new ofs_net();
   n->device = device; n->max_batch = max_batch; n->is_bf16 = precision == OFS_PREC_BF16;
+  { const char* e = getenv("OFS_GRAPH"); n->use_graphs = (e && e[0] == '0') ? 0 : 1; }
   const size_t B = (size_t)max_batch;
   struct { void** p; size_t elems; } bufs[] = {
       {&n->x0, B * 384 * 512 * 32},    {&n->conv1, B * 192 * 256 * 64}, {&n->concat2, B * 96 * 128 * 200},
@@ -640,6 +661,8 @@ int ofs_net_destroy(ofs_net* n) {
     if (n->ev_h2d[i]) cudaEventDestroy(n->ev_h2d[i]);
     if (n->ev_comp[i]) cudaEventDestroy(n->ev_comp[i]);
   }
+  for (auto& g : n->graphs) cudaGraphExecDestroy(g.exec);
+  n->graphs.clear();
   for (void* p : n->allocs) cudaFree(p);
   if (n->ws) cudaFree(n->ws);
   if (n->st_frames) cudaFree(n->st_frames);
@@ -749,6 +772,9 @@ int ofs_net_load_weights(ofs_net* n, const ofs_named_array* arrays, int count) {
   n->loaded = true;
   n->prepared_B = 0;
   for (Layer& L : n->layers) L.plans.clear();
+  OFS_CUDA(cudaDeviceSynchronize());
+  for (auto& g : n->graphs) cudaGraphExecDestroy(g.exec);   // head biases etc. are kernel arguments
+  n->graphs.clear();
   return OFS_OK;
 }
 
@@ -765,14 +791,62 @@ int ofs_net_forward(ofs_net* n, const float* feats, int B, float* f6, float* f5,
   return OFS_OK;
 }
 
+// One step = 30-odd dependent kernels of 3-150 us each: replayed as ONE CUDA graph (kernel nodes joined by
+// programmatic-dependent-launch edges), so neither host launch latency nor inter-kernel drain sits between
+// them.  A graph bakes in its pointers, so graphs are cached per (feats, frames, out, flow2_out, B, H, W);
+// streaming callers cycle through a few staging buffers and hit the cache after the first lap.
+// OFS_GRAPH=0 in the environment (read at ofs_net_create) falls back to plain stream launches.
 int ofs_net_stabilize(ofs_net* n, const float* feats, const float* frames, float* out, float* flow2_out, int B, int H,
                       int W, ofs_stream stream) {
-  OFS_REQUIRE(frames && out, "ofs_net_stabilize: null pointer");
+  OFS_REQUIRE(n && feats && frames && out, "ofs_net_stabilize: null pointer");
   OFS_REQUIRE(H > 0 && W > 0, "ofs_net_stabilize: bad frame size %dx%d", H, W);
+  OFS_REQUIRE(B >= 1 && B <= n->max_batch, "ofs_net_stabilize: batch %d outside [1, %d]", B, n->max_batch);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = forward_impl(n, feats, B, flow2_out, st);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (n->use_graphs) cudaStreamIsCapturing(st, &cap);
+  if (!n->use_graphs || !n->loaded || cap != cudaStreamCaptureStatusNone) {   // plain path (also when the caller captures)
+    int rc = forward_impl(n, feats, B, flow2_out, st);
+    if (rc != OFS_OK) return rc;
+    return flow_resize_warp_impl(frames, n->f2s, out, B, H, W, 382, 510, st, 1);
+  }
+  OFS_CUDA(cudaSetDevice(n->device));
+  ++n->graph_clock;
+  for (auto& g : n->graphs)
+    if (g.feats == feats && g.frames == frames && g.out == out && g.flow2 == flow2_out && g.B == B && g.H == H && g.W == W) {
+      g.last_use = n->graph_clock;
+      OFS_CUDA(cudaGraphLaunch(g.exec, st));
+      count_launch(g.launches);
+      return OFS_OK;
+    }
+  int rc = prepare(n, B);   // plans, TMA descriptors and workspace exist before the capture starts
   if (rc != OFS_OK) return rc;
-  return flow_resize_warp_impl(frames, n->f2s, out, B, H, W, 382, 510, st, 1);
+  const uint64_t l0 = launch_count();
+  // captured on the net's own stream (the caller's may be the legacy default stream, which cannot capture);
+  // the instantiated graph is launched on the caller's stream
+  cudaStream_t cs = n->stream;
+  OFS_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+  rc = forward_impl(n, feats, B, flow2_out, cs);
+  if (rc == OFS_OK) rc = flow_resize_warp_impl(frames, n->f2s, out, B, H, W, 382, 510, cs, 1);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+  const int launches = (int)(launch_count() - l0);
+  count_launch(-launches);   // captured, not executed
+  if (rc != OFS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+  OFS_CUDA(ce);
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  OFS_CUDA(ie);
+  if (n->graphs.size() >= 16) {   // evict the least recently used step
+    size_t lru = 0;
+    for (size_t i = 1; i < n->graphs.size(); ++i) if (n->graphs[i].last_use < n->graphs[lru].last_use) lru = i;
+    cudaGraphExecDestroy(n->graphs[lru].exec);
+    n->graphs.erase(n->graphs.begin() + lru);
+  }
+  n->graphs.push_back({feats, frames, out, flow2_out, B, H, W, exec, launches, n->graph_clock});
+  OFS_CUDA(cudaGraphLaunch(exec, st));
+  count_launch(launches);
+  return OFS_OK;
 }
 
 int ofs_net_stabilize_host(ofs_net* n, const float* feats_host, const float* frames_host, float* out_host, int B,

@@ -12,8 +12,17 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_err; }
-void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+void count_launch(int n) { g_launches.fetch_add((uint64_t)(int64_t)n, std::memory_order_relaxed); }
 uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("OFS_PDL");
+    cached = (e && e[0] == '1') ? 1 : 0;   // default off: inside the step graph PDL edges measured slower (profiles/r01_tuning.md)
+  }
+  return cached == 1;
+}
 
 int sm_count() {
   static int cached[64] = {0};

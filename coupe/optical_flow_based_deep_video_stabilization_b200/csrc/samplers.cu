@@ -326,6 +326,8 @@ __global__ void __launch_bounds__(256) warp3_kernel(Provider prov, const float* 
   __shared__ float tile[kStaged ? kStageMaxPx * 3 : 1];
   __shared__ int red[4][8];
   __shared__ int bbox[4];
+  pdl_wait();
+  pdl_launch_dependents();
   const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
   const size_t ntiles = (size_t)B * tiles_y * tiles_x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -499,9 +501,9 @@ template <class Provider>
 int launch_warp3(Provider prov, const float* img, float* out, int B, int H, int W, cudaStream_t st) {
   const size_t nt = tile_count(B, H, W);
   if (g_warp_variant == 1)
-    warp3_kernel<Provider, true><<<tile_grid(nt, 5), 256, 0, st>>>(prov, img, out, B, H, W);
+    OFS_CUDA(launch_pdl(warp3_kernel<Provider, true>, dim3(tile_grid(nt, 5)), dim3(256), 0, st, prov, img, out, B, H, W));
   else
-    warp3_kernel<Provider, false><<<tile_grid(nt, 8), 256, 0, st>>>(prov, img, out, B, H, W);
+    OFS_CUDA(launch_pdl(warp3_kernel<Provider, false>, dim3(tile_grid(nt, 8)), dim3(256), 0, st, prov, img, out, B, H, W));
   OFS_LAUNCH_CHECK();
   return OFS_OK;
 }
