@@ -84,7 +84,7 @@ def main():
                 continue
             ms = C.c_float(0)
             grid = C.c_int(0)
-            cap = 1024 * 16
+            cap = 1024 * 32
             trace = (C.c_longlong * cap)()
             rc = fn(args.batch, H, W, cin, in_cs, cout, out_cs, k, s, tr, bn, ks, cg, dbg, args.iters, args.flush_mb,
                     C.byref(ms), C.cast(trace, C.c_void_p) if args.trace else None, cap, C.byref(grid),
@@ -97,9 +97,14 @@ def main():
                    "us": us, "tflops": tf}
             if args.trace:
                 g = grid.value
-                rows = [[trace[i * 16 + j] for j in range(16)] for i in range(g)]
+                rows = [[trace[i * 32 + j] for j in range(32)] for i in range(g)]
+                prev = [[trace[(g + i) * 32 + j] for j in range(32)] for i in range(g)]
+                gap2_ns = min(r[11] for r in rows) - max(r[13] for r in prev)
                 t0 = min(r[0] for r in rows)
-                span_ns = max(r[7] for r in rows) - t0
+                span_ns = max(r[13] for r in rows) - t0
+                tk0 = min(r[11] for r in rows)
+                entry_skew = max(r[11] for r in rows) - tk0
+                full_span = max(r[13] for r in rows) - tk0
                 import statistics as st
 
                 def med(f):
@@ -117,6 +122,16 @@ def main():
                 mma_done = med(lambda r: r[4] - r[1] if r[4] else None)
                 epi_first = med(lambda r: r[5] - r[1] if r[5] else None)
                 epi_done = med(lambda r: r[6] - r[1] if r[6] else None)
+                prologue = med(lambda r: r[1] - r[12])
+                epi_loop = med(lambda r: r[10] - r[1] if r[10] else None)
+                mhz = med(lambda r: (r[9] - r[12]) / max(r[7] - r[11], 1) * 1e3)
+                line += (f"\n           previous launch end -> this launch first CTA entry: {gap2_ns / 1e3:.1f} us"
+                         f"\n           SM clock during the traced launch {mhz:.0f} MHz; entry->end {full_span / 1e3:.1f} us, entry skew {entry_skew / 1e3:.1f} us, prologue {prologue:.0f} cyc, "
+                         f"epi loop end {epi_loop:.0f}")
+                nch = med(lambda r: r[21])
+                if nch and nch == nch and nch > 0:
+                    line += ("\n           epilogue per 64-col chunk (cycles): ld+math+sts %.0f | tmem release+fence %.0f | wait_read %.0f | bar %.0f | issue %.0f  (%d chunks)"
+                             % tuple([med(lambda r, k=k: r[k] / max(r[21], 1)) for k in (16, 17, 18, 19, 20)] + [nch]))
                 line += (f"\n           trace: span {span_ns / 1e3:.1f} us, start skew {start_skew / 1e3:.1f} us; cycles (median CTA): "
                          f"total {total:.0f} (max {tmax:.0f}) | producer done {prod:.0f} | first full {first_full:.0f} | "
                          f"mma issued {mma_done:.0f} | epi first {epi_first:.0f} | epi done {epi_done:.0f}")
