@@ -85,18 +85,18 @@ def main():
             flows = ["zero", "smooth", "adversarial"] if (B in (1, 8)) else ["smooth"]
             for kind in flows:
                 flow = make_flow(kind, B, H, W, dev, gen)
-                for variant in (1, 0):
+                for variant in (3, 2, 1, 0):
                     ofs.set_warp_variant(variant)
                     ofs.tf_warp(img, flow, H, W)
                     ms = timed(lambda: ofs.tf_warp(img, flow, H, W), flush, iters)
-                    results.append(dict(op="tf_warp", variant="staged" if variant else "direct", flow=kind, B=B, H=H, W=W,
+                    results.append(dict(op="tf_warp", variant={0: "direct", 1: "staged12", 2: "staged16", 3: "lean"}[variant], flow=kind, B=B, H=H, W=W,
                                         ms=ms, gbs=px * 32 / ms / 1e6))
-                ofs.set_warp_variant(1)
+                ofs.set_warp_variant(3)
                 del flow
             f2 = torch.randn((B, 382, 510, 2), generator=gen).to(dev) * 2.0
             ofs.flow_resize_warp(img, f2)
             ms = timed(lambda: ofs.flow_resize_warp(img, f2), flush, iters)
-            results.append(dict(op="flow_resize_warp", variant="staged", flow="net-like N(0,2^2)", B=B, H=H, W=W, ms=ms,
+            results.append(dict(op="flow_resize_warp", variant="lean", flow="net-like N(0,2^2)", B=B, H=H, W=W, ms=ms,
                                 gbs=(px * 24 + B * 382 * 510 * 8) / ms / 1e6))
             c, s_ = np.cos(np.deg2rad(5)) * 1.02, np.sin(np.deg2rad(5)) * 1.02
             th6 = torch.tensor([[c, -s_, 0.01, s_, c, -0.02]] * B, dtype=torch.float32, device=dev)

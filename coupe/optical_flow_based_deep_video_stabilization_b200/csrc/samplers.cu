@@ -19,6 +19,7 @@
 // (truncation vs floor, clip order, fp32 coordinate products); see oracle/samplers.py.
 #include <algorithm>
 #include <climits>
+#include <type_traits>
 
 #include "ofs_common.cuh"
 
@@ -413,6 +414,241 @@ __global__ void __launch_bounds__(256) warp3_kernel(Provider prov, const float* 
   }
 }
 
+// tf_warp / fused flow-resize + tf_warp, variant 2: the tile's source bounding box is staged in shared memory
+// as PADDED 16-byte pixels (x aligned to 4 px so the global side is whole 128-bit loads), every bilinear corner
+// is then ONE 128-bit shared load instead of three 32-bit ones, and the taps are computed once (the sample
+// position is kept in registers between the bounding-box pass and the gather pass).
+constexpr int kStage4MaxPx = 2304;  // 36 KB of padded fp32 RGB source pixels per block
+template <class Provider>
+__global__ void __launch_bounds__(256) warp4_kernel(Provider prov, const float* __restrict__ img,
+                                                    float* __restrict__ out, int B, int H, int W) {
+  __shared__ __align__(16) float obuf[8][192];
+  __shared__ __align__(16) float4 tile[kStage4MaxPx];
+  __shared__ int red[4][8];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
+  const size_t ntiles = (size_t)B * tiles_y * tiles_x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (size_t tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
+    const TileId t = decode_tile(tile_id, tiles_x, tiles_y);
+    const float* imgb = img + (size_t)t.b * H * W * 3;
+    const int valid_px = min(kTileW, W - t.ox0);
+    // this thread's 4 pixels: rows 2w, 2w+1 x columns lane, lane+32: sample position (main_dl.py:83)
+    float sx[2][2], sy[2][2];
+    bool on[2][2];
+    int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int oy = t.oy0 + wid * 2 + rr, ox = t.ox0 + lane + 32 * h;
+        on[rr][h] = (oy < H) && (ox < W);
+        sx[rr][h] = sy[rr][h] = 0.f;
+        if (on[rr][h]) {
+          const float2 f = prov.flow_at(t.b, oy, ox);
+          const float x = (float)ox + f.x, y = (float)oy + f.y;
+          sx[rr][h] = x; sy[rr][h] = y;
+          const int xi = __float2int_rz(x), yi = __float2int_rz(y);
+          xmin = min(xmin, clip_i(xi, 0, W - 1)); ymin = min(ymin, clip_i(yi, 0, H - 1));
+          xmax = max(xmax, (xi >= W - 1) ? (W - 1) : max(xi + 1, 0));
+          ymax = max(ymax, (yi >= H - 1) ? (H - 1) : max(yi + 1, 0));
+        }
+      }
+    xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
+    ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
+    if (lane == 0) { red[0][wid] = xmin; red[1][wid] = xmax; red[2][wid] = ymin; red[3][wid] = ymax; }
+    __syncthreads();
+    int bx0 = red[0][0], bx1 = red[1][0], by0 = red[2][0], by1 = red[3][0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      bx0 = min(bx0, red[0][i]); bx1 = max(bx1, red[1][i]); by0 = min(by0, red[2][i]); by1 = max(by1, red[3][i]);
+    }
+    bx0 &= ~3;                                    // 16-byte aligned row segments (W % 4 == 0)
+    const int bw = ((bx1 + 4) & ~3) - bx0;        // px, multiple of 4, <= W - bx0
+    const int bh = by1 - by0 + 1;
+    const bool staged = (bw > 0) && (bh > 0) && (bw * bh <= kStage4MaxPx);
+    if (staged) {
+      const int nvec = (bw * 3) >> 2;             // float4 per source row segment
+      float* tf = reinterpret_cast<float*>(tile);
+      for (int r = wid; r < bh; r += 8) {
+        const float4* src = reinterpret_cast<const float4*>(imgb + ((size_t)(by0 + r) * W + bx0) * 3);
+        float* dst = tf + (size_t)r * bw * 4;
+        for (int k = lane; k < nvec; k += 32) {
+          const float4 v = __ldg(src + k);
+          const int i = 4 * k;                    // float index in the row segment: pixel i / 3, channel i % 3
+          const int p0 = i / 3, c0 = i - 3 * p0;
+          const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int cc = c0 + q;
+            const int pp = p0 + (cc >= 3 ? 1 : 0) + (cc >= 6 ? 1 : 0);   // c0 <= 2, q <= 3: at most two carries
+            const int ch = cc - 3 * (pp - p0);
+            dst[pp * 4 + ch] = e[q];
+          }
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int oy = t.oy0 + wid * 2 + rr;
+      if (oy < H) {  // warp-uniform
+        float v[2][3];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          v[h][0] = v[h][1] = v[h][2] = 0.0f;
+          if (on[rr][h]) {
+            // main_dl.py:88-120 on the stored sample position
+            const float x = sx[rr][h], y = sy[rr][h];
+            const int xi = __float2int_rz(x), yi = __float2int_rz(y);
+            const int x0 = clip_i(xi, 0, W - 1), y0 = clip_i(yi, 0, H - 1);
+            const int x1 = (xi >= W - 1) ? (W - 1) : max(xi + 1, 0);
+            const int y1 = (yi >= H - 1) ? (H - 1) : max(yi + 1, 0);
+            const float x0f = (float)x0, x1f = (float)x1, y0f = (float)y0, y1f = (float)y1;
+            const float wa = (x1f - x) * (y1f - y), wb = (x1f - x) * (y - y0f);
+            const float wc = (x - x0f) * (y1f - y), wd = (x - x0f) * (y - y0f);
+            if (staged) {
+              const float4* r0 = tile + (y0 - by0) * bw - bx0, *r1 = tile + (y1 - by0) * bw - bx0;
+              const float4 Ia = r0[x0], Ib = r1[x0], Ic = r0[x1], Id = r1[x1];
+              v[h][0] = mul_add_rn(mul_add_rn(mul_add_rn(mul_add_rn(0.f, wa, Ia.x), wb, Ib.x), wc, Ic.x), wd, Id.x);
+              v[h][1] = mul_add_rn(mul_add_rn(mul_add_rn(mul_add_rn(0.f, wa, Ia.y), wb, Ib.y), wc, Ic.y), wd, Id.y);
+              v[h][2] = mul_add_rn(mul_add_rn(mul_add_rn(mul_add_rn(0.f, wa, Ia.z), wb, Ib.z), wc, Ic.z), wd, Id.z);
+            } else {
+              gather3(imgb, W, y0, x0, wa, v[h]);
+              gather3(imgb, W, y1, x0, wb, v[h]);
+              gather3(imgb, W, y0, x1, wc, v[h]);
+              gather3(imgb, W, y1, x1, wd, v[h]);
+            }
+          }
+        }
+        store_row3(obuf[wid], out + (((size_t)t.b * H + oy) * W + t.ox0) * 3, lane, valid_px, v[0], v[1]);
+      }
+    }
+    __syncthreads();  // tile / red reuse
+  }
+}
+
+// tf_warp / fused flow-resize + tf_warp, variant 3 (default): an instruction-lean rewrite of the direct-gather
+// kernel.  ncu on variants 0-2 (profiles/r01_tuning.md): 174 (tf_warp) and 326 (fused) warp-instructions
+// per 32 pixels-per-lane... i.e. per pixel, issue-bound at ~60 % issue-active with DRAM at 25-40 %.  Here:
+//   * all image / flow indexing is 32-bit (one 64-bit base per image), rows and columns of a thread's 2x2
+//     pixels share their resize set-up (y terms per row, x terms per column);
+//   * the test-mode rescale flow_y * H / 384 is an exactly rounded division by a constant: q = t * RN(1/3),
+//     r = fma(-3, q, t), q' = fma(r, RN(1/3), q) (Markstein), then an exact scale by 2^-7;
+//   * 6 resident blocks per SM (launch bounds) instead of 4-5.
+struct Resize2 {             // fused provider: pre-scaled flow2 [B,fh,fw,2] -> flow at the output pixel
+  const float2* f2;
+  int fh, fw;
+  float hs, ws, Wf, Hf;
+};
+__device__ __forceinline__ float div384(float t) {
+  const float c = 0.333333343267440796f;   // RN(1/3)
+  float q = t * c;
+  const float r = __fmaf_rn(-3.0f, q, t);
+  q = __fmaf_rn(r, c, q);
+  return q * 0.0078125f;
+}
+
+template <bool kFused>
+__global__ void __launch_bounds__(256, 6) warp5_kernel(const float* __restrict__ img, const float2* __restrict__ flow,
+                                                        Resize2 rz, float* __restrict__ out, int B, int H, int W) {
+  __shared__ __align__(16) float obuf[8][192];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int Wm1 = W - 1, Hm1 = H - 1;
+  {   // one block per 64 x 16 output tile: grid (tiles_x, tiles_y, B), no tile decode arithmetic
+    const int b = blockIdx.z;
+    const int ox0 = blockIdx.x * kTileW, oy0 = blockIdx.y * kTileH + wid * 2;
+    const float* __restrict__ imgb = img + (size_t)b * H * W * 3;
+    const int valid_px = min(kTileW, W - ox0);
+    // ---- flow at this thread's 2 x 2 pixels (rows oy0, oy0+1; columns ox0+lane, ox0+lane+32)
+    float2 f[2][2];
+    if (kFused) {
+      // main_dl.py:497-498: TF1 legacy bilinear of the pre-scaled flow, then x * W / 512, y * H / 384
+      const float2* __restrict__ fb = rz.f2 + (size_t)b * rz.fh * rz.fw;
+      int xa[2], xb[2], ya[2], yb[2];
+      float xl[2], yl[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float ix = (float)(ox0 + lane + 32 * h) * rz.ws;
+        const float fl = floorf(ix);
+        xa[h] = min((int)fl, rz.fw - 1);          // columns past W are never stored; keep the loads in bounds
+        xb[h] = min(xa[h] + 1, rz.fw - 1);
+        xl[h] = ix - fl;
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float iy = (float)(oy0 + r) * rz.hs;
+        const float fl = floorf(iy);
+        const int y0 = min((int)fl, rz.fh - 1);
+        ya[r] = y0 * rz.fw;
+        yb[r] = min(y0 + 1, rz.fh - 1) * rz.fw;
+        yl[r] = iy - fl;
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float2 tl = __ldg(fb + ya[r] + xa[h]), tr = __ldg(fb + ya[r] + xb[h]);
+          const float2 bl = __ldg(fb + yb[r] + xa[h]), br = __ldg(fb + yb[r] + xb[h]);
+          const float topx = tl.x + (tr.x - tl.x) * xl[h], topy = tl.y + (tr.y - tl.y) * xl[h];
+          const float botx = bl.x + (br.x - bl.x) * xl[h], boty = bl.y + (br.y - bl.y) * xl[h];
+          const float vx = topx + (botx - topx) * yl[r], vy = topy + (boty - topy) * yl[r];
+          f[r][h].x = (vx * rz.Wf) * 0.001953125f;
+          f[r][h].y = div384(vy * rz.Hf);
+        }
+    } else {
+      const float2* __restrict__ fb = flow + (size_t)b * H * W;
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int oy = min(oy0 + r, Hm1), ox = min(ox0 + lane + 32 * h, Wm1);
+          f[r][h] = __ldg(fb + oy * W + ox);
+        }
+    }
+    // ---- main_dl.py:83-129 per pixel
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int oy = oy0 + r;
+      if (oy < H) {   // warp-uniform
+        float v[2][3];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int ox = ox0 + lane + 32 * h;
+          const float x = (float)ox + f[r][h].x, y = (float)oy + f[r][h].y;
+          const int xi = __float2int_rz(x), yi = __float2int_rz(y);
+          const int x0 = clip_i(xi, 0, Wm1), y0 = clip_i(yi, 0, Hm1);
+          const int x1 = (xi >= Wm1) ? Wm1 : max(xi + 1, 0);
+          const int y1 = (yi >= Hm1) ? Hm1 : max(yi + 1, 0);
+          const float dx1 = (float)x1 - x, dx0 = x - (float)x0, dy1 = (float)y1 - y, dy0 = y - (float)y0;
+          const float wa = dx1 * dy1, wb = dx1 * dy0, wc = dx0 * dy1, wd = dx0 * dy0;
+          const int r0 = y0 * W, r1 = y1 * W;
+          const float* pa = imgb + (r0 + x0) * 3;
+          const float* pb = imgb + (r1 + x0) * 3;
+          const float* pc = imgb + (r0 + x1) * 3;
+          const float* pd = imgb + (r1 + x1) * 3;
+          if (ox < W) {
+            const float a0 = __ldg(pa), a1 = __ldg(pa + 1), a2 = __ldg(pa + 2);
+            const float b0 = __ldg(pb), b1 = __ldg(pb + 1), b2 = __ldg(pb + 2);
+            const float c0 = __ldg(pc), c1 = __ldg(pc + 1), c2 = __ldg(pc + 2);
+            const float d0 = __ldg(pd), d1 = __ldg(pd + 1), d2 = __ldg(pd + 2);
+            // tf.add_n([wa*Ia, wb*Ib, wc*Ic, wd*Id]): rounded products, summed left to right
+            v[h][0] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wa, a0), __fmul_rn(wb, b0)), __fmul_rn(wc, c0)), __fmul_rn(wd, d0));
+            v[h][1] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wa, a1), __fmul_rn(wb, b1)), __fmul_rn(wc, c1)), __fmul_rn(wd, d1));
+            v[h][2] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wa, a2), __fmul_rn(wb, b2)), __fmul_rn(wc, c2)), __fmul_rn(wd, d2));
+          } else {
+            v[h][0] = v[h][1] = v[h][2] = 0.0f;
+          }
+        }
+        store_row3(obuf[wid], out + (((size_t)b * H + oy) * W + ox0) * 3, lane, valid_px, v[0], v[1]);
+      }
+    }
+  }
+}
+
 __global__ void flow_resize_kernel(FlowResize fr, float* __restrict__ out, int B) {
   const size_t total = (size_t)B * fr.H * fr.W;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -470,10 +706,13 @@ int grid_for(size_t work_items, int threads) {
   return (int)blocks;
 }
 
-int g_warp_variant = 1;  // 0 = direct gathers, 1 = shared-memory staged (default)
+int g_warp_variant = 3;  // 0 = direct gathers, 1 = staged (12-byte pixels), 2 = staged (padded 16-byte pixels), 3 = lean direct (default)
 
 size_t tile_count(int B, int oH, int oW) {
   return (size_t)B * ((oH + kTileH - 1) / kTileH) * ((oW + kTileW - 1) / kTileW);
+}
+dim3 tile_grid3(int B, int oH, int oW) {
+  return dim3((unsigned)((oW + kTileW - 1) / kTileW), (unsigned)((oH + kTileH - 1) / kTileH), (unsigned)B);
 }
 int tile_grid(size_t ntiles, int blocks_per_sm) {
   const size_t cap = (size_t)sm_count() * blocks_per_sm;
@@ -500,7 +739,26 @@ int launch_sampler(Provider prov, const float* img, float* out, int B, int srcH,
 template <class Provider>
 int launch_warp3(Provider prov, const float* img, float* out, int B, int H, int W, cudaStream_t st) {
   const size_t nt = tile_count(B, H, W);
-  if (g_warp_variant == 1)
+  if (g_warp_variant == 3 && (size_t)H * W * 3 < (1u << 31) && B <= 65535 && (H + kTileH - 1) / kTileH <= 65535) {
+    if constexpr (std::is_same<Provider, ResizeWarpProvider>::value) {
+      const FlowResize& fr = prov.fr;
+      if (fr.prescaled) {
+        Resize2 rz{reinterpret_cast<const float2*>(fr.flow2), fr.fh, fr.fw, fr.hs, fr.ws, (float)W, (float)H};
+        OFS_CUDA(launch_pdl(warp5_kernel<true>, tile_grid3(B, H, W), dim3(256), 0, st, img, (const float2*)nullptr, rz, out, B, H, W));
+        OFS_LAUNCH_CHECK();
+        return OFS_OK;
+      }
+    } else {
+      Resize2 rz{};
+      OFS_CUDA(launch_pdl(warp5_kernel<false>, tile_grid3(B, H, W), dim3(256), 0, st, img,
+                          reinterpret_cast<const float2*>(prov.flow), rz, out, B, H, W));
+      OFS_LAUNCH_CHECK();
+      return OFS_OK;
+    }
+  }
+  if (g_warp_variant == 2 && (((uintptr_t)img) % 16 == 0))
+    OFS_CUDA(launch_pdl(warp4_kernel<Provider>, dim3(tile_grid(nt, 4)), dim3(256), 0, st, prov, img, out, B, H, W));
+  else if (g_warp_variant == 1)
     OFS_CUDA(launch_pdl(warp3_kernel<Provider, true>, dim3(tile_grid(nt, 5)), dim3(256), 0, st, prov, img, out, B, H, W));
   else
     OFS_CUDA(launch_pdl(warp3_kernel<Provider, false>, dim3(tile_grid(nt, 8)), dim3(256), 0, st, prov, img, out, B, H, W));
@@ -551,7 +809,7 @@ int flow_resize_warp_impl(const float* img, const float* flow2, float* out, int 
 extern "C" {
 
 int ofs_set_warp_variant(int v) {
-  ofs::g_warp_variant = v ? 1 : 0;
+  ofs::g_warp_variant = (v >= 0 && v <= 3) ? v : 3;
   return OFS_OK;
 }
 

@@ -22,14 +22,14 @@ def g(a, dev):
     return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("case", ["k1", "k2", "k3", "k4"])
 def test_tf_warp_golden(ofs, cuda_dev, golden, case, variant):
     ofs.set_warp_variant(variant)
     img = g(golden["k1_img"], cuda_dev)
     out = ofs.tf_warp(img, g(golden[f"{case}_flow"], cuda_dev), img.shape[1], img.shape[2])
     np.testing.assert_allclose(out.cpu().numpy(), golden[f"{case}_out"], rtol=0, atol=1e-6)
-    ofs.set_warp_variant(1)
+    ofs.set_warp_variant(3)
 
 
 def _flows(kind, B, H, W, gen):
@@ -45,7 +45,7 @@ def _flows(kind, B, H, W, gen):
     return (torch.rand((B, H, W, 2), generator=gen) - 0.5) * 64.0      # adversarial U(-32,32)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("kind", ["zero", "const", "smooth", "adversarial"])
 @pytest.mark.parametrize("B,H,W,C", [(2, 64, 96, 3), (1, 256, 256, 3), (2, 37, 52, 3), (1, 33, 47, 3), (2, 40, 64, 5)])
 def test_tf_warp_vs_oracle(ofs, cuda_dev, variant, kind, B, H, W, C):
@@ -55,7 +55,7 @@ def test_tf_warp_vs_oracle(ofs, cuda_dev, variant, kind, B, H, W, C):
     ref = S.tf_warp(img, flow, H, W)
     ofs.set_warp_variant(variant)
     out = ofs.tf_warp(img.to(cuda_dev), flow.to(cuda_dev), H, W).cpu()
-    ofs.set_warp_variant(1)
+    ofs.set_warp_variant(3)
     assert float((out - ref).abs().max()) <= TOL
 
 
@@ -79,7 +79,7 @@ def test_tf_warp_720p_properties(ofs, cuda_dev):
     # variant equivalence at full size
     ofs.set_warp_variant(0)
     a0 = ofs.tf_warp(img, flow, H, W)
-    ofs.set_warp_variant(1)
+    ofs.set_warp_variant(3)
     assert float((a0 - a).abs().max()) < 1e-6
     # exact oracle check on a window (warp of the cropped inputs differs only where taps leave the crop)
     fl = flow[:1, :64].clone()
@@ -109,13 +109,13 @@ def test_flow_resize_and_fused_warp(ofs, cuda_dev, golden, H, W):
     got_flow = ofs.flow_resize(f2.to(cuda_dev), H, W).cpu()
     assert float((got_flow - ref_flow).abs().max()) < 1e-4
     ref = S.flow_resize_warp(img, f2, H, W)
-    for variant in (0, 1):
+    for variant in (0, 1, 2, 3):
         ofs.set_warp_variant(variant)
         got = ofs.flow_resize_warp(img.to(cuda_dev), f2.to(cuda_dev)).cpu()
         # a 1-ulp flow difference can flip a truncation; bound the count, not just the max
         bad = ((got - ref).abs() > TOL).float().mean()
         assert float(bad) < 1e-4, float(bad)
-    ofs.set_warp_variant(1)
+    ofs.set_warp_variant(3)
     # two-step (resize then warp) == fused
     two = ofs.tf_warp(img.to(cuda_dev), ofs.flow_resize(f2.to(cuda_dev), H, W), H, W).cpu()
     assert float(((two - got).abs() > 1e-5).float().mean()) < 1e-4
