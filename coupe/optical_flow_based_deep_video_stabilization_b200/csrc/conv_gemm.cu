@@ -89,16 +89,18 @@ __device__ __forceinline__ void epilogue_store(const ConvGemmParams& p, const ui
 // Tile configuration.  kPair = CTA pairs (tcgen05 cta_group::2): a pair computes 256 GEMM rows x BLOCK_N, each
 // CTA TMA-loads the A tile of its own 128 rows and HALF of the B tile; the leader (cluster rank 0) issues one
 // M=256 MMA reading both CTAs' shared memory; D rows 0-127 land in the leader's TMEM, rows 128-255 in the peer's.
-template <int BLOCK_N, bool kPair>
+// kT = K blocks (taps of one slab group) per pipeline stage: 1, or 3 / 4 in slab mode.
+template <int BLOCK_N, bool kPair, int kT = 1>
 struct GemmCfg {
-  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kABytes = kT > 1 ? (kBlockM + 8) * kBlockK * 2 : kBlockM * kBlockK * 2;   // slab: up to 7 extra pixels
   static constexpr int kBBytes = (BLOCK_N / (kPair ? 2 : 1)) * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kStageBytes = kABytes + kT * kBBytes;
   static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
   static constexpr int kBarBytes = 256;
   static constexpr int kStgBytes = kBlockM * 128;        // one 64-channel chunk of the 16-bit output tile (SW128 rows)
   static constexpr int kStgTotal = BLOCK_N >= 64 ? 2 * kStgBytes : 0;   // double buffered; narrow tiles store directly
+  static constexpr int kBudget = 227 * 1024 - 1024 - kBarBytes - kStgTotal;   // 227 KB per CTA on sm_100
+  static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr size_t kSmem = (size_t)kStages * kStageBytes + kStgTotal + kBarBytes + 1024;  // + alignment slack
 };
 
@@ -185,9 +187,9 @@ __device__ __forceinline__ void mma(uint32_t d, uint32_t da_lo, uint32_t db_lo, 
 // shared-memory addresses, TMA coordinates and UMMA descriptors in uniform registers.  A loop entered by
 // lane 0 alone (`if (lane == 0)`) makes every operand "possibly divergent" and each UTMALDG / UTCHMMA is then
 // wrapped in an ELECT + R2UR waterfall loop: ~2x the cycles per K block (see profiles/r01_tuning.md).
-template <int BLOCK_N, bool kPair>
+template <int BLOCK_N, bool kPair, int kT>
 __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
-  using Cfg = GemmCfg<BLOCK_N, kPair>;
+  using Cfg = GemmCfg<BLOCK_N, kPair, kT>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -252,7 +254,8 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
     // ===================================== TMA producer =====================================
     const bool leader = ptx::elect_one();
     const bool do_a = !(p.debug & 2), do_b = !(p.debug & 4);
-    const uint32_t stage_tx = (kPair ? 2u : 1u) * (uint32_t)((do_a ? p.a_bytes : 0) + (do_b ? Cfg::kBBytes : 0));
+    const uint32_t a_tx = (kPair ? 2u : 1u) * (uint32_t)(do_a ? p.a_bytes : 0);
+    const uint32_t b_tx = (kPair ? 2u : 1u) * (uint32_t)(do_b ? Cfg::kBBytes : 0);
     const uint32_t full_tgt0 = kPair ? ptx::mapa_u32(full0, 0) : full0;   // where TMA bytes are posted
     const int piece_bytes = p.piece_rows * tileW * kBlockK * 2;
     const int npieces = p.npieces;
@@ -286,9 +289,10 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
         const int ylim = p.Hg + p.tap_y[ti];
         const int ch_end = min(p.nchunks, ch + (kb1 - kb));
         for (; ch < ch_end; ++ch, ++kb) {
+          const int gn = kT > 1 ? (int)p.grp_n[ti] : 1;   // K blocks of this stage (slab group)
           lean::wait(empty_s, phase ^ 1);
           if (leader) {
-            if (!kPair || rank == 0) lean::expect_tx(full_s, stage_tx);
+            if (!kPair || rank == 0) lean::expect_tx(full_s, a_tx + (uint32_t)gn * b_tx);
             if (do_a) {
               if (npieces == 1) {
                 lean::tma5d<kPair>(sa, &p.tmap_a, full_t, c, x, pp, yy, b0);
@@ -303,10 +307,16 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
                 }
               }
             }
-            if (do_b) lean::tma2d<kPair>(sa + Cfg::kABytes, &p.tmap_w, full_t, kcol, w_row);
+            if (do_b) {
+              lean::tma2d<kPair>(sa + Cfg::kABytes, &p.tmap_w, full_t, kcol, w_row);
+              if constexpr (kT > 1) {
+                for (int t = 1; t < gn; ++t)
+                  lean::tma2d<kPair>(sa + Cfg::kABytes + t * Cfg::kBBytes, &p.tmap_w, full_t, kcol + t * kBlockK, w_row);
+              }
+            }
           }
           c += kBlockK;
-          kcol += kBlockK;
+          kcol += gn * kBlockK;
           sa += Cfg::kStageBytes; full_s += 8; empty_s += 8; full_t += 8;
           if (++stage == S) { stage = 0; phase ^= 1; sa = smem_base; full_s = full0; empty_s = empty0; full_t = full_tgt0; }
         }
@@ -345,10 +355,27 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
           if (trace && leader && tile == unit && i == 0) trace[3] = clock64();
           if (leader) {
             if (do_mma) {
-              lean::mma<kPair>(d_tmem, da, db, kDescHi, idesc, i > 0 ? 1u : 0u);   // 4 x K=16 inside the 128-byte swizzle row
-              lean::mma<kPair>(d_tmem, da + 2, db + 2, kDescHi, idesc, 1u);
-              lean::mma<kPair>(d_tmem, da + 4, db + 4, kDescHi, idesc, 1u);
-              lean::mma<kPair>(d_tmem, da + 6, db + 6, kDescHi, idesc, 1u);
+              if constexpr (kT > 1) {
+                // slab group: tap t reads the slab through a start address advanced by grp_off rows of 128 bytes.
+                // The 128-byte swizzle is a function of the absolute shared-memory address (bits 4-6 ^= bits 7-9)
+                // for TMA writes and UMMA reads alike, so a row-shifted start address needs no further descriptor
+                // change (measured on B200: the base-offset field must stay 0 -- tests "slab_*").
+                const int gi = ((tile / (p.tiles_n * p.tiles_mp)) % p.phases) * p.ntaps + kb0 + i;
+                const int gn = (int)p.grp_n[gi];
+                for (int t = 0; t < gn; ++t) {
+                  const uint32_t a_lo = da + (uint32_t)p.grp_off[gi][t] * 8u;
+                  const uint32_t b_lo = db + (uint32_t)t * (uint32_t)(Cfg::kBBytes >> 4);
+                  lean::mma<kPair>(d_tmem, a_lo, b_lo, kDescHi, idesc, (i > 0 || t > 0) ? 1u : 0u);
+                  lean::mma<kPair>(d_tmem, a_lo + 2, b_lo + 2, kDescHi, idesc, 1u);
+                  lean::mma<kPair>(d_tmem, a_lo + 4, b_lo + 4, kDescHi, idesc, 1u);
+                  lean::mma<kPair>(d_tmem, a_lo + 6, b_lo + 6, kDescHi, idesc, 1u);
+                }
+              } else {
+                lean::mma<kPair>(d_tmem, da, db, kDescHi, idesc, i > 0 ? 1u : 0u);   // 4 x K=16 inside the 128-byte swizzle row
+                lean::mma<kPair>(d_tmem, da + 2, db + 2, kDescHi, idesc, 1u);
+                lean::mma<kPair>(d_tmem, da + 4, db + 4, kDescHi, idesc, 1u);
+                lean::mma<kPair>(d_tmem, da + 6, db + 6, kDescHi, idesc, 1u);
+              }
             }
             lean::commit<kPair>(empty_s);   // the stage is reusable (in both CTAs) once these MMAs have read it
           }
@@ -536,12 +563,18 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  conv_gemm_body<BLOCK_N, false>(p);
+  conv_gemm_body<BLOCK_N, false, 1>(p);
 }
 template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
-  conv_gemm_body<BLOCK_N, true>(p);
+  conv_gemm_body<BLOCK_N, true, 1>(p);
+}
+// slab mode (CTA pairs): kT taps of a group per stage
+template <int BLOCK_N, int kT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    conv_gemm2s_kernel(const __grid_constant__ ConvGemmParams p) {
+  conv_gemm_body<BLOCK_N, true, kT>(p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -675,6 +708,21 @@ int launch_t2(const ConvPlan& plan, cudaStream_t st) {
     attr_set[dev] = true;
   }
   OFS_CUDA(launch_pdl(conv_gemm2_kernel<BLOCK_N>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, true>::kSmem, st, plan.p));
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
+}
+
+template <int BLOCK_N, int kT>
+int launch_t2s(const ConvPlan& plan, cudaStream_t st) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  OFS_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    OFS_CUDA(cudaFuncSetAttribute(conv_gemm2s_kernel<BLOCK_N, kT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)GemmCfg<BLOCK_N, true, kT>::kSmem));
+    attr_set[dev] = true;
+  }
+  OFS_CUDA(launch_pdl(conv_gemm2s_kernel<BLOCK_N, kT>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, true, kT>::kSmem, st, plan.p));
   OFS_LAUNCH_CHECK();
   return OFS_OK;
 }
@@ -858,6 +906,64 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
         p.tap_y[ti] = (short)(ty >> 1);
       }
   }
+  // K order of the weight taps (one entry per K block of `nchunks` chunks; slab mode rewrites it below)
+  if (!deconv) {
+    if (plan.paired) {
+      const int nj = (d.k + 1) / 2;
+      for (int ky = 0; ky < d.k; ++ky) for (int j = 0; j < nj; ++j) { plan.wt_ky.push_back(ky); plan.wt_kx.push_back(2 * j - 1); }
+    } else {
+      for (int ky = 0; ky < d.k; ++ky) for (int kx = 0; kx < d.k; ++kx) { plan.wt_ky.push_back(ky); plan.wt_kx.push_back(kx); }
+    }
+  }
+  if (d.slab) {
+    OFS_REQUIRE(!deconv && d.stride == 2 && tileW == 128 && p.npieces == 1 && p.tile_rows == 1,
+                "slab mode needs a stride-2 conv whose tiles are one 128-pixel output row (Wg %% 128 == 0)");
+    OFS_REQUIRE(plan.paired || (d.in_cs == 64 && d.cin <= 64), "slab mode needs one 64-element K chunk per tap");
+    OFS_REQUIRE(d.cta_group == 2 && d.ksplit <= 1 && (d.block_n == 64 || d.block_n == 128),
+                "slab mode runs on CTA pairs with block_n 64 or 128 and no split-K");
+    const int pad = d.k / 2;
+    plan.wt_ky.clear(); plan.wt_kx.clear();
+    int ng = 0, extra = 0, gmax = 0;
+    auto add_group = [&](int ky, int cbase, const std::vector<int>& xoffs, const std::vector<int>& kxs) {
+      const int ty = ky - pad;
+      int xmin = xoffs[0];
+      for (int v : xoffs) xmin = std::min(xmin, v);
+      p.tap_c[ng] = (short)cbase; p.tap_x[ng] = (short)xmin; p.tap_p[ng] = (short)(ty & 1); p.tap_y[ng] = (short)(ty >> 1);
+      p.grp_n[ng] = (unsigned char)xoffs.size();
+      for (size_t t = 0; t < xoffs.size(); ++t) {
+        p.grp_off[ng][t] = (unsigned char)(xoffs[t] - xmin);
+        extra = std::max(extra, xoffs[t] - xmin);
+        plan.wt_ky.push_back(ky); plan.wt_kx.push_back(kxs[t]);
+      }
+      gmax = std::max(gmax, (int)xoffs.size());
+      ++ng;
+    };
+    for (int ky = 0; ky < d.k; ++ky) {
+      if (plan.paired) {   // K block j = x-parity pair (kx = 2j-1, 2j): all pairs of a row are x shifts of each other
+        std::vector<int> xo, kxs;
+        for (int j = 0; j < (d.k + 1) / 2; ++j) { xo.push_back((2 * j - 1 - pad) >> 1); kxs.push_back(2 * j - 1); }
+        add_group(ky, 0, xo, kxs);
+      } else {             // in_cs == 64: even and odd x taps live in different parity halves of the view
+        for (int par = 0; par < 2; ++par) {
+          std::vector<int> xo, kxs;
+          for (int kx = 0; kx < d.k; ++kx) {
+            const int tx = kx - pad;
+            if ((tx & 1) == par) { xo.push_back(tx >> 1); kxs.push_back(kx); }
+          }
+          for (size_t s0 = 0; s0 < xo.size(); s0 += 4) {   // at most 4 taps per group
+            const size_t s1 = std::min(xo.size(), s0 + 4);
+            add_group(ky, par * d.in_cs, std::vector<int>(xo.begin() + s0, xo.begin() + s1),
+                      std::vector<int>(kxs.begin() + s0, kxs.begin() + s1));
+          }
+        }
+      }
+    }
+    OFS_REQUIRE(ng <= kMaxTapEntries && extra <= 7, "slab mode: too many groups / shift too large");
+    p.slab = 1; p.slab_extra = extra;
+    p.ntaps = ng; p.nchunks = 1;
+    plan.group_max = gmax;
+    p.a_bytes = (128 + extra) * kBlockK * 2;
+  }
   plan.block_n = d.block_n;
   p.n_pad = ((d.cout + d.block_n - 1) / d.block_n) * d.block_n;
   p.tiles_n = p.n_pad / d.block_n;
@@ -868,7 +974,7 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
     OFS_REQUIRE(p.n_pad == d.cout, "16-bit output mode needs cout %% block_n == 0 (cout %d, block_n %d)", d.cout, d.block_n);
     OFS_REQUIRE(d.out_cstride % 8 == 0 && d.out_coff % 8 == 0, "16-bit output slice must be 16-byte aligned");
   }
-  plan.k_total = p.ntaps * p.nchunks * kBlockK;
+  plan.k_total = (p.slab ? (int)plan.wt_ky.size() : p.ntaps * p.nchunks) * kBlockK;
   plan.w_rows = p.phases * p.n_pad;
   {
     const int num_kb = p.ntaps * p.nchunks;
@@ -883,7 +989,10 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
   p.tma_store = (p.out_mode == 0 && d.block_n >= 64) ? 1 : 0;
   p.tiles_mp = d.cta_group == 2 ? (p.tiles_m + 1) / 2 : p.tiles_m;
   const int total_tiles = p.tiles_mp * p.tiles_n * p.phases * p.ksplit;
-  if (d.cta_group == 2) {
+  if (p.slab) {
+    plan.grid = 2 * std::max(1, std::min(total_tiles, sm_count() / 2));
+    plan.smem = d.block_n == 64 ? GemmCfg<64, true, 4>::kSmem : GemmCfg<128, true, 3>::kSmem;
+  } else if (d.cta_group == 2) {
     plan.grid = 2 * std::max(1, std::min(total_tiles, sm_count() / 2));
     switch (d.block_n) {
       case 32: plan.smem = GemmCfg<32, true>::kSmem; break;
@@ -931,27 +1040,25 @@ void conv_pack_weights(const ConvPlan& plan, const float* w, const float* bias, 
             }
           }
   } else if (plan.paired) {
-    const int pad = d.k / 2, nj = (d.k + 1) / 2;
-    (void)pad;
-    for (int ky = 0; ky < d.k; ++ky)
-      for (int j = 0; j < nj; ++j)
-        for (int xp = 0; xp < 2; ++xp) {
-          const int kx = 2 * j - 1 + xp;
-          if (kx < 0 || kx >= d.k) continue;
-          for (int ci = 0; ci < d.cin; ++ci) {
-            const float* src = w + (((size_t)ky * d.k + kx) * d.cin + ci) * d.cout;
-            const size_t kidx = (size_t)(ky * nj + j) * kBlockK + xp * 32 + ci;
-            for (int n = 0; n < d.cout; ++n) out[(size_t)n * K + kidx] = cvt(src[n]);
-          }
-        }
-  } else {
-    for (int ky = 0; ky < d.k; ++ky)
-      for (int kx = 0; kx < d.k; ++kx)
+    for (size_t i = 0; i < plan.wt_ky.size(); ++i)
+      for (int xp = 0; xp < 2; ++xp) {
+        const int ky = plan.wt_ky[i], kx = plan.wt_kx[i] + xp;
+        if (kx < 0 || kx >= d.k) continue;
         for (int ci = 0; ci < d.cin; ++ci) {
           const float* src = w + (((size_t)ky * d.k + kx) * d.cin + ci) * d.cout;
-          const size_t kidx = (size_t)(ky * d.k + kx) * p.nchunks * kBlockK + ci;
+          const size_t kidx = i * kBlockK + xp * 32 + ci;
           for (int n = 0; n < d.cout; ++n) out[(size_t)n * K + kidx] = cvt(src[n]);
         }
+      }
+  } else {
+    for (size_t i = 0; i < plan.wt_ky.size(); ++i) {
+      const int ky = plan.wt_ky[i], kx = plan.wt_kx[i];
+      for (int ci = 0; ci < d.cin; ++ci) {
+        const float* src = w + (((size_t)ky * d.k + kx) * d.cin + ci) * d.cout;
+        const size_t kidx = i * (size_t)p.nchunks * kBlockK + ci;
+        for (int n = 0; n < d.cout; ++n) out[(size_t)n * K + kidx] = cvt(src[n]);
+      }
+    }
   }
 }
 
@@ -978,7 +1085,8 @@ int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const 
   cuuint64_t dims[5], str[4];
   for (int i = 0; i < 5; ++i) dims[i] = vd[i];
   for (int i = 0; i < 4; ++i) str[i] = vs[i];
-  cuuint32_t box[5] = {(cuuint32_t)kBlockK, tileW, 1, (cuuint32_t)p.box_y, (cuuint32_t)p.box_b};
+  cuuint32_t box[5] = {(cuuint32_t)kBlockK, tileW + (cuuint32_t)(p.slab ? p.slab_extra : 0), 1, (cuuint32_t)p.box_y,
+                       (cuuint32_t)p.box_b};
   int st = encode_map(&p.tmap_a, d.is_bf16, 5, act_in, dims, str, box);
   if (st != OFS_OK) return st;
   if (p.tma_store) {
@@ -1000,7 +1108,11 @@ int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const 
 
 int conv_launch(const ConvPlan& plan, cudaStream_t st) {
   int rc = OFS_EINVAL;
-  if (plan.d.cta_group == 2) {
+  if (plan.p.slab) {
+    if (plan.block_n == 64 && plan.group_max <= 4) rc = launch_t2s<64, 4>(plan, st);
+    else if (plan.block_n == 128 && plan.group_max <= 3) rc = launch_t2s<128, 3>(plan, st);
+    else { set_error("conv_launch: no slab kernel for block_n %d with %d taps per group", plan.block_n, plan.group_max); return OFS_EINVAL; }
+  } else if (plan.d.cta_group == 2) {
     switch (plan.block_n) {
       case 32: rc = launch_t2<32>(plan, st); break;
       case 64: rc = launch_t2<64>(plan, st); break;
@@ -1066,7 +1178,8 @@ extern "C" int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const flo
   if (!transposed && stride == 2 && d.in_cs != 32) d.cin = d.in_cs;  // zero channels + zero weights
   d.block_n = block_n > 0 ? block_n : (Cout >= 128 ? 128 : (Cout >= 64 ? 64 : (Cout >= 32 ? 32 : 16)));
   d.ksplit = ksplit > 1 ? ksplit : 1;
-  d.cta_group = cta_group == 2 ? 2 : 1;
+  d.cta_group = (cta_group == 2 || cta_group == 4) ? 2 : 1;
+  d.slab = cta_group == 4 ? 1 : 0;   // 4 = CTA pairs + slab groups
   const bool via16 = d.ksplit > 1 || out16;   // the network's 16-bit activation epilogue (split-K always reduces into it)
   const int cout8 = ((Cout + 7) / 8) * 8;
   d.out_mode = via16 ? 0 : 1; d.lrelu = lrelu; d.is_bf16 = is_bf16;
@@ -1163,7 +1276,7 @@ extern "C" int ofs_conv2d_bench(int B, int H, int W, int Cin, int in_cs, int Cou
   ConvDesc d;
   d.kind = transposed ? kDeconvK4S2 : kConv;
   d.B = B; d.H = H; d.W = W; d.cin = Cin; d.in_cs = in_cs; d.cout = Cout; d.k = k; d.stride = stride;
-  d.block_n = block_n; d.ksplit = ksplit > 1 ? ksplit : 1; d.cta_group = cta_group == 2 ? 2 : 1; d.debug = debug;
+  d.block_n = block_n; d.ksplit = ksplit > 1 ? ksplit : 1; d.cta_group = (cta_group == 2 || cta_group == 4) ? 2 : 1; d.slab = cta_group == 4 ? 1 : 0; d.debug = debug;
   const bool out16 = (Cout % block_n) == 0;
   d.out_mode = out16 ? 0 : 1; d.lrelu = 1; d.is_bf16 = 1; d.out_cstride = out_cs; d.out_coff = 0;
   ConvPlan plan;

@@ -53,6 +53,13 @@ struct ConvGemmParams {
   int out_oy[4], out_ox[4];  // per-phase sub-pixel offset
   // per (phase, tap) TMA coordinate offsets: channel base, x offset, parity plane, y offset
   short tap_c[kMaxTapEntries], tap_x[kMaxTapEntries], tap_p[kMaxTapEntries], tap_y[kMaxTapEntries];
+  // slab mode (slab = 1): a table entry is a GROUP of up to 4 taps that differ only by an x shift.  One TMA
+  // box of tileW + slab_extra pixels (the "slab") is loaded per group and tap t reads it through a UMMA
+  // descriptor whose start address is advanced by grp_off[t] 128-byte rows: one pipeline stage, one
+  // handshake and one A fetch per group instead of per tap.
+  int slab, slab_extra;
+  unsigned char grp_n[kMaxTapEntries];
+  unsigned char grp_off[kMaxTapEntries][4];
 };
 
 enum ConvKind { kConv = 0, kDeconvK4S2 = 1 };
@@ -69,6 +76,7 @@ struct ConvDesc {
   int out_cstride, out_coff;
   int ksplit = 1;      // > 1: split the K loop over this many CTAs per tile (16-bit output mode only)
   int cta_group = 1;   // 2: CTA pairs (tcgen05 cta_group::2): tile = 256 GEMM rows x BLOCK_N, B split over the pair
+  int slab = 0;        // 1: x-shifted taps share one shared-memory slab (stride-2 convs whose tiles are one 128-px row)
   int debug = 0;       // see ConvGemmParams::debug
   long long* trace = nullptr;  // see ConvGemmParams::trace
 };
@@ -82,6 +90,10 @@ struct ConvPlan {
   int k_total = 0;
   int w_rows = 0;            // phases * n_pad
   bool paired = false;       // conv1-style stride-2 layer with in_cs == 32: two x-taps per K chunk
+  int group_max = 1;         // slab mode: most taps in one group (sizes the pipeline stage)
+  // K order of the packed weights: K block i holds weight tap (wt_ky[i], wt_kx[i]) (paired form: kx and kx + 1
+  // of the x-parity pair starting at wt_kx[i], which may be -1)
+  std::vector<int> wt_ky, wt_kx;
   double macs = 0;           // literal MACs of the layer (roofline numerator)
   size_t ws_bytes = 0;       // split-K workspace this plan needs (0 when ksplit == 1)
   // split-K reduction (filled by bind)

@@ -382,6 +382,7 @@ int prepare(ofs_net* n, int B) {
       set_error("OFS_TUNE: block_n %d does not divide the padded N %d of layer %s", bn, L.n_pad, L.name.c_str());
       return OFS_EINVAL;
     }
+    if (L.d.slab) { cg = 2; bn = L.d.block_n; ks = 1; }   // the packed K order is the slab order: tiling is fixed
     if (ks > 1 || bn != L.d.block_n || cg == 2 || dbg) {
       ConvDesc d = L.d;
       d.block_n = bn;
@@ -621,7 +622,9 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
   // BLOCK_N = 256 where cout allows: the kernel is bound by L2 -> shared-memory delivery, and a wider N
   // tile halves the A-operand re-fetch per FLOP (measured: profiles/r01_tuning.md).
   for (Layer& L : Ls) {
-    if (L.name == "3" || L.name == "3_1" || L.name == "4" || L.name == "4_1") { L.block_n_run = 256; }
+    if ((L.name == "1" || L.name == "2") && !(getenv("OFS_NOSLAB") && getenv("OFS_NOSLAB")[0] == '1')) {
+      L.d.slab = 1; L.d.cta_group = 2;   // x-shifted taps share one A slab per stage (CTA pairs); fixes the packed K order
+    } else if (L.name == "3" || L.name == "3_1" || L.name == "4" || L.name == "4_1") { L.block_n_run = 256; }
     else if (L.name == "5" || L.name == "5_1") { L.block_n_run = 256; L.ksplit = 6; }
     else if (L.name == "6" || L.name == "6_1") { L.block_n_run = 256; L.ksplit = 8; }
     else if (L.name == "deconv5") { L.block_n_run = 256; L.ksplit = 4; }

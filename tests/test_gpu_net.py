@@ -99,6 +99,14 @@ TILING_CASES = [
     pytest.param(1, 24, 32, 96, 64, 4, 2, True, 64, -1, 1, id="tma_store_deconv_pieces"),
     pytest.param(1, 48, 64, 256, 256, 3, 1, False, 256, -1, 2, id="tma_store_pair_n256"),
     pytest.param(3, 6, 8, 256, 256, 3, 1, False, 128, -1, 2, id="tma_store_pair_odd_tiles"),
+    # slab groups (cta_group = 4: CTA pairs, x-shifted taps share one shared-memory slab per pipeline stage)
+    pytest.param(1, 32, 256, 27, 64, 7, 2, False, 64, 1, 4, id="slab_conv1_form"),
+    pytest.param(2, 16, 512, 27, 64, 7, 2, False, 64, -1, 4, id="slab_conv1_form_two_x_tiles_out16"),
+    pytest.param(1, 6, 256, 27, 64, 7, 2, False, 64, 1, 4, id="slab_conv1_form_odd_tile_count"),
+    pytest.param(1, 16, 256, 64, 128, 5, 2, False, 128, 1, 4, id="slab_conv2_form"),
+    pytest.param(3, 10, 256, 64, 128, 5, 2, False, 128, -1, 4, id="slab_conv2_form_odd_tiles_out16"),
+    pytest.param(1, 8, 256, 16, 64, 3, 2, False, 64, 1, 4, id="slab_k3_paired"),
+    pytest.param(1, 8, 256, 64, 64, 3, 2, False, 64, 1, 4, id="slab_k3_cin64"),
 ]
 
 
