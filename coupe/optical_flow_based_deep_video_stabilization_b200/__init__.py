@@ -13,6 +13,7 @@ from .model import (FlowNetSPyramid, assign_weights, flownetS_pyramid, get_net, 
                     load_and_assign_npz_dict)
 from .ops import (conv2d_nhwc, flow_resize, flow_resize_warp, get_pixel_value, set_warp_variant,  # noqa: F401
                   tf_warp)
+from .sharding import gather_output, shard_range                                                # noqa: F401
 from .spatial_transformer import AffineTransformer, ProjectiveTransformer, transformer          # noqa: F401
 from .warp import compose, fit, inverse, transformCropImage, transformImage, vec2mtrx           # noqa: F401
 
@@ -21,5 +22,6 @@ __all__ = [
     "tf_warp", "get_pixel_value", "flow_resize", "flow_resize_warp", "set_warp_variant", "conv2d_nhwc",
     "AffineTransformer", "ProjectiveTransformer", "transformer",
     "vec2mtrx", "transformImage", "transformCropImage", "fit", "compose", "inverse",
+    "shard_range", "gather_output",
     "OfstabError", "lib_path", "load_library",
 ]

@@ -64,8 +64,9 @@ uint64_t ofs_launch_count(void);
  */
 int ofs_tf_warp(const float* img, const float* flow, float* out, int B, int H, int W, int C, ofs_stream stream);
 
-/* Tuning knob for ofs_tf_warp / ofs_flow_resize_warp at C=3: 1 (default) = shared-memory staged
- * source tiles, 0 = direct read-only-path gathers.  Results are identical. */
+/* Tuning knob for ofs_tf_warp / ofs_flow_resize_warp at C=3: 3 (default) = instruction-lean direct
+ * gathers, 0 = first direct-gather kernel, 1 / 2 = shared-memory staged source tiles (12-byte / padded
+ * 16-byte pixels).  Results are identical. */
 int ofs_set_warp_variant(int variant);
 
 /* Test-mode flow glue (main_dl.py:497-498): flow2*(384/fh) -> TF1 legacy bilinear resize to
