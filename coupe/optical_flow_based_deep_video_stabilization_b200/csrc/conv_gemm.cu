@@ -90,12 +90,14 @@ __device__ __forceinline__ void epilogue_store(const ConvGemmParams& p, const ui
 // CTA TMA-loads the A tile of its own 128 rows and HALF of the B tile; the leader (cluster rank 0) issues one
 // M=256 MMA reading both CTAs' shared memory; D rows 0-127 land in the leader's TMEM, rows 128-255 in the peer's.
 // kT = K blocks (taps of one slab group) per pipeline stage: 1, or 3 / 4 in slab mode.
-template <int BLOCK_N, bool kPair, int kT = 1>
+// kHead = 16: the LAST N tile of every phase carries 16 extra accumulator columns (2 real) for the fused flow head.
+template <int BLOCK_N, bool kPair, int kT = 1, int kHead = 0>
 struct GemmCfg {
+  static constexpr int kNB = BLOCK_N + kHead;            // B rows per stage / accumulator columns per TMEM stage
   static constexpr int kABytes = kT > 1 ? (kBlockM + 8) * kBlockK * 2 : kBlockM * kBlockK * 2;   // slab: up to 7 extra pixels
-  static constexpr int kBBytes = (BLOCK_N / (kPair ? 2 : 1)) * kBlockK * 2;
+  static constexpr int kBBytes = (kNB / (kPair ? 2 : 1)) * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kT * kBBytes;
-  static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+  static constexpr int kTmemCols = 2 * kNB <= 32 ? 32 : 2 * kNB <= 64 ? 64 : 2 * kNB <= 128 ? 128 : 2 * kNB <= 256 ? 256 : 512;
   static constexpr int kBarBytes = 256;
   static constexpr int kStgBytes = kBlockM * 128;        // one 64-channel chunk of the 16-bit output tile (SW128 rows)
   static constexpr int kStgTotal = BLOCK_N >= 64 ? 2 * kStgBytes : 0;   // double buffered; narrow tiles store directly
@@ -187,9 +189,11 @@ __device__ __forceinline__ void mma(uint32_t d, uint32_t da_lo, uint32_t db_lo, 
 // shared-memory addresses, TMA coordinates and UMMA descriptors in uniform registers.  A loop entered by
 // lane 0 alone (`if (lane == 0)`) makes every operand "possibly divergent" and each UTMALDG / UTCHMMA is then
 // wrapped in an ELECT + R2UR waterfall loop: ~2x the cycles per K block (see profiles/r01_tuning.md).
-template <int BLOCK_N, bool kPair, int kT>
+template <int BLOCK_N, bool kPair, int kT, int kHead>
 __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
-  using Cfg = GemmCfg<BLOCK_N, kPair, kT>;
+  using Cfg = GemmCfg<BLOCK_N, kPair, kT, kHead>;
+  static_assert(kHead == 0 || (!kPair && kT == 1 && BLOCK_N >= 64), "fused head: 1-CTA tiles of 64+ columns");
+  constexpr int kNB = Cfg::kNB;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -271,7 +275,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
       const int ks = rest2 / p.phases;
       const int gy0 = (m_t / p.tiles_x) * p.tile_rows;
       const int ox0 = (m_t % p.tiles_x) << p.tileW_log2;
-      const int w_row = ph * p.n_pad + n_t * BLOCK_N + (kPair ? (int)rank * (BLOCK_N / 2) : 0);
+      const int w_row = ph * p.w_rows_phase + n_t * BLOCK_N + (kPair ? (int)rank * (BLOCK_N / 2) : 0);
       const int b0 = gy0 / p.Hg;
       const int y0 = gy0 - b0 * p.Hg;
       int kb = ks * p.kb_per_split;
@@ -330,7 +334,8 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
       // ====================================== MMA issuer ======================================
       const bool leader = ptx::elect_one();
       const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-      const uint32_t idesc = ptx::umma_idesc_f16(kPair ? 2 * kBlockM : kBlockM, BLOCK_N, p.is_bf16);
+      const uint32_t idesc_main = ptx::umma_idesc_f16(kPair ? 2 * kBlockM : kBlockM, BLOCK_N, p.is_bf16);
+      const uint32_t idesc_last = ptx::umma_idesc_f16(kPair ? 2 * kBlockM : kBlockM, kNB, p.is_bf16);
       // descriptors: only the low word (start address >> 4) changes; the high word is a constant
       constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
       const uint32_t da0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);
@@ -345,7 +350,8 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
       for (int tile = unit; tile < total_tiles; tile += nunits) {
         lean::wait(tempty0 + 8 * acc, acc_phase ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        const uint32_t d_tmem = tmem_base + acc * kNB;
+        const uint32_t idesc = (kHead && (tile % p.tiles_n) == p.tiles_n - 1) ? idesc_last : idesc_main;
         const int ks = tile / (p.tiles_n * p.tiles_mp * p.phases);
         const int kb0 = ks * p.kb_per_split;
         const int nkb = min(num_kb, kb0 + p.kb_per_split) - kb0;
@@ -416,7 +422,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
       lean::wait(tfull0 + 8 * acc, acc_phase);
       ptx::tc_fence_after();
       if (trace && threadIdx.x == 64) { if (tile == unit) trace[5] = clock64(); trace[8] = clock64(); }
-      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * kNB;
       bool stored = false;
       if constexpr (BLOCK_N >= 64) {
         if (p.tma_store) {
@@ -457,6 +463,16 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
             }
             if (trace && threadIdx.x == 64) tq1 = clock64();
             if (c0 + 64 >= BLOCK_N) {   // every accumulator column of this tile has been read: release the TMEM stage
+              if constexpr (kHead > 0) {
+                // fused flow head (model.py:847-874): columns BLOCK_N, BLOCK_N+1 of the last N tile hold this phase's
+                // share of the 3x3 head on the same input; pyr_kernel sums the 4 phase shares per pixel
+                if (p.head_out && n_t == p.tiles_n - 1) {
+                  uint32_t hv[16];
+                  ptx::tmem_ld16(t_addr + BLOCK_N, hv);
+                  ptx::tmem_wait_ld();
+                  if (valid) p.head_out[pix] = make_float2(__uint_as_float(hv[0]), __uint_as_float(hv[1]));
+                }
+              }
               ptx::tc_fence_before();
               __syncwarp();
               if (lane == 0) {
@@ -563,18 +579,23 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  conv_gemm_body<BLOCK_N, false, 1>(p);
+  conv_gemm_body<BLOCK_N, false, 1, 0>(p);
+}
+// transposed conv with the level's flow head fused as 16 extra accumulator columns
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1) conv_gemmh_kernel(const __grid_constant__ ConvGemmParams p) {
+  conv_gemm_body<BLOCK_N, false, 1, 16>(p);
 }
 template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
-  conv_gemm_body<BLOCK_N, true, 1>(p);
+  conv_gemm_body<BLOCK_N, true, 1, 0>(p);
 }
 // slab mode (CTA pairs): kT taps of a group per stage
 template <int BLOCK_N, int kT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     conv_gemm2s_kernel(const __grid_constant__ ConvGemmParams p) {
-  conv_gemm_body<BLOCK_N, true, kT>(p);
+  conv_gemm_body<BLOCK_N, true, kT, 0>(p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -708,6 +729,21 @@ int launch_t2(const ConvPlan& plan, cudaStream_t st) {
     attr_set[dev] = true;
   }
   OFS_CUDA(launch_pdl(conv_gemm2_kernel<BLOCK_N>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, true>::kSmem, st, plan.p));
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
+}
+
+template <int BLOCK_N>
+int launch_th(const ConvPlan& plan, cudaStream_t st) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  OFS_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    OFS_CUDA(cudaFuncSetAttribute(conv_gemmh_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)GemmCfg<BLOCK_N, false, 1, 16>::kSmem));
+    attr_set[dev] = true;
+  }
+  OFS_CUDA(launch_pdl(conv_gemmh_kernel<BLOCK_N>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, false, 1, 16>::kSmem, st, plan.p));
   OFS_LAUNCH_CHECK();
   return OFS_OK;
 }
@@ -974,8 +1010,13 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
     OFS_REQUIRE(p.n_pad == d.cout, "16-bit output mode needs cout %% block_n == 0 (cout %d, block_n %d)", d.cout, d.block_n);
     OFS_REQUIRE(d.out_cstride % 8 == 0 && d.out_coff % 8 == 0, "16-bit output slice must be 16-byte aligned");
   }
+  if (d.head) {
+    OFS_REQUIRE(deconv && d.out_mode == 0 && d.cta_group == 1 && d.ksplit <= 1 && (d.block_n == 64 || d.block_n == 128),
+                "fused head: transposed conv, 16-bit output, 1-CTA tiles of 64 / 128 columns, no split-K");
+  }
+  p.w_rows_phase = p.n_pad + (d.head ? 16 : 0);
   plan.k_total = (p.slab ? (int)plan.wt_ky.size() : p.ntaps * p.nchunks) * kBlockK;
-  plan.w_rows = p.phases * p.n_pad;
+  plan.w_rows = p.phases * p.w_rows_phase;
   {
     const int num_kb = p.ntaps * p.nchunks;
     int ks = std::max(1, std::min(d.ksplit, num_kb));
@@ -989,7 +1030,10 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
   p.tma_store = (p.out_mode == 0 && d.block_n >= 64) ? 1 : 0;
   p.tiles_mp = d.cta_group == 2 ? (p.tiles_m + 1) / 2 : p.tiles_m;
   const int total_tiles = p.tiles_mp * p.tiles_n * p.phases * p.ksplit;
-  if (p.slab) {
+  if (d.head) {
+    plan.grid = std::max(1, std::min(total_tiles, sm_count()));
+    plan.smem = d.block_n == 64 ? GemmCfg<64, false, 1, 16>::kSmem : GemmCfg<128, false, 1, 16>::kSmem;
+  } else if (p.slab) {
     plan.grid = 2 * std::max(1, std::min(total_tiles, sm_count() / 2));
     plan.smem = d.block_n == 64 ? GemmCfg<64, true, 4>::kSmem : GemmCfg<128, true, 3>::kSmem;
   } else if (d.cta_group == 2) {
@@ -1016,7 +1060,7 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
 }
 
 void conv_pack_weights(const ConvPlan& plan, const float* w, const float* bias, std::vector<uint16_t>& out,
-                       std::vector<float>& b_padded) {
+                       std::vector<float>& b_padded, const float* head_w) {
   const ConvGemmParams& p = plan.p;
   const ConvDesc& d = plan.d;
   const int K = plan.k_total;
@@ -1035,8 +1079,20 @@ void conv_pack_weights(const ConvPlan& plan, const float* w, const float* bias, 
             const int kx = px == 0 ? (b == 0 ? 1 : 3) : (b == 0 ? 0 : 2);
             for (int n = 0; n < d.cout; ++n) {
               const float* src = w + (((size_t)ky * 4 + kx) * d.cout + n) * d.cin;
-              uint16_t* dst = out.data() + ((size_t)ph * p.n_pad + n) * K + (size_t)t * p.nchunks * kBlockK;
+              uint16_t* dst = out.data() + ((size_t)ph * p.w_rows_phase + n) * K + (size_t)t * p.nchunks * kBlockK;
               for (int ci = 0; ci < d.cin; ++ci) dst[ci] = cvt(src[ci]);
+            }
+            if (d.head && head_w) {
+              // 3x3 head on the same input, tap (dy,dx) = this phase tap's input offset; every head tap is owned
+              // by exactly one phase: (py,px) = (dy == 1, dx == 1)
+              const int dy = p.tap_y[ph * 4 + t], dx = p.tap_x[ph * 4 + t];
+              if ((dy == 1) == (py == 1) && (dx == 1) == (px == 1)) {
+                for (int o = 0; o < 2; ++o) {
+                  uint16_t* dst = out.data() + ((size_t)ph * p.w_rows_phase + p.n_pad + o) * K + (size_t)t * p.nchunks * kBlockK;
+                  for (int ci = 0; ci < d.cin; ++ci)
+                    dst[ci] = cvt(head_w[(((size_t)(dy + 1) * 3 + (dx + 1)) * d.cin + ci) * 2 + o]);
+                }
+              }
             }
           }
   } else if (plan.paired) {
@@ -1063,7 +1119,7 @@ void conv_pack_weights(const ConvPlan& plan, const float* w, const float* bias, 
 }
 
 int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const float* bias_dev, void* out,
-                   float* workspace) {
+                   float* workspace, float* head_out) {
   ConvGemmParams& p = plan.p;
   const ConvDesc& d = plan.d;
   OFS_REQUIRE(act_in && w_dev && bias_dev && out, "conv bind: null pointer");
@@ -1079,6 +1135,8 @@ int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const 
     p.out = out;
   }
   p.bias = bias_dev;
+  p.head_out = reinterpret_cast<float2*>(head_out);
+  OFS_REQUIRE(!d.head || head_out, "conv bind: the fused head needs its output buffer");
   const cuuint32_t tileW = 1u << p.tileW_log2;
   unsigned long long vd[5], vs[4];
   conv_act_view(d, vd, vs);
@@ -1102,13 +1160,17 @@ int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const 
   }
   cuuint64_t wd[2] = {(cuuint64_t)plan.k_total, (cuuint64_t)plan.w_rows};
   cuuint64_t ws[1] = {(cuuint64_t)plan.k_total * 2};
-  cuuint32_t wb[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(plan.block_n / d.cta_group)};
+  cuuint32_t wb[2] = {(cuuint32_t)kBlockK, (cuuint32_t)((plan.block_n + (d.head ? 16 : 0)) / d.cta_group)};
   return encode_map(&p.tmap_w, d.is_bf16, 2, w_dev, wd, ws, wb);
 }
 
 int conv_launch(const ConvPlan& plan, cudaStream_t st) {
   int rc = OFS_EINVAL;
-  if (plan.p.slab) {
+  if (plan.d.head) {
+    if (plan.block_n == 64) rc = launch_th<64>(plan, st);
+    else if (plan.block_n == 128) rc = launch_th<128>(plan, st);
+    else { set_error("conv_launch: fused head needs block_n 64 or 128 (got %d)", plan.block_n); return OFS_EINVAL; }
+  } else if (plan.p.slab) {
     if (plan.block_n == 64 && plan.group_max <= 4) rc = launch_t2s<64, 4>(plan, st);
     else if (plan.block_n == 128 && plan.group_max <= 3) rc = launch_t2s<128, 3>(plan, st);
     else { set_error("conv_launch: no slab kernel for block_n %d with %d taps per group", plan.block_n, plan.group_max); return OFS_EINVAL; }

@@ -36,6 +36,8 @@ struct ConvGemmParams {
   long long ws_split_stride;  // workspace elements between two splits = out pixels * n_pad
   int ntaps, nchunks;  // K_total = ntaps * nchunks * 64
   int n_pad;           // padded output channels per phase
+  int w_rows_phase;    // packed weight rows per phase = n_pad (+ 16 with a fused head)
+  float2* head_out;    // fused head: this phase's share per OUTPUT pixel [B, out_H, out_W] (null: no head)
   // epilogue
   void* out;           // 16-bit activations (mode 0) or fp32 (mode 1)
   const float* bias;   // [n_pad]
@@ -76,6 +78,7 @@ struct ConvDesc {
   int out_cstride, out_coff;
   int ksplit = 1;      // > 1: split the K loop over this many CTAs per tile (16-bit output mode only)
   int cta_group = 1;   // 2: CTA pairs (tcgen05 cta_group::2): tile = 256 GEMM rows x BLOCK_N, B split over the pair
+  int head = 0;        // 1: transposed conv with the level's 3x3 flow head fused as 16 extra accumulator columns
   int slab = 0;        // 1: x-shifted taps share one shared-memory slab (stride-2 convs whose tiles are one 128-px row)
   int debug = 0;       // see ConvGemmParams::debug
   long long* trace = nullptr;  // see ConvGemmParams::trace
@@ -107,10 +110,10 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d);
 // Packs float32 weights (TF layout: conv [k,k,cin,cout]; deconv [4,4,cout,cin]) into the 16-bit
 // K-major GEMM layout of `plan` (w_rows x k_total) and the padded bias [n_pad].
 void conv_pack_weights(const ConvPlan& plan, const float* w_tf, const float* bias, std::vector<uint16_t>& w_packed,
-                       std::vector<float>& b_padded);
+                       std::vector<float>& b_padded, const float* head_w = nullptr /* [3,3,cin,2] when plan.d.head */);
 // Binds device pointers and encodes the TMA descriptors.
 int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_packed_dev, const float* bias_dev, void* out,
-                   float* workspace = nullptr);
+                   float* workspace = nullptr, float* head_out = nullptr);
 int conv_launch(const ConvPlan& plan, cudaStream_t st);
 
 // 5-D TMA view of the input activation (dims in elements, strides in bytes; dim 0 is contiguous)

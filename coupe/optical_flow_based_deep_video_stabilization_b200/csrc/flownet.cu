@@ -1,7 +1,7 @@
 // ofs_net: the FlowNetS-pyramid forward of the stabiliser (reference model.py:786-893) on sm_100a.
 //
 //   feats fp32 [B,384,512,27] --pack--> 16-bit [B,384,512,32]
-//   10 encoder convs + 4 transposed convs + 5 flow heads  -> conv_gemm.cu (tcgen05 implicit GEMM)
+//   10 encoder convs + 4 transposed convs (+ the 4 flow heads predict6..3 fused as extra columns) -> conv_gemm.cu
 //   BatchNorm (moving stats, no gamma, eps 1e-5) is folded into W'/b' at load time
 //   ConcatLayer            -> never materialised: producers write channel slices of concat buffers
 //   flow pyramid           -> pyr_kernel: f_n = head_n + up(f_{n+1}) + up(f_{n+1})  (TF1 legacy bilinear)
@@ -62,7 +62,8 @@ __device__ __forceinline__ float2 tf1_bilinear2(const float2* __restrict__ src, 
 }
 
 struct PyrParams {
-  const float2* raw;     // head output at this level [B,h,w]
+  const float2* hpart;   // fused head: per-phase shares at this level [B,2h,2w] (written by the level's deconv GEMM)
+  float hb0, hb1;        // head bias
   const float2* f_prev;  // summed flow of the coarser level [B,h/2,w/2] or null (level 6)
   float2* f_out;         // summed flow at this level [B,h,w]
   const float* up_w;     // [4,4,2,2] (ky,kx,co,ci) then [2] bias
@@ -72,7 +73,12 @@ struct PyrParams {
 
 // model.py:857/866/875 (ElementwiseLayer left fold) + model.py:852/861/870/879 (flow up-sampler)
 __device__ __forceinline__ float2 pyr_flow_at(const PyrParams& p, int b, int i, int j) {
-  float2 v = p.raw[((size_t)b * p.h + i) * p.w + j];
+  // predictN = sum of the 4 phase shares (fixed order) + bias (model.py:847-848,855-856,864-865,873-874)
+  const float2* hp = p.hpart + ((size_t)b * 2 * p.h + 2 * i) * (2 * p.w) + 2 * j;
+  const float2 s00 = hp[0], s01 = hp[1], s10 = hp[2 * p.w], s11 = hp[2 * p.w + 1];
+  float2 v;
+  v.x = ((s00.x + s01.x) + (s10.x + s11.x)) + p.hb0;
+  v.y = ((s00.y + s01.y) + (s10.y + s11.y)) + p.hb1;
   if (p.f_prev) {
     const int hp = p.h >> 1, wp = p.w >> 1;
     const float2 u = tf1_bilinear2(p.f_prev + (size_t)b * hp * wp, hp, wp, (float)hp / (float)p.h,
@@ -164,89 +170,15 @@ __global__ void predict2_gather_kernel(Predict2Params p) {
   }
 }
 
-// Flow heads predict6..predict3 (model.py:847-848,855-856,864-865,873-874): zero-pad 1 + 3x3 conv to 2
-// channels + bias, no activation.  N = 2 is far below a tcgen05 tile (the N=16 GEMM form spent 0.39 ms on
-// the four heads), so this is a warp-level mma.sync kernel: a block of 9 warps owns 16 consecutive output
-// pixels, warp k = tap k.  Per 32 input channels a lane issues two 128-bit activation loads (rows g, g+8)
-// and, on lanes 0-7, one 128-bit weight load, feeding two m16n8k16 MMAs (columns 0,1 of N are real).
-// The K index is only summed over, so the 8 channels a lane loads are mapped onto the fragment's k slots
-// in load order -- identically for A and B.  The 9 per-tap partials are summed in a fixed order.
-struct HeadParams {
-  const uint16_t* act;  // [B,h,w,cs]
-  const uint16_t* wgt;  // [9][2][cs]   (zero for c >= cin)
-  float2* out;          // [B,h,w]
-  float b0, b1;
-  int B, h, w, cs, is_bf16;
-};
-
-__device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
-                                         uint32_t b1, int is_bf16) {
-  if (is_bf16) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-  } else {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-  }
-}
-
-__global__ void __launch_bounds__(288) head3x3_kernel(HeadParams p) {
-  __shared__ float part[9][32];
-  pdl_wait();
-  pdl_launch_dependents();
-  const int lane = threadIdx.x & 31, tap = threadIdx.x >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-  const int npix = p.B * p.h * p.w;
-  const int ngroups = (npix + 15) >> 4;
-  const uint4 zero4 = make_uint4(0, 0, 0, 0);
-  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-    const uint16_t* ap[2];
-    bool ok[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int pix = grp * 16 + g + 8 * r;
-      const int x = pix % p.w, rest = pix / p.w;
-      const int y = rest % p.h, b = rest / p.h;
-      const int yy = y + dy, xx = x + dx;
-      ok[r] = (pix < npix) && yy >= 0 && yy < p.h && xx >= 0 && xx < p.w;
-      ap[r] = p.act + (((size_t)b * p.h + (ok[r] ? yy : 0)) * p.w + (ok[r] ? xx : 0)) * p.cs;
-    }
-    const uint16_t* wp = p.wgt + (size_t)(tap * 2 + (g < 2 ? g : 0)) * p.cs;
-    float c[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-    for (int c0 = 0; c0 < p.cs; c0 += 32) {
-      const int ch = c0 + 8 * t;
-      const bool in = ch < p.cs;
-      const uint4 A0 = (ok[0] && in) ? __ldg(reinterpret_cast<const uint4*>(ap[0] + ch)) : zero4;
-      const uint4 A1 = (ok[1] && in) ? __ldg(reinterpret_cast<const uint4*>(ap[1] + ch)) : zero4;
-      const uint4 Bv = (g < 2 && in) ? __ldg(reinterpret_cast<const uint4*>(wp + ch)) : zero4;
-      mma16816(c, A0.x, A1.x, A0.y, A1.y, Bv.x, Bv.y, p.is_bf16);
-      mma16816(c, A0.z, A1.z, A0.w, A1.w, Bv.z, Bv.w, p.is_bf16);
-    }
-    if (t == 0) {  // columns 0,1 of the 16x8 tile: rows g and g+8
-      part[tap][g * 2 + 0] = c[0]; part[tap][g * 2 + 1] = c[1];
-      part[tap][(g + 8) * 2 + 0] = c[2]; part[tap][(g + 8) * 2 + 1] = c[3];
-    }
-    __syncthreads();
-    if (tap == 0) {
-      float s = (lane & 1) ? p.b1 : p.b0;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) s += part[k][lane];
-      const int pix = grp * 16 + (lane >> 1);
-      if (pix < npix) reinterpret_cast<float*>(p.out)[(size_t)pix * 2 + (lane & 1)] = s;
-    }
-    __syncthreads();
-  }
-}
-
+// Flow heads predict6..predict3 (model.py:847-848,855-856,864-865,873-874: zero-pad 1 + 3x3 conv to 2 channels +
+// bias) read the same input as the level's transposed conv, and the 4 sub-pixel phases of that conv together visit
+// exactly the head's 9 taps.  Each head is therefore FUSED into its level's deconv GEMM as 16 extra accumulator
+// columns (2 real) on the last N tile: phase (py,px) accumulates the head taps (dy,dx) with (dy==1, dx==1) ==
+// (py,px), the epilogue writes the phase share per output pixel, and pyr_kernel adds the 4 shares and the bias.
+// (The stand-alone mma.sync head kernel this replaces cost 90 us per step at batch 8 for 36 MMAC.)
 struct Head {
   std::string name;   // "predict6" .. "predict3"
-  int level, h, w, cin, cs;
-  const void* in = nullptr;
-  void* w_dev = nullptr;  // [9][2][cs] 16-bit
+  int level, cin;
   float bias[2] = {0, 0};
 };
 
@@ -281,7 +213,7 @@ struct ofs_net {
   void *x0 = nullptr, *conv1 = nullptr, *concat2 = nullptr, *conv3 = nullptr, *concat3 = nullptr, *conv4 = nullptr,
        *concat4 = nullptr, *conv5 = nullptr, *concat5 = nullptr, *conv6 = nullptr, *conv6_1 = nullptr;
   // fp32
-  float *raw[7] = {nullptr}, *f[7] = {nullptr};  // index = pyramid level 3..6; f[2] = flow2
+  float *hpart[7] = {nullptr}, *f[7] = {nullptr};  // index = pyramid level 3..6 (hpart: fused-head phase shares); f[2] = flow2
   float* P2 = nullptr;
   float* f2s = nullptr;  // pre-scaled flow2 for the fused flow-resize + warp
   float* upw = nullptr;  // 4 x (64 + 2) floats: upsample6_5, 5_4, 4_3, 3_2
@@ -408,25 +340,13 @@ int prepare(ofs_net* n, int B) {
     n->ws_bytes = want;
   }
   for (Layer& L : n->layers) {
-    int rc = conv_plan_bind(L.plan, L.in, L.w_dev, L.b_dev, L.out, n->ws);
+    float* head_out = nullptr;
+    if (L.d.head) head_out = n->hpart[L.name == "deconv5" ? 6 : L.name == "deconv4" ? 5 : L.name == "deconv3" ? 4 : 3];
+    int rc = conv_plan_bind(L.plan, L.in, L.w_dev, L.b_dev, L.out, n->ws, head_out);
     if (rc != OFS_OK) return rc;
     L.plans[B] = L.plan;
   }
   n->prepared_B = B;
-  return OFS_OK;
-}
-
-int launch_head(ofs_net* n, const Head& h, int B, cudaStream_t st) {
-  HeadParams p;
-  p.act = reinterpret_cast<const uint16_t*>(h.in);
-  p.wgt = reinterpret_cast<const uint16_t*>(h.w_dev);
-  p.out = reinterpret_cast<float2*>(n->raw[h.level]);
-  p.b0 = h.bias[0]; p.b1 = h.bias[1];
-  p.B = B; p.h = h.h; p.w = h.w; p.cs = h.cs; p.is_bf16 = n->is_bf16;
-  const size_t npix = (size_t)B * h.h * h.w;
-  const int blocks = (int)std::min<size_t>((npix + 15) / 16, (size_t)sm_count() * 6);
-  OFS_CUDA(launch_pdl(head3x3_kernel, dim3(blocks), dim3(288), 0, st, p));
-  OFS_LAUNCH_CHECK();
   return OFS_OK;
 }
 
@@ -445,7 +365,8 @@ int launch_pyr(ofs_net* n, int level, int B, cudaStream_t st) {
   // level in {6,5,4,3}; grid h x w of that level; writes into the concat buffer of level-1
   static const int hs[7] = {0, 0, 0, 48, 24, 12, 6}, ws[7] = {0, 0, 0, 64, 32, 16, 8};
   PyrParams p;
-  p.raw = reinterpret_cast<const float2*>(n->raw[level]);
+  p.hpart = reinterpret_cast<const float2*>(n->hpart[level]);
+  p.hb0 = n->heads[6 - level].bias[0]; p.hb1 = n->heads[6 - level].bias[1];
   p.f_prev = level == 6 ? nullptr : reinterpret_cast<const float2*>(n->f[level + 1]);
   p.f_out = reinterpret_cast<float2*>(n->f[level]);
   p.up_w = n->upw + (6 - level) * 66;
@@ -509,12 +430,6 @@ int forward_impl(ofs_net* n, const float* feats, int B, float* f2_target, cudaSt
     else if (L.name == "deconv4") lvl = 5;
     else if (L.name == "deconv3") lvl = 4;
     else if (L.name == "deconv2") lvl = 3;
-    if (lvl) {  // the head of this level reads the same input as the transposed conv
-      const Head& h = n->heads[6 - lvl];
-      rc = launch_head(n, h, B, st);
-      if (rc != OFS_OK) return rc;
-      OFS_MARK("head:" + h.name, 0.0);
-    }
     rc = conv_launch(L.plan, st);
     if (rc != OFS_OK) return rc;
     OFS_MARK(L.name == "predict2" ? std::string("gemm:predict2_product") : "gemm:" + L.name,
@@ -570,7 +485,7 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
   static const int hs[7] = {0, 0, 382, 48, 24, 12, 6}, ws[7] = {0, 0, 510, 64, 32, 16, 8};
   for (int l = 2; l <= 6; ++l) {
     rc = dev_alloc(n, (void**)&n->f[l], B * hs[l] * ws[l] * 2 * 4, true);
-    if (rc == OFS_OK && l >= 3) rc = dev_alloc(n, (void**)&n->raw[l], B * hs[l] * ws[l] * 2 * 4, true);
+    if (rc == OFS_OK && l >= 3) rc = dev_alloc(n, (void**)&n->hpart[l], B * 4 * hs[l] * ws[l] * 2 * 4, true);
     if (rc != OFS_OK) { ofs_net_destroy(n); return rc; }
   }
   rc = dev_alloc(n, (void**)&n->P2, B * 96 * 128 * 18 * 4, true);
@@ -607,15 +522,7 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
   Ls.push_back(make_layer("deconv2", "deconv2_bn", kDeconvK4S2, 48, 64, 386, 392, 64, 4, 2, 64, 0, 1, 200, 128, n->concat3, n->concat2));
   // predict2 as a 1x1 GEMM with 18 columns on the 96x128 grid
   Ls.push_back(make_layer("predict2", "", kConv, 96, 128, 194, 200, 18, 1, 1, 32, 1, 0, 18, 0, n->concat2, n->P2));
-  {
-    Head h6{"predict6", 6, 6, 8, 1024, 1024, n->conv6_1}, h5{"predict5", 5, 12, 16, 1026, 1032, n->concat5},
-        h4{"predict4", 4, 24, 32, 770, 776, n->concat4}, h3{"predict3", 3, 48, 64, 386, 392, n->concat3};
-    n->heads = {h6, h5, h4, h3};
-    for (Head& h : n->heads) {
-      rc = dev_alloc(n, &h.w_dev, (size_t)9 * h.cs * 2 * 2, true);
-      if (rc != OFS_OK) { ofs_net_destroy(n); return rc; }
-    }
-  }
+  n->heads = {Head{"predict6", 6, 1024}, Head{"predict5", 5, 1026}, Head{"predict4", 4, 770}, Head{"predict3", 3, 386}};
   // Deep layers have few output tiles (conv6_1 at B=8: 32) but long K loops: their K loop is split over
   // several CTAs (fp32 partials in a workspace, summed in a fixed order).  The factors are constants of the
   // layer -- not of the batch -- so a frame pair's result is bit-identical whatever batch it rides in.
@@ -627,8 +534,7 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
     } else if (L.name == "3" || L.name == "3_1" || L.name == "4" || L.name == "4_1") { L.block_n_run = 256; }
     else if (L.name == "5" || L.name == "5_1") { L.block_n_run = 256; L.ksplit = 6; }
     else if (L.name == "6" || L.name == "6_1") { L.block_n_run = 256; L.ksplit = 8; }
-    else if (L.name == "deconv5") { L.block_n_run = 256; L.ksplit = 4; }
-    else if (L.name == "deconv4") { L.block_n_run = 256; L.ksplit = 3; }
+    else if (L.d.kind == kDeconvK4S2) { L.d.head = 1; }   // the level's flow head rides in the deconv GEMM (128 / 64-column tiles)
   }
   for (Layer& L : Ls) {
     L.d.is_bf16 = n->is_bf16;
@@ -738,28 +644,23 @@ int ofs_net_load_weights(ofs_net* n, const ofs_named_array* arrays, int count) {
           for (int o = 0; o < 2; ++o) w1[(size_t)ci * 18 + t * 2 + o] = wf[((size_t)t * cin + ci) * 2 + o];
       conv_pack_weights(L.plan, w1.data(), nullptr, wp, bp);
       n->p2_bias[0] = bf[0]; n->p2_bias[1] = bf[1];
+    } else if (L.d.head) {
+      // the flow head of this level (predict6 with deconv5, ... predict3 with deconv2) shares the GEMM
+      Head& h = n->heads[L.name == "deconv5" ? 0 : L.name == "deconv4" ? 1 : L.name == "deconv3" ? 2 : 3];
+      const float *hw = nullptr, *hb = nullptr;
+      rc = find(h.name + "/W_conv2d", (int64_t)9 * h.cin * 2, &hw, true);
+      if (rc == OFS_OK) rc = find(h.name + "/b_conv2d", 2, &hb, false);
+      if (rc != OFS_OK) return rc;
+      OFS_REQUIRE(h.cin == cin, "internal: head / deconv input mismatch for %s", L.name.c_str());
+      h.bias[0] = hb ? hb[0] : 0.f;
+      h.bias[1] = hb ? hb[1] : 0.f;
+      conv_pack_weights(L.plan, wf.data(), bf.data(), wp, bp, hw);
     } else {
       conv_pack_weights(L.plan, wf.data(), bf.data(), wp, bp);
     }
     OFS_REQUIRE(wp.size() == L.w_elems && (int)bp.size() == L.n_pad, "internal: packed size mismatch for %s", L.name.c_str());
     OFS_CUDA(cudaMemcpy(L.w_dev, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
     OFS_CUDA(cudaMemcpy(L.b_dev, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice));
-  }
-  for (Head& h : n->heads) {
-    const float *w = nullptr, *b = nullptr;
-    int rc = find(h.name + "/W_conv2d", (int64_t)9 * h.cin * 2, &w, true);
-    if (rc == OFS_OK) rc = find(h.name + "/b_conv2d", 2, &b, false);
-    if (rc != OFS_OK) return rc;
-    std::vector<uint16_t> wp((size_t)9 * 2 * h.cs, 0);   // [tap][o][c]; TF layout is [ky,kx,ci,o]
-    for (int t = 0; t < 9; ++t)
-      for (int c = 0; c < h.cin; ++c)
-        for (int o = 0; o < 2; ++o) {
-          const float v = w[((size_t)t * h.cin + c) * 2 + o];
-          wp[((size_t)t * 2 + o) * h.cs + c] = n->is_bf16 ? f32_to_bf16_rn(v) : f32_to_fp16_rn(v);
-        }
-    h.bias[0] = b ? b[0] : 0.f;
-    h.bias[1] = b ? b[1] : 0.f;
-    OFS_CUDA(cudaMemcpy(h.w_dev, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
   }
   static const char* ups[4] = {"upsample6_5", "upsample5_4", "upsample4_3", "upsample3_2"};
   std::vector<float> upw(4 * 66, 0.0f);
@@ -951,7 +852,7 @@ int ofs_net_profile(ofs_net* n, const float* feats, const float* frames, float* 
 
 int ofs_net_launches_per_forward(const ofs_net* n) {
   if (!n) return 0;
-  int k = 1 + (int)n->layers.size() + (int)n->heads.size() + 4 + 1;  // pack + GEMMs + heads + pyramid steps + gather
+  int k = 1 + (int)n->layers.size() + 4 + 1;  // pack + GEMMs (heads ride in the deconvs) + pyramid steps + gather
   for (const Layer& L : n->layers) k += L.plan.p.ksplit > 1 ? 1 : 0;  // split-K reductions (after prepare())
   return k;
 }
