@@ -13,7 +13,8 @@ random-init weights, synthetic frames.  Rank 0 prints ONE JSON line (see the key
     e2e          same metric through the C-ABI host-buffer call (ofs_net_stabilize_host): pinned host
                  inputs, H2D + compute + D2H inside the timed region
     roofline     dominant kernel (tcgen05 implicit-GEMM conv): algorithmic FLOPs of the 14 dense layers /
-                 their summed launch time, measured live with CUDA events, vs MEASURED_PEAKS.json
+                 their launch time (replayed from one CUDA graph as in the step, CUDA events), vs MEASURED_PEAKS.json
+    breakdown    per-launch times with an event after every launch (diagnostic: includes launch gaps)
     roofline_warp  the HBM-bound fused flow-resize + warp kernel
     cpu_baseline the CPU oracle (a port of the reference arithmetic; TensorFlow 1.10 is not installable)
                  timed on this box's host cores on a bounded sample
@@ -38,6 +39,10 @@ UNIT = "pairs/s"
 BATCH, FRAME_H, FRAME_W = 8, 720, 1280
 DENSE_GFLOP_PER_PAIR = 37.89      # 10 encoder convs + 4 transposed convs, literal MACs x 2
 WARP_BYTES_PER_PX = 24.0          # fused flow-resize+warp: image 12 + out 12 (+1.56 MB of flow2 per frame)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch (set) from the committed ncu --set full capture of this
+# workload (profiles/r01_ncu_full_summary.md); refreshed by hand when the capture is
+NCU_TRAFFIC_DENSE_SET_BYTES = 448.0e6   # 14 dense GEMM launches + 4 split-K reductions, batch 8
+NCU_TRAFFIC_WARP_BYTES = 146.6e6        # warp5_kernel<true>, 8 x 720p
 FLOW2_BYTES = 382 * 510 * 2 * 4
 
 
@@ -220,24 +225,27 @@ def run_ours(args):
     roofline = roofline_warp = breakdown = None
     if rank == 0:
         prof = net.profile(sets[0][0], sets[0][1], iters=max(3, min(args.steps, 10)))
-        dense = [(n, ms, m) for (n, ms, m) in prof if n.startswith("gemm:") and not n.startswith("gemm:predict")]
-        gemm_ms = sum(ms for _, ms, _ in dense)
-        flops = 2.0 * sum(m for _, _, m in dense)
-        step_ms = sum(ms for _, ms, _ in prof)
+        step_ms = ms_total / args.steps
+        # dominant kernel = the tcgen05 implicit-GEMM conv: its 14 launches per step (plus split-K reductions) are
+        # replayed from one CUDA graph, exactly as the step runs them, between two CUDA events on the net's stream
+        gemm_ms, macs, gemm_launches = net.time_kernels("dense", BATCH, iters=20)
+        flops = 2.0 * macs
         ach = flops / (gemm_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
-                    "kernel": "conv_gemm_kernel<BLOCK_N> (14 dense conv/deconv layers of one step)",
-                    "launches_per_step": len(dense), "ms_per_step_in_kernel": gemm_ms, "share_of_step": gemm_ms / step_ms,
+                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": NCU_TRAFFIC_DENSE_SET_BYTES,
+                    "traffic_source": "ncu --set full, profiles/r01_ncu_full_summary.md (DRAM bytes of the launch set)",
+                    "kernel": "conv_gemm*_kernel (the 14 dense conv / transposed-conv layers of one step, incl. split-K reductions)",
+                    "launches_per_step": gemm_launches, "ms_per_step_in_kernel": gemm_ms, "share_of_step": gemm_ms / step_ms,
                     "algorithmic_gflop_per_launch_set": flops / 1e9, "peak_source": peaks["source"] + " (sustained bf16)",
-                    "frac_of_burst_peak": ach / peaks["bf16_tflops"], "frac_of_nominal_2250": ach / 2250.0}
-        wms = [ms for n, ms, _ in prof if n == "flow_resize_warp"][0]
+                    "frac_of_burst_peak": ach / peaks["bf16_tflops"], "frac_of_nominal_2250": ach / 2250.0,
+                    "timing": "20 repetitions of the launch set replayed from one CUDA graph, CUDA events on the launching stream"}
+        wms, _, _ = net.time_kernels("warp", BATCH, frames=sets[0][1], iters=20)
         wbytes = BATCH * (FRAME_H * FRAME_W * WARP_BYTES_PER_PX + FLOW2_BYTES)
         wach = wbytes / (wms * 1e-3) / 1e9
         roofline_warp = {"bound": "hbm", "achieved": wach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": wach / peaks["hbm_gbs"], "traffic": None, "kernel": "warp_staged3_kernel (fused flow-resize + tf_warp)",
+                         "frac": wach / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC_WARP_BYTES, "kernel": "warp5_kernel<true> (fused flow-resize + tf_warp)",
                          "ms_per_launch": wms, "algorithmic_bytes_per_launch": wbytes, "frac_of_nominal_7700": wach / 7700.0,
-                         "peak_source": peaks["source"]}
+                         "share_of_step": wms / step_ms, "peak_source": peaks["source"]}
         breakdown = [{"kernel": n, "ms": round(ms, 4), "tflops": (2 * m / (ms * 1e-3) / 1e12 if m else None)} for n, ms, m in prof]
 
     # ---- e2e: the C-ABI host-buffer call, pinned host inputs, H2D + compute + D2H every step
@@ -288,7 +296,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--precision", choices=["bf16", "fp16"], default="bf16")

@@ -51,6 +51,7 @@ PROTOTYPES = {
     "ofs_net_stabilize_host": (_i, [_p, _p, _p, _p, _i, _i, _i]),
     "ofs_net_get_activation": (_i, [_p, C.c_char_p, _i, _p, C.c_int64, C.POINTER(_i), _p]),
     "ofs_net_profile": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, C.POINTER(_i), _p]),
+    "ofs_net_time_kernels": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "ofs_net_launches_per_forward": (_i, [_p]),
     "ofs_conv2d_nhwc": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ofs_conv2d_nhwc_ex": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),

@@ -1372,20 +1372,38 @@ extern "C" int ofs_conv2d_bench(int B, int H, int W, int Cin, int in_cs, int Cou
   // back-to-back launches between ONE event pair (no host sync inside): steady-state time per launch including
   // the inter-kernel gap, excluding host launch latency.  With flush_mb the same loop is timed with the flush
   // kernel alone and subtracted.
+  // `iters` launches captured into ONE CUDA graph and replayed (as the network does): no host launch cost
+  // between them.  With flush_mb the same graph is built with the flush kernel alone and its time subtracted.
   double total_ms = 0.0;
+  cudaStream_t cs = nullptr;
+  if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { cleanup(); set_error("stream create failed"); return OFS_ECUDA; }
+  cudaStreamSynchronize(st);
   for (int pass = 0; pass < (fl ? 2 : 1) && rc == OFS_OK; ++pass) {
     const bool with_conv = pass == 0;
-    for (int it = -3; it < iters && rc == OFS_OK; ++it) {   // 3 warm-up launches
-      if (it == 0) cudaEventRecord(e0, st);
-      if (fl) flush_kernel<<<sm_count() * 8, 256, 0, st>>>((uint4*)fl, flush_bytes / 16);
-      if (with_conv) rc = conv_launch(plan, st);
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    rc = check_cuda(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal), "begin capture", __FILE__, __LINE__);
+    for (int it = 0; it < iters && rc == OFS_OK; ++it) {
+      if (fl) flush_kernel<<<sm_count() * 8, 256, 0, cs>>>((uint4*)fl, flush_bytes / 16);
+      if (with_conv) rc = conv_launch(plan, cs);
     }
-    cudaEventRecord(e1, st);
-    if (rc == OFS_OK) rc = check_cuda(cudaStreamSynchronize(st), "conv bench sync", __FILE__, __LINE__);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    total_ms += with_conv ? ms : -ms;
+    cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    if (rc == OFS_OK) rc = check_cuda(ce, "end capture", __FILE__, __LINE__);
+    if (rc == OFS_OK) rc = check_cuda(cudaGraphInstantiate(&exec, graph, 0), "instantiate", __FILE__, __LINE__);
+    if (rc == OFS_OK) {
+      cudaGraphLaunch(exec, cs);   // warm-up replay
+      cudaEventRecord(e0, cs);
+      cudaGraphLaunch(exec, cs);
+      cudaEventRecord(e1, cs);
+      rc = check_cuda(cudaStreamSynchronize(cs), "conv bench sync", __FILE__, __LINE__);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      total_ms += with_conv ? ms : -ms;
+    }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
   }
+  cudaStreamDestroy(cs);
   if (rc == OFS_OK) *ms_avg = (float)(total_ms / iters);
   if (rc == OFS_OK && trace_host && trace_cap >= plan.grid * 32) {
     // the traced launch is the LAST of another back-to-back burst: same clocks / cache state as the timed loop

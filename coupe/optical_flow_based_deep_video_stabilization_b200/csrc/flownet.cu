@@ -850,6 +850,61 @@ int ofs_net_profile(ofs_net* n, const float* feats, const float* frames, float* 
   return rc;
 }
 
+int ofs_net_time_kernels(ofs_net* n, int which, const float* frames, float* out, int B, int H, int W, int iters,
+                         float* ms_per_set, double* macs_per_set, int* launches_per_set) {
+  OFS_REQUIRE(n && ms_per_set && iters >= 1 && (which == 0 || which == 1), "ofs_net_time_kernels: bad arguments");
+  OFS_REQUIRE(B >= 1 && B <= n->max_batch, "ofs_net_time_kernels: batch %d outside [1, %d]", B, n->max_batch);
+  OFS_REQUIRE(which == 0 || (frames && out && H > 0 && W > 0), "ofs_net_time_kernels: the warp needs frames / out");
+  if (!n->loaded) { set_error("ofs_net_time_kernels: weights not loaded"); return OFS_ESTATE; }
+  OFS_CUDA(cudaSetDevice(n->device));
+  int rc = prepare(n, B);
+  if (rc != OFS_OK) return rc;
+  cudaStream_t cs = n->stream;
+  OFS_CUDA(cudaStreamSynchronize(cs));
+  double macs = 0.0;
+  const uint64_t l0 = launch_count();
+  OFS_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+  for (int it = 0; it < iters && rc == OFS_OK; ++it) {
+    if (which == 0) {
+      for (Layer& L : n->layers) {
+        if (L.name == "predict2") continue;
+        rc = conv_launch(L.plan, cs);
+        if (rc != OFS_OK) break;
+        if (it == 0) macs += L.plan.macs;
+      }
+    } else {
+      rc = flow_resize_warp_impl(frames, n->f2s, out, B, H, W, 382, 510, cs, 1);
+    }
+  }
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+  const int launches = (int)(launch_count() - l0);
+  count_launch(-launches);
+  if (rc != OFS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+  OFS_CUDA(ce);
+  cudaGraphExec_t exec = nullptr;
+  cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  OFS_CUDA(ie);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaGraphLaunch(exec, cs);           // warm-up replay
+  cudaEventRecord(e0, cs);
+  cudaGraphLaunch(exec, cs);
+  cudaEventRecord(e1, cs);
+  rc = check_cuda(cudaStreamSynchronize(cs), "time_kernels sync", __FILE__, __LINE__);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaGraphExecDestroy(exec);
+  count_launch(2 * launches);
+  if (rc != OFS_OK) return rc;
+  *ms_per_set = ms / (float)iters;
+  if (macs_per_set) *macs_per_set = macs;
+  if (launches_per_set) *launches_per_set = launches / iters;
+  return OFS_OK;
+}
+
 int ofs_net_launches_per_forward(const ofs_net* n) {
   if (!n) return 0;
   int k = 1 + (int)n->layers.size() + 4 + 1;  // pack + GEMMs (heads ride in the deconvs) + pyramid steps + gather

@@ -152,6 +152,24 @@ class FlowNetSPyramid:
             res.append((nm, float(ms[i]), float(macs[i])))
         return res
 
+    def time_kernels(self, which, batch, frames=None, iters=20):
+        """Device time per repetition of a kernel set replayed from one CUDA graph (see ofs_net_time_kernels):
+        which = "dense" -> (ms, macs, launches) of the 14 conv / deconv GEMM launches; "warp" -> fused warp."""
+        ms = C.c_float(0)
+        macs = C.c_double(0)
+        nl = C.c_int(0)
+        H = W = 0
+        out = None
+        if which == "warp":
+            frames = _cuda_f32(frames, "frames")
+            _, H, W, _ = frames.shape
+            out = torch.empty_like(frames)
+        dev = torch.device("cuda", self.device) if not isinstance(self.device, torch.device) else self.device
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.ofs_net_time_kernels(self._h, 0 if which == "dense" else 1, _lib.ptr(frames), _lib.ptr(out),
+                                                      int(batch), H, W, int(iters), C.byref(ms), C.byref(macs), C.byref(nl)))
+        return float(ms.value), float(macs.value), int(nl.value)
+
     @property
     def launches_per_forward(self):
         return int(self._lib.ofs_net_launches_per_forward(self._h))

@@ -146,6 +146,14 @@ int ofs_net_get_activation(ofs_net* net, const char* name, int B, float* out, in
  * the layer, 0 for non-GEMM kernels), names[cap*32] (NUL-terminated, 32 bytes each).  Synchronous. */
 int ofs_net_profile(ofs_net* net, const float* feats, const float* frames, float* out, int B, int H, int W, int iters,
                     float* ms, double* macs, char* names, int cap, int* count, ofs_stream stream);
+/* Measurement aid (bench.py roofline): `iters` back-to-back repetitions of one kernel set are captured into
+ * one CUDA graph and replayed between two CUDA events on the net's stream -- the kernels' device time as the
+ * step executes them, without per-launch event or host overhead.  which = 0: the 14 dense conv / transposed
+ * conv GEMM launches of a forward (plus their split-K reductions) on the activations left by the last forward,
+ * macs_per_set = their literal multiply-accumulates; which = 1: the fused flow-resize + warp of
+ * frames [B,H,W,3] dev -> out dev on the last forward's flow.  Synchronous. */
+int ofs_net_time_kernels(ofs_net* net, int which, const float* frames, float* out, int B, int H, int W, int iters,
+                         float* ms_per_set, double* macs_per_set, int* launches_per_set);
 /* per-forward kernel launches (constant for a given B) */
 int ofs_net_launches_per_forward(const ofs_net* net);
 

@@ -5,7 +5,7 @@ timeout 900 python -m pytest tests/test_gpu_samplers.py -m gpu -q --timeout 300 
 timeout 900 python -m pytest tests/test_gpu_net.py -m gpu -q --timeout 300 --tb=short -k "conv_gemm" 2>&1 | tail -40 > gpurun_out/t_conv.log
 timeout 900 python -m pytest tests/test_gpu_net.py -m gpu -q --timeout 600 --tb=short -s -k "not conv_gemm" 2>&1 | tail -60 > gpurun_out/t_net.log
 timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
-timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.log 2>&1
+timeout 900 python bench.py --steps 200 --warmup 5 > gpurun_out/bench.log 2>&1
 for f in t_samplers.log t_conv.log t_net.log smoke.log; do echo "=== $f"; tail -30 gpurun_out/$f; done
 echo "=== bench"; python - <<'PY'
 import json
@@ -20,10 +20,10 @@ except Exception as e:
     print("bench parse failed", e); print(open("gpurun_out/bench.log").read()[-3000:])
 PY
 if [ "$1" == "ncu" ]; then
-  CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline"
+  CMD="env OFS_GRAPH=0 python bench.py --steps 2 --warmup 1 --no-cpu-baseline"
   $CMD > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
-  $CMD > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:conv_gemm -s 30 -c 15 -o gpurun_out/prof_conv -f $CMD > gpurun_out/ncu_conv.log 2>&1
-  $CMD > gpurun_out/plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"warp_staged|head3x3|pack_act|predict2_gather" -s 8 -c 8 -o gpurun_out/prof_misc -f $CMD > gpurun_out/ncu_misc.log 2>&1
+  $CMD > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:conv_gemm -s 30 -c 16 -o gpurun_out/prof_conv -f $CMD > gpurun_out/ncu_conv.log 2>&1
+  $CMD > gpurun_out/plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"warp5|pack_act|predict2_gather|pyr_kernel|splitk" -s 12 -c 12 -o gpurun_out/prof_misc -f $CMD > gpurun_out/ncu_misc.log 2>&1
   tail -3 gpurun_out/ncu_launches.log gpurun_out/ncu_conv.log gpurun_out/ncu_misc.log
   ls -la gpurun_out
 fi
