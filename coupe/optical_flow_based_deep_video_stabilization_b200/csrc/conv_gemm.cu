@@ -841,8 +841,9 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
   OFS_REQUIRE(d.B >= 1 && d.H >= 1 && d.W >= 1 && d.cin >= 1 && d.cout >= 1, "conv plan: bad shape");
   OFS_REQUIRE(d.in_cs % 8 == 0 && d.in_cs >= d.cin, "conv plan: input channel stride %d must be a multiple of 8 and >= cin %d",
               d.in_cs, d.cin);
-  OFS_REQUIRE(d.block_n == 16 || d.block_n == 32 || d.block_n == 64 || d.block_n == 128 || d.block_n == 256,
+  OFS_REQUIRE(d.block_n == 16 || d.block_n == 32 || d.block_n == 64 || d.block_n == 128 || d.block_n == 192 || d.block_n == 256,
               "conv plan: block_n %d unsupported", d.block_n);
+  OFS_REQUIRE(d.block_n != 192 || (d.cta_group == 1 && !d.slab && !d.head), "block_n 192 runs on 1-CTA plain tiles only");
   OFS_REQUIRE(d.cta_group == 1 || (d.cta_group == 2 && d.block_n >= 32),
               "conv plan: cta_group must be 1, or 2 with block_n >= 32 (got %d / %d)", d.cta_group, d.block_n);
   const bool deconv = d.kind == kDeconvK4S2;
@@ -1007,7 +1008,10 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
   p.out_mode = d.out_mode; p.lrelu = d.lrelu; p.is_bf16 = d.is_bf16; p.debug = d.debug; p.trace = d.trace;
   p.out_cstride = d.out_cstride; p.out_coff = d.out_coff;
   if (d.out_mode == 0) {
-    OFS_REQUIRE(p.n_pad == d.cout, "16-bit output mode needs cout %% block_n == 0 (cout %d, block_n %d)", d.cout, d.block_n);
+    // a padded last N tile is fine when the epilogue goes through TMA stores (columns >= cout are clipped by the
+    // tensor map) and the 64-column store chunks do not straddle cout; direct stores need an exact fit
+    OFS_REQUIRE(p.n_pad == d.cout || (d.block_n >= 64 && d.cout % 64 == 0 && d.ksplit <= 1 && !deconv),
+                "16-bit output mode needs cout %% block_n == 0 (cout %d, block_n %d)", d.cout, d.block_n);
     OFS_REQUIRE(d.out_cstride % 8 == 0 && d.out_coff % 8 == 0, "16-bit output slice must be 16-byte aligned");
   }
   if (d.head) {
@@ -1051,6 +1055,7 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
       case 32: plan.smem = GemmCfg<32, false>::kSmem; break;
       case 64: plan.smem = GemmCfg<64, false>::kSmem; break;
       case 128: plan.smem = GemmCfg<128, false>::kSmem; break;
+      case 192: plan.smem = GemmCfg<192, false>::kSmem; break;
       default: plan.smem = GemmCfg<256, false>::kSmem; break;
     }
   }
@@ -1188,6 +1193,7 @@ int conv_launch(const ConvPlan& plan, cudaStream_t st) {
       case 32: rc = launch_t<32>(plan, st); break;
       case 64: rc = launch_t<64>(plan, st); break;
       case 128: rc = launch_t<128>(plan, st); break;
+      case 192: rc = launch_t<192>(plan, st); break;
       case 256: rc = launch_t<256>(plan, st); break;
       default: set_error("conv_launch: unsupported block_n %d", plan.block_n); return OFS_EINVAL;
     }
@@ -1339,7 +1345,7 @@ extern "C" int ofs_conv2d_bench(int B, int H, int W, int Cin, int in_cs, int Cou
   d.kind = transposed ? kDeconvK4S2 : kConv;
   d.B = B; d.H = H; d.W = W; d.cin = Cin; d.in_cs = in_cs; d.cout = Cout; d.k = k; d.stride = stride;
   d.block_n = block_n; d.ksplit = ksplit > 1 ? ksplit : 1; d.cta_group = (cta_group == 2 || cta_group == 4) ? 2 : 1; d.slab = cta_group == 4 ? 1 : 0; d.debug = debug;
-  const bool out16 = (Cout % block_n) == 0;
+  const bool out16 = (Cout % block_n) == 0 || (!transposed && block_n >= 64 && Cout % 64 == 0 && ksplit <= 1);
   d.out_mode = out16 ? 0 : 1; d.lrelu = 1; d.is_bf16 = 1; d.out_cstride = out_cs; d.out_coff = 0;
   ConvPlan plan;
   rc = conv_plan_geometry(plan, d);
