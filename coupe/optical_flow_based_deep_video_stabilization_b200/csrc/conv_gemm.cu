@@ -100,7 +100,7 @@ struct GemmCfg {
   static constexpr int kTmemCols = 2 * kNB <= 32 ? 32 : 2 * kNB <= 64 ? 64 : 2 * kNB <= 128 ? 128 : 2 * kNB <= 256 ? 256 : 512;
   static constexpr int kBarBytes = 256;
   static constexpr int kStgBytes = kBlockM * 128;        // one 64-channel chunk of the 16-bit output tile (SW128 rows)
-  static constexpr int kStgTotal = BLOCK_N >= 64 ? 2 * kStgBytes : 0;   // double buffered; narrow tiles store directly
+  static constexpr int kStgTotal = BLOCK_N >= 64 ? 2 * kStgBytes : kBlockM * 32 * 4;   // double buffered chunk / fp32 tile of a narrow layer
   static constexpr int kBudget = 227 * 1024 - 1024 - kBarBytes - kStgTotal;   // 227 KB per CTA on sm_100
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr size_t kSmem = (size_t)kStages * kStageBytes + kStgTotal + kBarBytes + 1024;  // + alignment slack
@@ -492,6 +492,42 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
               trace[16] += tq1 - tq0; trace[17] += tq2 - tq1; trace[18] += tq3 - tq2; trace[19] += tq4 - tq3;
               trace[20] += tq5 - tq4; trace[21] += 1;
             }
+          }
+        }
+      }
+      if constexpr (BLOCK_N <= 32) {
+        // narrow fp32 layer (predict2 product, 18 columns) whose tile is a run of consecutive output pixels: the
+        // [128][n_valid] block is contiguous in memory -> transpose through shared memory, 128-bit coalesced stores
+        if (p.out_mode == 1 && p.out_scale == 1 && tileW == p.Wg && p.out_coff == 0 && p.out_cstride == p.n_valid &&
+            p.tiles_n == 1 && (p.n_valid & 3) == 2) {
+          stored = true;
+          uint32_t v[BLOCK_N];
+          if constexpr (BLOCK_N == 32) ptx::tmem_ld32(t_addr, v); else ptx::tmem_ld16(t_addr, v);
+          ptx::tmem_wait_ld();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kPair) ptx::mbar_arrive_cluster(tempty_tgt0 + 8 * acc);
+            else ptx::mbar_arrive(&tempty[acc]);
+          }
+          float* sf = reinterpret_cast<float*>(smem + (size_t)S * Cfg::kStageBytes);
+          const int nv = p.n_valid;
+          ptx::named_bar_sync(1, 128);               // the previous tile's copy-out has finished reading the buffer
+#pragma unroll
+          for (int j = 0; j < BLOCK_N; ++j)
+            if (j < nv) {
+              float a = __uint_as_float(v[j]) + __ldg(p.bias + j);
+              if (p.lrelu) a = fmaxf(a, 0.1f * a);
+              sf[row * nv + j] = a;
+            }
+          ptx::named_bar_sync(1, 128);
+          const int gy0 = (m_t / p.tiles_x) * p.tile_rows;
+          const int rows_valid = min(p.tile_rows, p.rows_total - gy0);
+          if (m_t < p.tiles_m && rows_valid > 0 && !(p.debug & 8)) {
+            const int nflt = rows_valid * tileW * nv;            // multiple of 2 (nv even); tile base is 8-byte aligned
+            float2* dst = reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + (size_t)gy0 * p.Wg * nv);
+            const float2* src = reinterpret_cast<const float2*>(sf);
+            for (int i = (int)threadIdx.x - 64; i < (nflt >> 1); i += 128) dst[i] = src[i];
           }
         }
       }

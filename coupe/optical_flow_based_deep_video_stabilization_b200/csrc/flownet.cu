@@ -131,40 +131,67 @@ struct Predict2Params {
   float bias0, bias1;
   float sy, sx;       // NN align_corners scales (98-1)/(384-1), (130-1)/(512-1) in fp32
   float hs, ws;       // bilinear scales 48/382, 64/510 in fp32
+  const short* iy_tab; // [384] NN source row of padded-grid row r, minus 1 (row of the unpadded 96-row grid, -1 / 96 = padding)
+  const short* ix_tab; // [512] same for columns (128-column grid)
   int B;
 };
 
-// model.py:882-887: zero-pad(1) -> nearest(align_corners) to 384x512 -> 3x3 VALID -> + 8 x up(f3)
-__global__ void predict2_gather_kernel(Predict2Params p) {
+// model.py:882-887: zero-pad(1) -> nearest(align_corners) to 384x512 -> 3x3 VALID -> + 8 x up(f3).
+// One block per 64 x 8 output tile (3-D grid), a thread owns columns lane, lane+32 of one row: the NN source
+// indices come from two small tables (built once on the host with the same fp32 round(dst * (in-1)/(out-1))),
+// the row terms are shared by both pixels, all indexing is 32-bit.
+__global__ void __launch_bounds__(256) predict2_gather_kernel(Predict2Params p) {
   pdl_wait();
   pdl_launch_dependents();
-  const size_t total = (size_t)p.B * 382 * 510;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int ox = (int)(idx % 510);
-    const size_t r = idx / 510;
-    const int oy = (int)(r % 382);
-    const int b = (int)(r / 382);
-    float a0 = p.bias0, a1 = p.bias1;
-    const float* Pb = p.P + (size_t)b * 96 * 128 * 18;
-    int ixs[3];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b = blockIdx.z;
+  const int oy = blockIdx.y * 8 + wid;
+  if (oy >= 382) return;
+  const int ox0 = blockIdx.x * 64 + lane;
+  const float* __restrict__ Pb = p.P + (size_t)b * 96 * 128 * 18;
+  int rowoff[3];   // (iy * 128) * 18 + ky * 6, or -1 when the tap reads the zero padding
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) ixs[kx] = min((int)roundf((float)(ox + kx) * p.sx), 129) - 1;
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = (int)p.iy_tab[oy + ky];
+    rowoff[ky] = (iy < 0 || iy >= 96) ? -1 : iy * (128 * 18) + ky * 6;
+  }
+  // TF1 bilinear of f3 (48x64 -> 382x510): row terms
+  const float fy = (float)oy * p.hs;
+  const int y0 = (int)floorf(fy), y1 = min(y0 + 1, 47);
+  const float yl = fy - (float)y0;
+  const float2* __restrict__ f3b = p.f3 + (size_t)b * 48 * 64;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int ox = ox0 + 32 * h;
+    if (ox >= 510) continue;
+    float a0 = p.bias0, a1 = p.bias1;
+    int ix[3];
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int v = (int)p.ix_tab[ox + kx];
+      ix[kx] = (v < 0 || v >= 128) ? -1 : v * 18 + kx * 2;
+    }
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-      const int iy = min((int)roundf((float)(oy + ky) * p.sy), 97) - 1;  // row of the unpadded 96x128 grid
-      if (iy < 0 || iy >= 96) continue;
+      if (rowoff[ky] < 0) continue;
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const int ix = ixs[kx];
-        if (ix < 0 || ix >= 128) continue;
-        const float2 v = __ldg(reinterpret_cast<const float2*>(Pb + ((size_t)iy * 128 + ix) * 18 + (ky * 3 + kx) * 2));
+        if (ix[kx] < 0) continue;
+        const float2 v = __ldg(reinterpret_cast<const float2*>(Pb + rowoff[ky] + ix[kx]));
         a0 += v.x;
         a1 += v.y;
       }
     }
-    const float2 u = tf1_bilinear2(p.f3 + (size_t)b * 48 * 64, 48, 64, p.hs, p.ws, oy, ox);
+    const float fx = (float)ox * p.ws;
+    const int x0 = (int)floorf(fx), x1 = min(x0 + 1, 63);
+    const float xl = fx - (float)x0;
+    const float2 tl = f3b[y0 * 64 + x0], tr = f3b[y0 * 64 + x1], bl = f3b[y1 * 64 + x0], br = f3b[y1 * 64 + x1];
+    const float topx = tl.x + (tr.x - tl.x) * xl, topy = tl.y + (tr.y - tl.y) * xl;
+    const float botx = bl.x + (br.x - bl.x) * xl, boty = bl.y + (br.y - bl.y) * xl;
+    const float ux = topx + (botx - topx) * yl, uy = topy + (boty - topy) * yl;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { a0 += u.x; a1 += u.y; }  // ElementwiseLayer left fold, model.py:887
+    for (int i = 0; i < 8; ++i) { a0 += ux; a1 += uy; }  // ElementwiseLayer left fold, model.py:887
+    const int idx = (b * 382 + oy) * 510 + ox;
     p.f2[idx] = make_float2(a0, a1);
     p.f2s[idx] = make_float2(__fdiv_rn(a0 * 384.0f, 382.0f), __fdiv_rn(a1 * 384.0f, 382.0f));
   }
@@ -217,6 +244,7 @@ struct ofs_net {
   float* P2 = nullptr;
   float* f2s = nullptr;  // pre-scaled flow2 for the fused flow-resize + warp
   float* upw = nullptr;  // 4 x (64 + 2) floats: upsample6_5, 5_4, 4_3, 3_2
+  short* nn_tab = nullptr;  // predict2: NN align_corners source index tables, 384 rows then 512 columns (value - 1)
   float p2_bias[2] = {0, 0};
   std::vector<Layer> layers;
   std::vector<Head> heads;   // predict6, predict5, predict4, predict3
@@ -449,9 +477,8 @@ int forward_impl(ofs_net* n, const float* feats, int B, float* f2_target, cudaSt
   pp.sy = 97.0f / 383.0f; pp.sx = 129.0f / 511.0f;
   pp.hs = 48.0f / 382.0f; pp.ws = 64.0f / 510.0f;
   pp.B = B;
-  const size_t total = (size_t)B * 382 * 510;
-  const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
-  OFS_CUDA(launch_pdl(predict2_gather_kernel, dim3(blocks), dim3(256), 0, st, pp));
+  pp.iy_tab = n->nn_tab; pp.ix_tab = n->nn_tab + 384;
+  OFS_CUDA(launch_pdl(predict2_gather_kernel, dim3((510 + 63) / 64, (382 + 7) / 8, (unsigned)B), dim3(256), 0, st, pp));
   OFS_LAUNCH_CHECK();
   OFS_MARK("predict2_gather", 0.0);
   return OFS_OK;
@@ -491,6 +518,16 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
   rc = dev_alloc(n, (void**)&n->P2, B * 96 * 128 * 18 * 4, true);
   if (rc == OFS_OK) rc = dev_alloc(n, (void**)&n->f2s, B * 382 * 510 * 2 * 4, true);
   if (rc == OFS_OK) rc = dev_alloc(n, (void**)&n->upw, 4 * 66 * 4, true);
+  if (rc == OFS_OK) rc = dev_alloc(n, (void**)&n->nn_tab, (384 + 512) * 2, true);
+  if (rc == OFS_OK) {
+    // model.py:795-802,883: resize_nearest_neighbor(align_corners=True): src = min(round(dst * (in-1)/(out-1)), in-1),
+    // evaluated in fp32 exactly as the kernel used to do per tap
+    std::vector<short> tab(384 + 512);
+    const float sy = 97.0f / 383.0f, sx = 129.0f / 511.0f;
+    for (int r = 0; r < 384; ++r) { const float v = (float)r * sy; tab[r] = (short)(std::min((int)roundf(v), 97) - 1); }
+    for (int c = 0; c < 512; ++c) { const float v = (float)c * sx; tab[384 + c] = (short)(std::min((int)roundf(v), 129) - 1); }
+    rc = check_cuda(cudaMemcpy(n->nn_tab, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice), "nn_tab upload", __FILE__, __LINE__);
+  }
   if (rc == OFS_OK) rc = dev_alloc(n, (void**)&n->st_feats, B * kNetH * kNetW * kNetC * 4, false);
   if (rc != OFS_OK) { ofs_net_destroy(n); return rc; }
   bool ok = cudaStreamCreateWithFlags(&n->stream, cudaStreamNonBlocking) == cudaSuccess &&
