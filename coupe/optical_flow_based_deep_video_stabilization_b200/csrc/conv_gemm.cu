@@ -749,6 +749,7 @@ int launch_t(const ConvPlan& plan, cudaStream_t st) {
                                   (int)GemmCfg<BLOCK_N, false>::kSmem));
     attr_set[dev] = true;
   }
+  pdl_set_kind(1);
   OFS_CUDA(launch_pdl(conv_gemm_kernel<BLOCK_N>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, false>::kSmem, st, plan.p));
   OFS_LAUNCH_CHECK();
   return OFS_OK;
@@ -764,6 +765,7 @@ int launch_t2(const ConvPlan& plan, cudaStream_t st) {
                                   (int)GemmCfg<BLOCK_N, true>::kSmem));
     attr_set[dev] = true;
   }
+  pdl_set_kind(1);
   OFS_CUDA(launch_pdl(conv_gemm2_kernel<BLOCK_N>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, true>::kSmem, st, plan.p));
   OFS_LAUNCH_CHECK();
   return OFS_OK;
@@ -779,6 +781,7 @@ int launch_th(const ConvPlan& plan, cudaStream_t st) {
                                   (int)GemmCfg<BLOCK_N, false, 1, 16>::kSmem));
     attr_set[dev] = true;
   }
+  pdl_set_kind(1);
   OFS_CUDA(launch_pdl(conv_gemmh_kernel<BLOCK_N>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, false, 1, 16>::kSmem, st, plan.p));
   OFS_LAUNCH_CHECK();
   return OFS_OK;
@@ -794,6 +797,7 @@ int launch_t2s(const ConvPlan& plan, cudaStream_t st) {
                                   (int)GemmCfg<BLOCK_N, true, kT>::kSmem));
     attr_set[dev] = true;
   }
+  pdl_set_kind(1);
   OFS_CUDA(launch_pdl(conv_gemm2s_kernel<BLOCK_N, kT>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, true, kT>::kSmem, st, plan.p));
   OFS_LAUNCH_CHECK();
   return OFS_OK;
@@ -804,6 +808,7 @@ int launch_reduce(const ConvPlan& plan, cudaStream_t st) {
   const size_t npix = (size_t)plan.d.B * p.out_H * p.out_W;
   const size_t total = npix * (p.n_pad / 8);
   const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
+  pdl_set_kind(2);
   OFS_CUDA(launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, st, (const float*)plan.ws, p.ksplit,
                       p.ws_split_stride, npix, p.n_pad, plan.bias_dev, reinterpret_cast<uint16_t*>(plan.final_out),
                       plan.d.out_cstride, plan.d.out_coff, plan.d.lrelu, plan.d.is_bf16));

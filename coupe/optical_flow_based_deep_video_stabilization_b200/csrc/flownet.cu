@@ -407,6 +407,7 @@ int launch_pyr(ofs_net* n, int level, int B, cudaStream_t st) {
   }
   const size_t total = (size_t)B * 4 * p.h * p.w;
   const int blocks = (int)std::min<size_t>((total + 127) / 128, (size_t)sm_count() * 8);
+  pdl_set_kind(2);
   OFS_CUDA(launch_pdl(pyr_kernel, dim3(blocks), dim3(128), 0, st, p));
   OFS_LAUNCH_CHECK();
   return OFS_OK;
@@ -813,7 +814,8 @@ int ofs_net_stabilize_host(ofs_net* n, const float* feats_host, const float* fra
   // The call is PCIe-bound (21 MB of feats + 11 MB of frame in, 11 MB out per 720p pair), so it is
   // software-pipelined over sub-batches: H2D of chunk k+1, compute of chunk k and D2H of chunk k-1 run on
   // three streams.  Sub-batching does not change results (fixed split-K factors: batch-invariant).
-  const int chunk = B >= 4 ? 2 : 1;
+  int chunk = B >= 4 ? 2 : 1;
+  if (const char* e = getenv("OFS_HOST_CHUNK")) chunk = std::max(1, std::min(B, atoi(e)));   // experiments only
   const int nchunks = (B + chunk - 1) / chunk;
   for (int c = 0; c < nchunks; ++c) {
     const int b0 = c * chunk, nb = std::min(chunk, B - b0);

@@ -15,13 +15,28 @@ const char* get_error() { return g_err; }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)(int64_t)n, std::memory_order_relaxed); }
 uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
-bool pdl_enabled() {
+static int pdl_mode() {
   static int cached = -1;
   if (cached < 0) {
     const char* e = getenv("OFS_PDL");
-    cached = (e && e[0] == '1') ? 1 : 0;   // default off: inside the step graph PDL edges measured slower (profiles/r01_tuning.md)
+    cached = e ? atoi(e) : 0;   // default off: with the step graph, PDL on every kernel measured 1.5 % slower
+    if (cached < 0 || cached > 2) cached = 0;
   }
-  return cached == 1;
+  return cached;
+}
+bool pdl_enabled() { return pdl_mode() != 0; }
+static thread_local int g_pdl_kind = 0, g_pdl_prev = 0;
+void pdl_set_kind(int kind) { g_pdl_kind = kind; }
+bool pdl_allow() {
+  const int kind = g_pdl_kind, prev = g_pdl_prev;
+  g_pdl_prev = kind;
+  g_pdl_kind = 0;
+  const int mode = pdl_mode();
+  if (mode == 1) return true;
+  // selective: only GEMM / helper kernels following GEMM / helper kernels start early (a 225 KB-smem GEMM CTA that
+  // lands beside a streaming kernel's blocks shrinks their L1)
+  if (mode == 2) return kind != 0 && prev != 0;
+  return false;
 }
 
 int sm_count() {

@@ -34,6 +34,10 @@ int require_sm100(int device);
 // while the previous kernel of the stream drains.  The attribute is OFF unless OFS_PDL=1 is set: measured
 // (B200, batch 8): stream launches 846 -> 820 us/step with PDL, one CUDA graph per step 786 us, graph + PDL 803 us.
 bool pdl_enabled();
+// kernel classes for the selective mode (OFS_PDL=2): 0 = streaming / large-grid kernel, 1 = persistent tcgen05 GEMM,
+// 2 = small helper (split-K reduce, pyramid step).  pdl_allow() is called once per launch, in launch order.
+void pdl_set_kind(int kind);
+bool pdl_allow();
 
 #ifdef __CUDACC__
 // blocks until every prerequisite grid has completed and its memory operations are visible (no-op when the
@@ -52,7 +56,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_allow() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);

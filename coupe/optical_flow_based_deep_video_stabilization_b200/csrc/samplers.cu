@@ -649,6 +649,54 @@ __global__ void __launch_bounds__(256, 6) warp5_kernel(const float* __restrict__
   }
 }
 
+// generic 4-tap sampler (grid_sample / Lie warp), lean form of sample3_kernel: one block per 64 x 16 output tile
+// (3-D grid), 32-bit image offsets, predicated loads instead of per-tap branches, 6 resident blocks per SM
+template <class Provider>
+__global__ void __launch_bounds__(256, 6) sample5_kernel(Provider prov, const float* __restrict__ img,
+                                                         float* __restrict__ out, int B, int srcH, int srcW, int oH,
+                                                         int oW) {
+  __shared__ __align__(16) float obuf[8][192];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b = blockIdx.z;
+  const int ox0 = blockIdx.x * kTileW, oy0 = blockIdx.y * kTileH + wid * 2;
+  const float* __restrict__ imgb = img + (size_t)b * srcH * srcW * 3;
+  const int valid_px = min(kTileW, oW - ox0);
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int oy = oy0 + rr;
+    if (oy >= oH) break;  // warp-uniform
+    float v[2][3];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int ox = ox0 + lane + 32 * h;
+      v[h][0] = v[h][1] = v[h][2] = 0.0f;
+      if (ox < oW) {
+        const Taps tp = prov.taps(b, oy, ox);
+        float px[4][3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool in = tp.x[k] >= 0;
+          const float* p = imgb + (tp.y[k] * srcW + (in ? tp.x[k] : 0)) * 3;
+          px[k][0] = in ? __ldg(p) : 0.0f;
+          px[k][1] = in ? __ldg(p + 1) : 0.0f;
+          px[k][2] = in ? __ldg(p + 2) : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {   // rounded products summed in tap order; an outside tap adds exactly +0
+          if (tp.x[k] >= 0) {
+            v[h][0] = mul_add_rn(v[h][0], tp.w[k], px[k][0]);
+            v[h][1] = mul_add_rn(v[h][1], tp.w[k], px[k][1]);
+            v[h][2] = mul_add_rn(v[h][2], tp.w[k], px[k][2]);
+          }
+        }
+      }
+    }
+    store_row3(obuf[wid], out + (((size_t)b * oH + oy) * oW + ox0) * 3, lane, valid_px, v[0], v[1]);
+  }
+}
+
 __global__ void flow_resize_kernel(FlowResize fr, float* __restrict__ out, int B) {
   const size_t total = (size_t)B * fr.H * fr.W;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -658,6 +706,12 @@ __global__ void flow_resize_kernel(FlowResize fr, float* __restrict__ out, int B
     const int b = (int)(r / fr.H);
     reinterpret_cast<float2*>(out)[i] = fr.at(b, oy, ox);
   }
+}
+
+// outputs['predict_flow2'] * 384.0 / 382 (main_dl.py:497): multiply, then true division
+__global__ void prescale_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n, float fhf) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __fdiv_rn(__ldg(in + i) * 384.0f, fhf);
 }
 
 // warp.py:25-43, one thread per batch element
@@ -725,8 +779,12 @@ int launch_sampler(Provider prov, const float* img, float* out, int B, int srcH,
                    cudaStream_t st) {
   if (B == 0 || oH == 0 || oW == 0) return OFS_OK;
   if (C == 3 && (oW % 4) == 0 && (((uintptr_t)out) % 16 == 0)) {
-    const size_t nt = tile_count(B, oH, oW);
-    sample3_kernel<Provider><<<tile_grid(nt, 8), 256, 0, st>>>(prov, img, out, B, srcH, srcW, oH, oW);
+    if ((size_t)srcH * srcW * 3 < (1u << 31) && B <= 65535 && (oH + kTileH - 1) / kTileH <= 65535) {
+      sample5_kernel<Provider><<<tile_grid3(B, oH, oW), 256, 0, st>>>(prov, img, out, B, srcH, srcW, oH, oW);
+    } else {
+      const size_t nt = tile_count(B, oH, oW);
+      sample3_kernel<Provider><<<tile_grid(nt, 8), 256, 0, st>>>(prov, img, out, B, srcH, srcW, oH, oW);
+    }
   } else {
     const size_t px = (size_t)B * oH * oW;
     sample_px_kernel<Provider><<<grid_for(px, 256), 256, 0, st>>>(prov, img, out, B, srcH, srcW, oH, oW, C);
@@ -796,6 +854,34 @@ int flow_resize_warp_impl(const float* img, const float* flow2, float* out, int 
   OFS_REQUIRE(B >= 0 && fh > 0 && fw > 0 && H > 0 && W > 0, "ofs_flow_resize_warp: bad shape");
   if (B == 0) return OFS_OK;
   OFS_REQUIRE(img && flow2 && out, "ofs_flow_resize_warp: null pointer");
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  if (!prescaled && g_warp_variant == 3 && cap == cudaStreamCaptureStatusNone && (W % 4) == 0 && (((uintptr_t)out) % 16 == 0)) {
+    // stand-alone op: (flow2 * 384) / fh once per flow texel into a stream-ordered scratch buffer (the network writes
+    // that copy itself), then the lean fused kernel
+    float* scratch = nullptr;
+    const size_t nflt = (size_t)B * fh * fw * 2;
+    {   // keep freed blocks in the device's default pool (the default threshold of 0 returns them to the OS at every
+        // synchronisation, which made this call 7x slower than the kernel it feeds)
+      static bool pool_set[64] = {false};
+      int dev = 0;
+      OFS_CUDA(cudaGetDevice(&dev));
+      if (dev >= 0 && dev < 64 && !pool_set[dev]) {
+        cudaMemPool_t pool;
+        OFS_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        unsigned long long thr = ~0ull;
+        OFS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        pool_set[dev] = true;
+      }
+    }
+    OFS_CUDA(cudaMallocAsync((void**)&scratch, nflt * 4, st));
+    prescale_kernel<<<grid_for(nflt, 256), 256, 0, st>>>(flow2, scratch, nflt, (float)fh);
+    OFS_LAUNCH_CHECK();
+    ResizeWarpProvider pv{FlowResize{scratch, fh, fw, H, W, (float)fh / (float)H, (float)fw / (float)W, 1}};
+    const int rc = launch_warp3(pv, img, out, B, H, W, st);
+    OFS_CUDA(cudaFreeAsync(scratch, st));
+    return rc;
+  }
   ResizeWarpProvider prov{FlowResize{flow2, fh, fw, H, W, (float)fh / (float)H, (float)fw / (float)W, prescaled}};
   if ((W % 4) == 0 && (((uintptr_t)out) % 16 == 0)) return launch_warp3(prov, img, out, B, H, W, st);
   const size_t px = (size_t)B * H * W;

@@ -259,3 +259,43 @@ def test_missing_weight_is_an_error(ofs, cuda_dev):
     w = {f"main_net/flownetS/{k}:0": v for k, v in F.make_weights(0, "he").items()}
     net.assign_weights(w)
     net.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W", [(8, 720, 1280), (16, 1080, 1920)], ids=["configs1_b8_720p", "configs2_b16_1080p"])
+def test_full_size_step_properties(ofs, cuda_dev, B, H, W):
+    """BASELINE configs[1] / configs[2] at full size, through size-independent properties (the oracle needs ~0.1 s per
+    pair, so only pair 0 is compared with it): batch invariance (pair i alone == pair i inside the batch, bit for bit,
+    although the batch rides a different CUDA graph and different split-K / tile schedules per launch), replay
+    determinism, host-buffer call == device call, warp linearity in the image, and the oracle on one pair."""
+    from oracle import samplers as S
+
+    w = F.make_weights(0, "calibrated", head_scale=0.02)
+    net = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=B)
+    net.assign_weights(w)
+    feats = F.make_feats(11, B)
+    gen = torch.Generator().manual_seed(12)
+    frames = torch.rand((B, H, W, 3), generator=gen)
+    fd, gd = feats.to(cuda_dev), frames.to(cuda_dev)
+    out, f2 = net.stabilize(fd, gd, return_flow=True)
+    out2, _ = net.stabilize(fd, gd, return_flow=True)                              # graph replay
+    assert torch.equal(out, out2)
+    for i in (0, B // 2, B - 1):
+        oi, fi = net.stabilize(fd[i:i + 1].contiguous(), gd[i:i + 1].contiguous(), return_flow=True)
+        assert torch.equal(fi[0], f2[i]) and torch.equal(oi[0], out[i])
+    host = net.stabilize_host(feats.pin_memory(), frames.pin_memory())
+    assert torch.equal(host, out.cpu())
+    # linearity of the warp in the image for a fixed flow
+    g2 = torch.rand((B, H, W, 3), generator=gen).to(cuda_dev)
+    a = ofs.flow_resize_warp(gd[:2], f2[:2], H, W)
+    b = ofs.flow_resize_warp(g2[:2], f2[:2], H, W)
+    ab = ofs.flow_resize_warp(0.25 * gd[:2] + 0.75 * g2[:2], f2[:2], H, W)
+    assert float((ab - (0.25 * a + 0.75 * b)).abs().max()) < 1e-5
+    assert float((a - out[:2]).abs().max()) < 1e-5                                   # stand-alone fused op == network path
+    # oracle on pair 0
+    ref = F.forward_literal(feats[:1], w)
+    e = F.epe(f2[:1].cpu(), ref["predict_flow2"])
+    assert e <= 2e-2, e                                                              # north-star tolerance, px at bf16
+    ref_img = S.flow_resize_warp(frames[:1], f2[:1].cpu(), H, W)
+    assert float(((out[:1].cpu() - ref_img).abs() > 1e-3).float().mean()) < 1e-4    # 1e-3 on [0,1] pixels
+    net.close()
