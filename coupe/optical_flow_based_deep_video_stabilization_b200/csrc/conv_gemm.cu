@@ -223,7 +223,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&p.tmap_a);
     ptx::prefetch_tensormap(&p.tmap_w);
-    if (p.tma_store) for (int i = 0; i < p.phases; ++i) ptx::prefetch_tensormap(&p.tmap_o[i]);
+    if (p.tma_store) for (int i = 0; i < (p.tma_store == 2 ? 1 : p.phases); ++i) ptx::prefetch_tensormap(&p.tmap_o[i]);
     for (int i = 0; i < S; ++i) {
       ptx::mbar_init(&full[i], 1);
       ptx::mbar_init(&empty[i], 1);
@@ -431,8 +431,10 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
           // by chunk c+2: thread 64 waits for its previous store to finish reading before the chunk barrier.
           stored = true;
           const uint32_t sw = (uint32_t)(row & 7);
+          // 128-byte staging rows: 64 16-bit channels, or 32 raw fp32 partial sums (split-K: tma_store == 2)
+          const int cw = p.tma_store == 2 ? 32 : 64;
 #pragma unroll 1
-          for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {
+          for (int c0 = 0; c0 < BLOCK_N; c0 += cw) {
             const uint32_t buf = stg0 + (stg_parity ? Cfg::kStgBytes : 0);
             const uint32_t rowaddr = buf + (uint32_t)row * 128u;
             long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0;
@@ -441,8 +443,13 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
             lean::wait(sempty0 + 8 * stg_parity, stg_phase ^ 1);   // the store of two chunks ago has read this buffer
             uint32_t v[64];
             ptx::tmem_ld32(t_addr + c0, v);          // both halves in flight before the single wait
-            ptx::tmem_ld32(t_addr + c0 + 32, v + 32);
+            if (cw == 64) ptx::tmem_ld32(t_addr + c0 + 32, v + 32);
             ptx::tmem_wait_ld();
+            if (cw == 32) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                ptx::st_shared_v4(rowaddr + ((((uint32_t)j) ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
             const float4* bias4 = reinterpret_cast<const float4*>(bias);   // 128-bit broadcast loads
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -461,8 +468,9 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
               }
               ptx::st_shared_v4(rowaddr + ((((uint32_t)j) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
             }
+            }
             if (trace && threadIdx.x == 64) tq1 = clock64();
-            if (c0 + 64 >= BLOCK_N) {   // every accumulator column of this tile has been read: release the TMEM stage
+            if (c0 + cw >= BLOCK_N) {   // every accumulator column of this tile has been read: release the TMEM stage
               if constexpr (kHead > 0) {
                 // fused flow head (model.py:847-874): columns BLOCK_N, BLOCK_N+1 of the last N tile hold this phase's
                 // share of the 3x3 head on the same input; pyr_kernel sums the 4 phase shares per pixel
@@ -568,14 +576,19 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
           const int ox0 = (m_t % p.tiles_x) << p.tileW_log2;
           const int b0 = gy0 / p.Hg, y0 = gy0 - b0 * p.Hg;
           const bool do_store = m_t < p.tiles_m && !(p.debug & 8);
+          const int ks = rest / (p.tiles_mp * p.phases);
+          const int cw = p.tma_store == 2 ? 32 : 64;
 #pragma unroll 1
-          for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {
+          for (int c0 = 0; c0 < BLOCK_N; c0 += cw) {
             lean::wait(sfull0 + 8 * par, phs);
             if (do_store) {
               int bb = b0, yy = y0;
               uint32_t src = stg0 + (par ? Cfg::kStgBytes : 0);
               for (int pc = 0; pc < p.npieces; ++pc) {
-                if (issuer) ptx::tma_store_4d(&p.tmap_o[ph], src, n_t * BLOCK_N + c0, ox0, yy, bb);
+                if (issuer) {
+                  if (cw == 32) ptx::tma_store_5d(&p.tmap_o[0], src, n_t * BLOCK_N + c0, ox0, yy, bb, ks);
+                  else ptx::tma_store_4d(&p.tmap_o[ph], src, n_t * BLOCK_N + c0, ox0, yy, bb);
+                }
                 src += piece_bytes;
                 yy += p.piece_rows;
                 if (yy >= p.Hg) { yy -= p.Hg; ++bb; }
@@ -719,6 +732,7 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// dtype: 1 bf16, 0 fp16, 2 fp32
 int encode_map(CUtensorMap* map, int is_bf16, int rank, const void* base, const cuuint64_t* dims,
                const cuuint64_t* strides_bytes, const cuuint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
@@ -727,7 +741,7 @@ int encode_map(CUtensorMap* map, int is_bf16, int rank, const void* base, const 
     return OFS_ECUDA;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
+  CUresult r = fn(map, is_bf16 == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
                   const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1072,7 +1086,9 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
     plan.ws_bytes = p.ksplit > 1 ? (size_t)p.ksplit * p.ws_split_stride * 4 : 0;
     if (p.ksplit > 1) p.out_mode = 2;
   }
-  p.tma_store = (p.out_mode == 0 && d.block_n >= 64) ? 1 : 0;
+  // 1: 16-bit activations; 2: raw fp32 split-K partials into the workspace (plain convs: the workspace pixel index
+  // is the output pixel index)
+  p.tma_store = (p.out_mode == 0 && d.block_n >= 64) ? 1 : (p.out_mode == 2 && d.block_n >= 64 && !deconv) ? 2 : 0;
   p.tiles_mp = d.cta_group == 2 ? (p.tiles_m + 1) / 2 : p.tiles_m;
   const int total_tiles = p.tiles_mp * p.tiles_n * p.phases * p.ksplit;
   if (d.head) {
@@ -1193,7 +1209,15 @@ int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const 
                        (cuuint32_t)p.box_b};
   int st = encode_map(&p.tmap_a, d.is_bf16, 5, act_in, dims, str, box);
   if (st != OFS_OK) return st;
-  if (p.tma_store) {
+  if (p.tma_store == 2) {
+    // workspace [ks][b][y][x][n_pad] fp32
+    const cuuint64_t np = (cuuint64_t)p.n_pad;
+    cuuint64_t od[5] = {np, (cuuint64_t)p.Wg, (cuuint64_t)p.Hg, (cuuint64_t)d.B, (cuuint64_t)p.ksplit};
+    cuuint64_t os[4] = {np * 4, (cuuint64_t)p.Wg * np * 4, (cuuint64_t)p.Hg * p.Wg * np * 4, (cuuint64_t)p.ws_split_stride * 4};
+    cuuint32_t ob[5] = {32, tileW, (cuuint32_t)p.box_y, (cuuint32_t)p.box_b, 1};
+    st = encode_map(&p.tmap_o[0], 2, 5, workspace, od, os, ob);
+    if (st != OFS_OK) return st;
+  } else if (p.tma_store) {
     const cuuint64_t cs = (cuuint64_t)d.out_cstride, sc = (cuuint64_t)p.out_scale;
     for (int ph = 0; ph < p.phases; ++ph) {
       const size_t off = ((size_t)p.out_oy[ph] * p.out_W + p.out_ox[ph]) * cs + (size_t)d.out_coff;

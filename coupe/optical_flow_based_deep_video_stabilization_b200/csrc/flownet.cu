@@ -569,7 +569,8 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
   for (Layer& L : Ls) {
     if ((L.name == "1" || L.name == "2") && !(getenv("OFS_NOSLAB") && getenv("OFS_NOSLAB")[0] == '1')) {
       L.d.slab = 1; L.d.cta_group = 2;   // x-shifted taps share one A slab per stage (CTA pairs); fixes the packed K order
-    } else if (L.name == "3" || L.name == "3_1") { L.block_n_run = 256; }
+    } else if (L.name == "3") { L.block_n_run = 256; L.cta_group = 2; }   // CTA pairs: 36.9 vs 40.3 us (conv_bench)
+    else if (L.name == "3_1") { L.block_n_run = 256; }
     // cout 512 on 48 M tiles: 3 N tiles of 192 (the last one a third empty, clipped by the TMA store) = 144 tiles, ONE
     // wave on 148 SMs, instead of 2 x 256 = 96 tiles on 65 % of the SMs (-25 % time, conv_bench A/B)
     else if (L.name == "4" || L.name == "4_1") { L.d.block_n = 192; }
