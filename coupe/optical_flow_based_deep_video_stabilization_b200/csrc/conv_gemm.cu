@@ -91,12 +91,13 @@ __device__ __forceinline__ void epilogue_store(const ConvGemmParams& p, const ui
 // M=256 MMA reading both CTAs' shared memory; D rows 0-127 land in the leader's TMEM, rows 128-255 in the peer's.
 // kT = K blocks (taps of one slab group) per pipeline stage: 1, or 3 / 4 in slab mode.
 // kHead = 16: the LAST N tile of every phase carries 16 extra accumulator columns (2 real) for the fused flow head.
-template <int BLOCK_N, bool kPair, int kT = 1, int kHead = 0>
+// kG = 2: two consecutive 64-channel K blocks of one tap per pipeline stage (halves the handshakes of narrow-N layers).
+template <int BLOCK_N, bool kPair, int kT = 1, int kHead = 0, int kG = 1>
 struct GemmCfg {
   static constexpr int kNB = BLOCK_N + kHead;            // B rows per stage / accumulator columns per TMEM stage
   static constexpr int kABytes = kT > 1 ? (kBlockM + 8) * kBlockK * 2 : kBlockM * kBlockK * 2;   // slab: up to 7 extra pixels
   static constexpr int kBBytes = (kNB / (kPair ? 2 : 1)) * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kT * kBBytes;
+  static constexpr int kStageBytes = kG * kABytes + kG * kT * kBBytes;
   static constexpr int kTmemCols = 2 * kNB <= 32 ? 32 : 2 * kNB <= 64 ? 64 : 2 * kNB <= 128 ? 128 : 2 * kNB <= 256 ? 256 : 512;
   static constexpr int kBarBytes = 256;
   static constexpr int kStgBytes = kBlockM * 128;        // one 64-channel chunk of the 16-bit output tile (SW128 rows)
@@ -189,9 +190,10 @@ __device__ __forceinline__ void mma(uint32_t d, uint32_t da_lo, uint32_t db_lo, 
 // shared-memory addresses, TMA coordinates and UMMA descriptors in uniform registers.  A loop entered by
 // lane 0 alone (`if (lane == 0)`) makes every operand "possibly divergent" and each UTMALDG / UTCHMMA is then
 // wrapped in an ELECT + R2UR waterfall loop: ~2x the cycles per K block (see profiles/r01_tuning.md).
-template <int BLOCK_N, bool kPair, int kT, int kHead>
+template <int BLOCK_N, bool kPair, int kT, int kHead, int kG>
 __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
-  using Cfg = GemmCfg<BLOCK_N, kPair, kT, kHead>;
+  using Cfg = GemmCfg<BLOCK_N, kPair, kT, kHead, kG>;
+  static_assert(kG == 1 || kT == 1, "chunk groups and slab groups are exclusive");
   static_assert(kHead == 0 || (!kPair && kT == 1 && BLOCK_N >= 64), "fused head: 1-CTA tiles of 64+ columns");
   constexpr int kNB = Cfg::kNB;
   constexpr int S = Cfg::kStages;
@@ -292,35 +294,41 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
         const int yy = y0 + p.tap_y[ti];
         const int ylim = p.Hg + p.tap_y[ti];
         const int ch_end = min(p.nchunks, ch + (kb1 - kb));
-        for (; ch < ch_end; ++ch, ++kb) {
+        while (ch < ch_end) {
           const int gn = kT > 1 ? (int)p.grp_n[ti] : 1;   // K blocks of this stage (slab group)
+          const int gc = kG > 1 ? min(kG, ch_end - ch) : 1;   // 64-channel chunks of this stage (chunk group)
           lean::wait(empty_s, phase ^ 1);
           if (leader) {
-            if (!kPair || rank == 0) lean::expect_tx(full_s, a_tx + (uint32_t)gn * b_tx);
-            if (do_a) {
-              if (npieces == 1) {
-                lean::tma5d<kPair>(sa, &p.tmap_a, full_t, c, x, pp, yy, b0);
-              } else {
-                int b = b0, y = yy;
-                uint32_t dst = sa;
-                for (int pc = 0; pc < npieces; ++pc) {
-                  lean::tma5d<kPair>(dst, &p.tmap_a, full_t, c, x, pp, y, b);
-                  dst += piece_bytes;
-                  y += p.piece_rows;
-                  if (y >= ylim) { y -= p.Hg; ++b; }
+            if (!kPair || rank == 0) lean::expect_tx(full_s, (uint32_t)gc * (a_tx + (uint32_t)gn * b_tx));
+            for (int g = 0; g < gc; ++g) {
+              const uint32_t sa_g = sa + (uint32_t)g * Cfg::kABytes;
+              if (do_a) {
+                if (npieces == 1) {
+                  lean::tma5d<kPair>(sa_g, &p.tmap_a, full_t, c + g * kBlockK, x, pp, yy, b0);
+                } else {
+                  int b = b0, y = yy;
+                  uint32_t dst = sa_g;
+                  for (int pc = 0; pc < npieces; ++pc) {
+                    lean::tma5d<kPair>(dst, &p.tmap_a, full_t, c + g * kBlockK, x, pp, y, b);
+                    dst += piece_bytes;
+                    y += p.piece_rows;
+                    if (y >= ylim) { y -= p.Hg; ++b; }
+                  }
+                }
+              }
+              if (do_b) {
+                const uint32_t sb_g = sa + kG * Cfg::kABytes + (uint32_t)g * Cfg::kBBytes;
+                lean::tma2d<kPair>(sb_g, &p.tmap_w, full_t, kcol + g * kBlockK, w_row);
+                if constexpr (kT > 1) {
+                  for (int t = 1; t < gn; ++t)
+                    lean::tma2d<kPair>(sb_g + t * Cfg::kBBytes, &p.tmap_w, full_t, kcol + t * kBlockK, w_row);
                 }
               }
             }
-            if (do_b) {
-              lean::tma2d<kPair>(sa + Cfg::kABytes, &p.tmap_w, full_t, kcol, w_row);
-              if constexpr (kT > 1) {
-                for (int t = 1; t < gn; ++t)
-                  lean::tma2d<kPair>(sa + Cfg::kABytes + t * Cfg::kBBytes, &p.tmap_w, full_t, kcol + t * kBlockK, w_row);
-              }
-            }
           }
-          c += kBlockK;
-          kcol += gn * kBlockK;
+          c += gc * kBlockK;
+          kcol += gc * gn * kBlockK;
+          ch += gc; kb += gc;
           sa += Cfg::kStageBytes; full_s += 8; empty_s += 8; full_t += 8;
           if (++stage == S) { stage = 0; phase ^= 1; sa = smem_base; full_s = full0; empty_s = empty0; full_t = full_tgt0; }
         }
@@ -339,7 +347,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
       // descriptors: only the low word (start address >> 4) changes; the high word is a constant
       constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
       const uint32_t da0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);
-      const uint32_t db0 = (((smem_base + Cfg::kABytes) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t db0 = (((smem_base + kG * Cfg::kABytes) & 0x3FFFFu) >> 4) | (1u << 16);
       constexpr uint32_t kStep = (uint32_t)(Cfg::kStageBytes >> 4);   // descriptor address field is in 16-byte units
       const bool do_mma = !(p.debug & 1);
       int stage = 0;
@@ -354,7 +362,8 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
         const uint32_t idesc = (kHead && (tile % p.tiles_n) == p.tiles_n - 1) ? idesc_last : idesc_main;
         const int ks = tile / (p.tiles_n * p.tiles_mp * p.phases);
         const int kb0 = ks * p.kb_per_split;
-        const int nkb = min(num_kb, kb0 + p.kb_per_split) - kb0;
+        const int nkb = kG > 1 ? p.ntaps * ((p.nchunks + kG - 1) / kG)      // stage items per tile (chunk groups)
+                               : min(num_kb, kb0 + p.kb_per_split) - kb0;
         for (int i = 0; i < nkb; ++i) {
           lean::wait(full_s, phase);
           ptx::tc_fence_after();
@@ -372,6 +381,19 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
                   const uint32_t a_lo = da + (uint32_t)p.grp_off[gi][t] * 8u;
                   const uint32_t b_lo = db + (uint32_t)t * (uint32_t)(Cfg::kBBytes >> 4);
                   lean::mma<kPair>(d_tmem, a_lo, b_lo, kDescHi, idesc, (i > 0 || t > 0) ? 1u : 0u);
+                  lean::mma<kPair>(d_tmem, a_lo + 2, b_lo + 2, kDescHi, idesc, 1u);
+                  lean::mma<kPair>(d_tmem, a_lo + 4, b_lo + 4, kDescHi, idesc, 1u);
+                  lean::mma<kPair>(d_tmem, a_lo + 6, b_lo + 6, kDescHi, idesc, 1u);
+                }
+              } else if constexpr (kG > 1) {
+                // chunk group (ksplit == 1): stage i of a tap holds chunks [kG*j, kG*j + gc) of that tap
+                const int per_tap = (p.nchunks + kG - 1) / kG;
+                const int j = i % per_tap;
+                const int gc = min(kG, p.nchunks - j * kG);
+                for (int g = 0; g < gc; ++g) {
+                  const uint32_t a_lo = da + (uint32_t)g * (uint32_t)(Cfg::kABytes >> 4);
+                  const uint32_t b_lo = db + (uint32_t)g * (uint32_t)(Cfg::kBBytes >> 4);
+                  lean::mma<kPair>(d_tmem, a_lo, b_lo, kDescHi, idesc, (i > 0 || g > 0) ? 1u : 0u);
                   lean::mma<kPair>(d_tmem, a_lo + 2, b_lo + 2, kDescHi, idesc, 1u);
                   lean::mma<kPair>(d_tmem, a_lo + 4, b_lo + 4, kDescHi, idesc, 1u);
                   lean::mma<kPair>(d_tmem, a_lo + 6, b_lo + 6, kDescHi, idesc, 1u);
@@ -628,23 +650,28 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  conv_gemm_body<BLOCK_N, false, 1, 0>(p);
+  conv_gemm_body<BLOCK_N, false, 1, 0, 1>(p);
 }
 // transposed conv with the level's flow head fused as 16 extra accumulator columns
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemmh_kernel(const __grid_constant__ ConvGemmParams p) {
-  conv_gemm_body<BLOCK_N, false, 1, 16>(p);
+  conv_gemm_body<BLOCK_N, false, 1, 16, 1>(p);
 }
 template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
-  conv_gemm_body<BLOCK_N, true, 1, 0>(p);
+  conv_gemm_body<BLOCK_N, true, 1, 0, 1>(p);
+}
+// chunk groups: two 64-channel K blocks per stage (narrow-N layers: half the handshakes), with / without fused head
+template <int BLOCK_N, int kHead>
+__global__ void __launch_bounds__(kThreads, 1) conv_gemmg_kernel(const __grid_constant__ ConvGemmParams p) {
+  conv_gemm_body<BLOCK_N, false, 1, kHead, 2>(p);
 }
 // slab mode (CTA pairs): kT taps of a group per stage
 template <int BLOCK_N, int kT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     conv_gemm2s_kernel(const __grid_constant__ ConvGemmParams p) {
-  conv_gemm_body<BLOCK_N, true, kT, 0>(p);
+  conv_gemm_body<BLOCK_N, true, kT, 0, 1>(p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -797,6 +824,22 @@ int launch_th(const ConvPlan& plan, cudaStream_t st) {
   }
   pdl_set_kind(1);
   OFS_CUDA(launch_pdl(conv_gemmh_kernel<BLOCK_N>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, false, 1, 16>::kSmem, st, plan.p));
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
+}
+
+template <int BLOCK_N, int kHead>
+int launch_tg(const ConvPlan& plan, cudaStream_t st) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  OFS_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    OFS_CUDA(cudaFuncSetAttribute(conv_gemmg_kernel<BLOCK_N, kHead>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)GemmCfg<BLOCK_N, false, 1, kHead, 2>::kSmem));
+    attr_set[dev] = true;
+  }
+  pdl_set_kind(1);
+  OFS_CUDA(launch_pdl(conv_gemmg_kernel<BLOCK_N, kHead>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, false, 1, kHead, 2>::kSmem, st, plan.p));
   OFS_LAUNCH_CHECK();
   return OFS_OK;
 }
@@ -1073,6 +1116,8 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
     OFS_REQUIRE(deconv && d.out_mode == 0 && d.cta_group == 1 && d.ksplit <= 1 && (d.block_n == 64 || d.block_n == 128),
                 "fused head: transposed conv, 16-bit output, 1-CTA tiles of 64 / 128 columns, no split-K");
   }
+  OFS_REQUIRE(d.kgroup == 1 || (d.kgroup == 2 && d.cta_group == 1 && !d.slab && d.ksplit <= 1 && (d.block_n == 64 || d.block_n == 128)),
+              "chunk groups: 1-CTA tiles of 64 / 128 columns, no slab, no split-K");
   p.w_rows_phase = p.n_pad + (d.head ? 16 : 0);
   plan.k_total = (p.slab ? (int)plan.wt_ky.size() : p.ntaps * p.nchunks) * kBlockK;
   plan.w_rows = p.phases * p.w_rows_phase;
@@ -1091,7 +1136,11 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
   p.tma_store = (p.out_mode == 0 && d.block_n >= 64) ? 1 : (p.out_mode == 2 && d.block_n >= 64 && !deconv) ? 2 : 0;
   p.tiles_mp = d.cta_group == 2 ? (p.tiles_m + 1) / 2 : p.tiles_m;
   const int total_tiles = p.tiles_mp * p.tiles_n * p.phases * p.ksplit;
-  if (d.head) {
+  if (d.kgroup == 2) {
+    plan.grid = std::max(1, std::min(total_tiles, sm_count()));
+    plan.smem = d.block_n == 64 ? (d.head ? GemmCfg<64, false, 1, 16, 2>::kSmem : GemmCfg<64, false, 1, 0, 2>::kSmem)
+                                : (d.head ? GemmCfg<128, false, 1, 16, 2>::kSmem : GemmCfg<128, false, 1, 0, 2>::kSmem);
+  } else if (d.head) {
     plan.grid = std::max(1, std::min(total_tiles, sm_count()));
     plan.smem = d.block_n == 64 ? GemmCfg<64, false, 1, 16>::kSmem : GemmCfg<128, false, 1, 16>::kSmem;
   } else if (p.slab) {
@@ -1236,7 +1285,11 @@ int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const 
 
 int conv_launch(const ConvPlan& plan, cudaStream_t st) {
   int rc = OFS_EINVAL;
-  if (plan.d.head) {
+  if (plan.d.kgroup == 2) {
+    if (plan.block_n == 64) rc = plan.d.head ? launch_tg<64, 16>(plan, st) : launch_tg<64, 0>(plan, st);
+    else if (plan.block_n == 128) rc = plan.d.head ? launch_tg<128, 16>(plan, st) : launch_tg<128, 0>(plan, st);
+    else { set_error("conv_launch: chunk groups need block_n 64 or 128 (got %d)", plan.block_n); return OFS_EINVAL; }
+  } else if (plan.d.head) {
     if (plan.block_n == 64) rc = launch_th<64>(plan, st);
     else if (plan.block_n == 128) rc = launch_th<128>(plan, st);
     else { set_error("conv_launch: fused head needs block_n 64 or 128 (got %d)", plan.block_n); return OFS_EINVAL; }
@@ -1313,6 +1366,7 @@ extern "C" int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const flo
   d.ksplit = ksplit > 1 ? ksplit : 1;
   d.cta_group = (cta_group == 2 || cta_group == 4) ? 2 : 1;
   d.slab = cta_group == 4 ? 1 : 0;   // 4 = CTA pairs + slab groups
+  d.kgroup = cta_group == 8 ? 2 : 1; // 8 = two K chunks per pipeline stage
   const bool via16 = d.ksplit > 1 || out16;   // the network's 16-bit activation epilogue (split-K always reduces into it)
   const int cout8 = ((Cout + 7) / 8) * 8;
   d.out_mode = via16 ? 0 : 1; d.lrelu = lrelu; d.is_bf16 = is_bf16;
@@ -1409,7 +1463,7 @@ extern "C" int ofs_conv2d_bench(int B, int H, int W, int Cin, int in_cs, int Cou
   ConvDesc d;
   d.kind = transposed ? kDeconvK4S2 : kConv;
   d.B = B; d.H = H; d.W = W; d.cin = Cin; d.in_cs = in_cs; d.cout = Cout; d.k = k; d.stride = stride;
-  d.block_n = block_n; d.ksplit = ksplit > 1 ? ksplit : 1; d.cta_group = (cta_group == 2 || cta_group == 4) ? 2 : 1; d.slab = cta_group == 4 ? 1 : 0; d.debug = debug;
+  d.block_n = block_n; d.ksplit = ksplit > 1 ? ksplit : 1; d.cta_group = (cta_group == 2 || cta_group == 4) ? 2 : 1; d.slab = cta_group == 4 ? 1 : 0; d.kgroup = cta_group == 8 ? 2 : 1; d.debug = debug;
   const bool out16 = (Cout % block_n) == 0 || (!transposed && block_n >= 64 && Cout % 64 == 0 && ksplit <= 1);
   d.out_mode = out16 ? 0 : 1; d.lrelu = 1; d.is_bf16 = 1; d.out_cstride = out_cs; d.out_coff = 0;
   ConvPlan plan;

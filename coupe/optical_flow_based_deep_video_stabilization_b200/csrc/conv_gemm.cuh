@@ -78,6 +78,7 @@ struct ConvDesc {
   int out_cstride, out_coff;
   int ksplit = 1;      // > 1: split the K loop over this many CTAs per tile (16-bit output mode only)
   int cta_group = 1;   // 2: CTA pairs (tcgen05 cta_group::2): tile = 256 GEMM rows x BLOCK_N, B split over the pair
+  int kgroup = 1;      // 2: two consecutive 64-channel K blocks of a tap per pipeline stage (narrow-N layers)
   int head = 0;        // 1: transposed conv with the level's 3x3 flow head fused as 16 extra accumulator columns
   int slab = 0;        // 1: x-shifted taps share one shared-memory slab (stride-2 convs whose tiles are one 128-px row)
   int debug = 0;       // see ConvGemmParams::debug

@@ -343,6 +343,8 @@ int prepare(ofs_net* n, int B) {
       return OFS_EINVAL;
     }
     if (L.d.slab) { cg = 2; bn = L.d.block_n; ks = 1; }   // the packed K order is the slab order: tiling is fixed
+    if (cg == 8 && !L.d.slab) { L.d.kgroup = 2; cg = 1; }   // OFS_TUNE cta_group 8 = chunk groups
+    if (L.d.kgroup == 2) { rc = conv_plan_geometry(L.plan, L.d); if (rc != OFS_OK) return rc; }
     if (ks > 1 || bn != L.d.block_n || cg == 2 || dbg) {
       ConvDesc d = L.d;
       d.block_n = bn;

@@ -550,7 +550,7 @@ __device__ __forceinline__ float div384(float t) {
   return q * 0.0078125f;
 }
 
-template <bool kFused>
+template <bool kFused, bool kDirectStore = false>
 __global__ void __launch_bounds__(256, 6) warp5_kernel(const float* __restrict__ img, const float2* __restrict__ flow,
                                                         Resize2 rz, float* __restrict__ out, int B, int H, int W) {
   __shared__ __align__(16) float obuf[8][192];
@@ -643,7 +643,13 @@ __global__ void __launch_bounds__(256, 6) warp5_kernel(const float* __restrict__
             v[h][0] = v[h][1] = v[h][2] = 0.0f;
           }
         }
-        store_row3(obuf[wid], out + (((size_t)b * H + oy) * W + ox0) * 3, lane, valid_px, v[0], v[1]);
+        if (kDirectStore) {
+          float* o = out + (((size_t)b * H + oy) * W + ox0 + lane) * 3;
+          if (ox0 + lane < W) { __stcs(o, v[0][0]); __stcs(o + 1, v[0][1]); __stcs(o + 2, v[0][2]); }
+          if (ox0 + lane + 32 < W) { __stcs(o + 96, v[1][0]); __stcs(o + 97, v[1][1]); __stcs(o + 98, v[1][2]); }
+        } else {
+          store_row3(obuf[wid], out + (((size_t)b * H + oy) * W + ox0) * 3, lane, valid_px, v[0], v[1]);
+        }
       }
     }
   }
@@ -655,14 +661,12 @@ template <class Provider>
 __global__ void __launch_bounds__(256, 6) sample5_kernel(Provider prov, const float* __restrict__ img,
                                                          float* __restrict__ out, int B, int srcH, int srcW, int oH,
                                                          int oW) {
-  __shared__ __align__(16) float obuf[8][192];
   pdl_wait();
   pdl_launch_dependents();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int b = blockIdx.z;
   const int ox0 = blockIdx.x * kTileW, oy0 = blockIdx.y * kTileH + wid * 2;
   const float* __restrict__ imgb = img + (size_t)b * srcH * srcW * 3;
-  const int valid_px = min(kTileW, oW - ox0);
 #pragma unroll
   for (int rr = 0; rr < 2; ++rr) {
     const int oy = oy0 + rr;
@@ -693,7 +697,9 @@ __global__ void __launch_bounds__(256, 6) sample5_kernel(Provider prov, const fl
         }
       }
     }
-    store_row3(obuf[wid], out + (((size_t)b * oH + oy) * oW + ox0) * 3, lane, valid_px, v[0], v[1]);
+    float* o = out + (((size_t)b * oH + oy) * oW + ox0 + lane) * 3;
+    if (ox0 + lane < oW) { __stcs(o, v[0][0]); __stcs(o + 1, v[0][1]); __stcs(o + 2, v[0][2]); }
+    if (ox0 + lane + 32 < oW) { __stcs(o + 96, v[1][0]); __stcs(o + 97, v[1][1]); __stcs(o + 98, v[1][2]); }
   }
 }
 
@@ -802,13 +808,15 @@ int launch_warp3(Provider prov, const float* img, float* out, int B, int H, int 
       const FlowResize& fr = prov.fr;
       if (fr.prescaled) {
         Resize2 rz{reinterpret_cast<const float2*>(fr.flow2), fr.fh, fr.fw, fr.hs, fr.ws, (float)W, (float)H};
-        OFS_CUDA(launch_pdl(warp5_kernel<true>, tile_grid3(B, H, W), dim3(256), 0, st, img, (const float2*)nullptr, rz, out, B, H, W));
+        // streaming 32-bit stores straight from registers: the three stores of a warp fill whole sectors between them,
+        // and dropping the shared-memory transpose saves ~12 instructions per pixel (47.6 -> 45.0 us at 8 x 720p)
+        OFS_CUDA(launch_pdl(warp5_kernel<true, true>, tile_grid3(B, H, W), dim3(256), 0, st, img, (const float2*)nullptr, rz, out, B, H, W));
         OFS_LAUNCH_CHECK();
         return OFS_OK;
       }
     } else {
       Resize2 rz{};
-      OFS_CUDA(launch_pdl(warp5_kernel<false>, tile_grid3(B, H, W), dim3(256), 0, st, img,
+      OFS_CUDA(launch_pdl(warp5_kernel<false, true>, tile_grid3(B, H, W), dim3(256), 0, st, img,
                           reinterpret_cast<const float2*>(prov.flow), rz, out, B, H, W));
       OFS_LAUNCH_CHECK();
       return OFS_OK;

@@ -101,6 +101,11 @@ TILING_CASES = [
     pytest.param(3, 6, 8, 256, 256, 3, 1, False, 128, -1, 2, id="tma_store_pair_odd_tiles"),
     pytest.param(2, 24, 32, 128, 512, 3, 1, False, 192, -1, 1, id="tma_store_n192_padded_last_tile"),
     pytest.param(1, 24, 32, 64, 320, 3, 1, False, 192, -1, 1, id="tma_store_n192_cout320"),
+    # chunk groups (cta_group = 8: two 64-channel K blocks of a tap per pipeline stage)
+    pytest.param(1, 24, 32, 192, 64, 3, 1, False, 64, -1, 8, id="kgroup_odd_chunk_count"),
+    pytest.param(2, 12, 16, 130, 128, 4, 2, True, 128, -1, 8, id="kgroup_deconv"),
+    pytest.param(1, 24, 32, 386, 64, 4, 2, True, 64, -1, 8, id="kgroup_deconv2_form"),
+    pytest.param(3, 6, 8, 256, 128, 3, 1, False, 128, 1, 8, id="kgroup_whole_image_tiles"),
     # slab groups (cta_group = 4: CTA pairs, x-shifted taps share one shared-memory slab per pipeline stage)
     pytest.param(1, 32, 256, 27, 64, 7, 2, False, 64, 1, 4, id="slab_conv1_form"),
     pytest.param(2, 16, 512, 27, 64, 7, 2, False, 64, -1, 4, id="slab_conv1_form_two_x_tiles_out16"),
