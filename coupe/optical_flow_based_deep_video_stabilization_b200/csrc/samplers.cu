@@ -93,26 +93,30 @@ struct GridSampleCoord {
   int projective;
   int H, W, oH, oW;
   float step_x, step_y;  // tf.linspace fp32 step
-  __device__ __forceinline__ Taps taps(int b, int oy, int ox) const {
+  struct Ctx { float t[8]; };   // theta of the block's batch element, loaded once per thread
+  __device__ __forceinline__ Ctx begin(int b) const {
+    Ctx c;
+    const int n = projective ? 8 : 6;
+    const float* t = theta + (size_t)b * n;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c.t[i] = i < n ? __ldg(t + i) : 0.0f;
+    return c;
+  }
+  __device__ __forceinline__ Taps taps(int b, int oy, int ox) const { return taps(begin(b), oy, ox); }
+  __device__ __forceinline__ Taps taps(const Ctx& c, int oy, int ox) const {
     const float xt = (oW == 1) ? -1.0f : __fadd_rn(-1.0f, __fmul_rn(step_x, (float)ox));
     const float yt = (oH == 1) ? -1.0f : __fadd_rn(-1.0f, __fmul_rn(step_y, (float)oy));
-    float xs, ys;
+    float xs = c.t[0] * xt + c.t[1] * yt + c.t[2];
+    float ys = c.t[3] * xt + c.t[4] * yt + c.t[5];
     if (projective) {
-      const float* t = theta + (size_t)b * 8;
-      xs = __ldg(t + 0) * xt + __ldg(t + 1) * yt + __ldg(t + 2);
-      ys = __ldg(t + 3) * xt + __ldg(t + 4) * yt + __ldg(t + 5);
-      float zs = __ldg(t + 6) * xt + __ldg(t + 7) * yt + 1.0f;
+      float zs = c.t[6] * xt + c.t[7] * yt + 1.0f;
       if (zs == 0.0f) zs = zs + 1e-8f;
       xs = __fdiv_rn(xs, zs);
       ys = __fdiv_rn(ys, zs);
-    } else {
-      const float* t = theta + (size_t)b * 6;
-      xs = __ldg(t + 0) * xt + __ldg(t + 1) * yt + __ldg(t + 2);
-      ys = __ldg(t + 3) * xt + __ldg(t + 4) * yt + __ldg(t + 5);
     }
     const float Wf = (float)W, Hf = (float)H;
-    float x = __fmul_rn(__fdiv_rn(__fadd_rn(xs, 1.0f), 2.0f), Wf - 1.0f);
-    float y = __fmul_rn(__fdiv_rn(__fadd_rn(ys, 1.0f), 2.0f), Hf - 1.0f);
+    float x = __fmul_rn(__fmul_rn(__fadd_rn(xs, 1.0f), 0.5f), Wf - 1.0f);   // / 2.0: an exact scaling
+    float y = __fmul_rn(__fmul_rn(__fadd_rn(ys, 1.0f), 0.5f), Hf - 1.0f);
     x = fminf(fmaxf(x, -1.0f), Wf) + 1.0f;  // clip to [-edge, W-1+edge], then += edge
     y = fminf(fmaxf(y, -1.0f), Hf) + 1.0f;
     const float x0f = floorf(x), y0f = floorf(y);
@@ -140,18 +144,26 @@ struct LieCoord {
   const float* pMtrx;    // [B,3,3]
   const float* refMtrx;  // [3,3]
   int srcH, srcW, oH, oW;
-  __device__ __forceinline__ Taps taps(int b, int oy, int ox) const {
-    float M[9];
+  struct Ctx { float M[9]; double sx, sy; };   // refMtrx @ pMtrx[b] and the linspace steps, once per thread
+  __device__ __forceinline__ Ctx begin(int b) const {
+    Ctx c;
     const float* P = pMtrx + (size_t)b * 9;
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        M[r * 3 + c] = __ldg(refMtrx + r * 3 + 0) * __ldg(P + 0 + c) + __ldg(refMtrx + r * 3 + 1) * __ldg(P + 3 + c) +
-                       __ldg(refMtrx + r * 3 + 2) * __ldg(P + 6 + c);
+      for (int k = 0; k < 3; ++k)
+        c.M[r * 3 + k] = __ldg(refMtrx + r * 3 + 0) * __ldg(P + 0 + k) + __ldg(refMtrx + r * 3 + 1) * __ldg(P + 3 + k) +
+                         __ldg(refMtrx + r * 3 + 2) * __ldg(P + 6 + k);
+    c.sx = oW > 1 ? 2.0 / (double)(oW - 1) : 0.0;
+    c.sy = oH > 1 ? 2.0 / (double)(oH - 1) : 0.0;
+    return c;
+  }
+  __device__ __forceinline__ Taps taps(int b, int oy, int ox) const { return taps(begin(b), oy, ox); }
+  __device__ __forceinline__ Taps taps(const Ctx& c, int oy, int ox) const {
+    const float* M = c.M;
     // np.linspace(-1,1,n) evaluated in float64, then astype(float32)
-    const float X = (oW == 1) ? -1.0f : (ox == oW - 1 ? 1.0f : (float)(-1.0 + (double)ox * (2.0 / (double)(oW - 1))));
-    const float Y = (oH == 1) ? -1.0f : (oy == oH - 1 ? 1.0f : (float)(-1.0 + (double)oy * (2.0 / (double)(oH - 1))));
+    const float X = (oW == 1) ? -1.0f : (ox == oW - 1 ? 1.0f : (float)(-1.0 + (double)ox * c.sx));
+    const float Y = (oH == 1) ? -1.0f : (oy == oH - 1 ? 1.0f : (float)(-1.0 + (double)oy * c.sy));
     const float h0 = M[0] * X + M[1] * Y + M[2];
     const float h1 = M[3] * X + M[4] * Y + M[5];
     const float h2 = M[6] * X + M[7] * Y + M[8];
@@ -203,6 +215,9 @@ struct ResizeWarpProvider {
 template <class Coord>
 struct CoordProvider {
   Coord c;
+  typedef typename Coord::Ctx Ctx;
+  __device__ __forceinline__ Ctx begin(int b) const { return c.begin(b); }
+  __device__ __forceinline__ Taps taps(const Ctx& ctx, int oy, int ox) const { return c.taps(ctx, oy, ox); }
   __device__ __forceinline__ Taps taps(int b, int oy, int ox) const { return c.taps(b, oy, ox); }
 };
 
@@ -667,6 +682,7 @@ __global__ void __launch_bounds__(256, 6) sample5_kernel(Provider prov, const fl
   const int b = blockIdx.z;
   const int ox0 = blockIdx.x * kTileW, oy0 = blockIdx.y * kTileH + wid * 2;
   const float* __restrict__ imgb = img + (size_t)b * srcH * srcW * 3;
+  const typename Provider::Ctx ctx = prov.begin(b);
 #pragma unroll
   for (int rr = 0; rr < 2; ++rr) {
     const int oy = oy0 + rr;
@@ -677,7 +693,7 @@ __global__ void __launch_bounds__(256, 6) sample5_kernel(Provider prov, const fl
       const int ox = ox0 + lane + 32 * h;
       v[h][0] = v[h][1] = v[h][2] = 0.0f;
       if (ox < oW) {
-        const Taps tp = prov.taps(b, oy, ox);
+        const Taps tp = prov.taps(ctx, oy, ox);
         float px[4][3];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
