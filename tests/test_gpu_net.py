@@ -304,3 +304,21 @@ def test_full_size_step_properties(ofs, cuda_dev, B, H, W):
     ref_img = S.flow_resize_warp(frames[:1], f2[:1].cpu(), H, W)
     assert float(((out[:1].cpu() - ref_img).abs() > 1e-3).float().mean()) < 1e-4    # 1e-3 on [0,1] pixels
     net.close()
+
+
+def test_npz_checkpoint_ingest(ofs, cuda_dev, tmp_path):
+    """tl.files.load_and_assign_npz_dict (main_dl.py:520): an npz keyed by TF variable names
+    ('main_net/flownetS/<layer>/<var>:0', as tl.files.save_npz_dict writes them, main_dl.py:424-426), with
+    non-trivial BN statistics, gives the same flows as handing the arrays over directly."""
+    w = F.make_weights(3, "calibrated", head_scale=0.02)
+    path = tmp_path / "flownetS_pyramid.npz"
+    np.savez(path, **{f"main_net/flownetS/{k}:0": np.asarray(v, dtype=np.float32) for k, v in w.items()})
+    x = F.make_feats(5, 1).to(cuda_dev)
+    direct = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=1)
+    direct.assign_weights(w)
+    want = direct.forward(x)
+    ofs.load_and_assign_npz_dict(name=str(path), sess=None, scope="npz_test", device=cuda_dev, max_batch=1)
+    got = ofs.flownetS_pyramid(x, 1, is_train=False, scope="npz_test")
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+    direct.close()
