@@ -1,0 +1,65 @@
+"""Device-side clip driver: the per-frame loop of evaluate_originalSize() (reference
+main_flownetS_pyramid_noprevloss_dataloader.py:535-630) behind one call per frame.
+
+    net = get_net(); load_and_assign_npz_dict(...)
+    stab = ClipStabilizer(net, n_clips=1, height=out_h, width=out_w)
+    for i in range(total_frames):                       # main_dl.py:540
+        ret, frame = cap.read()                         # :547  (BGR uint8)
+        out.write(stab.step(frame))                     # :550-630 on the GPU
+
+The history of stabilised frames lives on the device as a ring of resized uint8 slices; a step moves 3 bytes per
+pixel each way over PCIe.  Several clips of the same size advance in lockstep as one batch (n_clips > 1).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class ClipStabilizer:
+    def __init__(self, net, n_clips=1, height=720, width=1280):
+        self._lib = _lib.load()
+        self.net = net                      # keeps the FlowNetSPyramid (and its ofs_net handle) alive
+        self.n, self.h, self.w = int(n_clips), int(height), int(width)
+        self._h = C.c_void_p()
+        _lib.check(self._lib.ofs_clips_create(C.byref(self._h), net._h, self.n, self.h, self.w))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.ofs_clips_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def frame_index(self):
+        return int(self._lib.ofs_clips_frame_index(self._h))
+
+    def reset(self):
+        _lib.check(self._lib.ofs_clips_reset(self._h))
+
+    def step(self, frames_bgr, return_float=False):
+        """frames_bgr: uint8 [H,W,3] (one clip) or [n_clips,H,W,3], BGR as cap.read() returns them.
+        Returns np.uint8(totaloutputFrame[i]) with the same leading shape (and totaloutputFrame[i] as float32
+        when return_float)."""
+        a = np.ascontiguousarray(frames_bgr, dtype=np.uint8)
+        single = a.ndim == 3
+        if single:
+            a = a[None]
+        if a.shape != (self.n, self.h, self.w, 3):
+            raise ValueError(f"frames must be uint8 [{self.n},{self.h},{self.w},3], got {a.shape}")
+        out = np.empty_like(a)
+        outf = np.empty(a.shape, np.float32) if return_float else None
+        _lib.check(self._lib.ofs_clips_step_host(self._h, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                                                 outf.ctypes.data_as(C.c_void_p) if return_float else None))
+        if single:
+            out = out[0]
+            outf = outf[0] if return_float else None
+        return (out, outf) if return_float else out

@@ -1,0 +1,343 @@
+// ofs_clips: the per-frame loop of evaluate_originalSize() (reference main_dl.py:535-630) with its state on the device.
+//
+// The reference keeps a float64 history of ALL output frames on the host and, per frame, runs nine cv2.resize +
+// cvtColor calls on full-resolution frames, feeds 21 MB + 11 MB of float32 through sess.run and fetches 11 MB back
+// (main_dl.py:550-569).  Only np.uint8() versions of the history are ever consumed (main_dl.py:556-558, :630), and a
+// frame is re-used by up to 8 later steps (offsets 31,23,15,7,4,3,2,1).  So the device keeps, per clip, a 32-slot
+// ring of the RESIZED (512x384), channel-swapped uint8 outputs; a step uploads one uint8 frame (2.8 MB at 720p
+// instead of 32 MB of float32), resizes it once, assembles the 27-channel network input from the ring through two
+// 256-entry look-up tables, runs forward + flow glue + warp, converts the warped frame to np.uint8 semantics,
+// resizes it into the ring and downloads the uint8 frame.  n clips advance in lockstep as one batch.
+//
+// Arithmetic restated exactly (the GPU test replays main_dl.py:540-630 with cv2 on the host and compares bytes):
+//   * cv2.resize(u8, (512,384)) INTER_LINEAR: OpenCV's fixed-point path -- coefficients cvRound(f * 2048) from
+//     f = (float)((d + 0.5) * scale - 0.5), horizontal int pass, vertical ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2 >> 2;
+//   * history taps: np.float32(u8) / 255.0 (float32 division); current frame: u8 / 255.0 (float64 division, cast to
+//     float32 by the feed); resizedInput: the same per pixel at full resolution;
+//   * totaloutputFrame[i] = cvtColor(warped * 255) in float32; np.uint8(): truncation toward zero, low 8 bits.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <vector>
+
+#include "conv_gemm.cuh"
+
+struct ofs_net;
+namespace ofs {
+void* net_x0(ofs_net* n);
+int net_max_batch(const ofs_net* n);
+int net_is_bf16(const ofs_net* n);
+int net_device(const ofs_net* n);
+bool net_loaded(const ofs_net* n);
+int net_prepare(ofs_net* n, int B);
+int net_stabilize_from_x0(ofs_net* n, const float* frames, float* out, int B, int H, int W, cudaStream_t st);
+}  // namespace ofs
+
+namespace {
+
+using namespace ofs;
+
+constexpr int kNetH = 384, kNetW = 512, kRing = 32;
+constexpr int kSlice = kNetH * kNetW * 3;   // bytes of one resized uint8 slice
+constexpr int kOffsets[8] = {31, 23, 15, 7, 4, 3, 2, 1};   // main_dl.py:553
+
+struct StepState {        // read by the kernels from device memory so the captured graph never changes
+  int hist_slot[8];       // ring slot of history tap j
+  int write_slot;         // ring slot of this step's output
+  int first;              // step 0: the resized input frame also seeds ring slot 0 (main_dl.py:548-549)
+  int pad[6];
+};
+
+// cv2.resize(src, (512, 384)), INTER_LINEAR, uint8, 3 channels; dst channels reversed (cvtColor RGB2BGR == swap)
+__global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restrict__ src, int H, int W,
+                                                        uint8_t* __restrict__ dst, size_t dst_clip_stride,
+                                                        const StepState* __restrict__ state, int dst_is_ring,
+                                                        uint8_t* __restrict__ seed_ring, size_t ring_clip_stride,
+                                                        const int* __restrict__ sx_tab, const short* __restrict__ ax_tab,
+                                                        const int* __restrict__ sy_tab, const short* __restrict__ ay_tab) {
+  const int dx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int dy = blockIdx.y;
+  const int clip = blockIdx.z;
+  if (dx >= kNetW) return;
+  const int sx = sx_tab[dx], sx1 = min(sx + 1, W - 1);
+  const int a0 = ax_tab[2 * dx], a1 = ax_tab[2 * dx + 1];
+  const int sy = sy_tab[dy];
+  const int y0 = min(max(sy, 0), H - 1), y1 = min(max(sy + 1, 0), H - 1);
+  const int b0 = ay_tab[2 * dy], b1 = ay_tab[2 * dy + 1];
+  const uint8_t* s = src + (size_t)clip * H * W * 3;
+  const uint8_t* r0 = s + (size_t)y0 * W * 3;
+  const uint8_t* r1 = s + (size_t)y1 * W * 3;
+  uint8_t o[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int h0 = (int)r0[sx * 3 + c] * a0 + (int)r0[sx1 * 3 + c] * a1;
+    const int h1 = (int)r1[sx * 3 + c] * a0 + (int)r1[sx1 * 3 + c] * a1;
+    o[2 - c] = (uint8_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
+  }
+  const size_t px = ((size_t)dy * kNetW + dx) * 3;
+  uint8_t* d = dst + (size_t)clip * dst_clip_stride + (dst_is_ring ? (size_t)state->write_slot * kSlice : 0) + px;
+  d[0] = o[0]; d[1] = o[1]; d[2] = o[2];
+  if (seed_ring && state->first) {
+    uint8_t* r = seed_ring + (size_t)clip * ring_clip_stride + px;   // slot 0
+    r[0] = o[0]; r[1] = o[1]; r[2] = o[2];
+  }
+}
+
+// curinput (main_dl.py:550-558) straight into the network's packed 16-bit input: 8 history taps + current frame
+__global__ void __launch_bounds__(256) assemble_x0_kernel(const uint8_t* __restrict__ ring, size_t ring_clip_stride,
+                                                          const uint8_t* __restrict__ cur, const StepState* __restrict__ state,
+                                                          const uint16_t* __restrict__ lut_hist,
+                                                          const uint16_t* __restrict__ lut_cur, uint4* __restrict__ x0) {
+  __shared__ uint16_t lh[256], lc[256];
+  lh[threadIdx.x] = lut_hist[threadIdx.x];
+  lc[threadIdx.x] = lut_cur[threadIdx.x];
+  __syncthreads();
+  const int clip = blockIdx.y;
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= kNetH * kNetW) return;
+  uint16_t v[32];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint8_t* s = ring + (size_t)clip * ring_clip_stride + (size_t)state->hist_slot[j] * kSlice + (size_t)px * 3;
+    v[3 * j] = lh[s[0]]; v[3 * j + 1] = lh[s[1]]; v[3 * j + 2] = lh[s[2]];
+  }
+  const uint8_t* c = cur + (size_t)clip * kSlice + (size_t)px * 3;
+  v[24] = lc[c[0]]; v[25] = lc[c[1]]; v[26] = lc[c[2]];
+#pragma unroll
+  for (int k = 27; k < 32; ++k) v[k] = 0;
+  uint4* o = x0 + ((size_t)clip * kNetH * kNetW + px) * 4;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    o[q] = make_uint4((uint32_t)v[8 * q] | ((uint32_t)v[8 * q + 1] << 16), (uint32_t)v[8 * q + 2] | ((uint32_t)v[8 * q + 3] << 16),
+                      (uint32_t)v[8 * q + 4] | ((uint32_t)v[8 * q + 5] << 16), (uint32_t)v[8 * q + 6] | ((uint32_t)v[8 * q + 7] << 16));
+}
+
+// resizedInput = cvtColor(frame_unstab, RGB2BGR) / 255.0 (main_dl.py:568), fed as float32
+__global__ void __launch_bounds__(256) frame_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
+                                                           size_t npix, const float* __restrict__ lut) {
+  __shared__ float l[256];
+  l[threadIdx.x] = lut[threadIdx.x];
+  __syncthreads();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    const uint8_t* s = src + i * 3;
+    float* d = dst + i * 3;
+    d[0] = l[s[2]]; d[1] = l[s[1]]; d[2] = l[s[0]];
+  }
+}
+
+// totaloutputFrame[i] = cvtColor(warped * 255, RGB2BGR) (float32 product); out.write(np.uint8(...)) (main_dl.py:625,630)
+__global__ void __launch_bounds__(256) finish_kernel(const float* __restrict__ warped, uint8_t* __restrict__ out_u8,
+                                                     float* __restrict__ out_f32, size_t npix) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    const float* s = warped + i * 3;
+    const float v0 = __fmul_rn(s[2], 255.0f), v1 = __fmul_rn(s[1], 255.0f), v2 = __fmul_rn(s[0], 255.0f);   // B, G, R
+    uint8_t* d = out_u8 + i * 3;
+    d[0] = (uint8_t)(__float2int_rz(v0) & 0xff);
+    d[1] = (uint8_t)(__float2int_rz(v1) & 0xff);
+    d[2] = (uint8_t)(__float2int_rz(v2) & 0xff);
+    if (out_f32) { float* f = out_f32 + i * 3; f[0] = v0; f[1] = v1; f[2] = v2; }
+  }
+}
+
+int grid_for(size_t work, int threads) {
+  size_t b = (work + threads - 1) / threads;
+  const size_t cap = (size_t)sm_count() * 8;
+  return (int)std::max<size_t>(1, std::min(b, cap));
+}
+
+// OpenCV resize.cpp: fx = (float)((dx+0.5)*scale_x - 0.5); sx = cvFloor(fx); fx -= sx; edge clamps; cvRound(f * 2048)
+void linear_tables(int src, int dst, std::vector<int>& s_tab, std::vector<short>& a_tab, bool clamp_x) {
+  s_tab.resize(dst);
+  a_tab.resize(2 * dst);
+  const double scale = (double)src / (double)dst;
+  for (int d = 0; d < dst; ++d) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= (float)s;
+    if (clamp_x) {   // horizontal pass only; the vertical pass clips the ROW indices instead
+      if (s < 0) { f = 0.f; s = 0; }
+      if (s >= src - 1) { f = 0.f; s = src - 1; }
+    }
+    s_tab[d] = s;
+    auto sat = [](float v) { long r = lrintf(v); return (short)std::max<long>(-32768, std::min<long>(32767, r)); };
+    a_tab[2 * d] = sat((1.f - f) * 2048.f);
+    a_tab[2 * d + 1] = sat(f * 2048.f);
+  }
+}
+
+}  // namespace
+
+struct ofs_clips {
+  ofs_net* net = nullptr;
+  int n = 0, H = 0, W = 0, device = 0;
+  long long frame = 0;
+  uint8_t *d_frame = nullptr, *d_out_u8 = nullptr, *d_ring = nullptr, *d_cur = nullptr;
+  float *d_frame_f32 = nullptr, *d_warped = nullptr, *d_out_f32 = nullptr, *d_lut_f32 = nullptr;
+  uint16_t *d_lut_hist = nullptr, *d_lut_cur = nullptr;
+  int *d_sx = nullptr, *d_sy = nullptr;
+  short *d_ax = nullptr, *d_ay = nullptr;
+  StepState* d_state = nullptr;
+  cudaStream_t st = nullptr;
+  cudaGraphExec_t graph = nullptr;
+  bool graph_f32 = false;
+  int graph_launches = 0;
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+int clips_alloc(ofs_clips* c, void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) { set_error("ofs_clips: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return OFS_ENOMEM; }
+  c->allocs.push_back(*p);
+  return check_cuda(cudaMemset(*p, 0, bytes), "memset", __FILE__, __LINE__);
+}
+
+int enqueue_step(ofs_clips* c, cudaStream_t st, bool want_f32) {
+  const int n = c->n, H = c->H, W = c->W;
+  const size_t npix = (size_t)n * H * W;
+  const size_t ring_stride = (size_t)kRing * kSlice;
+  const dim3 rgrid((kNetW + 255) / 256, kNetH, n);
+  resize_u8_kernel<<<rgrid, 256, 0, st>>>(c->d_frame, H, W, c->d_cur, (size_t)kSlice, c->d_state, 0, c->d_ring, ring_stride,
+                                          c->d_sx, c->d_ax, c->d_sy, c->d_ay);
+  OFS_LAUNCH_CHECK();
+  assemble_x0_kernel<<<dim3((kNetH * kNetW + 255) / 256, n), 256, 0, st>>>(c->d_ring, ring_stride, c->d_cur, c->d_state,
+                                                                         c->d_lut_hist, c->d_lut_cur,
+                                                                         reinterpret_cast<uint4*>(net_x0(c->net)));
+  OFS_LAUNCH_CHECK();
+  frame_to_f32_kernel<<<grid_for(npix, 256), 256, 0, st>>>(c->d_frame, c->d_frame_f32, npix, c->d_lut_f32);
+  OFS_LAUNCH_CHECK();
+  int rc = net_stabilize_from_x0(c->net, c->d_frame_f32, c->d_warped, n, H, W, st);
+  if (rc != OFS_OK) return rc;
+  finish_kernel<<<grid_for(npix, 256), 256, 0, st>>>(c->d_warped, c->d_out_u8, want_f32 ? c->d_out_f32 : nullptr, npix);
+  OFS_LAUNCH_CHECK();
+  resize_u8_kernel<<<rgrid, 256, 0, st>>>(c->d_out_u8, H, W, c->d_ring, ring_stride, c->d_state, 1, nullptr, 0, c->d_sx,
+                                          c->d_ax, c->d_sy, c->d_ay);
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ofs_clips_create(ofs_clips** out, ofs_net* net, int n_clips, int H, int W) {
+  OFS_REQUIRE(out && net, "ofs_clips_create: null pointer");
+  *out = nullptr;
+  OFS_REQUIRE(n_clips >= 1 && n_clips <= net_max_batch(net), "ofs_clips_create: %d clips outside [1, max_batch %d]", n_clips,
+              net_max_batch(net));
+  OFS_REQUIRE(H >= 2 && W >= 2, "ofs_clips_create: bad frame size %dx%d", H, W);
+  OFS_CUDA(cudaSetDevice(net_device(net)));
+  ofs_clips* c = new ofs_clips();
+  c->net = net; c->n = n_clips; c->H = H; c->W = W; c->device = net_device(net);
+  const size_t fpx = (size_t)n_clips * H * W * 3;
+  int rc = clips_alloc(c, (void**)&c->d_frame, fpx);
+  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_out_u8, fpx);
+  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_frame_f32, fpx * 4);
+  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_warped, fpx * 4);
+  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_out_f32, fpx * 4);
+  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_ring, (size_t)n_clips * kRing * kSlice);
+  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_cur, (size_t)n_clips * kSlice);
+  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_lut_hist, 512);
+  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_lut_cur, 512);
+  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_lut_f32, 1024);
+  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_sx, kNetW * 4);
+  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_sy, kNetH * 4);
+  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_ax, kNetW * 4);
+  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_ay, kNetH * 4);
+  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_state, sizeof(StepState));
+  if (rc == OFS_OK && cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("ofs_clips_create: cudaStreamCreate failed");
+    rc = OFS_ECUDA;
+  }
+  if (rc == OFS_OK) {
+    const int is_bf16 = net_is_bf16(net);
+    std::vector<uint16_t> lh(256), lc(256);
+    std::vector<float> lf(256);
+    for (int v = 0; v < 256; ++v) {
+      const float hist = (float)v / 255.0f;                 // np.float32(u8) / 255.0        (main_dl.py:556,558)
+      const float cur = (float)((double)v / 255.0);         // u8 / 255.0 -> float32 at the feed (main_dl.py:550,568)
+      lh[v] = is_bf16 ? f32_to_bf16_rn(hist) : f32_to_fp16_rn(hist);
+      lc[v] = is_bf16 ? f32_to_bf16_rn(cur) : f32_to_fp16_rn(cur);
+      lf[v] = cur;
+    }
+    std::vector<int> sx, sy;
+    std::vector<short> ax, ay;
+    linear_tables(W, kNetW, sx, ax, true);
+    linear_tables(H, kNetH, sy, ay, false);
+    cudaMemcpy(c->d_lut_hist, lh.data(), 512, cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_lut_cur, lc.data(), 512, cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_lut_f32, lf.data(), 1024, cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_sx, sx.data(), kNetW * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_sy, sy.data(), kNetH * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_ax, ax.data(), kNetW * 4, cudaMemcpyHostToDevice);
+    rc = check_cuda(cudaMemcpy(c->d_ay, ay.data(), kNetH * 4, cudaMemcpyHostToDevice), "table upload", __FILE__, __LINE__);
+  }
+  if (rc != OFS_OK) { ofs_clips_destroy(c); return rc; }
+  *out = c;
+  return OFS_OK;
+}
+
+int ofs_clips_destroy(ofs_clips* c) {
+  if (!c) return OFS_OK;
+  cudaSetDevice(c->device);
+  if (c->st) { cudaStreamSynchronize(c->st); }
+  if (c->graph) cudaGraphExecDestroy(c->graph);
+  if (c->st) cudaStreamDestroy(c->st);
+  for (void* p : c->allocs) cudaFree(p);
+  delete c;
+  return OFS_OK;
+}
+
+int ofs_clips_reset(ofs_clips* c) {
+  OFS_REQUIRE(c, "ofs_clips_reset: null handle");
+  c->frame = 0;
+  return OFS_OK;
+}
+
+long long ofs_clips_frame_index(const ofs_clips* c) { return c ? c->frame : -1; }
+
+int ofs_clips_step_host(ofs_clips* c, const uint8_t* frames_bgr, uint8_t* out_bgr_u8, float* out_bgr_f32) {
+  OFS_REQUIRE(c && frames_bgr && out_bgr_u8, "ofs_clips_step_host: null pointer");
+  if (!net_loaded(c->net)) { set_error("ofs_clips_step_host: weights not loaded"); return OFS_ESTATE; }
+  OFS_CUDA(cudaSetDevice(c->device));
+  const size_t fpx = (size_t)c->n * c->H * c->W * 3;
+  const bool want_f32 = out_bgr_f32 != nullptr;
+  StepState s = {};
+  const long long i = c->frame;
+  for (int j = 0; j < 8; ++j) s.hist_slot[j] = (int)(std::max<long long>(i - kOffsets[j], 0) % kRing);
+  s.write_slot = (int)(i % kRing);
+  s.first = i == 0;
+  cudaStream_t st = c->st;
+  OFS_CUDA(cudaMemcpyAsync(c->d_state, &s, sizeof(s), cudaMemcpyHostToDevice, st));
+  OFS_CUDA(cudaMemcpyAsync(c->d_frame, frames_bgr, fpx, cudaMemcpyHostToDevice, st));
+  if (!c->graph || c->graph_f32 != want_f32) {
+    if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
+    int rc = net_prepare(c->net, c->n);
+    if (rc != OFS_OK) return rc;
+    const uint64_t l0 = launch_count();
+    OFS_CUDA(cudaStreamSynchronize(st));   // the state / frame copies above are not part of the graph
+    OFS_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_step(c, st, want_f32);
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &g);
+    c->graph_launches = (int)(launch_count() - l0);
+    count_launch(-c->graph_launches);
+    if (rc != OFS_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    OFS_CUDA(ce);
+    const cudaError_t ie = cudaGraphInstantiate(&c->graph, g, 0);
+    cudaGraphDestroy(g);
+    OFS_CUDA(ie);
+    c->graph_f32 = want_f32;
+  }
+  OFS_CUDA(cudaGraphLaunch(c->graph, st));
+  count_launch(c->graph_launches);
+  OFS_CUDA(cudaMemcpyAsync(out_bgr_u8, c->d_out_u8, fpx, cudaMemcpyDeviceToHost, st));
+  if (want_f32) OFS_CUDA(cudaMemcpyAsync(out_bgr_f32, c->d_out_f32, fpx * 4, cudaMemcpyDeviceToHost, st));
+  OFS_CUDA(cudaStreamSynchronize(st));
+  ++c->frame;
+  return OFS_OK;
+}
+
+}  // extern "C"

@@ -441,6 +441,8 @@ struct Marks {
     }                                                    \
   } while (0)
 
+// feats == kFromX0: the packed 16-bit input buffer x0 has already been filled on the device (clip driver)
+const float* const kFromX0 = reinterpret_cast<const float*>(uintptr_t(1));
 int forward_impl(ofs_net* n, const float* feats, int B, float* f2_target, cudaStream_t st, Marks* marks = nullptr) {
   OFS_REQUIRE(n && feats, "ofs_net_forward: null pointer");
   OFS_REQUIRE(B >= 1 && B <= n->max_batch, "ofs_net_forward: batch %d outside [1, %d]", B, n->max_batch);
@@ -452,8 +454,10 @@ int forward_impl(ofs_net* n, const float* feats, int B, float* f2_target, cudaSt
   int rc = prepare(n, B);
   if (rc != OFS_OK) return rc;
   OFS_MARK("start", 0.0);
-  rc = launch_pack_act(feats, n->x0, (size_t)B * kNetH * kNetW, kNetC, 32, n->is_bf16, st);
-  if (rc != OFS_OK) return rc;
+  if (feats != kFromX0) {
+    rc = launch_pack_act(feats, n->x0, (size_t)B * kNetH * kNetW, kNetC, 32, n->is_bf16, st);
+    if (rc != OFS_OK) return rc;
+  }
   OFS_MARK("pack_input", 0.0);
   for (Layer& L : n->layers) {
     int lvl = 0;
@@ -488,6 +492,22 @@ int forward_impl(ofs_net* n, const float* feats, int B, float* f2_target, cudaSt
 }
 
 }  // namespace
+
+// ---- internal interface for the clip driver (clip.cu) -------------------------------------------------------------
+namespace ofs {
+void* net_x0(ofs_net* n) { return n->x0; }
+int net_max_batch(const ofs_net* n) { return n->max_batch; }
+int net_is_bf16(const ofs_net* n) { return n->is_bf16; }
+int net_device(const ofs_net* n) { return n->device; }
+bool net_loaded(const ofs_net* n) { return n->loaded; }
+int net_prepare(ofs_net* n, int B) { return prepare(n, B); }
+// forward from the pre-filled x0 + fused flow glue / warp of frames -> out (all device pointers), on `st`
+int net_stabilize_from_x0(ofs_net* n, const float* frames, float* out, int B, int H, int W, cudaStream_t st) {
+  int rc = forward_impl(n, kFromX0, B, nullptr, st);
+  if (rc != OFS_OK) return rc;
+  return flow_resize_warp_impl(frames, n->f2s, out, B, H, W, 382, 510, st, 1);
+}
+}  // namespace ofs
 
 extern "C" {
 

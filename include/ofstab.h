@@ -158,6 +158,24 @@ int ofs_net_time_kernels(ofs_net* net, int which, const float* frames, float* ou
 int ofs_net_launches_per_forward(const ofs_net* net);
 
 /* ------------------------------------------------------------------------------------------
+ * Clip driver (SURVEY 8(f) "next" row 1): the per-frame loop of evaluate_originalSize(), main_dl.py:535-630, with its
+ * state on the device.  n_clips clips of H x W frames advance in lockstep as one batch (n_clips <= the net's
+ * max_batch; the faithful single-clip loop is n_clips = 1).  Per clip the handle keeps a 32-slot ring of the
+ * resized (512x384, cv2.resize INTER_LINEAR fixed-point arithmetic), channel-swapped np.uint8 outputs; one step =
+ * one iteration of the reference loop body: curinput assembly (main_dl.py:544-558: 8 history taps at offsets
+ * 31,23,15,7,4,3,2,1 with the frame-0 clamp, + the current frame), sess.run (:569), totaloutputFrame[i] (:625).
+ *   frames_bgr   host uint8 [n_clips,H,W,3]: cap.read() of every clip (BGR)
+ *   out_bgr_u8   host uint8 [n_clips,H,W,3]: np.uint8(totaloutputFrame[i]), what out.write() receives (:630)
+ *   out_bgr_f32  host float32 [n_clips,H,W,3] or NULL: totaloutputFrame[i] itself (BGR, 0..255, not clipped)
+ * Synchronous; 3 bytes per pixel cross PCIe each way instead of 32 MB + 11 MB of float32 per 720p frame. */
+typedef struct ofs_clips ofs_clips;
+int ofs_clips_create(ofs_clips** clips, ofs_net* net, int n_clips, int H, int W);
+int ofs_clips_destroy(ofs_clips* clips);
+int ofs_clips_reset(ofs_clips* clips); /* next step is frame 0 again */
+long long ofs_clips_frame_index(const ofs_clips* clips);
+int ofs_clips_step_host(ofs_clips* clips, const uint8_t* frames_bgr, uint8_t* out_bgr_u8, float* out_bgr_f32);
+
+/* ------------------------------------------------------------------------------------------
  * Stand-alone implicit-GEMM convolution on the same tcgen05 kernel the network uses (unit
  * tests, micro-benchmarks):  y = act(conv2d(zero_pad(x, k/2), W, stride) + b), NHWC.
  *   x [B,H,W,Cin] dev f32, w host [k,k,Cin,Cout] f32, b host [Cout] f32 (may be NULL),

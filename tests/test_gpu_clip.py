@@ -1,0 +1,86 @@
+"""Clip driver against a literal replay of the reference loop body,
+main_flownetS_pyramid_noprevloss_dataloader.py:540-630, with cv2 / numpy on the host and sess.run replaced by the
+(already parity-tested) fused GPU step.  The device-side driver must reproduce the written uint8 frames and the
+float32 history byte for byte: same cv2.resize fixed-point arithmetic, same /255 variants, same np.uint8 cast."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import flownet as F
+
+cv2 = pytest.importorskip("cv2")
+pytestmark = pytest.mark.gpu
+
+STABIDXS = [31, 23, 15, 7, 4, 3, 2, 1]                                              # main_dl.py:553
+
+
+@pytest.fixture(scope="module")
+def ofs(cuda_dev):
+    import coupe.optical_flow_based_deep_video_stabilization_b200 as m
+
+    m.load_library()
+    return m
+
+
+def reference_loop(net, frames, dev):
+    """frames: uint8 [T,H,W,3] BGR (what cap.read() returns).  Returns (written uint8 [T,H,W,3], totaloutputFrame)."""
+    T, out_h, out_w, _ = frames.shape
+    total = np.zeros([T, out_h, out_w, 3])                                           # :535 (float64)
+    written = np.zeros([T, out_h, out_w, 3], np.uint8)
+    for i in range(T):                                                               # :540
+        curinput = np.zeros([1, 384, 512, 27])                                       # :544
+        frame_unstab = frames[i]                                                     # :547
+        if i == 0:
+            total[0] = frame_unstab                                                  # :548-549
+        curinput[0, :, :, 24:27] = cv2.cvtColor(cv2.resize(frame_unstab, (512, 384)), cv2.COLOR_RGB2BGR) / 255.0   # :550
+        for j in range(len(STABIDXS)):                                               # :554-558
+            idx = 0 if i - STABIDXS[j] < 0 else i - STABIDXS[j]
+            with np.errstate(invalid="ignore"):
+                hist = np.uint8(total[idx])
+            curinput[0, :, :, j * 3:(j + 1) * 3] = np.float32(cv2.cvtColor(cv2.resize(hist, (512, 384)), cv2.COLOR_RGB2BGR)) / 255.0
+        resized = np.expand_dims(cv2.cvtColor(frame_unstab, cv2.COLOR_RGB2BGR) / 255.0, axis=0)                     # :568
+        feats = torch.from_numpy(curinput.astype(np.float32)).to(dev)                # feed_dict -> float32 placeholders
+        frame = torch.from_numpy(resized.astype(np.float32)).to(dev)
+        curwarpedimg = net.stabilize(feats, frame).cpu().numpy()                     # :569 sess.run(outputs_warpedimg)
+        total[i] = cv2.cvtColor(np.squeeze(curwarpedimg) * 255, cv2.COLOR_RGB2BGR)   # :625
+        with np.errstate(invalid="ignore"):
+            written[i] = np.uint8(total[i])                                          # :630 out.write(...)
+    return written, total
+
+
+def synth_clip(seed, T, H, W):
+    """A smooth, slowly drifting scene with frame-to-frame jitter: values stay well inside [0, 255]."""
+    rng = np.random.default_rng(seed)
+    base = cv2.GaussianBlur(rng.integers(0, 256, (H + 32, W + 32, 3)).astype(np.float32), (0, 0), 3.0)
+    base = (base - base.min()) / (base.max() - base.min()) * 200 + 25
+    out = np.zeros((T, H, W, 3), np.uint8)
+    for i in range(T):
+        dy, dx = rng.integers(0, 9, 2) + 8
+        out[i] = base[dy:dy + H, dx:dx + W].astype(np.uint8)
+    return out
+
+
+@pytest.mark.parametrize("n_clips,T,H,W", [(1, 36, 96, 128), (2, 8, 120, 160)], ids=["one_clip_ring_wraps", "two_clips_lockstep"])
+def test_clip_driver_matches_reference_loop(ofs, cuda_dev, n_clips, T, H, W):
+    w = F.make_weights(0, "calibrated", head_scale=0.02)
+    net = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=max(2, n_clips))
+    net.assign_weights(w)
+    clips = [synth_clip(100 + c, T, H, W) for c in range(n_clips)]
+    want = [reference_loop(net, clip, cuda_dev) for clip in clips]
+    stab = ofs.ClipStabilizer(net, n_clips=n_clips, height=H, width=W)
+    for i in range(T):
+        frames = np.stack([clip[i] for clip in clips])
+        got_u8, got_f32 = stab.step(frames, return_float=True)
+        assert stab.frame_index == i + 1
+        for c in range(n_clips):
+            np.testing.assert_array_equal(got_u8[c], want[c][0][i], err_msg=f"clip {c} frame {i}: written frame")
+            np.testing.assert_array_equal(got_f32[c], want[c][1][i].astype(np.float32), err_msg=f"clip {c} frame {i}: history")
+    # reset starts the clip over and reproduces frame 0
+    stab.reset()
+    again = stab.step(np.stack([clip[0] for clip in clips]))
+    for c in range(n_clips):
+        np.testing.assert_array_equal(again[c], want[c][0][0])
+    with pytest.raises(ValueError):
+        stab.step(np.zeros((n_clips, H + 1, W, 3), np.uint8))
+    stab.close()
+    net.close()
