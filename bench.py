@@ -263,6 +263,25 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = world * BATCH * e2e_steps / float(dt.item())
+    # ---- the same loop through the device-side clip driver: uint8 frames in and out, history ring
+    # on the device -- BATCH clips in lockstep, one reference loop iteration per step
+    import numpy as np
+    clip_steps = max(5, min(args.steps, 40))
+    stab = ofs.ClipStabilizer(net, n_clips=BATCH, height=FRAME_H, width=FRAME_W)
+    u8, u8_out = stab.pinned_buffer(), stab.pinned_buffer()
+    u8[...] = np.random.default_rng(7 + rank).integers(0, 256, u8.shape, dtype=np.uint8)
+    for _ in range(3):
+        stab.step(u8, out=u8_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(clip_steps):
+        stab.step(u8, out=u8_out)
+    barrier()
+    dtc = torch.tensor([time.perf_counter() - t0], device=dev)
+    if dist is not None:
+        dist.all_reduce(dtc, op=dist.ReduceOp.MAX)
+    clip_value = world * BATCH * clip_steps / float(dtc.item())
+    stab.close()
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
@@ -283,6 +302,9 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hf.numel() * 4 + hfr.numel() * 4),
                     "d2h_bytes_per_step": int(hout.numel() * 4), "steps": e2e_steps,
                     "api": "ofs_net_stabilize_host (C ABI, pinned host float32 buffers)"},
+            "e2e_clip_driver": {"value": clip_value, "unit": UNIT, "h2d_bytes_per_step": int(u8.nbytes), "d2h_bytes_per_step": int(u8.nbytes),
+                                "steps": clip_steps, "api": "ofs_clips_step_host (uint8 BGR frames in / out, device-side history ring; "
+                                "one iteration of main_dl.py:540-630 per clip per step, pinned host buffers)"},
             "gpu_launches": launches, "launches_per_step": launches // max(args.steps, 1),
             "clocks": clocks, "roofline": roofline, "roofline_warp": roofline_warp, "cpu_baseline": cpu,
             "breakdown": breakdown, "lib": os.path.relpath(ofs.lib_path(), ROOT),

@@ -45,17 +45,28 @@ class ClipStabilizer:
     def reset(self):
         _lib.check(self._lib.ofs_clips_reset(self._h))
 
-    def step(self, frames_bgr, return_float=False):
+    def pinned_buffer(self):
+        """A page-locked uint8 [n_clips,H,W,3] numpy array: frames decoded straight into it (and outputs written into
+        one) cross PCIe at full speed; pageable arrays are staged by the driver at a fraction of it."""
+        import torch
+
+        return torch.empty((self.n, self.h, self.w, 3), dtype=torch.uint8).pin_memory().numpy()
+
+    def step(self, frames_bgr, return_float=False, out=None):
         """frames_bgr: uint8 [H,W,3] (one clip) or [n_clips,H,W,3], BGR as cap.read() returns them.
         Returns np.uint8(totaloutputFrame[i]) with the same leading shape (and totaloutputFrame[i] as float32
-        when return_float)."""
+        when return_float).  `out`: optional uint8 [n_clips,H,W,3] array to receive the frames (e.g. pinned_buffer())."""
         a = np.ascontiguousarray(frames_bgr, dtype=np.uint8)
         single = a.ndim == 3
         if single:
             a = a[None]
         if a.shape != (self.n, self.h, self.w, 3):
             raise ValueError(f"frames must be uint8 [{self.n},{self.h},{self.w},3], got {a.shape}")
-        out = np.empty_like(a)
+        if out is not None:
+            if out.dtype != np.uint8 or out.shape != a.shape or not out.flags["C_CONTIGUOUS"]:
+                raise ValueError("out must be a C-contiguous uint8 array of the frames' shape")
+        else:
+            out = np.empty_like(a)
         outf = np.empty(a.shape, np.float32) if return_float else None
         _lib.check(self._lib.ofs_clips_step_host(self._h, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
                                                  outf.ctypes.data_as(C.c_void_p) if return_float else None))
