@@ -41,8 +41,8 @@ DENSE_GFLOP_PER_PAIR = 37.89      # 10 encoder convs + 4 transposed
 WARP_BYTES_PER_PX = 24.0          # fused flow-resize+warp: image 12 + out 12 (+1.56 MB of flow2 per frame)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch (set) from the committed ncu --set full capture of this
 # workload (profiles/r01_ncu_full_summary.md); refreshed by hand when the capture is
-NCU_TRAFFIC_DENSE_SET_BYTES = 448.0e6   # 14 dense GEMM launches + 4 split-K reductions, batch 8
-NCU_TRAFFIC_WARP_BYTES = 146.6e6        # warp5_kernel<true>, 8 x 720p
+NCU_TRAFFIC_DENSE_SET_BYTES = 451.0e6   # 14 dense GEMM launches + 4 split-K reductions, batch 8
+NCU_TRAFFIC_WARP_BYTES = 146.2e6        # warp5_kernel<true>, 8 x 720p
 FLOW2_BYTES = 382 * 510 * 2 * 4
 
 
@@ -288,7 +288,7 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            n_pairs = 4
+            n_pairs = 128                                   # ~10-15 s of CPU work on a 16-24 core host
             rate, secs = cpu_oracle_rate(torch, n_pairs, FRAME_H, FRAME_W, threads)
             cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{n_pairs} 720p frame pairs (batch 1 each) of the same step, fp32 torch-CPU oracle, {secs:.1f} s"}
