@@ -343,6 +343,25 @@ int prepare(ofs_net* n, int B) {
       return OFS_EINVAL;
     }
     if (L.d.slab) { cg = 2; bn = L.d.block_n; ks = 1; }   // the packed K order is the slab order: tiling is fixed
+    if (!tuned && !L.d.slab && ks == 1 && L.d.out_mode == 0) {
+      // small batches leave the wide-N tilings with a handful of tiles (conv4_1 at batch 1: 18): narrow the N tile
+      // until ~100 tiles exist.  The N tiling does not touch the K summation order, so results stay bit-identical
+      // across batch sizes (tests: batch independence).
+      auto tiles_for = [&](int b) {
+        ConvDesc d = L.d;
+        d.block_n = b;
+        d.cta_group = cg == 2 ? 2 : 1;
+        ConvPlan t;
+        if (conv_plan_geometry(t, d) != OFS_OK) return -1;
+        return t.p.tiles_mp * t.p.tiles_n * t.p.phases;
+      };
+      int t = tiles_for(bn);
+      for (int cand : {128, 64}) {
+        if (t >= 96 || cand >= bn) continue;
+        const int tc = tiles_for(cand);
+        if (tc > t) { bn = cand; t = tc; }
+      }
+    }
     if (cg == 8 && !L.d.slab) { L.d.kgroup = 2; cg = 1; }   // OFS_TUNE cta_group 8 = chunk groups
     if (L.d.kgroup == 2) { rc = conv_plan_geometry(L.plan, L.d); if (rc != OFS_OK) return rc; }
     if (ks > 1 || bn != L.d.block_n || cg == 2 || dbg) {
