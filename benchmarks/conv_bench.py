@@ -132,6 +132,10 @@ def main():
                 if nch and nch == nch and nch > 0:
                     line += ("\n           epilogue per 64-col chunk (cycles): ld+math+sts %.0f | tmem release+fence %.0f | wait_read %.0f | bar %.0f | issue %.0f  (%d chunks)"
                              % tuple([med(lambda r, k=k: r[k] / max(r[21], 1)) for k in (16, 17, 18, 19, 20)] + [nch]))
+                line += ("\n           per stage item (median CTA, %d items): MMA warp blocked on operands %.0f cyc, on a free accumulator %.0f cyc per item; "
+                         "producer blocked on a free stage %.0f cyc per item"
+                         % (med(lambda r: r[23]), med(lambda r: r[22] / max(r[23], 1)), med(lambda r: r[25] / max(r[23], 1)),
+                            med(lambda r: r[24] / max(r[23], 1))))
                 line += (f"\n           trace: span {span_ns / 1e3:.1f} us, start skew {start_skew / 1e3:.1f} us; cycles (median CTA): "
                          f"total {total:.0f} (max {tmax:.0f}) | producer done {prod:.0f} | first full {first_full:.0f} | "
                          f"mma issued {mma_done:.0f} | epi first {epi_first:.0f} | epi done {epi_done:.0f}")

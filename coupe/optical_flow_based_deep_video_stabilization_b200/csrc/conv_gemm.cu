@@ -297,7 +297,10 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
         while (ch < ch_end) {
           const int gn = kT > 1 ? (int)p.grp_n[ti] : 1;   // K blocks of this stage (slab group)
           const int gc = kG > 1 ? min(kG, ch_end - ch) : 1;   // 64-channel chunks of this stage (chunk group)
+          long long tw0 = 0;
+          if (trace) tw0 = clock64();
           lean::wait(empty_s, phase ^ 1);
+          if (trace && leader) trace[24] += clock64() - tw0;     // producer: cycles blocked on a free stage
           if (leader) {
             if (!kPair || rank == 0) lean::expect_tx(full_s, (uint32_t)gc * (a_tx + (uint32_t)gn * b_tx));
             for (int g = 0; g < gc; ++g) {
@@ -356,8 +359,11 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
       uint32_t full_s = full0, empty_s = empty0;
       uint32_t acc = 0, acc_phase = 0;
       for (int tile = unit; tile < total_tiles; tile += nunits) {
+        long long tt0 = 0;
+        if (trace) tt0 = clock64();
         lean::wait(tempty0 + 8 * acc, acc_phase ^ 1);
         ptx::tc_fence_after();
+        if (trace && leader) trace[25] += clock64() - tt0;       // MMA warp: cycles blocked on a free accumulator stage
         const uint32_t d_tmem = tmem_base + acc * kNB;
         const uint32_t idesc = (kHead && (tile % p.tiles_n) == p.tiles_n - 1) ? idesc_last : idesc_main;
         const int ks = tile / (p.tiles_n * p.tiles_mp * p.phases);
@@ -365,8 +371,11 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
         const int nkb = kG > 1 ? p.ntaps * ((p.nchunks + kG - 1) / kG)      // stage items per tile (chunk groups)
                                : min(num_kb, kb0 + p.kb_per_split) - kb0;
         for (int i = 0; i < nkb; ++i) {
+          long long tw0 = 0;
+          if (trace) tw0 = clock64();
           lean::wait(full_s, phase);
           ptx::tc_fence_after();
+          if (trace && leader) { trace[22] += clock64() - tw0; trace[23] += 1; }   // MMA warp: cycles blocked on operands
           if (trace && leader && tile == unit && i == 0) trace[3] = clock64();
           if (leader) {
             if (do_mma) {
