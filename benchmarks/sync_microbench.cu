@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(64, 1) k(int variant, int iters, int bn, const
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_slot;
   const uint32_t sbase = (s32(smem) + 1023u) & ~1023u;
-  const int stage_bytes = 32768;
+  const int stage_bytes = bn > 128 ? 49152 : 32768;   // A 16 KB + B 16 / 32 KB
   long long t0 = 0, t1 = 0;
   if (warp == 0 && lane == 0) {
     t0 = clock64();
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(64, 1) k(int variant, int iters, int bn, const
 
 template <int S>
 void run(int variant, int iters, int bn, const uint8_t* src, long long* out, int grid) {
-  const size_t smem = (size_t)S * 32768 + 2048;
+  const size_t smem = (size_t)S * (bn > 128 ? 49152 : 32768) + 2048;
   cudaFuncSetAttribute(k<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k<S><<<grid, 64, smem>>>(variant, iters, bn, src, out);
   cudaError_t e = cudaDeviceSynchronize();
@@ -146,9 +146,9 @@ int main() {
       run<6>(v, iters, bn, src, out, grid);
     }
     run<6>(2, iters, 64, src, out, grid);
-    run<6>(2, iters, 256, src, out, grid);
+    run<4>(2, iters, 256, src, out, grid);
     run<6>(5, iters, 64, src, out, grid);
-    run<6>(5, iters, 256, src, out, grid);
+    run<4>(5, iters, 256, src, out, grid);
   }
   return 0;
 }

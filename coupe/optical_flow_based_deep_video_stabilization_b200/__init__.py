@@ -10,6 +10,7 @@ No CPU fallback, no Triton, no backend dispatch: importing is cheap, the first d
 """
 from ._lib import OfstabError, lib_path, load as load_library            # noqa: F401
 from .clip import ClipStabilizer                                                               # noqa: F401
+from .driver import stabilize_video                                                            # noqa: F401
 from .model import (FlowNetSPyramid, assign_weights, flownetS_pyramid, get_net,                 # noqa: F401
                     load_and_assign_npz_dict)
 from .ops import (conv2d_nhwc, flow_resize, flow_resize_warp, get_pixel_value, set_warp_variant,  # noqa: F401
@@ -23,6 +24,6 @@ __all__ = [
     "tf_warp", "get_pixel_value", "flow_resize", "flow_resize_warp", "set_warp_variant", "conv2d_nhwc",
     "AffineTransformer", "ProjectiveTransformer", "transformer",
     "vec2mtrx", "transformImage", "transformCropImage", "fit", "compose", "inverse",
-    "shard_range", "gather_output", "ClipStabilizer",
+    "shard_range", "gather_output", "ClipStabilizer", "stabilize_video",
     "OfstabError", "lib_path", "load_library",
 ]

@@ -84,3 +84,42 @@ def test_clip_driver_matches_reference_loop(ofs, cuda_dev, n_clips, T, H, W):
         stab.step(np.zeros((n_clips, H + 1, W, 3), np.uint8))
     stab.close()
     net.close()
+
+
+def test_stabilize_video_file_boundary(ofs, cuda_dev, tmp_path):
+    """evaluate_originalSize()'s file handling (main_dl.py:477-487, :540-547, :630-632): MJPG AVI in, MJPG AVI out,
+    CAP_PROP_FRAME_COUNT - 2 frames, each equal to what the clip driver returns for the decoded frames."""
+    T, H, W = 12, 96, 128
+    clip = synth_clip(7, T, H, W)
+    src, dst = str(tmp_path / "in.avi"), str(tmp_path / "result_video" / "in_out.avi")
+    wr = cv2.VideoWriter(src, cv2.VideoWriter_fourcc("M", "J", "P", "G"), 30.0, (W, H))
+    assert wr.isOpened()
+    for f in clip:
+        wr.write(f)
+    wr.release()
+    w = F.make_weights(0, "calibrated", head_scale=0.02)
+    net = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=1)
+    net.assign_weights(w)
+    n = ofs.stabilize_video(src, dst, net=net)
+    assert n == T - 2                                                                # :479
+    # expected: the clip driver on the DECODED frames (MJPG is lossy), re-encoded by the same writer
+    cap = cv2.VideoCapture(src)
+    decoded = [cap.read()[1] for _ in range(T - 2)]
+    cap.release()
+    stab = ofs.ClipStabilizer(net, n_clips=1, height=H, width=W)
+    want = [stab.step(f) for f in decoded]
+    stab.close()
+    ref_path = str(tmp_path / "ref.avi")
+    wr = cv2.VideoWriter(ref_path, cv2.VideoWriter_fourcc("M", "J", "P", "G"), 30.0, (W, H))
+    for f in want:
+        wr.write(f)
+    wr.release()
+    a, b = cv2.VideoCapture(dst), cv2.VideoCapture(ref_path)
+    assert int(a.get(7)) == T - 2 and int(a.get(3)) == W and int(a.get(4)) == H and abs(a.get(5) - 30.0) < 1e-6
+    for _ in range(T - 2):
+        ra, fa = a.read()
+        rb, fb = b.read()
+        assert ra and rb
+        np.testing.assert_array_equal(fa, fb)
+    a.release(); b.release()
+    net.close()
