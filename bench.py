@@ -184,16 +184,26 @@ def run_ours(args):
     lib = ofs.load_library()
     peaks = load_peaks()
 
-    net = ofs.FlowNetSPyramid(device=dev, max_batch=BATCH, precision=args.precision)
-    net.assign_weights(F.make_weights(0, "calibrated", head_scale=0.02))
-    # two input sets alternate so no step re-reads what the previous one left in the 126 MB L2
-    sets = [synth_inputs(torch, 100 + rank * 2 + i, BATCH, FRAME_H, FRAME_W, device=dev) for i in range(2)]
-    outs = [torch.empty_like(sets[0][1]) for _ in range(2)]
+    weights = F.make_weights(0, "calibrated", head_scale=0.02)
+    # Frame-pair batches are independent, and the step is a chain of 26 kernels several of which leave SMs idle (192
+    # tiles on 148 SMs, the M <= 1536 layers): `--streams` batches are kept in flight on as many CUDA streams, each
+    # with its own net instance (weights + activation workspace), and fill those holes (+17 % at 2 streams).
+    nstreams = max(1, args.streams)
+    nets = [ofs.FlowNetSPyramid(device=dev, max_batch=BATCH, precision=args.precision) for _ in range(nstreams)]
+    for n_ in nets:
+        n_.assign_weights(weights)
+    net = nets[0]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
+    # 2 input sets per stream alternate so no step re-reads what an earlier one left in the 126 MB L2
+    nsets = 2 * nstreams
+    sets = [synth_inputs(torch, 100 + rank * nsets + i, BATCH, FRAME_H, FRAME_W, device=dev) for i in range(nsets)]
+    outs = [torch.empty_like(sets[0][1]) for _ in range(nsets)]
 
     def step(i):
-        feats, frames = sets[i & 1]
-        ofs._lib.check(lib.ofs_net_stabilize(net._h, ofs._lib.ptr(feats), ofs._lib.ptr(frames), ofs._lib.ptr(outs[i & 1]),
-                                             None, BATCH, FRAME_H, FRAME_W, ofs._lib.current_stream_ptr(dev)))
+        k, j = i % nstreams, i % nsets
+        feats, frames = sets[j]
+        ofs._lib.check(lib.ofs_net_stabilize(nets[k]._h, ofs._lib.ptr(feats), ofs._lib.ptr(frames), ofs._lib.ptr(outs[j]),
+                                             None, BATCH, FRAME_H, FRAME_W, streams[k].cuda_stream))
 
     def barrier():
         torch.cuda.synchronize()
@@ -201,31 +211,50 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
+    def timed_steps(nsteps):
+        """ms from one event on the current stream (every step stream waits for it) to the LAST step stream's end."""
+        e0 = torch.cuda.Event(enable_timing=True)
+        ends = [torch.cuda.Event(enable_timing=True) for _ in streams]
+        e0.record(torch.cuda.current_stream())
+        for s in streams:
+            s.wait_event(e0)
+        for i in range(nsteps):
+            step(i)
+        for s, e in zip(streams, ends):
+            e.record(s)
+        torch.cuda.synchronize()
+        return max(e0.elapsed_time(e) for e in ends)
+
+    for i in range(max(args.warmup, 3) * nstreams):
         step(i)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     l0 = lib.ofs_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    e1.record()
+    ms_local = timed_steps(args.steps)
     barrier()
     launches = int(lib.ofs_launch_count() - l0)
-    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    ms_total = torch.tensor([ms_local], device=dev)
     if dist is not None:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
     ms_total = float(ms_total.item())
     value = world * BATCH * args.steps / (ms_total * 1e-3)
+    # the same K steps strictly one after the other on one stream (what a single synchronous caller gets)
+    single_ms = None
+    if nstreams > 1:
+        nstreams_saved, nstreams = nstreams, 1
+        streams_saved, streams = streams, streams[:1]
+        barrier()
+        single_ms = timed_steps(args.steps)
+        nstreams, streams = nstreams_saved, streams_saved
+        barrier()
 
     # ---- per-kernel breakdown, measured live with CUDA events on the launching stream (rank 0)
     roofline = roofline_warp = breakdown = None
     if rank == 0:
         prof = net.profile(sets[0][0], sets[0][1], iters=max(3, min(args.steps, 10)))
-        step_ms = ms_total / args.steps
+        step_ms = (single_ms if single_ms else ms_total) / args.steps   # shares refer to one step executed alone
         # dominant kernel = the tcgen05 implicit-GEMM conv: its 14 launches per step (plus split-K reductions) are
         # replayed from one CUDA graph, exactly as the step runs them, between two CUDA events on the net's stream
         gemm_ms, macs, gemm_launches = net.time_kernels("dense", BATCH, iters=20)
@@ -249,15 +278,36 @@ def run_ours(args):
         breakdown = [{"kernel": n, "ms": round(ms, 4), "tflops": (2 * m / (ms * 1e-3) / 1e12 if m else None)} for n, ms, m in prof]
 
     # ---- e2e: the C-ABI host-buffer call, pinned host inputs, H2D + compute + D2H every step
-    hf, hfr = synth_inputs(torch, 300 + rank, BATCH, FRAME_H, FRAME_W, pinned=True)
-    hout = torch.empty_like(hfr).pin_memory()
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        net.stabilize_host(hf, hfr, hout)
+    # `--streams` caller threads, each with its own net and pinned buffers, call the synchronous C-ABI entry point
+    # concurrently (ctypes drops the GIL): one call's D2H tail overlaps the next call's H2D
+    host_sets = []
+    for k in range(nstreams):
+        hf, hfr = synth_inputs(torch, 300 + rank * nstreams + k, BATCH, FRAME_H, FRAME_W, pinned=True)
+        host_sets.append((hf, hfr, torch.empty_like(hfr).pin_memory()))
+    hf, hfr, hout = host_sets[0]
+    e2e_steps = max(4, min(args.steps, 12))
+    e2e_steps -= e2e_steps % nstreams
+
+    def e2e_worker(k, nsteps):
+        torch.cuda.set_device(local)
+        f_, fr_, o_ = host_sets[k]
+        for _ in range(nsteps):
+            nets[k].stabilize_host(f_, fr_, o_)
+
+    def e2e_run(nsteps_total):
+        if nstreams == 1:
+            e2e_worker(0, nsteps_total)
+            return
+        ts = [threading.Thread(target=e2e_worker, args=(k, nsteps_total // nstreams)) for k in range(nstreams)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+
+    e2e_run(2 * nstreams)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        net.stabilize_host(hf, hfr, hout)
+    e2e_run(e2e_steps)
     barrier()
     dt = torch.tensor([time.perf_counter() - t0], device=dev)
     if dist is not None:
@@ -266,22 +316,43 @@ def run_ours(args):
     # ---- the same loop through the device-side clip driver: uint8 frames in and out, history ring
     # on the device -- BATCH clips in lockstep, one reference loop iteration per step
     import numpy as np
-    clip_steps = max(5, min(args.steps, 40))
-    stab = ofs.ClipStabilizer(net, n_clips=BATCH, height=FRAME_H, width=FRAME_W)
-    u8, u8_out = stab.pinned_buffer(), stab.pinned_buffer()
-    u8[...] = np.random.default_rng(7 + rank).integers(0, 256, u8.shape, dtype=np.uint8)
-    for _ in range(3):
-        stab.step(u8, out=u8_out)
+    clip_steps = max(6, min(args.steps, 40))
+    clip_steps -= clip_steps % nstreams
+    stabs = [ofs.ClipStabilizer(nets[k], n_clips=BATCH, height=FRAME_H, width=FRAME_W) for k in range(nstreams)]
+    clip_bufs = []
+    for k, stab in enumerate(stabs):
+        u8, u8_out = stab.pinned_buffer(), stab.pinned_buffer()
+        u8[...] = np.random.default_rng(7 + rank * nstreams + k).integers(0, 256, u8.shape, dtype=np.uint8)
+        clip_bufs.append((u8, u8_out))
+
+    def clip_worker(k, nsteps):
+        torch.cuda.set_device(local)
+        u8_, out_ = clip_bufs[k]
+        for _ in range(nsteps):
+            stabs[k].step(u8_, out=out_)
+
+    def clip_run(nsteps_total):
+        if nstreams == 1:
+            clip_worker(0, nsteps_total)
+            return
+        ts = [threading.Thread(target=clip_worker, args=(k, nsteps_total // nstreams)) for k in range(nstreams)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+
+    clip_run(3 * nstreams)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(clip_steps):
-        stab.step(u8, out=u8_out)
+    clip_run(clip_steps)
     barrier()
     dtc = torch.tensor([time.perf_counter() - t0], device=dev)
     if dist is not None:
         dist.all_reduce(dtc, op=dist.ReduceOp.MAX)
     clip_value = world * BATCH * clip_steps / float(dtc.item())
-    stab.close()
+    for stab in stabs:
+        stab.close()
+    u8 = clip_bufs[0][0]
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
@@ -297,20 +368,25 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": workload_name(), "pairs_per_step_per_gpu": BATCH, "frame": [FRAME_H, FRAME_W],
-                       "net_input": [384, 512, 27], "l2": "two alternating input sets, 258 MB each (> 126 MB L2)",
-                       "parallelism": f"replicas x{world}, no data-path collective"},
+                       "net_input": [384, 512, 27], "l2": f"{nsets} alternating input sets, 258 MB each (> 126 MB L2)",
+                       "steps_in_flight": nstreams,
+                       "parallelism": f"replicas x{world}, no data-path collective; {nstreams} independent batches in flight per GPU "
+                                      f"on {nstreams} CUDA streams"},
+            "value_one_step_at_a_time": (world * BATCH * args.steps / (single_ms * 1e-3)) if single_ms else None,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hf.numel() * 4 + hfr.numel() * 4),
                     "d2h_bytes_per_step": int(hout.numel() * 4), "steps": e2e_steps,
-                    "api": "ofs_net_stabilize_host (C ABI, pinned host float32 buffers)"},
+                    "api": f"ofs_net_stabilize_host (C ABI, pinned host float32 buffers), {nstreams} concurrent caller thread(s)"},
             "e2e_clip_driver": {"value": clip_value, "unit": UNIT, "h2d_bytes_per_step": int(u8.nbytes), "d2h_bytes_per_step": int(u8.nbytes),
                                 "steps": clip_steps, "api": "ofs_clips_step_host (uint8 BGR frames in / out, device-side history ring; "
-                                "one iteration of main_dl.py:540-630 per clip per step, pinned host buffers)"},
+                                f"one iteration of main_dl.py:540-630 per clip per step, pinned host buffers), {nstreams} clip set(s) of {BATCH} "
+                                       "stepped by concurrent caller threads"},
             "gpu_launches": launches, "launches_per_step": launches // max(args.steps, 1),
             "clocks": clocks, "roofline": roofline, "roofline_warp": roofline_warp, "cpu_baseline": cpu,
             "breakdown": breakdown, "lib": os.path.relpath(ofs.lib_path(), ROOT),
         }
         print(json.dumps(line), flush=True)
-    net.close()
+    for n_ in nets:
+        n_.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -323,6 +399,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--precision", choices=["bf16", "fp16"], default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=2, help="independent batches in flight per GPU (1 = strictly sequential steps)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
