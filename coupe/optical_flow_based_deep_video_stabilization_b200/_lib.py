@@ -64,6 +64,7 @@ PROTOTYPES = {
 # host-only introspection used by the CPU test-suite (not part of the product API)
 DEBUG_PROTOTYPES = {
     "ofs_debug_conv_plan": (_i, [_i] * 11 + [_p, _p, _p, _p, _p, _ll, _p]),
+    "ofs_debug_conv_plan_ex": (_i, [_i] * 12 + [_p, _p, _p, _p, _p, _p, _p, _ll, _p]),
     "ofs_debug_cvt16": (C.c_uint, [_f, _i]),
 }
 

@@ -1602,4 +1602,51 @@ extern "C" int ofs_debug_conv_plan(int kind, int B, int H, int W, int cin, int i
   return OFS_OK;
 }
 
+// Same for the slab-group and fused-head variants: flags bit0 = slab groups (CTA pairs), bit1 = fused 3x3 head.
+// info[48] = the 44 values of ofs_debug_conv_plan + slab_extra, w_rows_phase, group_max, tiles_mp; grp[64*5] = per table
+// entry {taps in the group, 4 row offsets}; head_w [3,3,cin,2] when bit1.
+extern "C" int ofs_debug_conv_plan_ex(int kind, int B, int H, int W, int cin, int in_cs, int cout, int k, int stride,
+                                      int block_n, int is_bf16, int flags, const float* w_tf, const float* bias,
+                                      const float* head_w, int* info /*[48]*/, short* taps /*[4][64]*/,
+                                      short* grp /*[64][5]*/, uint16_t* w_packed, long long w_cap, float* b_padded) {
+  using namespace ofs;
+  ConvDesc d;
+  d.kind = kind ? kDeconvK4S2 : kConv;
+  d.B = B; d.H = H; d.W = W; d.cin = cin; d.in_cs = in_cs; d.cout = cout; d.k = k; d.stride = stride;
+  d.block_n = block_n; d.out_mode = 0; d.lrelu = 0; d.is_bf16 = is_bf16; d.out_cstride = ((cout + 7) / 8) * 8; d.out_coff = 0;
+  d.slab = flags & 1; d.head = (flags >> 1) & 1; d.cta_group = (flags & 1) ? 2 : 1;
+  ConvPlan plan;
+  int rc = conv_plan_geometry(plan, d);
+  if (rc != OFS_OK) return rc;
+  const ConvGemmParams& p = plan.p;
+  unsigned long long vd[5], vs[4];
+  conv_act_view(d, vd, vs);
+  const int vals[] = {p.Hg, p.Wg, p.rows_total, p.tileW_log2, p.tile_rows, p.piece_rows, p.tiles_x, p.tiles_m, p.tiles_n, p.phases,
+                      p.ntaps, p.nchunks, p.n_pad, plan.k_total, plan.w_rows, plan.paired ? 1 : 0, p.out_scale, p.out_H,
+                      p.out_W, plan.grid, (int)vd[0], (int)vd[1], (int)vd[2], (int)vd[3], (int)vd[4], (int)(vs[0] / 2),
+                      (int)(vs[1] / 2), (int)(vs[2] / 2), (int)(vs[3] / 2), p.out_oy[0], p.out_oy[1], p.out_oy[2],
+                      p.out_oy[3], p.out_ox[0], p.out_ox[1], p.out_ox[2], p.out_ox[3], (int)plan.smem, p.npieces, p.box_y,
+                      p.box_b, p.a_bytes, p.ksplit, p.kb_per_split, p.slab ? p.slab_extra : 0, p.w_rows_phase, plan.group_max,
+                      p.tiles_mp};
+  static_assert(sizeof(vals) / sizeof(int) == 48, "info layout");
+  for (int i = 0; i < 48; ++i) info[i] = vals[i];
+  for (int i = 0; i < kMaxTapEntries; ++i) {
+    taps[0 * kMaxTapEntries + i] = p.tap_c[i];
+    taps[1 * kMaxTapEntries + i] = p.tap_x[i];
+    taps[2 * kMaxTapEntries + i] = p.tap_p[i];
+    taps[3 * kMaxTapEntries + i] = p.tap_y[i];
+    grp[i * 5] = p.slab ? p.grp_n[i] : 1;
+    for (int t = 0; t < 4; ++t) grp[i * 5 + 1 + t] = p.slab ? p.grp_off[i][t] : 0;
+  }
+  if (w_tf && w_packed) {
+    std::vector<uint16_t> wp;
+    std::vector<float> bp;
+    conv_pack_weights(plan, w_tf, bias, wp, bp, head_w);
+    OFS_REQUIRE((long long)wp.size() <= w_cap, "ofs_debug_conv_plan_ex: w_packed capacity %lld < %zu", w_cap, wp.size());
+    memcpy(w_packed, wp.data(), wp.size() * 2);
+    if (b_padded) memcpy(b_padded, bp.data(), bp.size() * 4);
+  }
+  return OFS_OK;
+}
+
 extern "C" unsigned ofs_debug_cvt16(float f, int is_bf16) { return is_bf16 ? ofs::f32_to_bf16_rn(f) : ofs::f32_to_fp16_rn(f); }

@@ -185,3 +185,106 @@ def _accumulate(plan, act, out, written):
             y = gy - b * Hg
             out[b, y * plan["out_scale"] + oys[ph], gx * plan["out_scale"] + oxs[ph], n_t * BN:(n_t + 1) * BN] += acc[row]
     return out.astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# slab groups (conv1 / conv2) and the fused flow head (deconvs): same idea through ofs_debug_conv_plan_ex
+def get_plan_ex(lib, kind, B, H, W, cin, in_cs, cout, k, stride, block_n, w_tf, bias, slab=False, head_w=None):
+    info = (C.c_int * 48)()
+    taps = (C.c_short * 256)()
+    grp = (C.c_short * 320)()
+    cap = 4 * (cout + 256) * (k * k * (cin + 64) + 4096)
+    wbuf = np.zeros(cap, np.uint16)
+    bbuf = np.zeros(cout + 256, np.float32)
+    w_tf = np.ascontiguousarray(w_tf, np.float32)
+    bias = np.ascontiguousarray(bias, np.float32)
+    hw = None if head_w is None else np.ascontiguousarray(head_w, np.float32)
+    flags = (1 if slab else 0) | (2 if head_w is not None else 0)
+    rc = lib.ofs_debug_conv_plan_ex(kind, B, H, W, cin, in_cs, cout, k, stride, block_n, 1, flags,
+                                    w_tf.ctypes.data_as(C.c_void_p), bias.ctypes.data_as(C.c_void_p),
+                                    None if hw is None else hw.ctypes.data_as(C.c_void_p), C.cast(info, C.c_void_p),
+                                    C.cast(taps, C.c_void_p), C.cast(grp, C.c_void_p), wbuf.ctypes.data_as(C.c_void_p), cap,
+                                    bbuf.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError(lib.ofs_last_error().decode())
+    keys = INFO_KEYS + ["slab_extra", "w_rows_phase", "group_max", "tiles_mp"]
+    d = {k_: int(info[i]) for i, k_ in enumerate(keys)}
+    t = np.array(list(taps), np.int64).reshape(4, 64)
+    d["tap_c"], d["tap_x"], d["tap_p"], d["tap_y"] = t[0], t[1], t[2], t[3]
+    g = np.array(list(grp), np.int64).reshape(64, 5)
+    d["grp_n"], d["grp_off"] = g[:, 0], g[:, 1:]
+    d["w"] = bf16_bits_to_f32(wbuf[: d["w_rows"] * d["k_total"]]).reshape(d["w_rows"], d["k_total"])
+    d["b"] = bbuf[: d["n_pad"]].copy()
+    d["block_n"] = block_n
+    d["slab"] = bool(slab)
+    d["head"] = head_w is not None
+    return d
+
+
+def emulate_ex(plan, act):
+    """Like emulate() for ksplit == 1 with slab groups and / or the fused head.  Returns (out [B,oH,oW,n_pad] fp32 with
+    bias, head shares [B,oH,oW,2] or None)."""
+    flat = np.ascontiguousarray(act, np.float32).reshape(-1)
+    tileW = 1 << plan["tileW_log2"]
+    tile_rows, piece_rows, Hg = plan["tile_rows"], plan["piece_rows"], plan["Hg"]
+    B = act.shape[0]
+    BN = plan["block_n"]
+    out = np.full((B, plan["out_H"], plan["out_W"], plan["n_pad"]), np.nan, np.float64)
+    head = np.full((B, plan["out_H"], plan["out_W"], 2), np.nan, np.float64) if plan["head"] else None
+    oys = [plan["oy0"], plan["oy1"], plan["oy2"], plan["oy3"]]
+    oxs = [plan["ox0"], plan["ox1"], plan["ox2"], plan["ox3"]]
+    slabW = tileW + plan["slab_extra"]
+    if plan["slab"]:
+        assert plan["npieces"] == 1 and tile_rows == 1 and tileW == 128 and plan["nchunks"] == 1
+        assert plan["a_bytes"] == slabW * 128
+    for tile in range(plan["tiles_m"] * plan["tiles_n"] * plan["phases"]):
+        n_t = tile % plan["tiles_n"]
+        rest = tile // plan["tiles_n"]
+        m_t = rest % plan["tiles_m"]
+        ph = rest // plan["tiles_m"]
+        gy0 = (m_t // plan["tiles_x"]) * tile_rows
+        ox0 = (m_t % plan["tiles_x"]) << plan["tileW_log2"]
+        last_n = n_t == plan["tiles_n"] - 1
+        nb = BN + (16 if (plan["head"] and last_n) else 0)
+        w_row = ph * plan["w_rows_phase"] + n_t * BN
+        acc = np.zeros((128, nb), np.float64)
+        kcol = 0
+        for tap in range(plan["ntaps"]):
+            ti = ph * plan["ntaps"] + tap
+            if plan["slab"]:
+                b = gy0 // Hg
+                y = gy0 - b * Hg + plan["tap_y"][ti]
+                p2 = dict(plan, box_y=1, box_b=1)
+                slab = tma_box(flat, p2, plan["tap_c"][ti], ox0 + plan["tap_x"][ti], plan["tap_p"][ti], y, b, slabW)
+                for t in range(plan["grp_n"][ti]):
+                    off = plan["grp_off"][ti][t]
+                    A = slab[off:off + 128]                       # the row-advanced UMMA window of the slab
+                    Wt = plan["w"][w_row:w_row + nb, kcol:kcol + 64]
+                    acc += A.astype(np.float64) @ Wt.astype(np.float64).T
+                    kcol += 64
+            else:
+                for ch in range(plan["nchunks"]):
+                    A = np.zeros((128, 64), np.float32)
+                    for pc in range(plan["npieces"]):
+                        gy = gy0 + pc * piece_rows
+                        b = gy // Hg
+                        y = gy - b * Hg + plan["tap_y"][ti]
+                        A[pc * piece_rows * tileW:(pc + 1) * piece_rows * tileW] = tma_box(
+                            flat, plan, plan["tap_c"][ti] + ch * 64, ox0 + plan["tap_x"][ti], plan["tap_p"][ti], y, b, tileW)
+                    Wt = plan["w"][w_row:w_row + nb, kcol:kcol + 64]
+                    acc += A.astype(np.float64) @ Wt.astype(np.float64).T
+                    kcol += 64
+        assert kcol == plan["k_total"]
+        for row in range(128):
+            ty = row >> plan["tileW_log2"]
+            gy = gy0 + ty
+            gx = ox0 + (row & (tileW - 1))
+            if ty >= tile_rows or gy >= plan["rows_total"]:
+                continue
+            b = gy // Hg
+            y = gy - b * Hg
+            oy, ox = y * plan["out_scale"] + oys[ph], gx * plan["out_scale"] + oxs[ph]
+            out[b, oy, ox, n_t * BN:(n_t + 1) * BN] = acc[row, :BN] + plan["b"][n_t * BN:(n_t + 1) * BN]
+            if plan["head"] and last_n:
+                head[b, oy, ox] = acc[row, BN:BN + 2]
+    return out.astype(np.float32), None if head is None else head.astype(np.float32)

@@ -126,15 +126,70 @@ def test_conv_plan_emulation_matches_oracle(lib, kind, B, H, W, cin, in_cs, cout
     np.testing.assert_allclose(got, ref.numpy(), rtol=1e-5, atol=1e-5)
 
 
+SLAB_CASES = [
+    pytest.param(1, 8, 256, 27, 32, 64, 7, 64, id="conv1_form_k7_paired"),
+    pytest.param(2, 6, 512, 27, 32, 64, 7, 64, id="conv1_form_two_x_tiles_two_images"),
+    pytest.param(1, 8, 256, 64, 64, 128, 5, 128, id="conv2_form_k5"),
+    pytest.param(1, 6, 256, 16, 32, 64, 3, 64, id="k3_paired"),
+    pytest.param(1, 6, 256, 64, 64, 64, 3, 64, id="k3_cin64"),
+]
+
+
+@pytest.mark.parametrize("B,H,W,cin,in_cs,cout,k,bn", SLAB_CASES)
+def test_slab_group_plan_emulation_matches_oracle(lib, B, H, W, cin, in_cs, cout, k, bn):
+    """Slab groups (conv1 / conv2): one TMA slab per group of x-shifted taps, tap t = the slab rows [off_t, off_t + 128),
+    weights packed in group-major K order.  The numpy emulation of exactly that must equal the oracle stride-2 conv."""
+    rng = np.random.RandomState(99 + k)
+    x = emu.bf16_round(rng.rand(B, H, W, cin).astype(np.float32))
+    w = emu.bf16_round(rng.randn(k, k, cin, cout).astype(np.float32) * 0.1)
+    b = rng.randn(cout).astype(np.float32)
+    plan = emu.get_plan_ex(lib, 0, B, H, W, cin, in_cs, cout, k, 2, bn, w, b, slab=True)
+    assert plan["group_max"] <= 4 and plan["slab_extra"] <= 7 and plan["tiles_mp"] == (plan["tiles_m"] + 1) // 2
+    assert plan["k_total"] == 64 * int(sum(plan["grp_n"][:plan["ntaps"]]))
+    act = np.zeros((B, H, W, in_cs), np.float32)
+    act[..., :cin] = x
+    got, _ = emu.emulate_ex(plan, act)
+    ref = T.conv2d_valid(T.pad_constant(torch.from_numpy(x).double(), k // 2), torch.from_numpy(w).double(),
+                         torch.from_numpy(b).double(), 2)
+    assert not np.isnan(got).any()
+    np.testing.assert_allclose(got[..., :cout], ref.numpy(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,H,W,cin,in_cs,cout,bn", [(2, 6, 8, 70, 72, 128, 128), (1, 12, 16, 130, 136, 64, 64),
+                                                      (1, 12, 16, 96, 96, 256, 128)],
+                         ids=["whole_image_tiles", "three_chunks", "two_n_tiles"])
+def test_fused_head_plan_emulation_matches_oracle(lib, B, H, W, cin, in_cs, cout, bn):
+    """Transposed conv with the level's 3x3 flow head fused as 16 extra accumulator columns: the deconv output must equal
+    the oracle conv2d_transpose and the 4 phase shares of every input pixel must add up to the oracle 3x3 head."""
+    rng = np.random.RandomState(5 + cout)
+    x = emu.bf16_round(rng.rand(B, H, W, cin).astype(np.float32))
+    w = emu.bf16_round(rng.randn(4, 4, cout, cin).astype(np.float32) * 0.1)
+    hw = emu.bf16_round(rng.randn(3, 3, cin, 2).astype(np.float32) * 0.1)
+    b = rng.randn(cout).astype(np.float32)
+    plan = emu.get_plan_ex(lib, 1, B, H, W, cin, in_cs, cout, 4, 2, bn, w, b, head_w=hw)
+    assert plan["w_rows_phase"] == plan["n_pad"] + 16 and plan["w_rows"] == 4 * plan["w_rows_phase"]
+    act = np.zeros((B, H, W, in_cs), np.float32)
+    act[..., :cin] = x
+    act[..., cin:] = 7.0
+    got, shares = emu.emulate_ex(plan, act)
+    xt = torch.from_numpy(x).double()
+    ref = T.conv2d_transpose_k4s2_same(xt, torch.from_numpy(w).double(), torch.from_numpy(b).double())
+    np.testing.assert_allclose(got[..., :cout], ref.numpy(), rtol=1e-5, atol=1e-5)
+    head = shares[:, 0::2, 0::2] + shares[:, 0::2, 1::2] + shares[:, 1::2, 0::2] + shares[:, 1::2, 1::2]
+    href = T.conv2d_valid(T.pad_constant(xt, 1), torch.from_numpy(hw).double(), torch.zeros(2).double(), 1)
+    np.testing.assert_allclose(head, href.numpy(), rtol=1e-5, atol=1e-5)
+
+
 def test_network_layer_plans_are_valid(lib):
-    """Geometry of all 19 GEMM layers at B=8: tiles cover the grid, K is whole 64-blocks, smem fits."""
+    """Geometry of the 15 GEMM layers (default 1-CTA tilings; the flow heads ride in the deconvs): tiles cover the grid,
+    K is whole 64-blocks, smem fits."""
     layers = [  # kind,H,W,cin,in_cs,cout,k,stride,bn
         (0, 384, 512, 27, 32, 64, 7, 2, 64), (0, 192, 256, 64, 64, 128, 5, 2, 128), (0, 96, 128, 128, 200, 256, 5, 2, 128),
         (0, 48, 64, 256, 256, 256, 3, 1, 128), (0, 48, 64, 256, 392, 512, 3, 2, 128), (0, 24, 32, 512, 512, 512, 3, 1, 128),
         (0, 24, 32, 512, 776, 512, 3, 2, 128), (0, 12, 16, 512, 512, 512, 3, 1, 128), (0, 12, 16, 512, 1032, 1024, 3, 2, 128),
-        (0, 6, 8, 1024, 1024, 1024, 3, 1, 128), (0, 6, 8, 1024, 1024, 2, 3, 1, 16), (1, 6, 8, 1024, 1024, 512, 4, 2, 128),
-        (0, 12, 16, 1026, 1032, 2, 3, 1, 16), (1, 12, 16, 1026, 1032, 256, 4, 2, 128), (0, 24, 32, 770, 776, 2, 3, 1, 16),
-        (1, 24, 32, 770, 776, 128, 4, 2, 128), (0, 48, 64, 386, 392, 2, 3, 1, 16), (1, 48, 64, 386, 392, 64, 4, 2, 64),
+        (0, 6, 8, 1024, 1024, 1024, 3, 1, 128), (1, 6, 8, 1024, 1024, 512, 4, 2, 128),
+        (1, 12, 16, 1026, 1032, 256, 4, 2, 128),
+        (1, 24, 32, 770, 776, 128, 4, 2, 128), (1, 48, 64, 386, 392, 64, 4, 2, 64),
         (0, 96, 128, 194, 200, 18, 1, 1, 32)]
     for B in (1, 8):
         for (kind, H, W, cin, in_cs, cout, k, s, bn) in layers:
