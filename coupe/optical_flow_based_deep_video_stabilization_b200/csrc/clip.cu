@@ -30,6 +30,7 @@ int net_max_batch(const ofs_net* n);
 int net_is_bf16(const ofs_net* n);
 int net_device(const ofs_net* n);
 bool net_loaded(const ofs_net* n);
+unsigned net_weights_generation(const ofs_net* n);
 int net_prepare(ofs_net* n, int B);
 int net_stabilize_from_x0(ofs_net* n, const float* frames, float* out, int B, int H, int W, cudaStream_t st);
 }  // namespace ofs
@@ -182,6 +183,7 @@ struct ofs_clips {
   cudaGraphExec_t graph = nullptr;
   bool graph_f32 = false;
   int graph_launches = 0;
+  unsigned graph_generation = 0;   // weights generation the graph was captured with (kernel arguments are baked in)
   std::vector<void*> allocs;
 };
 
@@ -266,13 +268,12 @@ int ofs_clips_create(ofs_clips** out, ofs_net* net, int n_clips, int H, int W) {
     std::vector<short> ax, ay;
     linear_tables(W, kNetW, sx, ax, true);
     linear_tables(H, kNetH, sy, ay, false);
-    cudaMemcpy(c->d_lut_hist, lh.data(), 512, cudaMemcpyHostToDevice);
-    cudaMemcpy(c->d_lut_cur, lc.data(), 512, cudaMemcpyHostToDevice);
-    cudaMemcpy(c->d_lut_f32, lf.data(), 1024, cudaMemcpyHostToDevice);
-    cudaMemcpy(c->d_sx, sx.data(), kNetW * 4, cudaMemcpyHostToDevice);
-    cudaMemcpy(c->d_sy, sy.data(), kNetH * 4, cudaMemcpyHostToDevice);
-    cudaMemcpy(c->d_ax, ax.data(), kNetW * 4, cudaMemcpyHostToDevice);
-    rc = check_cuda(cudaMemcpy(c->d_ay, ay.data(), kNetH * 4, cudaMemcpyHostToDevice), "table upload", __FILE__, __LINE__);
+    const struct { void* dst; const void* src; size_t bytes; } ups[] = {
+        {c->d_lut_hist, lh.data(), 512}, {c->d_lut_cur, lc.data(), 512}, {c->d_lut_f32, lf.data(), 1024},
+        {c->d_sx, sx.data(), (size_t)kNetW * 4}, {c->d_sy, sy.data(), (size_t)kNetH * 4},
+        {c->d_ax, ax.data(), (size_t)kNetW * 4}, {c->d_ay, ay.data(), (size_t)kNetH * 4}};
+    for (const auto& u : ups)
+      if (rc == OFS_OK) rc = check_cuda(cudaMemcpy(u.dst, u.src, u.bytes, cudaMemcpyHostToDevice), "table upload", __FILE__, __LINE__);
   }
   if (rc != OFS_OK) { ofs_clips_destroy(c); return rc; }
   *out = c;
@@ -312,7 +313,7 @@ int ofs_clips_step_host(ofs_clips* c, const uint8_t* frames_bgr, uint8_t* out_bg
   cudaStream_t st = c->st;
   OFS_CUDA(cudaMemcpyAsync(c->d_state, &s, sizeof(s), cudaMemcpyHostToDevice, st));
   OFS_CUDA(cudaMemcpyAsync(c->d_frame, frames_bgr, fpx, cudaMemcpyHostToDevice, st));
-  if (!c->graph || c->graph_f32 != want_f32) {
+  if (!c->graph || c->graph_f32 != want_f32 || c->graph_generation != net_weights_generation(c->net)) {
     if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
     int rc = net_prepare(c->net, c->n);
     if (rc != OFS_OK) return rc;
@@ -330,6 +331,7 @@ int ofs_clips_step_host(ofs_clips* c, const uint8_t* frames_bgr, uint8_t* out_bg
     cudaGraphDestroy(g);
     OFS_CUDA(ie);
     c->graph_f32 = want_f32;
+    c->graph_generation = net_weights_generation(c->net);
   }
   OFS_CUDA(cudaGraphLaunch(c->graph, st));
   count_launch(c->graph_launches);

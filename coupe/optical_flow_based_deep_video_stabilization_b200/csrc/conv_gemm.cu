@@ -387,7 +387,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
                 const int gi = ((tile / (p.tiles_n * p.tiles_mp)) % p.phases) * p.ntaps + kb0 + i;
                 const int gn = (int)p.grp_n[gi];
                 for (int t = 0; t < gn; ++t) {
-                  const uint32_t a_lo = da + (uint32_t)p.grp_off[gi][t] * 8u;
+                  const uint32_t a_lo = da + ((p.debug & 128) ? 0u : (uint32_t)p.grp_off[gi][t] * 8u);   // debug 128: timing of aligned windows
                   const uint32_t b_lo = db + (uint32_t)t * (uint32_t)(Cfg::kBBytes >> 4);
                   lean::mma<kPair>(d_tmem, a_lo, b_lo, kDescHi, idesc, (i > 0 || t > 0) ? 1u : 0u);
                   lean::mma<kPair>(d_tmem, a_lo + 2, b_lo + 2, kDescHi, idesc, 1u);

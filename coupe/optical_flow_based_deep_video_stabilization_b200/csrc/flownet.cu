@@ -267,6 +267,7 @@ struct ofs_net {
   std::vector<StepGraph> graphs;
   uint64_t graph_clock = 0;
   int use_graphs = 1;
+  unsigned weights_generation = 0;   // bumped by ofs_net_load_weights: captured graphs of dependants are stale
 };
 
 namespace {
@@ -519,6 +520,7 @@ int net_max_batch(const ofs_net* n) { return n->max_batch; }
 int net_is_bf16(const ofs_net* n) { return n->is_bf16; }
 int net_device(const ofs_net* n) { return n->device; }
 bool net_loaded(const ofs_net* n) { return n->loaded; }
+unsigned net_weights_generation(const ofs_net* n) { return n->weights_generation; }
 int net_prepare(ofs_net* n, int B) { return prepare(n, B); }
 // forward from the pre-filled x0 + fused flow glue / warp of frames -> out (all device pointers), on `st`
 int net_stabilize_from_x0(ofs_net* n, const float* frames, float* out, int B, int H, int W, cudaStream_t st) {
@@ -757,6 +759,7 @@ int ofs_net_load_weights(ofs_net* n, const ofs_named_array* arrays, int count) {
   }
   OFS_CUDA(cudaMemcpy(n->upw, upw.data(), upw.size() * 4, cudaMemcpyHostToDevice));
   n->loaded = true;
+  ++n->weights_generation;
   n->prepared_B = 0;
   for (Layer& L : n->layers) L.plans.clear();
   OFS_CUDA(cudaDeviceSynchronize());
