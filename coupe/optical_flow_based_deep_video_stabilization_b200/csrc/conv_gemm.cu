@@ -22,6 +22,7 @@
 //             slice of the consumer's concat buffer).  Persistent: grid = min(tiles, #SM).
 #include "conv_gemm.cuh"
 
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -218,7 +219,8 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
   }
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = kPair ? __shfl_sync(0xffffffffu, ptx::cluster_ctarank(), 0) : 0u;
+  // the intrinsic behind block_rank() is known to be CTA-uniform (S2UR); a value read through inline asm is not
+  const uint32_t rank = kPair ? (uint32_t)cooperative_groups::this_cluster().block_rank() : 0u;
   const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // scheduling unit: CTA or CTA pair
   const int nunits = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
@@ -262,7 +264,8 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
     const bool do_a = !(p.debug & 2), do_b = !(p.debug & 4);
     const uint32_t a_tx = (kPair ? 2u : 1u) * (uint32_t)(do_a ? p.a_bytes : 0);
     const uint32_t b_tx = (kPair ? 2u : 1u) * (uint32_t)(do_b ? Cfg::kBBytes : 0);
-    const uint32_t full_tgt0 = kPair ? ptx::mapa_u32(full0, 0) : full0;   // where TMA bytes are posted
+    // where TMA bytes are posted; mapa comes out of inline asm, so broadcast it to make it provably warp-uniform
+    const uint32_t full_tgt0 = kPair ? __shfl_sync(0xffffffffu, ptx::mapa_u32(full0, 0), 0) : full0;
     const int piece_bytes = p.piece_rows * tileW * kBlockK * 2;
     const int npieces = p.npieces;
     int stage = 0;
@@ -1073,9 +1076,9 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
       int xmin = xoffs[0];
       for (int v : xoffs) xmin = std::min(xmin, v);
       p.tap_c[ng] = (short)cbase; p.tap_x[ng] = (short)xmin; p.tap_p[ng] = (short)(ty & 1); p.tap_y[ng] = (short)(ty >> 1);
-      p.grp_n[ng] = (unsigned char)xoffs.size();
+      p.grp_n[ng] = (short)xoffs.size();
       for (size_t t = 0; t < xoffs.size(); ++t) {
-        p.grp_off[ng][t] = (unsigned char)(xoffs[t] - xmin);
+        p.grp_off[ng][t] = (short)(xoffs[t] - xmin);
         extra = std::max(extra, xoffs[t] - xmin);
         plan.wt_ky.push_back(ky); plan.wt_kx.push_back(kxs[t]);
       }

@@ -60,8 +60,8 @@ struct ConvGemmParams {
   // descriptor whose start address is advanced by grp_off[t] 128-byte rows: one pipeline stage, one
   // handshake and one A fetch per group instead of per tap.
   int slab, slab_extra;
-  unsigned char grp_n[kMaxTapEntries];
-  unsigned char grp_off[kMaxTapEntries][4];
+  short grp_n[kMaxTapEntries];          // 16-bit like the tap tables: byte-wide constant loads are not uniform loads
+  short grp_off[kMaxTapEntries][4];
 };
 
 enum ConvKind { kConv = 0, kDeconvK4S2 = 1 };

@@ -1,5 +1,7 @@
 #!/bin/bash
-for tune in "3_1:256:1:1:16" "3_1:256:1:1:23" "3_1:256:1:1:31" "2:128:1:1:16" "2:128:1:1:31" "1:64:1:1:16"; do
-  echo "=== OFS_TUNE=$tune"
-  OFS_TUNE="$tune" timeout 300 python bench.py --steps 3 --warmup 1 --no-cpu-baseline 2>&1 | grep "conv dbg" | sort | uniq -c | sort -rn | head -8
-done
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_net.py -m gpu -q --timeout 200 --tb=short -k "conv or slab" 2>&1 | tail -8
+timeout 300 python benchmarks/conv_bench.py --layers 1 --variants 64:1:4:0 --batch 8 2>&1 | tail -4
+timeout 300 python benchmarks/conv_bench.py --layers 2 --variants 128:1:4:0 --batch 8 2>&1 | tail -4
+timeout 300 python benchmarks/conv_bench.py --layers 3 --variants 256:1:2:0 --batch 8 2>&1 | tail -4
+timeout 300 python bench.py --steps 100 --warmup 5 2>&1 | tail -3
