@@ -321,15 +321,20 @@ def run_ours(args):
     stabs = [ofs.ClipStabilizer(nets[k], n_clips=BATCH, height=FRAME_H, width=FRAME_W) for k in range(nstreams)]
     clip_bufs = []
     for k, stab in enumerate(stabs):
-        u8, u8_out = stab.pinned_buffer(), stab.pinned_buffer()
-        u8[...] = np.random.default_rng(7 + rank * nstreams + k).integers(0, 256, u8.shape, dtype=np.uint8)
+        u8, u8_out = [stab.pinned_buffer() for _ in range(2)], [stab.pinned_buffer() for _ in range(2)]
+        u8[0][...] = np.random.default_rng(7 + rank * nstreams + k).integers(0, 256, u8[0].shape, dtype=np.uint8)
+        u8[1][...] = u8[0][:, ::-1]
         clip_bufs.append((u8, u8_out))
 
     def clip_worker(k, nsteps):
         torch.cuda.set_device(local)
         u8_, out_ = clip_bufs[k]
-        for _ in range(nsteps):
-            stabs[k].step(u8_, out=out_)
+        for i in range(nsteps):          # two steps in flight: upload i+1 / download i-1 overlap the kernels of i
+            if stabs[k].in_flight == 2:
+                stabs[k].wait()
+            stabs[k].submit(u8_[i % 2], out=out_[i % 2])
+        while stabs[k].in_flight:
+            stabs[k].wait()
 
     def clip_run(nsteps_total):
         if nstreams == 1:
@@ -352,7 +357,7 @@ def run_ours(args):
     clip_value = world * BATCH * clip_steps / float(dtc.item())
     for stab in stabs:
         stab.close()
-    u8 = clip_bufs[0][0]
+    u8 = clip_bufs[0][0][0]
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
@@ -377,7 +382,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(hout.numel() * 4), "steps": e2e_steps,
                     "api": f"ofs_net_stabilize_host (C ABI, pinned host float32 buffers), {nstreams} concurrent caller thread(s)"},
             "e2e_clip_driver": {"value": clip_value, "unit": UNIT, "h2d_bytes_per_step": int(u8.nbytes), "d2h_bytes_per_step": int(u8.nbytes),
-                                "steps": clip_steps, "api": "ofs_clips_step_host (uint8 BGR frames in / out, device-side history ring; "
+                                "steps": clip_steps, "api": "ofs_clips_submit_host / ofs_clips_wait (uint8 BGR frames in / out, device-side history ring, 2 steps in flight; "
                                 f"one iteration of main_dl.py:540-630 per clip per step, pinned host buffers), {nstreams} clip set(s) of {BATCH} "
                                        "stepped by concurrent caller threads"},
             "gpu_launches": launches, "launches_per_step": launches // max(args.steps, 1),

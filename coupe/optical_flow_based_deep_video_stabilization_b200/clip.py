@@ -12,6 +12,7 @@ pixel each way over PCIe.  Several clips of the same size advance in lockstep as
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 
 import numpy as np
@@ -26,6 +27,7 @@ class ClipStabilizer:
         self.n, self.h, self.w = int(n_clips), int(height), int(width)
         self._h = C.c_void_p()
         _lib.check(self._lib.ofs_clips_create(C.byref(self._h), net._h, self.n, self.h, self.w))
+        self._pending = collections.deque()   # (frames, out, outf, single) of submitted steps: keeps the buffers alive
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -44,6 +46,11 @@ class ClipStabilizer:
 
     def reset(self):
         _lib.check(self._lib.ofs_clips_reset(self._h))
+        self._pending.clear()
+
+    @property
+    def in_flight(self):
+        return len(self._pending)
 
     def pinned_buffer(self):
         """A page-locked uint8 [n_clips,H,W,3] numpy array: frames decoded straight into it (and outputs written into
@@ -52,10 +59,7 @@ class ClipStabilizer:
 
         return torch.empty((self.n, self.h, self.w, 3), dtype=torch.uint8).pin_memory().numpy()
 
-    def step(self, frames_bgr, return_float=False, out=None):
-        """frames_bgr: uint8 [H,W,3] (one clip) or [n_clips,H,W,3], BGR as cap.read() returns them.
-        Returns np.uint8(totaloutputFrame[i]) with the same leading shape (and totaloutputFrame[i] as float32
-        when return_float).  `out`: optional uint8 [n_clips,H,W,3] array to receive the frames (e.g. pinned_buffer())."""
+    def _check_args(self, frames_bgr, return_float, out):
         a = np.ascontiguousarray(frames_bgr, dtype=np.uint8)
         single = a.ndim == 3
         if single:
@@ -68,9 +72,37 @@ class ClipStabilizer:
         else:
             out = np.empty_like(a)
         outf = np.empty(a.shape, np.float32) if return_float else None
-        _lib.check(self._lib.ofs_clips_step_host(self._h, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
-                                                 outf.ctypes.data_as(C.c_void_p) if return_float else None))
+        return a, out, outf, single
+
+    @staticmethod
+    def _result(out, outf, single):
         if single:
             out = out[0]
-            outf = outf[0] if return_float else None
-        return (out, outf) if return_float else out
+            outf = outf[0] if outf is not None else None
+        return (out, outf) if outf is not None else out
+
+    def step(self, frames_bgr, return_float=False, out=None):
+        """frames_bgr: uint8 [H,W,3] (one clip) or [n_clips,H,W,3], BGR as cap.read() returns them.
+        Returns np.uint8(totaloutputFrame[i]) with the same leading shape (and totaloutputFrame[i] as float32
+        when return_float).  `out`: optional uint8 [n_clips,H,W,3] array to receive the frames (e.g. pinned_buffer())."""
+        a, out, outf, single = self._check_args(frames_bgr, return_float, out)
+        _lib.check(self._lib.ofs_clips_step_host(self._h, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                                                 outf.ctypes.data_as(C.c_void_p) if return_float else None))
+        return self._result(out, outf, single)
+
+    def submit(self, frames_bgr, return_float=False, out=None):
+        """step() without the wait: queues the upload, the kernels and the download of one frame per clip and returns.
+        At most 2 steps may be in flight; collect them in order with wait().  `frames_bgr` (and `out`) must not be
+        written until the matching wait() returns -- use pinned_buffer() arrays, two of each, alternating."""
+        a, out, outf, single = self._check_args(frames_bgr, return_float, out)
+        _lib.check(self._lib.ofs_clips_submit_host(self._h, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                                                   outf.ctypes.data_as(C.c_void_p) if return_float else None))
+        self._pending.append((a, out, outf, single))
+
+    def wait(self):
+        """Blocks until the oldest submitted step has landed and returns what step() would have returned for it."""
+        if not self._pending:
+            raise RuntimeError("ClipStabilizer.wait(): no step in flight")
+        _lib.check(self._lib.ofs_clips_wait(self._h))
+        _, out, outf, single = self._pending.popleft()
+        return self._result(out, outf, single)

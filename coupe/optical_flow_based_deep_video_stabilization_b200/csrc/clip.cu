@@ -18,7 +18,9 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cmath>
+#include <initializer_list>
 #include <vector>
 
 #include "conv_gemm.cuh"
@@ -169,21 +171,35 @@ void linear_tables(int src, int dst, std::vector<int>& s_tab, std::vector<short>
 
 }  // namespace
 
-struct ofs_clips {
-  ofs_net* net = nullptr;
-  int n = 0, H = 0, W = 0, device = 0;
-  long long frame = 0;
-  uint8_t *d_frame = nullptr, *d_out_u8 = nullptr, *d_ring = nullptr, *d_cur = nullptr;
-  float *d_frame_f32 = nullptr, *d_warped = nullptr, *d_out_f32 = nullptr, *d_lut_f32 = nullptr;
-  uint16_t *d_lut_hist = nullptr, *d_lut_cur = nullptr;
-  int *d_sx = nullptr, *d_sy = nullptr;
-  short *d_ax = nullptr, *d_ay = nullptr;
+// One step in flight owns one Slot: its own input / output staging and its own captured graph (a graph's kernel
+// arguments are baked in), so the upload of step i+1 and the download of step i-1 overlap the kernels of step i.
+struct ClipSlot {
+  uint8_t *d_frame = nullptr, *d_out_u8 = nullptr;
+  float* d_out_f32 = nullptr;
   StepState* d_state = nullptr;
-  cudaStream_t st = nullptr;
+  StepState* h_state = nullptr;       // pinned
   cudaGraphExec_t graph = nullptr;
   bool graph_f32 = false;
   int graph_launches = 0;
-  unsigned graph_generation = 0;   // weights generation the graph was captured with (kernel arguments are baked in)
+  unsigned graph_generation = 0;      // weights generation the graph was captured with
+  cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
+  bool busy = false;
+};
+
+constexpr int kSlots = 2;
+
+struct ofs_clips {
+  ofs_net* net = nullptr;
+  int n = 0, H = 0, W = 0, device = 0;
+  long long frame = 0;                // steps submitted
+  long long collected = 0;            // steps waited for
+  ClipSlot slot[kSlots];
+  uint8_t *d_ring = nullptr, *d_cur = nullptr;
+  float *d_frame_f32 = nullptr, *d_warped = nullptr, *d_lut_f32 = nullptr;
+  uint16_t *d_lut_hist = nullptr, *d_lut_cur = nullptr;
+  int *d_sx = nullptr, *d_sy = nullptr;
+  short *d_ax = nullptr, *d_ay = nullptr;
+  cudaStream_t st = nullptr, st_in = nullptr, st_out = nullptr;
   std::vector<void*> allocs;
 };
 
@@ -196,25 +212,25 @@ int clips_alloc(ofs_clips* c, void** p, size_t bytes) {
   return check_cuda(cudaMemset(*p, 0, bytes), "memset", __FILE__, __LINE__);
 }
 
-int enqueue_step(ofs_clips* c, cudaStream_t st, bool want_f32) {
+int enqueue_step(ofs_clips* c, const ClipSlot& s, cudaStream_t st, bool want_f32) {
   const int n = c->n, H = c->H, W = c->W;
   const size_t npix = (size_t)n * H * W;
   const size_t ring_stride = (size_t)kRing * kSlice;
   const dim3 rgrid((kNetW + 255) / 256, kNetH, n);
-  resize_u8_kernel<<<rgrid, 256, 0, st>>>(c->d_frame, H, W, c->d_cur, (size_t)kSlice, c->d_state, 0, c->d_ring, ring_stride,
+  resize_u8_kernel<<<rgrid, 256, 0, st>>>(s.d_frame, H, W, c->d_cur, (size_t)kSlice, s.d_state, 0, c->d_ring, ring_stride,
                                           c->d_sx, c->d_ax, c->d_sy, c->d_ay);
   OFS_LAUNCH_CHECK();
-  assemble_x0_kernel<<<dim3((kNetH * kNetW + 255) / 256, n), 256, 0, st>>>(c->d_ring, ring_stride, c->d_cur, c->d_state,
+  assemble_x0_kernel<<<dim3((kNetH * kNetW + 255) / 256, n), 256, 0, st>>>(c->d_ring, ring_stride, c->d_cur, s.d_state,
                                                                          c->d_lut_hist, c->d_lut_cur,
                                                                          reinterpret_cast<uint4*>(net_x0(c->net)));
   OFS_LAUNCH_CHECK();
-  frame_to_f32_kernel<<<grid_for(npix, 256), 256, 0, st>>>(c->d_frame, c->d_frame_f32, npix, c->d_lut_f32);
+  frame_to_f32_kernel<<<grid_for(npix, 256), 256, 0, st>>>(s.d_frame, c->d_frame_f32, npix, c->d_lut_f32);
   OFS_LAUNCH_CHECK();
   int rc = net_stabilize_from_x0(c->net, c->d_frame_f32, c->d_warped, n, H, W, st);
   if (rc != OFS_OK) return rc;
-  finish_kernel<<<grid_for(npix, 256), 256, 0, st>>>(c->d_warped, c->d_out_u8, want_f32 ? c->d_out_f32 : nullptr, npix);
+  finish_kernel<<<grid_for(npix, 256), 256, 0, st>>>(c->d_warped, s.d_out_u8, want_f32 ? s.d_out_f32 : nullptr, npix);
   OFS_LAUNCH_CHECK();
-  resize_u8_kernel<<<rgrid, 256, 0, st>>>(c->d_out_u8, H, W, c->d_ring, ring_stride, c->d_state, 1, nullptr, 0, c->d_sx,
+  resize_u8_kernel<<<rgrid, 256, 0, st>>>(s.d_out_u8, H, W, c->d_ring, ring_stride, s.d_state, 1, nullptr, 0, c->d_sx,
                                           c->d_ax, c->d_sy, c->d_ay);
   OFS_LAUNCH_CHECK();
   return OFS_OK;
@@ -234,11 +250,24 @@ int ofs_clips_create(ofs_clips** out, ofs_net* net, int n_clips, int H, int W) {
   ofs_clips* c = new ofs_clips();
   c->net = net; c->n = n_clips; c->H = H; c->W = W; c->device = net_device(net);
   const size_t fpx = (size_t)n_clips * H * W * 3;
-  int rc = clips_alloc(c, (void**)&c->d_frame, fpx);
-  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_out_u8, fpx);
+  int rc = OFS_OK;
+  for (ClipSlot& s : c->slot) {
+    if (rc == OFS_OK) rc = clips_alloc(c, (void**)&s.d_frame, fpx);
+    if (rc == OFS_OK) rc = clips_alloc(c, (void**)&s.d_out_u8, fpx);
+    if (rc == OFS_OK) rc = clips_alloc(c, (void**)&s.d_out_f32, fpx * 4);
+    if (rc == OFS_OK) rc = clips_alloc(c, (void**)&s.d_state, sizeof(StepState));
+    if (rc == OFS_OK && cudaMallocHost((void**)&s.h_state, sizeof(StepState)) != cudaSuccess) {
+      set_error("ofs_clips_create: cudaMallocHost failed");
+      rc = OFS_ENOMEM;
+    }
+    for (cudaEvent_t* e : {&s.ev_in, &s.ev_done, &s.ev_out})
+      if (rc == OFS_OK && cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("ofs_clips_create: cudaEventCreate failed");
+        rc = OFS_ECUDA;
+      }
+  }
   if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_frame_f32, fpx * 4);
   if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_warped, fpx * 4);
-  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_out_f32, fpx * 4);
   if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_ring, (size_t)n_clips * kRing * kSlice);
   if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_cur, (size_t)n_clips * kSlice);
   if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_lut_hist, 512);
@@ -248,11 +277,11 @@ int ofs_clips_create(ofs_clips** out, ofs_net* net, int n_clips, int H, int W) {
   if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_sy, kNetH * 4);
   if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_ax, kNetW * 4);
   if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_ay, kNetH * 4);
-  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_state, sizeof(StepState));
-  if (rc == OFS_OK && cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) {
-    set_error("ofs_clips_create: cudaStreamCreate failed");
-    rc = OFS_ECUDA;
-  }
+  for (cudaStream_t* s : {&c->st, &c->st_in, &c->st_out})
+    if (rc == OFS_OK && cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) != cudaSuccess) {
+      set_error("ofs_clips_create: cudaStreamCreate failed");
+      rc = OFS_ECUDA;
+    }
   if (rc == OFS_OK) {
     const int is_bf16 = net_is_bf16(net);
     std::vector<uint16_t> lh(256), lc(256);
@@ -283,63 +312,111 @@ int ofs_clips_create(ofs_clips** out, ofs_net* net, int n_clips, int H, int W) {
 int ofs_clips_destroy(ofs_clips* c) {
   if (!c) return OFS_OK;
   cudaSetDevice(c->device);
-  if (c->st) { cudaStreamSynchronize(c->st); }
-  if (c->graph) cudaGraphExecDestroy(c->graph);
-  if (c->st) cudaStreamDestroy(c->st);
+  for (cudaStream_t s : {c->st_in, c->st, c->st_out})
+    if (s) cudaStreamSynchronize(s);
+  for (ClipSlot& s : c->slot) {
+    if (s.graph) cudaGraphExecDestroy(s.graph);
+    for (cudaEvent_t e : {s.ev_in, s.ev_done, s.ev_out})
+      if (e) cudaEventDestroy(e);
+    if (s.h_state) cudaFreeHost(s.h_state);
+  }
+  for (cudaStream_t s : {c->st_in, c->st, c->st_out})
+    if (s) cudaStreamDestroy(s);
   for (void* p : c->allocs) cudaFree(p);
   delete c;
   return OFS_OK;
 }
 
+int ofs_clips_wait(ofs_clips* c) {
+  OFS_REQUIRE(c, "ofs_clips_wait: null handle");
+  if (c->collected == c->frame) { set_error("ofs_clips_wait: no step in flight"); return OFS_ESTATE; }
+  ClipSlot& s = c->slot[c->collected % kSlots];
+  OFS_CUDA(cudaEventSynchronize(s.ev_out));
+  s.busy = false;
+  ++c->collected;
+  return OFS_OK;
+}
+
+int ofs_clips_in_flight(const ofs_clips* c) { return c ? (int)(c->frame - c->collected) : -1; }
+
 int ofs_clips_reset(ofs_clips* c) {
   OFS_REQUIRE(c, "ofs_clips_reset: null handle");
-  c->frame = 0;
+  while (c->collected < c->frame) {
+    const int rc = ofs_clips_wait(c);
+    if (rc != OFS_OK) return rc;
+  }
+  c->frame = c->collected = 0;
   return OFS_OK;
 }
 
 long long ofs_clips_frame_index(const ofs_clips* c) { return c ? c->frame : -1; }
 
-int ofs_clips_step_host(ofs_clips* c, const uint8_t* frames_bgr, uint8_t* out_bgr_u8, float* out_bgr_f32) {
-  OFS_REQUIRE(c && frames_bgr && out_bgr_u8, "ofs_clips_step_host: null pointer");
-  if (!net_loaded(c->net)) { set_error("ofs_clips_step_host: weights not loaded"); return OFS_ESTATE; }
+// Three streams per clip set: uploads, kernels, downloads.  Step i uses slot i % 2; the slot's events order
+//   upload(i) -> graph(i) -> download(i),   graph(i-2) -> upload(i)  (input staging free),
+//   download(i-2) -> graph(i)               (output staging free),
+// and graphs run in submission order on one stream, which is the recurrence through the history ring.
+int ofs_clips_submit_host(ofs_clips* c, const uint8_t* frames_bgr, uint8_t* out_bgr_u8, float* out_bgr_f32) {
+  OFS_REQUIRE(c && frames_bgr && out_bgr_u8, "ofs_clips_submit_host: null pointer");
+  if (!net_loaded(c->net)) { set_error("ofs_clips_submit_host: weights not loaded"); return OFS_ESTATE; }
+  if (c->frame - c->collected >= kSlots) {
+    set_error("ofs_clips_submit_host: %d steps already in flight; call ofs_clips_wait first", kSlots);
+    return OFS_ESTATE;
+  }
   OFS_CUDA(cudaSetDevice(c->device));
   const size_t fpx = (size_t)c->n * c->H * c->W * 3;
   const bool want_f32 = out_bgr_f32 != nullptr;
-  StepState s = {};
   const long long i = c->frame;
-  for (int j = 0; j < 8; ++j) s.hist_slot[j] = (int)(std::max<long long>(i - kOffsets[j], 0) % kRing);
-  s.write_slot = (int)(i % kRing);
-  s.first = i == 0;
-  cudaStream_t st = c->st;
-  OFS_CUDA(cudaMemcpyAsync(c->d_state, &s, sizeof(s), cudaMemcpyHostToDevice, st));
-  OFS_CUDA(cudaMemcpyAsync(c->d_frame, frames_bgr, fpx, cudaMemcpyHostToDevice, st));
-  if (!c->graph || c->graph_f32 != want_f32 || c->graph_generation != net_weights_generation(c->net)) {
-    if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
+  ClipSlot& s = c->slot[i % kSlots];
+  if (!s.graph || s.graph_f32 != want_f32 || s.graph_generation != net_weights_generation(c->net)) {
+    if (s.graph) { cudaGraphExecDestroy(s.graph); s.graph = nullptr; }
     int rc = net_prepare(c->net, c->n);
     if (rc != OFS_OK) return rc;
     const uint64_t l0 = launch_count();
-    OFS_CUDA(cudaStreamSynchronize(st));   // the state / frame copies above are not part of the graph
-    OFS_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    rc = enqueue_step(c, st, want_f32);
+    OFS_CUDA(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_step(c, s, c->st, want_f32);
     cudaGraph_t g = nullptr;
-    const cudaError_t ce = cudaStreamEndCapture(st, &g);
-    c->graph_launches = (int)(launch_count() - l0);
-    count_launch(-c->graph_launches);
+    const cudaError_t ce = cudaStreamEndCapture(c->st, &g);
+    s.graph_launches = (int)(launch_count() - l0);
+    count_launch(-s.graph_launches);
     if (rc != OFS_OK) { if (g) cudaGraphDestroy(g); return rc; }
     OFS_CUDA(ce);
-    const cudaError_t ie = cudaGraphInstantiate(&c->graph, g, 0);
+    const cudaError_t ie = cudaGraphInstantiate(&s.graph, g, 0);
     cudaGraphDestroy(g);
     OFS_CUDA(ie);
-    c->graph_f32 = want_f32;
-    c->graph_generation = net_weights_generation(c->net);
+    s.graph_f32 = want_f32;
+    s.graph_generation = net_weights_generation(c->net);
   }
-  OFS_CUDA(cudaGraphLaunch(c->graph, st));
-  count_launch(c->graph_launches);
-  OFS_CUDA(cudaMemcpyAsync(out_bgr_u8, c->d_out_u8, fpx, cudaMemcpyDeviceToHost, st));
-  if (want_f32) OFS_CUDA(cudaMemcpyAsync(out_bgr_f32, c->d_out_f32, fpx * 4, cudaMemcpyDeviceToHost, st));
-  OFS_CUDA(cudaStreamSynchronize(st));
+  StepState& h = *s.h_state;   // the slot's previous upload completed before its step was waited for
+  h = StepState{};
+  for (int j = 0; j < 8; ++j) h.hist_slot[j] = (int)(std::max<long long>(i - kOffsets[j], 0) % kRing);
+  h.write_slot = (int)(i % kRing);
+  h.first = i == 0;
+  if (i >= kSlots) OFS_CUDA(cudaStreamWaitEvent(c->st_in, s.ev_done, 0));
+  OFS_CUDA(cudaMemcpyAsync(s.d_state, &h, sizeof(h), cudaMemcpyHostToDevice, c->st_in));
+  OFS_CUDA(cudaMemcpyAsync(s.d_frame, frames_bgr, fpx, cudaMemcpyHostToDevice, c->st_in));
+  OFS_CUDA(cudaEventRecord(s.ev_in, c->st_in));
+  OFS_CUDA(cudaStreamWaitEvent(c->st, s.ev_in, 0));
+  if (i >= kSlots) OFS_CUDA(cudaStreamWaitEvent(c->st, s.ev_out, 0));
+  OFS_CUDA(cudaGraphLaunch(s.graph, c->st));
+  count_launch(s.graph_launches);
+  OFS_CUDA(cudaEventRecord(s.ev_done, c->st));
+  OFS_CUDA(cudaStreamWaitEvent(c->st_out, s.ev_done, 0));
+  OFS_CUDA(cudaMemcpyAsync(out_bgr_u8, s.d_out_u8, fpx, cudaMemcpyDeviceToHost, c->st_out));
+  if (want_f32) OFS_CUDA(cudaMemcpyAsync(out_bgr_f32, s.d_out_f32, fpx * 4, cudaMemcpyDeviceToHost, c->st_out));
+  OFS_CUDA(cudaEventRecord(s.ev_out, c->st_out));
+  s.busy = true;
   ++c->frame;
   return OFS_OK;
+}
+
+int ofs_clips_step_host(ofs_clips* c, const uint8_t* frames_bgr, uint8_t* out_bgr_u8, float* out_bgr_f32) {
+  OFS_REQUIRE(c, "ofs_clips_step_host: null handle");
+  if (c->frame != c->collected) {
+    set_error("ofs_clips_step_host: %d submitted step(s) not yet waited for", (int)(c->frame - c->collected));
+    return OFS_ESTATE;
+  }
+  const int rc = ofs_clips_submit_host(c, frames_bgr, out_bgr_u8, out_bgr_f32);
+  return rc != OFS_OK ? rc : ofs_clips_wait(c);
 }
 
 }  // extern "C"

@@ -167,13 +167,21 @@ int ofs_net_launches_per_forward(const ofs_net* net);
  *   frames_bgr   host uint8 [n_clips,H,W,3]: cap.read() of every clip (BGR)
  *   out_bgr_u8   host uint8 [n_clips,H,W,3]: np.uint8(totaloutputFrame[i]), what out.write() receives (:630)
  *   out_bgr_f32  host float32 [n_clips,H,W,3] or NULL: totaloutputFrame[i] itself (BGR, 0..255, not clipped)
- * Synchronous; 3 bytes per pixel cross PCIe each way instead of 32 MB + 11 MB of float32 per 720p frame. */
+ * 3 bytes per pixel cross PCIe each way instead of 32 MB + 11 MB of float32 per 720p frame.
+ * ofs_clips_step_host is synchronous.  ofs_clips_submit_host / ofs_clips_wait are the same step split in two so
+ * that the upload of frame i+1 and the download of frame i-1 overlap the kernels of frame i (the input frames do
+ * not depend on earlier outputs; the recurrence through the history ring stays ordered on the device): at most
+ * 2 steps may be in flight, ofs_clips_wait blocks until the OLDEST one has landed in its host buffers, which must
+ * stay valid (and should be page-locked) until then.  Results are identical to stepping synchronously. */
 typedef struct ofs_clips ofs_clips;
 int ofs_clips_create(ofs_clips** clips, ofs_net* net, int n_clips, int H, int W);
 int ofs_clips_destroy(ofs_clips* clips);
 int ofs_clips_reset(ofs_clips* clips); /* next step is frame 0 again */
 long long ofs_clips_frame_index(const ofs_clips* clips);
 int ofs_clips_step_host(ofs_clips* clips, const uint8_t* frames_bgr, uint8_t* out_bgr_u8, float* out_bgr_f32);
+int ofs_clips_submit_host(ofs_clips* clips, const uint8_t* frames_bgr, uint8_t* out_bgr_u8, float* out_bgr_f32);
+int ofs_clips_wait(ofs_clips* clips);
+int ofs_clips_in_flight(const ofs_clips* clips); /* submitted, not yet waited for */
 
 /* ------------------------------------------------------------------------------------------
  * Stand-alone implicit-GEMM convolution on the same tcgen05 kernel the network uses (unit

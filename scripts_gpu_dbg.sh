@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_net.py -m gpu -q --timeout 200 --tb=short -k "conv or slab" 2>&1 | tail -8
-timeout 300 python benchmarks/conv_bench.py --layers 1 --variants 64:1:4:0 --batch 8 2>&1 | tail -4
-timeout 300 python benchmarks/conv_bench.py --layers 2 --variants 128:1:4:0 --batch 8 2>&1 | tail -4
-timeout 300 python benchmarks/conv_bench.py --layers 3 --variants 256:1:2:0 --batch 8 2>&1 | tail -4
-timeout 300 python bench.py --steps 100 --warmup 5 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_gpu_clip.py -m gpu -q --timeout 300 --tb=short 2>&1 | tail -15
+timeout 300 python benchmarks/clip_bench.py 2>&1 | tail -12
+timeout 300 python bench.py --steps 100 --warmup 5 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], d['e2e_clip_driver'])"

@@ -86,6 +86,49 @@ def test_clip_driver_matches_reference_loop(ofs, cuda_dev, n_clips, T, H, W):
     net.close()
 
 
+def test_pipelined_submit_wait_equals_stepping(ofs, cuda_dev):
+    """submit / wait (two steps in flight, upload and download overlapping the kernels) returns exactly what the
+    synchronous step returns, frame for frame, through a ring wrap; depth and ordering errors are reported."""
+    n_clips, T, H, W = 2, 40, 96, 128
+    net = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=2)
+    net.assign_weights(F.make_weights(0, "calibrated", head_scale=0.02))
+    clips = np.stack([synth_clip(300 + c, T, H, W) for c in range(n_clips)])         # [n,T,H,W,3]
+    sync = ofs.ClipStabilizer(net, n_clips=n_clips, height=H, width=W)
+    want = [sync.step(np.ascontiguousarray(clips[:, i]), return_float=True) for i in range(T)]
+    sync.close()
+    pipe = ofs.ClipStabilizer(net, n_clips=n_clips, height=H, width=W)
+    fin = [pipe.pinned_buffer() for _ in range(2)]
+    fout = [pipe.pinned_buffer() for _ in range(2)]
+    got = []
+    for i in range(T):
+        if pipe.in_flight == 2:
+            u8, f32 = pipe.wait()
+            got.append((u8.copy(), f32.copy()))
+        fin[i % 2][...] = clips[:, i]
+        pipe.submit(fin[i % 2], return_float=True, out=fout[i % 2])
+        assert pipe.frame_index == i + 1
+    with pytest.raises(RuntimeError, match="in flight"):
+        pipe.submit(fin[0], out=fout[0])                                             # a third step is refused
+    with pytest.raises(RuntimeError, match="not yet waited"):
+        pipe.step(fin[0])
+    while pipe.in_flight:
+        u8, f32 = pipe.wait()
+        got.append((u8.copy(), f32.copy()))
+    with pytest.raises(RuntimeError):
+        pipe.wait()
+    assert len(got) == T
+    for i in range(T):
+        np.testing.assert_array_equal(got[i][0], want[i][0], err_msg=f"frame {i}: written frame")
+        np.testing.assert_array_equal(got[i][1], want[i][1], err_msg=f"frame {i}: history")
+    # reset drains and restarts
+    pipe.submit(fin[0], out=fout[0])
+    pipe.reset()
+    assert pipe.in_flight == 0 and pipe.frame_index == 0
+    np.testing.assert_array_equal(pipe.step(np.ascontiguousarray(clips[:, 0])), want[0][0])
+    pipe.close()
+    net.close()
+
+
 def test_stabilize_video_file_boundary(ofs, cuda_dev, tmp_path):
     """evaluate_originalSize()'s file handling (main_dl.py:477-487, :540-547, :630-632): MJPG AVI in, MJPG AVI out,
     CAP_PROP_FRAME_COUNT - 2 frames, each equal to what the clip driver returns for the decoded frames."""
