@@ -321,18 +321,20 @@ def run_ours(args):
     stabs = [ofs.ClipStabilizer(nets[k], n_clips=BATCH, height=FRAME_H, width=FRAME_W) for k in range(nstreams)]
     clip_bufs = []
     for k, stab in enumerate(stabs):
-        u8, u8_out = [stab.pinned_buffer() for _ in range(2)], [stab.pinned_buffer() for _ in range(2)]
+        u8, u8_out = [stab.pinned_buffer() for _ in range(stab.depth)], [stab.pinned_buffer() for _ in range(stab.depth)]
         u8[0][...] = np.random.default_rng(7 + rank * nstreams + k).integers(0, 256, u8[0].shape, dtype=np.uint8)
-        u8[1][...] = u8[0][:, ::-1]
+        for b in u8[1:]:
+            b[...] = u8[0][:, ::-1]
         clip_bufs.append((u8, u8_out))
 
     def clip_worker(k, nsteps):
         torch.cuda.set_device(local)
         u8_, out_ = clip_bufs[k]
-        for i in range(nsteps):          # two steps in flight: upload i+1 / download i-1 overlap the kernels of i
-            if stabs[k].in_flight == 2:
+        depth = stabs[k].depth
+        for i in range(nsteps):          # steps in flight: upload i+1 / download i-1 overlap the kernels of i
+            if stabs[k].in_flight == depth:
                 stabs[k].wait()
-            stabs[k].submit(u8_[i % 2], out=out_[i % 2])
+            stabs[k].submit(u8_[i % depth], out=out_[i % depth])
         while stabs[k].in_flight:
             stabs[k].wait()
 
@@ -382,7 +384,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(hout.numel() * 4), "steps": e2e_steps,
                     "api": f"ofs_net_stabilize_host (C ABI, pinned host float32 buffers), {nstreams} concurrent caller thread(s)"},
             "e2e_clip_driver": {"value": clip_value, "unit": UNIT, "h2d_bytes_per_step": int(u8.nbytes), "d2h_bytes_per_step": int(u8.nbytes),
-                                "steps": clip_steps, "api": "ofs_clips_submit_host / ofs_clips_wait (uint8 BGR frames in / out, device-side history ring, 2 steps in flight; "
+                                "steps": clip_steps, "api": "ofs_clips_submit_host / ofs_clips_wait (uint8 BGR frames in / out, device-side history ring, up to 3 steps in flight; "
                                 f"one iteration of main_dl.py:540-630 per clip per step, pinned host buffers), {nstreams} clip set(s) of {BATCH} "
                                        "stepped by concurrent caller threads"},
             "gpu_launches": launches, "launches_per_step": launches // max(args.steps, 1),

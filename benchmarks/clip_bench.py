@@ -31,16 +31,18 @@ for (H, W) in ((720, 1280), (1080, 1920)):
         for _ in range(steps):
             stab.step(fin, out=fout)
         dt = time.perf_counter() - t0
-        fin2, fout2 = stab.pinned_buffer(), stab.pinned_buffer()
-        fin2[...] = fin[:, ::-1]
-        ins, outs = (fin, fin2), (fout, fout2)
+        depth = stab.depth
+        ins = [fin] + [stab.pinned_buffer() for _ in range(depth - 1)]
+        outs = [fout] + [stab.pinned_buffer() for _ in range(depth - 1)]
+        for b in ins[1:]:
+            b[...] = fin[:, ::-1]
         stab.reset()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(steps):
-            if stab.in_flight == 2:
+            if stab.in_flight == depth:
                 stab.wait()
-            stab.submit(ins[i % 2], out=outs[i % 2])
+            stab.submit(ins[i % depth], out=outs[i % depth])
         while stab.in_flight:
             stab.wait()
         dtp = time.perf_counter() - t0

@@ -61,6 +61,7 @@ PROTOTYPES = {
     "ofs_clips_submit_host": (_i, [_p, _p, _p, _p]),
     "ofs_clips_wait": (_i, [_p]),
     "ofs_clips_in_flight": (_i, [_p]),
+    "ofs_clips_depth": (_i, []),
     "ofs_conv2d_nhwc": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ofs_conv2d_nhwc_ex": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
 }

@@ -49,6 +49,11 @@ class ClipStabilizer:
         self._pending.clear()
 
     @property
+    def depth(self):
+        """How many submitted steps may be in flight."""
+        return int(self._lib.ofs_clips_depth())
+
+    @property
     def in_flight(self):
         return len(self._pending)
 
@@ -92,8 +97,8 @@ class ClipStabilizer:
 
     def submit(self, frames_bgr, return_float=False, out=None):
         """step() without the wait: queues the upload, the kernels and the download of one frame per clip and returns.
-        At most 2 steps may be in flight; collect them in order with wait().  `frames_bgr` (and `out`) must not be
-        written until the matching wait() returns -- use pinned_buffer() arrays, two of each, alternating."""
+        At most `depth` (3) steps may be in flight; collect them in order with wait().  `frames_bgr` (and `out`) must
+        not be written until the matching wait() returns -- use pinned_buffer() arrays, `depth` of each, in rotation."""
         a, out, outf, single = self._check_args(frames_bgr, return_float, out)
         _lib.check(self._lib.ofs_clips_submit_host(self._h, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
                                                    outf.ctypes.data_as(C.c_void_p) if return_float else None))

@@ -34,7 +34,8 @@ int net_device(const ofs_net* n);
 bool net_loaded(const ofs_net* n);
 unsigned net_weights_generation(const ofs_net* n);
 int net_prepare(ofs_net* n, int B);
-int net_stabilize_from_x0(ofs_net* n, const float* frames, float* out, int B, int H, int W, cudaStream_t st);
+int net_stabilize_u8_from_x0(ofs_net* n, const uint8_t* frames, uint8_t* out_u8, float* out_f32, int B, int H, int W,
+                             cudaStream_t st);
 }  // namespace ofs
 
 namespace {
@@ -116,39 +117,6 @@ __global__ void __launch_bounds__(256) assemble_x0_kernel(const uint8_t* __restr
                       (uint32_t)v[8 * q + 4] | ((uint32_t)v[8 * q + 5] << 16), (uint32_t)v[8 * q + 6] | ((uint32_t)v[8 * q + 7] << 16));
 }
 
-// resizedInput = cvtColor(frame_unstab, RGB2BGR) / 255.0 (main_dl.py:568), fed as float32
-__global__ void __launch_bounds__(256) frame_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
-                                                           size_t npix, const float* __restrict__ lut) {
-  __shared__ float l[256];
-  l[threadIdx.x] = lut[threadIdx.x];
-  __syncthreads();
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
-    const uint8_t* s = src + i * 3;
-    float* d = dst + i * 3;
-    d[0] = l[s[2]]; d[1] = l[s[1]]; d[2] = l[s[0]];
-  }
-}
-
-// totaloutputFrame[i] = cvtColor(warped * 255, RGB2BGR) (float32 product); out.write(np.uint8(...)) (main_dl.py:625,630)
-__global__ void __launch_bounds__(256) finish_kernel(const float* __restrict__ warped, uint8_t* __restrict__ out_u8,
-                                                     float* __restrict__ out_f32, size_t npix) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
-    const float* s = warped + i * 3;
-    const float v0 = __fmul_rn(s[2], 255.0f), v1 = __fmul_rn(s[1], 255.0f), v2 = __fmul_rn(s[0], 255.0f);   // B, G, R
-    uint8_t* d = out_u8 + i * 3;
-    d[0] = (uint8_t)(__float2int_rz(v0) & 0xff);
-    d[1] = (uint8_t)(__float2int_rz(v1) & 0xff);
-    d[2] = (uint8_t)(__float2int_rz(v2) & 0xff);
-    if (out_f32) { float* f = out_f32 + i * 3; f[0] = v0; f[1] = v1; f[2] = v2; }
-  }
-}
-
-int grid_for(size_t work, int threads) {
-  size_t b = (work + threads - 1) / threads;
-  const size_t cap = (size_t)sm_count() * 8;
-  return (int)std::max<size_t>(1, std::min(b, cap));
-}
-
 // OpenCV resize.cpp: fx = (float)((dx+0.5)*scale_x - 0.5); sx = cvFloor(fx); fx -= sx; edge clamps; cvRound(f * 2048)
 void linear_tables(int src, int dst, std::vector<int>& s_tab, std::vector<short>& a_tab, bool clamp_x) {
   s_tab.resize(dst);
@@ -186,7 +154,9 @@ struct ClipSlot {
   bool busy = false;
 };
 
-constexpr int kSlots = 2;
+// 3 slots: with 2, upload(i) could not start before download(i-2) had landed (the host only submits step i after
+// waiting for step i-2), a chain of download + upload + kernels per two steps that left the GPU idle a third of the time
+constexpr int kSlots = 3;
 
 struct ofs_clips {
   ofs_net* net = nullptr;
@@ -195,7 +165,6 @@ struct ofs_clips {
   long long collected = 0;            // steps waited for
   ClipSlot slot[kSlots];
   uint8_t *d_ring = nullptr, *d_cur = nullptr;
-  float *d_frame_f32 = nullptr, *d_warped = nullptr, *d_lut_f32 = nullptr;
   uint16_t *d_lut_hist = nullptr, *d_lut_cur = nullptr;
   int *d_sx = nullptr, *d_sy = nullptr;
   short *d_ax = nullptr, *d_ay = nullptr;
@@ -214,7 +183,6 @@ int clips_alloc(ofs_clips* c, void** p, size_t bytes) {
 
 int enqueue_step(ofs_clips* c, const ClipSlot& s, cudaStream_t st, bool want_f32) {
   const int n = c->n, H = c->H, W = c->W;
-  const size_t npix = (size_t)n * H * W;
   const size_t ring_stride = (size_t)kRing * kSlice;
   const dim3 rgrid((kNetW + 255) / 256, kNetH, n);
   resize_u8_kernel<<<rgrid, 256, 0, st>>>(s.d_frame, H, W, c->d_cur, (size_t)kSlice, s.d_state, 0, c->d_ring, ring_stride,
@@ -224,12 +192,9 @@ int enqueue_step(ofs_clips* c, const ClipSlot& s, cudaStream_t st, bool want_f32
                                                                          c->d_lut_hist, c->d_lut_cur,
                                                                          reinterpret_cast<uint4*>(net_x0(c->net)));
   OFS_LAUNCH_CHECK();
-  frame_to_f32_kernel<<<grid_for(npix, 256), 256, 0, st>>>(s.d_frame, c->d_frame_f32, npix, c->d_lut_f32);
-  OFS_LAUNCH_CHECK();
-  int rc = net_stabilize_from_x0(c->net, c->d_frame_f32, c->d_warped, n, H, W, st);
+  // forward + flow glue + the warp on the uint8 frame: resizedInput (:568), sess.run (:569), * 255 and np.uint8 (:625, :630)
+  int rc = net_stabilize_u8_from_x0(c->net, s.d_frame, s.d_out_u8, want_f32 ? s.d_out_f32 : nullptr, n, H, W, st);
   if (rc != OFS_OK) return rc;
-  finish_kernel<<<grid_for(npix, 256), 256, 0, st>>>(c->d_warped, s.d_out_u8, want_f32 ? s.d_out_f32 : nullptr, npix);
-  OFS_LAUNCH_CHECK();
   resize_u8_kernel<<<rgrid, 256, 0, st>>>(s.d_out_u8, H, W, c->d_ring, ring_stride, s.d_state, 1, nullptr, 0, c->d_sx,
                                           c->d_ax, c->d_sy, c->d_ay);
   OFS_LAUNCH_CHECK();
@@ -266,13 +231,10 @@ int ofs_clips_create(ofs_clips** out, ofs_net* net, int n_clips, int H, int W) {
         rc = OFS_ECUDA;
       }
   }
-  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_frame_f32, fpx * 4);
-  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_warped, fpx * 4);
   if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_ring, (size_t)n_clips * kRing * kSlice);
   if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_cur, (size_t)n_clips * kSlice);
   if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_lut_hist, 512);
   if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_lut_cur, 512);
-  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_lut_f32, 1024);
   if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_sx, kNetW * 4);
   if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_sy, kNetH * 4);
   if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_ax, kNetW * 4);
@@ -285,20 +247,18 @@ int ofs_clips_create(ofs_clips** out, ofs_net* net, int n_clips, int H, int W) {
   if (rc == OFS_OK) {
     const int is_bf16 = net_is_bf16(net);
     std::vector<uint16_t> lh(256), lc(256);
-    std::vector<float> lf(256);
     for (int v = 0; v < 256; ++v) {
       const float hist = (float)v / 255.0f;                 // np.float32(u8) / 255.0        (main_dl.py:556,558)
       const float cur = (float)((double)v / 255.0);         // u8 / 255.0 -> float32 at the feed (main_dl.py:550,568)
       lh[v] = is_bf16 ? f32_to_bf16_rn(hist) : f32_to_fp16_rn(hist);
       lc[v] = is_bf16 ? f32_to_bf16_rn(cur) : f32_to_fp16_rn(cur);
-      lf[v] = cur;
     }
     std::vector<int> sx, sy;
     std::vector<short> ax, ay;
     linear_tables(W, kNetW, sx, ax, true);
     linear_tables(H, kNetH, sy, ay, false);
     const struct { void* dst; const void* src; size_t bytes; } ups[] = {
-        {c->d_lut_hist, lh.data(), 512}, {c->d_lut_cur, lc.data(), 512}, {c->d_lut_f32, lf.data(), 1024},
+        {c->d_lut_hist, lh.data(), 512}, {c->d_lut_cur, lc.data(), 512},
         {c->d_sx, sx.data(), (size_t)kNetW * 4}, {c->d_sy, sy.data(), (size_t)kNetH * 4},
         {c->d_ax, ax.data(), (size_t)kNetW * 4}, {c->d_ay, ay.data(), (size_t)kNetH * 4}};
     for (const auto& u : ups)
@@ -339,6 +299,8 @@ int ofs_clips_wait(ofs_clips* c) {
 
 int ofs_clips_in_flight(const ofs_clips* c) { return c ? (int)(c->frame - c->collected) : -1; }
 
+int ofs_clips_depth(void) { return kSlots; }
+
 int ofs_clips_reset(ofs_clips* c) {
   OFS_REQUIRE(c, "ofs_clips_reset: null handle");
   while (c->collected < c->frame) {
@@ -351,9 +313,9 @@ int ofs_clips_reset(ofs_clips* c) {
 
 long long ofs_clips_frame_index(const ofs_clips* c) { return c ? c->frame : -1; }
 
-// Three streams per clip set: uploads, kernels, downloads.  Step i uses slot i % 2; the slot's events order
-//   upload(i) -> graph(i) -> download(i),   graph(i-2) -> upload(i)  (input staging free),
-//   download(i-2) -> graph(i)               (output staging free),
+// Three streams per clip set: uploads, kernels, downloads.  Step i uses slot i % 3; the slot's events order
+//   upload(i) -> graph(i) -> download(i),   graph(i-3) -> upload(i)  (input staging free),
+//   download(i-3) -> graph(i)               (output staging free),
 // and graphs run in submission order on one stream, which is the recurrence through the history ring.
 int ofs_clips_submit_host(ofs_clips* c, const uint8_t* frames_bgr, uint8_t* out_bgr_u8, float* out_bgr_f32) {
   OFS_REQUIRE(c && frames_bgr && out_bgr_u8, "ofs_clips_submit_host: null pointer");

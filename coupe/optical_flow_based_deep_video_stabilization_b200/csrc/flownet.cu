@@ -26,6 +26,8 @@
 #include "conv_gemm.cuh"
 
 namespace ofs {
+int flow_resize_warp_u8_impl(const uint8_t* img, const float* flow2_prescaled, uint8_t* out_u8, float* out_f32, int B, int H,
+                             int W, int fh, int fw, cudaStream_t st);
 int flow_resize_warp_impl(const float* img, const float* flow2, float* out, int B, int H, int W, int fh, int fw,
                           cudaStream_t st, int prescaled);
 }
@@ -523,6 +525,14 @@ bool net_loaded(const ofs_net* n) { return n->loaded; }
 unsigned net_weights_generation(const ofs_net* n) { return n->weights_generation; }
 int net_prepare(ofs_net* n, int B) { return prepare(n, B); }
 // forward from the pre-filled x0 + fused flow glue / warp of frames -> out (all device pointers), on `st`
+// clip driver: x0 already assembled on the device, uint8 frames in, np.uint8 frames (+ optional float32) out
+int net_stabilize_u8_from_x0(ofs_net* n, const uint8_t* frames, uint8_t* out_u8, float* out_f32, int B, int H, int W,
+                             cudaStream_t st) {
+  int rc = forward_impl(n, kFromX0, B, nullptr, st);
+  if (rc != OFS_OK) return rc;
+  return flow_resize_warp_u8_impl(frames, n->f2s, out_u8, out_f32, B, H, W, 382, 510, st);
+}
+
 int net_stabilize_from_x0(ofs_net* n, const float* frames, float* out, int B, int H, int W, cudaStream_t st) {
   int rc = forward_impl(n, kFromX0, B, nullptr, st);
   if (rc != OFS_OK) return rc;

@@ -565,6 +565,43 @@ __device__ __forceinline__ float div384(float t) {
   return q * 0.0078125f;
 }
 
+// flow at a thread's 2 x 2 pixels (rows oy0, oy0+1; columns ox0+lane, ox0+lane+32) of the fused step --
+// main_dl.py:497-498: TF1 legacy bilinear of the pre-scaled flow, then x * W / 512, y * H / 384
+__device__ __forceinline__ void fused_flow_2x2(const Resize2& rz, int b, int ox0, int oy0, int lane, float2 (&f)[2][2]) {
+  const float2* __restrict__ fb = rz.f2 + (size_t)b * rz.fh * rz.fw;
+  int xa[2], xb[2], ya[2], yb[2];
+  float xl[2], yl[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float ix = (float)(ox0 + lane + 32 * h) * rz.ws;
+    const float fl = floorf(ix);
+    xa[h] = min((int)fl, rz.fw - 1);          // columns past W are never stored; keep the loads in bounds
+    xb[h] = min(xa[h] + 1, rz.fw - 1);
+    xl[h] = ix - fl;
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const float iy = (float)(oy0 + r) * rz.hs;
+    const float fl = floorf(iy);
+    const int y0 = min((int)fl, rz.fh - 1);
+    ya[r] = y0 * rz.fw;
+    yb[r] = min(y0 + 1, rz.fh - 1) * rz.fw;
+    yl[r] = iy - fl;
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float2 tl = __ldg(fb + ya[r] + xa[h]), tr = __ldg(fb + ya[r] + xb[h]);
+      const float2 bl = __ldg(fb + yb[r] + xa[h]), br = __ldg(fb + yb[r] + xb[h]);
+      const float topx = tl.x + (tr.x - tl.x) * xl[h], topy = tl.y + (tr.y - tl.y) * xl[h];
+      const float botx = bl.x + (br.x - bl.x) * xl[h], boty = bl.y + (br.y - bl.y) * xl[h];
+      const float vx = topx + (botx - topx) * yl[r], vy = topy + (boty - topy) * yl[r];
+      f[r][h].x = (vx * rz.Wf) * 0.001953125f;
+      f[r][h].y = div384(vy * rz.Hf);
+    }
+}
+
 template <bool kFused, bool kDirectStore = false>
 __global__ void __launch_bounds__(256, 6) warp5_kernel(const float* __restrict__ img, const float2* __restrict__ flow,
                                                         Resize2 rz, float* __restrict__ out, int B, int H, int W) {
@@ -581,39 +618,7 @@ __global__ void __launch_bounds__(256, 6) warp5_kernel(const float* __restrict__
     // ---- flow at this thread's 2 x 2 pixels (rows oy0, oy0+1; columns ox0+lane, ox0+lane+32)
     float2 f[2][2];
     if (kFused) {
-      // main_dl.py:497-498: TF1 legacy bilinear of the pre-scaled flow, then x * W / 512, y * H / 384
-      const float2* __restrict__ fb = rz.f2 + (size_t)b * rz.fh * rz.fw;
-      int xa[2], xb[2], ya[2], yb[2];
-      float xl[2], yl[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float ix = (float)(ox0 + lane + 32 * h) * rz.ws;
-        const float fl = floorf(ix);
-        xa[h] = min((int)fl, rz.fw - 1);          // columns past W are never stored; keep the loads in bounds
-        xb[h] = min(xa[h] + 1, rz.fw - 1);
-        xl[h] = ix - fl;
-      }
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const float iy = (float)(oy0 + r) * rz.hs;
-        const float fl = floorf(iy);
-        const int y0 = min((int)fl, rz.fh - 1);
-        ya[r] = y0 * rz.fw;
-        yb[r] = min(y0 + 1, rz.fh - 1) * rz.fw;
-        yl[r] = iy - fl;
-      }
-#pragma unroll
-      for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float2 tl = __ldg(fb + ya[r] + xa[h]), tr = __ldg(fb + ya[r] + xb[h]);
-          const float2 bl = __ldg(fb + yb[r] + xa[h]), br = __ldg(fb + yb[r] + xb[h]);
-          const float topx = tl.x + (tr.x - tl.x) * xl[h], topy = tl.y + (tr.y - tl.y) * xl[h];
-          const float botx = bl.x + (br.x - bl.x) * xl[h], boty = bl.y + (br.y - bl.y) * xl[h];
-          const float vx = topx + (botx - topx) * yl[r], vy = topy + (boty - topy) * yl[r];
-          f[r][h].x = (vx * rz.Wf) * 0.001953125f;
-          f[r][h].y = div384(vy * rz.Hf);
-        }
+      fused_flow_2x2(rz, b, ox0, oy0, lane, f);
     } else {
       const float2* __restrict__ fb = flow + (size_t)b * H * W;
 #pragma unroll
@@ -665,6 +670,87 @@ __global__ void __launch_bounds__(256, 6) warp5_kernel(const float* __restrict__
         } else {
           store_row3(obuf[wid], out + (((size_t)b * H + oy) * W + ox0) * 3, lane, valid_px, v[0], v[1]);
         }
+      }
+    }
+  }
+}
+
+// The clip driver's warp (main_dl.py:568-569, :625, :630) on the uint8 frame itself:
+//   resizedInput = cvtColor(frame, RGB2BGR) / 255.0 (float64 quotient, float32 at the feed), tf_warp, then
+//   totaloutputFrame = cvtColor(warped * 255, RGB2BGR) in float32 and np.uint8() of it.
+// The two channel swaps cancel, so output byte k is computed from source byte k.  byte / 255 in the reference's
+// rounding is q = v * RN(1/255), r = fma(-q, 255, v), q' = fma(r, RN(1/255), q): equal to
+// (float)((double)v / 255.0) for all 256 byte values (tests/test_gpu_clip.py checks every one of them).
+// 3 bytes in and 3 bytes out per pixel instead of three kernels moving 12 + 24 + 15.
+__device__ __forceinline__ float byte_over_255(uint32_t v) {
+  const float c = 0.00392156885936856270f;   // RN(1/255)
+  const float x = (float)v;
+  const float q = x * c;
+  const float r = __fmaf_rn(-q, 255.0f, x);
+  return __fmaf_rn(r, c, q);
+}
+
+template <bool kWantF32>
+__global__ void __launch_bounds__(256, 6) warp5_u8_kernel(const uint8_t* __restrict__ img, Resize2 rz,
+                                                           uint8_t* __restrict__ out_u8, float* __restrict__ out_f32,
+                                                           int B, int H, int W) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int Wm1 = W - 1, Hm1 = H - 1;
+  const int b = blockIdx.z;
+  const int ox0 = blockIdx.x * kTileW, oy0 = blockIdx.y * kTileH + wid * 2;
+  const uint8_t* __restrict__ imgb = img + (size_t)b * H * W * 3;
+  float2 f[2][2];
+  fused_flow_2x2(rz, b, ox0, oy0, lane, f);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int oy = oy0 + r;
+    if (oy < H) {   // warp-uniform
+      uint32_t packed[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ox = ox0 + lane + 32 * h;
+        const float x = (float)ox + f[r][h].x, y = (float)oy + f[r][h].y;
+        const int xi = __float2int_rz(x), yi = __float2int_rz(y);
+        const int x0 = clip_i(xi, 0, Wm1), y0 = clip_i(yi, 0, Hm1);
+        const int x1 = (xi >= Wm1) ? Wm1 : max(xi + 1, 0);
+        const int y1 = (yi >= Hm1) ? Hm1 : max(yi + 1, 0);
+        const float dx1 = (float)x1 - x, dx0 = x - (float)x0, dy1 = (float)y1 - y, dy0 = y - (float)y0;
+        const float wa = dx1 * dy1, wb = dx1 * dy0, wc = dx0 * dy1, wd = dx0 * dy0;
+        const int r0 = y0 * W, r1 = y1 * W;
+        const uint8_t* pa = imgb + (r0 + x0) * 3;
+        const uint8_t* pb = imgb + (r1 + x0) * 3;
+        const uint8_t* pc = imgb + (r0 + x1) * 3;
+        const uint8_t* pd = imgb + (r1 + x1) * 3;
+        packed[h] = 0;
+        if (ox < W) {
+          float v[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const float a = byte_over_255(__ldg(pa + k)), bb = byte_over_255(__ldg(pb + k));
+            const float cc = byte_over_255(__ldg(pc + k)), d = byte_over_255(__ldg(pd + k));
+            // tf.add_n([wa*Ia, wb*Ib, wc*Ic, wd*Id]): rounded products, summed left to right; then * 255 (float32)
+            const float s = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wa, a), __fmul_rn(wb, bb)), __fmul_rn(wc, cc)), __fmul_rn(wd, d));
+            v[k] = __fmul_rn(s, 255.0f);
+            packed[h] |= (uint32_t)(__float2int_rz(v[k]) & 0xff) << (8 * k);   // np.uint8(): truncate, keep the low 8 bits
+          }
+          if (kWantF32) {
+            float* o = out_f32 + (((size_t)b * H + oy) * W + ox) * 3;
+            __stcs(o, v[0]); __stcs(o + 1, v[1]); __stcs(o + 2, v[2]);
+          }
+        }
+      }
+      // 32 lanes x 3 bytes -> 24 aligned 32-bit words per half row: word w takes its bytes from lanes 4w/3 and 4w/3 + 1
+      const int src = (4 * lane) / 3, sh = 8 * (lane % 3);
+      uint8_t* orow = out_u8 + (((size_t)b * H + oy) * W + ox0) * 3;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t lo = __shfl_sync(0xffffffffu, packed[h], src & 31);
+        const uint32_t hi = __shfl_sync(0xffffffffu, packed[h], (src + 1) & 31);
+        const uint32_t word = (lo >> sh) | (hi << (24 - sh));
+        // W % 4 == 0: the valid part of a half row is a whole number of words
+        if (lane < 24 && ox0 + 32 * h + (4 * lane) / 3 < W) __stcs(reinterpret_cast<uint32_t*>(orow + 96 * h) + lane, word);
       }
     }
   }
@@ -910,6 +996,21 @@ int flow_resize_warp_impl(const float* img, const float* flow2, float* out, int 
   if ((W % 4) == 0 && (((uintptr_t)out) % 16 == 0)) return launch_warp3(prov, img, out, B, H, W, st);
   const size_t px = (size_t)B * H * W;
   sample_px_kernel<ResizeWarpProvider><<<grid_for(px, 256), 256, 0, st>>>(prov, img, out, B, H, W, H, W, 3);
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
+}
+
+// clip driver: uint8 BGR frame in, np.uint8(totaloutputFrame) out (+ the float32 totaloutputFrame when out_f32 != null)
+int flow_resize_warp_u8_impl(const uint8_t* img, const float* flow2_prescaled, uint8_t* out_u8, float* out_f32, int B, int H,
+                             int W, int fh, int fw, cudaStream_t st) {
+  OFS_REQUIRE(B > 0 && fh > 0 && fw > 0 && H > 0 && W > 0, "flow_resize_warp_u8: bad shape");
+  OFS_REQUIRE(img && flow2_prescaled && out_u8, "flow_resize_warp_u8: null pointer");
+  OFS_REQUIRE((W % 4) == 0 && ((uintptr_t)out_u8) % 4 == 0, "flow_resize_warp_u8: W %% 4 != 0 or unaligned output");
+  Resize2 rz{reinterpret_cast<const float2*>(flow2_prescaled), fh, fw, (float)fh / (float)H, (float)fw / (float)W, (float)W, (float)H};
+  if (out_f32)
+    OFS_CUDA(launch_pdl(warp5_u8_kernel<true>, tile_grid3(B, H, W), dim3(256), 0, st, img, rz, out_u8, out_f32, B, H, W));
+  else
+    OFS_CUDA(launch_pdl(warp5_u8_kernel<false>, tile_grid3(B, H, W), dim3(256), 0, st, img, rz, out_u8, out_f32, B, H, W));
   OFS_LAUNCH_CHECK();
   return OFS_OK;
 }

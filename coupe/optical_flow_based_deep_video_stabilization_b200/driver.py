@@ -35,21 +35,22 @@ def stabilize_video(src_path, dst_path, ckpt=None, net=None, scope="flownetS", d
     os.makedirs(os.path.dirname(os.path.abspath(dst_path)) or ".", exist_ok=True)
     out = cv2.VideoWriter(dst_path, cv2.VideoWriter_fourcc("M", "J", "P", "G"), fps, (out_w, out_h))   # :483-487
     stab = ClipStabilizer(net, n_clips=1, height=out_h, width=out_w)
-    # two page-locked frame / result buffers: frame i+1 is decoded and uploaded, frame i-1 downloaded and encoded,
-    # while the GPU works on frame i
-    fin = [stab.pinned_buffer() for _ in range(2)]
-    fout = [stab.pinned_buffer() for _ in range(2)]
+    # page-locked frame / result buffers in rotation: frame i+1 is decoded and uploaded, frame i-1 downloaded and
+    # encoded, while the GPU works on frame i
+    depth = stab.depth
+    fin = [stab.pinned_buffer() for _ in range(depth)]
+    fout = [stab.pinned_buffer() for _ in range(depth)]
     written = 0
     try:
         for i in range(max(total_frames, 0)):                                        # main_dl.py:540
             ret_unstab, frame_unstab = cap.read()                                    # :547
             if not ret_unstab:
                 break                                                                # the reference would crash in cv2.resize
-            if stab.in_flight == 2:
+            if stab.in_flight == depth:
                 out.write(stab.wait()[0])                                            # :630
                 written += 1
-            fin[i % 2][0] = frame_unstab
-            stab.submit(fin[i % 2], out=fout[i % 2])                                 # :550-625
+            fin[i % depth][0] = frame_unstab
+            stab.submit(fin[i % depth], out=fout[i % depth])                                 # :550-625
         while stab.in_flight:
             out.write(stab.wait()[0])
             written += 1

@@ -171,7 +171,7 @@ int ofs_net_launches_per_forward(const ofs_net* net);
  * ofs_clips_step_host is synchronous.  ofs_clips_submit_host / ofs_clips_wait are the same step split in two so
  * that the upload of frame i+1 and the download of frame i-1 overlap the kernels of frame i (the input frames do
  * not depend on earlier outputs; the recurrence through the history ring stays ordered on the device): at most
- * 2 steps may be in flight, ofs_clips_wait blocks until the OLDEST one has landed in its host buffers, which must
+ * ofs_clips_depth() (= 3) steps may be in flight, ofs_clips_wait blocks until the OLDEST one has landed in its host buffers, which must
  * stay valid (and should be page-locked) until then.  Results are identical to stepping synchronously. */
 typedef struct ofs_clips ofs_clips;
 int ofs_clips_create(ofs_clips** clips, ofs_net* net, int n_clips, int H, int W);
@@ -182,6 +182,7 @@ int ofs_clips_step_host(ofs_clips* clips, const uint8_t* frames_bgr, uint8_t* ou
 int ofs_clips_submit_host(ofs_clips* clips, const uint8_t* frames_bgr, uint8_t* out_bgr_u8, float* out_bgr_f32);
 int ofs_clips_wait(ofs_clips* clips);
 int ofs_clips_in_flight(const ofs_clips* clips); /* submitted, not yet waited for */
+int ofs_clips_depth(void);                        /* how many steps may be in flight */
 
 /* ------------------------------------------------------------------------------------------
  * Stand-alone implicit-GEMM convolution on the same tcgen05 kernel the network uses (unit

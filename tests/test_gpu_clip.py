@@ -87,7 +87,7 @@ def test_clip_driver_matches_reference_loop(ofs, cuda_dev, n_clips, T, H, W):
 
 
 def test_pipelined_submit_wait_equals_stepping(ofs, cuda_dev):
-    """submit / wait (two steps in flight, upload and download overlapping the kernels) returns exactly what the
+    """submit / wait (`depth` steps in flight, upload and download overlapping the kernels) returns exactly what the
     synchronous step returns, frame for frame, through a ring wrap; depth and ordering errors are reported."""
     n_clips, T, H, W = 2, 40, 96, 128
     net = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=2)
@@ -97,18 +97,20 @@ def test_pipelined_submit_wait_equals_stepping(ofs, cuda_dev):
     want = [sync.step(np.ascontiguousarray(clips[:, i]), return_float=True) for i in range(T)]
     sync.close()
     pipe = ofs.ClipStabilizer(net, n_clips=n_clips, height=H, width=W)
-    fin = [pipe.pinned_buffer() for _ in range(2)]
-    fout = [pipe.pinned_buffer() for _ in range(2)]
+    depth = pipe.depth
+    assert depth >= 2
+    fin = [pipe.pinned_buffer() for _ in range(depth)]
+    fout = [pipe.pinned_buffer() for _ in range(depth)]
     got = []
     for i in range(T):
-        if pipe.in_flight == 2:
+        if pipe.in_flight == depth:
             u8, f32 = pipe.wait()
             got.append((u8.copy(), f32.copy()))
-        fin[i % 2][...] = clips[:, i]
-        pipe.submit(fin[i % 2], return_float=True, out=fout[i % 2])
+        fin[i % depth][...] = clips[:, i]
+        pipe.submit(fin[i % depth], return_float=True, out=fout[i % depth])
         assert pipe.frame_index == i + 1
     with pytest.raises(RuntimeError, match="in flight"):
-        pipe.submit(fin[0], out=fout[0])                                             # a third step is refused
+        pipe.submit(fin[0], out=fout[0])                                             # one more than `depth` is refused
     with pytest.raises(RuntimeError, match="not yet waited"):
         pipe.step(fin[0])
     while pipe.in_flight:
@@ -126,6 +128,27 @@ def test_pipelined_submit_wait_equals_stepping(ofs, cuda_dev):
     assert pipe.in_flight == 0 and pipe.frame_index == 0
     np.testing.assert_array_equal(pipe.step(np.ascontiguousarray(clips[:, 0])), want[0][0])
     pipe.close()
+    net.close()
+
+
+def test_every_byte_value_through_the_uint8_warp(ofs, cuda_dev):
+    """Zero flow heads make the warp the identity in the interior, so the step's output is
+    float32(float32(v / 255.0) * 255) per byte (main_dl.py:568, :625) -- for all 256 values v, which pins the
+    on-the-fly v / 255 of the uint8 warp kernel to the reference's float64 quotient rounded to float32."""
+    H, W = 96, 128
+    net = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=1)
+    net.assign_weights(F.make_weights(0, "he", head_scale=0.0))
+    frame = (np.arange(H * W * 3, dtype=np.int64) % 256).astype(np.uint8).reshape(H, W, 3)
+    frame = np.ascontiguousarray(frame[:, ::-1])                                     # any arrangement holding all values
+    assert len(np.unique(frame[:-1, :-1])) == 256
+    stab = ofs.ClipStabilizer(net, n_clips=1, height=H, width=W)
+    u8, f32 = stab.step(frame, return_float=True)
+    want_f32 = (frame / 255.0).astype(np.float32) * np.float32(255)                  # cvtColor swaps cancel
+    want_f32[-1, :] = 0                                                              # x1 == x0 / y1 == y0 at the far border:
+    want_f32[:, -1] = 0                                                              # all four weights vanish (main_dl.py:96-118)
+    np.testing.assert_array_equal(f32, want_f32)
+    np.testing.assert_array_equal(u8, want_f32.astype(np.int32).astype(np.uint8))
+    stab.close()
     net.close()
 
 
