@@ -5,9 +5,9 @@
 // (main_dl.py:550-569).  Only np.uint8() versions of the history are ever consumed (main_dl.py:556-558, :630), and a
 // frame is re-used by up to 8 later steps (offsets 31,23,15,7,4,3,2,1).  So the device keeps, per clip, a 32-slot
 // ring of the RESIZED (512x384), channel-swapped uint8 outputs; a step uploads one uint8 frame (2.8 MB at 720p
-// instead of 32 MB of float32), resizes it once, assembles the 27-channel network input from the ring through two
-// 256-entry look-up tables, runs forward + flow glue + warp, converts the warped frame to np.uint8 semantics,
-// resizes it into the ring and downloads the uint8 frame.  n clips advance in lockstep as one batch.
+// instead of 32 MB of float32), resizes it once, assembles the 27-channel network input from the ring, runs forward +
+// flow glue, warps the uint8 frame itself into the np.uint8 output frame (ofs::flow_resize_warp_u8_impl), resizes that
+// into the ring and downloads it.  n clips advance in lockstep as one batch; up to 3 steps are in flight.
 //
 // Arithmetic restated exactly (the GPU test replays main_dl.py:540-630 with cv2 on the host and compares bytes):
 //   * cv2.resize(u8, (512,384)) INTER_LINEAR: OpenCV's fixed-point path -- coefficients cvRound(f * 2048) from
@@ -88,33 +88,56 @@ __global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restric
   }
 }
 
-// curinput (main_dl.py:550-558) straight into the network's packed 16-bit input: 8 history taps + current frame
-__global__ void __launch_bounds__(256) assemble_x0_kernel(const uint8_t* __restrict__ ring, size_t ring_clip_stride,
+// byte / 255 in float32.  The reference divides the history taps in float32 (np.float32(u8) / 255.0, main_dl.py:556-558)
+// and the current frame in float64 before the feed casts it to float32 (:550, :568); the two agree for every byte
+// value, and both equal q' = fma(fma(-q, 255, v), RN(1/255), q) with q = v * RN(1/255) (checked for all 256 values by
+// ofs_clips_create against the host quotients, so a compiler that contracts differently cannot go unnoticed).
+__device__ __forceinline__ float byte_over_255(uint32_t v) {
+  const float c = 0.00392156885936856270f;   // RN(1/255)
+  const float x = (float)v;
+  const float q = x * c;
+  const float r = __fmaf_rn(-q, 255.0f, x);
+  return __fmaf_rn(r, c, q);
+}
+
+__global__ void byte_over_255_table_kernel(float* out) { out[threadIdx.x] = byte_over_255(threadIdx.x); }
+
+template <bool kBf16>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  if (kBf16) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+  }
+  const __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// curinput (main_dl.py:550-558) straight into the network's packed 16-bit input: 8 history taps + current frame.
+// One pixel per thread: 27 byte loads (a warp reads 96 contiguous bytes per load), the quotients in registers (a
+// 256-entry shared-memory table cost more in bank conflicts than the 3 FMAs it saved), four 16-byte stores.
+template <bool kBf16>
+__global__ void __launch_bounds__(256) assemble_x0_kernel(const uint8_t* __restrict__ ring, uint32_t ring_clip_stride,
                                                           const uint8_t* __restrict__ cur, const StepState* __restrict__ state,
-                                                          const uint16_t* __restrict__ lut_hist,
-                                                          const uint16_t* __restrict__ lut_cur, uint4* __restrict__ x0) {
-  __shared__ uint16_t lh[256], lc[256];
-  lh[threadIdx.x] = lut_hist[threadIdx.x];
-  lc[threadIdx.x] = lut_cur[threadIdx.x];
-  __syncthreads();
+                                                          uint4* __restrict__ x0) {
   const int clip = blockIdx.y;
-  const int px = blockIdx.x * blockDim.x + threadIdx.x;
-  if (px >= kNetH * kNetW) return;
-  uint16_t v[32];
+  const uint32_t px = blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= (uint32_t)(kNetH * kNetW)) return;
+  const uint8_t* rb = ring + (size_t)clip * ring_clip_stride + px * 3u;
+  float v[28];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const uint8_t* s = ring + (size_t)clip * ring_clip_stride + (size_t)state->hist_slot[j] * kSlice + (size_t)px * 3;
-    v[3 * j] = lh[s[0]]; v[3 * j + 1] = lh[s[1]]; v[3 * j + 2] = lh[s[2]];
+    const uint8_t* s = rb + (uint32_t)__ldg(&state->hist_slot[j]) * (uint32_t)kSlice;
+    v[3 * j] = byte_over_255(__ldg(s)); v[3 * j + 1] = byte_over_255(__ldg(s + 1)); v[3 * j + 2] = byte_over_255(__ldg(s + 2));
   }
-  const uint8_t* c = cur + (size_t)clip * kSlice + (size_t)px * 3;
-  v[24] = lc[c[0]]; v[25] = lc[c[1]]; v[26] = lc[c[2]];
-#pragma unroll
-  for (int k = 27; k < 32; ++k) v[k] = 0;
+  const uint8_t* c = cur + (size_t)clip * kSlice + px * 3u;
+  v[24] = byte_over_255(__ldg(c)); v[25] = byte_over_255(__ldg(c + 1)); v[26] = byte_over_255(__ldg(c + 2));
+  v[27] = 0.0f;
   uint4* o = x0 + ((size_t)clip * kNetH * kNetW + px) * 4;
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
-    o[q] = make_uint4((uint32_t)v[8 * q] | ((uint32_t)v[8 * q + 1] << 16), (uint32_t)v[8 * q + 2] | ((uint32_t)v[8 * q + 3] << 16),
-                      (uint32_t)v[8 * q + 4] | ((uint32_t)v[8 * q + 5] << 16), (uint32_t)v[8 * q + 6] | ((uint32_t)v[8 * q + 7] << 16));
+  for (int q = 0; q < 3; ++q)
+    o[q] = make_uint4(pack2<kBf16>(v[8 * q], v[8 * q + 1]), pack2<kBf16>(v[8 * q + 2], v[8 * q + 3]),
+                      pack2<kBf16>(v[8 * q + 4], v[8 * q + 5]), pack2<kBf16>(v[8 * q + 6], v[8 * q + 7]));
+  o[3] = make_uint4(pack2<kBf16>(v[24], v[25]), pack2<kBf16>(v[26], v[27]), 0u, 0u);
 }
 
 // OpenCV resize.cpp: fx = (float)((dx+0.5)*scale_x - 0.5); sx = cvFloor(fx); fx -= sx; edge clamps; cvRound(f * 2048)
@@ -165,7 +188,7 @@ struct ofs_clips {
   long long collected = 0;            // steps waited for
   ClipSlot slot[kSlots];
   uint8_t *d_ring = nullptr, *d_cur = nullptr;
-  uint16_t *d_lut_hist = nullptr, *d_lut_cur = nullptr;
+  float* d_quot = nullptr;
   int *d_sx = nullptr, *d_sy = nullptr;
   short *d_ax = nullptr, *d_ay = nullptr;
   cudaStream_t st = nullptr, st_in = nullptr, st_out = nullptr;
@@ -188,9 +211,14 @@ int enqueue_step(ofs_clips* c, const ClipSlot& s, cudaStream_t st, bool want_f32
   resize_u8_kernel<<<rgrid, 256, 0, st>>>(s.d_frame, H, W, c->d_cur, (size_t)kSlice, s.d_state, 0, c->d_ring, ring_stride,
                                           c->d_sx, c->d_ax, c->d_sy, c->d_ay);
   OFS_LAUNCH_CHECK();
-  assemble_x0_kernel<<<dim3((kNetH * kNetW + 255) / 256, n), 256, 0, st>>>(c->d_ring, ring_stride, c->d_cur, s.d_state,
-                                                                         c->d_lut_hist, c->d_lut_cur,
-                                                                         reinterpret_cast<uint4*>(net_x0(c->net)));
+  {
+    const dim3 agrid((kNetH * kNetW + 255) / 256, n);
+    uint4* x0 = reinterpret_cast<uint4*>(net_x0(c->net));
+    if (net_is_bf16(c->net))
+      assemble_x0_kernel<true><<<agrid, 256, 0, st>>>(c->d_ring, (uint32_t)ring_stride, c->d_cur, s.d_state, x0);
+    else
+      assemble_x0_kernel<false><<<agrid, 256, 0, st>>>(c->d_ring, (uint32_t)ring_stride, c->d_cur, s.d_state, x0);
+  }
   OFS_LAUNCH_CHECK();
   // forward + flow glue + the warp on the uint8 frame: resizedInput (:568), sess.run (:569), * 255 and np.uint8 (:625, :630)
   int rc = net_stabilize_u8_from_x0(c->net, s.d_frame, s.d_out_u8, want_f32 ? s.d_out_f32 : nullptr, n, H, W, st);
@@ -233,8 +261,7 @@ int ofs_clips_create(ofs_clips** out, ofs_net* net, int n_clips, int H, int W) {
   }
   if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_ring, (size_t)n_clips * kRing * kSlice);
   if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_cur, (size_t)n_clips * kSlice);
-  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_lut_hist, 512);
-  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_lut_cur, 512);
+  if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_quot, 1024);
   if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_sx, kNetW * 4);
   if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_sy, kNetH * 4);
   if (rc == OFS_OK) rc = clips_alloc(c, (void**)&c->d_ax, kNetW * 4);
@@ -245,20 +272,23 @@ int ofs_clips_create(ofs_clips** out, ofs_net* net, int n_clips, int H, int W) {
       rc = OFS_ECUDA;
     }
   if (rc == OFS_OK) {
-    const int is_bf16 = net_is_bf16(net);
-    std::vector<uint16_t> lh(256), lc(256);
-    for (int v = 0; v < 256; ++v) {
+    // the device's byte / 255 against the reference's two host quotients, all 256 values
+    float got[256];
+    byte_over_255_table_kernel<<<1, 256>>>(c->d_quot);
+    rc = check_cuda(cudaMemcpy(got, c->d_quot, sizeof(got), cudaMemcpyDeviceToHost), "quotient check", __FILE__, __LINE__);
+    for (int v = 0; v < 256 && rc == OFS_OK; ++v) {
       const float hist = (float)v / 255.0f;                 // np.float32(u8) / 255.0        (main_dl.py:556,558)
       const float cur = (float)((double)v / 255.0);         // u8 / 255.0 -> float32 at the feed (main_dl.py:550,568)
-      lh[v] = is_bf16 ? f32_to_bf16_rn(hist) : f32_to_fp16_rn(hist);
-      lc[v] = is_bf16 ? f32_to_bf16_rn(cur) : f32_to_fp16_rn(cur);
+      if (got[v] != hist || got[v] != cur) {
+        set_error("ofs_clips_create: device %d / 255 = %.9g, reference %.9g / %.9g", v, got[v], hist, cur);
+        rc = OFS_ECUDA;
+      }
     }
     std::vector<int> sx, sy;
     std::vector<short> ax, ay;
     linear_tables(W, kNetW, sx, ax, true);
     linear_tables(H, kNetH, sy, ay, false);
     const struct { void* dst; const void* src; size_t bytes; } ups[] = {
-        {c->d_lut_hist, lh.data(), 512}, {c->d_lut_cur, lc.data(), 512},
         {c->d_sx, sx.data(), (size_t)kNetW * 4}, {c->d_sy, sy.data(), (size_t)kNetH * 4},
         {c->d_ax, ax.data(), (size_t)kNetW * 4}, {c->d_ay, ay.data(), (size_t)kNetH * 4}};
     for (const auto& u : ups)
