@@ -191,9 +191,17 @@ __device__ __forceinline__ void mma(uint32_t d, uint32_t da_lo, uint32_t db_lo, 
 // shared-memory addresses, TMA coordinates and UMMA descriptors in uniform registers.  A loop entered by
 // lane 0 alone (`if (lane == 0)`) makes every operand "possibly divergent" and each UTMALDG / UTCHMMA is then
 // wrapped in an ELECT + R2UR waterfall loop: ~2x the cycles per K block (see profiles/r01_tuning.md).
-template <int BLOCK_N, bool kPair, int kT, int kHead, int kG>
+//
+// kKC (cluster split-K): the ksplit CTAs that share an output tile are one thread-block cluster (rank = K split).
+// Each runs its K range into its own accumulator, parks the fp32 tile in its (now idle) pipeline stages, and after a
+// cluster barrier every CTA sums its share of the tile's ROWS over all peers through distributed shared memory in
+// split order -- bias first, exactly the order of splitk_reduce_kernel, so both paths give the same bits -- and
+// stores final 16-bit activations.  No workspace round trip through L2, no reduce launch.
+template <int BLOCK_N, bool kPair, int kT, int kHead, int kG, bool kKC = false>
 __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
   using Cfg = GemmCfg<BLOCK_N, kPair, kT, kHead, kG>;
+  static_assert(!kKC || (!kPair && kT == 1 && kHead == 0 && kG == 1 && BLOCK_N == 256), "cluster split-K: plain 1-CTA 256-column tiles");
+  static_assert(!kKC || Cfg::kStages * Cfg::kStageBytes >= kBlockM * BLOCK_N * 4, "cluster split-K parks the fp32 tile in the stage buffers");
   static_assert(kG == 1 || kT == 1, "chunk groups and slab groups are exclusive");
   static_assert(kHead == 0 || (!kPair && kT == 1 && BLOCK_N >= 64), "fused head: 1-CTA tiles of 64+ columns");
   constexpr int kNB = Cfg::kNB;
@@ -221,8 +229,11 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
   const int lane = threadIdx.x & 31;
   // the intrinsic behind block_rank() is known to be CTA-uniform (S2UR); a value read through inline asm is not
   const uint32_t rank = kPair ? (uint32_t)cooperative_groups::this_cluster().block_rank() : 0u;
-  const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // scheduling unit: CTA or CTA pair
-  const int nunits = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // cluster split-K: one unit per CTA; cluster rank = K split, which is the slowest digit of the tile index
+  const int kc_rank = kKC ? (int)(blockIdx.x % (unsigned)p.ksplit) : 0;
+  const int unit = kKC ? (int)(blockIdx.x / (unsigned)p.ksplit) + kc_rank * (p.tiles_mp * p.tiles_n * p.phases)
+                       : kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // scheduling unit: CTA or CTA pair
+  const int nunits = kKC ? (1 << 30) : kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&p.tmap_a);
@@ -458,7 +469,27 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
       if (trace && threadIdx.x == 64) { if (tile == unit) trace[5] = clock64(); trace[8] = clock64(); }
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * kNB;
       bool stored = false;
-      if constexpr (BLOCK_N >= 64) {
+      if constexpr (kKC) {
+        // park the raw fp32 accumulator row in the idle stage buffers: [128 rows][256 columns], 16-byte chunks XOR-swizzled
+        // by the row so that a warp's 32 rows spread over the banks
+        stored = true;
+        const uint32_t rowaddr = smem_base + (uint32_t)row * (uint32_t)(BLOCK_N * 4);
+        const uint32_t sw = (uint32_t)(row & 7);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {
+          uint32_t v[64];
+          ptx::tmem_ld32(t_addr + c0, v);
+          ptx::tmem_ld32(t_addr + c0 + 32, v + 32);
+          ptx::tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            ptx::st_shared_v4(rowaddr + ((((uint32_t)(c0 >> 2) + j) ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+      }
+      if constexpr (BLOCK_N >= 64 && !kKC) {
         if (p.tma_store) {
           // 16-bit epilogue: TMEM -> registers -> (+bias, lrelu, pack) -> SW128-swizzled staging rows ->
           // one TMA store per 64-channel chunk and A-style piece.  The staging buffer of chunk c is reused
@@ -648,10 +679,56 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
     }
   }
 
+  if constexpr (kKC) {
+    ptx::cluster_sync();   // every split's partial tile is parked and visible cluster-wide
+    if (trace && threadIdx.x == 64) trace[6] = clock64();
+    const int tile = unit;
+    const int n_t = tile % p.tiles_n;
+    const int m_t = (tile / p.tiles_n) % p.tiles_mp;
+    const int n0 = n_t * BLOCK_N;
+    const int nsplit = p.ksplit;
+    const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0);
+    // rows kc_rank, kc_rank + nsplit, ... of the tile belong to this CTA; its 7 warps take them in turn
+    for (int row = kc_rank + nsplit * warp; row < kBlockM; row += nsplit * (kThreads / 32)) {
+      const int ty = row >> p.tileW_log2;
+      const int gy = (m_t / p.tiles_x) * p.tile_rows + ty;
+      const int gx = ((m_t % p.tiles_x) << p.tileW_log2) + (row & (tileW - 1));
+      const bool valid = (m_t < p.tiles_m) && (ty < p.tile_rows) && (gy < p.rows_total) && !(p.debug & 8);
+      if (!valid) continue;   // warp-uniform
+      const int b = gy / p.Hg;
+      const int y = gy - b * p.Hg;
+      const size_t pix = ((size_t)b * p.out_H + (size_t)(y * p.out_scale + p.out_oy[0])) * p.out_W + (size_t)(gx * p.out_scale + p.out_ox[0]);
+      const uint32_t rowaddr = smem_base + (uint32_t)row * (uint32_t)(BLOCK_N * 4);
+      const uint32_t sw = (uint32_t)(row & 7);
+      const uint32_t a0 = rowaddr + ((((uint32_t)lane) ^ sw) << 4), a1 = rowaddr + ((((uint32_t)lane + 32u) ^ sw) << 4);
+      float4 part0[8], part1[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < nsplit) {   // all the remote loads in flight before the first add
+          part0[k] = ptx::ld_shared_cluster_v4(ptx::mapa_u32(a0, (uint32_t)k));
+          part1[k] = ptx::ld_shared_cluster_v4(ptx::mapa_u32(a1, (uint32_t)k));
+        }
+      float4 s0 = __ldg(bias4 + lane), s1 = __ldg(bias4 + lane + 32);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < nsplit) {
+          s0.x += part0[k].x; s0.y += part0[k].y; s0.z += part0[k].z; s0.w += part0[k].w;
+          s1.x += part1[k].x; s1.y += part1[k].y; s1.z += part1[k].z; s1.w += part1[k].w;
+        }
+      if (p.lrelu) {
+        s0.x = fmaxf(s0.x, 0.1f * s0.x); s0.y = fmaxf(s0.y, 0.1f * s0.y); s0.z = fmaxf(s0.z, 0.1f * s0.z); s0.w = fmaxf(s0.w, 0.1f * s0.w);
+        s1.x = fmaxf(s1.x, 0.1f * s1.x); s1.y = fmaxf(s1.y, 0.1f * s1.y); s1.z = fmaxf(s1.z, 0.1f * s1.z); s1.w = fmaxf(s1.w, 0.1f * s1.w);
+      }
+      uint2* o = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + pix * p.out_cstride + p.out_coff + n0);
+      o[lane] = make_uint2(pack16(s0.x, s0.y, p.is_bf16), pack16(s0.z, s0.w, p.is_bf16));
+      o[lane + 32] = make_uint2(pack16(s1.x, s1.y, p.is_bf16), pack16(s1.z, s1.w, p.is_bf16));
+    }
+    if (trace && threadIdx.x == 64) trace[10] = clock64();
+  }
   ptx::tc_fence_before();
   __syncthreads();
   if (trace && threadIdx.x == 0) { trace[7] = (long long)ptx::globaltimer(); trace[9] = clock64(); }
-  if constexpr (kPair) ptx::cluster_sync();  // no CTA frees TMEM or exits while the pair still references it
+  if constexpr (kPair || kKC) ptx::cluster_sync();  // no CTA frees TMEM / leaves while a peer still references it (pair MMAs, DSMEM reads)
   if (warp == 1) {
     const uint32_t tmem_base = *tmem_slot;
     if constexpr (kPair) ptx::tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
@@ -663,6 +740,11 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   conv_gemm_body<BLOCK_N, false, 1, 0, 1>(p);
+}
+// split-K inside a thread-block cluster of ksplit CTAs (cluster size set at launch)
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1) conv_gemmk_kernel(const __grid_constant__ ConvGemmParams p) {
+  conv_gemm_body<BLOCK_N, false, 1, 0, 1, true>(p);
 }
 // transposed conv with the level's flow head fused as 16 extra accumulator columns
 template <int BLOCK_N>
@@ -820,6 +902,33 @@ int launch_t2(const ConvPlan& plan, cudaStream_t st) {
   }
   pdl_set_kind(1);
   OFS_CUDA(launch_pdl(conv_gemm2_kernel<BLOCK_N>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, true>::kSmem, st, plan.p));
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
+}
+
+template <int BLOCK_N>
+int launch_tk(const ConvPlan& plan, cudaStream_t st) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  OFS_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    OFS_CUDA(cudaFuncSetAttribute(conv_gemmk_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)GemmCfg<BLOCK_N, false>::kSmem));
+    attr_set[dev] = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(plan.grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = GemmCfg<BLOCK_N, false>::kSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)plan.p.ksplit;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OFS_CUDA(cudaLaunchKernelEx(&cfg, conv_gemmk_kernel<BLOCK_N>, plan.p));
   OFS_LAUNCH_CHECK();
   return OFS_OK;
 }
@@ -1140,15 +1249,21 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
     p.kb_per_split = (num_kb + ks - 1) / ks;
     p.ksplit = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
     p.ws_split_stride = (long long)d.B * p.out_H * p.out_W * p.n_pad;
-    plan.ws_bytes = p.ksplit > 1 ? (size_t)p.ksplit * p.ws_split_stride * 4 : 0;
-    if (p.ksplit > 1) p.out_mode = 2;
+    p.kcluster = (d.kcluster && p.ksplit > 1) ? 1 : 0;
+    OFS_REQUIRE(!p.kcluster || (p.ksplit <= 8 && d.block_n == 256 && d.cta_group == 1 && !d.head && !p.slab && d.kgroup == 1 && !deconv),
+                "cluster split-K: ksplit <= 8, block_n 256, plain 1-CTA convolution tiles (got ksplit %d block_n %d)", p.ksplit, d.block_n);
+    plan.ws_bytes = (p.ksplit > 1 && !p.kcluster) ? (size_t)p.ksplit * p.ws_split_stride * 4 : 0;
+    if (p.ksplit > 1 && !p.kcluster) p.out_mode = 2;
   }
   // 1: 16-bit activations; 2: raw fp32 split-K partials into the workspace (plain convs: the workspace pixel index
   // is the output pixel index)
-  p.tma_store = (p.out_mode == 0 && d.block_n >= 64) ? 1 : (p.out_mode == 2 && d.block_n >= 64 && !deconv) ? 2 : 0;
+  p.tma_store = p.kcluster ? 0 : (p.out_mode == 0 && d.block_n >= 64) ? 1 : (p.out_mode == 2 && d.block_n >= 64 && !deconv) ? 2 : 0;
   p.tiles_mp = d.cta_group == 2 ? (p.tiles_m + 1) / 2 : p.tiles_m;
   const int total_tiles = p.tiles_mp * p.tiles_n * p.phases * p.ksplit;
-  if (d.kgroup == 2) {
+  if (p.kcluster) {
+    plan.grid = total_tiles;   // one CTA per (tile, K split); clusters are gang-scheduled, a second wave is merely slower
+    plan.smem = GemmCfg<256, false>::kSmem;
+  } else if (d.kgroup == 2) {
     plan.grid = std::max(1, std::min(total_tiles, sm_count()));
     plan.smem = d.block_n == 64 ? (d.head ? GemmCfg<64, false, 1, 16, 2>::kSmem : GemmCfg<64, false, 1, 0, 2>::kSmem)
                                 : (d.head ? GemmCfg<128, false, 1, 16, 2>::kSmem : GemmCfg<128, false, 1, 0, 2>::kSmem);
@@ -1251,7 +1366,7 @@ int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const 
   plan.final_out = out;
   plan.bias_dev = bias_dev;
   plan.ws = workspace;
-  if (p.ksplit > 1) {
+  if (p.ksplit > 1 && !p.kcluster) {
     OFS_REQUIRE(workspace && ((uintptr_t)workspace) % 16 == 0, "conv bind: split-K needs a 16-byte aligned workspace");
     p.out = workspace;
   } else {
@@ -1297,7 +1412,9 @@ int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const 
 
 int conv_launch(const ConvPlan& plan, cudaStream_t st) {
   int rc = OFS_EINVAL;
-  if (plan.d.kgroup == 2) {
+  if (plan.p.kcluster) {
+    return launch_tk<256>(plan, st);
+  } else if (plan.d.kgroup == 2) {
     if (plan.block_n == 64) rc = plan.d.head ? launch_tg<64, 16>(plan, st) : launch_tg<64, 0>(plan, st);
     else if (plan.block_n == 128) rc = plan.d.head ? launch_tg<128, 16>(plan, st) : launch_tg<128, 0>(plan, st);
     else { set_error("conv_launch: chunk groups need block_n 64 or 128 (got %d)", plan.block_n); return OFS_EINVAL; }
@@ -1379,6 +1496,7 @@ extern "C" int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const flo
   d.cta_group = (cta_group == 2 || cta_group == 4) ? 2 : 1;
   d.slab = cta_group == 4 ? 1 : 0;   // 4 = CTA pairs + slab groups
   d.kgroup = cta_group == 8 ? 2 : 1; // 8 = two K chunks per pipeline stage
+  d.kcluster = cta_group == 16 ? 1 : 0;   // 16 = split-K inside a thread-block cluster (DSMEM reduction)
   const bool via16 = d.ksplit > 1 || out16;   // the network's 16-bit activation epilogue (split-K always reduces into it)
   const int cout8 = ((Cout + 7) / 8) * 8;
   d.out_mode = via16 ? 0 : 1; d.lrelu = lrelu; d.is_bf16 = is_bf16;
@@ -1476,6 +1594,7 @@ extern "C" int ofs_conv2d_bench(int B, int H, int W, int Cin, int in_cs, int Cou
   d.kind = transposed ? kDeconvK4S2 : kConv;
   d.B = B; d.H = H; d.W = W; d.cin = Cin; d.in_cs = in_cs; d.cout = Cout; d.k = k; d.stride = stride;
   d.block_n = block_n; d.ksplit = ksplit > 1 ? ksplit : 1; d.cta_group = (cta_group == 2 || cta_group == 4) ? 2 : 1; d.slab = cta_group == 4 ? 1 : 0; d.kgroup = cta_group == 8 ? 2 : 1; d.debug = debug;
+  d.kcluster = cta_group == 16 ? 1 : 0;
   const bool out16 = (Cout % block_n) == 0 || (!transposed && block_n >= 64 && Cout % 64 == 0 && ksplit <= 1);
   d.out_mode = out16 ? 0 : 1; d.lrelu = 1; d.is_bf16 = 1; d.out_cstride = out_cs; d.out_coff = 0;
   ConvPlan plan;

@@ -33,6 +33,7 @@ struct ConvGemmParams {
   int phases;          // 1 (conv) or 4 (transposed conv sub-pixel phases)
   int ksplit;          // split-K factor (partials go to an fp32 workspace, reduced by splitk_reduce_kernel)
   int kb_per_split;    // K blocks per split
+  int kcluster;        // 1: the ksplit CTAs of a tile form one cluster and reduce their partials through DSMEM
   long long ws_split_stride;  // workspace elements between two splits = out pixels * n_pad
   int ntaps, nchunks;  // K_total = ntaps * nchunks * 64
   int n_pad;           // padded output channels per phase
@@ -77,6 +78,7 @@ struct ConvDesc {
   int out_mode, lrelu, is_bf16;
   int out_cstride, out_coff;
   int ksplit = 1;      // > 1: split the K loop over this many CTAs per tile (16-bit output mode only)
+  int kcluster = 0;    // 1: split-K inside a thread-block cluster (ksplit <= 8, block_n 256, 1-CTA tiles): no workspace, no reduce kernel
   int cta_group = 1;   // 2: CTA pairs (tcgen05 cta_group::2): tile = 256 GEMM rows x BLOCK_N, B split over the pair
   int kgroup = 1;      // 2: two consecutive 64-channel K blocks of a tap per pipeline stage (narrow-N layers)
   int head = 0;        // 1: transposed conv with the level's 3x3 flow head fused as 16 extra accumulator columns

@@ -366,6 +366,7 @@ int prepare(ofs_net* n, int B) {
       }
     }
     if (cg == 8 && !L.d.slab) { L.d.kgroup = 2; cg = 1; }   // OFS_TUNE cta_group 8 = chunk groups
+    const bool kc = cg == 16 && ks > 1 && ks <= 8 && bn == 256 && !L.d.slab && L.d.out_mode == 0;   // 16 = cluster split-K
     if (L.d.kgroup == 2) { rc = conv_plan_geometry(L.plan, L.d); if (rc != OFS_OK) return rc; }
     if (ks > 1 || bn != L.d.block_n || cg == 2 || dbg) {
       ConvDesc d = L.d;
@@ -373,6 +374,7 @@ int prepare(ofs_net* n, int B) {
       d.cta_group = cg == 2 ? 2 : 1;
       d.debug = dbg;
       d.ksplit = (L.d.out_mode == 0 && ks > 1) ? ks : 1;
+      d.kcluster = kc ? 1 : 0;
       rc = conv_plan_geometry(L.plan, d);
       if (rc != OFS_OK) return rc;
     }

@@ -114,6 +114,12 @@ TILING_CASES = [
     pytest.param(3, 10, 256, 64, 128, 5, 2, False, 128, -1, 4, id="slab_conv2_form_odd_tiles_out16"),
     pytest.param(1, 8, 256, 16, 64, 3, 2, False, 64, 1, 4, id="slab_k3_paired"),
     pytest.param(1, 8, 256, 64, 64, 3, 2, False, 64, 1, 4, id="slab_k3_cin64"),
+    # cluster split-K (cta_group = 16: the K splits of a tile are one thread-block cluster, reduced through DSMEM)
+    pytest.param(3, 6, 8, 512, 512, 3, 1, False, 256, 8, 16, id="kcluster8_whole_image_tiles_ragged_batch"),
+    pytest.param(2, 12, 16, 256, 256, 3, 2, False, 256, 4, 16, id="kcluster4_k3s2"),
+    pytest.param(1, 24, 32, 128, 512, 3, 1, False, 256, 6, 16, id="kcluster6_two_n_tiles"),
+    pytest.param(2, 6, 8, 320, 256, 3, 1, False, 256, 7, 16, id="kcluster7_uneven_splits"),
+    pytest.param(8, 6, 8, 1024, 1024, 3, 1, False, 256, 8, 16, id="kcluster8_conv6_1_shape"),
 ]
 
 
@@ -136,6 +142,18 @@ def test_conv_gemm_tilings(ofs, cuda_dev, B, H, W, cin, cout, k, stride, transpo
     ref = T.lrelu(ref, 0.1).float()
     tol = 6e-3 if (ksplit > 1 or out16) else 2e-3
     assert float(((got - ref).abs() / (1 + ref.abs())).max()) <= tol
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,ks", [(8, 12, 16, 512, 512, 4), (8, 6, 8, 512, 1024, 8), (3, 6, 8, 256, 256, 5)])
+def test_cluster_splitk_bit_identical_to_workspace_splitk(ofs, cuda_dev, B, H, W, cin, cout, ks):
+    """The DSMEM reduction adds bias + the partial tiles in split order, as splitk_reduce_kernel does: same bits."""
+    gen = torch.Generator().manual_seed(5 + ks)
+    x = _round(torch.rand((B, H, W, cin), generator=gen), "bf16").to(cuda_dev)
+    w = _round(torch.randn((3, 3, cin, cout), generator=gen) * (1.0 / np.sqrt(9 * cin)), "bf16")
+    b = torch.randn(cout, generator=gen) * 0.1
+    a = ofs.conv2d_nhwc(x, w, b, lrelu=True, precision="bf16", block_n=256, ksplit=ks, cta_group=1).cpu()
+    c = ofs.conv2d_nhwc(x, w, b, lrelu=True, precision="bf16", block_n=256, ksplit=ks, cta_group=16).cpu()
+    assert torch.equal(a, c)
 
 
 @pytest.fixture(scope="module")
