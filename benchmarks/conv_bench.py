@@ -36,10 +36,11 @@ LAYERS = {
     "deconv4": (12, 16, 1026, 1032, 256, 776, 4, 2, 1),
     "deconv3": (24, 32, 770, 776, 128, 392, 4, 2, 1),
     "deconv2": (48, 64, 386, 392, 64, 200, 4, 2, 1),
+    "predict2": (96, 128, 194, 200, 18, 18, 1, 1, 0),
 }
 DEFAULTS = {"1": "64:1:1", "2": "128:1:1", "3": "256:1:1", "3_1": "256:1:1", "4": "256:1:1", "4_1": "256:1:1",
             "5": "256:6:1", "5_1": "256:6:1", "6": "256:8:1", "6_1": "256:8:1", "deconv5": "256:4:1",
-            "deconv4": "256:3:1", "deconv3": "128:1:1", "deconv2": "64:1:1"}
+            "deconv4": "256:3:1", "deconv3": "128:1:1", "deconv2": "64:1:1", "predict2": "32:1:1"}
 
 
 def macs(name, B):
@@ -80,7 +81,7 @@ def main():
             parts = [int(x) for x in v.split(":")]
             bn, ks, cg = parts[0], parts[1], parts[2]
             dbg = parts[3] if len(parts) > 3 else 0
-            if cout % bn != 0 and not (bn == 192 and cout % 64 == 0 and not tr):
+            if cout % bn != 0 and not (bn == 192 and cout % 64 == 0 and not tr) and name != "predict2":
                 continue
             ms = C.c_float(0)
             grid = C.c_int(0)

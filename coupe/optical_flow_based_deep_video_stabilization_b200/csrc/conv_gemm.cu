@@ -583,24 +583,28 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
             if constexpr (kPair) ptx::mbar_arrive_cluster(tempty_tgt0 + 8 * acc);
             else ptx::mbar_arrive(&tempty[acc]);
           }
-          float* sf = reinterpret_cast<float*>(smem + (size_t)S * Cfg::kStageBytes);
+          // each epilogue warp owns 32 consecutive rows = one contiguous run of 32 * n_valid floats: it transposes
+          // them through its own slice of the staging buffer and copies them out itself -- no CTA-wide barrier
+          // (two named barriers per tile made this epilogue, not the loads or the MMAs, the bound of the kernel)
           const int nv = p.n_valid;
-          ptx::named_bar_sync(1, 128);               // the previous tile's copy-out has finished reading the buffer
+          float* sf = reinterpret_cast<float*>(smem + (size_t)S * Cfg::kStageBytes) + quad * 32 * nv;
+          __syncwarp();                              // this warp's previous copy-out has finished reading its slice
 #pragma unroll
           for (int j = 0; j < BLOCK_N; ++j)
             if (j < nv) {
               float a = __uint_as_float(v[j]) + __ldg(p.bias + j);
               if (p.lrelu) a = fmaxf(a, 0.1f * a);
-              sf[row * nv + j] = a;
+              sf[lane * nv + j] = a;
             }
-          ptx::named_bar_sync(1, 128);
+          __syncwarp();
           const int gy0 = (m_t / p.tiles_x) * p.tile_rows;
           const int rows_valid = min(p.tile_rows, p.rows_total - gy0);
           if (m_t < p.tiles_m && rows_valid > 0 && !(p.debug & 8)) {
             const int nflt = rows_valid * tileW * nv;            // multiple of 2 (nv even); tile base is 8-byte aligned
-            float2* dst = reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + (size_t)gy0 * p.Wg * nv);
+            const int w0 = quad * 32 * nv, w1 = min(nflt, w0 + 32 * nv);
+            float2* dst = reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + (size_t)gy0 * p.Wg * nv + w0);
             const float2* src = reinterpret_cast<const float2*>(sf);
-            for (int i = (int)threadIdx.x - 64; i < (nflt >> 1); i += 128) dst[i] = src[i];
+            for (int i = lane; i < ((w1 - w0) >> 1); i += 32) dst[i] = src[i];
           }
         }
       }
