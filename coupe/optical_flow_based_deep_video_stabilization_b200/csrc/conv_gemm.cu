@@ -264,7 +264,15 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
   pdl_launch_dependents();
 
   const int num_kb = p.ntaps * p.nchunks;
-  const int total_tiles = p.tiles_mp * p.tiles_n * p.phases * p.ksplit;
+  // tail split (see ConvGemmParams::tail_t0): only compiled into the plain 256-column kernels
+  constexpr bool kTail = BLOCK_N == 256 && kT == 1 && kHead == 0 && kG == 1 && !kKC;
+  const int tail_t0 = kTail ? p.tail_t0 : 0x7fffffff;
+  const int total_tiles = p.tiles_mp * p.tiles_n * p.phases * p.ksplit + ((kTail && tail_t0 < p.tiles_mp) ? p.tiles_mp - tail_t0 : 0);
+  // unit -> (N tile, everything else, which half): half = -1 for a full tile
+  auto decode_tile = [&](int tile, int& n_t, int& rest, int& half) {
+    if (kTail && tile >= tail_t0) { const int t = tile - tail_t0; n_t = 0; rest = tail_t0 + (t >> 1); half = t & 1; }
+    else { n_t = tile % p.tiles_n; rest = tile / p.tiles_n; half = -1; }
+  };
   const int tileW = 1 << p.tileW_log2;
   long long* trace = p.trace ? p.trace + (size_t)blockIdx.x * 32 : nullptr;
   if (trace && threadIdx.x == 0) { trace[0] = (long long)ptx::globaltimer(); trace[1] = clock64(); }
@@ -283,15 +291,18 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
     uint32_t phase = 0;
     uint32_t sa = smem_base, full_s = full0, empty_s = empty0, full_t = full_tgt0;
     for (int tile = unit; tile < total_tiles; tile += nunits) {
-      const int n_t = tile % p.tiles_n;
-      const int rest = tile / p.tiles_n;
+      int n_t, rest, half;
+      decode_tile(tile, n_t, rest, half);
       const int m_t = kPair ? (rest % p.tiles_mp) * 2 + (int)rank : rest % p.tiles_mp;
       const int rest2 = rest / p.tiles_mp;
       const int ph = rest2 % p.phases;
       const int ks = rest2 / p.phases;
       const int gy0 = (m_t / p.tiles_x) * p.tile_rows;
       const int ox0 = (m_t % p.tiles_x) << p.tileW_log2;
-      const int w_row = ph * p.w_rows_phase + n_t * BLOCK_N + (kPair ? (int)rank * (BLOCK_N / 2) : 0);
+      const int w_row = half >= 0 ? half * (BLOCK_N / 2) + (kPair ? (int)rank * (BLOCK_N / 4) : 0)
+                                  : ph * p.w_rows_phase + n_t * BLOCK_N + (kPair ? (int)rank * (BLOCK_N / 2) : 0);
+      const CUtensorMap* tmap_w = (kTail && half >= 0) ? &p.tmap_w_half : &p.tmap_w;
+      const uint32_t b_tx_t = (kTail && half >= 0) ? b_tx / 2 : b_tx;
       const int b0 = gy0 / p.Hg;
       const int y0 = gy0 - b0 * p.Hg;
       int kb = ks * p.kb_per_split;
@@ -316,7 +327,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
           lean::wait(empty_s, phase ^ 1);
           if (trace && leader) trace[24] += clock64() - tw0;     // producer: cycles blocked on a free stage
           if (leader) {
-            if (!kPair || rank == 0) lean::expect_tx(full_s, (uint32_t)gc * (a_tx + (uint32_t)gn * b_tx));
+            if (!kPair || rank == 0) lean::expect_tx(full_s, (uint32_t)gc * (a_tx + (uint32_t)gn * b_tx_t));
             for (int g = 0; g < gc; ++g) {
               const uint32_t sa_g = sa + (uint32_t)g * Cfg::kABytes;
               if (do_a) {
@@ -335,10 +346,10 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
               }
               if (do_b) {
                 const uint32_t sb_g = sa + kG * Cfg::kABytes + (uint32_t)g * Cfg::kBBytes;
-                lean::tma2d<kPair>(sb_g, &p.tmap_w, full_t, kcol + g * kBlockK, w_row);
+                lean::tma2d<kPair>(sb_g, tmap_w, full_t, kcol + g * kBlockK, w_row);
                 if constexpr (kT > 1) {
                   for (int t = 1; t < gn; ++t)
-                    lean::tma2d<kPair>(sb_g + t * Cfg::kBBytes, &p.tmap_w, full_t, kcol + t * kBlockK, w_row);
+                    lean::tma2d<kPair>(sb_g + t * Cfg::kBBytes, tmap_w, full_t, kcol + t * kBlockK, w_row);
                 }
               }
             }
@@ -361,6 +372,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
       const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
       const uint32_t idesc_main = ptx::umma_idesc_f16(kPair ? 2 * kBlockM : kBlockM, BLOCK_N, p.is_bf16);
       const uint32_t idesc_last = ptx::umma_idesc_f16(kPair ? 2 * kBlockM : kBlockM, kNB, p.is_bf16);
+      const uint32_t idesc_half = ptx::umma_idesc_f16(kPair ? 2 * kBlockM : kBlockM, BLOCK_N / 2, p.is_bf16);
       // descriptors: only the low word (start address >> 4) changes; the high word is a constant
       constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
       const uint32_t da0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);
@@ -379,8 +391,9 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
         ptx::tc_fence_after();
         if (trace && leader) trace[25] += clock64() - tt0;       // MMA warp: cycles blocked on a free accumulator stage
         const uint32_t d_tmem = tmem_base + acc * kNB;
-        const uint32_t idesc = (kHead && (tile % p.tiles_n) == p.tiles_n - 1) ? idesc_last : idesc_main;
-        const int ks = tile / (p.tiles_n * p.tiles_mp * p.phases);
+        const uint32_t idesc = (kTail && tile >= tail_t0) ? idesc_half
+                               : (kHead && (tile % p.tiles_n) == p.tiles_n - 1) ? idesc_last : idesc_main;
+        const int ks = (kTail && tile >= tail_t0) ? 0 : tile / (p.tiles_n * p.tiles_mp * p.phases);
         const int kb0 = ks * p.kb_per_split;
         const int nkb = kG > 1 ? p.ntaps * ((p.nchunks + kG - 1) / kG)      // stage items per tile (chunk groups)
                                : min(num_kb, kb0 + p.kb_per_split) - kb0;
@@ -447,8 +460,8 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
     uint32_t acc = 0, acc_phase = 0, stg_parity = 0, stg_phase = 0;
     const uint32_t tempty_tgt0 = kPair ? ptx::mapa_u32(tempty0, 0) : tempty0;
     for (int tile = unit; tile < total_tiles; tile += nunits) {
-      const int n_t = tile % p.tiles_n;
-      const int rest = tile / p.tiles_n;
+      int n_t, rest, half;
+      decode_tile(tile, n_t, rest, half);
       const int m_t = kPair ? (rest % p.tiles_mp) * 2 + (int)rank : rest % p.tiles_mp;
       const int rest2 = rest / p.tiles_mp;
       const int ph = rest2 % p.phases;
@@ -462,7 +475,8 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
       const int oy = y * p.out_scale + p.out_oy[ph];
       const int ox = gx * p.out_scale + p.out_ox[ph];
       const size_t pix = ((size_t)b * p.out_H + oy) * p.out_W + ox;
-      const int n0 = n_t * BLOCK_N;
+      const int n0 = half >= 0 ? half * (BLOCK_N / 2) : n_t * BLOCK_N;
+      const int ncols = half >= 0 ? BLOCK_N / 2 : BLOCK_N;   // accumulator columns of this unit
 
       lean::wait(tfull0 + 8 * acc, acc_phase);
       ptx::tc_fence_after();
@@ -499,7 +513,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
           // 128-byte staging rows: 64 16-bit channels, or 32 raw fp32 partial sums (split-K: tma_store == 2)
           const int cw = p.tma_store == 2 ? 32 : 64;
 #pragma unroll 1
-          for (int c0 = 0; c0 < BLOCK_N; c0 += cw) {
+          for (int c0 = 0; c0 < ncols; c0 += cw) {
             const uint32_t buf = stg0 + (stg_parity ? Cfg::kStgBytes : 0);
             const uint32_t rowaddr = buf + (uint32_t)row * 128u;
             long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0;
@@ -535,7 +549,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
             }
             }
             if (trace && threadIdx.x == 64) tq1 = clock64();
-            if (c0 + cw >= BLOCK_N) {   // every accumulator column of this tile has been read: release the TMEM stage
+            if (c0 + cw >= ncols) {   // every accumulator column of this tile has been read: release the TMEM stage
               if constexpr (kHead > 0) {
                 // fused flow head (model.py:847-874): columns BLOCK_N, BLOCK_N+1 of the last N tile hold this phase's
                 // share of the 3x3 head on the same input; pyr_kernel sums the 4 phase shares per pixel
@@ -611,7 +625,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
       if (!stored) {
         constexpr int kChunk = BLOCK_N >= 32 ? 32 : 16;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += kChunk) {
+        for (int c0 = 0; c0 < ncols; c0 += kChunk) {
           uint32_t v[kChunk];
           if constexpr (kChunk == 32) ptx::tmem_ld32(t_addr + c0, v); else ptx::tmem_ld16(t_addr + c0, v);
           ptx::tmem_wait_ld();
@@ -637,8 +651,10 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
         bool pending = false;            // a committed store whose buffer has not been handed back yet
         const uint32_t piece_bytes = (uint32_t)(p.piece_rows << p.tileW_log2) * 128u;
         for (int tile = unit; tile < total_tiles; tile += nunits) {
-          const int n_t = tile % p.tiles_n;
-          const int rest = tile / p.tiles_n;
+          int n_t, rest, half;
+          decode_tile(tile, n_t, rest, half);
+          const int n0 = half >= 0 ? half * (BLOCK_N / 2) : n_t * BLOCK_N;
+          const int ncols = half >= 0 ? BLOCK_N / 2 : BLOCK_N;
           const int m_t = kPair ? (rest % p.tiles_mp) * 2 + (int)rank : rest % p.tiles_mp;
           const int ph = (rest / p.tiles_mp) % p.phases;
           const int gy0 = (m_t / p.tiles_x) * p.tile_rows;
@@ -648,15 +664,15 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
           const int ks = rest / (p.tiles_mp * p.phases);
           const int cw = p.tma_store == 2 ? 32 : 64;
 #pragma unroll 1
-          for (int c0 = 0; c0 < BLOCK_N; c0 += cw) {
+          for (int c0 = 0; c0 < ncols; c0 += cw) {
             lean::wait(sfull0 + 8 * par, phs);
             if (do_store) {
               int bb = b0, yy = y0;
               uint32_t src = stg0 + (par ? Cfg::kStgBytes : 0);
               for (int pc = 0; pc < p.npieces; ++pc) {
                 if (issuer) {
-                  if (cw == 32) ptx::tma_store_5d(&p.tmap_o[0], src, n_t * BLOCK_N + c0, ox0, yy, bb, ks);
-                  else ptx::tma_store_4d(&p.tmap_o[ph], src, n_t * BLOCK_N + c0, ox0, yy, bb);
+                  if (cw == 32) ptx::tma_store_5d(&p.tmap_o[0], src, n0 + c0, ox0, yy, bb, ks);
+                  else ptx::tma_store_4d(&p.tmap_o[ph], src, n0 + c0, ox0, yy, bb);
                 }
                 src += piece_bytes;
                 yy += p.piece_rows;
@@ -1263,7 +1279,19 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
   // is the output pixel index)
   p.tma_store = p.kcluster ? 0 : (p.out_mode == 0 && d.block_n >= 64) ? 1 : (p.out_mode == 2 && d.block_n >= 64 && !deconv) ? 2 : 0;
   p.tiles_mp = d.cta_group == 2 ? (p.tiles_m + 1) / 2 : p.tiles_m;
-  const int total_tiles = p.tiles_mp * p.tiles_n * p.phases * p.ksplit;
+  int total_tiles = p.tiles_mp * p.tiles_n * p.phases * p.ksplit;
+  p.tail_t0 = 0x7fffffff;
+  const char* tail_env = getenv("OFS_TAIL_HALF");   // "0": A/B switch for tests and measurements
+  if (d.tail_half && !(tail_env && tail_env[0] == '0') && d.block_n == 256 && p.tiles_n == 1 && p.phases == 1 && p.ksplit == 1 && p.tma_store == 1 && !p.slab &&
+      !d.head && d.kgroup == 1) {
+    // a last wave that fills at most half of the machine is issued as half tiles (128 columns) on twice as many CTAs
+    const int slots = std::max(1, d.cta_group == 2 ? sm_count() / 2 : sm_count());
+    const int rem = p.tiles_mp % slots;
+    if (p.tiles_mp > slots && rem > 0 && 2 * rem <= slots) {
+      p.tail_t0 = p.tiles_mp - rem;
+      total_tiles += rem;
+    }
+  }
   if (p.kcluster) {
     plan.grid = total_tiles;   // one CTA per (tile, K split); clusters are gang-scheduled, a second wave is merely slower
     plan.smem = GemmCfg<256, false>::kSmem;
@@ -1411,6 +1439,11 @@ int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const 
   cuuint64_t wd[2] = {(cuuint64_t)plan.k_total, (cuuint64_t)plan.w_rows};
   cuuint64_t ws[1] = {(cuuint64_t)plan.k_total * 2};
   cuuint32_t wb[2] = {(cuuint32_t)kBlockK, (cuuint32_t)((plan.block_n + (d.head ? 16 : 0)) / d.cta_group)};
+  if (p.tail_t0 != 0x7fffffff) {
+    cuuint32_t wh[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(plan.block_n / 2 / d.cta_group)};
+    st = encode_map(&p.tmap_w_half, d.is_bf16, 2, w_dev, wd, ws, wh);
+    if (st != OFS_OK) return st;
+  }
   return encode_map(&p.tmap_w, d.is_bf16, 2, w_dev, wd, ws, wb);
 }
 

@@ -15,6 +15,11 @@ struct ConvGemmParams {
   CUtensorMap tmap_a;  // 5-D view of the NHWC 16-bit activation (see conv_gemm.cu)
   CUtensorMap tmap_w;  // 2-D packed weights [phases * n_pad rows][K_total], K-major (box rows: BLOCK_N / cta_group)
   CUtensorMap tmap_o[4];  // per phase: 4-D view [c, x, y, b] of this layer's 16-bit output slice (TMA-store epilogue)
+  CUtensorMap tmap_w_half;  // tail split: the weights with a box of 128 / cta_group rows (half a 256-column tile)
+  int tail_t0;         // tail split (256-column layers with one N tile): scheduling units >= tail_t0 are HALF tiles --
+                       // unit tail_t0 + 2j + h computes columns [128h, 128h+128) of M tile tail_t0 + j.  A last wave
+                       // that would leave most SMs idle is spread over twice as many CTAs at ~0.64 of the tile time;
+                       // N splits do not touch the K summation order, results stay bit-identical.  INT_MAX: off.
   int tma_store;       // 1: 16-bit epilogue goes through swizzled shared-memory staging + cp.async.bulk.tensor stores
   // M grid (output pixels; for the transposed conv: input pixels, one GEMM per sub-pixel phase)
   int Hg, Wg;          // grid height / width per image
@@ -78,6 +83,7 @@ struct ConvDesc {
   int out_mode, lrelu, is_bf16;
   int out_cstride, out_coff;
   int ksplit = 1;      // > 1: split the K loop over this many CTAs per tile (16-bit output mode only)
+  int tail_half = 1;   // 0: never split the tail wave into half tiles (see ConvGemmParams::tail_t0)
   int kcluster = 0;    // 1: split-K inside a thread-block cluster (ksplit <= 8, block_n 256, 1-CTA tiles): no workspace, no reduce kernel
   int cta_group = 1;   // 2: CTA pairs (tcgen05 cta_group::2): tile = 256 GEMM rows x BLOCK_N, B split over the pair
   int kgroup = 1;      // 2: two consecutive 64-channel K blocks of a tap per pipeline stage (narrow-N layers)

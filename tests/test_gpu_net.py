@@ -114,6 +114,10 @@ TILING_CASES = [
     pytest.param(3, 10, 256, 64, 128, 5, 2, False, 128, -1, 4, id="slab_conv2_form_odd_tiles_out16"),
     pytest.param(1, 8, 256, 16, 64, 3, 2, False, 64, 1, 4, id="slab_k3_paired"),
     pytest.param(1, 8, 256, 64, 64, 3, 2, False, 64, 1, 4, id="slab_k3_cin64"),
+    # tail split: > 148 M tiles of 256 columns, the last wave runs as half tiles on twice as many CTAs
+    pytest.param(7, 48, 64, 64, 256, 3, 1, False, 256, -1, 1, id="tail_half_168_tiles"),
+    pytest.param(7, 48, 64, 64, 256, 3, 1, False, 256, -1, 2, id="tail_half_pairs_84_pair_tiles"),
+    pytest.param(5, 96, 64, 64, 256, 3, 2, False, 256, -1, 2, id="tail_half_pairs_k3s2_odd_pair_count"),
     # cluster split-K (cta_group = 16: the K splits of a tile are one thread-block cluster, reduced through DSMEM)
     pytest.param(3, 6, 8, 512, 512, 3, 1, False, 256, 8, 16, id="kcluster8_whole_image_tiles_ragged_batch"),
     pytest.param(2, 12, 16, 256, 256, 3, 2, False, 256, 4, 16, id="kcluster4_k3s2"),
@@ -142,6 +146,20 @@ def test_conv_gemm_tilings(ofs, cuda_dev, B, H, W, cin, cout, k, stride, transpo
     ref = T.lrelu(ref, 0.1).float()
     tol = 6e-3 if (ksplit > 1 or out16) else 2e-3
     assert float(((got - ref).abs() / (1 + ref.abs())).max()) <= tol
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_tail_half_tiles_bit_identical(ofs, cuda_dev, cta_group, monkeypatch):
+    """Splitting the last wave's tiles into two 128-column halves does not touch the K order: same bits."""
+    gen = torch.Generator().manual_seed(11)
+    x = _round(torch.rand((8, 48, 64, 128), generator=gen), "bf16").to(cuda_dev)   # 192 M tiles (conv3_1's grid)
+    w = _round(torch.randn((3, 3, 128, 256), generator=gen) * (1.0 / np.sqrt(9 * 128)), "bf16")
+    b = torch.randn(256, generator=gen) * 0.1
+    monkeypatch.setenv("OFS_TAIL_HALF", "0")
+    a = ofs.conv2d_nhwc(x, w, b, lrelu=True, precision="bf16", block_n=256, cta_group=cta_group, out16=True).cpu()
+    monkeypatch.setenv("OFS_TAIL_HALF", "1")
+    c = ofs.conv2d_nhwc(x, w, b, lrelu=True, precision="bf16", block_n=256, cta_group=cta_group, out16=True).cpu()
+    assert torch.equal(a, c)
 
 
 @pytest.mark.parametrize("B,H,W,cin,cout,ks", [(8, 12, 16, 512, 512, 4), (8, 6, 8, 512, 1024, 8), (3, 6, 8, 256, 256, 5)])
