@@ -37,10 +37,12 @@ LAYERS = {
     "deconv3": (24, 32, 770, 776, 128, 392, 4, 2, 1),
     "deconv2": (48, 64, 386, 392, 64, 200, 4, 2, 1),
     "predict2": (96, 128, 194, 200, 18, 18, 1, 1, 0),
+    # proxy for conv1 in space-to-depth form (25 K blocks of a 128-column 1-CTA tile on the 192 x 128 pair grid; the real thing has 35)
+    "s2d_proxy": (192, 128, 64, 64, 128, 128, 5, 1, 0),
 }
 DEFAULTS = {"1": "64:1:1", "2": "128:1:1", "3": "256:1:1", "3_1": "256:1:1", "4": "256:1:1", "4_1": "256:1:1",
             "5": "256:6:1", "5_1": "256:6:1", "6": "256:8:1", "6_1": "256:8:1", "deconv5": "256:4:1",
-            "deconv4": "256:3:1", "deconv3": "128:1:1", "deconv2": "64:1:1", "predict2": "32:1:1"}
+            "deconv4": "256:3:1", "deconv3": "128:1:1", "deconv2": "64:1:1", "predict2": "32:1:1", "s2d_proxy": "128:1:1"}
 
 
 def macs(name, B):
