@@ -4,9 +4,10 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_samplers.py -m gpu -q --timeout 300 --tb=short 2>&1 | tail -25 > gpurun_out/t_samplers.log
 timeout 900 python -m pytest tests/test_gpu_net.py -m gpu -q --timeout 300 --tb=short -k "conv_gemm" 2>&1 | tail -40 > gpurun_out/t_conv.log
 timeout 900 python -m pytest tests/test_gpu_net.py -m gpu -q --timeout 600 --tb=short -s -k "not conv_gemm" 2>&1 | tail -60 > gpurun_out/t_net.log
+timeout 900 python -m pytest tests/test_gpu_clip.py -m gpu -q --timeout 300 --tb=short 2>&1 | tail -25 > gpurun_out/t_clip.log
 timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 timeout 900 python bench.py --steps 200 --warmup 5 > gpurun_out/bench.log 2>&1
-for f in t_samplers.log t_conv.log t_net.log smoke.log; do echo "=== $f"; tail -30 gpurun_out/$f; done
+for f in t_samplers.log t_conv.log t_net.log t_clip.log smoke.log; do echo "=== $f"; tail -30 gpurun_out/$f; done
 echo "=== bench"; python - <<'PY'
 import json
 try:
