@@ -92,7 +92,8 @@ __device__ __forceinline__ void epilogue_store(const ConvGemmParams& p, const ui
 // M=256 MMA reading both CTAs' shared memory; D rows 0-127 land in the leader's TMEM, rows 128-255 in the peer's.
 // kT = K blocks (taps of one slab group) per pipeline stage: 1, or 3 / 4 in slab mode.
 // kHead = 16: the LAST N tile of every phase carries 16 extra accumulator columns (2 real) for the fused flow head.
-// kG = 2: two consecutive 64-channel K blocks of one tap per pipeline stage (halves the handshakes of narrow-N layers).
+// kG = 2 / 4: that many consecutive 64-channel K blocks of one tap per pipeline stage (fewer handshakes for narrow-N
+// layers; kG = 4 with 32-column tiles puts the whole K of the predict2 product in one stage).
 template <int BLOCK_N, bool kPair, int kT = 1, int kHead = 0, int kG = 1>
 struct GemmCfg {
   static constexpr int kNB = BLOCK_N + kHead;            // B rows per stage / accumulator columns per TMEM stage
@@ -761,6 +762,11 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   conv_gemm_body<BLOCK_N, false, 1, 0, 1>(p);
 }
+// four K chunks per stage, narrow fp32 tiles (predict2 product)
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1) conv_gemmg4_kernel(const __grid_constant__ ConvGemmParams p) {
+  conv_gemm_body<BLOCK_N, false, 1, 0, 4>(p);
+}
 // split-K inside a thread-block cluster of ksplit CTAs (cluster size set at launch)
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemmk_kernel(const __grid_constant__ ConvGemmParams p) {
@@ -981,6 +987,22 @@ int launch_tg(const ConvPlan& plan, cudaStream_t st) {
   }
   pdl_set_kind(1);
   OFS_CUDA(launch_pdl(conv_gemmg_kernel<BLOCK_N, kHead>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, false, 1, kHead, 2>::kSmem, st, plan.p));
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
+}
+
+template <int BLOCK_N>
+int launch_tg4(const ConvPlan& plan, cudaStream_t st) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  OFS_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    OFS_CUDA(cudaFuncSetAttribute(conv_gemmg4_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)GemmCfg<BLOCK_N, false, 1, 0, 4>::kSmem));
+    attr_set[dev] = true;
+  }
+  pdl_set_kind(1);
+  OFS_CUDA(launch_pdl(conv_gemmg4_kernel<BLOCK_N>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, false, 1, 0, 4>::kSmem, st, plan.p));
   OFS_LAUNCH_CHECK();
   return OFS_OK;
 }
@@ -1257,8 +1279,9 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
     OFS_REQUIRE(deconv && d.out_mode == 0 && d.cta_group == 1 && d.ksplit <= 1 && (d.block_n == 64 || d.block_n == 128),
                 "fused head: transposed conv, 16-bit output, 1-CTA tiles of 64 / 128 columns, no split-K");
   }
-  OFS_REQUIRE(d.kgroup == 1 || (d.kgroup == 2 && d.cta_group == 1 && !d.slab && d.ksplit <= 1 && (d.block_n == 64 || d.block_n == 128)),
-              "chunk groups: 1-CTA tiles of 64 / 128 columns, no slab, no split-K");
+  OFS_REQUIRE(d.kgroup == 1 || (d.kgroup == 2 && d.cta_group == 1 && !d.slab && d.ksplit <= 1 && (d.block_n == 64 || d.block_n == 128)) ||
+                  (d.kgroup == 4 && d.cta_group == 1 && !d.slab && !d.head && d.ksplit <= 1 && d.block_n == 32),
+              "chunk groups: 2 per stage for 1-CTA tiles of 64 / 128 columns, 4 per stage for 32 columns; no slab, no split-K");
   p.w_rows_phase = p.n_pad + (d.head ? 16 : 0);
   plan.k_total = (p.slab ? (int)plan.wt_ky.size() : p.ntaps * p.nchunks) * kBlockK;
   plan.w_rows = p.phases * p.w_rows_phase;
@@ -1295,6 +1318,9 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
   if (p.kcluster) {
     plan.grid = total_tiles;   // one CTA per (tile, K split); clusters are gang-scheduled, a second wave is merely slower
     plan.smem = GemmCfg<256, false>::kSmem;
+  } else if (d.kgroup == 4) {
+    plan.grid = std::max(1, std::min(total_tiles, sm_count()));
+    plan.smem = GemmCfg<32, false, 1, 0, 4>::kSmem;
   } else if (d.kgroup == 2) {
     plan.grid = std::max(1, std::min(total_tiles, sm_count()));
     plan.smem = d.block_n == 64 ? (d.head ? GemmCfg<64, false, 1, 16, 2>::kSmem : GemmCfg<64, false, 1, 0, 2>::kSmem)
@@ -1451,6 +1477,8 @@ int conv_launch(const ConvPlan& plan, cudaStream_t st) {
   int rc = OFS_EINVAL;
   if (plan.p.kcluster) {
     return launch_tk<256>(plan, st);
+  } else if (plan.d.kgroup == 4) {
+    rc = launch_tg4<32>(plan, st);
   } else if (plan.d.kgroup == 2) {
     if (plan.block_n == 64) rc = plan.d.head ? launch_tg<64, 16>(plan, st) : launch_tg<64, 0>(plan, st);
     else if (plan.block_n == 128) rc = plan.d.head ? launch_tg<128, 16>(plan, st) : launch_tg<128, 0>(plan, st);
@@ -1532,7 +1560,7 @@ extern "C" int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const flo
   d.ksplit = ksplit > 1 ? ksplit : 1;
   d.cta_group = (cta_group == 2 || cta_group == 4) ? 2 : 1;
   d.slab = cta_group == 4 ? 1 : 0;   // 4 = CTA pairs + slab groups
-  d.kgroup = cta_group == 8 ? 2 : 1; // 8 = two K chunks per pipeline stage
+  d.kgroup = cta_group == 8 ? 2 : cta_group == 32 ? 4 : 1; // 8 / 32 = two / four K chunks per pipeline stage
   d.kcluster = cta_group == 16 ? 1 : 0;   // 16 = split-K inside a thread-block cluster (DSMEM reduction)
   const bool via16 = d.ksplit > 1 || out16;   // the network's 16-bit activation epilogue (split-K always reduces into it)
   const int cout8 = ((Cout + 7) / 8) * 8;
@@ -1630,7 +1658,7 @@ extern "C" int ofs_conv2d_bench(int B, int H, int W, int Cin, int in_cs, int Cou
   ConvDesc d;
   d.kind = transposed ? kDeconvK4S2 : kConv;
   d.B = B; d.H = H; d.W = W; d.cin = Cin; d.in_cs = in_cs; d.cout = Cout; d.k = k; d.stride = stride;
-  d.block_n = block_n; d.ksplit = ksplit > 1 ? ksplit : 1; d.cta_group = (cta_group == 2 || cta_group == 4) ? 2 : 1; d.slab = cta_group == 4 ? 1 : 0; d.kgroup = cta_group == 8 ? 2 : 1; d.debug = debug;
+  d.block_n = block_n; d.ksplit = ksplit > 1 ? ksplit : 1; d.cta_group = (cta_group == 2 || cta_group == 4) ? 2 : 1; d.slab = cta_group == 4 ? 1 : 0; d.kgroup = cta_group == 8 ? 2 : cta_group == 32 ? 4 : 1; d.debug = debug;
   d.kcluster = cta_group == 16 ? 1 : 0;
   const bool out16 = (Cout % block_n) == 0 || (!transposed && block_n >= 64 && Cout % 64 == 0 && ksplit <= 1);
   d.out_mode = out16 ? 0 : 1; d.lrelu = 1; d.is_bf16 = 1; d.out_cstride = out_cs; d.out_coff = 0;

@@ -366,8 +366,9 @@ int prepare(ofs_net* n, int B) {
       }
     }
     if (cg == 8 && !L.d.slab) { L.d.kgroup = 2; cg = 1; }   // OFS_TUNE cta_group 8 = chunk groups
+    if (cg == 32 && !L.d.slab && bn == 32) { L.d.kgroup = 4; cg = 1; }   // 32 = four chunks per stage (32-column tiles)
     const bool kc = cg == 16 && ks > 1 && ks <= 8 && bn == 256 && !L.d.slab && L.d.out_mode == 0;   // 16 = cluster split-K
-    if (L.d.kgroup == 2) { rc = conv_plan_geometry(L.plan, L.d); if (rc != OFS_OK) return rc; }
+    if (L.d.kgroup >= 2) { rc = conv_plan_geometry(L.plan, L.d); if (rc != OFS_OK) return rc; }
     if (ks > 1 || bn != L.d.block_n || cg == 2 || dbg) {
       ConvDesc d = L.d;
       d.block_n = bn;

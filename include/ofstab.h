@@ -200,7 +200,7 @@ int ofs_conv2d_nhwc(const float* x, const float* w_host, const float* b_host, fl
  * (ksplit > 1 reduces fp32 partials from a workspace into the 16-bit activation format, so the result
  * carries one 16-bit rounding, exactly as the network's split-K layers do) and cta_group (1, or 2 = CTA
  * pairs: tcgen05 cta_group::2, 256-row tiles, weight tile split over the pair; needs block_n >= 32;
- * 4 = pairs + slab groups, 8 = two K chunks per stage, 16 = split-K inside a thread-block cluster of
+ * 4 = pairs + slab groups, 8 / 32 = two / four K chunks per stage, 16 = split-K inside a thread-block cluster of
  * ksplit <= 8 CTAs reduced through distributed shared memory, block_n 256 -- same bits as the workspace path).
  * out16 = 1 runs the network's 16-bit activation epilogue (shared-memory staging + TMA stores when
  * block_n >= 64; needs Cout % block_n == 0) and widens the result to fp32 afterwards. */

@@ -106,6 +106,10 @@ TILING_CASES = [
     pytest.param(2, 12, 16, 130, 128, 4, 2, True, 128, -1, 8, id="kgroup_deconv"),
     pytest.param(1, 24, 32, 386, 64, 4, 2, True, 64, -1, 8, id="kgroup_deconv2_form"),
     pytest.param(3, 6, 8, 256, 128, 3, 1, False, 128, 1, 8, id="kgroup_whole_image_tiles"),
+    # four K chunks per stage for 32-column fp32 tiles (cta_group = 32: the predict2 product form)
+    pytest.param(2, 96, 128, 194, 18, 1, 1, False, 32, 1, 32, id="kgroup4_predict2_form"),
+    pytest.param(1, 24, 32, 300, 18, 3, 1, False, 32, 1, 32, id="kgroup4_k3_five_chunks"),
+    pytest.param(3, 6, 8, 64, 32, 3, 1, False, 32, 1, 32, id="kgroup4_single_chunk_whole_image_tiles"),
     # slab groups (cta_group = 4: CTA pairs, x-shifted taps share one shared-memory slab per pipeline stage)
     pytest.param(1, 32, 256, 27, 64, 7, 2, False, 64, 1, 4, id="slab_conv1_form"),
     pytest.param(2, 16, 512, 27, 64, 7, 2, False, 64, -1, 4, id="slab_conv1_form_two_x_tiles_out16"),
