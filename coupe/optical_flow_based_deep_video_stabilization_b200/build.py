@@ -7,6 +7,7 @@ box without a GPU, and the built .so travels with the source tree to the GPU box
 """
 from __future__ import annotations
 
+import fcntl
 import hashlib
 import os
 import shutil
@@ -56,17 +57,36 @@ def is_fresh():
 
 
 def build_library(force=False, verbose=False):
-    """Compile csrc/*.cu into libofstab.so when sources changed.  Returns the library path."""
+    """Compile csrc/*.cu into libofstab.so when sources changed.  Returns the library path.
+
+    Safe under concurrent callers (torchrun ranks importing a stale tree at the same moment): one process builds
+    under an exclusive file lock into a temporary file and renames it into place; the others wait for the lock,
+    find the library fresh and return.  A reader never sees a half-written .so."""
     if not force and is_fresh():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        print(" ".join(cmd), flush=True)
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    with open(STAMP, "w") as f:
-        f.write(source_digest())
+    with open(os.path.join(HERE, ".libofstab.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_fresh():          # built by another process while this one waited
+                return LIB_PATH
+            digest = source_digest()
+            tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+            cmd = [_nvcc()] + NVCC_FLAGS + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            if os.path.exists(STAMP):
+                os.remove(STAMP)                  # never a new library under an old stamp or vice versa
+            os.replace(tmp, LIB_PATH)
+            with open(STAMP + ".tmp", "w") as f:
+                f.write(digest)
+            os.replace(STAMP + ".tmp", STAMP)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
