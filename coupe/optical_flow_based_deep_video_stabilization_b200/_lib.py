@@ -69,6 +69,7 @@ PROTOTYPES = {
 DEBUG_PROTOTYPES = {
     "ofs_debug_conv_plan": (_i, [_i] * 11 + [_p, _p, _p, _p, _p, _ll, _p]),
     "ofs_debug_conv_plan_ex": (_i, [_i] * 12 + [_p, _p, _p, _p, _p, _p, _p, _ll, _p]),
+    "ofs_debug_conv_schedule": (_i, [_i] * 12 + [_p]),
     "ofs_debug_cvt16": (C.c_uint, [_f, _i]),
 }
 

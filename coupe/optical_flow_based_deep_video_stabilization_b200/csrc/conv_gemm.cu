@@ -1836,4 +1836,25 @@ extern "C" int ofs_debug_conv_plan_ex(int kind, int B, int H, int W, int cin, in
   return OFS_OK;
 }
 
+// host-only: how a layer is scheduled (grid, tail split, split-K form) -- CPU tests of the planning rules
+extern "C" int ofs_debug_conv_schedule(int kind, int B, int H, int W, int cin, int in_cs, int cout, int k, int stride,
+                                       int block_n, int cta_group, int ksplit, int* out /*[10]*/) {
+  using namespace ofs;
+  ConvDesc d;
+  d.kind = kind ? kDeconvK4S2 : kConv;
+  d.B = B; d.H = H; d.W = W; d.cin = cin; d.in_cs = in_cs; d.cout = cout; d.k = k; d.stride = stride;
+  d.block_n = block_n; d.out_mode = 0; d.lrelu = 0; d.is_bf16 = 1; d.out_cstride = ((cout + 7) / 8) * 8; d.out_coff = 0;
+  d.cta_group = cta_group == 2 ? 2 : 1;
+  d.kcluster = cta_group == 16 ? 1 : 0;
+  d.ksplit = ksplit > 1 ? ksplit : 1;
+  ConvPlan plan;
+  int rc = conv_plan_geometry(plan, d);
+  if (rc != OFS_OK) return rc;
+  const ConvGemmParams& p = plan.p;
+  const int vals[10] = {plan.grid, p.tail_t0, p.tiles_mp, p.tiles_n, p.phases, p.ksplit, p.kcluster, p.tma_store,
+                        (int)(plan.ws_bytes >> 10), (int)plan.smem};
+  for (int i = 0; i < 10; ++i) out[i] = vals[i];
+  return OFS_OK;
+}
+
 extern "C" unsigned ofs_debug_cvt16(float f, int is_bf16) { return is_bf16 ? ofs::f32_to_bf16_rn(f) : ofs::f32_to_fp16_rn(f); }

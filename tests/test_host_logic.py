@@ -217,3 +217,68 @@ def test_plan_rejects_unsupported_shapes(lib):
     assert rc(0, 1, 8, 16, 64, 64, 16, 3, 1, 48) != 0    # block_n
     assert rc(1, 1, 8, 16, 64, 64, 16, 3, 2, 16) != 0    # transposed conv must be k4 s2
     assert b"k=4" in lib.ofs_last_error()
+
+
+def _schedule(lib, kind, B, H, W, cin, in_cs, cout, k, stride, bn, cta_group=1, ksplit=1):
+    out = (C.c_int * 10)()
+    rc = lib.ofs_debug_conv_schedule(kind, B, H, W, cin, in_cs, cout, k, stride, bn, cta_group, ksplit, C.cast(out, C.c_void_p))
+    assert rc == 0, lib.ofs_last_error()
+    keys = ("grid", "tail_t0", "tiles_mp", "tiles_n", "phases", "ksplit", "kcluster", "tma_store", "ws_kib", "smem")
+    return dict(zip(keys, list(out)))
+
+
+OFF = 0x7FFFFFFF
+
+
+def test_tail_split_schedule(lib, monkeypatch):
+    """A last wave that fills at most half of the 148 SMs (74 CTA pairs) is issued as half tiles: every (M tile, column
+    half) of the tail is visited exactly once by the unit -> tile decode the kernel uses."""
+    monkeypatch.delenv("OFS_TAIL_HALF", raising=False)
+    conv3_1 = (0, 8, 48, 64, 256, 256, 256, 3, 1, 256)
+    s = _schedule(lib, *conv3_1)                                   # 192 tiles of 256 columns on 148 CTAs
+    assert (s["tiles_mp"], s["tiles_n"], s["grid"], s["tail_t0"]) == (192, 1, 148, 148)
+    units = s["tail_t0"] + 2 * (s["tiles_mp"] - s["tail_t0"])
+    seen = set()
+    for u in range(units):                                          # conv_gemm_body::decode_tile
+        if u >= s["tail_t0"]:
+            t = u - s["tail_t0"]
+            seen.add((s["tail_t0"] + (t >> 1), t & 1))
+        else:
+            seen.add((u, -1))
+    assert seen == {(m, -1) for m in range(148)} | {(m, h) for m in range(148, 192) for h in (0, 1)}
+    assert max(sum(1 for u in range(c, units, s["grid"])) for c in range(s["grid"])) == 2      # one full + one half at most
+    pairs = _schedule(lib, 0, 8, 96, 128, 128, 200, 256, 5, 2, 256, cta_group=2)              # conv3 on CTA pairs
+    assert (pairs["tiles_mp"], pairs["grid"], pairs["tail_t0"]) == (96, 148, 74)
+    assert _schedule(lib, 0, 16, 48, 64, 256, 256, 256, 3, 1, 256)["tail_t0"] == OFF           # 384 tiles: the rest (88) fills > half
+    assert _schedule(lib, 0, 1, 48, 64, 256, 256, 256, 3, 1, 256)["tail_t0"] == OFF            # 24 tiles: a single partial wave
+    assert _schedule(lib, 0, 8, 48, 64, 256, 392, 512, 3, 2, 256)["tail_t0"] == OFF            # two N tiles
+    assert _schedule(lib, 0, 8, 12, 16, 512, 512, 512, 3, 1, 256, ksplit=6)["tail_t0"] == OFF  # split-K
+    monkeypatch.setenv("OFS_TAIL_HALF", "0")
+    assert _schedule(lib, *conv3_1)["tail_t0"] == OFF
+
+
+def test_splitk_schedules(lib):
+    """Workspace split-K: one persistent wave, fp32 partials in a workspace; cluster split-K: one CTA per (tile, split),
+    no workspace, reduced on chip; shapes the cluster form cannot take are rejected."""
+    conv6_1 = (0, 8, 6, 8, 1024, 1024, 1024, 3, 1, 256)
+    ws = _schedule(lib, *conv6_1, ksplit=8)
+    assert (ws["ksplit"], ws["kcluster"], ws["grid"], ws["tma_store"]) == (8, 0, 128, 2)
+    assert ws["ws_kib"] == 8 * 8 * 6 * 8 * 1024 * 4 // 1024
+    kc = _schedule(lib, *conv6_1, cta_group=16, ksplit=8)
+    assert (kc["ksplit"], kc["kcluster"], kc["grid"], kc["tma_store"], kc["ws_kib"]) == (8, 1, 16 * 8, 0, 0)
+    uneven = _schedule(lib, 0, 2, 6, 8, 320, 320, 256, 3, 1, 256, cta_group=16, ksplit=7)      # 45 K blocks: 7 + ... + 3
+    assert uneven["ksplit"] == 7 and uneven["grid"] % 7 == 0
+    out = (C.c_int * 10)()
+    bad = lib.ofs_debug_conv_schedule(0, 8, 6, 8, 1024, 1024, 1024, 3, 1, 128, 16, 8, C.cast(out, C.c_void_p))   # 128-column tiles
+    assert bad != 0 and b"cluster split-K" in lib.ofs_last_error()
+    bad = lib.ofs_debug_conv_schedule(0, 8, 6, 8, 1024, 1024, 1024, 3, 1, 256, 16, 12, C.cast(out, C.c_void_p))  # 12 > 8 CTAs
+    assert bad != 0
+
+
+def test_build_is_a_no_op_when_fresh(monkeypatch):
+    """A fresh tree never shells out to nvcc (the GPU box loads the shipped library); stale trees rebuild under a lock."""
+    from coupe.optical_flow_based_deep_video_stabilization_b200 import build
+
+    assert build.is_fresh()
+    monkeypatch.setattr(build, "_nvcc", lambda: (_ for _ in ()).throw(AssertionError("nvcc invoked on a fresh tree")))
+    assert build.build_library() == build.LIB_PATH
