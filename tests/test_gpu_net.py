@@ -121,7 +121,8 @@ TILING_CASES = [
     # tail split: > 148 M tiles of 256 columns, the last wave runs as half tiles on twice as many CTAs
     pytest.param(7, 48, 64, 64, 256, 3, 1, False, 256, -1, 1, id="tail_half_168_tiles"),
     pytest.param(7, 48, 64, 64, 256, 3, 1, False, 256, -1, 2, id="tail_half_pairs_84_pair_tiles"),
-    pytest.param(5, 96, 64, 64, 256, 3, 2, False, 256, -1, 2, id="tail_half_pairs_k3s2_odd_pair_count"),
+    pytest.param(7, 46, 64, 64, 256, 3, 1, False, 256, -1, 2, id="tail_half_pairs_odd_tile_count_161"),
+    pytest.param(5, 96, 64, 64, 256, 3, 2, False, 256, -1, 2, id="pairs_n256_k3s2_out16"),
     # cluster split-K (cta_group = 16: the K splits of a tile are one thread-block cluster, reduced through DSMEM)
     pytest.param(3, 6, 8, 512, 512, 3, 1, False, 256, 8, 16, id="kcluster8_whole_image_tiles_ragged_batch"),
     pytest.param(2, 12, 16, 256, 256, 3, 2, False, 256, 4, 16, id="kcluster4_k3s2"),
