@@ -103,22 +103,37 @@ __global__ void pyr_kernel(PyrParams p) {
     const int b = (int)(r / H2);
     if (((oy | ox) & 1) == 0) p.f_out[((size_t)b * p.h + (oy >> 1)) * p.w + (ox >> 1)] = pyr_flow_at(p, b, oy >> 1, ox >> 1);
     float a0 = __ldg(p.up_w + 64), a1 = __ldg(p.up_w + 65);
+    // the 2 x 2 taps of the k4 s2 up-sampler: flows are fetched unconditionally at clamped positions (all ~32 loads of a
+    // pixel in flight together -- these kernels are a handful of blocks deep and purely latency-bound) and a tap outside
+    // the grid is skipped when it is accumulated, so the sum has the same terms in the same order as before
+    float2 f[2][2];
+    int kyv[2], kxv[2];
+    bool vy[2], vx[2];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      const int ky = ((oy + 1) & 1) + 2 * s;
-      const int i = (oy + 1 - ky) >> 1;  // 2i + ky - 1 == oy
-      if (i < 0 || i >= p.h) continue;
+      kyv[s] = ((oy + 1) & 1) + 2 * s;
+      const int i = (oy + 1 - kyv[s]) >> 1;  // 2i + ky - 1 == oy
+      vy[s] = i >= 0 && i < p.h;
+      kxv[s] = ((ox + 1) & 1) + 2 * s;
+      const int j = (ox + 1 - kxv[s]) >> 1;
+      vx[s] = j >= 0 && j < p.w;
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        const int kx = ((ox + 1) & 1) + 2 * t;
-        const int j = (ox + 1 - kx) >> 1;
-        if (j < 0 || j >= p.w) continue;
-        const float2 f = pyr_flow_at(p, b, i, j);
-        const float* wk = p.up_w + (ky * 4 + kx) * 4;  // [co][ci]
-        a0 += f.x * __ldg(wk + 0) + f.y * __ldg(wk + 1);
-        a1 += f.x * __ldg(wk + 2) + f.y * __ldg(wk + 3);
+        const int i = min(max((oy + 1 - kyv[s]) >> 1, 0), p.h - 1), j = min(max((ox + 1 - kxv[t]) >> 1, 0), p.w - 1);
+        f[s][t] = pyr_flow_at(p, b, i, j);
       }
-    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const float* wk = p.up_w + (kyv[s] * 4 + kxv[t]) * 4;  // [co][ci]
+        const float t0 = f[s][t].x * __ldg(wk + 0) + f[s][t].y * __ldg(wk + 1);
+        const float t1 = f[s][t].x * __ldg(wk + 2) + f[s][t].y * __ldg(wk + 3);
+        if (vy[s] && vx[t]) { a0 += t0; a1 += t1; }
+      }
     uint16_t* o = p.concat + idx * p.cstride + p.coff;
     const uint32_t packed = (uint32_t)cvt16(a0, p.is_bf16) | ((uint32_t)cvt16(a1, p.is_bf16) << 16);
     *reinterpret_cast<uint32_t*>(o) = packed;
