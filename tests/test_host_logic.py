@@ -282,3 +282,21 @@ def test_build_is_a_no_op_when_fresh(monkeypatch):
     assert build.is_fresh()
     monkeypatch.setattr(build, "_nvcc", lambda: (_ for _ in ()).throw(AssertionError("nvcc invoked on a fresh tree")))
     assert build.build_library() == build.LIB_PATH
+
+
+def test_byte_over_255_formula_matches_both_reference_quotients():
+    """clip.cu / samplers.cu compute byte / 255 as q' = fma(fma(-q, 255, v), c, q), q = v * c, c = RN(1/255).  For all 256
+    byte values that equals np.float32(v) / 255.0 (float32 division: the history taps, main_dl.py:556-558) and
+    float32(v / 255.0) (float64 division cast at the feed: the current frame, main_dl.py:550, :568).  The two FMAs are
+    emulated in float64, which holds their exact products and sums for these magnitudes before the single rounding."""
+    v = np.arange(256, dtype=np.float64)
+    c = np.float64(np.float32(1.0) / np.float32(255.0))
+    assert np.float32(c) == np.float32(0.00392156885936856270)
+    q = (v * c).astype(np.float32).astype(np.float64)                 # fmul.rn
+    r = v - q * 255.0                                                 # fma(-q, 255, v): exact in float64, exact in float32
+    assert np.array_equal(r.astype(np.float32).astype(np.float64), r)
+    q2 = (r * c + q).astype(np.float32)                               # fma(r, c, q): one rounding
+    hist = np.arange(256, dtype=np.float32) / np.float32(255.0)
+    cur = (np.arange(256, dtype=np.float64) / 255.0).astype(np.float32)
+    assert np.array_equal(q2, hist) and np.array_equal(q2, cur)
+    assert np.count_nonzero(q.astype(np.float32) != cur) > 100        # the plain product is NOT enough
