@@ -756,6 +756,31 @@ __global__ void __launch_bounds__(256, 6) warp5_u8_kernel(const uint8_t* __restr
   }
 }
 
+// any width (W % 4 != 0): one thread per pixel, the taps and summation order of sample_px_kernel<ResizeWarpProvider>
+__global__ void __launch_bounds__(256) warp_u8_px_kernel(ResizeWarpProvider prov, const uint8_t* __restrict__ img,
+                                                         uint8_t* __restrict__ out_u8, float* __restrict__ out_f32, int B,
+                                                         int H, int W) {
+  const size_t total = (size_t)B * H * W;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % W);
+    const size_t r = i / W;
+    const int oy = (int)(r % H);
+    const int b = (int)(r / H);
+    const Taps t = prov.taps(b, oy, ox);
+    const uint8_t* imgb = img + (size_t)b * H * W * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (t.x[k] >= 0) acc = mul_add_rn(acc, t.w[k], byte_over_255(__ldg(imgb + ((size_t)t.y[k] * W + t.x[k]) * 3 + c)));
+      const float v = __fmul_rn(acc, 255.0f);
+      out_u8[i * 3 + c] = (uint8_t)(__float2int_rz(v) & 0xff);
+      if (out_f32) out_f32[i * 3 + c] = v;
+    }
+  }
+}
+
 // generic 4-tap sampler (grid_sample / Lie warp), lean form of sample3_kernel: one block per 64 x 16 output tile
 // (3-D grid), 32-bit image offsets, predicated loads instead of per-tap branches, 6 resident blocks per SM
 template <class Provider>
@@ -1005,7 +1030,14 @@ int flow_resize_warp_u8_impl(const uint8_t* img, const float* flow2_prescaled, u
                              int W, int fh, int fw, cudaStream_t st) {
   OFS_REQUIRE(B > 0 && fh > 0 && fw > 0 && H > 0 && W > 0, "flow_resize_warp_u8: bad shape");
   OFS_REQUIRE(img && flow2_prescaled && out_u8, "flow_resize_warp_u8: null pointer");
-  OFS_REQUIRE((W % 4) == 0 && ((uintptr_t)out_u8) % 4 == 0, "flow_resize_warp_u8: W %% 4 != 0 or unaligned output");
+  if ((W % 4) != 0 || ((uintptr_t)out_u8) % 4 != 0 || (size_t)H * W * 3 >= (1u << 31) || B > 65535 ||
+      (H + kTileH - 1) / kTileH > 65535) {
+    ResizeWarpProvider prov{FlowResize{flow2_prescaled, fh, fw, H, W, (float)fh / (float)H, (float)fw / (float)W, 1}};
+    const size_t px = (size_t)B * H * W;
+    warp_u8_px_kernel<<<grid_for(px, 256), 256, 0, st>>>(prov, img, out_u8, out_f32, B, H, W);
+    OFS_LAUNCH_CHECK();
+    return OFS_OK;
+  }
   Resize2 rz{reinterpret_cast<const float2*>(flow2_prescaled), fh, fw, (float)fh / (float)H, (float)fw / (float)W, (float)W, (float)H};
   if (out_f32)
     OFS_CUDA(launch_pdl(warp5_u8_kernel<true>, tile_grid3(B, H, W), dim3(256), 0, st, img, rz, out_u8, out_f32, B, H, W));

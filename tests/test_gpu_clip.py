@@ -60,7 +60,8 @@ def synth_clip(seed, T, H, W):
     return out
 
 
-@pytest.mark.parametrize("n_clips,T,H,W", [(1, 36, 96, 128), (2, 8, 120, 160)], ids=["one_clip_ring_wraps", "two_clips_lockstep"])
+@pytest.mark.parametrize("n_clips,T,H,W", [(1, 36, 96, 128), (2, 8, 120, 160), (1, 5, 90, 126)],
+                         ids=["one_clip_ring_wraps", "two_clips_lockstep", "width_not_a_multiple_of_4"])
 def test_clip_driver_matches_reference_loop(ofs, cuda_dev, n_clips, T, H, W):
     w = F.make_weights(0, "calibrated", head_scale=0.02)
     net = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=max(2, n_clips))
