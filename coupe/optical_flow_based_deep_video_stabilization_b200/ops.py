@@ -96,6 +96,10 @@ def conv2d_nhwc(x, w, b=None, stride=1, transposed=False, lrelu=False, precision
 
     x [B,H,W,Cin] CUDA f32; w CPU f32 TF layout ([k,k,Cin,Cout], or [4,4,Cout,Cin] when transposed);
     zero padding k//2 (conv) / TF SAME (transposed k4 s2).  Returns [B,Ho,Wo,Cout] CUDA f32.
+    block_n: N tile (0 = automatic); ksplit > 1: split-K (the result then carries one 16-bit rounding, as in the
+    network); cta_group: 1 single CTAs, 2 CTA pairs (tcgen05 cta_group::2), 4 pairs + slab groups (conv1 / conv2 form),
+    8 / 32 two / four K chunks per pipeline stage, 16 split-K inside a thread-block cluster (DSMEM reduction, same bits
+    as the workspace split-K); out16: the network's 16-bit TMA-store epilogue, widened to f32 afterwards.
     """
     x = _cuda_f32(x, "x")
     w = w.detach().to("cpu", torch.float32).contiguous()
