@@ -90,7 +90,7 @@ class ClockSampler(threading.Thread):
 
 
 def synth_inputs(torch, seed, batch, h, w, device=None, pinned=False):
-    from oracle import flownet as F  # deterministic generators only (no oracle arithmetic on this path)
+    from coupe.optical_flow_based_deep_video_stabilization_b200 import synthetic as F   # shared by both arms
 
     g = torch.Generator().manual_seed(seed)
     feats = F.make_feats(seed, batch)
@@ -169,7 +169,7 @@ def run_ours(args):
     import torch
 
     import coupe.optical_flow_based_deep_video_stabilization_b200 as ofs
-    from oracle import flownet as F  # weight / input generators only
+    from coupe.optical_flow_based_deep_video_stabilization_b200 import synthetic as F   # random-init weights, synthetic inputs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -8,7 +8,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import coupe.optical_flow_based_deep_video_stabilization_b200 as ofs  # noqa: E402
-from oracle import flownet as F  # noqa: E402
+from coupe.optical_flow_based_deep_video_stabilization_b200 import synthetic as F  # noqa: E402
 
 dev = torch.device("cuda", 0)
 net = ofs.FlowNetSPyramid(device=dev, max_batch=16)

@@ -9,7 +9,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import coupe.optical_flow_based_deep_video_stabilization_b200 as ofs  # noqa: E402
-from oracle import flownet as F  # noqa: E402  (weight generator only)
+from coupe.optical_flow_based_deep_video_stabilization_b200 import synthetic as F  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4

@@ -300,3 +300,18 @@ def test_byte_over_255_formula_matches_both_reference_quotients():
     cur = (np.arange(256, dtype=np.float64) / 255.0).astype(np.float32)
     assert np.array_equal(q2, hist) and np.array_equal(q2, cur)
     assert np.count_nonzero(q.astype(np.float32) != cur) > 100        # the plain product is NOT enough
+
+
+def test_package_and_oracle_generators_agree():
+    """bench.py / benchmarks draw random-init checkpoints and inputs from the package (they may not touch oracle/);
+    the oracle keeps its own copy.  Same seeds, same arrays."""
+    from coupe.optical_flow_based_deep_video_stabilization_b200 import synthetic as P
+    from oracle import flownet as O
+
+    for kind, hs in (("he", None), ("calibrated", 0.02)):
+        a, b = P.make_weights(3, kind, head_scale=hs), O.make_weights(3, kind, head_scale=hs)
+        assert list(a) == list(b)
+        for k in a:
+            assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k
+    assert torch.equal(P.make_feats(5, 1), O.make_feats(5, 1))
+    assert torch.equal(P.make_feats(5, 1, "smooth"), O.make_feats(5, 1, "smooth"))
