@@ -39,11 +39,22 @@ UNIT = "pairs/s"
 BATCH, FRAME_H, FRAME_W = 8, 720, 1280
 DENSE_GFLOP_PER_PAIR = 37.89      # 10 encoder convs + 4 transposed convs, literal MACs x 2
 WARP_BYTES_PER_PX = 24.0          # fused flow-resize+warp: image 12 + out 12 (+1.56 MB of flow2 per frame)
-# dram__bytes_read.sum + dram__bytes_write.sum per launch (set) from the committed ncu --set full capture of this
-# workload (profiles/r01_ncu_full_summary.md); refreshed by hand when the capture is
-NCU_TRAFFIC_DENSE_SET_BYTES = 451.0e6   # 14 dense GEMM launches + 4 split-K reductions, batch 8
-NCU_TRAFFIC_WARP_BYTES = 146.2e6        # warp5_kernel<true>, 8 x 720p
 FLOW2_BYTES = 382 * 510 * 2 * 4
+
+
+def load_ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch (set) of the dominant kernels, parsed from the newest
+    committed profiles/rNN_ncu_traffic.json (written by benchmarks/ncu_summarize.py from an `ncu --set full` capture of
+    this very command).  No file -> no claim (traffic: null)."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")))
+    if not files:
+        return None
+    with open(files[-1]) as f:
+        t = json.load(f)
+    t["source"] = os.path.relpath(files[-1], ROOT)
+    return t
 
 
 def load_peaks():
@@ -121,39 +132,42 @@ def cpu_oracle_rate(torch, n_pairs, h, w, threads):
 
 
 def run_reference(args):
+    """The reference's own CPU implementation of the path = the oracle port (TensorFlow 1.10 cannot be installed here),
+    on all host threads, on the SAME workload as the GPU arm: every step is one full batch of 8 distinct 720p frame
+    pairs (forward + flow glue + tf_warp each), two input sets alternating between steps."""
     import torch
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    pairs_per_step = 2                                        # bounded sample of the 8-pair step
-    rate_w, _ = cpu_oracle_rate(torch, 1, FRAME_H, FRAME_W, threads)
-    del rate_w
+    torch.set_num_threads(threads)
     from oracle import flownet as F
     from oracle import samplers as S
 
     wts = F.make_weights(0, "calibrated", head_scale=0.02)
-    feats, frames = synth_inputs(torch, 7, 1, FRAME_H, FRAME_W)
+    sets = [synth_inputs(torch, 100 + i, BATCH, FRAME_H, FRAME_W) for i in range(2)]
 
-    def step():
-        for _ in range(pairs_per_step):
-            o = F.forward_literal(feats, wts)
-            S.flow_resize_warp(frames, o["predict_flow2"], FRAME_H, FRAME_W)
+    def step(i):
+        feats, frames = sets[i % 2]
+        for b in range(BATCH):                                # the reference runs batch 1 per sess.run (main_dl.py:491)
+            o = F.forward_literal(feats[b:b + 1], wts)
+            S.flow_resize_warp(frames[b:b + 1], o["predict_flow2"], FRAME_H, FRAME_W)
 
-    for _ in range(args.warmup):
-        step()
+    for i in range(args.warmup):
+        step(i)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
+    for i in range(args.steps):
+        step(i)
     dt = time.perf_counter() - t0
-    value = pairs_per_step * args.steps / dt
-    sample = f"{pairs_per_step} of the {BATCH} 720p pairs per step, batch 1 each, fp32, {threads} torch threads"
+    value = BATCH * args.steps / dt
+    sample = (f"all {BATCH} pairs of every step ({args.steps} steps, 2 alternating input sets of {BATCH} distinct 720p pairs), "
+              f"batch 1 per call as the reference does, fp32 torch-CPU oracle, {threads} torch threads, {dt:.1f} s")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(), "pairs_per_step_timed": pairs_per_step},
+        "config": workload_config(),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference = CPU port (oracle/) of the TF-1.10 graph; TensorFlow/TensorLayer cannot be installed offline",
@@ -163,6 +177,13 @@ def run_reference(args):
 def workload_name():
     return (f"BASELINE configs[1]: FlowNetS-pyramid fwd (384x512x27) + flow glue + tf_warp at {FRAME_H}x{FRAME_W}, "
             f"batch {BATCH} independent frame pairs per GPU, random-init weights")
+
+
+def workload_config():
+    """The `config` object: identical for both arms (how each arm EXECUTES the workload is reported outside it)."""
+    return {"workload": workload_name(), "pairs_per_step_per_gpu": BATCH, "frame": [FRAME_H, FRAME_W],
+            "net_input": [384, 512, 27],
+            "l2": "every step reads a fresh 258 MB input set (> 126 MB L2); consecutive steps alternate between input sets"}
 
 
 def run_ours(args):
@@ -250,6 +271,29 @@ def run_ours(args):
         nstreams, streams = nstreams_saved, streams_saved
         barrier()
 
+    # ---- sustained: the same steps looped for >= args.sustained_seconds (the K-step region above is ~10 ms at boost
+    # clocks; MEASURED_PEAKS shows a B200 settling near 1.3 GHz under seconds of dense GEMM load)
+    sustained = None
+    if args.sustained_seconds > 0:
+        s_sampler = ClockSampler(local) if rank == 0 else None
+        barrier()
+        if s_sampler:
+            s_sampler.start()
+        chunk = 40 * nstreams
+        s_ms, s_steps, t_wall = 0.0, 0, time.perf_counter()
+        while time.perf_counter() - t_wall < args.sustained_seconds:
+            s_ms += timed_steps(chunk)
+            s_steps += chunk
+        barrier()
+        s_clocks = s_sampler.stop() if s_sampler else None
+        t_s = torch.tensor([s_ms], device=dev)
+        if dist is not None:
+            dist.all_reduce(t_s, op=dist.ReduceOp.MAX)
+        sustained = {"value": world * BATCH * s_steps / (float(t_s.item()) * 1e-3), "unit": UNIT, "steps": s_steps,
+                     "seconds": float(t_s.item()) * 1e-3, "ms_per_step": float(t_s.item()) / s_steps, "clocks": s_clocks,
+                     "how": f"chunks of {chunk} steps, {nstreams} in flight, CUDA-event timed back to back until "
+                            f">= {args.sustained_seconds} s of wall time; nvidia-smi sampled every 0.2 s meanwhile"}
+
     # ---- per-kernel breakdown, measured live with CUDA events on the launching stream (rank 0)
     roofline = roofline_warp = breakdown = None
     if rank == 0:
@@ -260,19 +304,23 @@ def run_ours(args):
         gemm_ms, macs, gemm_launches = net.time_kernels("dense", BATCH, iters=20)
         flops = 2.0 * macs
         ach = flops / (gemm_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": NCU_TRAFFIC_DENSE_SET_BYTES,
-                    "traffic_source": "ncu --set full, profiles/r01_ncu_full_summary.md (DRAM bytes of the launch set)",
+        ncu = load_ncu_traffic()
+        # the launch set is timed alone as a ~10 ms graph replay at boost clocks: the BURST peak is the denominator
+        roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["bf16_tflops"], "traffic": ncu.get("dense_set_bytes") if ncu else None,
+                    "traffic_source": (ncu["source"] + " (ncu --set full: DRAM bytes of the launch set)") if ncu else None,
                     "kernel": "conv_gemm*_kernel (the 14 dense conv / transposed-conv layers of one step, incl. split-K reductions)",
                     "launches_per_step": gemm_launches, "ms_per_step_in_kernel": gemm_ms, "share_of_step": gemm_ms / step_ms,
-                    "algorithmic_gflop_per_launch_set": flops / 1e9, "peak_source": peaks["source"] + " (sustained bf16)",
-                    "frac_of_burst_peak": ach / peaks["bf16_tflops"], "frac_of_nominal_2250": ach / 2250.0,
+                    "algorithmic_gflop_per_launch_set": flops / 1e9, "peak_source": peaks["source"] + " (burst bf16: kernel set timed alone)",
+                    "frac_of_sustained_peak": ach / peaks["bf16_tflops_sustained"], "peak_sustained": peaks["bf16_tflops_sustained"],
+                    "frac_of_nominal_2250": ach / 2250.0,
                     "timing": "20 repetitions of the launch set replayed from one CUDA graph, CUDA events on the launching stream"}
         wms, _, _ = net.time_kernels("warp", BATCH, frames=sets[0][1], iters=20)
         wbytes = BATCH * (FRAME_H * FRAME_W * WARP_BYTES_PER_PX + FLOW2_BYTES)
         wach = wbytes / (wms * 1e-3) / 1e9
         roofline_warp = {"bound": "hbm", "achieved": wach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": wach / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC_WARP_BYTES, "kernel": "warp5_kernel<true> (fused flow-resize + tf_warp)",
+                         "frac": wach / peaks["hbm_gbs"], "traffic": ncu.get("warp_bytes") if ncu else None,
+                         "kernel": "warp5_kernel<true> (fused flow-resize + tf_warp)",
                          "ms_per_launch": wms, "algorithmic_bytes_per_launch": wbytes, "frac_of_nominal_7700": wach / 7700.0,
                          "share_of_step": wms / step_ms, "peak_source": peaks["source"]}
         breakdown = [{"kernel": n, "ms": round(ms, 4), "tflops": (2 * m / (ms * 1e-3) / 1e12 if m else None)} for n, ms, m in prof]
@@ -374,11 +422,11 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": workload_name(), "pairs_per_step_per_gpu": BATCH, "frame": [FRAME_H, FRAME_W],
-                       "net_input": [384, 512, 27], "l2": f"{nsets} alternating input sets, 258 MB each (> 126 MB L2)",
-                       "steps_in_flight": nstreams,
-                       "parallelism": f"replicas x{world}, no data-path collective; {nstreams} independent batches in flight per GPU "
-                                      f"on {nstreams} CUDA streams"},
+            "config": workload_config(),
+            "execution": {"steps_in_flight": nstreams, "input_sets": nsets,
+                          "parallelism": f"replicas x{world}, no data-path collective; {nstreams} independent batches in flight per GPU "
+                                         f"on {nstreams} CUDA streams"},
+            "sustained": sustained,
             "value_one_step_at_a_time": (world * BATCH * args.steps / (single_ms * 1e-3)) if single_ms else None,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hf.numel() * 4 + hfr.numel() * 4),
                     "d2h_bytes_per_step": int(hout.numel() * 4), "steps": e2e_steps,
@@ -406,6 +454,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--precision", choices=["bf16", "fp16"], default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sustained-seconds", type=float, default=3.0, help="0 skips the sustained-clock block")
     ap.add_argument("--streams", type=int, default=2, help="independent batches in flight per GPU (1 = strictly sequential steps)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -37,12 +37,26 @@ LAYERS = {
     "deconv3": (24, 32, 770, 776, 128, 392, 4, 2, 1),
     "deconv2": (48, 64, 386, 392, 64, 200, 4, 2, 1),
     "predict2": (96, 128, 194, 200, 18, 18, 1, 1, 0),
+    # the same layers with every concat buffer padded to a multiple of 64 channels (128-byte aligned pixel rows for TMA)
+    "2a": (192, 256, 64, 64, 128, 256, 5, 2, 0),
+    "3a": (96, 128, 128, 256, 256, 256, 5, 2, 0),
+    "3_1a": (48, 64, 256, 256, 256, 448, 3, 1, 0),
+    "4a": (48, 64, 256, 448, 512, 512, 3, 2, 0),
+    "4_1a": (24, 32, 512, 512, 512, 832, 3, 1, 0),
+    "5a": (24, 32, 512, 832, 512, 512, 3, 2, 0),
+    "5_1a": (12, 16, 512, 512, 512, 1088, 3, 1, 0),
+    "6a": (12, 16, 512, 1088, 1024, 1024, 3, 2, 0),
+    "deconv5a": (6, 8, 1024, 1024, 512, 1088, 4, 2, 1),
+    "deconv4a": (12, 16, 1026, 1088, 256, 832, 4, 2, 1),
+    "deconv3a": (24, 32, 770, 832, 128, 448, 4, 2, 1),
+    "deconv2a": (48, 64, 386, 448, 64, 256, 4, 2, 1),
     # proxy for conv1 in space-to-depth form (25 K blocks of a 128-column 1-CTA tile on the 192 x 128 pair grid; the real thing has 35)
     "s2d_proxy": (192, 128, 64, 64, 128, 128, 5, 1, 0),
 }
 DEFAULTS = {"1": "64:1:1", "2": "128:1:1", "3": "256:1:1", "3_1": "256:1:1", "4": "256:1:1", "4_1": "256:1:1",
             "5": "256:6:1", "5_1": "256:6:1", "6": "256:8:1", "6_1": "256:8:1", "deconv5": "256:4:1",
             "deconv4": "256:3:1", "deconv3": "128:1:1", "deconv2": "64:1:1", "predict2": "32:1:1", "s2d_proxy": "128:1:1"}
+DEFAULTS.update({k + "a": v for k, v in DEFAULTS.items() if k + "a" in LAYERS})
 
 
 def macs(name, B):
@@ -142,6 +156,24 @@ def main():
                 line += (f"\n           trace: span {span_ns / 1e3:.1f} us, start skew {start_skew / 1e3:.1f} us; cycles (median CTA): "
                          f"total {total:.0f} (max {tmax:.0f}) | producer done {prod:.0f} | first full {first_full:.0f} | "
                          f"mma issued {mma_done:.0f} | epi first {epi_first:.0f} | epi done {epi_done:.0f}")
+                if dbg & 256:
+                    fine = [trace[g * 64 + j] for j in range(4096)]
+                    n_it = 0
+                    while n_it < 1024 and fine[n_it * 4 + 3]:
+                        n_it += 1
+                    pw, pi, mw, mc = ([fine[i * 4 + k] for i in range(n_it)] for k in range(4))
+                    lo, hi = min(8, n_it // 4), n_it
+                    def md(vals):
+                        vals = sorted(vals)
+                        return vals[len(vals) // 2] if vals else float("nan")
+                    line += ("\n           fine (CTA 0, %d items; medians over items %d..): producer wait-done -> loads issued %.0f | loads issued -> next wait-done %.0f"
+                             " || MMA wait-done -> committed %.0f | committed -> next wait-done %.0f"
+                             " || loads issued -> MMA sees full %.0f | period (MMA wait-done to wait-done) %.0f"
+                             % (n_it, lo, md([pi[i] - pw[i] for i in range(lo, hi)]), md([pw[i + 1] - pi[i] for i in range(lo, hi - 1)]),
+                                md([mc[i] - mw[i] for i in range(lo, hi)]), md([mw[i + 1] - mc[i] for i in range(lo, hi - 1)]),
+                                md([mw[i] - pi[i] for i in range(lo, hi)]), md([mw[i + 1] - mw[i] for i in range(lo, hi - 1)])))
+                    line += "\n           fine first 12 items (producer wait-done, issued, MMA wait-done, committed; cycles from the first stamp): " + " ".join(
+                        "[%d %d %d %d]" % (pw[i] - pw[0], pi[i] - pw[0], mw[i] - pw[0], mc[i] - pw[0]) for i in range(min(12, n_it)))
                 rec["trace"] = {"span_us": span_ns / 1e3, "start_skew_us": start_skew / 1e3, "total": total, "total_max": tmax,
                                 "producer_done": prod, "first_full": first_full, "mma_issued": mma_done,
                                 "epi_first": epi_first, "epi_done": epi_done}

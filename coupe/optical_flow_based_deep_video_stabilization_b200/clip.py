@@ -27,12 +27,14 @@ class ClipStabilizer:
         self.n, self.h, self.w = int(n_clips), int(height), int(width)
         self._h = C.c_void_p()
         _lib.check(self._lib.ofs_clips_create(C.byref(self._h), net._h, self.n, self.h, self.w))
+        net.retain()                        # the C side keeps the raw ofs_net*: the net must not be destroyed under it
         self._pending = collections.deque()   # (frames, out, outf, single) of submitted steps: keeps the buffers alive
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.ofs_clips_destroy(self._h)
             self._h = C.c_void_p()
+            self.net.release()
 
     def __del__(self):
         try:
@@ -103,6 +105,19 @@ class ClipStabilizer:
         _lib.check(self._lib.ofs_clips_submit_host(self._h, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
                                                    outf.ctypes.data_as(C.c_void_p) if return_float else None))
         self._pending.append((a, out, outf, single))
+
+    def submit_device(self, frames_u8, out_u8):
+        """submit() for frames that already live on the GPU: `frames_u8` / `out_u8` are contiguous CUDA uint8 tensors
+        [n_clips,H,W,3] (BGR); the stabilised frames land in `out_u8` on the device -- e.g. a slice of a per-rank
+        [n_frames,H,W,3] buffer that sharding.gather_output() later collects over NCCL.  Same ordering rules as submit()."""
+        import torch
+
+        shape = (self.n, self.h, self.w, 3)
+        for t, name in ((frames_u8, "frames_u8"), (out_u8, "out_u8")):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous() and tuple(t.shape) == shape):
+                raise ValueError(f"{name} must be a contiguous CUDA uint8 tensor of shape {shape}")
+        _lib.check(self._lib.ofs_clips_submit_host(self._h, C.c_void_p(frames_u8.data_ptr()), C.c_void_p(out_u8.data_ptr()), None))
+        self._pending.append((frames_u8, out_u8, None, False))
 
     def wait(self):
         """Blocks until the oldest submitted step has landed and returns what step() would have returned for it."""

@@ -385,7 +385,7 @@ int ofs_clips_submit_host(ofs_clips* c, const uint8_t* frames_bgr, uint8_t* out_
   h.first = i == 0;
   if (i >= kSlots) OFS_CUDA(cudaStreamWaitEvent(c->st_in, s.ev_done, 0));
   OFS_CUDA(cudaMemcpyAsync(s.d_state, &h, sizeof(h), cudaMemcpyHostToDevice, c->st_in));
-  OFS_CUDA(cudaMemcpyAsync(s.d_frame, frames_bgr, fpx, cudaMemcpyHostToDevice, c->st_in));
+  OFS_CUDA(cudaMemcpyAsync(s.d_frame, frames_bgr, fpx, cudaMemcpyDefault, c->st_in));   // host (pinned) or device source
   OFS_CUDA(cudaEventRecord(s.ev_in, c->st_in));
   OFS_CUDA(cudaStreamWaitEvent(c->st, s.ev_in, 0));
   if (i >= kSlots) OFS_CUDA(cudaStreamWaitEvent(c->st, s.ev_out, 0));
@@ -393,8 +393,8 @@ int ofs_clips_submit_host(ofs_clips* c, const uint8_t* frames_bgr, uint8_t* out_
   count_launch(s.graph_launches);
   OFS_CUDA(cudaEventRecord(s.ev_done, c->st));
   OFS_CUDA(cudaStreamWaitEvent(c->st_out, s.ev_done, 0));
-  OFS_CUDA(cudaMemcpyAsync(out_bgr_u8, s.d_out_u8, fpx, cudaMemcpyDeviceToHost, c->st_out));
-  if (want_f32) OFS_CUDA(cudaMemcpyAsync(out_bgr_f32, s.d_out_f32, fpx * 4, cudaMemcpyDeviceToHost, c->st_out));
+  OFS_CUDA(cudaMemcpyAsync(out_bgr_u8, s.d_out_u8, fpx, cudaMemcpyDefault, c->st_out));   // host or device destination
+  if (want_f32) OFS_CUDA(cudaMemcpyAsync(out_bgr_f32, s.d_out_f32, fpx * 4, cudaMemcpyDefault, c->st_out));
   OFS_CUDA(cudaEventRecord(s.ev_out, c->st_out));
   s.busy = true;
   ++c->frame;

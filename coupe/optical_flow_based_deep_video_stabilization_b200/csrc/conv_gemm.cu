@@ -28,6 +28,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "ptx.cuh"
 
@@ -198,7 +201,10 @@ __device__ __forceinline__ void mma(uint32_t d, uint32_t da_lo, uint32_t db_lo, 
 // cluster barrier every CTA sums its share of the tile's ROWS over all peers through distributed shared memory in
 // split order -- bias first, exactly the order of splitk_reduce_kernel, so both paths give the same bits -- and
 // stores final 16-bit activations.  No workspace round trip through L2, no reduce launch.
-template <int BLOCK_N, bool kPair, int kT, int kHead, int kG, bool kKC = false>
+// kInstr: instrumented build of the same kernel (per-CTA trace stamps, per-item stamps, the debug skip switches) used by
+// benchmarks/conv_bench.py only.  The production instantiations carry none of it: the two single-thread role loops are
+// bound by their instruction count (~4 cycles per dependent instruction), so every test inside them costs time.
+template <int BLOCK_N, bool kPair, int kT, int kHead, int kG, bool kKC = false, bool kInstr = false>
 __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
   using Cfg = GemmCfg<BLOCK_N, kPair, kT, kHead, kG>;
   static_assert(!kKC || (!kPair && kT == 1 && kHead == 0 && kG == 1 && BLOCK_N == 256), "cluster split-K: plain 1-CTA 256-column tiles");
@@ -222,9 +228,11 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
   const uint32_t full0 = stg0 + Cfg::kStgTotal, empty0 = full0 + 8 * S;
   const uint32_t tfull0 = full0 + 16 * S, tempty0 = tfull0 + 16, sfull0 = tfull0 + 32, sempty0 = tfull0 + 48;
 
-  if (p.trace && threadIdx.x == 0) {
-    p.trace[(size_t)blockIdx.x * 32 + 11] = (long long)ptx::globaltimer();
-    p.trace[(size_t)blockIdx.x * 32 + 12] = clock64();
+  const int dbg = kInstr ? p.debug : 0;
+  long long* const trace_base = kInstr ? p.trace : nullptr;
+  if (trace_base && threadIdx.x == 0) {
+    trace_base[(size_t)blockIdx.x * 32 + 11] = (long long)ptx::globaltimer();
+    trace_base[(size_t)blockIdx.x * 32 + 12] = clock64();
   }
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
@@ -262,7 +270,10 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
   ptx::tc_fence_after();
   // everything above overlapped the previous kernel's tail; from here on its results are needed
   pdl_wait();
-  pdl_launch_dependents();
+  // (the trigger that lets the NEXT kernel of the stream start launching sits at the end of the producer loop: this
+  // kernel fills every SM with one 225 KB CTA, so a dependent launched earlier could not become resident anyway;
+  // triggered late, its CTAs take over SMs whose CTA has already exited -- the idle part of the last wave -- and run
+  // their prologue there while this kernel's stragglers finish)
 
   const int num_kb = p.ntaps * p.nchunks;
   // tail split (see ConvGemmParams::tail_t0): only compiled into the plain 256-column kernels
@@ -275,22 +286,25 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
     else { n_t = tile % p.tiles_n; rest = tile / p.tiles_n; half = -1; }
   };
   const int tileW = 1 << p.tileW_log2;
-  long long* trace = p.trace ? p.trace + (size_t)blockIdx.x * 32 : nullptr;
+  long long* trace = trace_base ? trace_base + (size_t)blockIdx.x * 32 : nullptr;
   if (trace && threadIdx.x == 0) { trace[0] = (long long)ptx::globaltimer(); trace[1] = clock64(); }
+  // debug bit 8 of the high byte (256): CTA 0 stamps every stage item of both single-thread roles (measurement only)
+  long long* fine = (trace_base && (dbg & 256) && blockIdx.x == 0) ? trace_base + (size_t)gridDim.x * 64 : nullptr;
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     const bool leader = ptx::elect_one();
-    const bool do_a = !(p.debug & 2), do_b = !(p.debug & 4);
+    const bool do_a = !(dbg & 2), do_b = !(dbg & 4);
     const uint32_t a_tx = (kPair ? 2u : 1u) * (uint32_t)(do_a ? p.a_bytes : 0);
     const uint32_t b_tx = (kPair ? 2u : 1u) * (uint32_t)(do_b ? Cfg::kBBytes : 0);
     // where TMA bytes are posted; mapa comes out of inline asm, so broadcast it to make it provably warp-uniform
     const uint32_t full_tgt0 = kPair ? __shfl_sync(0xffffffffu, ptx::mapa_u32(full0, 0), 0) : full0;
     const int piece_bytes = p.piece_rows * tileW * kBlockK * 2;
     const int npieces = p.npieces;
-    int stage = 0;
+    // Addresses of a stage are derived from the stage index (one multiply / shift-add each) instead of being carried as
+    // running pointers with their wrap-around values: fewer live uniform registers, fewer instructions per item.
+    int stage = 0, fitem = 0;
     uint32_t phase = 0;
-    uint32_t sa = smem_base, full_s = full0, empty_s = empty0, full_t = full_tgt0;
     for (int tile = unit; tile < total_tiles; tile += nunits) {
       int n_t, rest, half;
       decode_tile(tile, n_t, rest, half);
@@ -320,52 +334,61 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
         const int yy = y0 + p.tap_y[ti];
         const int ylim = p.Hg + p.tap_y[ti];
         const int ch_end = min(p.nchunks, ch + (kb1 - kb));
+        const int gn = kT > 1 ? (int)p.grp_n[ti] : 1;   // K blocks of a stage of this tap (slab group)
         while (ch < ch_end) {
-          const int gn = kT > 1 ? (int)p.grp_n[ti] : 1;   // K blocks of this stage (slab group)
           const int gc = kG > 1 ? min(kG, ch_end - ch) : 1;   // 64-channel chunks of this stage (chunk group)
+          const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)Cfg::kStageBytes;
+          const uint32_t boff = 8u * (uint32_t)stage;
           long long tw0 = 0;
           if (trace) tw0 = clock64();
-          lean::wait(empty_s, phase ^ 1);
+          lean::wait(empty0 + boff, phase ^ 1);
           if (trace && leader) trace[24] += clock64() - tw0;     // producer: cycles blocked on a free stage
+          if (fine && leader && fitem < 1024) fine[fitem * 4 + 0] = clock64();
           if (leader) {
-            if (!kPair || rank == 0) lean::expect_tx(full_s, (uint32_t)gc * (a_tx + (uint32_t)gn * b_tx_t));
-            for (int g = 0; g < gc; ++g) {
-              const uint32_t sa_g = sa + (uint32_t)g * Cfg::kABytes;
-              if (do_a) {
-                if (npieces == 1) {
-                  lean::tma5d<kPair>(sa_g, &p.tmap_a, full_t, c + g * kBlockK, x, pp, yy, b0);
-                } else {
-                  int b = b0, y = yy;
-                  uint32_t dst = sa_g;
-                  for (int pc = 0; pc < npieces; ++pc) {
-                    lean::tma5d<kPair>(dst, &p.tmap_a, full_t, c + g * kBlockK, x, pp, y, b);
-                    dst += piece_bytes;
-                    y += p.piece_rows;
-                    if (y >= ylim) { y -= p.Hg; ++b; }
+            const uint32_t full_t = full_tgt0 + boff;
+            if (!kPair || rank == 0) lean::expect_tx(full0 + boff, (uint32_t)gc * (a_tx + (uint32_t)gn * b_tx_t));
+#pragma unroll
+            for (int g = 0; g < kG; ++g) {
+              if (g < gc) {
+                const uint32_t sa_g = sa + (uint32_t)g * Cfg::kABytes;
+                if (do_a) {
+                  if (npieces == 1) {
+                    lean::tma5d<kPair>(sa_g, &p.tmap_a, full_t, c + g * kBlockK, x, pp, yy, b0);
+                  } else {
+                    int b = b0, y = yy;
+                    uint32_t dst = sa_g;
+                    for (int pc = 0; pc < npieces; ++pc) {
+                      lean::tma5d<kPair>(dst, &p.tmap_a, full_t, c + g * kBlockK, x, pp, y, b);
+                      dst += piece_bytes;
+                      y += p.piece_rows;
+                      if (y >= ylim) { y -= p.Hg; ++b; }
+                    }
                   }
                 }
-              }
-              if (do_b) {
-                const uint32_t sb_g = sa + kG * Cfg::kABytes + (uint32_t)g * Cfg::kBBytes;
-                lean::tma2d<kPair>(sb_g, tmap_w, full_t, kcol + g * kBlockK, w_row);
-                if constexpr (kT > 1) {
-                  for (int t = 1; t < gn; ++t)
-                    lean::tma2d<kPair>(sb_g + t * Cfg::kBBytes, tmap_w, full_t, kcol + t * kBlockK, w_row);
+                if (do_b) {
+                  const uint32_t sb_g = sa + kG * Cfg::kABytes + (uint32_t)g * Cfg::kBBytes;
+                  lean::tma2d<kPair>(sb_g, tmap_w, full_t, kcol + g * kBlockK, w_row);
+                  if constexpr (kT > 1) {
+                    for (int t = 1; t < gn; ++t)
+                      lean::tma2d<kPair>(sb_g + t * Cfg::kBBytes, tmap_w, full_t, kcol + t * kBlockK, w_row);
+                  }
                 }
               }
             }
           }
+          if (fine && leader && fitem < 1024) fine[fitem * 4 + 1] = clock64();
+          ++fitem;
           c += gc * kBlockK;
           kcol += gc * gn * kBlockK;
           ch += gc; kb += gc;
-          sa += Cfg::kStageBytes; full_s += 8; empty_s += 8; full_t += 8;
-          if (++stage == S) { stage = 0; phase ^= 1; sa = smem_base; full_s = full0; empty_s = empty0; full_t = full_tgt0; }
+          if (++stage == S) { stage = 0; phase ^= 1; }
         }
         ch = 0;
         ++tap;
       }
     }
     if (trace && leader) trace[2] = clock64();
+    pdl_launch_dependents();   // every load of this CTA has been issued
   } else if (warp == 1) {
     if (rank == 0) {
       // ====================================== MMA issuer ======================================
@@ -379,11 +402,9 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
       const uint32_t da0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t db0 = (((smem_base + kG * Cfg::kABytes) & 0x3FFFFu) >> 4) | (1u << 16);
       constexpr uint32_t kStep = (uint32_t)(Cfg::kStageBytes >> 4);   // descriptor address field is in 16-byte units
-      const bool do_mma = !(p.debug & 1);
-      int stage = 0;
+      const bool do_mma = !(dbg & 1);
+      int stage = 0, fitem = 0;
       uint32_t phase = 0;
-      uint32_t da = da0, db = db0;
-      uint32_t full_s = full0, empty_s = empty0;
       uint32_t acc = 0, acc_phase = 0;
       for (int tile = unit; tile < total_tiles; tile += nunits) {
         long long tt0 = 0;
@@ -396,15 +417,20 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
                                : (kHead && (tile % p.tiles_n) == p.tiles_n - 1) ? idesc_last : idesc_main;
         const int ks = (kTail && tile >= tail_t0) ? 0 : tile / (p.tiles_n * p.tiles_mp * p.phases);
         const int kb0 = ks * p.kb_per_split;
-        const int nkb = kG > 1 ? p.ntaps * ((p.nchunks + kG - 1) / kG)      // stage items per tile (chunk groups)
+        const int per_tap = (p.nchunks + kG - 1) / kG;
+        const int nkb = kG > 1 ? p.ntaps * per_tap      // stage items per tile (chunk groups)
                                : min(num_kb, kb0 + p.kb_per_split) - kb0;
+        const int gi0 = kT > 1 ? ((tile / (p.tiles_n * p.tiles_mp)) % p.phases) * p.ntaps + kb0 : 0;
         for (int i = 0; i < nkb; ++i) {
+          const uint32_t da = da0 + (uint32_t)stage * kStep, db = db0 + (uint32_t)stage * kStep;
+          const uint32_t boff = 8u * (uint32_t)stage;
           long long tw0 = 0;
           if (trace) tw0 = clock64();
-          lean::wait(full_s, phase);
+          lean::wait(full0 + boff, phase);
           ptx::tc_fence_after();
           if (trace && leader) { trace[22] += clock64() - tw0; trace[23] += 1; }   // MMA warp: cycles blocked on operands
           if (trace && leader && tile == unit && i == 0) trace[3] = clock64();
+          if (fine && leader && fitem < 1024) fine[fitem * 4 + 2] = clock64();
           if (leader) {
             if (do_mma) {
               if constexpr (kT > 1) {
@@ -412,10 +438,10 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
                 // The 128-byte swizzle is a function of the absolute shared-memory address (bits 4-6 ^= bits 7-9)
                 // for TMA writes and UMMA reads alike, so a row-shifted start address needs no further descriptor
                 // change (measured on B200: the base-offset field must stay 0 -- tests "slab_*").
-                const int gi = ((tile / (p.tiles_n * p.tiles_mp)) % p.phases) * p.ntaps + kb0 + i;
+                const int gi = gi0 + i;
                 const int gn = (int)p.grp_n[gi];
                 for (int t = 0; t < gn; ++t) {
-                  const uint32_t a_lo = da + ((p.debug & 128) ? 0u : (uint32_t)p.grp_off[gi][t] * 8u);   // debug 128: timing of aligned windows
+                  const uint32_t a_lo = da + ((dbg & 128) ? 0u : (uint32_t)p.grp_off[gi][t] * 8u);   // debug 128: timing of aligned windows
                   const uint32_t b_lo = db + (uint32_t)t * (uint32_t)(Cfg::kBBytes >> 4);
                   lean::mma<kPair>(d_tmem, a_lo, b_lo, kDescHi, idesc, (i > 0 || t > 0) ? 1u : 0u);
                   lean::mma<kPair>(d_tmem, a_lo + 2, b_lo + 2, kDescHi, idesc, 1u);
@@ -424,7 +450,6 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
                 }
               } else if constexpr (kG > 1) {
                 // chunk group (ksplit == 1): stage i of a tap holds chunks [kG*j, kG*j + gc) of that tap
-                const int per_tap = (p.nchunks + kG - 1) / kG;
                 const int j = i % per_tap;
                 const int gc = min(kG, p.nchunks - j * kG);
                 for (int g = 0; g < gc; ++g) {
@@ -442,10 +467,11 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
                 lean::mma<kPair>(d_tmem, da + 6, db + 6, kDescHi, idesc, 1u);
               }
             }
-            lean::commit<kPair>(empty_s);   // the stage is reusable (in both CTAs) once these MMAs have read it
+            lean::commit<kPair>(empty0 + boff);   // the stage is reusable (in both CTAs) once these MMAs have read it
           }
-          da += kStep; db += kStep; full_s += 8; empty_s += 8;
-          if (++stage == S) { stage = 0; phase ^= 1; da = da0; db = db0; full_s = full0; empty_s = empty0; }
+          if (fine && leader && fitem < 1024) fine[fitem * 4 + 3] = clock64();
+          ++fitem;
+          if (++stage == S) { stage = 0; phase ^= 1; }
         }
         if (leader) lean::commit<kPair>(tfull0 + 8 * acc);   // accumulator complete
         acc ^= 1;
@@ -470,7 +496,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
       const int ty = row >> p.tileW_log2;
       const int gy = (m_t / p.tiles_x) * p.tile_rows + ty;
       const int gx = ((m_t % p.tiles_x) << p.tileW_log2) + (row & (tileW - 1));
-      const bool valid = (m_t < p.tiles_m) && (ty < p.tile_rows) && (gy < p.rows_total) && !(p.debug & 8);
+      const bool valid = (m_t < p.tiles_m) && (ty < p.tile_rows) && (gy < p.rows_total) && !(dbg & 8);
       const int b = gy / p.Hg;
       const int y = gy - b * p.Hg;
       const int oy = y * p.out_scale + p.out_oy[ph];
@@ -614,7 +640,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
           __syncwarp();
           const int gy0 = (m_t / p.tiles_x) * p.tile_rows;
           const int rows_valid = min(p.tile_rows, p.rows_total - gy0);
-          if (m_t < p.tiles_m && rows_valid > 0 && !(p.debug & 8)) {
+          if (m_t < p.tiles_m && rows_valid > 0 && !(dbg & 8)) {
             const int nflt = rows_valid * tileW * nv;            // multiple of 2 (nv even); tile base is 8-byte aligned
             const int w0 = quad * 32 * nv, w1 = min(nflt, w0 + 32 * nv);
             float2* dst = reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + (size_t)gy0 * p.Wg * nv + w0);
@@ -661,7 +687,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
           const int gy0 = (m_t / p.tiles_x) * p.tile_rows;
           const int ox0 = (m_t % p.tiles_x) << p.tileW_log2;
           const int b0 = gy0 / p.Hg, y0 = gy0 - b0 * p.Hg;
-          const bool do_store = m_t < p.tiles_m && !(p.debug & 8);
+          const bool do_store = m_t < p.tiles_m && !(dbg & 8);
           const int ks = rest / (p.tiles_mp * p.phases);
           const int cw = p.tma_store == 2 ? 32 : 64;
 #pragma unroll 1
@@ -714,7 +740,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
       const int ty = row >> p.tileW_log2;
       const int gy = (m_t / p.tiles_x) * p.tile_rows + ty;
       const int gx = ((m_t % p.tiles_x) << p.tileW_log2) + (row & (tileW - 1));
-      const bool valid = (m_t < p.tiles_m) && (ty < p.tile_rows) && (gy < p.rows_total) && !(p.debug & 8);
+      const bool valid = (m_t < p.tiles_m) && (ty < p.tile_rows) && (gy < p.rows_total) && !(dbg & 8);
       if (!valid) continue;   // warp-uniform
       const int b = gy / p.Hg;
       const int y = gy - b * p.Hg;
@@ -758,40 +784,40 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
   }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool kInstr>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  conv_gemm_body<BLOCK_N, false, 1, 0, 1>(p);
+  conv_gemm_body<BLOCK_N, false, 1, 0, 1, false, kInstr>(p);
 }
 // four K chunks per stage, narrow fp32 tiles (predict2 product)
-template <int BLOCK_N>
+template <int BLOCK_N, bool kInstr>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemmg4_kernel(const __grid_constant__ ConvGemmParams p) {
-  conv_gemm_body<BLOCK_N, false, 1, 0, 4>(p);
+  conv_gemm_body<BLOCK_N, false, 1, 0, 4, false, kInstr>(p);
 }
 // split-K inside a thread-block cluster of ksplit CTAs (cluster size set at launch)
-template <int BLOCK_N>
+template <int BLOCK_N, bool kInstr>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemmk_kernel(const __grid_constant__ ConvGemmParams p) {
-  conv_gemm_body<BLOCK_N, false, 1, 0, 1, true>(p);
+  conv_gemm_body<BLOCK_N, false, 1, 0, 1, true, kInstr>(p);
 }
 // transposed conv with the level's flow head fused as 16 extra accumulator columns
-template <int BLOCK_N>
+template <int BLOCK_N, bool kInstr>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemmh_kernel(const __grid_constant__ ConvGemmParams p) {
-  conv_gemm_body<BLOCK_N, false, 1, 16, 1>(p);
+  conv_gemm_body<BLOCK_N, false, 1, 16, 1, false, kInstr>(p);
 }
-template <int BLOCK_N>
+template <int BLOCK_N, bool kInstr>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
-  conv_gemm_body<BLOCK_N, true, 1, 0, 1>(p);
+  conv_gemm_body<BLOCK_N, true, 1, 0, 1, false, kInstr>(p);
 }
 // chunk groups: two 64-channel K blocks per stage (narrow-N layers: half the handshakes), with / without fused head
-template <int BLOCK_N, int kHead>
+template <int BLOCK_N, int kHead, bool kInstr>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemmg_kernel(const __grid_constant__ ConvGemmParams p) {
-  conv_gemm_body<BLOCK_N, false, 1, kHead, 2>(p);
+  conv_gemm_body<BLOCK_N, false, 1, kHead, 2, false, kInstr>(p);
 }
 // slab mode (CTA pairs): kT taps of a group per stage
-template <int BLOCK_N, int kT>
+template <int BLOCK_N, int kT, bool kInstr>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     conv_gemm2s_kernel(const __grid_constant__ ConvGemmParams p) {
-  conv_gemm_body<BLOCK_N, true, kT, 0, 1>(p);
+  conv_gemm_body<BLOCK_N, true, kT, 0, 1, false, kInstr>(p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -900,127 +926,74 @@ int encode_map(CUtensorMap* map, int is_bf16, int rank, const void* base, const 
   return OFS_OK;
 }
 
+// One launch path for every GEMM variant.  The opt-in to > 48 KB of dynamic shared memory is a per-function,
+// per-device attribute: it is set once per (kernel, device) under a mutex (several caller threads may hit the first
+// launch of a kernel at the same time -- bench.py drives two).
+int launch_gemm(void (*kernel)(const ConvGemmParams), size_t smem, const ConvPlan& plan, cudaStream_t st, unsigned cluster_x) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  OFS_CUDA(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_pair((const void*)kernel, dev);
+    if (!done.count(key)) {
+      OFS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      done.insert(key);
+    }
+  }
+  if (cluster_x) {   // cluster split-K: cluster size = split factor, set at launch
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(plan.grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_x;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OFS_CUDA(cudaLaunchKernelEx(&cfg, kernel, plan.p));
+  } else {
+    pdl_set_kind(1);
+    OFS_CUDA(launch_pdl(kernel, dim3(plan.grid), dim3(kThreads), smem, st, plan.p));
+  }
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
+}
+
+// instrumented instantiations only when the plan asks for a trace or a debug switch (benchmarks/conv_bench.py)
+#define OFS_PICK(plan, K, ...) (((plan).p.trace || (plan).p.debug) ? K<__VA_ARGS__, true> : K<__VA_ARGS__, false>)
+
 template <int BLOCK_N>
 int launch_t(const ConvPlan& plan, cudaStream_t st) {
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  OFS_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    OFS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)GemmCfg<BLOCK_N, false>::kSmem));
-    attr_set[dev] = true;
-  }
-  pdl_set_kind(1);
-  OFS_CUDA(launch_pdl(conv_gemm_kernel<BLOCK_N>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, false>::kSmem, st, plan.p));
-  OFS_LAUNCH_CHECK();
-  return OFS_OK;
+  return launch_gemm(OFS_PICK(plan, conv_gemm_kernel, BLOCK_N), GemmCfg<BLOCK_N, false>::kSmem, plan, st, 0);
 }
-
 template <int BLOCK_N>
 int launch_t2(const ConvPlan& plan, cudaStream_t st) {
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  OFS_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    OFS_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)GemmCfg<BLOCK_N, true>::kSmem));
-    attr_set[dev] = true;
-  }
-  pdl_set_kind(1);
-  OFS_CUDA(launch_pdl(conv_gemm2_kernel<BLOCK_N>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, true>::kSmem, st, plan.p));
-  OFS_LAUNCH_CHECK();
-  return OFS_OK;
+  return launch_gemm(OFS_PICK(plan, conv_gemm2_kernel, BLOCK_N), GemmCfg<BLOCK_N, true>::kSmem, plan, st, 0);
 }
-
 template <int BLOCK_N>
 int launch_tk(const ConvPlan& plan, cudaStream_t st) {
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  OFS_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    OFS_CUDA(cudaFuncSetAttribute(conv_gemmk_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)GemmCfg<BLOCK_N, false>::kSmem));
-    attr_set[dev] = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(plan.grid);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = GemmCfg<BLOCK_N, false>::kSmem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)plan.p.ksplit;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  OFS_CUDA(cudaLaunchKernelEx(&cfg, conv_gemmk_kernel<BLOCK_N>, plan.p));
-  OFS_LAUNCH_CHECK();
-  return OFS_OK;
+  return launch_gemm(OFS_PICK(plan, conv_gemmk_kernel, BLOCK_N), GemmCfg<BLOCK_N, false>::kSmem, plan, st, (unsigned)plan.p.ksplit);
 }
-
 template <int BLOCK_N>
 int launch_th(const ConvPlan& plan, cudaStream_t st) {
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  OFS_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    OFS_CUDA(cudaFuncSetAttribute(conv_gemmh_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)GemmCfg<BLOCK_N, false, 1, 16>::kSmem));
-    attr_set[dev] = true;
-  }
-  pdl_set_kind(1);
-  OFS_CUDA(launch_pdl(conv_gemmh_kernel<BLOCK_N>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, false, 1, 16>::kSmem, st, plan.p));
-  OFS_LAUNCH_CHECK();
-  return OFS_OK;
+  return launch_gemm(OFS_PICK(plan, conv_gemmh_kernel, BLOCK_N), GemmCfg<BLOCK_N, false, 1, 16>::kSmem, plan, st, 0);
 }
-
 template <int BLOCK_N, int kHead>
 int launch_tg(const ConvPlan& plan, cudaStream_t st) {
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  OFS_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    OFS_CUDA(cudaFuncSetAttribute(conv_gemmg_kernel<BLOCK_N, kHead>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)GemmCfg<BLOCK_N, false, 1, kHead, 2>::kSmem));
-    attr_set[dev] = true;
-  }
-  pdl_set_kind(1);
-  OFS_CUDA(launch_pdl(conv_gemmg_kernel<BLOCK_N, kHead>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, false, 1, kHead, 2>::kSmem, st, plan.p));
-  OFS_LAUNCH_CHECK();
-  return OFS_OK;
+  return launch_gemm(OFS_PICK(plan, conv_gemmg_kernel, BLOCK_N, kHead), GemmCfg<BLOCK_N, false, 1, kHead, 2>::kSmem, plan, st, 0);
 }
-
 template <int BLOCK_N>
 int launch_tg4(const ConvPlan& plan, cudaStream_t st) {
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  OFS_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    OFS_CUDA(cudaFuncSetAttribute(conv_gemmg4_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)GemmCfg<BLOCK_N, false, 1, 0, 4>::kSmem));
-    attr_set[dev] = true;
-  }
-  pdl_set_kind(1);
-  OFS_CUDA(launch_pdl(conv_gemmg4_kernel<BLOCK_N>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, false, 1, 0, 4>::kSmem, st, plan.p));
-  OFS_LAUNCH_CHECK();
-  return OFS_OK;
+  return launch_gemm(OFS_PICK(plan, conv_gemmg4_kernel, BLOCK_N), GemmCfg<BLOCK_N, false, 1, 0, 4>::kSmem, plan, st, 0);
 }
-
 template <int BLOCK_N, int kT>
 int launch_t2s(const ConvPlan& plan, cudaStream_t st) {
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  OFS_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    OFS_CUDA(cudaFuncSetAttribute(conv_gemm2s_kernel<BLOCK_N, kT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)GemmCfg<BLOCK_N, true, kT>::kSmem));
-    attr_set[dev] = true;
-  }
-  pdl_set_kind(1);
-  OFS_CUDA(launch_pdl(conv_gemm2s_kernel<BLOCK_N, kT>, dim3(plan.grid), dim3(kThreads), GemmCfg<BLOCK_N, true, kT>::kSmem, st, plan.p));
-  OFS_LAUNCH_CHECK();
-  return OFS_OK;
+  return launch_gemm(OFS_PICK(plan, conv_gemm2s_kernel, BLOCK_N, kT), GemmCfg<BLOCK_N, true, kT>::kSmem, plan, st, 0);
 }
 
 int launch_reduce(const ConvPlan& plan, cudaStream_t st) {
@@ -1682,13 +1655,13 @@ extern "C" int ofs_conv2d_bench(int B, int H, int W, int Cin, int in_cs, int Cou
             cudaMalloc((void**)&b_dev, (size_t)plan.p.n_pad * 4) == cudaSuccess &&
             (plan.ws_bytes == 0 || cudaMalloc((void**)&ws, plan.ws_bytes) == cudaSuccess) &&
             (flush_bytes == 0 || cudaMalloc(&fl, flush_bytes) == cudaSuccess) &&
-            cudaMalloc((void**)&tr, (size_t)plan.grid * 64 * 8) == cudaSuccess &&
+            cudaMalloc((void**)&tr, ((size_t)plan.grid * 96 + 4096) * 8) == cudaSuccess &&
             cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess;
   if (!ok) { cleanup(); set_error("ofs_conv2d_bench: allocation failed"); return OFS_ENOMEM; }
   fill16_kernel<<<sm_count() * 4, 256, 0, st>>>((uint16_t*)x16, npix * in_cs, 1u, 1, 1.0f);
   fill16_kernel<<<sm_count() * 4, 256, 0, st>>>((uint16_t*)w_dev, w_elems, 2u, 1, 0.05f);
   cudaMemsetAsync(b_dev, 0, (size_t)plan.p.n_pad * 4, st);
-  cudaMemsetAsync(tr, 0, (size_t)plan.grid * 64 * 8, st);
+  cudaMemsetAsync(tr, 0, ((size_t)plan.grid * 96 + 4096) * 8, st);
   rc = conv_plan_bind(plan, x16, w_dev, b_dev, y, ws);
   // back-to-back launches between ONE event pair (no host sync inside): steady-state time per launch including
   // the inter-kernel gap, excluding host launch latency.  With flush_mb the same loop is timed with the flush
@@ -1737,7 +1710,8 @@ extern "C" int ofs_conv2d_bench(int B, int H, int W, int Cin, int in_cs, int Cou
     }
     if (rc == OFS_OK) rc = check_cuda(cudaStreamSynchronize(st), "conv bench trace sync", __FILE__, __LINE__);
     if (rc == OFS_OK)
-      cudaMemcpy(trace_host, tr, (size_t)plan.grid * (trace_cap >= plan.grid * 64 ? 64 : 32) * 8, cudaMemcpyDeviceToHost);
+      cudaMemcpy(trace_host, tr, ((size_t)plan.grid * (trace_cap >= plan.grid * 64 ? 64 : 32) + (trace_cap >= plan.grid * 64 + 4096 ? 4096 : 0)) * 8,
+                 cudaMemcpyDeviceToHost);
   }
   if (grid_out) *grid_out = plan.grid;
   cleanup();

@@ -272,22 +272,84 @@ struct ofs_net {
   // host-API staging
   float *st_feats = nullptr, *st_frames = nullptr, *st_out = nullptr;
   size_t st_frames_cap = 0;
-  // CUDA graphs of whole stabilize() steps, keyed by the call's pointers and shape (see ofs_net_stabilize)
+  // CUDA graphs of whole stabilize() steps, one per (B, H, W, flow2 wanted, alignment class of out).  The caller's four
+  // pointers are baked into a handful of kernel nodes (pack_act: feats; the warp: frames, out; predict2_gather:
+  // flow2_out); `patches` records where, so a call with other addresses updates those nodes of the instantiated
+  // graph (cudaGraphExecKernelNodeSetParams) instead of re-capturing -- see ofs_net_stabilize.
   struct StepGraph {
-    const float *feats, *frames;
-    float *out, *flow2;
+    const void* baked[4];          // feats, frames, out, flow2 as currently set in `exec`
     int B, H, W;
+    bool out_aligned16;
+    cudaGraph_t graph;             // kept alive: its node handles address the nodes of `exec`
     cudaGraphExec_t exec;
     int launches;
     uint64_t last_use;
+    struct Loc { int arg, off, which; };
+    struct Patch {
+      cudaGraphNode_t node;
+      cudaKernelNodeParams params;                  // kernelParams -> argptr
+      std::vector<std::vector<uint8_t>> argbuf;     // private copy of every argument
+      std::vector<void*> argptr;
+      std::vector<Loc> locs;                        // 8-byte words holding one of the four pointers
+    };
+    std::vector<Patch> patches;
   };
   std::vector<StepGraph> graphs;
   uint64_t graph_clock = 0;
+  uint64_t graph_captures = 0, graph_updates = 0;   // how often a step was captured / re-pointed (tests, diagnostics)
   int use_graphs = 1;
-  unsigned weights_generation = 0;   // bumped by ofs_net_load_weights: captured graphs of dependants are stale
+  unsigned weights_generation = 0;   // bumped by ofs_net_load_weights AND whenever prepare() reallocates the split-K workspace:
+                                     // graphs captured by dependants (clip driver) bake both in and are stale afterwards
 };
 
 namespace {
+
+void drop_graphs(ofs_net* n) {
+  for (auto& g : n->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+  }
+  n->graphs.clear();
+}
+
+// Finds every kernel-node argument word of `graph` that equals one of the call's four pointers.
+int collect_patches(cudaGraph_t graph, const void* const ptrs[4], std::vector<ofs_net::StepGraph::Patch>& out) {
+  size_t nn = 0;
+  OFS_CUDA(cudaGraphGetNodes(graph, nullptr, &nn));
+  std::vector<cudaGraphNode_t> nodes(nn);
+  if (nn) OFS_CUDA(cudaGraphGetNodes(graph, nodes.data(), &nn));
+  for (cudaGraphNode_t node : nodes) {
+    cudaGraphNodeType type;
+    OFS_CUDA(cudaGraphNodeGetType(node, &type));
+    if (type != cudaGraphNodeTypeKernel) continue;
+    ofs_net::StepGraph::Patch pt;
+    pt.node = node;
+    OFS_CUDA(cudaGraphKernelNodeGetParams(node, &pt.params));
+    if (!pt.params.kernelParams) continue;   // (never the case for launches made with an argument array)
+    for (size_t i = 0;; ++i) {
+      size_t off = 0, size = 0;
+      if (cudaFuncGetParamInfo(pt.params.func, i, &off, &size) != cudaSuccess) { cudaGetLastError(); break; }
+      const uint8_t* src = static_cast<const uint8_t*>(pt.params.kernelParams[i]);
+      pt.argbuf.emplace_back(src, src + size);
+      for (size_t o = 0; o + 8 <= size; o += 8) {
+        const void* v;
+        memcpy(&v, src + o, 8);
+        if (!v) continue;
+        for (int w = 0; w < 4; ++w)
+          if (ptrs[w] && v == ptrs[w]) pt.locs.push_back({(int)i, (int)o, w});
+      }
+    }
+    if (pt.locs.empty()) continue;
+    out.push_back(std::move(pt));
+  }
+  for (auto& pt : out) {   // argptr must point into the Patch's final resting place
+    pt.argptr.clear();
+    for (auto& b : pt.argbuf) pt.argptr.push_back(b.data());
+    pt.params.kernelParams = pt.argptr.data();
+    pt.params.extra = nullptr;
+  }
+  return OFS_OK;
+}
 
 int dev_alloc(ofs_net* n, void** p, size_t bytes, bool zero) {
   cudaError_t e = cudaMalloc(p, bytes);
@@ -403,8 +465,8 @@ int prepare(ofs_net* n, int B) {
     n->ws = nullptr;
     n->ws_bytes = 0;
     for (Layer& L : n->layers) L.plans.clear();
-    for (auto& g : n->graphs) cudaGraphExecDestroy(g.exec);   // they hold the old workspace pointer
-    n->graphs.clear();
+    drop_graphs(n);   // they hold the old workspace pointer
+    ++n->weights_generation;   // ... and so do the graphs of dependants (clip driver slots): they compare this counter
     const size_t want = std::max(ws_need, (ws_need / (size_t)B) * (size_t)n->max_batch);
     OFS_CUDA(cudaMalloc((void**)&n->ws, want));
     n->ws_bytes = want;
@@ -683,8 +745,7 @@ int ofs_net_destroy(ofs_net* n) {
     if (n->ev_h2d[i]) cudaEventDestroy(n->ev_h2d[i]);
     if (n->ev_comp[i]) cudaEventDestroy(n->ev_comp[i]);
   }
-  for (auto& g : n->graphs) cudaGraphExecDestroy(g.exec);
-  n->graphs.clear();
+  drop_graphs(n);
   for (void* p : n->allocs) cudaFree(p);
   if (n->ws) cudaFree(n->ws);
   if (n->st_frames) cudaFree(n->st_frames);
@@ -696,11 +757,18 @@ int ofs_net_destroy(ofs_net* n) {
 int ofs_net_load_weights(ofs_net* n, const ofs_named_array* arrays, int count) {
   OFS_REQUIRE(n && arrays && count > 0, "ofs_net_load_weights: null / empty input");
   OFS_CUDA(cudaSetDevice(n->device));
+  n->loaded = false;   // a failed ingest leaves the net unusable rather than half-updated
   std::map<std::string, const ofs_named_array*> by_name;
   for (int i = 0; i < count; ++i) {
     OFS_REQUIRE(arrays[i].name && arrays[i].data, "ofs_net_load_weights: entry %d has a null name / data", i);
     by_name[norm_key(arrays[i].name)] = &arrays[i];
   }
+  // Every variable the reference checkpoint carries for this network (main_dl.py:330 saves ALL 'main_net' variables,
+  // moving statistics included) is REQUIRED: a missing or differently named bias / beta / moving_mean /
+  // moving_variance must not silently load as 0 / 1, and an array nothing consumed (a gamma, a layer of another
+  // model) is reported instead of dropped.
+  std::map<std::string, bool> consumed;
+  for (auto& kv : by_name) consumed[kv.first] = false;
   auto find = [&](const std::string& key, int64_t numel, const float** ptr, bool required) -> int {
     auto it = by_name.find(key);
     if (it == by_name.end()) {
@@ -708,6 +776,7 @@ int ofs_net_load_weights(ofs_net* n, const ofs_named_array* arrays, int count) {
       if (required) { set_error("ofs_net_load_weights: missing array '%s'", key.c_str()); return OFS_EINVAL; }
       return OFS_OK;
     }
+    consumed[key] = true;
     if (it->second->numel != numel) {
       set_error("ofs_net_load_weights: '%s' has %lld elements, expected %lld", key.c_str(), (long long)it->second->numel,
                 (long long)numel);
@@ -723,11 +792,11 @@ int ofs_net_load_weights(ofs_net* n, const ofs_named_array* arrays, int count) {
     const int64_t wn = (int64_t)k * k * cin * cout;
     const float *w = nullptr, *b = nullptr, *beta = nullptr, *mean = nullptr, *var = nullptr;
     int rc = find(L.name + (deconv ? "/W_deconv2d" : "/W_conv2d"), wn, &w, true);
-    if (rc == OFS_OK) rc = find(L.name + (deconv ? "/b_deconv2d" : "/b_conv2d"), cout, &b, false);
+    if (rc == OFS_OK) rc = find(L.name + (deconv ? "/b_deconv2d" : "/b_conv2d"), cout, &b, true);
     if (rc == OFS_OK && !L.bn.empty()) {
-      rc = find(L.bn + "/beta", cout, &beta, false);
-      if (rc == OFS_OK) rc = find(L.bn + "/moving_mean", cout, &mean, false);
-      if (rc == OFS_OK) rc = find(L.bn + "/moving_variance", cout, &var, false);
+      rc = find(L.bn + "/beta", cout, &beta, true);
+      if (rc == OFS_OK) rc = find(L.bn + "/moving_mean", cout, &mean, true);
+      if (rc == OFS_OK) rc = find(L.bn + "/moving_variance", cout, &var, true);
     }
     if (rc != OFS_OK) return rc;
     // fold BN: W' = W r, b' = (b - mu) r + beta, r = 1/sqrt(var + eps)   (double math, fp32 result)
@@ -762,7 +831,7 @@ int ofs_net_load_weights(ofs_net* n, const ofs_named_array* arrays, int count) {
       Head& h = n->heads[L.name == "deconv5" ? 0 : L.name == "deconv4" ? 1 : L.name == "deconv3" ? 2 : 3];
       const float *hw = nullptr, *hb = nullptr;
       rc = find(h.name + "/W_conv2d", (int64_t)9 * h.cin * 2, &hw, true);
-      if (rc == OFS_OK) rc = find(h.name + "/b_conv2d", 2, &hb, false);
+      if (rc == OFS_OK) rc = find(h.name + "/b_conv2d", 2, &hb, true);
       if (rc != OFS_OK) return rc;
       OFS_REQUIRE(h.cin == cin, "internal: head / deconv input mismatch for %s", L.name.c_str());
       h.bias[0] = hb ? hb[0] : 0.f;
@@ -780,10 +849,21 @@ int ofs_net_load_weights(ofs_net* n, const ofs_named_array* arrays, int count) {
   for (int i = 0; i < 4; ++i) {
     const float *w = nullptr, *b = nullptr;
     int rc = find(std::string(ups[i]) + "/W_deconv2d", 64, &w, true);
-    if (rc == OFS_OK) rc = find(std::string(ups[i]) + "/b_deconv2d", 2, &b, false);
+    if (rc == OFS_OK) rc = find(std::string(ups[i]) + "/b_deconv2d", 2, &b, true);
     if (rc != OFS_OK) return rc;
     memcpy(&upw[i * 66], w, 64 * 4);
     if (b) { upw[i * 66 + 64] = b[0]; upw[i * 66 + 65] = b[1]; }
+  }
+  {
+    std::string extra;
+    int n_extra = 0;
+    for (auto& kv : consumed)
+      if (!kv.second) { if (n_extra < 6) extra += (n_extra ? ", " : "") + kv.first; ++n_extra; }
+    if (n_extra) {
+      set_error("ofs_net_load_weights: %d array(s) match no variable of flownetS_pyramid (model.py:786-893 has no gamma, "
+                "no other layers): %s%s", n_extra, extra.c_str(), n_extra > 6 ? ", ..." : "");
+      return OFS_EINVAL;
+    }
   }
   OFS_CUDA(cudaMemcpy(n->upw, upw.data(), upw.size() * 4, cudaMemcpyHostToDevice));
   n->loaded = true;
@@ -791,8 +871,7 @@ int ofs_net_load_weights(ofs_net* n, const ofs_named_array* arrays, int count) {
   n->prepared_B = 0;
   for (Layer& L : n->layers) L.plans.clear();
   OFS_CUDA(cudaDeviceSynchronize());
-  for (auto& g : n->graphs) cudaGraphExecDestroy(g.exec);   // head biases etc. are kernel arguments
-  n->graphs.clear();
+  drop_graphs(n);   // head biases etc. are kernel arguments
   return OFS_OK;
 }
 
@@ -809,11 +888,13 @@ int ofs_net_forward(ofs_net* n, const float* feats, int B, float* f6, float* f5,
   return OFS_OK;
 }
 
-// One step = 30-odd dependent kernels of 3-150 us each: replayed as ONE CUDA graph (kernel nodes joined by
-// programmatic-dependent-launch edges), so neither host launch latency nor inter-kernel drain sits between
-// them.  A graph bakes in its pointers, so graphs are cached per (feats, frames, out, flow2_out, B, H, W);
-// streaming callers cycle through a few staging buffers and hit the cache after the first lap.
-// OFS_GRAPH=0 in the environment (read at ofs_net_create) falls back to plain stream launches.
+// One step = 26 dependent kernels of 3-100 us each: replayed as ONE CUDA graph, so neither host launch latency nor
+// inter-kernel drain sits between them.  A graph bakes in its pointers; the reference's call pattern feeds a NEW numpy
+// array every frame (main_dl.py:568-569) and the Python drop-in allocates a fresh output per call, so the graph is
+// cached per SHAPE and the few kernel-node arguments that hold the caller's pointers are re-pointed in the
+// instantiated graph when the addresses differ from the previous launch (microseconds on the host, nothing on the
+// device) -- one capture per (B, H, W), whatever the addresses.  OFS_GRAPH=0 (read at ofs_net_create) falls back to
+// plain stream launches.
 int ofs_net_stabilize(ofs_net* n, const float* feats, const float* frames, float* out, float* flow2_out, int B, int H,
                       int W, ofs_stream stream) {
   OFS_REQUIRE(n && feats && frames && out, "ofs_net_stabilize: null pointer");
@@ -822,20 +903,36 @@ int ofs_net_stabilize(ofs_net* n, const float* feats, const float* frames, float
   cudaStream_t st = (cudaStream_t)stream;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (n->use_graphs) cudaStreamIsCapturing(st, &cap);
-  if (!n->use_graphs || !n->loaded || cap != cudaStreamCaptureStatusNone) {   // plain path (also when the caller captures)
+  const void* ptrs[4] = {feats, frames, out, flow2_out};
+  bool distinct = true;   // the patch table tells the four pointers apart by value
+  for (int i = 0; i < 4; ++i)
+    for (int j = i + 1; j < 4; ++j)
+      if (ptrs[i] && ptrs[i] == ptrs[j]) distinct = false;
+  if (!n->use_graphs || !n->loaded || cap != cudaStreamCaptureStatusNone || !distinct) {   // plain path (also when the caller captures)
     int rc = forward_impl(n, feats, B, flow2_out, st);
     if (rc != OFS_OK) return rc;
     return flow_resize_warp_impl(frames, n->f2s, out, B, H, W, 382, 510, st, 1);
   }
   OFS_CUDA(cudaSetDevice(n->device));
   ++n->graph_clock;
-  for (auto& g : n->graphs)
-    if (g.feats == feats && g.frames == frames && g.out == out && g.flow2 == flow2_out && g.B == B && g.H == H && g.W == W) {
-      g.last_use = n->graph_clock;
-      OFS_CUDA(cudaGraphLaunch(g.exec, st));
-      count_launch(g.launches);
-      return OFS_OK;
+  const bool aligned = (((uintptr_t)out) % 16) == 0;   // selects the warp kernel variant at capture time
+  for (auto& g : n->graphs) {
+    if (g.B != B || g.H != H || g.W != W || g.out_aligned16 != aligned || (g.baked[3] == nullptr) != (flow2_out == nullptr)) continue;
+    g.last_use = n->graph_clock;
+    bool same = true;
+    for (int w = 0; w < 4; ++w) same = same && g.baked[w] == ptrs[w];
+    if (!same) {
+      for (auto& pt : g.patches) {
+        for (const auto& loc : pt.locs) memcpy(pt.argbuf[loc.arg].data() + loc.off, &ptrs[loc.which], 8);
+        OFS_CUDA(cudaGraphExecKernelNodeSetParams(g.exec, pt.node, &pt.params));
+      }
+      for (int w = 0; w < 4; ++w) g.baked[w] = ptrs[w];
+      ++n->graph_updates;
     }
+    OFS_CUDA(cudaGraphLaunch(g.exec, st));
+    count_launch(g.launches);
+    return OFS_OK;
+  }
   int rc = prepare(n, B);   // plans, TMA descriptors and workspace exist before the capture starts
   if (rc != OFS_OK) return rc;
   const uint64_t l0 = launch_count();
@@ -851,20 +948,33 @@ int ofs_net_stabilize(ofs_net* n, const float* feats, const float* frames, float
   count_launch(-launches);   // captured, not executed
   if (rc != OFS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
   OFS_CUDA(ce);
-  cudaGraphExec_t exec = nullptr;
-  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
-  cudaGraphDestroy(graph);
+  ofs_net::StepGraph sg{};
+  for (int w = 0; w < 4; ++w) sg.baked[w] = ptrs[w];
+  sg.B = B; sg.H = H; sg.W = W; sg.out_aligned16 = aligned; sg.graph = graph; sg.launches = launches; sg.last_use = n->graph_clock;
+  rc = collect_patches(graph, ptrs, sg.patches);
+  if (rc != OFS_OK) { cudaGraphDestroy(graph); return rc; }
+  const cudaError_t ie = cudaGraphInstantiate(&sg.exec, graph, 0);
+  if (ie != cudaSuccess) cudaGraphDestroy(graph);
   OFS_CUDA(ie);
-  if (n->graphs.size() >= 16) {   // evict the least recently used step
+  ++n->graph_captures;
+  if (n->graphs.size() >= 16) {   // evict the least recently used shape
     size_t lru = 0;
     for (size_t i = 1; i < n->graphs.size(); ++i) if (n->graphs[i].last_use < n->graphs[lru].last_use) lru = i;
     cudaGraphExecDestroy(n->graphs[lru].exec);
+    cudaGraphDestroy(n->graphs[lru].graph);
     n->graphs.erase(n->graphs.begin() + lru);
   }
-  n->graphs.push_back({feats, frames, out, flow2_out, B, H, W, exec, launches, n->graph_clock});
-  OFS_CUDA(cudaGraphLaunch(exec, st));
+  n->graphs.push_back(std::move(sg));
+  // (the moved Patch vectors keep their heap buffers, but argptr / kernelParams were taken before the move of the
+  // enclosing vector only -- element addresses are unchanged by moving a std::vector, so they stay valid)
+  OFS_CUDA(cudaGraphLaunch(n->graphs.back().exec, st));
   count_launch(launches);
   return OFS_OK;
+}
+
+long long ofs_net_graph_stats(const ofs_net* n, int what) {
+  if (!n) return -1;
+  return what == 0 ? (long long)n->graph_captures : what == 1 ? (long long)n->graph_updates : (long long)n->graphs.size();
 }
 
 int ofs_net_stabilize_host(ofs_net* n, const float* feats_host, const float* frames_host, float* out_host, int B,

@@ -33,8 +33,11 @@ class FlowNetSPyramid:
     def __init__(self, device=None, max_batch=8, precision="bf16"):
         if not torch.cuda.is_available():
             raise RuntimeError("FlowNetSPyramid needs a CUDA device (sm_100a); there is no CPU fallback")
-        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else
-                                   (device.index if isinstance(device, torch.device) else int(device)))
+        if isinstance(device, str):
+            device = torch.device(device)
+        if isinstance(device, torch.device):
+            device = device.index                       # torch.device("cuda") has index None = the current device
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
         self.max_batch = int(max_batch)
         self.precision = precision
         self._lib = _lib.load()
@@ -42,14 +45,25 @@ class FlowNetSPyramid:
         prec = {"bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16}[precision]
         _lib.check(self._lib.ofs_net_create(C.byref(self._h), self.device.index, self.max_batch, prec))
         self.loaded = False
+        self._weights = None     # the mapping last assigned (by reference): lets get_net() rebuild a scope at a larger batch
+        self._users = 0          # ClipStabilizers holding the raw ofs_net* of this handle (see retain / release)
+
+    def retain(self):
+        self._users += 1
+
+    def release(self):
+        self._users = max(0, self._users - 1)
 
     def close(self):
+        if getattr(self, "_users", 0):
+            raise RuntimeError(f"FlowNetSPyramid.close: {self._users} ClipStabilizer(s) still hold this net; close them first")
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.ofs_net_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
         try:
+            self._users = 0
             self.close()
         except Exception:
             pass
@@ -64,8 +78,10 @@ class FlowNetSPyramid:
             arr[i].name = str(name).encode()
             arr[i].data = a.ctypes.data_as(C.c_void_p)
             arr[i].numel = a.size
+        self.loaded = False
         _lib.check(self._lib.ofs_net_load_weights(self._h, arr, len(weights)))
         self.loaded = True
+        self._weights = weights
 
     def load_npz(self, path):
         with np.load(path, allow_pickle=False) as z:
@@ -170,6 +186,10 @@ class FlowNetSPyramid:
                                                       int(batch), H, W, int(iters), C.byref(ms), C.byref(macs), C.byref(nl)))
         return float(ms.value), float(macs.value), int(nl.value)
 
+    def graph_stats(self):
+        """(captures, re-pointings, cached graphs) of the stabilize() step-graph cache."""
+        return tuple(int(self._lib.ofs_net_graph_stats(self._h, k)) for k in range(3))
+
     @property
     def launches_per_forward(self):
         return int(self._lib.ofs_net_launches_per_forward(self._h))
@@ -189,16 +209,27 @@ _NETS = {}
 
 
 def _scope_key(scope, device):
-    return (scope, torch.device(device).index if device is not None else torch.cuda.current_device())
+    idx = None
+    if device is not None:
+        idx = device if isinstance(device, int) else torch.device(device).index
+    return (scope, torch.cuda.current_device() if idx is None else int(idx))   # "cuda" (index None) = the current device
 
 
 def get_net(scope="flownetS", device=None, max_batch=8, precision="bf16"):
+    """The net of a scope (created on first use).  Asking for a larger max_batch or another precision REBUILDS the
+    scope's net: the weights assigned to the old one are re-assigned to the new one, and the old handle is destroyed
+    -- which is refused while a ClipStabilizer still holds it (its C side keeps the raw ofs_net*)."""
     key = _scope_key(scope, device)
     net = _NETS.get(key)
     if net is None or net.max_batch < max_batch or net.precision != precision:
         old = net
+        if old is not None and old._users:
+            raise RuntimeError(f"scope '{scope}': cannot rebuild the net (max_batch {old.max_batch} -> {max_batch}, precision "
+                               f"{old.precision} -> {precision}) while {old._users} ClipStabilizer(s) use it; close them first")
         net = FlowNetSPyramid(device=key[1], max_batch=max(max_batch, old.max_batch if old else 1), precision=precision)
         if old is not None:
+            if old.loaded and old._weights is not None:
+                net.assign_weights(old._weights)
             old.close()
         _NETS[key] = net
     return net

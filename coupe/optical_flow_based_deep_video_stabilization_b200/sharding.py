@@ -20,10 +20,12 @@ def shard_range(n_items: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_output(local: torch.Tensor, n_items: int, group=None):
-    """All-gathers the per-rank output frames [n_local, H, W, C] of a split clip into [n_items, H, W, C] in pair
-    order on every rank (NCCL for CUDA tensors, gloo for CPU tensors).  Ranks may own different counts
-    (shard_range); shards are padded to the largest count for the collective and trimmed afterwards."""
+def gather_output(local: torch.Tensor, n_items: int, group=None, dst=None):
+    """Collects the per-rank output frames [n_local, H, W, C] of a split clip (or of a set of clips laid end to end) into
+    [n_items, H, W, C] in pair order: on every rank (`dst=None`, all_gather) or on rank `dst` only (the other ranks
+    return None).  NCCL for CUDA tensors, gloo for CPU tensors; any dtype -- send the np.uint8 frames the video writer
+    consumes (2.76 MB per 720p frame) rather than float32 (11.06 MB).  Ranks may own different counts (shard_range);
+    shards are padded to the largest count for the collective and trimmed afterwards."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()):
@@ -36,10 +38,23 @@ def gather_output(local: torch.Tensor, n_items: int, group=None):
     lo, hi = counts[rank]
     if local.shape[0] != hi - lo:
         raise ValueError(f"rank {rank} owns pairs [{lo},{hi}) but holds {local.shape[0]} frames")
+    if dst is not None and not (0 <= dst < world):
+        raise ValueError(f"dst {dst} outside [0, {world})")
     nmax = max(h - l for l, h in counts)
     padded = local
     if local.shape[0] < nmax:
         padded = torch.cat([local, local.new_zeros((nmax - local.shape[0],) + tuple(local.shape[1:]))], 0)
-    parts = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(parts, padded.contiguous(), group=group)
-    return torch.cat([p[: h - l] for p, (l, h) in zip(parts, counts)], 0)
+    padded = padded.contiguous()
+    even = all(h - l == nmax for l, h in counts)
+    if dst is None:
+        out = local.new_empty((world * nmax,) + tuple(local.shape[1:]))
+        dist.all_gather_into_tensor(out, padded, group=group)      # one flat receive buffer: no per-rank list, no concat
+    else:
+        out = local.new_empty((world * nmax,) + tuple(local.shape[1:])) if rank == dst else None
+        parts = list(out.view((world, nmax) + tuple(local.shape[1:])).unbind(0)) if rank == dst else None
+        dist.gather(padded, parts, dst=dst, group=group)
+        if rank != dst:
+            return None
+    if even:
+        return out
+    return torch.cat([out[r * nmax: r * nmax + (h - l)] for r, (l, h) in enumerate(counts)], 0)

@@ -3,7 +3,7 @@
     vec2mtrx(config, p)                     warp.py:25-43
     transformImage(config, image, pMtrx)    warp.py:46-86
     transformCropImage(config, image, pMtrx) warp.py:89-129
-    fit / compose / inverse                 warp.py:6-23 (host-side numpy helpers)
+    fit / compose / inverse                 warp.py:6-23 (host-side helpers, written independently: QR least squares)
 
 ``config`` is any object with the attributes the reference reads: warpType, warpApprox, batch_size,
 refMtrx (3x3) / refMtrx_b, height, width, W, dataH, dataW.  Device work runs through libofstab.so.
@@ -18,24 +18,28 @@ from .ops import _cuda_f32
 
 
 def fit(Xsrc, Xdst):
-    """Least-squares affine fit between two point sets (warp.py:6-15); host numpy."""
-    import scipy.linalg
-
-    ptsN = len(Xsrc)
-    X, Y, U, V = Xsrc[:, 0], Xsrc[:, 1], Xdst[:, 0], Xdst[:, 1]
-    O, I = np.zeros([ptsN]), np.ones([ptsN])
-    A = np.concatenate((np.stack([X, Y, I, O, O, O], axis=1), np.stack([O, O, O, X, Y, I], axis=1)), axis=0)
-    b = np.concatenate((U, V), axis=0)
-    p1, p2, p3, p4, p5, p6 = scipy.linalg.lstsq(A, b)[0].squeeze()
-    return np.array([[p1, p2, p3], [p4, p5, p6], [0, 0, 1]], dtype=np.float32)
+    """Affine map (3x3, last row 0 0 1) taking the points Xsrc [N,2] onto Xdst [N,2] in the least-squares sense
+    (same contract as the reference helper warp.py:6-15).  The two output coordinates are independent problems over
+    the same design matrix [x y 1], so one QR-based solve with a two-column right-hand side covers both."""
+    src = np.asarray(Xsrc, dtype=np.float64).reshape(-1, 2)
+    dst = np.asarray(Xdst, dtype=np.float64).reshape(-1, 2)
+    if src.shape != dst.shape or src.shape[0] < 3:
+        raise ValueError("fit: need two [N,2] point sets with N >= 3")
+    design = np.column_stack([src, np.ones(len(src))])          # [N,3]
+    rows, *_ = np.linalg.lstsq(design, dst, rcond=None)         # [3,2]: column j holds the row of output coordinate j
+    M = np.eye(3, dtype=np.float32)
+    M[:2, :] = rows.T
+    return M
 
 
 def compose(config, p, dp):
-    return p + dp
+    """Additive composition of warp parameters (first-order in the Lie algebra), as the reference does (warp.py:17-19)."""
+    return torch.add(p, dp) if isinstance(p, torch.Tensor) else np.add(p, dp)
 
 
 def inverse(config, p):
-    return -p
+    """Parameter vector of the inverse warp under the same first-order approximation (warp.py:21-23)."""
+    return torch.neg(p) if isinstance(p, torch.Tensor) else np.negative(p)
 
 
 def _ref_tensor(ref, device):

@@ -156,6 +156,10 @@ int ofs_net_time_kernels(ofs_net* net, int which, const float* frames, float* ou
                          float* ms_per_set, double* macs_per_set, int* launches_per_set);
 /* per-forward kernel launches (constant for a given B) */
 int ofs_net_launches_per_forward(const ofs_net* net);
+/* Diagnostics of the step-graph cache of ofs_net_stabilize: what = 0 -> graphs captured so far, 1 -> launches that
+ * re-pointed a cached graph at new feats / frames / out / flow2 addresses, 2 -> graphs currently cached.  The
+ * reference feeds a new array every frame (main_dl.py:568-569); one capture per (B, H, W) must serve them all. */
+long long ofs_net_graph_stats(const ofs_net* net, int what);
 
 /* ------------------------------------------------------------------------------------------
  * Clip driver (SURVEY 8(f) "next" row 1): the per-frame loop of evaluate_originalSize(), main_dl.py:535-630, with its

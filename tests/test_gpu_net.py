@@ -363,3 +363,62 @@ def test_npz_checkpoint_ingest(ofs, cuda_dev, tmp_path):
     for k in want:
         assert torch.equal(got[k], want[k]), k
     direct.close()
+
+
+def test_checkpoint_ingest_is_strict(ofs, cuda_dev):
+    """A checkpoint that lacks a BatchNorm statistic / a bias, or carries an array no variable of flownetS_pyramid consumes
+    (model.py:786-893 has gamma_init=None), is refused with the offending key named -- never loaded with defaults."""
+    from coupe.optical_flow_based_deep_video_stabilization_b200._lib import OfstabError
+
+    w = F.make_weights(0, "calibrated", head_scale=0.02)
+    net = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=1)
+    for missing in ("3_1/moving_variance", "deconv4_bn/beta", "4/b_conv2d", "predict5/b_conv2d", "upsample4_3/b_deconv2d"):
+        bad = {k: v for k, v in w.items() if k != missing}
+        with pytest.raises(OfstabError, match=missing):
+            net.assign_weights(bad)
+        with pytest.raises(OfstabError):                 # a failed ingest leaves the net unloaded
+            net.forward(F.make_feats(5, 1).to(cuda_dev))
+    extra = dict(w)
+    extra["main_net/flownetS/2/gamma:0"] = np.ones(128, np.float32)
+    with pytest.raises(OfstabError, match="2/gamma"):
+        net.assign_weights(extra)
+    net.assign_weights(w)                                 # and a complete one still loads afterwards
+    assert net.forward(F.make_feats(5, 1).to(cuda_dev))["flow"].shape == (1, 382, 510, 2)
+    net.close()
+
+
+def test_stabilize_replays_one_graph_for_fresh_tensors(ofs, cuda_dev):
+    """The reference feeds a NEW array every frame (main_dl.py:568-569) and the drop-in allocates a fresh output per
+    call: 100 calls with freshly allocated tensors must be served by ONE captured graph (re-pointed, not
+    re-captured), and give exactly what the plain stream-launched path gives."""
+    w = F.make_weights(0, "calibrated", head_scale=0.02)
+    net = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=2)
+    net.assign_weights(w)
+    g = torch.Generator().manual_seed(11)
+    H, W = 96, 128
+    base_feats = F.make_feats(9, 2)
+    base_frames = torch.rand((2, H, W, 3), generator=g)
+    keep, outs = [], []
+    for i in range(100):
+        feats = (base_feats if i % 2 == 0 else base_feats.flip(0)).to(cuda_dev).clone()
+        frames = (base_frames if i % 2 == 0 else base_frames.flip(0)).to(cuda_dev).clone()
+        keep.append((feats, frames))                                   # keep them alive: every call sees new addresses
+        if i % 3 == 0:
+            keep.append(torch.empty(1 + 7 * i, device=cuda_dev))       # shift the allocator
+        outs.append(net.stabilize(feats, frames))
+    torch.cuda.synchronize()
+    captures, updates, cached = net.graph_stats()
+    assert captures == 1 and cached == 1, (captures, updates, cached)
+    assert updates >= 90, updates
+    assert len({o.data_ptr() for o in outs}) > 50
+    for i in (2, 3, 98, 99):
+        assert torch.equal(outs[i], outs[i % 2]), i                    # same inputs -> same bits, whatever the addresses
+    assert torch.equal(outs[1], outs[0].flip(0))                       # batch order follows the inputs
+    # with the flow output as well (another cached graph), and against the un-graphed path
+    out_a, flow_a = net.stabilize(keep[0][0], keep[0][1], return_flow=True)
+    out_b, flow_b = net.stabilize(keep[0][0].clone(), keep[0][1].clone(), return_flow=True)
+    assert torch.equal(out_a, outs[0]) and torch.equal(out_b, outs[0]) and torch.equal(flow_a, flow_b)
+    assert net.graph_stats()[0] == 2
+    ref = net.forward(keep[0][0])["predict_flow2"]
+    assert torch.equal(flow_a, ref)
+    net.close()

@@ -47,6 +47,13 @@ def _worker(rank, world, port, n_items, q):
         local = torch.arange(lo, hi, dtype=torch.float32).view(-1, 1, 1, 1).expand(hi - lo, 6, 8, 3).contiguous()
         full = gather_output(local, n_items)
         ok = full.shape == (n_items, 6, 8, 3) and bool((full[:, 0, 0, 0] == torch.arange(n_items, dtype=torch.float32)).all())
+        # the uint8 payload the video writer consumes (4x fewer bytes than float32), gathered to rank 0 only
+        u8 = gather_output(local.to(torch.uint8), n_items, dst=0)
+        if rank == 0:
+            ok = ok and u8.dtype == torch.uint8 and u8.shape == (n_items, 6, 8, 3) and bool(
+                (u8[:, 5, 7, 2] == torch.arange(n_items, dtype=torch.uint8)).all())
+        else:
+            ok = ok and u8 is None
         # max-over-ranks timing reduction used by bench.py
         t = torch.tensor([float(rank + 1)])
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
