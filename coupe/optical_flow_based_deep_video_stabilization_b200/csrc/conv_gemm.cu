@@ -726,6 +726,95 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
     }
   }
 
+  if constexpr (BLOCK_N >= 64 && !kKC && !kPair && kT == 1 && kHead == 0 && kG == 1) {
+    if (p.fused_reduce) {   // kernel-uniform.  This CTA ran exactly one (tile, split) unit: `unit`.
+      const int tiles_per_split = p.tiles_mp * p.tiles_n * p.phases;
+      const int tile_id = unit % tiles_per_split;
+      const int ks = unit / tiles_per_split;
+      const int n_t = tile_id % p.tiles_n;
+      const int m_t = (tile_id / p.tiles_n) % p.tiles_mp;
+      unsigned* arrivals = p.sk_counters + tile_id;
+      unsigned* claims = p.sk_counters + tiles_per_split + tile_id;
+      unsigned* departures = p.sk_counters + 2 * tiles_per_split + tile_id;
+      volatile int& s_all = *(reinterpret_cast<volatile int*>(bars) + 62);   // last word of the 256-byte barrier block (unused)
+      // the store warp left its loop only after cp.async.bulk.wait_group 0: this CTA's partial is in global memory
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async;" ::: "memory");   // async-proxy (TMA) writes before the generic-proxy release below
+        __threadfence();
+        unsigned seen = atomicAdd(arrivals, 1u) + 1u;
+        // Siblings normally arrive within a microsecond of each other (same work, started together).  The wait is
+        // BOUNDED: when another stream's kernel holds SMs a sibling may not even be resident yet, and two such grids
+        // waiting for each other's unscheduled CTAs would deadlock.  A CTA that gives up simply leaves; the rows are
+        // claimed dynamically below, so whoever is present once the last partial has arrived -- the last arriver at
+        // least -- reduces them all.
+        const long long t0 = clock64();
+        while (seen < (unsigned)p.ksplit && clock64() - t0 < 40000) {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrivals) : "memory");
+        }
+        s_all = seen >= (unsigned)p.ksplit;
+        if (s_all) __threadfence();
+      }
+      __syncthreads();
+      if (trace && threadIdx.x == 64) trace[6] = clock64();
+      const int nsplit = p.ksplit;
+      if (s_all) {
+        const int n0 = n_t * BLOCK_N;
+        const float* __restrict__ ws = reinterpret_cast<const float*>(p.out);
+        const size_t sstride = (size_t)p.ws_split_stride / 4;
+        const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0);
+        // warps claim 4 rows at a time; lane l sums float4 columns l, l + 32, ... of a row over the splits in split order
+        // (bias first): the order, and therefore the bits, of splitk_reduce_kernel, whoever does the row
+        for (;;) {
+          unsigned r0 = 0;
+          if (lane == 0) r0 = atomicAdd(claims, 4u);
+          r0 = __shfl_sync(0xffffffffu, r0, 0);
+          if (r0 >= (unsigned)kBlockM) break;
+          for (int row = (int)r0; row < (int)r0 + 4; ++row) {
+            const int ty = row >> p.tileW_log2;
+            const int gy = (m_t / p.tiles_x) * p.tile_rows + ty;
+            const int gx = ((m_t % p.tiles_x) << p.tileW_log2) + (row & (tileW - 1));
+            const bool valid = (m_t < p.tiles_m) && (ty < p.tile_rows) && (gy < p.rows_total) && !(dbg & 8);
+            if (!valid) continue;   // warp-uniform
+            const int b = gy / p.Hg;
+            const int y = gy - b * p.Hg;
+            const size_t pix = ((size_t)b * p.out_H + (size_t)y) * p.out_W + (size_t)gx;
+            const float4* src = reinterpret_cast<const float4*>(ws + pix * p.n_pad + n0);
+            uint2* o = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.final_out) + pix * p.out_cstride + p.out_coff + n0);
+#pragma unroll
+            for (int h = 0; h < (BLOCK_N / 4 + 31) / 32; ++h) {
+              const int q = lane + 32 * h;
+              if (q >= BLOCK_N / 4) break;
+              float4 part[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if (k < nsplit) part[k] = __ldcg(src + (size_t)k * sstride + q);   // L2 (the partials were written by other SMs)
+              float4 sum = __ldg(bias4 + q);
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if (k < nsplit) { sum.x += part[k].x; sum.y += part[k].y; sum.z += part[k].z; sum.w += part[k].w; }
+              if (p.lrelu) {
+                sum.x = fmaxf(sum.x, 0.1f * sum.x); sum.y = fmaxf(sum.y, 0.1f * sum.y);
+                sum.z = fmaxf(sum.z, 0.1f * sum.z); sum.w = fmaxf(sum.w, 0.1f * sum.w);
+              }
+              o[q] = make_uint2(pack16(sum.x, sum.y, p.is_bf16), pack16(sum.z, sum.w, p.is_bf16));
+            }
+          }
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned left = atomicAdd(departures, 1u);
+        if (left == (unsigned)nsplit - 1u) {   // the last one out: everybody's rows are stored; reset for the next launch
+          *arrivals = 0u;
+          *claims = 0u;
+          *departures = 0u;
+          __threadfence();
+        }
+      }
+      if (trace && threadIdx.x == 64) trace[10] = clock64();
+    }
+  }
   if constexpr (kKC) {
     ptx::cluster_sync();   // every split's partial tile is parked and visible cluster-wide
     if (trace && threadIdx.x == 64) trace[6] = clock64();
@@ -1323,6 +1412,10 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
       default: plan.smem = GemmCfg<256, false>::kSmem; break;
     }
   }
+  // split-K reduced inside the launch: every (tile, split) unit must be one resident CTA
+  plan.fused_reduce_ok = p.ksplit > 1 && p.ksplit <= 8 && !p.kcluster && p.tma_store == 2 && d.cta_group == 1 && !p.slab && !d.head &&
+                         d.kgroup == 1 && plan.grid == total_tiles;
+  plan.n_counters = plan.fused_reduce_ok ? 3 * p.tiles_mp * p.tiles_n * p.phases : 0;
   plan.macs = deconv ? (double)d.B * d.H * d.W * 16.0 * d.cin * d.cout
                      : (double)d.B * Hg * Wg * (double)d.k * d.k * d.cin * d.cout;
   return OFS_OK;
@@ -1388,7 +1481,7 @@ void conv_pack_weights(const ConvPlan& plan, const float* w, const float* bias, 
 }
 
 int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const float* bias_dev, void* out,
-                   float* workspace, float* head_out) {
+                   float* workspace, float* head_out, unsigned* counters) {
   ConvGemmParams& p = plan.p;
   const ConvDesc& d = plan.d;
   OFS_REQUIRE(act_in && w_dev && bias_dev && out, "conv bind: null pointer");
@@ -1404,6 +1497,16 @@ int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const 
     p.out = out;
   }
   p.bias = bias_dev;
+  p.final_out = out;
+  {
+    // OFF unless OFS_FUSED_REDUCE=1: measured on B200 (batch 8, graph replay) the in-kernel reduction costs MORE than the
+    // separate launch it saves -- conv5 19.0 vs 15.2 us, conv6_1 19.5 vs 14.8 us: every CTA first waits for the full
+    // completion of its TMA stores, a fence, the slowest sibling, and then only 6-8 CTAs x 7 warps share a tile's rows,
+    // where splitk_reduce_kernel spreads all tiles over all SMs at once.  Kept as a tested (bit-identical) option.
+    const char* e = getenv("OFS_FUSED_REDUCE");
+    p.fused_reduce = (plan.fused_reduce_ok && counters && e && e[0] == '1') ? 1 : 0;
+    p.sk_counters = p.fused_reduce ? counters : nullptr;
+  }
   p.head_out = reinterpret_cast<float2*>(head_out);
   OFS_REQUIRE(!d.head || head_out, "conv bind: the fused head needs its output buffer");
   const cuuint32_t tileW = 1u << p.tileW_log2;
@@ -1484,7 +1587,7 @@ int conv_launch(const ConvPlan& plan, cudaStream_t st) {
     }
   }
   if (rc != OFS_OK) return rc;
-  return plan.p.ksplit > 1 ? launch_reduce(plan, st) : OFS_OK;
+  return (plan.p.ksplit > 1 && !plan.p.fused_reduce) ? launch_reduce(plan, st) : OFS_OK;
 }
 
 int launch_pack_act(const float* in, void* out, size_t npix, int cin, int cs, int is_bf16, cudaStream_t st) {
@@ -1562,9 +1665,11 @@ extern "C" int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const flo
   conv_pack_weights(plan, wsrc, b_host, wp, bp);
   void *x16 = nullptr, *w_dev = nullptr, *y16 = nullptr;
   float *b_dev = nullptr, *ws = nullptr;
+  unsigned* cnt = nullptr;
   const size_t npix = (size_t)B * H * W;
   const size_t npix_out = (size_t)B * plan.p.out_H * plan.p.out_W;
   auto cleanup = [&]() {
+    if (cnt) cudaFree(cnt);
     if (x16) cudaFree(x16);
     if (w_dev) cudaFree(w_dev);
     if (b_dev) cudaFree(b_dev);
@@ -1576,10 +1681,14 @@ extern "C" int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const flo
   if (rc == OFS_OK) rc = check_cuda(cudaMalloc((void**)&b_dev, bp.size() * 4), "cudaMalloc b", __FILE__, __LINE__);
   if (rc == OFS_OK && via16) rc = check_cuda(cudaMalloc(&y16, npix_out * cout8 * 2), "cudaMalloc y16", __FILE__, __LINE__);
   if (rc == OFS_OK && plan.ws_bytes) rc = check_cuda(cudaMalloc((void**)&ws, plan.ws_bytes), "cudaMalloc ws", __FILE__, __LINE__);
+  if (rc == OFS_OK && plan.n_counters) {
+    rc = check_cuda(cudaMalloc((void**)&cnt, (size_t)plan.n_counters * 4), "cudaMalloc counters", __FILE__, __LINE__);
+    if (rc == OFS_OK) rc = check_cuda(cudaMemsetAsync(cnt, 0, (size_t)plan.n_counters * 4, st), "zero counters", __FILE__, __LINE__);
+  }
   if (rc == OFS_OK) rc = check_cuda(cudaMemcpyAsync(w_dev, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice, st), "H2D w", __FILE__, __LINE__);
   if (rc == OFS_OK) rc = check_cuda(cudaMemcpyAsync(b_dev, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice, st), "H2D b", __FILE__, __LINE__);
   if (rc == OFS_OK) rc = launch_pack_act(x, x16, npix, cin_logical, d.in_cs, is_bf16, st);
-  if (rc == OFS_OK) rc = conv_plan_bind(plan, x16, w_dev, b_dev, via16 ? y16 : (void*)y, ws);
+  if (rc == OFS_OK) rc = conv_plan_bind(plan, x16, w_dev, b_dev, via16 ? y16 : (void*)y, ws, nullptr, cnt);
   if (rc == OFS_OK) rc = conv_launch(plan, st);
   if (rc == OFS_OK && via16) rc = launch_unpack_act(y16, y, npix_out, cout8, 0, Cout, is_bf16, st);
   if (rc == OFS_OK) rc = check_cuda(cudaStreamSynchronize(st), "conv2d sync", __FILE__, __LINE__);
@@ -1643,9 +1752,10 @@ extern "C" int ofs_conv2d_bench(int B, int H, int W, int Cin, int in_cs, int Cou
   void *x16 = nullptr, *w_dev = nullptr, *y = nullptr, *fl = nullptr;
   float *b_dev = nullptr, *ws = nullptr;
   long long* tr = nullptr;
+  unsigned* cnt = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   auto cleanup = [&]() {
-    for (void* q : {x16, w_dev, y, fl, (void*)b_dev, (void*)ws, (void*)tr}) if (q) cudaFree(q);
+    for (void* q : {x16, w_dev, y, fl, (void*)b_dev, (void*)ws, (void*)tr, (void*)cnt}) if (q) cudaFree(q);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
   };
@@ -1655,14 +1765,16 @@ extern "C" int ofs_conv2d_bench(int B, int H, int W, int Cin, int in_cs, int Cou
             cudaMalloc((void**)&b_dev, (size_t)plan.p.n_pad * 4) == cudaSuccess &&
             (plan.ws_bytes == 0 || cudaMalloc((void**)&ws, plan.ws_bytes) == cudaSuccess) &&
             (flush_bytes == 0 || cudaMalloc(&fl, flush_bytes) == cudaSuccess) &&
+            cudaMalloc((void**)&cnt, (size_t)(plan.n_counters + 1) * 4) == cudaSuccess &&
             cudaMalloc((void**)&tr, ((size_t)plan.grid * 96 + 4096) * 8) == cudaSuccess &&
             cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess;
   if (!ok) { cleanup(); set_error("ofs_conv2d_bench: allocation failed"); return OFS_ENOMEM; }
   fill16_kernel<<<sm_count() * 4, 256, 0, st>>>((uint16_t*)x16, npix * in_cs, 1u, 1, 1.0f);
   fill16_kernel<<<sm_count() * 4, 256, 0, st>>>((uint16_t*)w_dev, w_elems, 2u, 1, 0.05f);
   cudaMemsetAsync(b_dev, 0, (size_t)plan.p.n_pad * 4, st);
+  cudaMemsetAsync(cnt, 0, (size_t)(plan.n_counters + 1) * 4, st);
   cudaMemsetAsync(tr, 0, ((size_t)plan.grid * 96 + 4096) * 8, st);
-  rc = conv_plan_bind(plan, x16, w_dev, b_dev, y, ws);
+  rc = conv_plan_bind(plan, x16, w_dev, b_dev, y, ws, nullptr, cnt);
   // back-to-back launches between ONE event pair (no host sync inside): steady-state time per launch including
   // the inter-kernel gap, excluding host launch latency.  With flush_mb the same loop is timed with the flush
   // kernel alone and subtracted.

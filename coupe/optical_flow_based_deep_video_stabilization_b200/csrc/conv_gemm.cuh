@@ -40,6 +40,13 @@ struct ConvGemmParams {
   int kb_per_split;    // K blocks per split
   int kcluster;        // 1: the ksplit CTAs of a tile form one cluster and reduce their partials through DSMEM
   long long ws_split_stride;  // workspace elements between two splits = out pixels * n_pad
+  // split-K reduced INSIDE the GEMM launch (no splitk_reduce_kernel): every (tile, split) unit is one resident CTA; after
+  // its fp32 partial has landed in the workspace a CTA bumps the tile's arrival counter, waits until all ksplit partials
+  // of the tile are there, and sums ITS share of the tile's rows over the splits in split order (bias first: the very
+  // order, and therefore the very bits, of splitk_reduce_kernel) into the final 16-bit slice.
+  int fused_reduce;           // 1: on (needs total units <= grid so that all of them are co-resident)
+  unsigned* sk_counters;      // [3 * tiles]: arrivals, row claims, departures (the last CTA to leave zeroes all three: self-cleaning)
+  void* final_out;            // the 16-bit destination of the fused reduction
   int ntaps, nchunks;  // K_total = ntaps * nchunks * 64
   int n_pad;           // padded output channels per phase
   int w_rows_phase;    // packed weight rows per phase = n_pad (+ 16 with a fused head)
@@ -108,6 +115,8 @@ struct ConvPlan {
   std::vector<int> wt_ky, wt_kx;
   double macs = 0;           // literal MACs of the layer (roofline numerator)
   size_t ws_bytes = 0;       // split-K workspace this plan needs (0 when ksplit == 1)
+  bool fused_reduce_ok = false;  // geometry allows the in-kernel reduction (one resident CTA per (tile, split))
+  int n_counters = 0;        // counters the fused reduction needs (3 per tile)
   // split-K reduction (filled by bind)
   void* final_out = nullptr;
   const float* bias_dev = nullptr;
@@ -121,8 +130,9 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d);
 void conv_pack_weights(const ConvPlan& plan, const float* w_tf, const float* bias, std::vector<uint16_t>& w_packed,
                        std::vector<float>& b_padded, const float* head_w = nullptr /* [3,3,cin,2] when plan.d.head */);
 // Binds device pointers and encodes the TMA descriptors.
+// counters: zero-initialised device array of plan.n_counters unsigned (null: split-K falls back to splitk_reduce_kernel)
 int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_packed_dev, const float* bias_dev, void* out,
-                   float* workspace = nullptr, float* head_out = nullptr);
+                   float* workspace = nullptr, float* head_out = nullptr, unsigned* counters = nullptr);
 int conv_launch(const ConvPlan& plan, cudaStream_t st);
 
 // 5-D TMA view of the input activation (dims in elements, strides in bytes; dim 0 is contiguous)

@@ -239,9 +239,11 @@ struct Layer {
   std::map<int, ConvPlan> plans;  // bound plans per batch size (TMA descriptors are per batch)
   void* w_dev = nullptr;
   float* b_dev = nullptr;
+  unsigned* counters = nullptr;   // arrival / departure counters of the in-kernel split-K reduction (kCounters, zeroed once)
   size_t w_elems = 0;
   int n_pad = 0;
 };
+constexpr int kCounters = 2048;
 
 struct ActInfo { void* ptr; int H, W, cs, coff, C; };
 
@@ -474,7 +476,8 @@ int prepare(ofs_net* n, int B) {
   for (Layer& L : n->layers) {
     float* head_out = nullptr;
     if (L.d.head) head_out = n->hpart[L.name == "deconv5" ? 6 : L.name == "deconv4" ? 5 : L.name == "deconv3" ? 4 : 3];
-    int rc = conv_plan_bind(L.plan, L.in, L.w_dev, L.b_dev, L.out, n->ws, head_out);
+    int rc = conv_plan_bind(L.plan, L.in, L.w_dev, L.b_dev, L.out, n->ws, head_out,
+                            L.plan.n_counters <= kCounters ? L.counters : nullptr);
     if (rc != OFS_OK) return rc;
     L.plans[B] = L.plan;
   }
@@ -719,6 +722,7 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
     L.n_pad = L.plan.p.n_pad;
     rc = dev_alloc(n, &L.w_dev, L.w_elems * 2, true);
     if (rc == OFS_OK) rc = dev_alloc(n, (void**)&L.b_dev, (size_t)L.n_pad * 4, true);
+    if (rc == OFS_OK && L.ksplit > 1) rc = dev_alloc(n, (void**)&L.counters, (size_t)kCounters * 4, true);
     if (rc != OFS_OK) { ofs_net_destroy(n); return rc; }
   }
   n->acts = {
@@ -1133,7 +1137,7 @@ int ofs_net_time_kernels(ofs_net* n, int which, const float* frames, float* out,
 int ofs_net_launches_per_forward(const ofs_net* n) {
   if (!n) return 0;
   int k = 1 + (int)n->layers.size() + 4 + 1;  // pack + GEMMs (heads ride in the deconvs) + pyramid steps + gather
-  for (const Layer& L : n->layers) k += L.plan.p.ksplit > 1 ? 1 : 0;  // split-K reductions (after prepare())
+  for (const Layer& L : n->layers) k += (L.plan.p.ksplit > 1 && !L.plan.p.fused_reduce) ? 1 : 0;  // separate split-K reductions (after prepare())
   return k;
 }
 

@@ -179,6 +179,24 @@ def test_cluster_splitk_bit_identical_to_workspace_splitk(ofs, cuda_dev, B, H, W
     assert torch.equal(a, c)
 
 
+@pytest.mark.parametrize("B,H,W,cin,cout,ks", [(8, 12, 16, 512, 512, 6), (8, 6, 8, 1024, 1024, 8), (8, 24, 32, 512, 512, 6),
+                                               (3, 6, 8, 256, 256, 5), (1, 6, 8, 512, 1024, 8)])
+def test_fused_splitk_reduce_bit_identical_to_reduce_kernel(ofs, cuda_dev, monkeypatch, B, H, W, cin, cout, ks):
+    """Split-K reduced inside the GEMM launch (arrival counters + dynamically claimed rows) sums bias + the partials in
+    split order exactly as splitk_reduce_kernel does: same bits, launch after launch (the counters clean themselves)."""
+    gen = torch.Generator().manual_seed(9 + ks)
+    x = _round(torch.rand((B, H, W, cin), generator=gen), "bf16").to(cuda_dev)
+    w = _round(torch.randn((3, 3, cin, cout), generator=gen) * (1.0 / np.sqrt(9 * cin)), "bf16")
+    b = torch.randn(cout, generator=gen) * 0.1
+    stride = 2 if H == 24 else 1
+    monkeypatch.setenv("OFS_FUSED_REDUCE", "0")
+    a = ofs.conv2d_nhwc(x, w, b, stride=stride, lrelu=True, precision="bf16", block_n=256, ksplit=ks, cta_group=1).cpu()
+    monkeypatch.setenv("OFS_FUSED_REDUCE", "1")
+    for _ in range(3):
+        c = ofs.conv2d_nhwc(x, w, b, stride=stride, lrelu=True, precision="bf16", block_n=256, ksplit=ks, cta_group=1).cpu()
+        assert torch.equal(a, c)
+
+
 @pytest.fixture(scope="module")
 def net_case(ofs, cuda_dev):
     w = F.make_weights(0, "calibrated", head_scale=0.02)
@@ -286,11 +304,18 @@ def test_reference_signature_and_stabilize(ofs, cuda_dev, net_case):
     two_step = ofs.tf_warp(frames.to(cuda_dev), outflow, H, W)
     fused, f2 = net.stabilize(x.to(cuda_dev), frames.to(cuda_dev), return_flow=True)
     torch.testing.assert_close(f2, out["predict_flow2"], rtol=0, atol=0)
-    assert float(((fused - two_step).abs() > 1e-5).float().mean()) < 1e-4
+    from parity import warp_max_abs
+
+    ref_flow = S.flow_resize(out["predict_flow2"].cpu(), H, W)                       # the oracle's resized flow of the GPU's flow2
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    src_x, src_y = xs + ref_flow[..., 0], ys + ref_flow[..., 1]
+    warp_max_abs(fused.cpu(), two_step.cpu(), 1e-5, src_x, src_y, H, W, what="fused vs two-step")
     host = net.stabilize_host(x.pin_memory(), frames.pin_memory())
     torch.testing.assert_close(host, fused.cpu(), rtol=0, atol=0)
     ref = S.flow_resize_warp(frames, out["predict_flow2"].cpu(), H, W)               # oracle warp on the GPU's flow
-    assert float(((fused.cpu() - ref).abs() > 1e-3).float().mean()) < 1e-4
+    # max-abs <= 1e-3 everywhere except within 2e-3 px of a tf_warp discontinuity (parity.py)
+    _, n_disc = warp_max_abs(fused.cpu(), ref, 1e-3, src_x, src_y, H, W, what="stabilize vs oracle warp")
+    assert n_disc <= 4, n_disc
 
 
 def test_missing_weight_is_an_error(ofs, cuda_dev):
@@ -343,7 +368,13 @@ def test_full_size_step_properties(ofs, cuda_dev, B, H, W):
     e = F.epe(f2[:1].cpu(), ref["predict_flow2"])
     assert e <= 2e-2, e                                                              # north-star tolerance, px at bf16
     ref_img = S.flow_resize_warp(frames[:1], f2[:1].cpu(), H, W)
-    assert float(((out[:1].cpu() - ref_img).abs() > 1e-3).float().mean()) < 1e-4    # 1e-3 on [0,1] pixels
+    from parity import warp_max_abs
+
+    ref_flow = S.flow_resize(f2[:1].cpu(), H, W)
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    _, n_disc = warp_max_abs(out[:1].cpu(), ref_img, 1e-3, xs + ref_flow[..., 0], ys + ref_flow[..., 1], H, W,
+                             what="720p stabilize vs oracle warp")                  # 1e-3 on [0,1] pixels (parity.py)
+    assert n_disc <= 8, n_disc
     net.close()
 
 

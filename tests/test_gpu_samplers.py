@@ -5,6 +5,7 @@ import pytest
 import torch
 
 from oracle import samplers as S
+from parity import strict_max_abs, warp_max_abs
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
@@ -109,16 +110,19 @@ def test_flow_resize_and_fused_warp(ofs, cuda_dev, golden, H, W):
     got_flow = ofs.flow_resize(f2.to(cuda_dev), H, W).cpu()
     assert float((got_flow - ref_flow).abs().max()) < 1e-4
     ref = S.flow_resize_warp(img, f2, H, W)
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    src_x, src_y = xs + ref_flow[..., 0], ys + ref_flow[..., 1]                   # the oracle's source coordinates
     for variant in (0, 1, 2, 3):
         ofs.set_warp_variant(variant)
         got = ofs.flow_resize_warp(img.to(cuda_dev), f2.to(cuda_dev)).cpu()
-        # a 1-ulp flow difference can flip a truncation; bound the count, not just the max
-        bad = ((got - ref).abs() > TOL).float().mean()
-        assert float(bad) < 1e-4, float(bad)
+        # strict max-abs everywhere except within 2e-3 px of a tf_warp discontinuity (source x = -1 / W-1, y = -1 / H-1),
+        # where a 1-ulp difference of the resized flow flips the output between a pixel value and 0
+        m, n_disc = warp_max_abs(got, ref, TOL, src_x, src_y, H, W, what=f"fused warp variant {variant} {H}x{W}")
+        assert n_disc <= 4, n_disc
     ofs.set_warp_variant(3)
-    # two-step (resize then warp) == fused
+    # two-step (resize then warp) == fused, same criterion
     two = ofs.tf_warp(img.to(cuda_dev), ofs.flow_resize(f2.to(cuda_dev), H, W), H, W).cpu()
-    assert float(((two - got).abs() > 1e-5).float().mean()) < 1e-4
+    warp_max_abs(two, got, 1e-5, src_x, src_y, H, W, what="two-step vs fused")
 
 
 def test_flow_glue_constant_golden(ofs, cuda_dev, golden):
@@ -155,8 +159,7 @@ def test_affine_vs_oracle(ofs, cuda_dev, name, B, H, W, C, oh, ow):
     th = torch.tensor([THETAS6[name]] * B, dtype=torch.float32) + torch.randn((B, 6), generator=gen) * 0.01
     ref = S.affine_transform(img, th, (oh, ow))
     got = ofs.AffineTransformer((oh, ow)).transform(img.to(cuda_dev), th.to(cuda_dev)).cpu()
-    bad = ((got - ref).abs() > TOL).float().mean()
-    assert float(bad) < 2e-4, float(bad)
+    strict_max_abs(got, ref, TOL, f"AffineTransformer {name} {B}x{H}x{W}x{C} -> {oh}x{ow}")   # bilinear_interp is continuous
     got2 = ofs.transformer(img.to(cuda_dev), th.to(cuda_dev), (oh, ow)).cpu()
     assert torch.equal(got, got2)
 
@@ -168,8 +171,7 @@ def test_projective_vs_oracle(ofs, cuda_dev, B, H, W, C, oh, ow):
     th = torch.tensor([[1, 0, 0, 0, 1, 0, 0, 0]] * B, dtype=torch.float32) + torch.randn((B, 8), generator=gen) * 0.05
     ref = S.projective_transform(img, th, (oh, ow))
     got = ofs.ProjectiveTransformer((oh, ow)).transform(img.to(cuda_dev), th.to(cuda_dev)).cpu()
-    bad = ((got - ref).abs() > TOL).float().mean()
-    assert float(bad) < 2e-4, float(bad)
+    strict_max_abs(got, ref, TOL, f"ProjectiveTransformer {B}x{H}x{W}x{C} -> {oh}x{ow}")
 
 
 class Cfg:
@@ -201,11 +203,11 @@ def test_lie_warp_golden_and_oracle(ofs, cuda_dev, golden):
     assert float((pm.cpu() - pm_ref).abs().max()) < 1e-6
     got = ofs.transformImage(cfg, im.to(cuda_dev), pm).cpu()
     ref = S.transform_image(im, pm_ref, ref_m, H, W)
-    assert float(((got - ref).abs() > TOL).float().mean()) < 2e-4
+    strict_max_abs(got, ref, TOL, "transformImage, random homographies")
     cfg.height, cfg.width, cfg.W, cfg.dataH, cfg.dataW, cfg.refMtrx_b = 32, 48, 48, H, W, ref_m
     got = ofs.transformCropImage(cfg, im.to(cuda_dev), pm).cpu()
     ref = S.transform_image(im, pm_ref, ref_m, 32, 48, H, W)
-    assert float(((got - ref).abs() > TOL).float().mean()) < 2e-4
+    strict_max_abs(got, ref, TOL, "transformCropImage, random homographies")
 
 
 def _cfg(warp_type, approx, batch):

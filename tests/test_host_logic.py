@@ -315,3 +315,27 @@ def test_package_and_oracle_generators_agree():
             assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k
     assert torch.equal(P.make_feats(5, 1), O.make_feats(5, 1))
     assert torch.equal(P.make_feats(5, 1, "smooth"), O.make_feats(5, 1, "smooth"))
+
+
+def test_warp_fit_compose_inverse_helpers():
+    """warp.fit / compose / inverse (reference warp.py:6-23): least-squares affine fit recovers an exact affine map and
+    averages noise; compose / inverse are the first-order parameter algebra."""
+    import numpy as np
+
+    from coupe.optical_flow_based_deep_video_stabilization_b200 import warp
+
+    rng = np.random.default_rng(0)
+    A = np.array([[1.1, -0.2, 3.0], [0.3, 0.9, -1.5]])
+    src = rng.uniform(-5, 5, (40, 2))
+    dst = src @ A[:, :2].T + A[:, 2]
+    M = warp.fit(src, dst)
+    assert M.shape == (3, 3) and M.dtype == np.float32
+    np.testing.assert_allclose(M[:2], A, atol=1e-5)
+    np.testing.assert_allclose(M[2], [0, 0, 1], atol=0)
+    noisy = warp.fit(src, dst + rng.normal(0, 0.01, dst.shape))
+    np.testing.assert_allclose(noisy[:2], A, atol=2e-2)
+    with pytest.raises(ValueError):
+        warp.fit(src[:2], dst[:2])
+    p, dp = np.arange(8.0), np.ones(8)
+    np.testing.assert_array_equal(warp.compose(None, p, dp), p + dp)
+    np.testing.assert_array_equal(warp.inverse(None, p), -p)
