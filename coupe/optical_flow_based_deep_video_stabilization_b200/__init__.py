@@ -13,6 +13,8 @@ from .clip import ClipStabilizer                                                
 from .driver import stabilize_video                                                            # noqa: F401
 from .model import (FlowNetSPyramid, assign_weights, flownetS_pyramid, get_net,                 # noqa: F401
                     load_and_assign_npz_dict)
+from .modes import (FixedSizeStabilizer, HomographyStabilizer, cv_resize_linear, flow_box_blur_ema,  # noqa: F401
+                    flow_resize_ex, medfilt, tf1_resize_images, warp_perspective_u8)
 from .ops import (conv2d_nhwc, flow_resize, flow_resize_warp, get_pixel_value, set_warp_variant,  # noqa: F401
                   tf_warp)
 from .sharding import gather_output, shard_range                                                # noqa: F401
@@ -25,5 +27,7 @@ __all__ = [
     "AffineTransformer", "ProjectiveTransformer", "transformer",
     "vec2mtrx", "transformImage", "transformCropImage", "fit", "compose", "inverse",
     "shard_range", "gather_output", "ClipStabilizer", "stabilize_video",
+    "HomographyStabilizer", "FixedSizeStabilizer", "warp_perspective_u8", "flow_resize_ex", "tf1_resize_images",
+    "cv_resize_linear", "flow_box_blur_ema", "medfilt",
     "OfstabError", "lib_path", "load_library",
 ]

@@ -39,6 +39,12 @@ PROTOTYPES = {
     "ofs_set_warp_variant": (_i, [_i]),
     "ofs_flow_resize": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "ofs_flow_resize_warp": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "ofs_flow_resize_ex": (_i, [_p, _p, _i, _i, _i, _i, _i, _f, _p]),
+    "ofs_warp_perspective_u8": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "ofs_tf1_resize_bilinear": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "ofs_cv_resize_linear_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _f, _p]),
+    "ofs_flow_box_blur_ema": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p]),
+    "ofs_medfilt_nd3": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "ofs_grid_sample_affine": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "ofs_grid_sample_projective": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "ofs_vec2mtrx": (_i, [_p, _p, _i, _i, _i, _p]),

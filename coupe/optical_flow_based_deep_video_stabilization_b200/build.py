@@ -20,7 +20,7 @@ REPO = os.path.abspath(os.path.join(HERE, "..", ".."))
 LIB_PATH = os.path.join(HERE, "libofstab.so")
 STAMP = os.path.join(HERE, ".libofstab.stamp")
 
-SOURCES = ["ofs_common.cu", "samplers.cu", "conv_gemm.cu", "flownet.cu", "clip.cu"]
+SOURCES = ["ofs_common.cu", "samplers.cu", "conv_gemm.cu", "flownet.cu", "clip.cu", "modes.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

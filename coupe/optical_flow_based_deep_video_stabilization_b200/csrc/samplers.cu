@@ -59,6 +59,8 @@ struct FlowResize {
   int fh, fw, H, W;
   float hs, ws;  // fh/H, fw/W in fp32 like CalculateResizeScale
   int prescaled; // flow2 already holds (flow2 * 384.0) / fh (the network writes that copy itself)
+  float pre_mul = 384.0f;   // the factor in front of "/ fh": 384.0 for predict_flow2 (main_dl.py:497), out_h for the
+                            // predict_flow3-based flow of the homography mode (main_dl.py:681: flow3 * out_h / 48)
   __device__ __forceinline__ float2 at(int b, int oy, int ox) const {
     const float iy = (float)oy * hs;
     const float ix = (float)ox * ws;
@@ -70,11 +72,11 @@ struct FlowResize {
     float2 bl = __ldg(base + (size_t)y1 * fw + x0), br = __ldg(base + (size_t)y1 * fw + x1);
     if (!prescaled) {
       const float fhf = (float)fh;
-      // outputs['predict_flow2'] * 384.0 / 382  (multiply, then true division)
-      tl.x = __fdiv_rn(tl.x * 384.0f, fhf); tl.y = __fdiv_rn(tl.y * 384.0f, fhf);
-      tr.x = __fdiv_rn(tr.x * 384.0f, fhf); tr.y = __fdiv_rn(tr.y * 384.0f, fhf);
-      bl.x = __fdiv_rn(bl.x * 384.0f, fhf); bl.y = __fdiv_rn(bl.y * 384.0f, fhf);
-      br.x = __fdiv_rn(br.x * 384.0f, fhf); br.y = __fdiv_rn(br.y * 384.0f, fhf);
+      // outputs['predict_flow2'] * 384.0 / 382, outputs['predict_flow3'] * out_h / 48  (multiply, then true division)
+      tl.x = __fdiv_rn(tl.x * pre_mul, fhf); tl.y = __fdiv_rn(tl.y * pre_mul, fhf);
+      tr.x = __fdiv_rn(tr.x * pre_mul, fhf); tr.y = __fdiv_rn(tr.y * pre_mul, fhf);
+      bl.x = __fdiv_rn(bl.x * pre_mul, fhf); bl.y = __fdiv_rn(bl.y * pre_mul, fhf);
+      br.x = __fdiv_rn(br.x * pre_mul, fhf); br.y = __fdiv_rn(br.y * pre_mul, fhf);
     }
     float2 top, bot, v;
     top.x = tl.x + (tr.x - tl.x) * xl; top.y = tl.y + (tr.y - tl.y) * xl;
@@ -974,11 +976,11 @@ int tf_warp_impl(const float* img, const float* flow, float* out, int B, int H, 
   return OFS_OK;
 }
 
-int flow_resize_impl(const float* flow2, float* out, int B, int fh, int fw, int H, int W, cudaStream_t st) {
+int flow_resize_impl(const float* flow2, float* out, int B, int fh, int fw, int H, int W, cudaStream_t st, float pre_mul = 384.0f) {
   OFS_REQUIRE(B >= 0 && fh > 0 && fw > 0 && H > 0 && W > 0, "ofs_flow_resize: bad shape");
   if (B == 0) return OFS_OK;
   OFS_REQUIRE(flow2 && out, "ofs_flow_resize: null pointer");
-  FlowResize fr{flow2, fh, fw, H, W, (float)fh / (float)H, (float)fw / (float)W, 0};
+  FlowResize fr{flow2, fh, fw, H, W, (float)fh / (float)H, (float)fw / (float)W, 0, pre_mul};
   flow_resize_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, st>>>(fr, out, B);
   OFS_LAUNCH_CHECK();
   return OFS_OK;
@@ -1062,6 +1064,10 @@ int ofs_tf_warp(const float* img, const float* flow, float* out, int B, int H, i
 
 int ofs_flow_resize(const float* flow2, float* out, int B, int fh, int fw, int H, int W, ofs_stream stream) {
   return ofs::flow_resize_impl(flow2, out, B, fh, fw, H, W, (cudaStream_t)stream);
+}
+
+int ofs_flow_resize_ex(const float* flow, float* out, int B, int fh, int fw, int H, int W, float pre_mul, ofs_stream stream) {
+  return ofs::flow_resize_impl(flow, out, B, fh, fw, H, W, (cudaStream_t)stream, pre_mul);
 }
 
 int ofs_flow_resize_warp(const float* img, const float* flow2, float* out, int B, int H, int W, int fh, int fw,

@@ -74,6 +74,10 @@ int ofs_set_warp_variant(int variant);
  * out [B,H,W,2] dev. */
 int ofs_flow_resize(const float* flow2, float* out, int B, int fh, int fw, int H, int W, ofs_stream stream);
 
+/* The same glue with the factor in front of "/ fh" spelled out: pre_mul = 384 gives ofs_flow_resize; the homography mode
+ * (evaluate_originalSize_homo, main_dl.py:681-682) resizes predict_flow3 * out_h / 48, i.e. flow [B,48,64,2], pre_mul = H. */
+int ofs_flow_resize_ex(const float* flow, float* out, int B, int fh, int fw, int H, int W, float pre_mul, ofs_stream stream);
+
 /* Fused main_dl.py:497-514: ofs_flow_resize + ofs_tf_warp without materialising the HxW flow.
  *   img [B,H,W,3] dev, flow2 [B,fh,fw,2] dev, out [B,H,W,3] dev. */
 int ofs_flow_resize_warp(const float* img, const float* flow2, float* out, int B, int H, int W, int fh, int fw,
@@ -160,6 +164,32 @@ int ofs_net_launches_per_forward(const ofs_net* net);
  * re-pointed a cached graph at new feats / frames / out / flow2 addresses, 2 -> graphs currently cached.  The
  * reference feeds a new array every frame (main_dl.py:568-569); one capture per (B, H, W) must serve them all. */
 long long ofs_net_graph_stats(const ofs_net* net, int what);
+
+/* ------------------------------------------------------------------------------------------
+ * The reference's other test modes around the same network.  All pointers are device pointers
+ * unless named *_host; every op runs on `stream`.
+ *
+ * cv2.warpPerspective(frame, h, (out_w, out_h)) of evaluate_originalSize_homo (main_dl.py:743): uint8 [B,src_h,src_w,3]
+ * -> uint8 [B,out_h,out_w,3], default flags (INTER_LINEAR, h is the FORWARD map and is inverted first), BORDER_CONSTANT 0.
+ * OpenCV's fixed-point arithmetic restated exactly: byte-identical to cv2 (tests/test_gpu_modes.py).
+ * h_host: B row-major 3x3 double matrices on the HOST (what cv2.findHomography returns). */
+int ofs_warp_perspective_u8(const uint8_t* src, const double* h_host, uint8_t* dst, int B, int src_h, int src_w, int out_h,
+                            int out_w, ofs_stream stream);
+/* tf.image.resize_images(x[..., c0:c0+C], [out_h, out_w]) of evaluate() (main_dl.py:806: the current frame, channels 24:27
+ * of the network input, to 382x510): TF-1.10 legacy bilinear.  in [B,H,W,in_channels] float32 -> out [B,out_h,out_w,C]. */
+int ofs_tf1_resize_bilinear(const float* in, float* out, int B, int H, int W, int in_channels, int c0, int C, int out_h,
+                            int out_w, ofs_stream stream);
+/* cv2.resize(float32 image, (out_w, out_h)), INTER_LINEAR, times post_mul (main_dl.py:862: cv2.resize(warped, (512, 384)) * 255). */
+int ofs_cv_resize_linear_f32(const float* in, float* out, int B, int H, int W, int C, int out_h, int out_w, float post_mul,
+                             ofs_stream stream);
+/* evaluate_blurNma (main_flownetS_pyramid.py:634-641): k x k mean filter with zero padding of both flow planes (conv2d with
+ * the constant 1/(k*k), SAME) and the mix a * smooth + b * prev (0.9 / 0.1).  prev may be NULL (out = smooth).
+ * flow, prev, out, scratch: [B,H,W,2] float32, all distinct. */
+int ofs_flow_box_blur_ema(const float* flow, const float* prev, float* out, float* scratch, int B, int H, int W, int k, float a,
+                          float b, ofs_stream stream);
+/* scipy.signal.medfilt(vol, k) of evaluate_medianNma (main_flownetS_pyramid.py:809) for a 3-d array [H,W,C] and a scalar
+ * kernel size k: the window is k x k x k -- it spans the channel axis too -- zero padded; odd k <= 7. */
+int ofs_medfilt_nd3(const float* in, float* out, int H, int W, int C, int k, ofs_stream stream);
 
 /* ------------------------------------------------------------------------------------------
  * Clip driver (SURVEY 8(f) "next" row 1): the per-frame loop of evaluate_originalSize(), main_dl.py:535-630, with its

@@ -43,7 +43,10 @@ def bilinear_tab():
             w = [np.float32(c1[i][k1] * c1[j][k2]) for k1 in range(2) for k2 in range(2)]
             iw = [_sat_short(np.float32(v) * np.float32(INTER_REMAP_COEF_SCALE)) for v in w]
             diff = sum(iw) - INTER_REMAP_COEF_SCALE
-            if diff != 0:       # the largest weight absorbs a deficit, the smallest a surplus
+            # (32768 * (a/32) * (b/32) = 32 a b is an exact integer for every fraction, so the four weights always sum to
+            # 32768 and only the fraction (0, 0) ever meets the int16 saturation: 32768 -> 32767, deficit 1.  Whether the
+            # deficit is put back or not, (w * p + 2^14) >> 15 == p for every byte p when the other weights are 0.)
+            if diff != 0:
                 k = int(np.argmax(iw)) if diff < 0 else int(np.argmin(iw))
                 iw[k] -= diff
             tab[i, j] = iw
@@ -152,9 +155,9 @@ def cv_resize_f32(img, dsize):
         idx = np.empty(dn, np.int64)
         a = np.empty((dn, 2), np.float32)
         for d in range(dn):
-            f = np.float32((d + 0.5) * scale - 0.5)
-            s = int(np.floor(f))
-            f = np.float32(f - np.float32(s))
+            fd = (d + 0.5) * scale - 0.5                           # double: cv2 4.13's results need the FRACTION taken in
+            s = int(np.floor(fd))                                  # double and only then rounded to float32 (checked
+            f = np.float32(fd - s)                                 # against cv2.resize in tests/test_oracle_cv.py)
             if s < 0:
                 f, s = np.float32(0), 0
             if s + 1 >= sn:                                        # the second tap would be outside: clamp, weight 0
