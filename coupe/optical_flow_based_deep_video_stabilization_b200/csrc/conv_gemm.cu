@@ -210,7 +210,7 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
   static_assert(!kKC || (!kPair && kT == 1 && kHead == 0 && kG == 1 && BLOCK_N == 256), "cluster split-K: plain 1-CTA 256-column tiles");
   static_assert(!kKC || Cfg::kStages * Cfg::kStageBytes >= kBlockM * BLOCK_N * 4, "cluster split-K parks the fp32 tile in the stage buffers");
   static_assert(kG == 1 || kT == 1, "chunk groups and slab groups are exclusive");
-  static_assert(kHead == 0 || (!kPair && kT == 1 && BLOCK_N >= 64), "fused head: 1-CTA tiles of 64+ columns");
+  static_assert(kHead == 0 || (kT == 1 && BLOCK_N >= 64), "fused head: plain tiles of 64+ columns (1 CTA or a CTA pair)");
   constexpr int kNB = Cfg::kNB;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -314,8 +314,11 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
       const int ks = rest2 / p.phases;
       const int gy0 = (m_t / p.tiles_x) * p.tile_rows;
       const int ox0 = (m_t % p.tiles_x) << p.tileW_log2;
+      // CTA pair: each CTA loads the half of the tile's B rows its tensor core serves to both -- BLOCK_N / 2 rows, or
+      // kNB / 2 on the last N tile of a fused-head kernel (the 16 head rows follow the phase's n_pad weight rows)
+      const int pair_rows = (kHead && n_t == p.tiles_n - 1) ? kNB / 2 : BLOCK_N / 2;
       const int w_row = half >= 0 ? half * (BLOCK_N / 2) + (kPair ? (int)rank * (BLOCK_N / 4) : 0)
-                                  : ph * p.w_rows_phase + n_t * BLOCK_N + (kPair ? (int)rank * (BLOCK_N / 2) : 0);
+                                  : ph * p.w_rows_phase + n_t * BLOCK_N + (kPair ? (int)rank * pair_rows : 0);
       const CUtensorMap* tmap_w = (kTail && half >= 0) ? &p.tmap_w_half : &p.tmap_w;
       const uint32_t b_tx_t = (kTail && half >= 0) ? b_tx / 2 : b_tx;
       const int b0 = gy0 / p.Hg;
@@ -897,6 +900,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
   conv_gemm_body<BLOCK_N, true, 1, 0, 1, false, kInstr>(p);
 }
+// transposed conv with fused head on CTA pairs (256 input pixels per tile, the B rows split over the pair)
+template <int BLOCK_N, bool kInstr>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    conv_gemm2h_kernel(const __grid_constant__ ConvGemmParams p) {
+  conv_gemm_body<BLOCK_N, true, 1, 16, 1, false, kInstr>(p);
+}
 // chunk groups: two 64-channel K blocks per stage (narrow-N layers: half the handshakes), with / without fused head
 template <int BLOCK_N, int kHead, bool kInstr>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemmg_kernel(const __grid_constant__ ConvGemmParams p) {
@@ -907,6 +916,362 @@ template <int BLOCK_N, int kT, bool kInstr>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     conv_gemm2s_kernel(const __grid_constant__ ConvGemmParams p) {
   conv_gemm_body<BLOCK_N, true, kT, 0, 1, false, kInstr>(p);
+}
+
+// ================================================================================================
+// Phase-STACKED k4-s2 transposed conv (cout = 64) with the level's 3x3 flow head -- deconv2 / predict3 (model.py:873-878).
+//
+// The four sub-pixel phases of the transposed conv read 16 (tap, phase) combinations of only 9 distinct input taps
+// (centre: all 4 phases, edges: 2, corners: 1), and the head reads all 9.  The per-phase form above fetches the A tile
+// of a tap once PER PHASE (16 fetches per 64-channel chunk, each feeding an 80-column MMA); these layers are bound by
+// L2 -> shared-memory delivery (profiles/r02_tuning.md), and the A tile is 60 % of every stage.  Here ONE tile
+// accumulates all four phases side by side in TMEM,
+//     columns  h(16) | ph0(64) | ph1(64) | h'(16) | ph3(64) | ph2(64) | h''(16)   = 304,
+// each of the 9 taps is fetched ONCE per chunk, and is multiplied by the weights of exactly the phases that use it: a
+// tap's B block is a run of rows in that column order, its MMAs target the matching column range (N = 144 / 160 / 80).
+// The phase order 0,1,3,2 makes every edge tap's phase pair adjacent except (ph0, ph2), which takes two MMAs; the head
+// is carried three times (h, h', h'': every tap must find a head copy next to its columns; each tap's head weights are
+// real in exactly ONE copy and zero rows elsewhere), and the epilogue writes the copies as three of the four "phase
+// shares" pyr_kernel sums.  The centre tap comes first and its two MMAs cover all 304 columns, so only they start with
+// accumulate = 0.  A (16 KB per item) and B (<= 20 KB per entry) run through two independent rings.
+// TMEM holds ONE accumulator stage (304 of 512 columns): the next tile's MMAs wait for the epilogue's drain while the
+// producer already refills both rings.
+constexpr int kStkTaps = 9;
+// tap t -> input offset (dy, dx); entry e of tap t -> {accumulator column, MMA N, first packed weight row}
+__host__ __device__ constexpr int stk_dy(int t) { return (t == 1 || t == 5 || t == 6) ? -1 : (t == 2 || t == 7 || t == 8) ? 1 : 0; }
+__host__ __device__ constexpr int stk_dx(int t) { return (t == 4 || t == 5 || t == 8) ? -1 : (t == 3 || t == 6 || t == 7) ? 1 : 0; }
+__host__ __device__ constexpr int stk_ne(int t) { return (t == 0 || t == 4) ? 2 : 1; }
+__host__ __device__ constexpr int stk_n(int t, int e) { return t == 0 ? (e == 0 ? 144 : 160) : t <= 3 ? 144 : 80; }
+__host__ __device__ constexpr int stk_col(int t, int e) {
+  return t == 0 ? (e == 0 ? 0 : 144) : t == 1 ? 0 : t == 2 ? 160 : t == 3 ? 80 : t == 4 ? (e == 0 ? 0 : 224) : t == 5 ? 0 : t == 6 ? 80 : t == 7 ? 144 : 224;
+}
+__host__ __device__ constexpr int stk_row(int t, int e) {
+  return t == 0 ? (e == 0 ? 0 : 144) : t == 1 ? 304 : t == 2 ? 448 : t == 3 ? 592 : t == 4 ? (e == 0 ? 736 : 816) : t == 5 ? 896 : t == 6 ? 976 : t == 7 ? 1056 : 1136;
+}
+constexpr int kStkRows = 1216;                              // packed weight rows (per K column)
+// accumulator columns: h 0 | ph0 16 | ph1 80 | h' 144 | ph3 160 | ph2 224 | h'' 288
+__host__ __device__ constexpr int stk_phase_col(int ph) { return ph == 0 ? 16 : ph == 1 ? 80 : ph == 2 ? 224 : 160; }
+__host__ __device__ constexpr int stk_head_col(int i) { return i == 0 ? 0 : i == 1 ? 144 : 288; }
+static_assert(stk_row(8, 0) + stk_n(8, 0) == kStkRows, "stacked deconv: row table");
+
+template <bool kPair>
+struct StackCfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBSlot = (160 / (kPair ? 2 : 1)) * kBlockK * 2;    // widest entry; a multiple of 1024
+  static constexpr int kSA = kPair ? 6 : 4;
+  static constexpr int kSB = kPair ? 9 : 6;
+  static constexpr int kStgBytes = kBlockM * 128;
+  static constexpr int kStgTotal = 2 * kStgBytes;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kTmemCols = 512;
+  static constexpr size_t kSmem = (size_t)kSA * kABytes + (size_t)kSB * kBSlot + kStgTotal + kBarBytes + 1024;
+  static_assert(kSmem <= 227 * 1024, "stacked deconv: shared memory budget");
+};
+
+template <bool kPair>
+__device__ __forceinline__ void deconv_stack_body(const ConvGemmParams& p) {
+  using Cfg = StackCfg<kPair>;
+  constexpr int SA = Cfg::kSA, SB = Cfg::kSB;
+  constexpr int kCG = kPair ? 2 : 1;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  const uint32_t b_base = smem_base + (uint32_t)SA * Cfg::kABytes;
+  const uint32_t stg0 = b_base + (uint32_t)SB * Cfg::kBSlot;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)SA * Cfg::kABytes + (size_t)SB * Cfg::kBSlot + Cfg::kStgTotal);
+  const uint32_t bar0 = stg0 + Cfg::kStgTotal;
+  const uint32_t fullA0 = bar0, emptyA0 = fullA0 + 8 * SA, fullB0 = emptyA0 + 8 * SA, emptyB0 = fullB0 + 8 * SB;
+  const uint32_t tfull0 = emptyB0 + 8 * SB, tempty0 = tfull0 + 8, sfull0 = tfull0 + 16, sempty0 = tfull0 + 32;
+  constexpr int kNBars = 2 * SA + 2 * SB + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNBars);
+  static_assert((kNBars + 1) * 8 <= Cfg::kBarBytes, "barrier block");
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = kPair ? (uint32_t)cooperative_groups::this_cluster().block_rank() : 0u;
+  const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nunits = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&p.tmap_a);
+    ptx::prefetch_tensormap(&p.tmap_w);
+    ptx::prefetch_tensormap(&p.tmap_w_half);
+    for (int i = 0; i < 4; ++i) ptx::prefetch_tensormap(&p.tmap_o[i]);
+    for (int i = 0; i < 2 * SA + 2 * SB; ++i) ptx::mbar_init(&bars[i], 1);
+    ptx::mbar_init(&bars[2 * SA + 2 * SB], 1);                   // tfull
+    ptx::mbar_init(&bars[2 * SA + 2 * SB + 1], kPair ? 8 : 4);   // tempty: one arrive per epilogue warp (of both CTAs)
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bars[2 * SA + 2 * SB + 2 + i], 4);         // sfull
+      ptx::mbar_init(&bars[2 * SA + 2 * SB + 4 + i], 1);         // sempty
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    if constexpr (kPair) { ptx::tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols); ptx::tmem_relinquish_2sm(); }
+    else { ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols); ptx::tmem_relinquish(); }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if constexpr (kPair) ptx::cluster_sync();
+  ptx::tc_fence_after();
+  pdl_wait();
+
+  const int nchunks = p.nchunks;
+  const int tileW = 1 << p.tileW_log2;
+  const int total_tiles = p.tiles_mp;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    const bool leader = ptx::elect_one();
+    const uint32_t fullA_t = kPair ? __shfl_sync(0xffffffffu, ptx::mapa_u32(fullA0, 0), 0) : fullA0;
+    const uint32_t fullB_t = kPair ? __shfl_sync(0xffffffffu, ptx::mapa_u32(fullB0, 0), 0) : fullB0;
+    const uint32_t a_tx = (uint32_t)kCG * (uint32_t)p.a_bytes;
+    const int piece_bytes = p.piece_rows * tileW * kBlockK * 2;
+    const int npieces = p.npieces;
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0;
+    for (int tile = unit; tile < total_tiles; tile += nunits) {
+      const int m_t = kPair ? tile * 2 + (int)rank : tile;
+      const int gy0 = (m_t / p.tiles_x) * p.tile_rows;
+      const int ox0 = (m_t % p.tiles_x) << p.tileW_log2;
+      const int b0 = gy0 / p.Hg;
+      const int y0 = gy0 - b0 * p.Hg;
+#pragma unroll
+      for (int t = 0; t < kStkTaps; ++t) {
+        const int x = ox0 + stk_dx(t);
+        const int yy = y0 + stk_dy(t);
+        const int ylim = p.Hg + stk_dy(t);
+        for (int ch = 0; ch < nchunks; ++ch) {
+          const int c = ch * kBlockK;
+          // ---- A item: the tap's 128 input pixels x 64 channels
+          lean::wait(emptyA0 + 8u * (uint32_t)sa, pha ^ 1);
+          if (leader) {
+            if (!kPair || rank == 0) lean::expect_tx(fullA0 + 8u * (uint32_t)sa, a_tx);
+            const uint32_t dst0 = smem_base + (uint32_t)sa * Cfg::kABytes;
+            if (npieces == 1) {
+              lean::tma5d<kPair>(dst0, &p.tmap_a, fullA_t + 8u * (uint32_t)sa, c, x, 0, yy, b0);
+            } else {
+              int b = b0, y = yy;
+              uint32_t dst = dst0;
+              for (int pc = 0; pc < npieces; ++pc) {
+                lean::tma5d<kPair>(dst, &p.tmap_a, fullA_t + 8u * (uint32_t)sa, c, x, 0, y, b);
+                dst += piece_bytes;
+                y += p.piece_rows;
+                if (y >= ylim) { y -= p.Hg; ++b; }
+              }
+            }
+          }
+          if (++sa == SA) { sa = 0; pha ^= 1; }
+          // ---- B items: one per entry (run of weight rows in accumulator-column order)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            if (e < stk_ne(t)) {
+              const int n_e = stk_n(t, e);
+              const int row = stk_row(t, e) + (int)rank * (n_e / kCG);
+              lean::wait(emptyB0 + 8u * (uint32_t)sb, phb ^ 1);
+              if (leader) {
+                if (!kPair || rank == 0) lean::expect_tx(fullB0 + 8u * (uint32_t)sb, (uint32_t)n_e * 128u);
+                const uint32_t dst = b_base + (uint32_t)sb * Cfg::kBSlot;
+                const uint32_t bar = fullB_t + 8u * (uint32_t)sb;
+                if (n_e == 144) {
+                  lean::tma2d<kPair>(dst, &p.tmap_w, bar, c, row);
+                } else if (n_e == 80) {
+                  lean::tma2d<kPair>(dst, &p.tmap_w_half, bar, c, row);
+                } else {   // 160 rows: two boxes of 80 / kCG
+                  lean::tma2d<kPair>(dst, &p.tmap_w_half, bar, c, row);
+                  lean::tma2d<kPair>(dst + (80 / kCG) * 128, &p.tmap_w_half, bar, c, row + 80 / kCG);
+                }
+              }
+              if (++sb == SB) { sb = 0; phb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+    pdl_launch_dependents();
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // ====================================== MMA issuer ======================================
+      const bool leader = ptx::elect_one();
+      const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+      constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t da0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t db0 = ((b_base & 0x3FFFFu) >> 4) | (1u << 16);
+      constexpr int kM = kPair ? 2 * kBlockM : kBlockM;
+      const uint32_t idesc144 = ptx::umma_idesc_f16(kM, 144, p.is_bf16);
+      const uint32_t idesc160 = ptx::umma_idesc_f16(kM, 160, p.is_bf16);
+      const uint32_t idesc80 = ptx::umma_idesc_f16(kM, 80, p.is_bf16);
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0, tph = 0;
+      for (int tile = unit; tile < total_tiles; tile += nunits) {
+        lean::wait(tempty0, tph ^ 1);     // the epilogue (of both CTAs) has drained the previous tile's accumulators
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int t = 0; t < kStkTaps; ++t) {
+          for (int ch = 0; ch < nchunks; ++ch) {
+            const uint32_t da = da0 + (uint32_t)sa * (uint32_t)(Cfg::kABytes >> 4);
+            lean::wait(fullA0 + 8u * (uint32_t)sa, pha);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              if (e < stk_ne(t)) {
+                const int n_e = stk_n(t, e);
+                const uint32_t idesc = n_e == 144 ? idesc144 : n_e == 80 ? idesc80 : idesc160;
+                const uint32_t db = db0 + (uint32_t)sb * (uint32_t)(Cfg::kBSlot >> 4);
+                const uint32_t d_tmem = tmem_base + (uint32_t)stk_col(t, e);
+                lean::wait(fullB0 + 8u * (uint32_t)sb, phb);
+                ptx::tc_fence_after();
+                if (leader) {
+                  lean::mma<kPair>(d_tmem, da, db, kDescHi, idesc, (t > 0 || ch > 0) ? 1u : 0u);
+                  lean::mma<kPair>(d_tmem, da + 2, db + 2, kDescHi, idesc, 1u);
+                  lean::mma<kPair>(d_tmem, da + 4, db + 4, kDescHi, idesc, 1u);
+                  lean::mma<kPair>(d_tmem, da + 6, db + 6, kDescHi, idesc, 1u);
+                  lean::commit<kPair>(emptyB0 + 8u * (uint32_t)sb);
+                }
+                if (++sb == SB) { sb = 0; phb ^= 1; }
+              }
+            }
+            if (leader) lean::commit<kPair>(emptyA0 + 8u * (uint32_t)sa);
+            if (++sa == SA) { sa = 0; pha ^= 1; }
+          }
+        }
+        if (leader) lean::commit<kPair>(tfull0);
+        tph ^= 1;
+      }
+    }
+  } else if (warp < 6) {
+    // ============================== epilogue (own 128 rows of every tile) =====================
+    const uint32_t tmem_base = *tmem_slot;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    uint32_t tph = 0, stg_parity = 0, stg_phase = 0;
+    const uint32_t tempty_t = kPair ? ptx::mapa_u32(tempty0, 0) : tempty0;
+    const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t sw = (uint32_t)(row & 7);
+    for (int tile = unit; tile < total_tiles; tile += nunits) {
+      const int m_t = kPair ? tile * 2 + (int)rank : tile;
+      const int ty = row >> p.tileW_log2;
+      const int gy = (m_t / p.tiles_x) * p.tile_rows + ty;
+      const int gx = ((m_t % p.tiles_x) << p.tileW_log2) + (row & (tileW - 1));
+      const bool valid = (m_t < p.tiles_m) && (ty < p.tile_rows) && (gy < p.rows_total);
+      const int b = gy / p.Hg;
+      const int y = gy - b * p.Hg;
+      lean::wait(tfull0, tph);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int ph = 0; ph < 4; ++ph) {
+        const uint32_t col = (uint32_t)stk_phase_col(ph);
+        const uint32_t buf = stg0 + (stg_parity ? Cfg::kStgBytes : 0);
+        const uint32_t rowaddr = buf + (uint32_t)row * 128u;
+        lean::wait(sempty0 + 8 * stg_parity, stg_phase ^ 1);
+        uint32_t v[64];
+        ptx::tmem_ld32(t_addr + col, v);
+        ptx::tmem_ld32(t_addr + col + 32, v + 32);
+        ptx::tmem_wait_ld();
+        const float4* bias4 = reinterpret_cast<const float4*>(p.bias);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const float4 bv = __ldg(bias4 + 2 * j + q);
+            float a0 = __uint_as_float(v[8 * j + 4 * q]) + bv.x, a1 = __uint_as_float(v[8 * j + 4 * q + 1]) + bv.y;
+            float a2 = __uint_as_float(v[8 * j + 4 * q + 2]) + bv.z, a3 = __uint_as_float(v[8 * j + 4 * q + 3]) + bv.w;
+            if (p.lrelu) {
+              a0 = fmaxf(a0, 0.1f * a0); a1 = fmaxf(a1, 0.1f * a1);
+              a2 = fmaxf(a2, 0.1f * a2); a3 = fmaxf(a3, 0.1f * a3);
+            }
+            pk[2 * q] = pack16(a0, a1, p.is_bf16);
+            pk[2 * q + 1] = pack16(a2, a3, p.is_bf16);
+          }
+          ptx::st_shared_v4(rowaddr + ((((uint32_t)j) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+        }
+        if (ph == 3) {
+          // the three head copies (columns 0-1 of each are real): written as three of the four phase shares pyr_kernel sums
+          uint32_t h0[16], h1[16], h2[16];
+          ptx::tmem_ld16(t_addr + stk_head_col(0), h0);
+          ptx::tmem_ld16(t_addr + stk_head_col(1), h1);
+          ptx::tmem_ld16(t_addr + stk_head_col(2), h2);
+          ptx::tmem_wait_ld();
+          if (valid && p.head_out) {
+            float2* hp = p.head_out + ((size_t)b * p.out_H + 2 * y) * p.out_W + 2 * gx;
+            hp[0] = make_float2(__uint_as_float(h0[0]), __uint_as_float(h0[1]));
+            hp[1] = make_float2(__uint_as_float(h1[0]), __uint_as_float(h1[1]));
+            hp[p.out_W] = make_float2(__uint_as_float(h2[0]), __uint_as_float(h2[1]));
+            hp[p.out_W + 1] = make_float2(0.0f, 0.0f);
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kPair) ptx::mbar_arrive_cluster(tempty_t);
+            else ptx::mbar_arrive(&bars[2 * SA + 2 * SB + 1]);
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars[2 * SA + 2 * SB + 2 + stg_parity]);   // sfull
+        stg_parity ^= 1u;
+        if (stg_parity == 0) stg_phase ^= 1u;
+      }
+      tph ^= 1;
+    }
+  } else {
+    // ============== TMA-store issuer: one 64-channel staging buffer per phase -> that phase's pixels of the slice ====
+    const bool issuer = lane == 0;
+    uint32_t par = 0, phs = 0;
+    bool pending = false;
+    const uint32_t piece_bytes = (uint32_t)(p.piece_rows << p.tileW_log2) * 128u;
+    for (int tile = unit; tile < total_tiles; tile += nunits) {
+      const int m_t = kPair ? tile * 2 + (int)rank : tile;
+      const int gy0 = (m_t / p.tiles_x) * p.tile_rows;
+      const int ox0 = (m_t % p.tiles_x) << p.tileW_log2;
+      const int b0 = gy0 / p.Hg, y0 = gy0 - b0 * p.Hg;
+      const bool do_store = m_t < p.tiles_m;
+#pragma unroll 1
+      for (int ph = 0; ph < 4; ++ph) {
+        lean::wait(sfull0 + 8 * par, phs);
+        if (do_store) {
+          int bb = b0, yy = y0;
+          uint32_t src = stg0 + (par ? Cfg::kStgBytes : 0);
+          for (int pc = 0; pc < p.npieces; ++pc) {
+            if (issuer) ptx::tma_store_4d(&p.tmap_o[ph], src, 0, ox0, yy, bb);
+            src += piece_bytes;
+            yy += p.piece_rows;
+            if (yy >= p.Hg) { yy -= p.Hg; ++bb; }
+          }
+        }
+        if (issuer) {
+          ptx::bulk_commit_group();
+          if (pending) {
+            ptx::bulk_wait_read1();
+            ptx::mbar_arrive(&bars[2 * SA + 2 * SB + 4 + (par ^ 1)]);   // sempty
+          }
+        }
+        pending = true;
+        par ^= 1u;
+        if (par == 0) phs ^= 1u;
+      }
+    }
+    if (issuer) {
+      if (pending) { ptx::bulk_wait_read0(); ptx::mbar_arrive(&bars[2 * SA + 2 * SB + 4 + (par ^ 1)]); }
+      ptx::bulk_wait_all();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if constexpr (kPair) ptx::cluster_sync();
+  if (warp == 1) {
+    const uint32_t tmem_base = *tmem_slot;
+    if constexpr (kPair) ptx::tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) deconv_stack_kernel(const __grid_constant__ ConvGemmParams p) {
+  deconv_stack_body<false>(p);
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) deconv_stack2_kernel(const __grid_constant__ ConvGemmParams p) {
+  deconv_stack_body<true>(p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1072,6 +1437,10 @@ template <int BLOCK_N>
 int launch_th(const ConvPlan& plan, cudaStream_t st) {
   return launch_gemm(OFS_PICK(plan, conv_gemmh_kernel, BLOCK_N), GemmCfg<BLOCK_N, false, 1, 16>::kSmem, plan, st, 0);
 }
+template <int BLOCK_N>
+int launch_t2h(const ConvPlan& plan, cudaStream_t st) {
+  return launch_gemm(OFS_PICK(plan, conv_gemm2h_kernel, BLOCK_N), GemmCfg<BLOCK_N, true, 1, 16>::kSmem, plan, st, 0);
+}
 template <int BLOCK_N, int kHead>
 int launch_tg(const ConvPlan& plan, cudaStream_t st) {
   return launch_gemm(OFS_PICK(plan, conv_gemmg_kernel, BLOCK_N, kHead), GemmCfg<BLOCK_N, false, 1, kHead, 2>::kSmem, plan, st, 0);
@@ -1083,6 +1452,11 @@ int launch_tg4(const ConvPlan& plan, cudaStream_t st) {
 template <int BLOCK_N, int kT>
 int launch_t2s(const ConvPlan& plan, cudaStream_t st) {
   return launch_gemm(OFS_PICK(plan, conv_gemm2s_kernel, BLOCK_N, kT), GemmCfg<BLOCK_N, true, kT>::kSmem, plan, st, 0);
+}
+
+int launch_stack(const ConvPlan& plan, cudaStream_t st) {
+  if (plan.d.cta_group == 2) return launch_gemm(deconv_stack2_kernel, StackCfg<true>::kSmem, plan, st, 0);
+  return launch_gemm(deconv_stack_kernel, StackCfg<false>::kSmem, plan, st, 0);
 }
 
 int launch_reduce(const ConvPlan& plan, cudaStream_t st) {
@@ -1166,7 +1540,7 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
               d.in_cs, d.cin);
   OFS_REQUIRE(d.block_n == 16 || d.block_n == 32 || d.block_n == 64 || d.block_n == 128 || d.block_n == 192 || d.block_n == 256,
               "conv plan: block_n %d unsupported", d.block_n);
-  OFS_REQUIRE(d.block_n != 192 || (d.cta_group == 1 && !d.slab && !d.head), "block_n 192 runs on 1-CTA plain tiles only");
+  OFS_REQUIRE(d.block_n != 192 || (!d.slab && !d.head), "block_n 192 runs on plain tiles only");
   OFS_REQUIRE(d.cta_group == 1 || (d.cta_group == 2 && d.block_n >= 32),
               "conv plan: cta_group must be 1, or 2 with block_n >= 32 (got %d / %d)", d.cta_group, d.block_n);
   const bool deconv = d.kind == kDeconvK4S2;
@@ -1338,15 +1712,19 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
     OFS_REQUIRE(d.out_cstride % 8 == 0 && d.out_coff % 8 == 0, "16-bit output slice must be 16-byte aligned");
   }
   if (d.head) {
-    OFS_REQUIRE(deconv && d.out_mode == 0 && d.cta_group == 1 && d.ksplit <= 1 && (d.block_n == 64 || d.block_n == 128),
-                "fused head: transposed conv, 16-bit output, 1-CTA tiles of 64 / 128 columns, no split-K");
+    OFS_REQUIRE(deconv && d.out_mode == 0 && d.ksplit <= 1 && (d.block_n == 64 || d.block_n == 128) && (d.cta_group == 1 || d.kgroup == 1),
+                "fused head: transposed conv, 16-bit output, tiles of 64 / 128 columns, no split-K (CTA pairs: no chunk groups)");
+  }
+  if (d.stack) {
+    OFS_REQUIRE(deconv && d.head && d.cout == 64 && d.block_n == 64 && d.out_mode == 0 && d.ksplit <= 1 && d.kgroup == 1 && !d.slab,
+                "stacked transposed conv: cout 64 with the fused head, 16-bit output, no split-K / chunk groups");
   }
   OFS_REQUIRE(d.kgroup == 1 || (d.kgroup == 2 && d.cta_group == 1 && !d.slab && d.ksplit <= 1 && (d.block_n == 64 || d.block_n == 128)) ||
                   (d.kgroup == 4 && d.cta_group == 1 && !d.slab && !d.head && d.ksplit <= 1 && d.block_n == 32),
               "chunk groups: 2 per stage for 1-CTA tiles of 64 / 128 columns, 4 per stage for 32 columns; no slab, no split-K");
   p.w_rows_phase = p.n_pad + (d.head ? 16 : 0);
-  plan.k_total = (p.slab ? (int)plan.wt_ky.size() : p.ntaps * p.nchunks) * kBlockK;
-  plan.w_rows = p.phases * p.w_rows_phase;
+  plan.k_total = (p.slab ? (int)plan.wt_ky.size() : d.stack ? p.nchunks : p.ntaps * p.nchunks) * kBlockK;
+  plan.w_rows = d.stack ? kStkRows : p.phases * p.w_rows_phase;
   {
     const int num_kb = p.ntaps * p.nchunks;
     int ks = std::max(1, std::min(d.ksplit, num_kb));
@@ -1377,7 +1755,11 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
       total_tiles += rem;
     }
   }
-  if (p.kcluster) {
+  if (d.stack) {
+    // one scheduling unit = one M tile (pair: two) with all four phases
+    plan.grid = d.cta_group == 2 ? 2 * std::max(1, std::min(p.tiles_mp, sm_count() / 2)) : std::max(1, std::min(p.tiles_mp, sm_count()));
+    plan.smem = d.cta_group == 2 ? StackCfg<true>::kSmem : StackCfg<false>::kSmem;
+  } else if (p.kcluster) {
     plan.grid = total_tiles;   // one CTA per (tile, K split); clusters are gang-scheduled, a second wave is merely slower
     plan.smem = GemmCfg<256, false>::kSmem;
   } else if (d.kgroup == 4) {
@@ -1387,6 +1769,9 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
     plan.grid = std::max(1, std::min(total_tiles, sm_count()));
     plan.smem = d.block_n == 64 ? (d.head ? GemmCfg<64, false, 1, 16, 2>::kSmem : GemmCfg<64, false, 1, 0, 2>::kSmem)
                                 : (d.head ? GemmCfg<128, false, 1, 16, 2>::kSmem : GemmCfg<128, false, 1, 0, 2>::kSmem);
+  } else if (d.head && d.cta_group == 2) {
+    plan.grid = 2 * std::max(1, std::min(total_tiles, sm_count() / 2));
+    plan.smem = d.block_n == 64 ? GemmCfg<64, true, 1, 16>::kSmem : GemmCfg<128, true, 1, 16>::kSmem;
   } else if (d.head) {
     plan.grid = std::max(1, std::min(total_tiles, sm_count()));
     plan.smem = d.block_n == 64 ? GemmCfg<64, false, 1, 16>::kSmem : GemmCfg<128, false, 1, 16>::kSmem;
@@ -1399,6 +1784,7 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
       case 32: plan.smem = GemmCfg<32, true>::kSmem; break;
       case 64: plan.smem = GemmCfg<64, true>::kSmem; break;
       case 128: plan.smem = GemmCfg<128, true>::kSmem; break;
+      case 192: plan.smem = GemmCfg<192, true>::kSmem; break;
       default: plan.smem = GemmCfg<256, true>::kSmem; break;
     }
   } else {
@@ -1430,7 +1816,35 @@ void conv_pack_weights(const ConvPlan& plan, const float* w, const float* bias, 
   b_padded.assign(p.n_pad, 0.0f);
   for (int n = 0; n < d.cout; ++n) b_padded[n] = bias ? bias[n] : 0.0f;
   auto cvt = [&](float f) { return d.is_bf16 ? f32_to_bf16_rn(f) : f32_to_fp16_rn(f); };
-  if (d.kind == kDeconvK4S2) {
+  if (d.stack) {
+    // rows in accumulator-column order per (tap, entry); K = the chunks of ONE tap.  Phase (py,px) reads tap (dy,dx)
+    // with weight (ky,kx) = (py + 1 - 2 dy, px + 1 - 2 dx) when that lies in [0,4); the head reads every tap with
+    // hw[dy+1][dx+1] -- real in the first head copy an entry of the tap covers, zero rows in any other.
+    for (int t = 0; t < kStkTaps; ++t) {
+      const int dy = stk_dy(t), dx = stk_dx(t);
+      bool head_done = false;
+      for (int e = 0; e < stk_ne(t); ++e) {
+        const int col0 = stk_col(t, e), ne = stk_n(t, e), row0 = stk_row(t, e);
+        for (int j = 0; j < ne; ++j) {
+          const int col = col0 + j;
+          uint16_t* dst = out.data() + (size_t)(row0 + j) * K;
+          int ph = -1, co = 0, hc = -1;
+          for (int q = 0; q < 4; ++q) if (col >= stk_phase_col(q) && col < stk_phase_col(q) + 64) { ph = q; co = col - stk_phase_col(q); }
+          for (int q = 0; q < 3; ++q) if (col >= stk_head_col(q) && col < stk_head_col(q) + 16) { hc = q; co = col - stk_head_col(q); }
+          if (ph >= 0) {
+            const int py = ph >> 1, px = ph & 1;
+            const int ky = py + 1 - 2 * dy, kx = px + 1 - 2 * dx;
+            if (ky < 0 || ky > 3 || kx < 0 || kx > 3) continue;   // (never: an entry only spans phases that use its tap)
+            const float* src = w + (((size_t)ky * 4 + kx) * d.cout + co) * d.cin;
+            for (int ci = 0; ci < d.cin; ++ci) dst[ci] = cvt(src[ci]);
+          } else if (hc >= 0 && co < 2 && head_w && !head_done) {
+            for (int ci = 0; ci < d.cin; ++ci) dst[ci] = cvt(head_w[(((size_t)(dy + 1) * 3 + (dx + 1)) * d.cin + ci) * 2 + co]);
+            if (co == 1) head_done = true;
+          }
+        }
+      }
+    }
+  } else if (d.kind == kDeconvK4S2) {
     // w: [4,4,cout,cin];  y[2i+ky-1, 2j+kx-1, co] += x[i,j,ci] w[ky,kx,co,ci]
     for (int py = 0; py < 2; ++py)
       for (int px = 0; px < 2; ++px)
@@ -1541,6 +1955,12 @@ int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const 
   cuuint64_t wd[2] = {(cuuint64_t)plan.k_total, (cuuint64_t)plan.w_rows};
   cuuint64_t ws[1] = {(cuuint64_t)plan.k_total * 2};
   cuuint32_t wb[2] = {(cuuint32_t)kBlockK, (cuuint32_t)((plan.block_n + (d.head ? 16 : 0)) / d.cta_group)};
+  if (d.stack) {   // entries of 144 rows (tmap_w) and of 80 rows (tmap_w_half; a 160-row entry is two of them)
+    wb[1] = (cuuint32_t)(144 / d.cta_group);
+    cuuint32_t wh[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(80 / d.cta_group)};
+    st = encode_map(&p.tmap_w_half, d.is_bf16, 2, w_dev, wd, ws, wh);
+    if (st != OFS_OK) return st;
+  }
   if (p.tail_t0 != 0x7fffffff) {
     cuuint32_t wh[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(plan.block_n / 2 / d.cta_group)};
     st = encode_map(&p.tmap_w_half, d.is_bf16, 2, w_dev, wd, ws, wh);
@@ -1551,7 +1971,9 @@ int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const 
 
 int conv_launch(const ConvPlan& plan, cudaStream_t st) {
   int rc = OFS_EINVAL;
-  if (plan.p.kcluster) {
+  if (plan.d.stack) {
+    return launch_stack(plan, st);
+  } else if (plan.p.kcluster) {
     return launch_tk<256>(plan, st);
   } else if (plan.d.kgroup == 4) {
     rc = launch_tg4<32>(plan, st);
@@ -1559,6 +1981,10 @@ int conv_launch(const ConvPlan& plan, cudaStream_t st) {
     if (plan.block_n == 64) rc = plan.d.head ? launch_tg<64, 16>(plan, st) : launch_tg<64, 0>(plan, st);
     else if (plan.block_n == 128) rc = plan.d.head ? launch_tg<128, 16>(plan, st) : launch_tg<128, 0>(plan, st);
     else { set_error("conv_launch: chunk groups need block_n 64 or 128 (got %d)", plan.block_n); return OFS_EINVAL; }
+  } else if (plan.d.head && plan.d.cta_group == 2) {
+    if (plan.block_n == 64) rc = launch_t2h<64>(plan, st);
+    else if (plan.block_n == 128) rc = launch_t2h<128>(plan, st);
+    else { set_error("conv_launch: fused head needs block_n 64 or 128 (got %d)", plan.block_n); return OFS_EINVAL; }
   } else if (plan.d.head) {
     if (plan.block_n == 64) rc = launch_th<64>(plan, st);
     else if (plan.block_n == 128) rc = launch_th<128>(plan, st);
@@ -1572,6 +1998,7 @@ int conv_launch(const ConvPlan& plan, cudaStream_t st) {
       case 32: rc = launch_t2<32>(plan, st); break;
       case 64: rc = launch_t2<64>(plan, st); break;
       case 128: rc = launch_t2<128>(plan, st); break;
+      case 192: rc = launch_t2<192>(plan, st); break;
       case 256: rc = launch_t2<256>(plan, st); break;
       default: set_error("conv_launch: unsupported block_n %d for CTA pairs", plan.block_n); return OFS_EINVAL;
     }
@@ -1638,7 +2065,10 @@ extern "C" int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const flo
   d.slab = cta_group == 4 ? 1 : 0;   // 4 = CTA pairs + slab groups
   d.kgroup = cta_group == 8 ? 2 : cta_group == 32 ? 4 : 1; // 8 / 32 = two / four K chunks per pipeline stage
   d.kcluster = cta_group == 16 ? 1 : 0;   // 16 = split-K inside a thread-block cluster (DSMEM reduction)
-  const bool via16 = d.ksplit > 1 || out16;   // the network's 16-bit activation epilogue (split-K always reduces into it)
+  if (cta_group == 64 || cta_group == 66) {   // 64 / 66 = phase-stacked transposed conv on 1 CTA / CTA pairs (head weights zero)
+    d.stack = 1; d.head = 1; d.cta_group = cta_group == 66 ? 2 : 1; d.block_n = 64;
+  }
+  const bool via16 = d.ksplit > 1 || out16 || d.stack;   // the network's 16-bit activation epilogue (split-K always reduces into it)
   const int cout8 = ((Cout + 7) / 8) * 8;
   d.out_mode = via16 ? 0 : 1; d.lrelu = lrelu; d.is_bf16 = is_bf16;
   d.out_cstride = via16 ? cout8 : Cout; d.out_coff = 0;
@@ -1664,12 +2094,13 @@ extern "C" int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const flo
   std::vector<float> bp;
   conv_pack_weights(plan, wsrc, b_host, wp, bp);
   void *x16 = nullptr, *w_dev = nullptr, *y16 = nullptr;
-  float *b_dev = nullptr, *ws = nullptr;
+  float *b_dev = nullptr, *ws = nullptr, *hd = nullptr;
   unsigned* cnt = nullptr;
   const size_t npix = (size_t)B * H * W;
   const size_t npix_out = (size_t)B * plan.p.out_H * plan.p.out_W;
   auto cleanup = [&]() {
     if (cnt) cudaFree(cnt);
+    if (hd) cudaFree(hd);
     if (x16) cudaFree(x16);
     if (w_dev) cudaFree(w_dev);
     if (b_dev) cudaFree(b_dev);
@@ -1681,6 +2112,7 @@ extern "C" int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const flo
   if (rc == OFS_OK) rc = check_cuda(cudaMalloc((void**)&b_dev, bp.size() * 4), "cudaMalloc b", __FILE__, __LINE__);
   if (rc == OFS_OK && via16) rc = check_cuda(cudaMalloc(&y16, npix_out * cout8 * 2), "cudaMalloc y16", __FILE__, __LINE__);
   if (rc == OFS_OK && plan.ws_bytes) rc = check_cuda(cudaMalloc((void**)&ws, plan.ws_bytes), "cudaMalloc ws", __FILE__, __LINE__);
+  if (rc == OFS_OK && d.head) rc = check_cuda(cudaMalloc((void**)&hd, npix_out * 8), "cudaMalloc head shares", __FILE__, __LINE__);
   if (rc == OFS_OK && plan.n_counters) {
     rc = check_cuda(cudaMalloc((void**)&cnt, (size_t)plan.n_counters * 4), "cudaMalloc counters", __FILE__, __LINE__);
     if (rc == OFS_OK) rc = check_cuda(cudaMemsetAsync(cnt, 0, (size_t)plan.n_counters * 4, st), "zero counters", __FILE__, __LINE__);
@@ -1688,7 +2120,7 @@ extern "C" int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const flo
   if (rc == OFS_OK) rc = check_cuda(cudaMemcpyAsync(w_dev, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice, st), "H2D w", __FILE__, __LINE__);
   if (rc == OFS_OK) rc = check_cuda(cudaMemcpyAsync(b_dev, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice, st), "H2D b", __FILE__, __LINE__);
   if (rc == OFS_OK) rc = launch_pack_act(x, x16, npix, cin_logical, d.in_cs, is_bf16, st);
-  if (rc == OFS_OK) rc = conv_plan_bind(plan, x16, w_dev, b_dev, via16 ? y16 : (void*)y, ws, nullptr, cnt);
+  if (rc == OFS_OK) rc = conv_plan_bind(plan, x16, w_dev, b_dev, via16 ? y16 : (void*)y, ws, hd, cnt);
   if (rc == OFS_OK) rc = conv_launch(plan, st);
   if (rc == OFS_OK && via16) rc = launch_unpack_act(y16, y, npix_out, cout8, 0, Cout, is_bf16, st);
   if (rc == OFS_OK) rc = check_cuda(cudaStreamSynchronize(st), "conv2d sync", __FILE__, __LINE__);
@@ -1742,6 +2174,8 @@ extern "C" int ofs_conv2d_bench(int B, int H, int W, int Cin, int in_cs, int Cou
   d.B = B; d.H = H; d.W = W; d.cin = Cin; d.in_cs = in_cs; d.cout = Cout; d.k = k; d.stride = stride;
   d.block_n = block_n; d.ksplit = ksplit > 1 ? ksplit : 1; d.cta_group = (cta_group == 2 || cta_group == 4) ? 2 : 1; d.slab = cta_group == 4 ? 1 : 0; d.kgroup = cta_group == 8 ? 2 : cta_group == 32 ? 4 : 1; d.debug = debug;
   d.kcluster = cta_group == 16 ? 1 : 0;
+  if (cta_group == 64 || cta_group == 66) { d.stack = 1; d.head = 1; d.cta_group = cta_group == 66 ? 2 : 1; }
+  if (cta_group == 34 || cta_group == 36) { d.head = 1; d.cta_group = cta_group == 36 ? 2 : 1; }   // per-phase form with the fused head
   const bool out16 = (Cout % block_n) == 0 || (!transposed && block_n >= 64 && Cout % 64 == 0 && ksplit <= 1);
   d.out_mode = out16 ? 0 : 1; d.lrelu = 1; d.is_bf16 = 1; d.out_cstride = out_cs; d.out_coff = 0;
   ConvPlan plan;
@@ -1750,12 +2184,12 @@ extern "C" int ofs_conv2d_bench(int B, int H, int W, int Cin, int in_cs, int Cou
   const size_t npix = (size_t)B * H * W, npix_out = (size_t)B * plan.p.out_H * plan.p.out_W;
   const size_t w_elems = (size_t)plan.w_rows * plan.k_total;
   void *x16 = nullptr, *w_dev = nullptr, *y = nullptr, *fl = nullptr;
-  float *b_dev = nullptr, *ws = nullptr;
+  float *b_dev = nullptr, *ws = nullptr, *hd = nullptr;
   long long* tr = nullptr;
   unsigned* cnt = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   auto cleanup = [&]() {
-    for (void* q : {x16, w_dev, y, fl, (void*)b_dev, (void*)ws, (void*)tr, (void*)cnt}) if (q) cudaFree(q);
+    for (void* q : {x16, w_dev, y, fl, (void*)b_dev, (void*)ws, (void*)tr, (void*)cnt, (void*)hd}) if (q) cudaFree(q);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
   };
@@ -1765,6 +2199,7 @@ extern "C" int ofs_conv2d_bench(int B, int H, int W, int Cin, int in_cs, int Cou
             cudaMalloc((void**)&b_dev, (size_t)plan.p.n_pad * 4) == cudaSuccess &&
             (plan.ws_bytes == 0 || cudaMalloc((void**)&ws, plan.ws_bytes) == cudaSuccess) &&
             (flush_bytes == 0 || cudaMalloc(&fl, flush_bytes) == cudaSuccess) &&
+            (!d.head || cudaMalloc((void**)&hd, npix_out * 8) == cudaSuccess) &&
             cudaMalloc((void**)&cnt, (size_t)(plan.n_counters + 1) * 4) == cudaSuccess &&
             cudaMalloc((void**)&tr, ((size_t)plan.grid * 96 + 4096) * 8) == cudaSuccess &&
             cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess;
@@ -1774,7 +2209,7 @@ extern "C" int ofs_conv2d_bench(int B, int H, int W, int Cin, int in_cs, int Cou
   cudaMemsetAsync(b_dev, 0, (size_t)plan.p.n_pad * 4, st);
   cudaMemsetAsync(cnt, 0, (size_t)(plan.n_counters + 1) * 4, st);
   cudaMemsetAsync(tr, 0, ((size_t)plan.grid * 96 + 4096) * 8, st);
-  rc = conv_plan_bind(plan, x16, w_dev, b_dev, y, ws, nullptr, cnt);
+  rc = conv_plan_bind(plan, x16, w_dev, b_dev, y, ws, hd, cnt);
   // back-to-back launches between ONE event pair (no host sync inside): steady-state time per launch including
   // the inter-kernel gap, excluding host launch latency.  With flush_mb the same loop is timed with the flush
   // kernel alone and subtracted.
@@ -1888,6 +2323,7 @@ extern "C" int ofs_debug_conv_plan_ex(int kind, int B, int H, int W, int cin, in
   d.B = B; d.H = H; d.W = W; d.cin = cin; d.in_cs = in_cs; d.cout = cout; d.k = k; d.stride = stride;
   d.block_n = block_n; d.out_mode = 0; d.lrelu = 0; d.is_bf16 = is_bf16; d.out_cstride = ((cout + 7) / 8) * 8; d.out_coff = 0;
   d.slab = flags & 1; d.head = (flags >> 1) & 1; d.cta_group = (flags & 1) ? 2 : 1;
+  if (flags & 4) { d.stack = 1; d.head = 1; }   // bit2: phase-stacked transposed conv (packed rows: see stk_row / stk_col)
   ConvPlan plan;
   int rc = conv_plan_geometry(plan, d);
   if (rc != OFS_OK) return rc;

@@ -96,6 +96,8 @@ struct ConvDesc {
   int kgroup = 1;      // 2: two consecutive 64-channel K blocks of a tap per pipeline stage (narrow-N layers)
   int head = 0;        // 1: transposed conv with the level's 3x3 flow head fused as 16 extra accumulator columns
   int slab = 0;        // 1: x-shifted taps share one shared-memory slab (stride-2 convs whose tiles are one 128-px row)
+  int stack = 0;       // 1: transposed conv (cout 64, fused head) with all 4 sub-pixel phases stacked in ONE accumulator tile: each
+                       //    of the 9 distinct input taps is fetched once per chunk (deconv_stack_kernel); cta_group 1 or 2
   int debug = 0;       // see ConvGemmParams::debug
   long long* trace = nullptr;  // see ConvGemmParams::trace
 };

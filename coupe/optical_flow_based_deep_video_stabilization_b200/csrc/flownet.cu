@@ -425,7 +425,13 @@ int prepare(ofs_net* n, int B) {
       return OFS_EINVAL;
     }
     if (L.d.slab) { cg = 2; bn = L.d.block_n; ks = 1; }   // the packed K order is the slab order: tiling is fixed
-    if (!tuned && !L.d.slab && ks == 1 && L.d.out_mode == 0) {
+    if (L.d.stack) {   // stacked deconv: only 1 CTA / CTA pair is a choice
+      bn = L.d.block_n; ks = 1; if (cg != 1) cg = 2;
+      L.d.cta_group = cg;
+      rc = conv_plan_geometry(L.plan, L.d);
+      if (rc != OFS_OK) return rc;
+    }
+    if (!tuned && !L.d.slab && !L.d.stack && ks == 1 && L.d.out_mode == 0) {
       // small batches leave the wide-N tilings with a handful of tiles (conv4_1 at batch 1: 18): narrow the N tile
       // until ~100 tiles exist.  The N tiling does not touch the K summation order, so results stay bit-identical
       // across batch sizes (tests: batch independence).
@@ -439,7 +445,7 @@ int prepare(ofs_net* n, int B) {
       };
       int t = tiles_for(bn);
       for (int cand : {128, 64}) {
-        if (t >= 96 || cand >= bn) continue;
+        if (t >= (cg == 2 ? 48 : 96) || cand >= bn) continue;
         const int tc = tiles_for(cand);
         if (tc > t) { bn = cand; t = tc; }
       }
@@ -709,10 +715,19 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
     else if (L.name == "3_1") { L.block_n_run = 256; }
     // cout 512 on 48 M tiles: 3 N tiles of 192 (the last one a third empty, clipped by the TMA store) = 144 tiles, ONE
     // wave on 148 SMs, instead of 2 x 256 = 96 tiles on 65 % of the SMs (-25 % time, conv_bench A/B)
-    else if (L.name == "4" || L.name == "4_1") { L.d.block_n = 192; }
+    // conv4 on CTA pairs (72 pair tiles on 74 pair slots; 16 KB of A + 12 KB of B per K block and CTA instead of 16 + 24):
+    // 17.8 vs 18.5 us isolated; conv4_1 measured the other way round (24.7 vs 23.7 us) and stays on single CTAs
+    // (profiles/r02_tuning.md)
+    else if (L.name == "4" || L.name == "4_1") { L.d.block_n = 192; if (L.name == "4") L.cta_group = 2; }
     else if (L.name == "5" || L.name == "5_1") { L.block_n_run = 256; L.ksplit = 6; }
     else if (L.name == "6" || L.name == "6_1") { L.block_n_run = 256; L.ksplit = 8; }
-    else if (L.d.kind == kDeconvK4S2) { L.d.head = 1; }   // the level's flow head rides in the deconv GEMM (128 / 64-column tiles)
+    // the level's flow head rides in the deconv GEMM (128 / 64-column tiles); CTA pairs halve the B fetch per CTA
+    else if (L.d.kind == kDeconvK4S2) {
+      L.d.head = 1; L.cta_group = 2;
+      // deconv2 (cout 64): all four sub-pixel phases stacked in one accumulator tile, each input tap fetched once
+      // (deconv_stack_kernel); fixes the packed weight layout.  OFS_NOSTACK=1: the per-phase form (A/B).
+      if (L.name == "deconv2" && !(getenv("OFS_NOSTACK") && getenv("OFS_NOSTACK")[0] == '1')) { L.d.stack = 1; L.d.cta_group = 2; }
+    }
   }
   for (Layer& L : Ls) {
     L.d.is_bf16 = n->is_bf16;

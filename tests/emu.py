@@ -189,7 +189,7 @@ def _accumulate(plan, act, out, written):
 
 # ---------------------------------------------------------------------------------------------------------------
 # slab groups (conv1 / conv2) and the fused flow head (deconvs): same idea through ofs_debug_conv_plan_ex
-def get_plan_ex(lib, kind, B, H, W, cin, in_cs, cout, k, stride, block_n, w_tf, bias, slab=False, head_w=None):
+def get_plan_ex(lib, kind, B, H, W, cin, in_cs, cout, k, stride, block_n, w_tf, bias, slab=False, head_w=None, stack=False):
     info = (C.c_int * 48)()
     taps = (C.c_short * 256)()
     grp = (C.c_short * 320)()
@@ -199,7 +199,7 @@ def get_plan_ex(lib, kind, B, H, W, cin, in_cs, cout, k, stride, block_n, w_tf, 
     w_tf = np.ascontiguousarray(w_tf, np.float32)
     bias = np.ascontiguousarray(bias, np.float32)
     hw = None if head_w is None else np.ascontiguousarray(head_w, np.float32)
-    flags = (1 if slab else 0) | (2 if head_w is not None else 0)
+    flags = (1 if slab else 0) | (2 if head_w is not None else 0) | (4 if stack else 0)
     rc = lib.ofs_debug_conv_plan_ex(kind, B, H, W, cin, in_cs, cout, k, stride, block_n, 1, flags,
                                     w_tf.ctypes.data_as(C.c_void_p), bias.ctypes.data_as(C.c_void_p),
                                     None if hw is None else hw.ctypes.data_as(C.c_void_p), C.cast(info, C.c_void_p),
@@ -288,3 +288,66 @@ def emulate_ex(plan, act):
             if plan["head"] and last_n:
                 head[b, oy, ox] = acc[row, BN:BN + 2]
     return out.astype(np.float32), None if head is None else head.astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# phase-stacked transposed conv (deconv_stack_kernel): the tap / entry tables of conv_gemm.cu restated
+STK_DY = [0, -1, 1, 0, 0, -1, -1, 1, 1]
+STK_DX = [0, 0, 0, 1, -1, -1, 1, 1, -1]
+STK_ENTRIES = [  # per tap: (accumulator column, N, first packed weight row)
+    [(0, 144, 0), (144, 160, 144)], [(0, 144, 304)], [(160, 144, 448)], [(80, 144, 592)], [(0, 80, 736), (224, 80, 816)],
+    [(0, 80, 896)], [(80, 80, 976)], [(144, 80, 1056)], [(224, 80, 1136)]]
+STK_PHASE_COL = [16, 80, 224, 160]
+STK_HEAD_COL = [0, 144, 288]
+
+
+def emulate_stack(plan, act):
+    """One 304-column accumulator per 128-pixel tile: every tap's A tile is fetched once per chunk and multiplied by the
+    packed weight rows of each of its entries into that entry's column range.  Returns (out [B,2H,2W,64] with bias, the
+    three head copies as phase shares [B,2H,2W,2] (share (1,1) zero))."""
+    flat = np.ascontiguousarray(act, np.float32).reshape(-1)
+    tileW = 1 << plan["tileW_log2"]
+    tile_rows, piece_rows, Hg = plan["tile_rows"], plan["piece_rows"], plan["Hg"]
+    B = act.shape[0]
+    assert plan["w_rows"] == 1216 and plan["k_total"] == plan["nchunks"] * 64 and plan["n_pad"] == 64
+    out = np.full((B, plan["out_H"], plan["out_W"], 64), np.nan, np.float64)
+    head = np.full((B, plan["out_H"], plan["out_W"], 2), np.nan, np.float64)
+    for m_t in range(plan["tiles_m"]):
+        gy0 = (m_t // plan["tiles_x"]) * tile_rows
+        ox0 = (m_t % plan["tiles_x"]) << plan["tileW_log2"]
+        acc = np.zeros((128, 304), np.float64)
+        touched = np.zeros(304, bool)
+        for t in range(9):
+            for ch in range(plan["nchunks"]):
+                A = np.zeros((128, 64), np.float32)
+                for pc in range(plan["npieces"]):
+                    gy = gy0 + pc * piece_rows
+                    b = gy // Hg
+                    y = gy - b * Hg + STK_DY[t]
+                    A[pc * piece_rows * tileW:(pc + 1) * piece_rows * tileW] = tma_box(flat, plan, ch * 64, ox0 + STK_DX[t], 0, y, b, tileW)
+                for col0, n, row0 in STK_ENTRIES[t]:
+                    Wt = plan["w"][row0:row0 + n, ch * 64:(ch + 1) * 64]
+                    prod = A.astype(np.float64) @ Wt.astype(np.float64).T
+                    if t == 0 and ch == 0:
+                        acc[:, col0:col0 + n] = prod          # accumulate = 0: must cover every column exactly once
+                        assert not touched[col0:col0 + n].any()
+                        touched[col0:col0 + n] = True
+                    else:
+                        acc[:, col0:col0 + n] += prod
+        assert touched.all()
+        for row in range(128):
+            ty = row >> plan["tileW_log2"]
+            gy = gy0 + ty
+            gx = ox0 + (row & (tileW - 1))
+            if ty >= tile_rows or gy >= plan["rows_total"]:
+                continue
+            b = gy // Hg
+            y = gy - b * Hg
+            for ph in range(4):
+                c0 = STK_PHASE_COL[ph]
+                out[b, 2 * y + (ph >> 1), 2 * gx + (ph & 1)] = acc[row, c0:c0 + 64] + plan["b"][:64]
+            head[b, 2 * y, 2 * gx] = acc[row, 0:2]
+            head[b, 2 * y, 2 * gx + 1] = acc[row, 144:146]
+            head[b, 2 * y + 1, 2 * gx] = acc[row, 288:290]
+            head[b, 2 * y + 1, 2 * gx + 1] = 0.0
+    return out.astype(np.float32), head.astype(np.float32)

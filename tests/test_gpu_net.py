@@ -101,6 +101,8 @@ TILING_CASES = [
     pytest.param(3, 6, 8, 256, 256, 3, 1, False, 128, -1, 2, id="tma_store_pair_odd_tiles"),
     pytest.param(2, 24, 32, 128, 512, 3, 1, False, 192, -1, 1, id="tma_store_n192_padded_last_tile"),
     pytest.param(1, 24, 32, 64, 320, 3, 1, False, 192, -1, 1, id="tma_store_n192_cout320"),
+    pytest.param(2, 24, 32, 128, 512, 3, 1, False, 192, -1, 2, id="tma_store_pair_n192_padded_last_tile"),
+    pytest.param(3, 24, 32, 64, 320, 3, 1, False, 192, -1, 2, id="tma_store_pair_n192_cout320_odd_tiles"),
     # chunk groups (cta_group = 8: two 64-channel K blocks of a tap per pipeline stage)
     pytest.param(1, 24, 32, 192, 64, 3, 1, False, 64, -1, 8, id="kgroup_odd_chunk_count"),
     pytest.param(2, 12, 16, 130, 128, 4, 2, True, 128, -1, 8, id="kgroup_deconv"),
@@ -118,6 +120,13 @@ TILING_CASES = [
     pytest.param(3, 10, 256, 64, 128, 5, 2, False, 128, -1, 4, id="slab_conv2_form_odd_tiles_out16"),
     pytest.param(1, 8, 256, 16, 64, 3, 2, False, 64, 1, 4, id="slab_k3_paired"),
     pytest.param(1, 8, 256, 64, 64, 3, 2, False, 64, 1, 4, id="slab_k3_cin64"),
+    # phase-stacked transposed conv (cta_group = 64: 1 CTA, 66: CTA pairs): the deconv2 form, cout 64
+    pytest.param(1, 24, 32, 386, 64, 4, 2, True, 64, -1, 64, id="stack_deconv2_form_1cta"),
+    pytest.param(1, 24, 32, 386, 64, 4, 2, True, 64, -1, 66, id="stack_deconv2_form_pairs"),
+    pytest.param(3, 12, 16, 130, 64, 4, 2, True, 64, -1, 64, id="stack_1cta_two_pieces_ragged_tail"),
+    pytest.param(3, 12, 16, 130, 64, 4, 2, True, 64, -1, 66, id="stack_pairs_odd_tile_count"),
+    pytest.param(3, 6, 8, 64, 64, 4, 2, True, 64, -1, 66, id="stack_pairs_whole_image_tiles"),
+    pytest.param(2, 48, 64, 200, 64, 4, 2, True, 64, -1, 66, id="stack_pairs_two_row_tiles_many"),
     # tail split: > 148 M tiles of 256 columns, the last wave runs as half tiles on twice as many CTAs
     pytest.param(7, 48, 64, 64, 256, 3, 1, False, 256, -1, 1, id="tail_half_168_tiles"),
     pytest.param(7, 48, 64, 64, 256, 3, 1, False, 256, -1, 2, id="tail_half_pairs_84_pair_tiles"),

@@ -180,6 +180,31 @@ def test_fused_head_plan_emulation_matches_oracle(lib, B, H, W, cin, in_cs, cout
     np.testing.assert_allclose(head, href.numpy(), rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("B,H,W,cin,in_cs", [(2, 6, 8, 70, 72), (1, 12, 16, 130, 136), (1, 24, 32, 64, 64)],
+                         ids=["whole_image_tiles", "three_chunks_two_pieces", "four_row_tiles"])
+def test_stacked_deconv_plan_emulation_matches_oracle(lib, B, H, W, cin, in_cs):
+    """Phase-stacked transposed conv (deconv2 form, cout 64): 9 taps fetched once each, 11 weight-row entries into a
+    304-column accumulator.  The four phase column blocks must equal the oracle conv2d_transpose, the three head copies
+    must add up to the oracle 3x3 head, and the first two MMAs must cover every accumulator column exactly once."""
+    rng = np.random.RandomState(17 + cin)
+    cout = 64
+    x = emu.bf16_round(rng.rand(B, H, W, cin).astype(np.float32))
+    w = emu.bf16_round(rng.randn(4, 4, cout, cin).astype(np.float32) * 0.1)
+    hw = emu.bf16_round(rng.randn(3, 3, cin, 2).astype(np.float32) * 0.1)
+    b = rng.randn(cout).astype(np.float32)
+    plan = emu.get_plan_ex(lib, 1, B, H, W, cin, in_cs, cout, 4, 2, 64, w, b, head_w=hw, stack=True)
+    act = np.zeros((B, H, W, in_cs), np.float32)
+    act[..., :cin] = x
+    act[..., cin:] = 7.0      # pad channels of a concat buffer may hold anything finite: their weights are zero
+    got, shares = emu.emulate_stack(plan, act)
+    xt = torch.from_numpy(x).double()
+    ref = T.conv2d_transpose_k4s2_same(xt, torch.from_numpy(w).double(), torch.from_numpy(b).double())
+    np.testing.assert_allclose(got, ref.numpy(), rtol=1e-5, atol=1e-5)
+    head = shares[:, 0::2, 0::2] + shares[:, 0::2, 1::2] + shares[:, 1::2, 0::2] + shares[:, 1::2, 1::2]
+    href = T.conv2d_valid(T.pad_constant(xt, 1), torch.from_numpy(hw).double(), torch.zeros(2).double(), 1)
+    np.testing.assert_allclose(head, href.numpy(), rtol=1e-5, atol=1e-5)
+
+
 def test_network_layer_plans_are_valid(lib):
     """Geometry of the 15 GEMM layers (default 1-CTA tilings; the flow heads ride in the deconvs): tiles cover the grid,
     K is whole 64-blocks, smem fits."""
