@@ -97,7 +97,7 @@ def main():
             parts = [int(x) for x in v.split(":")]
             bn, ks, cg = parts[0], parts[1], parts[2]
             dbg = parts[3] if len(parts) > 3 else 0
-            if cout % bn != 0 and not (bn == 192 and cout % 64 == 0 and not tr) and name != "predict2":
+            if cout % bn != 0 and not (bn == 192 and cout % 64 == 0 and not tr) and name != "predict2" and cg != 5:
                 continue
             ms = C.c_float(0)
             grid = C.c_int(0)

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Turns the scratch ncu outputs of scripts_gpu_run.sh (gpurun_out/launches.csv, prof_conv.ncu-rep, prof_misc.ncu-rep)
-into the tracked summaries under profiles/.   python benchmarks/ncu_summarize.py r01"""
+"""Turns the scratch ncu outputs of tools/gpu_profile_r2.sh (gpurun_out/launches.csv, prof_conv.ncu-rep, prof_misc.ncu-rep)
+into the tracked summaries under profiles/ -- launch shares, the --set full table, and <tag>_ncu_traffic.json (DRAM bytes
+per launch set of the dominant kernels, which bench.py reports as roofline.traffic).   python benchmarks/ncu_summarize.py r02"""
+import json
 import collections
 import csv
 import os
@@ -72,9 +74,12 @@ def raw(rep):
 
 
 def full_summary():
-    labels = ["conv1 (slab, pairs)", "conv2 (slab, pairs)", "conv3 (pairs)", "conv3_1", "conv4 (192)", "conv4_1 (192)",
-              "conv5 (split-K 6)", "conv5_1 (split-K 6)", "conv6 (split-K 8)", "conv6_1 (split-K 8)", "deconv5 + predict6",
-              "deconv4 + predict5", "deconv3 + predict4", "deconv2 + predict3", "predict2 1x1 product", "conv1 (next step)"]
+    labels = ["conv1 (slab, pairs, two pixels per row)", "conv2 (slab, pairs)", "conv3 (pairs)", "conv3_1", "conv4 (192, pairs)", "conv4_1 (192)",
+              "conv5 (split-K 6)", "conv5 reduce", "conv5_1 (split-K 6)", "conv5_1 reduce", "conv6 (split-K 8)", "conv6 reduce",
+              "conv6_1 (split-K 8)", "conv6_1 reduce", "deconv5 + predict6 (pairs)", "deconv4 + predict5 (pairs)",
+              "deconv3 + predict4 (pairs)", "deconv2 + predict3 (stacked, pairs)", "predict2 1x1 product"]
+    traffic = {"how": "ncu --set full --clock-control none, one step of `OFS_GRAPH=0 python bench.py --steps 2 --warmup 1 --no-cpu-baseline "
+                      "--sustained-seconds 0` in launch order; dram__bytes_read.sum + dram__bytes_write.sum per launch", "per_launch": []}
     out = [f"# ncu --set full summaries ({tag}, B200, `OFS_GRAPH=0 python bench.py --steps 2 --warmup 1 --no-cpu-baseline`)", "",
            "`--clock-control none --import-source on`; per-launch values are cold-cache and serialised (ncu flushes caches between",
            "replays): compare utilisations and shares, not absolute times.  Scratch reports: gpurun_out/prof_conv.ncu-rep, prof_misc.ncu-rep.", ""]
@@ -100,6 +105,8 @@ def full_summary():
                 "| layer / kernel | kernel | grid | time us | tensor pipe active % of elapsed | of active (avg / busiest SM) | DRAM read MB | "
                 "DRAM write MB | L2 hit % | issue active % | regs |", "|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
         for i, r in enumerate(rows):
+            if labs and i >= len(labs):
+                break
             t = float(g(r, "gpu__time_duration.sum"))
             t_us = t / 1e3 if units[idx["gpu__time_duration.sum"]] in ("ns", "nsecond") else t
             name = short(g(r, "Kernel Name"))[:40]
@@ -111,7 +118,19 @@ def full_summary():
                 f(r, "sm__pipe_tensor_cycles_active.max.pct_of_peak_sustained_active"),
                 mb(r, "dram__bytes_read.sum"), mb(r, "dram__bytes_write.sum"), f(r, "lts__t_sector_hit_rate.pct"),
                 f(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"), g(r, "launch__registers_per_thread")))
+            try:
+                traffic["per_launch"].append({"label": lab, "kernel": name, "us": t_us,
+                                              "dram_bytes": (mb(r, "dram__bytes_read.sum") + mb(r, "dram__bytes_write.sum")) * 1e6})
+            except ValueError:
+                pass
         out.append("")
+    dense = [e for e in traffic["per_launch"] if ("conv_gemm" in e["kernel"] or "deconv_stack" in e["kernel"] or "splitk" in e["kernel"])
+             and "predict2" not in e["label"]]
+    warp = [e for e in traffic["per_launch"] if e["kernel"].startswith("warp5")]
+    traffic["dense_set_bytes"] = sum(e["dram_bytes"] for e in dense)
+    traffic["dense_set_launches"] = len(dense)
+    traffic["warp_bytes"] = warp[0]["dram_bytes"] if warp else None
+    json.dump(traffic, open(os.path.join(P, f"{tag}_ncu_traffic.json"), "w"), indent=1)
     extra = os.path.join(P, f"{tag}_ncu_reading.md")
     if os.path.exists(extra):
         out += open(extra).read().splitlines()

@@ -1517,7 +1517,12 @@ uint16_t f32_to_fp16_rn(float f) {
 void conv_act_view(const ConvDesc& d, unsigned long long dims[5], unsigned long long strides_bytes[4]) {
   const unsigned long long cs = (unsigned long long)d.in_cs, H = (unsigned long long)d.H, W = (unsigned long long)d.W,
                            B = (unsigned long long)d.B;
-  if (d.kind == kConv && d.stride == 2) {
+  if (d.kind == kConv && d.stride == 2 && d.slab == 2) {
+    // quad view: [(x mod 4, c), x/4, ypar, y/2, b]
+    dims[0] = 4 * cs; dims[1] = W / 4; dims[2] = 2; dims[3] = H / 2; dims[4] = B;
+    strides_bytes[0] = 4 * cs * 2; strides_bytes[1] = W * cs * 2; strides_bytes[2] = 2 * W * cs * 2;
+    strides_bytes[3] = H * W * cs * 2;
+  } else if (d.kind == kConv && d.stride == 2) {
     // parity view: [(xpar, c), x/2, ypar, y/2, b]
     dims[0] = 2 * cs; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = B;
     strides_bytes[0] = 2 * cs * 2; strides_bytes[1] = W * cs * 2; strides_bytes[2] = 2 * W * cs * 2;
@@ -1556,8 +1561,17 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
     Hg = (d.H + 2 * pad - d.k) / d.stride + 1;
     Wg = (d.W + 2 * pad - d.k) / d.stride + 1;
     if (d.stride == 2) OFS_REQUIRE(d.H % 2 == 0 && d.W % 2 == 0, "stride-2 conv needs even H, W (got %dx%d)", d.H, d.W);
+    if (d.slab == 2) {
+      // conv1 form with TWO output pixels per GEMM row: the GEMM grid is [Hg, Wg / 2] and its 128 accumulator columns are
+      // [pixel 2m: cout | pixel 2m+1: cout] -- contiguous in the NHWC output, which is simply viewed as [B, Hg, Wg/2, 2 cout]
+      OFS_REQUIRE(d.k == 7 && d.stride == 2 && d.in_cs == 32 && d.cout == 64 && d.block_n == 128 && d.W % 512 == 0 && d.cta_group == 2 &&
+                      d.out_mode == 0 && d.out_coff == 0 && d.out_cstride == d.cout && d.ksplit <= 1,
+                  "two-pixel slab form: k7 s2 conv, 32-channel input buffer, cout 64 stored densely, W %% 512 == 0, CTA pairs, block_n 128");
+      Wg /= 2;
+    }
     p.phases = 1; p.out_scale = 1; p.out_H = Hg; p.out_W = Wg;
   }
+  const int cout_eff = d.slab == 2 ? 2 * d.cout : d.cout;   // accumulator columns of the layer
   // tiling of the M grid
   int tileW = 1 << ilog2(std::min(Wg, 128));
   OFS_REQUIRE(tileW >= 8 && Wg % tileW == 0, "conv plan: output grid width %d must be a multiple of a power of two >= 8", Wg);
@@ -1673,7 +1687,12 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
       ++ng;
     };
     for (int ky = 0; ky < d.k; ++ky) {
-      if (plan.paired) {   // K block j = x-parity pair (kx = 2j-1, 2j): all pairs of a row are x shifts of each other
+      if (d.slab == 2) {
+        // input viewed as quads [(x mod 4, c) = 128, x / 4]: GEMM row m (output pixels 2m, 2m+1) reads quads m-1, m, m+1
+        // through the first 64 elements (input x = 4q, 4q+1) and quads m-1, m through the last 64 (x = 4q+2, 4q+3)
+        add_group(ky, 0, {-1, 0, 1}, {0, 0, 0});
+        add_group(ky, 64, {-1, 0}, {0, 0});
+      } else if (plan.paired) {   // K block j = x-parity pair (kx = 2j-1, 2j): all pairs of a row are x shifts of each other
         std::vector<int> xo, kxs;
         for (int j = 0; j < (d.k + 1) / 2; ++j) { xo.push_back((2 * j - 1 - pad) >> 1); kxs.push_back(2 * j - 1); }
         add_group(ky, 0, xo, kxs);
@@ -1699,15 +1718,15 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
     p.a_bytes = (128 + extra) * kBlockK * 2;
   }
   plan.block_n = d.block_n;
-  p.n_pad = ((d.cout + d.block_n - 1) / d.block_n) * d.block_n;
+  p.n_pad = ((cout_eff + d.block_n - 1) / d.block_n) * d.block_n;
   p.tiles_n = p.n_pad / d.block_n;
-  p.n_valid = d.cout;
+  p.n_valid = cout_eff;
   p.out_mode = d.out_mode; p.lrelu = d.lrelu; p.is_bf16 = d.is_bf16; p.debug = d.debug; p.trace = d.trace;
-  p.out_cstride = d.out_cstride; p.out_coff = d.out_coff;
+  p.out_cstride = d.slab == 2 ? 2 * d.out_cstride : d.out_cstride; p.out_coff = d.out_coff;
   if (d.out_mode == 0) {
     // a padded last N tile is fine when the epilogue goes through TMA stores (columns >= cout are clipped by the
     // tensor map) and the 64-column store chunks do not straddle cout; direct stores need an exact fit
-    OFS_REQUIRE(p.n_pad == d.cout || (d.block_n >= 64 && d.cout % 64 == 0 && d.ksplit <= 1 && !deconv),
+    OFS_REQUIRE(p.n_pad == cout_eff || (d.block_n >= 64 && d.cout % 64 == 0 && d.ksplit <= 1 && !deconv),
                 "16-bit output mode needs cout %% block_n == 0 (cout %d, block_n %d)", d.cout, d.block_n);
     OFS_REQUIRE(d.out_cstride % 8 == 0 && d.out_coff % 8 == 0, "16-bit output slice must be 16-byte aligned");
   }
@@ -1803,7 +1822,7 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
                          d.kgroup == 1 && plan.grid == total_tiles;
   plan.n_counters = plan.fused_reduce_ok ? 3 * p.tiles_mp * p.tiles_n * p.phases : 0;
   plan.macs = deconv ? (double)d.B * d.H * d.W * 16.0 * d.cin * d.cout
-                     : (double)d.B * Hg * Wg * (double)d.k * d.k * d.cin * d.cout;
+                     : (double)d.B * Hg * Wg * (d.slab == 2 ? 2.0 : 1.0) * (double)d.k * d.k * d.cin * d.cout;
   return OFS_OK;
 }
 
@@ -1815,8 +1834,30 @@ void conv_pack_weights(const ConvPlan& plan, const float* w, const float* bias, 
   out.assign((size_t)plan.w_rows * K, 0);
   b_padded.assign(p.n_pad, 0.0f);
   for (int n = 0; n < d.cout; ++n) b_padded[n] = bias ? bias[n] : 0.0f;
+  if (d.slab == 2) for (int n = 0; n < d.cout; ++n) b_padded[d.cout + n] = b_padded[n];
   auto cvt = [&](float f) { return d.is_bf16 ? f32_to_bf16_rn(f) : f32_to_fp16_rn(f); };
-  if (d.stack) {
+  if (d.slab == 2) {
+    // K blocks in group order: per ky the quads (q = -1, 0, +1) through elements e = 0, 1 and the quads (q = -1, 0) through
+    // e = 2, 3; element index inside a block = (e & 1) * 32 + ci.  GEMM row m covers input x = 4 (m + q) + e; output pixel
+    // 2m reads x = 4m + kx - 3 (kx = 4q + e + 3), pixel 2m+1 reads x = 4m + kx - 1 (kx = 4q + e + 1); taps outside [0,7)
+    // are zero rows (they cost MMA columns but no memory traffic worth mentioning).
+    size_t blk = 0;
+    for (int ky = 0; ky < d.k; ++ky)
+      for (int half = 0; half < 2; ++half)
+        for (int q = -1; q <= (half == 0 ? 1 : 0); ++q, ++blk)
+          for (int el = 0; el < 2; ++el) {
+            const int e = 2 * half + el;
+            for (int pix = 0; pix < 2; ++pix) {
+              const int kx = 4 * q + e + (pix == 0 ? 3 : 1);
+              if (kx < 0 || kx >= d.k) continue;
+              for (int ci = 0; ci < d.cin; ++ci) {
+                const float* src = w + (((size_t)ky * d.k + kx) * d.cin + ci) * d.cout;
+                const size_t kidx = blk * kBlockK + (size_t)el * 32 + ci;
+                for (int n = 0; n < d.cout; ++n) out[(size_t)(pix * d.cout + n) * K + kidx] = cvt(src[n]);
+              }
+            }
+          }
+  } else if (d.stack) {
     // rows in accumulator-column order per (tap, entry); K = the chunks of ONE tap.  Phase (py,px) reads tap (dy,dx)
     // with weight (ky,kx) = (py + 1 - 2 dy, px + 1 - 2 dx) when that lies in [0,4); the head reads every tap with
     // hw[dy+1][dx+1] -- real in the first head copy an entry of the tap covers, zero rows in any other.
@@ -1942,10 +1983,10 @@ int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const 
     st = encode_map(&p.tmap_o[0], 2, 5, workspace, od, os, ob);
     if (st != OFS_OK) return st;
   } else if (p.tma_store) {
-    const cuuint64_t cs = (cuuint64_t)d.out_cstride, sc = (cuuint64_t)p.out_scale;
+    const cuuint64_t cs = (cuuint64_t)p.out_cstride, sc = (cuuint64_t)p.out_scale;   // (two-pixel form: the pair view)
     for (int ph = 0; ph < p.phases; ++ph) {
       const size_t off = ((size_t)p.out_oy[ph] * p.out_W + p.out_ox[ph]) * cs + (size_t)d.out_coff;
-      cuuint64_t od[4] = {(cuuint64_t)d.cout, (cuuint64_t)p.Wg, (cuuint64_t)p.Hg, (cuuint64_t)d.B};
+      cuuint64_t od[4] = {(cuuint64_t)p.n_valid, (cuuint64_t)p.Wg, (cuuint64_t)p.Hg, (cuuint64_t)d.B};
       cuuint64_t os[3] = {sc * cs * 2, sc * (cuuint64_t)p.out_W * cs * 2, (cuuint64_t)p.out_H * p.out_W * cs * 2};
       cuuint32_t ob[4] = {(cuuint32_t)kBlockK, tileW, (cuuint32_t)p.box_y, (cuuint32_t)p.box_b};
       st = encode_map(&p.tmap_o[ph], d.is_bf16, 4, reinterpret_cast<uint16_t*>(out) + off, od, os, ob);
@@ -2062,13 +2103,14 @@ extern "C" int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const flo
   d.block_n = block_n > 0 ? block_n : (Cout >= 128 ? 128 : (Cout >= 64 ? 64 : (Cout >= 32 ? 32 : 16)));
   d.ksplit = ksplit > 1 ? ksplit : 1;
   d.cta_group = (cta_group == 2 || cta_group == 4) ? 2 : 1;
-  d.slab = cta_group == 4 ? 1 : 0;   // 4 = CTA pairs + slab groups
+  d.slab = cta_group == 4 ? 1 : cta_group == 5 ? 2 : 0;   // 4 = CTA pairs + slab groups; 5 = the same with two output pixels per GEMM row
+  if (cta_group == 5) { d.cta_group = 2; d.block_n = 128; }
   d.kgroup = cta_group == 8 ? 2 : cta_group == 32 ? 4 : 1; // 8 / 32 = two / four K chunks per pipeline stage
   d.kcluster = cta_group == 16 ? 1 : 0;   // 16 = split-K inside a thread-block cluster (DSMEM reduction)
   if (cta_group == 64 || cta_group == 66) {   // 64 / 66 = phase-stacked transposed conv on 1 CTA / CTA pairs (head weights zero)
     d.stack = 1; d.head = 1; d.cta_group = cta_group == 66 ? 2 : 1; d.block_n = 64;
   }
-  const bool via16 = d.ksplit > 1 || out16 || d.stack;   // the network's 16-bit activation epilogue (split-K always reduces into it)
+  const bool via16 = d.ksplit > 1 || out16 || d.stack || d.slab == 2;   // the network's 16-bit activation epilogue (split-K always reduces into it)
   const int cout8 = ((Cout + 7) / 8) * 8;
   d.out_mode = via16 ? 0 : 1; d.lrelu = lrelu; d.is_bf16 = is_bf16;
   d.out_cstride = via16 ? cout8 : Cout; d.out_coff = 0;
@@ -2097,7 +2139,7 @@ extern "C" int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const flo
   float *b_dev = nullptr, *ws = nullptr, *hd = nullptr;
   unsigned* cnt = nullptr;
   const size_t npix = (size_t)B * H * W;
-  const size_t npix_out = (size_t)B * plan.p.out_H * plan.p.out_W;
+  const size_t npix_out = (size_t)B * plan.p.out_H * plan.p.out_W * (d.slab == 2 ? 2 : 1);
   auto cleanup = [&]() {
     if (cnt) cudaFree(cnt);
     if (hd) cudaFree(hd);
@@ -2172,7 +2214,7 @@ extern "C" int ofs_conv2d_bench(int B, int H, int W, int Cin, int in_cs, int Cou
   ConvDesc d;
   d.kind = transposed ? kDeconvK4S2 : kConv;
   d.B = B; d.H = H; d.W = W; d.cin = Cin; d.in_cs = in_cs; d.cout = Cout; d.k = k; d.stride = stride;
-  d.block_n = block_n; d.ksplit = ksplit > 1 ? ksplit : 1; d.cta_group = (cta_group == 2 || cta_group == 4) ? 2 : 1; d.slab = cta_group == 4 ? 1 : 0; d.kgroup = cta_group == 8 ? 2 : cta_group == 32 ? 4 : 1; d.debug = debug;
+  d.block_n = block_n; d.ksplit = ksplit > 1 ? ksplit : 1; d.cta_group = (cta_group == 2 || cta_group == 4 || cta_group == 5) ? 2 : 1; d.slab = cta_group == 4 ? 1 : cta_group == 5 ? 2 : 0; d.kgroup = cta_group == 8 ? 2 : cta_group == 32 ? 4 : 1; d.debug = debug;
   d.kcluster = cta_group == 16 ? 1 : 0;
   if (cta_group == 64 || cta_group == 66) { d.stack = 1; d.head = 1; d.cta_group = cta_group == 66 ? 2 : 1; }
   if (cta_group == 34 || cta_group == 36) { d.head = 1; d.cta_group = cta_group == 36 ? 2 : 1; }   // per-phase form with the fused head
@@ -2181,7 +2223,7 @@ extern "C" int ofs_conv2d_bench(int B, int H, int W, int Cin, int in_cs, int Cou
   ConvPlan plan;
   rc = conv_plan_geometry(plan, d);
   if (rc != OFS_OK) return rc;
-  const size_t npix = (size_t)B * H * W, npix_out = (size_t)B * plan.p.out_H * plan.p.out_W;
+  const size_t npix = (size_t)B * H * W, npix_out = (size_t)B * plan.p.out_H * plan.p.out_W * (d.slab == 2 ? 2 : 1);
   const size_t w_elems = (size_t)plan.w_rows * plan.k_total;
   void *x16 = nullptr, *w_dev = nullptr, *y = nullptr, *fl = nullptr;
   float *b_dev = nullptr, *ws = nullptr, *hd = nullptr;
@@ -2323,7 +2365,8 @@ extern "C" int ofs_debug_conv_plan_ex(int kind, int B, int H, int W, int cin, in
   d.B = B; d.H = H; d.W = W; d.cin = cin; d.in_cs = in_cs; d.cout = cout; d.k = k; d.stride = stride;
   d.block_n = block_n; d.out_mode = 0; d.lrelu = 0; d.is_bf16 = is_bf16; d.out_cstride = ((cout + 7) / 8) * 8; d.out_coff = 0;
   d.slab = flags & 1; d.head = (flags >> 1) & 1; d.cta_group = (flags & 1) ? 2 : 1;
-  if (flags & 4) { d.stack = 1; d.head = 1; }   // bit2: phase-stacked transposed conv (packed rows: see stk_row / stk_col)
+  if (flags & 4) { d.stack = 1; d.head = 1; }
+  if (flags & 8) { d.slab = 2; d.cta_group = 2; d.out_cstride = cout; }   // bit3: slab groups with two output pixels per GEMM row   // bit2: phase-stacked transposed conv (packed rows: see stk_row / stk_col)
   ConvPlan plan;
   int rc = conv_plan_geometry(plan, d);
   if (rc != OFS_OK) return rc;

@@ -20,12 +20,14 @@ def shard_range(n_items: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_output(local: torch.Tensor, n_items: int, group=None, dst=None):
+def gather_output(local: torch.Tensor, n_items: int, group=None, dst=None, out=None):
     """Collects the per-rank output frames [n_local, H, W, C] of a split clip (or of a set of clips laid end to end) into
     [n_items, H, W, C] in pair order: on every rank (`dst=None`, all_gather) or on rank `dst` only (the other ranks
     return None).  NCCL for CUDA tensors, gloo for CPU tensors; any dtype -- send the np.uint8 frames the video writer
     consumes (2.76 MB per 720p frame) rather than float32 (11.06 MB).  Ranks may own different counts (shard_range);
-    shards are padded to the largest count for the collective and trimmed afterwards."""
+    shards are padded to the largest count for the collective and trimmed afterwards.  `out`: optional preallocated
+    receive buffer [world * max_count, H, W, C] on the receiving rank(s) (a 1024-frame 720p clip set is tens of GB: allocate
+    it once, outside the loop that calls this)."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()):
@@ -46,11 +48,19 @@ def gather_output(local: torch.Tensor, n_items: int, group=None, dst=None):
         padded = torch.cat([local, local.new_zeros((nmax - local.shape[0],) + tuple(local.shape[1:]))], 0)
     padded = padded.contiguous()
     even = all(h - l == nmax for l, h in counts)
+    full_shape = (world * nmax,) + tuple(local.shape[1:])
+    if out is not None and (tuple(out.shape) != full_shape or out.dtype != local.dtype or out.device != local.device
+                            or not out.is_contiguous()):
+        raise ValueError(f"out must be a contiguous {local.dtype} tensor of shape {full_shape} on {local.device}")
     if dst is None:
-        out = local.new_empty((world * nmax,) + tuple(local.shape[1:]))
+        if out is None:
+            out = local.new_empty(full_shape)
         dist.all_gather_into_tensor(out, padded, group=group)      # one flat receive buffer: no per-rank list, no concat
     else:
-        out = local.new_empty((world * nmax,) + tuple(local.shape[1:])) if rank == dst else None
+        if rank != dst:
+            out = None
+        elif out is None:
+            out = local.new_empty(full_shape)
         parts = list(out.view((world, nmax) + tuple(local.shape[1:])).unbind(0)) if rank == dst else None
         dist.gather(padded, parts, dst=dst, group=group)
         if rank != dst:

@@ -189,7 +189,7 @@ def _accumulate(plan, act, out, written):
 
 # ---------------------------------------------------------------------------------------------------------------
 # slab groups (conv1 / conv2) and the fused flow head (deconvs): same idea through ofs_debug_conv_plan_ex
-def get_plan_ex(lib, kind, B, H, W, cin, in_cs, cout, k, stride, block_n, w_tf, bias, slab=False, head_w=None, stack=False):
+def get_plan_ex(lib, kind, B, H, W, cin, in_cs, cout, k, stride, block_n, w_tf, bias, slab=False, head_w=None, stack=False, slab2=False):
     info = (C.c_int * 48)()
     taps = (C.c_short * 256)()
     grp = (C.c_short * 320)()
@@ -199,7 +199,7 @@ def get_plan_ex(lib, kind, B, H, W, cin, in_cs, cout, k, stride, block_n, w_tf, 
     w_tf = np.ascontiguousarray(w_tf, np.float32)
     bias = np.ascontiguousarray(bias, np.float32)
     hw = None if head_w is None else np.ascontiguousarray(head_w, np.float32)
-    flags = (1 if slab else 0) | (2 if head_w is not None else 0) | (4 if stack else 0)
+    flags = (1 if (slab or slab2) else 0) | (2 if head_w is not None else 0) | (4 if stack else 0) | (8 if slab2 else 0)
     rc = lib.ofs_debug_conv_plan_ex(kind, B, H, W, cin, in_cs, cout, k, stride, block_n, 1, flags,
                                     w_tf.ctypes.data_as(C.c_void_p), bias.ctypes.data_as(C.c_void_p),
                                     None if hw is None else hw.ctypes.data_as(C.c_void_p), C.cast(info, C.c_void_p),
@@ -216,7 +216,7 @@ def get_plan_ex(lib, kind, B, H, W, cin, in_cs, cout, k, stride, block_n, w_tf, 
     d["w"] = bf16_bits_to_f32(wbuf[: d["w_rows"] * d["k_total"]]).reshape(d["w_rows"], d["k_total"])
     d["b"] = bbuf[: d["n_pad"]].copy()
     d["block_n"] = block_n
-    d["slab"] = bool(slab)
+    d["slab"] = bool(slab or slab2)
     d["head"] = head_w is not None
     return d
 

@@ -127,6 +127,10 @@ TILING_CASES = [
     pytest.param(3, 12, 16, 130, 64, 4, 2, True, 64, -1, 66, id="stack_pairs_odd_tile_count"),
     pytest.param(3, 6, 8, 64, 64, 4, 2, True, 64, -1, 66, id="stack_pairs_whole_image_tiles"),
     pytest.param(2, 48, 64, 200, 64, 4, 2, True, 64, -1, 66, id="stack_pairs_two_row_tiles_many"),
+    # conv1 form with two output pixels per GEMM row (cta_group = 5: CTA pairs, quad view, 128 accumulator columns)
+    pytest.param(1, 32, 512, 27, 64, 7, 2, False, 128, -1, 5, id="slab2_conv1_two_pixel_form"),
+    pytest.param(2, 16, 1024, 27, 64, 7, 2, False, 128, -1, 5, id="slab2_two_x_tiles"),
+    pytest.param(1, 6, 512, 27, 64, 7, 2, False, 128, -1, 5, id="slab2_odd_tile_count"),
     # tail split: > 148 M tiles of 256 columns, the last wave runs as half tiles on twice as many CTAs
     pytest.param(7, 48, 64, 64, 256, 3, 1, False, 256, -1, 1, id="tail_half_168_tiles"),
     pytest.param(7, 48, 64, 64, 256, 3, 1, False, 256, -1, 2, id="tail_half_pairs_84_pair_tiles"),

@@ -180,6 +180,26 @@ def test_fused_head_plan_emulation_matches_oracle(lib, B, H, W, cin, in_cs, cout
     np.testing.assert_allclose(head, href.numpy(), rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("B,H,W", [(1, 8, 512), (2, 6, 1024)], ids=["one_x_tile", "two_x_tiles_two_images"])
+def test_two_pixel_slab_plan_emulation_matches_oracle(lib, B, H, W):
+    """conv1 form with two output pixels per GEMM row (quad view of the 32-channel input, 5 quad taps per kernel row,
+    [pixel 2m | pixel 2m+1] accumulator columns): the emulated tiles, read back as [B, H/2, W/2, 64], equal the oracle."""
+    rng = np.random.RandomState(23)
+    cin, in_cs, cout, k = 27, 32, 64, 7
+    x = emu.bf16_round(rng.rand(B, H, W, cin).astype(np.float32))
+    w = emu.bf16_round(rng.randn(k, k, cin, cout).astype(np.float32) * 0.1)
+    b = rng.randn(cout).astype(np.float32)
+    plan = emu.get_plan_ex(lib, 0, B, H, W, cin, in_cs, cout, k, 2, 128, w, b, slab2=True)
+    assert plan["n_pad"] == 128 and plan["Wg"] == W // 4 and plan["ntaps"] == 14 and plan["k_total"] == 35 * 64
+    act = np.zeros((B, H, W, in_cs), np.float32)
+    act[..., :cin] = x
+    got, _ = emu.emulate_ex(plan, act)                       # [B, H/2, W/4, 128]
+    got = got.reshape(B, H // 2, W // 2, cout)               # the same memory as NHWC [B, H/2, W/2, 64]
+    ref = T.conv2d_valid(T.pad_constant(torch.from_numpy(x).double(), k // 2), torch.from_numpy(w).double(),
+                         torch.from_numpy(b).double(), 2)
+    np.testing.assert_allclose(got, ref.numpy(), rtol=1e-5, atol=1e-5)
+
+
 @pytest.mark.parametrize("B,H,W,cin,in_cs", [(2, 6, 8, 70, 72), (1, 12, 16, 130, 136), (1, 24, 32, 64, 64)],
                          ids=["whole_image_tiles", "three_chunks_two_pieces", "four_row_tiles"])
 def test_stacked_deconv_plan_emulation_matches_oracle(lib, B, H, W, cin, in_cs):
