@@ -711,10 +711,11 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
   for (Layer& L : Ls) {
     if ((L.name == "1" || L.name == "2") && !(getenv("OFS_NOSLAB") && getenv("OFS_NOSLAB")[0] == '1')) {
       L.d.slab = 1; L.d.cta_group = 2;   // x-shifted taps share one A slab per stage (CTA pairs); fixes the packed K order
-      // conv1 (cout 64): two output pixels per GEMM row -> 128-column MMAs over 5 quad taps per kernel row instead of
-      // 64-column MMAs over 2 x 4 pair taps (the narrow MMAs run at half the math rate: shared-memory operand bound).
-      // OFS_CONV1X2=0: the one-pixel form (A/B).
-      if (L.name == "1" && !(getenv("OFS_CONV1X2") && getenv("OFS_CONV1X2")[0] == '0')) { L.d.slab = 2; L.d.block_n = 128; }
+      // conv1 with two output pixels per GEMM row (quad view, 128-column MMAs over 5 quad taps per kernel row instead of
+      // 64-column MMAs over 2 x 4 pair taps): built and tested, -6 % cycles but the zero-weight halves of the two edge taps
+      // cost power -- under the 1 kW cap the clock drops by as much (79.5 vs 74.6 us alone, profiles/r02_tuning.md).
+      // OFS_CONV1X2=1 selects it.
+      if (L.name == "1" && getenv("OFS_CONV1X2") && getenv("OFS_CONV1X2")[0] == '1') { L.d.slab = 2; L.d.block_n = 128; }
     } else if (L.name == "3") { L.block_n_run = 256; L.cta_group = 2; }   // CTA pairs: 36.9 vs 40.3 us (conv_bench)
     else if (L.name == "3_1") { L.block_n_run = 256; }
     // cout 512 on 48 M tiles: 3 N tiles of 192 (the last one a third empty, clipped by the TMA store) = 144 tiles, ONE
