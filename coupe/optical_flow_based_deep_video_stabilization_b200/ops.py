@@ -99,7 +99,9 @@ def conv2d_nhwc(x, w, b=None, stride=1, transposed=False, lrelu=False, precision
     block_n: N tile (0 = automatic); ksplit > 1: split-K (the result then carries one 16-bit rounding, as in the
     network); cta_group: 1 single CTAs, 2 CTA pairs (tcgen05 cta_group::2), 4 pairs + slab groups (conv1 / conv2 form),
     8 / 32 two / four K chunks per pipeline stage, 16 split-K inside a thread-block cluster (DSMEM reduction, same bits
-    as the workspace split-K); out16: the network's 16-bit TMA-store epilogue, widened to f32 afterwards.
+    as the workspace split-K), 5 pairs + slab groups with two output pixels per GEMM row (conv1 form, block_n 128), 64 / 66
+    the phase-stacked transposed conv (cout 64) on single CTAs / CTA pairs; out16: the network's 16-bit TMA-store
+    epilogue, widened to f32 afterwards.
     """
     x = _cuda_f32(x, "x")
     w = w.detach().to("cpu", torch.float32).contiguous()

@@ -235,7 +235,9 @@ int ofs_conv2d_nhwc(const float* x, const float* w_host, const float* b_host, fl
  * carries one 16-bit rounding, exactly as the network's split-K layers do) and cta_group (1, or 2 = CTA
  * pairs: tcgen05 cta_group::2, 256-row tiles, weight tile split over the pair; needs block_n >= 32;
  * 4 = pairs + slab groups, 8 / 32 = two / four K chunks per stage, 16 = split-K inside a thread-block cluster of
- * ksplit <= 8 CTAs reduced through distributed shared memory, block_n 256 -- same bits as the workspace path).
+ * ksplit <= 8 CTAs reduced through distributed shared memory, block_n 256 -- same bits as the workspace path;
+ * 5 = pairs + slab groups with two output pixels per GEMM row (the k7 s2 conv1 form, block_n 128); 64 / 66 = the
+ * phase-stacked transposed conv (Cout 64, fused head columns with zero head weights) on single CTAs / CTA pairs).
  * out16 = 1 runs the network's 16-bit activation epilogue (shared-memory staging + TMA stores when
  * block_n >= 64; needs Cout % block_n == 0) and widens the result to fp32 afterwards. */
 int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const float* b_host, float* y, int B, int H, int W,

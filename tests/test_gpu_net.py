@@ -285,6 +285,29 @@ def test_network_he_init_relative_epe(ofs, cuda_dev):
     net.close()
 
 
+def test_precision_options_report(ofs, cuda_dev):
+    """the operand precision is a per-net option.  Reports mean EPE(predict_flow2) against the fp32 oracle for
+    bf16 and fp16 operands on the calibrated set (|flow2| ~ 1.8 px, the regime of a trained stabiliser) and on the
+    reference's own initialisers (|flow2| ~ 90 px), and pins what each buys: fp16 operands (same tensor rate, 3 more
+    mantissa bits) hold the calibrated set with a 4x margin under 2e-2 px and cut the He-init error several-fold."""
+    res = {}
+    for wname, w, seed in (("calibrated", F.make_weights(0, "calibrated", head_scale=0.02), 2), ("he", F.make_weights(0, "he"), 6)):
+        x = F.make_feats(seed, 1)
+        ref = F.forward_literal(x, w)["predict_flow2"]
+        mag = float(torch.sqrt((ref ** 2).sum(-1)).mean())
+        for prec in ("bf16", "fp16"):
+            net = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=1, precision=prec)
+            net.assign_weights(w)
+            e = F.epe(net.forward(x.to(cuda_dev))["predict_flow2"].cpu(), ref)
+            net.close()
+            res[(wname, prec)] = (e, mag)
+            print(f"{wname:10s} {prec}: EPE = {e:.5f} px, |flow2| = {mag:.2f} px, EPE/|flow| = {e / mag:.4%}")
+    assert res[("calibrated", "bf16")][0] <= 2e-2
+    assert res[("calibrated", "fp16")][0] <= 5e-3
+    assert res[("he", "fp16")][0] <= 0.5 * res[("he", "bf16")][0]
+    assert res[("he", "fp16")][0] / res[("he", "fp16")][1] <= 3e-3
+
+
 def test_batch_independence_and_determinism(net_case, cuda_dev):
     """Frame pairs are independent units: a pair's result must not depend on its batch neighbours."""
     w, x, net, out = net_case
