@@ -56,7 +56,7 @@ def launch_shares():
         stot += float(d["Metric Value"]) / 1e3
     for k, (n, t) in sorted(step.items(), key=lambda kv: -kv[1][1]):
         out.append(f"| `{k}` | {n} | {t:.1f} | {100 * t / stot:.1f}% |")
-    dense = sum(t for k, (n, t) in step.items() if ("conv_gemm" in k and "<32>" not in k) or "splitk" in k)
+    dense = sum(t for k, (n, t) in step.items() if ("conv_gemm" in k and "<32," not in k) or "deconv_stack" in k or "splitk" in k)
     warp = sum(t for k, (n, t) in step.items() if k.startswith("warp5"))
     out += ["", f"One step under ncu: {stot:.0f} us in {end + 1 - start} launches; dense conv / deconv GEMMs incl. split-K reductions "
             f"{100 * dense / stot:.1f} % (bench.py live: roofline.share_of_step), fused warp {100 * warp / stot:.1f} % "
@@ -74,7 +74,7 @@ def raw(rep):
 
 
 def full_summary():
-    labels = ["conv1 (slab, pairs, two pixels per row)", "conv2 (slab, pairs)", "conv3 (pairs)", "conv3_1", "conv4 (192, pairs)", "conv4_1 (192)",
+    labels = ["conv1 (slab, pairs)", "conv2 (slab, pairs)", "conv3 (pairs)", "conv3_1", "conv4 (192, pairs)", "conv4_1 (192)",
               "conv5 (split-K 6)", "conv5 reduce", "conv5_1 (split-K 6)", "conv5_1 reduce", "conv6 (split-K 8)", "conv6 reduce",
               "conv6_1 (split-K 8)", "conv6_1 reduce", "deconv5 + predict6 (pairs)", "deconv4 + predict5 (pairs)",
               "deconv3 + predict4 (pairs)", "deconv2 + predict3 (stacked, pairs)", "predict2 1x1 product"]

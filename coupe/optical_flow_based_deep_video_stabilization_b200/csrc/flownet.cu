@@ -214,6 +214,144 @@ __global__ void __launch_bounds__(256) predict2_gather_kernel(Predict2Params p) 
   }
 }
 
+
+// model.py:882-887 in ONE kernel: the 1x1 product (18 dot products of 194 channels per source pixel of concat2) on
+// mma.sync tensor cores straight into shared memory, and the 9-tap gather through the NN index maps + 8 x up(f3) out of
+// it -- no 7 MB product tensor, no second launch.  A block owns a 4 x 32 tile of the 96 x 128 source grid plus the row /
+// column after it (every output pixel's three taps per axis fall on its first tap's source row / column or the next one:
+// the NN scale is ~1/3.95), i.e. 5 x 33 = 165 source pixels = 11 m16 tiles, one per warp; it writes the output pixels
+// whose FIRST tap lands in its 4 x 32 interior (row / column ranges from two small host tables).
+// The sum per output pixel has the terms and the order of predict2_gather_kernel (bias, then ky-major taps; a tap on the
+// zero padding adds +0.0f instead of being skipped: the same value).
+struct P2FusedParams {
+  const uint16_t* concat2;  // [B,96,128,200] 16-bit
+  const uint16_t* w;        // packed predict2 product weights [32 rows][256] K-major; row (ky*3+kx)*2 + o
+  const float2* f3;         // [B,48,64]
+  float2* f2;               // [B,382,510]
+  float2* f2s;              // [B,382,510]: (f2 * 384.0) / 382
+  float bias0, bias1;
+  float hs, ws;             // bilinear scales 48/382, 64/510 in fp32
+  const short* iy_tab;      // [384] NN source row - 1 of padded row r (-1 / 96: padding)
+  const short* ix_tab;      // [512]
+  const short* oy_start;    // [25] first output row whose first tap falls in source rows >= 4 i  ([24] = 382)
+  const short* ox_start;    // [5]  same for 32-column source tiles ([4] = 510)
+  int is_bf16;
+};
+constexpr int kP2RegionW = 33, kP2Region = 5 * kP2RegionW, kP2Threads = 352, kP2WStride = 216, kP2PStride = 24;
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, int is_bf16) {
+  if (is_bf16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(kP2Threads) predict2_fused_kernel(P2FusedParams p) {
+  __shared__ __align__(16) uint16_t Ws[24 * kP2WStride];
+  __shared__ __align__(16) float Ps[176 * kP2PStride];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * 4, c0 = blockIdx.x * 32;
+  // ---- weights: 24 rows (18 real) x 208 K (194 real) of the packed [32][256] K-major matrix
+  {
+    const uint32_t* __restrict__ wsrc = reinterpret_cast<const uint32_t*>(p.w);
+    uint32_t* wdst = reinterpret_cast<uint32_t*>(Ws);
+    for (int i = threadIdx.x; i < 24 * 104; i += kP2Threads) {
+      const int n = i / 104, k2 = i - n * 104;
+      wdst[n * (kP2WStride / 2) + k2] = __ldg(wsrc + n * 128 + k2);
+    }
+  }
+  __syncthreads();
+  // ---- product: warp w computes region pixels [16 w, 16 w + 16) x 24 columns over K = 208
+  {
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t* rowp[2];
+    bool valid[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int pp = warp * 16 + g + 8 * h;
+      const int rr = pp / kP2RegionW, cc = pp - rr * kP2RegionW;
+      const int sr = r0 + rr, sc = c0 + cc;
+      valid[h] = pp < kP2Region && sr < 96 && sc < 128;
+      rowp[h] = reinterpret_cast<const uint32_t*>(p.concat2 + ((size_t)(b * 96 + min(sr, 95)) * 128 + min(sc, 127)) * 200);
+    }
+    float acc[3][4] = {};
+    const uint32_t* Ws32 = reinterpret_cast<const uint32_t*>(Ws);
+#pragma unroll
+    for (int ks = 0; ks < 13; ++ks) {
+      // words of this k16 step: element 2t (+1) -> word 8 ks + t, element 2t + 8 (+9) -> word 8 ks + t + 4; the last step's
+      // second half (elements 200..207) lies past the 200-element pixel row: re-read the first half (its weights are zero)
+      const int w0 = 8 * ks + t, w1 = ks == 12 ? w0 : w0 + 4;
+      uint32_t a[4];
+      a[0] = __ldg(rowp[0] + w0); a[1] = __ldg(rowp[1] + w0); a[2] = __ldg(rowp[0] + w1); a[3] = __ldg(rowp[1] + w1);
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        const uint32_t* wr = Ws32 + (nt * 8 + g) * (kP2WStride / 2) + 8 * ks + t;
+        mma16816(acc[nt], a, wr[0], wr[4], p.is_bf16);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int pp = warp * 16 + g + 8 * h;
+      float* dst = Ps + pp * kP2PStride + 2 * t;
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        const float v0 = valid[h] ? acc[nt][2 * h] : 0.0f, v1 = valid[h] ? acc[nt][2 * h + 1] : 0.0f;
+        *reinterpret_cast<float2*>(dst + nt * 8) = make_float2(v0, v1);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- gather: output pixels whose first tap lands in source rows [r0, r0 + 4) x columns [c0, c0 + 32)
+  const int oy_lo = p.oy_start[blockIdx.y], oy_hi = p.oy_start[blockIdx.y + 1];
+  const int ox_lo = p.ox_start[blockIdx.x], ox_hi = p.ox_start[blockIdx.x + 1];
+  const int ncols = ox_hi - ox_lo, total = (oy_hi - oy_lo) * ncols;
+  const float2* __restrict__ f3b = p.f3 + (size_t)b * 48 * 64;
+  for (int idx = threadIdx.x; idx < total; idx += kP2Threads) {
+    const int dy = idx / ncols;
+    const int oy = oy_lo + dy, ox = ox_lo + (idx - dy * ncols);
+    float a0 = p.bias0, a1 = p.bias1;
+    int lc[3];
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int v = (int)p.ix_tab[ox + kx];
+      lc[kx] = v < 0 ? -1 : (v - c0) * kP2PStride + kx * 2;    // v - c0 in [0, 32]: column 128 is a zeroed region column
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int v = (int)p.iy_tab[oy + ky];
+      if (v < 0) continue;
+      const int rbase = (v - r0) * kP2RegionW * kP2PStride + ky * 6;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        if (lc[kx] < 0) continue;
+        const float2 pv = *reinterpret_cast<const float2*>(Ps + rbase + lc[kx]);
+        a0 += pv.x;
+        a1 += pv.y;
+      }
+    }
+    const float fy = (float)oy * p.hs;
+    const int y0 = (int)floorf(fy), y1 = min(y0 + 1, 47);
+    const float yl = fy - (float)y0;
+    const float fx = (float)ox * p.ws;
+    const int x0 = (int)floorf(fx), x1 = min(x0 + 1, 63);
+    const float xl = fx - (float)x0;
+    const float2 tl = f3b[y0 * 64 + x0], tr = f3b[y0 * 64 + x1], bl = f3b[y1 * 64 + x0], br = f3b[y1 * 64 + x1];
+    const float topx = tl.x + (tr.x - tl.x) * xl, topy = tl.y + (tr.y - tl.y) * xl;
+    const float botx = bl.x + (br.x - bl.x) * xl, boty = bl.y + (br.y - bl.y) * xl;
+    const float ux = topx + (botx - topx) * yl, uy = topy + (boty - topy) * yl;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a0 += ux; a1 += uy; }  // ElementwiseLayer left fold, model.py:887
+    const int o = (b * 382 + oy) * 510 + ox;
+    p.f2[o] = make_float2(a0, a1);
+    p.f2s[o] = make_float2(__fdiv_rn(a0 * 384.0f, 382.0f), __fdiv_rn(a1 * 384.0f, 382.0f));
+  }
+}
+
 // Flow heads predict6..predict3 (model.py:847-848,855-856,864-865,873-874: zero-pad 1 + 3x3 conv to 2 channels +
 // bias) read the same input as the level's transposed conv, and the 4 sub-pixel phases of that conv together visit
 // exactly the head's 9 taps.  Each head is therefore FUSED into its level's deconv GEMM as 16 extra accumulator
@@ -264,6 +402,8 @@ struct ofs_net {
   float* f2s = nullptr;  // pre-scaled flow2 for the fused flow-resize + warp
   float* upw = nullptr;  // 4 x (64 + 2) floats: upsample6_5, 5_4, 4_3, 3_2
   short* nn_tab = nullptr;  // predict2: NN align_corners source index tables, 384 rows then 512 columns (value - 1)
+  short* p2_tab = nullptr;  // predict2_fused_kernel: first output row / column per source tile row (25) / column (5)
+  int p2_fused = 1;         // 1: predict2 product + gather in one kernel (OFS_P2_FUSED=0: 1x1 GEMM + predict2_gather_kernel)
   float p2_bias[2] = {0, 0};
   std::vector<Layer> layers;
   std::vector<Head> heads;   // predict6, predict5, predict4, predict3
@@ -571,6 +711,7 @@ int forward_impl(ofs_net* n, const float* feats, int B, float* f2_target, cudaSt
   }
   OFS_MARK("pack_input", 0.0);
   for (Layer& L : n->layers) {
+    if (n->p2_fused && L.name == "predict2") continue;   // product + gather run as one kernel below
     int lvl = 0;
     if (L.name == "deconv5") lvl = 6;
     else if (L.name == "deconv4") lvl = 5;
@@ -585,6 +726,25 @@ int forward_impl(ofs_net* n, const float* feats, int B, float* f2_target, cudaSt
       if (rc != OFS_OK) return rc;
       OFS_MARK("pyramid:level" + std::to_string(lvl), 0.0);
     }
+  }
+  if (n->p2_fused) {
+    P2FusedParams fp;
+    fp.concat2 = reinterpret_cast<const uint16_t*>(n->concat2);
+    fp.w = nullptr;
+    for (const Layer& L : n->layers) if (L.name == "predict2") fp.w = reinterpret_cast<const uint16_t*>(L.w_dev);
+    fp.f3 = reinterpret_cast<const float2*>(n->f[3]);
+    fp.f2 = reinterpret_cast<float2*>(f2_target ? f2_target : n->f[2]);
+    fp.f2s = reinterpret_cast<float2*>(n->f2s);
+    fp.bias0 = n->p2_bias[0]; fp.bias1 = n->p2_bias[1];
+    fp.hs = 48.0f / 382.0f; fp.ws = 64.0f / 510.0f;
+    fp.iy_tab = n->nn_tab; fp.ix_tab = n->nn_tab + 384;
+    fp.oy_start = n->p2_tab; fp.ox_start = n->p2_tab + 25;
+    fp.is_bf16 = n->is_bf16;
+    OFS_REQUIRE(fp.w, "internal: predict2 weights missing");
+    OFS_CUDA(launch_pdl(predict2_fused_kernel, dim3(4, 24, (unsigned)B), dim3(kP2Threads), 0, st, fp));
+    OFS_LAUNCH_CHECK();
+    OFS_MARK("predict2_fused", (double)B * 96 * 128 * 194 * 18);
+    return OFS_OK;
   }
   Predict2Params pp;
   pp.P = n->P2;
@@ -642,6 +802,7 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
   ofs_net* n = new ofs_net();
   n->device = device; n->max_batch = max_batch; n->is_bf16 = precision == OFS_PREC_BF16;
   { const char* e = getenv("OFS_GRAPH"); n->use_graphs = (e && e[0] == '0') ? 0 : 1; }
+  { const char* e = getenv("OFS_P2_FUSED"); n->p2_fused = (e && e[0] == '0') ? 0 : 1; }
   const size_t B = (size_t)max_batch;
   struct { void** p; size_t elems; } bufs[] = {
       {&n->x0, B * 384 * 512 * 32},    {&n->conv1, B * 192 * 256 * 64}, {&n->concat2, B * 96 * 128 * 200},
@@ -670,6 +831,15 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
     for (int r = 0; r < 384; ++r) { const float v = (float)r * sy; tab[r] = (short)(std::min((int)roundf(v), 97) - 1); }
     for (int c = 0; c < 512; ++c) { const float v = (float)c * sx; tab[384 + c] = (short)(std::min((int)roundf(v), 129) - 1); }
     rc = check_cuda(cudaMemcpy(n->nn_tab, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice), "nn_tab upload", __FILE__, __LINE__);
+    // predict2_fused_kernel: tile (i, j) of the source grid (4 rows x 32 columns) writes the output rows / columns whose
+    // FIRST tap lands in it (the tables are non-decreasing; rows / columns on the top / left padding go to tile 0)
+    std::vector<short> st(32, 0);
+    for (int i = 1; i < 24; ++i) { int oy = 0; while (oy < 382 && tab[oy] < 4 * i) ++oy; st[i] = (short)oy; }
+    st[24] = 382;
+    for (int j = 1; j < 4; ++j) { int ox = 0; while (ox < 510 && tab[384 + ox] < 32 * j) ++ox; st[25 + j] = (short)ox; }
+    st[25] = 0; st[29] = 510;
+    if (rc == OFS_OK) rc = dev_alloc(n, (void**)&n->p2_tab, 32 * 2, true);
+    if (rc == OFS_OK) rc = check_cuda(cudaMemcpy(n->p2_tab, st.data(), 32 * 2, cudaMemcpyHostToDevice), "p2_tab upload", __FILE__, __LINE__);
   }
   if (rc == OFS_OK) rc = dev_alloc(n, (void**)&n->st_feats, B * kNetH * kNetW * kNetC * 4, false);
   if (rc != OFS_OK) { ofs_net_destroy(n); return rc; }
@@ -1157,6 +1327,7 @@ int ofs_net_time_kernels(ofs_net* n, int which, const float* frames, float* out,
 int ofs_net_launches_per_forward(const ofs_net* n) {
   if (!n) return 0;
   int k = 1 + (int)n->layers.size() + 4 + 1;  // pack + GEMMs (heads ride in the deconvs) + pyramid steps + gather
+  if (n->p2_fused) --k;                       // predict2: product and gather are one kernel
   for (const Layer& L : n->layers) k += (L.plan.p.ksplit > 1 && !L.plan.p.fused_reduce) ? 1 : 0;  // separate split-K reductions (after prepare())
   return k;
 }
