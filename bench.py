@@ -428,9 +428,11 @@ def run_ours(args):
                                          f"on {nstreams} CUDA streams"},
             "sustained": sustained,
             "value_one_step_at_a_time": (world * BATCH * args.steps / (single_ms * 1e-3)) if single_ms else None,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hf.numel() * 4 + hfr.numel() * 4),
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(lib.ofs_net_host_h2d_bytes(net._h, BATCH, FRAME_H, FRAME_W)),
                     "d2h_bytes_per_step": int(hout.numel() * 4), "steps": e2e_steps,
-                    "api": f"ofs_net_stabilize_host (C ABI, pinned host float32 buffers), {nstreams} concurrent caller thread(s)"},
+                    "host_buffer_bytes_per_step": int(hf.numel() * 4 + hfr.numel() * 4),
+                    "api": f"ofs_net_stabilize_host (C ABI, pinned host float32 buffers in and out), {nstreams} concurrent caller thread(s)"},
             "e2e_clip_driver": {"value": clip_value, "unit": UNIT, "h2d_bytes_per_step": int(u8.nbytes), "d2h_bytes_per_step": int(u8.nbytes),
                                 "steps": clip_steps, "api": "ofs_clips_submit_host / ofs_clips_wait (uint8 BGR frames in / out, device-side history ring, up to 3 steps in flight; "
                                 f"one iteration of main_dl.py:540-630 per clip per step, pinned host buffers), {nstreams} clip set(s) of {BATCH} "

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "ofs_net_forward": (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _p]),
     "ofs_net_stabilize": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "ofs_net_stabilize_host": (_i, [_p, _p, _p, _p, _i, _i, _i]),
+    "ofs_net_host_h2d_bytes": (_ll, [_p, _i, _i, _i]),
     "ofs_net_get_activation": (_i, [_p, C.c_char_p, _i, _p, C.c_int64, C.POINTER(_i), _p]),
     "ofs_net_profile": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, C.POINTER(_i), _p]),
     "ofs_net_time_kernels": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
@@ -78,6 +79,7 @@ DEBUG_PROTOTYPES = {
     "ofs_debug_conv_plan_ex": (_i, [_i] * 12 + [_p, _p, _p, _p, _p, _p, _p, _ll, _p]),
     "ofs_debug_conv_schedule": (_i, [_i] * 12 + [_p]),
     "ofs_debug_cvt16": (C.c_uint, [_f, _i]),
+    "ofs_debug_host_pack_bf16": (_i, [_p, _p, _ll, _i]),
 }
 
 _lib = None

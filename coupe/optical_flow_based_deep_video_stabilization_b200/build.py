@@ -20,7 +20,7 @@ REPO = os.path.abspath(os.path.join(HERE, "..", ".."))
 LIB_PATH = os.path.join(HERE, "libofstab.so")
 STAMP = os.path.join(HERE, ".libofstab.stamp")
 
-SOURCES = ["ofs_common.cu", "samplers.cu", "conv_gemm.cu", "flownet.cu", "clip.cu", "modes.cu"]
+SOURCES = ["ofs_common.cu", "samplers.cu", "conv_gemm.cu", "flownet.cu", "clip.cu", "modes.cu", "host_pack.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
@@ -57,7 +57,7 @@ def is_fresh():
 
 
 def build_library(force=False, verbose=False):
-    """Compile csrc/*.cu into libofstab.so when sources changed.  Returns the library path.
+    """Compile csrc/*.cu (+ host_pack.cpp) into libofstab.so when sources changed.  Returns the library path.
 
     Safe under concurrent callers (torchrun ranks importing a stale tree at the same moment): one process builds
     under an exclusive file lock into a temporary file and renames it into place; the others wait for the lock,

@@ -23,7 +23,10 @@
 #include <string>
 #include <vector>
 
+#include <thread>
+
 #include "conv_gemm.cuh"
+#include "host_pack.h"
 
 namespace ofs {
 int flow_resize_warp_u8_impl(const uint8_t* img, const float* flow2_prescaled, uint8_t* out_u8, float* out_f32, int B, int H,
@@ -140,6 +143,23 @@ __global__ void pyr_kernel(PyrParams p) {
   }
 }
 
+// 16-bit network input as it crosses PCIe from ofs_net_stabilize_host ([npix, 27], rounded on the host) -> the packed
+// [npix, 32] layout conv1 reads (channels 27..31 zero)
+__global__ void repack27_kernel(const uint16_t* __restrict__ in, uint4* __restrict__ out, size_t npix) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const size_t total = npix * 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = i >> 2;
+    const int c0 = (int)(i & 3) << 3;
+    const uint16_t* src = in + pix * 27 + c0;
+    uint32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c0 + j < 27) ? (uint32_t)__ldg(src + j) : 0u;
+    out[i] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+  }
+}
+
 struct Predict2Params {
   const float* P;     // [B,96,128,18]: column (ky*3+kx)*2 + o
   const float2* f3;   // [B,48,64]
@@ -248,28 +268,33 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(kP2Threads) predict2_fused_kernel(P2FusedParams p) {
-  __shared__ __align__(16) uint16_t Ws[24 * kP2WStride];
+__global__ void __launch_bounds__(kP2Threads, 3) predict2_fused_kernel(P2FusedParams p) {
+  // B fragments pre-arranged per (32-element K block, k16 half, n8 tile): 32 lanes x 8 bytes each, conflict-free LDS.64
+  __shared__ __align__(16) uint2 Bf[7 * 2 * 3 * 32];
   __shared__ __align__(16) float Ps[176 * kP2PStride];
   pdl_wait();
   pdl_launch_dependents();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.z;
   const int r0 = blockIdx.y * 4, c0 = blockIdx.x * 32;
-  // ---- weights: 24 rows (18 real) x 208 K (194 real) of the packed [32][256] K-major matrix
+  // The K order inside a 32-element block is permuted so that a thread's A operands of both k16 halves are ONE 16-byte
+  // load per pixel row: lane (g, t) holds elements 32 kb + 8 t + [0, 8) of rows g and g + 8; half s multiplies elements
+  // 4 s .. 4 s + 3 of them (the fragment's "k = 2t, 2t+1" and "k = 2t+8, 2t+9" slots).  The B fragments are gathered
+  // from the packed [32][256] K-major weights with the same permutation: a sum over k does not care about its order.
   {
     const uint32_t* __restrict__ wsrc = reinterpret_cast<const uint32_t*>(p.w);
-    uint32_t* wdst = reinterpret_cast<uint32_t*>(Ws);
-    for (int i = threadIdx.x; i < 24 * 104; i += kP2Threads) {
-      const int n = i / 104, k2 = i - n * 104;
-      wdst[n * (kP2WStride / 2) + k2] = __ldg(wsrc + n * 128 + k2);
+    for (int i = threadIdx.x; i < 7 * 2 * 3 * 32; i += kP2Threads) {
+      const int l = i & 31, nt = (i >> 5) % 3, s2 = (i / 96) & 1, kb = i / 192;
+      const int g = l >> 2, t = l & 3;
+      const uint32_t* src = wsrc + (nt * 8 + g) * 128 + 16 * kb + 4 * t + 2 * s2;   // words: element 32 kb + 8 t + 4 s2
+      Bf[i] = make_uint2(__ldg(src), __ldg(src + 1));
     }
   }
   __syncthreads();
-  // ---- product: warp w computes region pixels [16 w, 16 w + 16) x 24 columns over K = 208
+  // ---- product: warp w computes region pixels [16 w, 16 w + 16) x 24 columns over K = 7 x 32 (194 real)
   {
     const int g = lane >> 2, t = lane & 3;
-    const uint32_t* rowp[2];
+    const uint4* rowp[2];
     bool valid[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -277,21 +302,32 @@ __global__ void __launch_bounds__(kP2Threads) predict2_fused_kernel(P2FusedParam
       const int rr = pp / kP2RegionW, cc = pp - rr * kP2RegionW;
       const int sr = r0 + rr, sc = c0 + cc;
       valid[h] = pp < kP2Region && sr < 96 && sc < 128;
-      rowp[h] = reinterpret_cast<const uint32_t*>(p.concat2 + ((size_t)(b * 96 + min(sr, 95)) * 128 + min(sc, 127)) * 200);
+      rowp[h] = reinterpret_cast<const uint4*>(p.concat2 + ((size_t)(b * 96 + min(sr, 95)) * 128 + min(sc, 127)) * 200);
     }
     float acc[3][4] = {};
-    const uint32_t* Ws32 = reinterpret_cast<const uint32_t*>(Ws);
+    // 16-byte unit 4 kb + t of the 400-byte pixel row; the last block's units past the row (elements >= 200, zero
+    // weights) re-read the row's last unit.  The loads of block kb + 2 are in flight while block kb is multiplied.
+    uint4 va[3], vb[3];
+    va[0] = __ldg(rowp[0] + t); vb[0] = __ldg(rowp[1] + t);
+    va[1] = __ldg(rowp[0] + 4 + t); vb[1] = __ldg(rowp[1] + 4 + t);
 #pragma unroll
-    for (int ks = 0; ks < 13; ++ks) {
-      // words of this k16 step: element 2t (+1) -> word 8 ks + t, element 2t + 8 (+9) -> word 8 ks + t + 4; the last step's
-      // second half (elements 200..207) lies past the 200-element pixel row: re-read the first half (its weights are zero)
-      const int w0 = 8 * ks + t, w1 = ks == 12 ? w0 : w0 + 4;
-      uint32_t a[4];
-      a[0] = __ldg(rowp[0] + w0); a[1] = __ldg(rowp[1] + w0); a[2] = __ldg(rowp[0] + w1); a[3] = __ldg(rowp[1] + w1);
+    for (int kb = 0; kb < 7; ++kb) {
+      if (kb + 2 < 7) {
+        const int u = min(4 * (kb + 2) + t, 24);
+        va[(kb + 2) % 3] = __ldg(rowp[0] + u);
+        vb[(kb + 2) % 3] = __ldg(rowp[1] + u);
+      }
+      const uint4 xa = va[kb % 3], xb = vb[kb % 3];
 #pragma unroll
-      for (int nt = 0; nt < 3; ++nt) {
-        const uint32_t* wr = Ws32 + (nt * 8 + g) * (kP2WStride / 2) + 8 * ks + t;
-        mma16816(acc[nt], a, wr[0], wr[4], p.is_bf16);
+      for (int s2 = 0; s2 < 2; ++s2) {
+        uint32_t a[4];
+        a[0] = s2 ? xa.z : xa.x; a[1] = s2 ? xb.z : xb.x;
+        a[2] = s2 ? xa.w : xa.y; a[3] = s2 ? xb.w : xb.y;
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+          const uint2 bw = Bf[((kb * 2 + s2) * 3 + nt) * 32 + lane];
+          mma16816(acc[nt], a, bw.x, bw.y, p.is_bf16);
+        }
       }
     }
 #pragma unroll
@@ -403,7 +439,7 @@ struct ofs_net {
   float* upw = nullptr;  // 4 x (64 + 2) floats: upsample6_5, 5_4, 4_3, 3_2
   short* nn_tab = nullptr;  // predict2: NN align_corners source index tables, 384 rows then 512 columns (value - 1)
   short* p2_tab = nullptr;  // predict2_fused_kernel: first output row / column per source tile row (25) / column (5)
-  int p2_fused = 1;         // 1: predict2 product + gather in one kernel (OFS_P2_FUSED=0: 1x1 GEMM + predict2_gather_kernel)
+  int p2_fused = 0;         // 1 (OFS_P2_FUSED=1): predict2 product + gather in one kernel instead of the 1x1 GEMM + predict2_gather_kernel
   float p2_bias[2] = {0, 0};
   std::vector<Layer> layers;
   std::vector<Head> heads;   // predict6, predict5, predict4, predict3
@@ -414,6 +450,12 @@ struct ofs_net {
   // host-API staging
   float *st_feats = nullptr, *st_frames = nullptr, *st_out = nullptr;
   size_t st_frames_cap = 0;
+  // ofs_net_stabilize_host, bf16 nets: the float32 input is rounded to bf16 on the host (worker pool, pinned staging) and
+  // crosses PCIe as [B,384,512,27] 16-bit; `feats_packed16` tells forward_impl that its `feats` argument is that array
+  HostPacker* packer = nullptr;
+  uint16_t* h_feats16 = nullptr;   // pinned, max_batch inputs
+  int feats_packed16 = 0;
+  int host_pack = 0;               // OFS_HOST_PACK=1: bf16 on the wire (rounded on the host); default float32
   // CUDA graphs of whole stabilize() steps, one per (B, H, W, flow2 wanted, alignment class of out).  The caller's four
   // pointers are baked into a handful of kernel nodes (pack_act: feats; the warp: frames, out; predict2_gather:
   // flow2_out); `patches` records where, so a call with other addresses updates those nodes of the instantiated
@@ -422,6 +464,7 @@ struct ofs_net {
     const void* baked[4];          // feats, frames, out, flow2 as currently set in `exec`
     int B, H, W;
     bool out_aligned16;
+    bool packed16;                 // feats is the 16-bit wire format (repack27_kernel instead of pack_act_kernel)
     cudaGraph_t graph;             // kept alive: its node handles address the nodes of `exec`
     cudaGraphExec_t exec;
     int launches;
@@ -705,7 +748,13 @@ int forward_impl(ofs_net* n, const float* feats, int B, float* f2_target, cudaSt
   int rc = prepare(n, B);
   if (rc != OFS_OK) return rc;
   OFS_MARK("start", 0.0);
-  if (feats != kFromX0) {
+  if (feats != kFromX0 && n->feats_packed16) {
+    const size_t npix = (size_t)B * kNetH * kNetW;
+    const int blocks = (int)std::min<size_t>((npix * 4 + 255) / 256, (size_t)sm_count() * 8);
+    OFS_CUDA(launch_pdl(repack27_kernel, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const uint16_t*>(feats),
+                        reinterpret_cast<uint4*>(n->x0), npix));
+    OFS_LAUNCH_CHECK();
+  } else if (feats != kFromX0) {
     rc = launch_pack_act(feats, n->x0, (size_t)B * kNetH * kNetW, kNetC, 32, n->is_bf16, st);
     if (rc != OFS_OK) return rc;
   }
@@ -802,7 +851,13 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
   ofs_net* n = new ofs_net();
   n->device = device; n->max_batch = max_batch; n->is_bf16 = precision == OFS_PREC_BF16;
   { const char* e = getenv("OFS_GRAPH"); n->use_graphs = (e && e[0] == '0') ? 0 : 1; }
-  { const char* e = getenv("OFS_P2_FUSED"); n->p2_fused = (e && e[0] == '0') ? 0 : 1; }
+  // measured on the 16-vCPU host of the B200 boxes: 1584-1609 pairs/s packed (5-8 workers) against 1622 with float32 on
+  // the wire -- there the host's memory system, which now also carries the conversion's read + write, is the limit, not
+  // the bus.  Bit-identical either way (tested); opt-in.
+  { const char* e = getenv("OFS_HOST_PACK"); n->host_pack = (e && e[0] == '1') ? 1 : 0; }
+  // predict2 product + gather as ONE mma.sync kernel: built, byte-for-byte the same flow pipeline, and measured at parity with
+  // the two launches it replaces (38.4-39.0 vs 38.8 us; 17.6 k vs 17.9 k pairs/s): opt-in (profiles/r02_tuning.md)
+  { const char* e = getenv("OFS_P2_FUSED"); n->p2_fused = (e && e[0] == '1') ? 1 : 0; }
   const size_t B = (size_t)max_batch;
   struct { void** p; size_t elems; } bufs[] = {
       {&n->x0, B * 384 * 512 * 32},    {&n->conv1, B * 192 * 256 * 64}, {&n->concat2, B * 96 * 128 * 200},
@@ -940,6 +995,8 @@ int ofs_net_destroy(ofs_net* n) {
     if (n->ev_comp[i]) cudaEventDestroy(n->ev_comp[i]);
   }
   drop_graphs(n);
+  if (n->packer) host_packer_destroy(n->packer);
+  if (n->h_feats16) cudaFreeHost(n->h_feats16);
   for (void* p : n->allocs) cudaFree(p);
   if (n->ws) cudaFree(n->ws);
   if (n->st_frames) cudaFree(n->st_frames);
@@ -1111,7 +1168,8 @@ int ofs_net_stabilize(ofs_net* n, const float* feats, const float* frames, float
   ++n->graph_clock;
   const bool aligned = (((uintptr_t)out) % 16) == 0;   // selects the warp kernel variant at capture time
   for (auto& g : n->graphs) {
-    if (g.B != B || g.H != H || g.W != W || g.out_aligned16 != aligned || (g.baked[3] == nullptr) != (flow2_out == nullptr)) continue;
+    if (g.B != B || g.H != H || g.W != W || g.out_aligned16 != aligned || (g.baked[3] == nullptr) != (flow2_out == nullptr) ||
+        g.packed16 != (n->feats_packed16 != 0)) continue;
     g.last_use = n->graph_clock;
     bool same = true;
     for (int w = 0; w < 4; ++w) same = same && g.baked[w] == ptrs[w];
@@ -1144,6 +1202,7 @@ int ofs_net_stabilize(ofs_net* n, const float* feats, const float* frames, float
   OFS_CUDA(ce);
   ofs_net::StepGraph sg{};
   for (int w = 0; w < 4; ++w) sg.baked[w] = ptrs[w];
+  sg.packed16 = n->feats_packed16 != 0;
   sg.B = B; sg.H = H; sg.W = W; sg.out_aligned16 = aligned; sg.graph = graph; sg.launches = launches; sg.last_use = n->graph_clock;
   rc = collect_patches(graph, ptrs, sg.patches);
   if (rc != OFS_OK) { cudaGraphDestroy(graph); return rc; }
@@ -1194,19 +1253,42 @@ int ofs_net_stabilize_host(ofs_net* n, const float* feats_host, const float* fra
   int chunk = B >= 4 ? 2 : 1;
   if (const char* e = getenv("OFS_HOST_CHUNK")) chunk = std::max(1, std::min(B, atoi(e)));   // experiments only
   const int nchunks = (B + chunk - 1) / chunk;
+  // bf16 nets: the network input crosses the bus as bf16, rounded here on the host exactly as pack_act_kernel would round
+  // it on the device (same bits, half the bytes); sub-batch c+1 is converted while sub-batch c is in flight
+  const bool packed = n->is_bf16 && n->host_pack;
+  if (packed && !n->packer) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    int threads = (int)std::max(1u, std::min(6u, hw / 3));
+    if (const char* e = getenv("OFS_HOST_PACK_THREADS")) threads = std::max(1, std::min(64, atoi(e)));
+    n->packer = host_packer_create(threads);
+    OFS_CUDA(cudaHostAlloc((void**)&n->h_feats16, (size_t)n->max_batch * feat_elems * 2, cudaHostAllocDefault));
+  }
+  if (packed) host_packer_start(n->packer, feats_host, n->h_feats16, (size_t)std::min(chunk, B) * feat_elems);
   for (int c = 0; c < nchunks; ++c) {
     const int b0 = c * chunk, nb = std::min(chunk, B - b0);
     float* d_feats = n->st_feats + (size_t)b0 * feat_elems;
     float* d_frames = n->st_frames + (size_t)b0 * frame_elems;
     float* d_out = n->st_out + (size_t)b0 * frame_elems;
+    if (packed) {
+      host_packer_wait(n->packer);                        // sub-batch c is converted
+      if (c + 1 < nchunks) {
+        const int b1 = (c + 1) * chunk, nb1 = std::min(chunk, B - b1);
+        host_packer_start(n->packer, feats_host + (size_t)b1 * feat_elems, n->h_feats16 + (size_t)b1 * feat_elems, (size_t)nb1 * feat_elems);
+      }
+      uint16_t* d16 = reinterpret_cast<uint16_t*>(n->st_feats) + (size_t)b0 * feat_elems;   // the float32 staging, reused
+      d_feats = reinterpret_cast<float*>(d16);
+      OFS_CUDA(cudaMemcpyAsync(d16, n->h_feats16 + (size_t)b0 * feat_elems, (size_t)nb * feat_elems * 2, cudaMemcpyHostToDevice, n->s_h2d));
+    } else
     OFS_CUDA(cudaMemcpyAsync(d_feats, feats_host + (size_t)b0 * feat_elems, (size_t)nb * feat_elems * 4,
                              cudaMemcpyHostToDevice, n->s_h2d));
     OFS_CUDA(cudaMemcpyAsync(d_frames, frames_host + (size_t)b0 * frame_elems, (size_t)nb * frame_elems * 4,
                              cudaMemcpyHostToDevice, n->s_h2d));
     OFS_CUDA(cudaEventRecord(n->ev_h2d[c], n->s_h2d));
     OFS_CUDA(cudaStreamWaitEvent(n->stream, n->ev_h2d[c], 0));
+    n->feats_packed16 = packed ? 1 : 0;
     int rc = ofs_net_stabilize(n, d_feats, d_frames, d_out, nullptr, nb, H, W, (ofs_stream)n->stream);
-    if (rc != OFS_OK) return rc;
+    n->feats_packed16 = 0;
+    if (rc != OFS_OK) { if (packed) host_packer_wait(n->packer); return rc; }
     OFS_CUDA(cudaEventRecord(n->ev_comp[c], n->stream));
     OFS_CUDA(cudaStreamWaitEvent(n->s_d2h, n->ev_comp[c], 0));
     OFS_CUDA(cudaMemcpyAsync(out_host + (size_t)b0 * frame_elems, d_out, (size_t)nb * frame_elems * 4,
@@ -1214,6 +1296,13 @@ int ofs_net_stabilize_host(ofs_net* n, const float* feats_host, const float* fra
   }
   OFS_CUDA(cudaStreamSynchronize(n->s_d2h));
   return OFS_OK;
+}
+
+// bytes the host call above moves host -> device for a batch (bench.py reports them as e2e.h2d_bytes_per_step)
+long long ofs_net_host_h2d_bytes(const ofs_net* n, int B, int H, int W) {
+  if (!n) return -1;
+  const long long feats = (long long)B * kNetH * kNetW * kNetC * ((n->is_bf16 && n->host_pack) ? 2 : 4);
+  return feats + (long long)B * H * W * 3 * 4;
 }
 
 int ofs_net_get_activation(ofs_net* n, const char* name, int B, float* out, int64_t capacity, int* shape4,

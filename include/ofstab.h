@@ -136,9 +136,16 @@ int ofs_net_forward(ofs_net* net, const float* feats, int B, float* f6, float* f
 int ofs_net_stabilize(ofs_net* net, const float* feats, const float* frames, float* out, float* flow2_out, int B,
                       int H, int W, ofs_stream stream);
 /* Same call on HOST buffers: H2D of feats+frames, compute, D2H of out, synchronous on return.
- * (This is the boundary the reference's feed_dict / fetch crosses, main_dl.py:568-569.) */
+ * (This is the boundary the reference's feed_dict / fetch crosses, main_dl.py:568-569.)
+ * The call is PCIe-bound and pipelined over sub-batches.  With OFS_HOST_PACK=1 in the environment of ofs_net_create, a
+ * bf16 net rounds the float32 network input to bf16 on the HOST (a small worker pool, one sub-batch ahead of the copies)
+ * and sends it as 16-bit: the device's first kernel performs the very same round-to-nearest-even, so the result is
+ * bit-identical and 85 MB instead of 170 MB of network input cross the bus per 8-pair step.  Off by default: on a host
+ * whose memory system is the bottleneck (measured) the conversion's own traffic cancels the gain.
+ * ofs_net_host_h2d_bytes: the bytes such a call copies host -> device. */
 int ofs_net_stabilize_host(ofs_net* net, const float* feats_host, const float* frames_host, float* out_host, int B,
                            int H, int W);
+long long ofs_net_host_h2d_bytes(const ofs_net* net, int B, int H, int W);
 /* Debug / parity: copy a named activation, widened to float32, into out (dev, capacity in
  * elements).  shape4 receives [B,H,W,C].  Names: conv1 conv2 conv3 conv3_1 conv4 conv4_1 conv5
  * conv5_1 conv6 conv6_1 concat5 concat4 concat3 concat2 (logical channels only). */

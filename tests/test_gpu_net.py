@@ -414,6 +414,27 @@ def test_full_size_step_properties(ofs, cuda_dev, B, H, W):
     net.close()
 
 
+def test_host_call_wire_format_does_not_change_results(ofs, cuda_dev, monkeypatch):
+    """ofs_net_stabilize_host with OFS_HOST_PACK=1 sends the network input as bf16 rounded on the host (half the PCIe
+    bytes); by default it sends float32 and pack_act_kernel rounds it on the device: same bits either way, odd batch."""
+    w = F.make_weights(0, "calibrated", head_scale=0.02)
+    gen = torch.Generator().manual_seed(21)
+    B, H, W = 3, 240, 320
+    feats, frames = F.make_feats(9, B), torch.rand((B, H, W, 3), generator=gen)
+    outs, wire = [], []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("OFS_HOST_PACK", flag)
+        net = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=4, precision="bf16")
+        net.assign_weights(w)
+        outs.append(net.stabilize_host(feats.pin_memory(), frames.pin_memory()))
+        outs.append(net.stabilize_host(feats, frames))                                # pageable buffers, second call: graph replay
+        wire.append(int(net._lib.ofs_net_host_h2d_bytes(net._h, B, H, W)))
+        net.close()
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    assert wire[0] == B * (384 * 512 * 27 * 2 + H * W * 3 * 4) and wire[1] == B * (384 * 512 * 27 * 4 + H * W * 3 * 4)
+
+
 def test_npz_checkpoint_ingest(ofs, cuda_dev, tmp_path):
     """tl.files.load_and_assign_npz_dict (main_dl.py:520): an npz keyed by TF variable names
     ('main_net/flownetS/<layer>/<var>:0', as tl.files.save_npz_dict writes them, main_dl.py:424-426), with

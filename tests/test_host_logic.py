@@ -35,6 +35,28 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.ofs_version() == 100
 
 
+def test_host_wire_packing_is_the_device_rounding(lib):
+    """ofs_net_stabilize_host rounds the float32 network input to bf16 on the host (worker pool, AVX2 or scalar) before it
+    crosses PCIe: the bits must be those of cvt.rn.bf16.f32 -- torch's float32 -> bfloat16 cast -- for ordinary values,
+    ties, denormals, infinities and NaN, whatever the worker count and the array length."""
+    import ctypes as C
+
+    rng = np.random.RandomState(3)
+    base = np.concatenate([rng.rand(100003).astype(np.float32), (rng.randn(5000) * 1e3).astype(np.float32),
+                           np.array([0.0, -0.0, 1.0, np.inf, -np.inf, np.nan, 1e-40, -1e-40, 3.3895314e38, 65504.0], np.float32)])
+    ties = (np.arange(4096, dtype=np.uint32) << 16 | 0x8000).view(np.float32)            # exactly half way: ties to even
+    near = ((np.arange(4096, dtype=np.uint32) << 16) | 0x7fff).view(np.float32)
+    x = np.ascontiguousarray(np.concatenate([base, ties, near]))
+    want = torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    for threads, n in ((1, len(x)), (5, len(x)), (3, 1000), (4, 63), (2, 0)):
+        got = np.full(len(x), 0xABCD, np.uint16)
+        assert lib.ofs_debug_host_pack_bf16(x.ctypes.data_as(C.c_void_p), got.ctypes.data_as(C.c_void_p), n, threads) == 0
+        nan = np.isnan(x[:n])
+        np.testing.assert_array_equal(got[:n][~nan], want[:n][~nan])
+        assert ((got[:n][nan] & 0x7fff) > 0x7f80).all()                                   # NaN stays NaN
+        assert (got[n:] == 0xABCD).all()                                                  # nothing past the end is touched
+
+
 def test_no_cpu_fallback_without_gpu(lib):
     import coupe.optical_flow_based_deep_video_stabilization_b200 as ofs
 
