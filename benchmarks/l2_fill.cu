@@ -16,8 +16,8 @@
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
 
-constexpr int STAGES = 4;
-constexpr int MAX_ROWS = 384;   // rows of 128 B per stage (48 KB)
+constexpr int MAX_STAGES = 12;
+constexpr int SMEM_ROWS = 1536;  // rows of 128 B in the ring (192 KB): stages x rows per stage <= SMEM_ROWS
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
@@ -47,6 +47,7 @@ struct Params {
   int a_rows, a_box;     // rows per iteration private to the CTA, fetched as a_rows / a_box boxes
   int b_rows, b_box;     // rows per iteration shared by all CTAs
   int iters, csize, multicast;
+  int stages, stage_rows;           // ring geometry
   int a_rows_total, b_rows_total;   // tensor heights (wrap-around)
   long long* cycles;     // per CTA
 };
@@ -54,8 +55,9 @@ struct Params {
 __global__ void __launch_bounds__(64, 1) fill_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = base + STAGES * MAX_ROWS * 128;
-  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES;
+  const int STAGES = p.stages;
+  const uint32_t bars = base + SMEM_ROWS * 128;
+  const uint32_t full0 = bars, empty0 = bars + 8 * MAX_STAGES;
   const uint32_t rank = p.csize > 1 ? cluster_rank() : 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, p.multicast ? p.csize : 1); }
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(64, 1) fill_kernel(const __grid_constant__ Par
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
       wait(empty0 + 8 * s, ph ^ 1);
-      const uint32_t dst = base + (uint32_t)s * MAX_ROWS * 128u;
+      const uint32_t dst = base + (uint32_t)s * (uint32_t)p.stage_rows * 128u;
       expect_tx(full0 + 8 * s, stage_bytes);
       for (int r = 0; r < p.a_rows; r += p.a_box) tma2d(dst + r * 128, &p.map_a, full0 + 8 * s, 0, a_row + r);
       if (p.multicast) {
@@ -124,7 +126,7 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&dc, sizeof(long long) * 1024));
   CK(cudaMemset(da, 1, (size_t)a_total * 128));
   CK(cudaMemset(db, 2, (size_t)b_total * 128));
-  const size_t smem = STAGES * MAX_ROWS * 128 + 1024 + 256;
+  const size_t smem = SMEM_ROWS * 128 + 1024 + 256;
   CK(cudaFuncSetAttribute(fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(cudaFuncSetAttribute(fill_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   auto make_map = [&](CUtensorMap* m, void* base, int rows_total, int box_rows) {
@@ -136,7 +138,7 @@ int main(int argc, char** argv) {
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); exit(1); }
   };
-  struct Case { const char* name; int a_rows, b_rows, csize, multicast, ctas; };
+  struct Case { const char* name; int a_rows, b_rows, csize, multicast, ctas; int stages = 4; int a_box = 0; int b_box = 0; };
   std::vector<Case> cases = {
       {"A only 128 rows (16 KB distinct per CTA)", 128, 0, 1, 0, 0},
       {"A only 256 rows", 256, 0, 1, 0, 0},
@@ -150,17 +152,34 @@ int main(int argc, char** argv) {
       {"A 128 + B 256 unicast, 74 CTAs", 128, 256, 1, 0, 74},
       {"A 128 + B 256 unicast, 37 CTAs", 128, 256, 1, 0, 37},
       {"A 128 + B 256 unicast, 8 CTAs", 128, 256, 1, 0, 8},
+      // is a stage's cost its bytes or its number of TMA boxes?  same bytes, more stages / fewer, larger boxes
+      {"A 128, 1 box, 4 stages", 128, 0, 1, 0, 0, 4},
+      {"A 128, 1 box, 8 stages", 128, 0, 1, 0, 0, 8},
+      {"A 128, 1 box, 12 stages", 128, 0, 1, 0, 0, 12},
+      {"A 128 as 2 boxes of 64, 8 stages", 128, 0, 1, 0, 0, 8, 64},
+      {"A 128 as 4 boxes of 32, 8 stages", 128, 0, 1, 0, 0, 8, 32},
+      {"A 256, 1 box, 6 stages", 256, 0, 1, 0, 0, 6},
+      {"A 256 as 2 boxes of 128, 6 stages", 256, 0, 1, 0, 0, 6, 128},
+      {"A 128 + B 144 (deconv3 stage), 2 boxes, 5 stages", 128, 144, 1, 0, 0, 5},
+      {"A 128 + B 144, 2 boxes, 3 stages", 128, 144, 1, 0, 0, 3},
+      {"A 256 + B 256 (two K chunks, merged boxes), 3 stages", 256, 256, 1, 0, 0, 3},
+      {"A 256 + B 256 as 4 boxes of 128, 3 stages", 256, 256, 1, 0, 0, 3, 128, 128},
+      {"A 128 + B 80 (deconv2 stage), 7 stages", 128, 80, 1, 0, 0, 7},
+      {"A 256 + B 160 (two deconv2 K chunks merged), 3 stages", 256, 160, 1, 0, 0, 3},
+      {"A 64 + B 64, 12 stages", 64, 64, 1, 0, 0, 12},
   };
   int clock_khz = 0;
   CK(cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, dev));
   printf("device %s, %d SMs, max clock %d MHz\n", prop.name, sms, clock_khz / 1000);
-  printf("%-58s %6s %9s %12s %12s %10s\n", "case", "CTAs", "us", "B/clk/SM in", "L2 B/clk all", "TB/s in");
+  printf("%-58s %6s %9s %9s %12s %12s %10s\n", "case", "CTAs", "us", "clk/iter", "B/clk/SM in", "L2 B/clk all", "TB/s in");
   for (const Case& c : cases) {
     Params p = {};
     p.a_rows = c.a_rows; p.b_rows = c.b_rows; p.csize = c.csize; p.multicast = c.multicast;
-    p.a_box = c.a_rows ? (c.a_rows > 256 ? 128 : c.a_rows) : 8;
+    p.a_box = c.a_box ? c.a_box : c.a_rows ? (c.a_rows > 256 ? 128 : c.a_rows) : 8;
     const int slice = c.multicast ? c.b_rows / c.csize : c.b_rows;
-    p.b_box = slice ? slice : 8;
+    p.b_box = c.b_box ? c.b_box : slice ? slice : 8;
+    p.stages = c.stages; p.stage_rows = c.a_rows + c.b_rows;
+    if (p.stages > MAX_STAGES || p.stages * p.stage_rows > SMEM_ROWS) { printf("%-58s skipped (ring too large)\n", c.name); continue; }
     p.iters = 2000;
     p.a_rows_total = a_total; p.b_rows_total = b_total;
     p.cycles = dc;
@@ -193,7 +212,7 @@ int main(int argc, char** argv) {
     }
     const double in_bytes = (double)(c.a_rows + c.b_rows) * 128.0 * p.iters;                 // landed per CTA
     const double l2_bytes = (double)(c.a_rows + slice) * 128.0 * p.iters * ctas;            // requested chip-wide
-    printf("%-58s %6d %9.1f %12.1f %12.0f %10.2f\n", c.name, ctas, best * 1e3, in_bytes / (double)cyc_max, l2_bytes / (double)cyc_max,
+    printf("%-58s %6d %9.1f %9.0f %12.1f %12.0f %10.2f\n", c.name, ctas, best * 1e3, (double)cyc_max / p.iters, in_bytes / (double)cyc_max, l2_bytes / (double)cyc_max,
            in_bytes * ctas / (best * 1e-3) / 1e12);
   }
   return 0;

@@ -950,10 +950,12 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
     // (profiles/r02_tuning.md)
     else if (L.name == "4" || L.name == "4_1") { L.d.block_n = 192; if (L.name == "4") L.cta_group = 2; }
     else if (L.name == "5" || L.name == "5_1") { L.block_n_run = 256; L.ksplit = 6; }
-    else if (L.name == "6" || L.name == "6_1") { L.block_n_run = 256; L.ksplit = 8; }
+    // conv6 / conv6_1 (M = 384 rows): 128-column tiles x split-K 4 = 128 units move half the fp32 partials of 256 x 8
+    // (alone: 11.8 vs 12.2 and 13.1 vs 14.8 us, profiles/r02_sweep_small_layers.txt)
+    else if (L.name == "6" || L.name == "6_1") { L.block_n_run = 128; L.ksplit = 4; }
     // the level's flow head rides in the deconv GEMM (128 / 64-column tiles); CTA pairs halve the B fetch per CTA
     else if (L.d.kind == kDeconvK4S2) {
-      L.d.head = 1; L.cta_group = 2;
+      L.d.head = 1; L.cta_group = L.name == "deconv5" ? 1 : 2;   // deconv5 (3 M tiles): single CTAs 13.8 vs 14.5 us
       // deconv2 (cout 64): all four sub-pixel phases stacked in one accumulator tile, each input tap fetched once
       // (deconv_stack_kernel); fixes the packed weight layout.  OFS_NOSTACK=1: the per-phase form (A/B).
       if (L.name == "deconv2" && !(getenv("OFS_NOSTACK") && getenv("OFS_NOSTACK")[0] == '1')) { L.d.stack = 1; L.d.cta_group = 2; }
