@@ -204,7 +204,9 @@ __device__ __forceinline__ void mma(uint32_t d, uint32_t da_lo, uint32_t db_lo, 
 // kInstr: instrumented build of the same kernel (per-CTA trace stamps, per-item stamps, the debug skip switches) used by
 // benchmarks/conv_bench.py only.  The production instantiations carry none of it: the two single-thread role loops are
 // bound by their instruction count (~4 cycles per dependent instruction), so every test inside them costs time.
-template <int BLOCK_N, bool kPair, int kT, int kHead, int kG, bool kKC = false, bool kInstr = false>
+// kChain: the body is one LAYER of a multi-layer persistent launch (conv_chain_kernel below): the CTA keeps its right
+// to allocate tensor memory (no relinquish: the next layer allocates again) and invalidates its barriers on the way out.
+template <int BLOCK_N, bool kPair, int kT, int kHead, int kG, bool kKC = false, bool kInstr = false, bool kChain = false>
 __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
   using Cfg = GemmCfg<BLOCK_N, kPair, kT, kHead, kG>;
   static_assert(!kKC || (!kPair && kT == 1 && kHead == 0 && kG == 1 && BLOCK_N == 256), "cluster split-K: plain 1-CTA 256-column tiles");
@@ -261,8 +263,8 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    if constexpr (kPair) { ptx::tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols); ptx::tmem_relinquish_2sm(); }
-    else { ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols); ptx::tmem_relinquish(); }
+    if constexpr (kPair) { ptx::tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols); if constexpr (!kChain) ptx::tmem_relinquish_2sm(); }
+    else { ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols); if constexpr (!kChain) ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -874,6 +876,12 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
     else ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
     if (trace && lane == 0) trace[13] = (long long)ptx::globaltimer();
   }
+  if constexpr (kChain) {
+    // every role has left its loop (the __syncthreads above): the barriers are quiescent; the next layer of the chain lays
+    // out its own set over this shared memory
+    if (threadIdx.x == 0)
+      for (int i = 0; i < 2 * S + 8; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(full0 + 8 * i) : "memory");
+  }
 }
 
 template <int BLOCK_N, bool kInstr>
@@ -1343,6 +1351,119 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int ksplit, l
   }
 }
 
+// ================================================================================================
+// Layer chain: conv5 -> conv5_1 -> conv6 -> conv6_1 (model.py:829-845) in ONE persistent launch.
+//
+// At batch 8 these four layers have 1536 / 384 GEMM rows: ~4 us of math each, run as split-K GEMMs (fp32 partials into
+// the workspace) + a reduce launch -- 8 launches whose fixed costs (2.5-3.8 us from the end of one launch to the first
+// CTA of the next, the prologue, the first TMA round trip) exceed their work (profiles/r02_tuning.md).  Here every CTA
+// stays resident and walks the four layers; between the phases the grid meets at a barrier in global memory:
+//     layer GEMM (the unchanged conv_gemm_body: partial tiles -> workspace by TMA store)   | grid barrier
+//     reduction of the partials by ALL CTAs (the arithmetic of splitk_reduce_kernel)       | grid barrier
+// The launch is cooperative (every CTA resident at once, also with another stream's kernels on the device), the
+// results are bit-identical to the separate launches (same K order per split, same split order in the sum).
+struct ChainReduce {
+  const float* ws;
+  uint16_t* out;
+  const float* bias;
+  long long split_stride;
+  unsigned long long npix;
+  int ksplit, n_pad, out_cstride, out_coff, lrelu, is_bf16;
+};
+constexpr int kChainLayers = 4;
+struct ConvChainParams {
+  ConvGemmParams layer[kChainLayers];
+  ChainReduce red[kChainLayers];
+  unsigned* sync;   // [0] arrivals of the current barrier, [1] barrier generation (both self-maintained: never reset by the host)
+  long long* trace; // measurement only (OFS_CHAIN_TRACE=1): per CTA 32 globaltimer stamps; null in production
+};
+
+// Sense-reversing grid barrier.  Entry: every thread's global writes (generic proxy) and completed TMA stores (async
+// proxy) are ordered before the arrival; exit: TMA loads and plain loads issued afterwards see them.
+__device__ __forceinline__ void chain_grid_sync(unsigned* sync, unsigned& gen) {
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(sync, 1u);
+    if (prev == gridDim.x - 1) {
+      *reinterpret_cast<volatile unsigned*>(sync) = 0u;   // ready for the next barrier before anybody is released
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(sync + 1), "r"(gen + 1u) : "memory");
+    } else {
+      unsigned g;
+      const long long t0 = clock64();
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(sync + 1) : "memory");
+        if (clock64() - t0 > 4000000000LL) __trap();   // a CTA of the grid never arrived: launch error, not a hung GPU
+      } while (g == gen);
+    }
+    __threadfence();
+  }
+  gen += 1u;
+  __syncthreads();
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+// splitk_reduce_kernel's work spread over the resident grid; the partials were written by other SMs' TMA stores during
+// this launch, so they are read from L2 (ld.global.cg), all splits of an element group in flight before the first add
+__device__ __forceinline__ void chain_reduce(const ChainReduce& r) {
+  const int groups = r.n_pad >> 3;
+  const size_t total = (size_t)r.npix * groups;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (size_t)gridDim.x * kThreads) {
+    const size_t pix = i / groups;
+    const int c0 = (int)(i - pix * groups) << 3;
+    const float4* src = reinterpret_cast<const float4*>(r.ws + pix * r.n_pad + c0);
+    const size_t sstride = (size_t)r.split_stride / 4;
+    float4 pa[8], pb[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+      if (s < r.ksplit) { pa[s] = __ldcg(src + (size_t)s * sstride); pb[s] = __ldcg(src + (size_t)s * sstride + 1); }
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(r.bias + c0 + j);
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+      if (s < r.ksplit) {
+        v[0] += pa[s].x; v[1] += pa[s].y; v[2] += pa[s].z; v[3] += pa[s].w;
+        v[4] += pb[s].x; v[5] += pb[s].y; v[6] += pb[s].z; v[7] += pb[s].w;
+      }
+    if (r.lrelu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);
+    }
+    uint4* o = reinterpret_cast<uint4*>(r.out + pix * r.out_cstride + r.out_coff + c0);
+    *o = make_uint4(pack16(v[0], v[1], r.is_bf16), pack16(v[2], v[3], r.is_bf16), pack16(v[4], v[5], r.is_bf16),
+                    pack16(v[6], v[7], r.is_bf16));
+  }
+}
+
+#define OFS_CHAIN_STAMP(k) do { if (tr && threadIdx.x == 0) tr[k] = (long long)ptx::globaltimer(); } while (0)
+template <int BLOCK_N>
+__device__ __forceinline__ void chain_layer(const ConvGemmParams& p, const ChainReduce& r, unsigned* sync, unsigned& gen,
+                                            long long* tr) {
+  conv_gemm_body<BLOCK_N, false, 1, 0, 1, false, false, true>(p);   // leaves after cp.async.bulk.wait_group 0: partials are in L2
+  OFS_CHAIN_STAMP(0);
+  chain_grid_sync(sync, gen);
+  OFS_CHAIN_STAMP(1);
+  chain_reduce(r);
+  OFS_CHAIN_STAMP(2);
+  chain_grid_sync(sync, gen);
+  OFS_CHAIN_STAMP(3);
+}
+
+// tilings of the four layers: 256, 256, 128, 128 columns (what ofs_net_create picks; conv_chain_launch checks)
+__global__ void __launch_bounds__(kThreads, 1) conv_chain_kernel(const __grid_constant__ ConvChainParams cp) {
+  unsigned gen = 0;
+  if (threadIdx.x == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(cp.sync + 1) : "memory");
+  long long* tr = cp.trace ? cp.trace + (size_t)blockIdx.x * 32 : nullptr;
+  OFS_CHAIN_STAMP(16);
+  chain_layer<256>(cp.layer[0], cp.red[0], cp.sync, gen, tr);
+  chain_layer<256>(cp.layer[1], cp.red[1], cp.sync, gen, tr ? tr + 4 : nullptr);
+  chain_layer<128>(cp.layer[2], cp.red[2], cp.sync, gen, tr ? tr + 8 : nullptr);
+  chain_layer<128>(cp.layer[3], cp.red[3], cp.sync, gen, tr ? tr + 12 : nullptr);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1470,6 +1591,31 @@ int launch_reduce(const ConvPlan& plan, cudaStream_t st) {
                       plan.d.out_cstride, plan.d.out_coff, plan.d.lrelu, plan.d.is_bf16));
   OFS_LAUNCH_CHECK();
   return OFS_OK;
+}
+
+// OFS_CHAIN_TRACE=1: one device buffer of sm_count x 32 stamps (per process and device; measurement runs are single-net)
+long long* chain_trace_buffer(bool peek) {
+  static long long* buf = nullptr;
+  static int state = -1;
+  if (state < 0) { const char* e = getenv("OFS_CHAIN_TRACE"); state = (e && e[0] == '1') ? 1 : 0; }
+  if (!state || peek) return buf;
+  if (!buf && cudaMalloc((void**)&buf, (size_t)sm_count() * 32 * sizeof(long long)) == cudaSuccess)
+    cudaMemset(buf, 0, (size_t)sm_count() * 32 * sizeof(long long));
+  return buf;
+}
+
+ChainReduce chain_reduce_args(const ConvPlan& plan) {
+  const ConvGemmParams& p = plan.p;
+  ChainReduce r = {};
+  r.ws = plan.ws;
+  r.out = reinterpret_cast<uint16_t*>(plan.final_out);
+  r.bias = plan.bias_dev;
+  r.split_stride = p.ws_split_stride;
+  r.npix = (unsigned long long)plan.d.B * p.out_H * p.out_W;
+  r.ksplit = p.ksplit; r.n_pad = p.n_pad;
+  r.out_cstride = plan.d.out_cstride; r.out_coff = plan.d.out_coff;
+  r.lrelu = plan.d.lrelu; r.is_bf16 = plan.d.is_bf16;
+  return r;
 }
 
 int ilog2(int v) {
@@ -2056,6 +2202,57 @@ int conv_launch(const ConvPlan& plan, cudaStream_t st) {
   }
   if (rc != OFS_OK) return rc;
   return (plan.p.ksplit > 1 && !plan.p.fused_reduce) ? launch_reduce(plan, st) : OFS_OK;
+}
+
+int conv_chain_trace_read(long long* host, int max_words) {
+  long long* buf = chain_trace_buffer(true);
+  if (!buf) return 0;
+  const int words = std::min(max_words, sm_count() * 32);
+  if (cudaMemcpy(host, buf, (size_t)words * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  return words;
+}
+
+bool conv_chain_supported(const ConvPlan* const plans[4]) {
+  static const int want_bn[kChainLayers] = {256, 256, 128, 128};
+  for (int i = 0; i < kChainLayers; ++i) {
+    const ConvPlan& q = *plans[i];
+    if (q.block_n != want_bn[i] || q.p.ksplit < 2 || q.p.ksplit > 8 || q.p.kcluster || q.p.fused_reduce || q.p.slab || q.d.stack ||
+        q.d.head || q.d.kgroup != 1 || q.d.cta_group == 2 || q.d.kind != kConv || q.p.out_mode != 2 || q.p.tma_store != 2 ||
+        q.p.trace || q.p.debug || !q.ws || !q.final_out)
+      return false;
+  }
+  return true;
+}
+
+int conv_chain_launch(const ConvPlan* const plans[4], unsigned* sync, cudaStream_t st) {
+  OFS_REQUIRE(conv_chain_supported(plans), "conv_chain_launch: the four plans do not have the chain's tilings");
+  static ConvChainParams cp;   // 9 KB: built under the mutex, copied by the launch
+  static std::mutex mu;
+  static std::set<int> done;
+  int dev = 0;
+  OFS_CUDA(cudaGetDevice(&dev));
+  const size_t smem = std::max(GemmCfg<256, false>::kSmem, GemmCfg<128, false>::kSmem);
+  std::lock_guard<std::mutex> lock(mu);
+  if (!done.count(dev)) {
+    OFS_CUDA(cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done.insert(dev);
+  }
+  for (int i = 0; i < kChainLayers; ++i) { cp.layer[i] = plans[i]->p; cp.red[i] = chain_reduce_args(*plans[i]); }
+  cp.sync = sync;
+  cp.trace = chain_trace_buffer(false);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)sm_count());   // one CTA per SM, all resident: the grid barrier needs every one of them
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OFS_CUDA(cudaLaunchKernelEx(&cfg, conv_chain_kernel, cp));
+  OFS_LAUNCH_CHECK();
+  return OFS_OK;
 }
 
 int launch_pack_act(const float* in, void* out, size_t npix, int cin, int cs, int is_bf16, cudaStream_t st) {

@@ -137,6 +137,15 @@ int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_packed_dev,
                    float* workspace = nullptr, float* head_out = nullptr, unsigned* counters = nullptr);
 int conv_launch(const ConvPlan& plan, cudaStream_t st);
 
+// conv5 -> conv5_1 -> conv6 -> conv6_1 as ONE cooperative persistent launch (split-K GEMM phases and all-CTA reductions
+// separated by grid barriers; bit-identical to four conv_launch calls).  `plans`: the four bound split-K plans in layer
+// order; `sync`: two zero-initialised device words owned by the caller (self-maintained afterwards).
+bool conv_chain_supported(const ConvPlan* const plans[4]);
+int conv_chain_launch(const ConvPlan* const plans[4], unsigned* sync, cudaStream_t st);
+// measurement only (OFS_CHAIN_TRACE=1): the last chain launch's per-CTA globaltimer stamps, 32 words per CTA:
+// [4l + {0 GEMM done, 1 barrier, 2 reduced, 3 barrier}] for layer l, [16] kernel entry; returns the words copied
+int conv_chain_trace_read(long long* host, int max_words);
+
 // 5-D TMA view of the input activation (dims in elements, strides in bytes; dim 0 is contiguous)
 void conv_act_view(const ConvDesc& d, unsigned long long dims[5], unsigned long long strides_bytes[4]);
 

@@ -445,6 +445,9 @@ struct ofs_net {
   std::vector<Head> heads;   // predict6, predict5, predict4, predict3
   float* ws = nullptr;       // split-K workspace (grow-only)
   size_t ws_bytes = 0;
+  // conv5 ... conv6_1 as one cooperative persistent launch (conv_chain_launch); OFS_CHAIN=1 turns it on (A/B)
+  int chain = 0;
+  unsigned* chain_sync = nullptr;   // the chain's grid-barrier words (zeroed once, self-maintained)
   std::map<std::string, ActInfo> acts;
   std::vector<void*> allocs;
   // host-API staging
@@ -735,6 +738,22 @@ struct Marks {
     }                                                    \
   } while (0)
 
+// Launches layer i of n->layers -- or, at conv5 with the chain on, the whole conv5 ... conv6_1 chain.  *covered = number of
+// layers the launch stands for (the caller skips the rest).
+int launch_layer(ofs_net* n, size_t i, cudaStream_t st, int* covered) {
+  *covered = 1;
+  std::vector<Layer>& Ls = n->layers;
+  if (n->chain && n->chain_sync && Ls[i].name == "5" && i + 3 < Ls.size() && Ls[i + 1].name == "5_1" && Ls[i + 2].name == "6" &&
+      Ls[i + 3].name == "6_1") {
+    const ConvPlan* plans[4] = {&Ls[i].plan, &Ls[i + 1].plan, &Ls[i + 2].plan, &Ls[i + 3].plan};
+    if (conv_chain_supported(plans)) {
+      *covered = 4;
+      return conv_chain_launch(plans, n->chain_sync, st);
+    }
+  }
+  return conv_launch(Ls[i].plan, st);
+}
+
 // feats == kFromX0: the packed 16-bit input buffer x0 has already been filled on the device (clip driver)
 const float* const kFromX0 = reinterpret_cast<const float*>(uintptr_t(1));
 int forward_impl(ofs_net* n, const float* feats, int B, float* f2_target, cudaStream_t st, Marks* marks = nullptr) {
@@ -759,15 +778,24 @@ int forward_impl(ofs_net* n, const float* feats, int B, float* f2_target, cudaSt
     if (rc != OFS_OK) return rc;
   }
   OFS_MARK("pack_input", 0.0);
-  for (Layer& L : n->layers) {
+  for (size_t li = 0; li < n->layers.size(); ++li) {
+    Layer& L = n->layers[li];
     if (n->p2_fused && L.name == "predict2") continue;   // product + gather run as one kernel below
     int lvl = 0;
     if (L.name == "deconv5") lvl = 6;
     else if (L.name == "deconv4") lvl = 5;
     else if (L.name == "deconv3") lvl = 4;
     else if (L.name == "deconv2") lvl = 3;
-    rc = conv_launch(L.plan, st);
+    int covered = 1;
+    rc = launch_layer(n, li, st, &covered);
     if (rc != OFS_OK) return rc;
+    if (covered > 1) {
+      double macs = 0.0;
+      for (int k = 0; k < covered; ++k) macs += n->layers[li + k].plan.macs;
+      OFS_MARK("gemm:" + L.name + ".." + n->layers[li + covered - 1].name, macs);
+      li += (size_t)covered - 1;
+      continue;
+    }
     OFS_MARK(L.name == "predict2" ? std::string("gemm:predict2_product") : "gemm:" + L.name,
              L.name == "predict2" ? (double)B * 96 * 128 * 194 * 18 : L.plan.macs);
     if (lvl) {
@@ -858,6 +886,12 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
   // predict2 product + gather as ONE mma.sync kernel: built, byte-for-byte the same flow pipeline, and measured at parity with
   // the two launches it replaces (38.4-39.0 vs 38.8 us; 17.6 k vs 17.9 k pairs/s): opt-in (profiles/r02_tuning.md)
   { const char* e = getenv("OFS_P2_FUSED"); n->p2_fused = (e && e[0] == '1') ? 1 : 0; }
+  // conv5 ... conv6_1 as one cooperative launch: built, bit-identical, and measured SLOWER than the eight launches it replaces
+  // (83.7 us against ~72 us in the step: a grid barrier costs 2.3-3.5 us, as much as a kernel boundary, and the chain
+  // needs two per layer; profiles/r02_tuning.md section 7): opt-in
+  { const char* e = getenv("OFS_CHAIN"); n->chain = (e && e[0] == '1') ? 1 : 0; }
+  rc = dev_alloc(n, (void**)&n->chain_sync, 16, true);
+  if (rc != OFS_OK) { ofs_net_destroy(n); return rc; }
   const size_t B = (size_t)max_batch;
   struct { void** p; size_t elems; } bufs[] = {
       {&n->x0, B * 384 * 512 * 32},    {&n->conv1, B * 192 * 256 * 64}, {&n->concat2, B * 96 * 128 * 200},
@@ -1376,11 +1410,13 @@ int ofs_net_time_kernels(ofs_net* n, int which, const float* frames, float* out,
   OFS_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
   for (int it = 0; it < iters && rc == OFS_OK; ++it) {
     if (which == 0) {
-      for (Layer& L : n->layers) {
-        if (L.name == "predict2") continue;
-        rc = conv_launch(L.plan, cs);
+      for (size_t li = 0; li < n->layers.size(); ++li) {
+        if (n->layers[li].name == "predict2") continue;
+        int covered = 1;
+        rc = launch_layer(n, li, cs, &covered);
         if (rc != OFS_OK) break;
-        if (it == 0) macs += L.plan.macs;
+        for (int k = 0; k < covered; ++k) if (it == 0) macs += n->layers[li + k].plan.macs;
+        li += (size_t)covered - 1;
       }
     } else {
       rc = flow_resize_warp_impl(frames, n->f2s, out, B, H, W, 382, 510, cs, 1);
@@ -1415,11 +1451,21 @@ int ofs_net_time_kernels(ofs_net* n, int which, const float* frames, float* out,
   return OFS_OK;
 }
 
+int ofs_chain_trace_read(long long* host_words, int max_words) {
+  if (!host_words || max_words <= 0) return 0;
+  return conv_chain_trace_read(host_words, max_words);
+}
+
 int ofs_net_launches_per_forward(const ofs_net* n) {
   if (!n) return 0;
   int k = 1 + (int)n->layers.size() + 4 + 1;  // pack + GEMMs (heads ride in the deconvs) + pyramid steps + gather
   if (n->p2_fused) --k;                       // predict2: product and gather are one kernel
   for (const Layer& L : n->layers) k += (L.plan.p.ksplit > 1 && !L.plan.p.fused_reduce) ? 1 : 0;  // separate split-K reductions (after prepare())
+  for (size_t i = 0; i + 3 < n->layers.size(); ++i)
+    if (n->chain && n->chain_sync && n->layers[i].name == "5") {
+      const ConvPlan* plans[4] = {&n->layers[i].plan, &n->layers[i + 1].plan, &n->layers[i + 2].plan, &n->layers[i + 3].plan};
+      if (conv_chain_supported(plans)) k -= 7;   // four GEMMs + four reductions are one launch
+    }
   return k;
 }
 

@@ -165,6 +165,10 @@ int ofs_net_profile(ofs_net* net, const float* feats, const float* frames, float
  * frames [B,H,W,3] dev -> out dev on the last forward's flow.  Synchronous. */
 int ofs_net_time_kernels(ofs_net* net, int which, const float* frames, float* out, int B, int H, int W, int iters,
                          float* ms_per_set, double* macs_per_set, int* launches_per_set);
+/* Measurement aid (OFS_CHAIN_TRACE=1 in the environment): per-CTA globaltimer stamps (ns) of the last conv5 ... conv6_1
+ * chain launch, 32 words per CTA: [4l + {0: layer l's GEMM phase done, 1: past the barrier, 2: reduction done, 3: past
+ * the barrier}], [16] kernel entry.  Returns the number of words copied (0 when tracing is off). */
+int ofs_chain_trace_read(long long* host_words, int max_words);
 /* per-forward kernel launches (constant for a given B) */
 int ofs_net_launches_per_forward(const ofs_net* net);
 /* Diagnostics of the step-graph cache of ofs_net_stabilize: what = 0 -> graphs captured so far, 1 -> launches that

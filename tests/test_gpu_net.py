@@ -435,6 +435,57 @@ def test_host_call_wire_format_does_not_change_results(ofs, cuda_dev, monkeypatc
     assert wire[0] == B * (384 * 512 * 27 * 2 + H * W * 3 * 4) and wire[1] == B * (384 * 512 * 27 * 4 + H * W * 3 * 4)
 
 
+@pytest.mark.parametrize("B", [1, 3, 8])
+def test_layer_chain_bit_identical_to_separate_launches(ofs, cuda_dev, monkeypatch, B):
+    """conv5 ... conv6_1 (model.py:829-845) as ONE cooperative persistent launch (split-K GEMM phases and all-CTA
+    reductions separated by grid barriers, conv_chain_kernel; opt-in with OFS_CHAIN=1, measured slower) gives the bits of
+    the eight separate launches: same K order per split, same split order in the sums.  Repeated calls reuse the self-maintained
+    barrier words; the step-graph path (stabilize) replays the chain from a CUDA graph; two nets on two streams run their
+    chains concurrently (the launch is cooperative: no partial residency)."""
+    w = F.make_weights(0, "calibrated", head_scale=0.02)
+    x = F.make_feats(5, B).to(cuda_dev)
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("OFS_CHAIN", flag)
+        net = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=B, precision="bf16")
+        net.assign_weights(w)
+        outs = []
+        for _ in range(3):
+            o = net.forward(x)
+            outs.append({k: o[k].clone() for k in ("predict_flow6", "predict_flow2")})
+            acts = {k: net.activation(k, B).clone() for k in ("conv5", "conv5_1", "conv6", "conv6_1")}
+        for o in outs[1:]:
+            assert torch.equal(o["predict_flow2"], outs[0]["predict_flow2"])
+        res[flag] = (outs[0], acts, net.launches_per_forward)
+        if flag == "1":
+            frames = torch.rand((B, 96, 128, 3), device=cuda_dev)
+            s0 = net.stabilize(x, frames)
+            s1 = net.stabilize(x, frames)                      # graph replay
+            assert torch.equal(s0, s1)
+            if B == 8:
+                net2 = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=B, precision="bf16")
+                net2.assign_weights(w)
+                st1, st2 = torch.cuda.Stream(device=cuda_dev), torch.cuda.Stream(device=cuda_dev)
+                torch.cuda.synchronize()
+                got = []
+                for _ in range(6):
+                    with torch.cuda.stream(st1):
+                        a = net.forward(x)["predict_flow2"].clone()
+                    with torch.cuda.stream(st2):
+                        b = net2.forward(x)["predict_flow2"].clone()
+                    got += [a, b]
+                torch.cuda.synchronize()
+                for g in got:
+                    assert torch.equal(g, outs[0]["predict_flow2"])
+                net2.close()
+        net.close()
+    assert res["0"][2] - res["1"][2] == 7, (res["0"][2], res["1"][2])   # 4 GEMMs + 4 reductions -> 1 launch
+    for k in ("conv5", "conv5_1", "conv6", "conv6_1"):
+        assert torch.equal(res["0"][1][k], res["1"][1][k]), k
+    for k in ("predict_flow6", "predict_flow2"):
+        assert torch.equal(res["0"][0][k], res["1"][0][k]), k
+
+
 def test_npz_checkpoint_ingest(ofs, cuda_dev, tmp_path):
     """tl.files.load_and_assign_npz_dict (main_dl.py:520): an npz keyed by TF variable names
     ('main_net/flownetS/<layer>/<var>:0', as tl.files.save_npz_dict writes them, main_dl.py:424-426), with
