@@ -467,6 +467,7 @@ struct ofs_net {
     const void* baked[4];          // feats, frames, out, flow2 as currently set in `exec`
     int B, H, W;
     bool out_aligned16;
+    bool feats_aligned16;          // selects the input-pack kernel at capture time (launch_pack_act)
     bool packed16;                 // feats is the 16-bit wire format (repack27_kernel instead of pack_act_kernel)
     cudaGraph_t graph;             // kept alive: its node handles address the nodes of `exec`
     cudaGraphExec_t exec;
@@ -1203,8 +1204,10 @@ int ofs_net_stabilize(ofs_net* n, const float* feats, const float* frames, float
   OFS_CUDA(cudaSetDevice(n->device));
   ++n->graph_clock;
   const bool aligned = (((uintptr_t)out) % 16) == 0;   // selects the warp kernel variant at capture time
+  const bool faligned = (((uintptr_t)feats) % 16) == 0;
   for (auto& g : n->graphs) {
-    if (g.B != B || g.H != H || g.W != W || g.out_aligned16 != aligned || (g.baked[3] == nullptr) != (flow2_out == nullptr) ||
+    if (g.B != B || g.H != H || g.W != W || g.out_aligned16 != aligned || g.feats_aligned16 != faligned ||
+        (g.baked[3] == nullptr) != (flow2_out == nullptr) ||
         g.packed16 != (n->feats_packed16 != 0)) continue;
     g.last_use = n->graph_clock;
     bool same = true;
@@ -1239,7 +1242,7 @@ int ofs_net_stabilize(ofs_net* n, const float* feats, const float* frames, float
   ofs_net::StepGraph sg{};
   for (int w = 0; w < 4; ++w) sg.baked[w] = ptrs[w];
   sg.packed16 = n->feats_packed16 != 0;
-  sg.B = B; sg.H = H; sg.W = W; sg.out_aligned16 = aligned; sg.graph = graph; sg.launches = launches; sg.last_use = n->graph_clock;
+  sg.B = B; sg.H = H; sg.W = W; sg.out_aligned16 = aligned; sg.feats_aligned16 = faligned; sg.graph = graph; sg.launches = launches; sg.last_use = n->graph_clock;
   rc = collect_patches(graph, ptrs, sg.patches);
   if (rc != OFS_OK) { cudaGraphDestroy(graph); return rc; }
   const cudaError_t ie = cudaGraphInstantiate(&sg.exec, graph, 0);

@@ -559,6 +559,20 @@ struct Resize2 {             // fused provider: pre-scaled flow2 [B,fh,fw,2] -> 
   int fh, fw;
   float hs, ws, Wf, Hf;
 };
+// Tap addresses of the tiled warps: a non-negative 32-bit element index times the element size, added to a per-image base
+// that lives in ONE 64-bit register pair (pin_base) -- a single IMAD.WIDE.U32 per address.  Left to itself the compiler
+// keeps the kernel-parameter part of the base apart and spends an LEA / LEA.HI.X (or IMAD.WIDE + IADD3 + IADD3.X) per tap;
+// these kernels are issue-bound (ncu: 77 % issue-active), 8 tap addresses per pixel.
+template <class T>
+__device__ __forceinline__ const T* pin_base(const T* p) {
+  asm("" : "+l"(p));
+  return p;
+}
+template <int kBytes, class T>
+__device__ __forceinline__ const T* tap_ptr(const T* base, int idx) {
+  return reinterpret_cast<const T*>(reinterpret_cast<const char*>(base) + (size_t)(unsigned)idx * (unsigned)kBytes);
+}
+
 __device__ __forceinline__ float div384(float t) {
   const float c = 0.333333343267440796f;   // RN(1/3)
   float q = t * c;
@@ -570,7 +584,7 @@ __device__ __forceinline__ float div384(float t) {
 // flow at a thread's 2 x 2 pixels (rows oy0, oy0+1; columns ox0+lane, ox0+lane+32) of the fused step --
 // main_dl.py:497-498: TF1 legacy bilinear of the pre-scaled flow, then x * W / 512, y * H / 384
 __device__ __forceinline__ void fused_flow_2x2(const Resize2& rz, int b, int ox0, int oy0, int lane, float2 (&f)[2][2]) {
-  const float2* __restrict__ fb = rz.f2 + (size_t)b * rz.fh * rz.fw;
+  const float2* __restrict__ fb = pin_base(rz.f2 + (size_t)b * rz.fh * rz.fw);
   int xa[2], xb[2], ya[2], yb[2];
   float xl[2], yl[2];
 #pragma unroll
@@ -594,8 +608,8 @@ __device__ __forceinline__ void fused_flow_2x2(const Resize2& rz, int b, int ox0
   for (int r = 0; r < 2; ++r)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const float2 tl = __ldg(fb + ya[r] + xa[h]), tr = __ldg(fb + ya[r] + xb[h]);
-      const float2 bl = __ldg(fb + yb[r] + xa[h]), br = __ldg(fb + yb[r] + xb[h]);
+      const float2 tl = __ldg(tap_ptr<8>(fb, ya[r] + xa[h])), tr = __ldg(tap_ptr<8>(fb, ya[r] + xb[h]));
+      const float2 bl = __ldg(tap_ptr<8>(fb, yb[r] + xa[h])), br = __ldg(tap_ptr<8>(fb, yb[r] + xb[h]));
       const float topx = tl.x + (tr.x - tl.x) * xl[h], topy = tl.y + (tr.y - tl.y) * xl[h];
       const float botx = bl.x + (br.x - bl.x) * xl[h], boty = bl.y + (br.y - bl.y) * xl[h];
       const float vx = topx + (botx - topx) * yl[r], vy = topy + (boty - topy) * yl[r];
@@ -604,18 +618,20 @@ __device__ __forceinline__ void fused_flow_2x2(const Resize2& rz, int b, int ox0
     }
 }
 
-template <bool kFused, bool kDirectStore = false>
-__global__ void __launch_bounds__(256, 6) warp5_kernel(const float* __restrict__ img, const float2* __restrict__ flow,
-                                                        Resize2 rz, float* __restrict__ out, int B, int H, int W) {
-  __shared__ __align__(16) float obuf[8][192];
+// kRows output rows per warp (2, or 4: two row pairs, the per-thread column set-up shared), kMinBlocks resident blocks per SM
+template <bool kFused, bool kDirectStore = false, int kRows = 2, int kMinBlocks = 6>
+__global__ void __launch_bounds__(256, kMinBlocks) warp5_kernel(const float* __restrict__ img, const float2* __restrict__ flow,
+                                                                 Resize2 rz, float* __restrict__ out, int B, int H, int W) {
+  __shared__ __align__(16) float obuf[kDirectStore ? 1 : 8][192];
   pdl_wait();
   pdl_launch_dependents();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int Wm1 = W - 1, Hm1 = H - 1;
-  {   // one block per 64 x 16 output tile: grid (tiles_x, tiles_y, B), no tile decode arithmetic
+#pragma unroll
+  for (int rp = 0; rp < kRows / 2; ++rp) {   // one block per 64 x (8 kRows) output tile: grid (tiles_x, tiles_y, B), no tile decode arithmetic
     const int b = blockIdx.z;
-    const int ox0 = blockIdx.x * kTileW, oy0 = blockIdx.y * kTileH + wid * 2;
-    const float* __restrict__ imgb = img + (size_t)b * H * W * 3;
+    const int ox0 = blockIdx.x * kTileW, oy0 = blockIdx.y * (8 * kRows) + wid * kRows + 2 * rp;
+    const float* __restrict__ imgb = pin_base(img + (size_t)b * H * W * 3);
     const int valid_px = min(kTileW, W - ox0);
     // ---- flow at this thread's 2 x 2 pixels (rows oy0, oy0+1; columns ox0+lane, ox0+lane+32)
     float2 f[2][2];
@@ -648,10 +664,10 @@ __global__ void __launch_bounds__(256, 6) warp5_kernel(const float* __restrict__
           const float dx1 = (float)x1 - x, dx0 = x - (float)x0, dy1 = (float)y1 - y, dy0 = y - (float)y0;
           const float wa = dx1 * dy1, wb = dx1 * dy0, wc = dx0 * dy1, wd = dx0 * dy0;
           const int r0 = y0 * W, r1 = y1 * W;
-          const float* pa = imgb + (r0 + x0) * 3;
-          const float* pb = imgb + (r1 + x0) * 3;
-          const float* pc = imgb + (r0 + x1) * 3;
-          const float* pd = imgb + (r1 + x1) * 3;
+          const float* pa = tap_ptr<12>(imgb, r0 + x0);
+          const float* pb = tap_ptr<12>(imgb, r1 + x0);
+          const float* pc = tap_ptr<12>(imgb, r0 + x1);
+          const float* pd = tap_ptr<12>(imgb, r1 + x1);
           if (ox < W) {
             const float a0 = __ldg(pa), a1 = __ldg(pa + 1), a2 = __ldg(pa + 2);
             const float b0 = __ldg(pb), b1 = __ldg(pb + 1), b2 = __ldg(pb + 2);
@@ -670,7 +686,7 @@ __global__ void __launch_bounds__(256, 6) warp5_kernel(const float* __restrict__
           if (ox0 + lane < W) { __stcs(o, v[0][0]); __stcs(o + 1, v[0][1]); __stcs(o + 2, v[0][2]); }
           if (ox0 + lane + 32 < W) { __stcs(o + 96, v[1][0]); __stcs(o + 97, v[1][1]); __stcs(o + 98, v[1][2]); }
         } else {
-          store_row3(obuf[wid], out + (((size_t)b * H + oy) * W + ox0) * 3, lane, valid_px, v[0], v[1]);
+          store_row3(obuf[kDirectStore ? 0 : wid], out + (((size_t)b * H + oy) * W + ox0) * 3, lane, valid_px, v[0], v[1]);
         }
       }
     }
@@ -702,7 +718,7 @@ __global__ void __launch_bounds__(256, 6) warp5_u8_kernel(const uint8_t* __restr
   const int Wm1 = W - 1, Hm1 = H - 1;
   const int b = blockIdx.z;
   const int ox0 = blockIdx.x * kTileW, oy0 = blockIdx.y * kTileH + wid * 2;
-  const uint8_t* __restrict__ imgb = img + (size_t)b * H * W * 3;
+  const uint8_t* __restrict__ imgb = pin_base(img + (size_t)b * H * W * 3);
   float2 f[2][2];
   fused_flow_2x2(rz, b, ox0, oy0, lane, f);
 #pragma unroll
@@ -721,10 +737,10 @@ __global__ void __launch_bounds__(256, 6) warp5_u8_kernel(const uint8_t* __restr
         const float dx1 = (float)x1 - x, dx0 = x - (float)x0, dy1 = (float)y1 - y, dy0 = y - (float)y0;
         const float wa = dx1 * dy1, wb = dx1 * dy0, wc = dx0 * dy1, wd = dx0 * dy0;
         const int r0 = y0 * W, r1 = y1 * W;
-        const uint8_t* pa = imgb + (r0 + x0) * 3;
-        const uint8_t* pb = imgb + (r1 + x0) * 3;
-        const uint8_t* pc = imgb + (r0 + x1) * 3;
-        const uint8_t* pd = imgb + (r1 + x1) * 3;
+        const uint8_t* pa = tap_ptr<3>(imgb, r0 + x0);
+        const uint8_t* pb = tap_ptr<3>(imgb, r1 + x0);
+        const uint8_t* pc = tap_ptr<3>(imgb, r0 + x1);
+        const uint8_t* pd = tap_ptr<3>(imgb, r1 + x1);
         packed[h] = 0;
         if (ox < W) {
           float v[3];
@@ -794,7 +810,7 @@ __global__ void __launch_bounds__(256, 6) sample5_kernel(Provider prov, const fl
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int b = blockIdx.z;
   const int ox0 = blockIdx.x * kTileW, oy0 = blockIdx.y * kTileH + wid * 2;
-  const float* __restrict__ imgb = img + (size_t)b * srcH * srcW * 3;
+  const float* __restrict__ imgb = pin_base(img + (size_t)b * srcH * srcW * 3);
   const typename Provider::Ctx ctx = prov.begin(b);
 #pragma unroll
   for (int rr = 0; rr < 2; ++rr) {
@@ -811,7 +827,7 @@ __global__ void __launch_bounds__(256, 6) sample5_kernel(Provider prov, const fl
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const bool in = tp.x[k] >= 0;
-          const float* p = imgb + (tp.y[k] * srcW + (in ? tp.x[k] : 0)) * 3;
+          const float* p = tap_ptr<12>(imgb, tp.y[k] * srcW + (in ? tp.x[k] : 0));
           px[k][0] = in ? __ldg(p) : 0.0f;
           px[k][1] = in ? __ldg(p + 1) : 0.0f;
           px[k][2] = in ? __ldg(p + 2) : 0.0f;
@@ -895,6 +911,7 @@ int grid_for(size_t work_items, int threads) {
   return (int)blocks;
 }
 
+int g_warp_tuning = 0;   // fused warp only: rows per warp / resident blocks per SM under test (see launch_warp3)
 int g_warp_variant = 3;  // 0 = direct gathers, 1 = staged (12-byte pixels), 2 = staged (padded 16-byte pixels), 3 = lean direct (default)
 
 size_t tile_count(int B, int oH, int oW) {
@@ -939,7 +956,19 @@ int launch_warp3(Provider prov, const float* img, float* out, int B, int H, int 
         Resize2 rz{reinterpret_cast<const float2*>(fr.flow2), fr.fh, fr.fw, fr.hs, fr.ws, (float)W, (float)H};
         // streaming 32-bit stores straight from registers: the three stores of a warp fill whole sectors between them,
         // and dropping the shared-memory transpose saves ~12 instructions per pixel (47.6 -> 45.0 us at 8 x 720p)
-        OFS_CUDA(launch_pdl(warp5_kernel<true, true>, tile_grid3(B, H, W), dim3(256), 0, st, img, (const float2*)nullptr, rz, out, B, H, W));
+        const float2* nf = nullptr;
+        const dim3 g4((unsigned)((W + kTileW - 1) / kTileW), (unsigned)((H + 31) / 32), (unsigned)B);   // 4 rows per warp: 64 x 32 tiles
+        switch (g_warp_tuning) {   // measurement only (ofs_set_warp_variant(3 + 16 t)); 0 = the shipped form
+          case 1: OFS_CUDA(launch_pdl(warp5_kernel<true, true, 4, 6>, g4, dim3(256), 0, st, img, nf, rz, out, B, H, W)); break;
+          case 2: OFS_CUDA(launch_pdl(warp5_kernel<true, true, 2, 5>, tile_grid3(B, H, W), dim3(256), 0, st, img, nf, rz, out, B, H, W)); break;
+          case 3: OFS_CUDA(launch_pdl(warp5_kernel<true, true, 2, 7>, tile_grid3(B, H, W), dim3(256), 0, st, img, nf, rz, out, B, H, W)); break;
+          case 4: OFS_CUDA(launch_pdl(warp5_kernel<true, true, 4, 5>, g4, dim3(256), 0, st, img, nf, rz, out, B, H, W)); break;
+          case 5: OFS_CUDA(launch_pdl(warp5_kernel<true, true, 4, 7>, g4, dim3(256), 0, st, img, nf, rz, out, B, H, W)); break;
+          case 6: OFS_CUDA(launch_pdl(warp5_kernel<true, true, 2, 6>, tile_grid3(B, H, W), dim3(256), 0, st, img, nf, rz, out, B, H, W)); break;
+          // shipped: 8 resident blocks per SM (32 registers, no spills): 42.5 us against 42.9 with 6 at 8 x 720p -- the kernel
+          // is issue-bound and every extra warp helps; 4 rows per warp measured 51 us (benchmarks/warp_tune.py)
+          default: OFS_CUDA(launch_pdl(warp5_kernel<true, true, 2, 8>, tile_grid3(B, H, W), dim3(256), 0, st, img, nf, rz, out, B, H, W));
+        }
         OFS_LAUNCH_CHECK();
         return OFS_OK;
       }
@@ -1054,6 +1083,8 @@ int flow_resize_warp_u8_impl(const uint8_t* img, const float* flow2_prescaled, u
 extern "C" {
 
 int ofs_set_warp_variant(int v) {
+  ofs::g_warp_tuning = (v >= 16 && (v & 15) == 3) ? (v >> 4) : 0;
+  if (v >= 16) v &= 15;
   ofs::g_warp_variant = (v >= 0 && v <= 3) ? v : 3;
   return OFS_OK;
 }

@@ -486,6 +486,33 @@ def test_layer_chain_bit_identical_to_separate_launches(ofs, cuda_dev, monkeypat
         assert torch.equal(res["0"][0][k], res["1"][0][k]), k
 
 
+def test_input_pack_kernels_agree(ofs, cuda_dev, monkeypatch):
+    """The network input [B,384,512,27] float32 is rounded to 16-bit channels-32 pixels by pack27_kernel (a warp streams 32
+    pixels through shared memory with 128-bit loads) when the caller's array is 16-byte aligned, and by the generic
+    pack_act_kernel otherwise: same bits, and the step graph keeps one capture per alignment class."""
+    w = F.make_weights(0, "calibrated", head_scale=0.02)
+    B = 2
+    x = F.make_feats(12, B)
+    buf = torch.empty(x.numel() + 4, device=cuda_dev)
+    aligned = buf[4:].view(x.shape) if buf.data_ptr() % 16 == 0 else buf[:x.numel()].view(x.shape)
+    shifted = buf[1:1 + x.numel()].view(x.shape)
+    assert aligned.data_ptr() % 16 == 0 and shifted.data_ptr() % 16 != 0
+    net = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=B, precision="bf16")
+    net.assign_weights(w)
+    frames = torch.rand((B, 96, 128, 3), device=cuda_dev)
+    res = []
+    for view in (shifted, aligned):          # views of one buffer: fill, run, read back before the next fill
+        view.copy_(x.to(cuda_dev))
+        out = net.forward(view)["predict_flow2"].clone()
+        act = net.activation("input", B).clone()
+        stab = net.stabilize(view, frames).clone()
+        res.append((out, act, stab))
+    assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][1], F.round_bf16(x).to(cuda_dev))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][2], res[1][2])
+    assert net.graph_stats()[0] == 2         # one capture per alignment class of feats
+    net.close()
+
+
 def test_npz_checkpoint_ingest(ofs, cuda_dev, tmp_path):
     """tl.files.load_and_assign_npz_dict (main_dl.py:520): an npz keyed by TF variable names
     ('main_net/flownetS/<layer>/<var>:0', as tl.files.save_npz_dict writes them, main_dl.py:424-426), with
