@@ -177,6 +177,21 @@ struct Predict2Params {
 // One block per 64 x 8 output tile (3-D grid), a thread owns columns lane, lane+32 of one row: the NN source
 // indices come from two small tables (built once on the host with the same fp32 round(dst * (in-1)/(out-1))),
 // the row terms are shared by both pixels, all indexing is 32-bit.
+// x * 384.0f / 382.0f with the rounding of the two float32 operations the reference performs (multiply, then true
+// division): the quotient by the constant is q = t * RN(1/382) corrected once, q' = fma(fma(-382, q, t), RN(1/382), q) --
+// the correctly rounded t / 382 whenever t is a normal number well inside the exponent range (Markstein: a faithful q,
+// the exact remainder by FMA, the correctly rounded reciprocal); anything else takes the IEEE division.
+__device__ __forceinline__ float mul384_div382(float x) {
+  const float t = x * 384.0f;
+  const float c = 0.00261780107393860817f;   // RN(1/382)
+  const float at = fabsf(t);
+  if (at > 1e-30f && at < 1e30f) {
+    const float q = t * c;
+    return __fmaf_rn(__fmaf_rn(-382.0f, q, t), c, q);
+  }
+  return __fdiv_rn(t, 382.0f);
+}
+
 __global__ void __launch_bounds__(256) predict2_gather_kernel(Predict2Params p) {
   pdl_wait();
   pdl_launch_dependents();
@@ -185,44 +200,57 @@ __global__ void __launch_bounds__(256) predict2_gather_kernel(Predict2Params p) 
   const int oy = blockIdx.y * 8 + wid;
   if (oy >= 382) return;
   const int ox0 = blockIdx.x * 64 + lane;
+  // one 64-bit base per array, 32-bit element offsets: a single IMAD.WIDE.U32 per address
   const float* __restrict__ Pb = p.P + (size_t)b * 96 * 128 * 18;
-  int rowoff[3];   // (iy * 128) * 18 + ky * 6, or -1 when the tap reads the zero padding
+  const float2* __restrict__ f3b = p.f3 + (size_t)b * 48 * 64;
+  asm("" : "+l"(Pb));
+  asm("" : "+l"(f3b));
+  int rowoff[3];    // (iy * 128) * 18 + ky * 6 of the tap row, clamped into the array when the tap reads the zero padding
+  bool rowok[3];
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int iy = (int)p.iy_tab[oy + ky];
-    rowoff[ky] = (iy < 0 || iy >= 96) ? -1 : iy * (128 * 18) + ky * 6;
+    rowok[ky] = iy >= 0 && iy < 96;
+    rowoff[ky] = (rowok[ky] ? iy : 0) * (128 * 18) + ky * 6;
   }
   // TF1 bilinear of f3 (48x64 -> 382x510): row terms
   const float fy = (float)oy * p.hs;
   const int y0 = (int)floorf(fy), y1 = min(y0 + 1, 47);
   const float yl = fy - (float)y0;
-  const float2* __restrict__ f3b = p.f3 + (size_t)b * 48 * 64;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int ox = ox0 + 32 * h;
     if (ox >= 510) continue;
-    float a0 = p.bias0, a1 = p.bias1;
     int ix[3];
+    bool colok[3];
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
       const int v = (int)p.ix_tab[ox + kx];
-      ix[kx] = (v < 0 || v >= 128) ? -1 : v * 18 + kx * 2;
+      colok[kx] = v >= 0 && v < 128;
+      ix[kx] = (colok[kx] ? v : 0) * 18 + kx * 2;
     }
+    // all nine taps and the four f3 taps are fetched unconditionally (in-bounds addresses) and in flight together; a tap
+    // on the zero padding contributes -0.0f, which leaves every partial sum unchanged (x + -0 == x for all x)
+    float2 t[3][3];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      if (rowoff[ky] < 0) continue;
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        if (ix[kx] < 0) continue;
-        const float2 v = __ldg(reinterpret_cast<const float2*>(Pb + rowoff[ky] + ix[kx]));
-        a0 += v.x;
-        a1 += v.y;
-      }
-    }
+      for (int kx = 0; kx < 3; ++kx)
+        t[ky][kx] = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const char*>(Pb) + (size_t)(unsigned)(rowoff[ky] + ix[kx]) * 4u));
     const float fx = (float)ox * p.ws;
     const int x0 = (int)floorf(fx), x1 = min(x0 + 1, 63);
     const float xl = fx - (float)x0;
-    const float2 tl = f3b[y0 * 64 + x0], tr = f3b[y0 * 64 + x1], bl = f3b[y1 * 64 + x0], br = f3b[y1 * 64 + x1];
+    const float2 tl = __ldg(f3b + (unsigned)(y0 * 64 + x0)), tr = __ldg(f3b + (unsigned)(y0 * 64 + x1));
+    const float2 bl = __ldg(f3b + (unsigned)(y1 * 64 + x0)), br = __ldg(f3b + (unsigned)(y1 * 64 + x1));
+    float a0 = p.bias0, a1 = p.bias1;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const bool ok = rowok[ky] && colok[kx];
+        a0 += ok ? t[ky][kx].x : -0.0f;
+        a1 += ok ? t[ky][kx].y : -0.0f;
+      }
     const float topx = tl.x + (tr.x - tl.x) * xl, topy = tl.y + (tr.y - tl.y) * xl;
     const float botx = bl.x + (br.x - bl.x) * xl, boty = bl.y + (br.y - bl.y) * xl;
     const float ux = topx + (botx - topx) * yl, uy = topy + (boty - topy) * yl;
@@ -230,7 +258,7 @@ __global__ void __launch_bounds__(256) predict2_gather_kernel(Predict2Params p) 
     for (int i = 0; i < 8; ++i) { a0 += ux; a1 += uy; }  // ElementwiseLayer left fold, model.py:887
     const int idx = (b * 382 + oy) * 510 + ox;
     p.f2[idx] = make_float2(a0, a1);
-    p.f2s[idx] = make_float2(__fdiv_rn(a0 * 384.0f, 382.0f), __fdiv_rn(a1 * 384.0f, 382.0f));
+    p.f2s[idx] = make_float2(mul384_div382(a0), mul384_div382(a1));
   }
 }
 

@@ -20,7 +20,7 @@ static int pdl_mode() {
   if (cached < 0) {
     const char* e = getenv("OFS_PDL");
     cached = e ? atoi(e) : 0;   // default off: with the step graph, PDL on every kernel measured 1.5 % slower
-    if (cached < 0 || cached > 2) cached = 0;
+    if (cached < 0 || cached > 4) cached = 0;
   }
   return cached;
 }
@@ -36,6 +36,10 @@ bool pdl_allow() {
   // selective: only GEMM / helper kernels following GEMM / helper kernels start early (a 225 KB-smem GEMM CTA that
   // lands beside a streaming kernel's blocks shrinks their L1)
   if (mode == 2) return kind != 0 && prev != 0;
+  // 3: only the small helpers behind a GEMM (their blocks fit beside the draining GEMM CTAs: the launch latency of the
+  // split-K reductions and pyramid steps overlaps the GEMM's tail); 4: also the GEMM behind a small helper
+  if (mode == 3) return kind == 2 && prev == 1;
+  if (mode == 4) return (kind == 2 && prev == 1) || (kind == 1 && prev == 2);
   return false;
 }
 

@@ -369,6 +369,36 @@ def test_byte_over_255_formula_matches_both_reference_quotients():
     assert np.count_nonzero(q.astype(np.float32) != cur) > 100        # the plain product is NOT enough
 
 
+def test_times_384_over_382_formula_is_the_float32_division():
+    """predict2_gather_kernel computes (flow2 * 384.0) / 382 (main_dl.py:497: float32 multiply, then true division) as
+    t = x * 384, q = t * c, q' = fma(fma(-382, q, t), c, q) with c = RN(1/382).  Emulated with exact rational arithmetic and
+    one rounding per operation, q' equals np.float32(t) / np.float32(382) on flow-sized values, tiny values and a sweep
+    of exponents; the plain product t * c alone does not."""
+    from fractions import Fraction
+
+    c = np.float32(1.0) / np.float32(382.0)
+    assert c == np.float32(0.00261780107393860817)
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([rng.normal(0, 5, 6000), rng.random(3000) * 1e-3, rng.normal(0, 300, 3000),
+                         2.0 ** rng.integers(-60, 60, 3000) * (rng.random(3000) + 0.5)]).astype(np.float32)
+
+    def rn(fr):                       # exact rational -> float32, round to nearest even
+        d = np.float64(float(fr))     # (float64 first: 53 bits hold every value here far beyond the float32 rounding point)
+        return np.float32(d)
+
+    plain_differs = 0
+    for x in xs:
+        t = np.float32(x * np.float32(384.0))
+        q = np.float32(t * c)
+        r = rn(Fraction(float(t)) - 382 * Fraction(float(q)))
+        assert Fraction(float(r)) == Fraction(float(t)) - 382 * Fraction(float(q))      # the remainder is exact
+        q2 = rn(Fraction(float(r)) * Fraction(float(c)) + Fraction(float(q)))
+        want = t / np.float32(382.0)
+        assert q2 == want, (x, q2, want)
+        plain_differs += int(q != want)
+    assert plain_differs > 100
+
+
 def test_package_and_oracle_generators_agree():
     """bench.py / benchmarks draw random-init checkpoints and inputs from the package (they may not touch oracle/);
     the oracle keeps its own copy.  Same seeds, same arrays."""
