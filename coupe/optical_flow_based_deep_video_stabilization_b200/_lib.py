@@ -61,6 +61,7 @@ PROTOTYPES = {
     "ofs_net_time_kernels": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "ofs_net_launches_per_forward": (_i, [_p]),
     "ofs_net_graph_stats": (_ll, [_p, _i]),
+    "ofs_chain_trace_read": (_i, [_p, _i]),
     "ofs_clips_create": (_i, [_p, _p, _i, _i, _i]),
     "ofs_clips_destroy": (_i, [_p]),
     "ofs_clips_reset": (_i, [_p]),

@@ -663,6 +663,15 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
           ptx::tmem_wait_ld();
           if (valid) epilogue_store<kChunk>(p, v, pix, n0 + c0, ks);
         }
+        if constexpr (kHead > 0) {
+          // split-K with the fused head (deconv4): this split's share of this phase's head goes to plane ks
+          if (p.head_out && n_t == p.tiles_n - 1) {
+            uint32_t hv[16];
+            ptx::tmem_ld16(t_addr + BLOCK_N, hv);
+            ptx::tmem_wait_ld();
+            if (valid) p.head_out[(size_t)ks * (size_t)p.head_split_stride + pix] = make_float2(__uint_as_float(hv[0]), __uint_as_float(hv[1]));
+          }
+        }
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -1915,8 +1924,9 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
     OFS_REQUIRE(d.out_cstride % 8 == 0 && d.out_coff % 8 == 0, "16-bit output slice must be 16-byte aligned");
   }
   if (d.head) {
-    OFS_REQUIRE(deconv && d.out_mode == 0 && d.ksplit <= 1 && (d.block_n == 64 || d.block_n == 128) && (d.cta_group == 1 || d.kgroup == 1),
-                "fused head: transposed conv, 16-bit output, tiles of 64 / 128 columns, no split-K (CTA pairs: no chunk groups)");
+    OFS_REQUIRE(deconv && d.out_mode == 0 && (d.ksplit <= 1 || (d.cta_group == 1 && d.kgroup == 1)) && (d.block_n == 64 || d.block_n == 128) &&
+                    (d.cta_group == 1 || d.kgroup == 1),
+                "fused head: transposed conv, 16-bit output, tiles of 64 / 128 columns (CTA pairs: no chunk groups, no split-K)");
   }
   if (d.stack) {
     OFS_REQUIRE(deconv && d.head && d.cout == 64 && d.block_n == 64 && d.out_mode == 0 && d.ksplit <= 1 && d.kgroup == 1 && !d.slab,
@@ -2147,6 +2157,7 @@ int conv_plan_bind(ConvPlan& plan, const void* act_in, const void* w_dev, const 
     p.sk_counters = p.fused_reduce ? counters : nullptr;
   }
   p.head_out = reinterpret_cast<float2*>(head_out);
+  p.head_split_stride = (long long)d.B * p.out_H * p.out_W;   // the buffer holds ksplit such planes
   OFS_REQUIRE(!d.head || head_out, "conv bind: the fused head needs its output buffer");
   const cuuint32_t tileW = 1u << p.tileW_log2;
   unsigned long long vd[5], vs[4];
@@ -2354,7 +2365,8 @@ extern "C" int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const flo
   if (cta_group == 64 || cta_group == 66) {   // 64 / 66 = phase-stacked transposed conv on 1 CTA / CTA pairs (head weights zero)
     d.stack = 1; d.head = 1; d.cta_group = cta_group == 66 ? 2 : 1; d.block_n = 64;
   }
-  const bool via16 = d.ksplit > 1 || out16 || d.stack || d.slab == 2;   // the network's 16-bit activation epilogue (split-K always reduces into it)
+  if (cta_group == 34 || cta_group == 36) { d.head = 1; d.cta_group = cta_group == 36 ? 2 : 1; }   // per-phase transposed conv with the fused head (head weights zero)
+  const bool via16 = d.ksplit > 1 || out16 || d.stack || d.slab == 2 || d.head;   // the network's 16-bit activation epilogue (split-K always reduces into it)
   const int cout8 = ((Cout + 7) / 8) * 8;
   d.out_mode = via16 ? 0 : 1; d.lrelu = lrelu; d.is_bf16 = is_bf16;
   d.out_cstride = via16 ? cout8 : Cout; d.out_coff = 0;
@@ -2398,7 +2410,7 @@ extern "C" int ofs_conv2d_nhwc_ex(const float* x, const float* w_host, const flo
   if (rc == OFS_OK) rc = check_cuda(cudaMalloc((void**)&b_dev, bp.size() * 4), "cudaMalloc b", __FILE__, __LINE__);
   if (rc == OFS_OK && via16) rc = check_cuda(cudaMalloc(&y16, npix_out * cout8 * 2), "cudaMalloc y16", __FILE__, __LINE__);
   if (rc == OFS_OK && plan.ws_bytes) rc = check_cuda(cudaMalloc((void**)&ws, plan.ws_bytes), "cudaMalloc ws", __FILE__, __LINE__);
-  if (rc == OFS_OK && d.head) rc = check_cuda(cudaMalloc((void**)&hd, npix_out * 8), "cudaMalloc head shares", __FILE__, __LINE__);
+  if (rc == OFS_OK && d.head) rc = check_cuda(cudaMalloc((void**)&hd, npix_out * 8 * (size_t)std::max(1, d.ksplit)), "cudaMalloc head shares", __FILE__, __LINE__);
   if (rc == OFS_OK && plan.n_counters) {
     rc = check_cuda(cudaMalloc((void**)&cnt, (size_t)plan.n_counters * 4), "cudaMalloc counters", __FILE__, __LINE__);
     if (rc == OFS_OK) rc = check_cuda(cudaMemsetAsync(cnt, 0, (size_t)plan.n_counters * 4, st), "zero counters", __FILE__, __LINE__);
@@ -2485,7 +2497,7 @@ extern "C" int ofs_conv2d_bench(int B, int H, int W, int Cin, int in_cs, int Cou
             cudaMalloc((void**)&b_dev, (size_t)plan.p.n_pad * 4) == cudaSuccess &&
             (plan.ws_bytes == 0 || cudaMalloc((void**)&ws, plan.ws_bytes) == cudaSuccess) &&
             (flush_bytes == 0 || cudaMalloc(&fl, flush_bytes) == cudaSuccess) &&
-            (!d.head || cudaMalloc((void**)&hd, npix_out * 8) == cudaSuccess) &&
+            (!d.head || cudaMalloc((void**)&hd, npix_out * 8 * (size_t)std::max(1, d.ksplit)) == cudaSuccess) &&
             cudaMalloc((void**)&cnt, (size_t)(plan.n_counters + 1) * 4) == cudaSuccess &&
             cudaMalloc((void**)&tr, ((size_t)plan.grid * 96 + 4096) * 8) == cudaSuccess &&
             cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess;

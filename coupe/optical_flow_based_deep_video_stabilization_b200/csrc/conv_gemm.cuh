@@ -51,6 +51,8 @@ struct ConvGemmParams {
   int n_pad;           // padded output channels per phase
   int w_rows_phase;    // packed weight rows per phase = n_pad (+ 16 with a fused head)
   float2* head_out;    // fused head: this phase's share per OUTPUT pixel [B, out_H, out_W] (null: no head)
+  long long head_split_stride;  // split-K with the fused head: K split s writes its share of the head into plane s,
+                                // head_out + s * head_split_stride (= B * out_H * out_W); the consumer sums the planes in order
   // epilogue
   void* out;           // 16-bit activations (mode 0) or fp32 (mode 1)
   const float* bias;   // [n_pad]

@@ -67,7 +67,9 @@ __device__ __forceinline__ float2 tf1_bilinear2(const float2* __restrict__ src, 
 }
 
 struct PyrParams {
-  const float2* hpart;   // fused head: per-phase shares at this level [B,2h,2w] (written by the level's deconv GEMM)
+  const float2* hpart;   // fused head: per-phase shares at this level [nsplit][B,2h,2w] (written by the level's deconv GEMM)
+  int nsplit;            // K splits of that GEMM (1 unless it runs split-K): each split leaves its own plane of shares
+  long long split_stride;  // B * 2h * 2w
   float hb0, hb1;        // head bias
   const float2* f_prev;  // summed flow of the coarser level [B,h/2,w/2] or null (level 6)
   float2* f_out;         // summed flow at this level [B,h,w]
@@ -80,7 +82,13 @@ struct PyrParams {
 __device__ __forceinline__ float2 pyr_flow_at(const PyrParams& p, int b, int i, int j) {
   // predictN = sum of the 4 phase shares (fixed order) + bias (model.py:847-848,855-856,864-865,873-874)
   const float2* hp = p.hpart + ((size_t)b * 2 * p.h + 2 * i) * (2 * p.w) + 2 * j;
-  const float2 s00 = hp[0], s01 = hp[1], s10 = hp[2 * p.w], s11 = hp[2 * p.w + 1];
+  float2 s00 = hp[0], s01 = hp[1], s10 = hp[2 * p.w], s11 = hp[2 * p.w + 1];
+  for (int k = 1; k < p.nsplit; ++k) {   // split-K: a phase share is the sum of its K splits, in split order
+    const float2* hk = hp + (size_t)k * p.split_stride;
+    const float2 t00 = hk[0], t01 = hk[1], t10 = hk[2 * p.w], t11 = hk[2 * p.w + 1];
+    s00.x += t00.x; s00.y += t00.y; s01.x += t01.x; s01.y += t01.y;
+    s10.x += t10.x; s10.y += t10.y; s11.x += t11.x; s11.y += t11.y;
+  }
   float2 v;
   v.x = ((s00.x + s01.x) + (s10.x + s11.x)) + p.hb0;
   v.y = ((s00.y + s01.y) + (s10.y + s11.y)) + p.hb1;
@@ -446,6 +454,7 @@ struct Layer {
   int n_pad = 0;
 };
 constexpr int kCounters = 2048;
+constexpr int kMaxHeadSplits = 4;   // planes of fused-head shares per level (a split-K deconv writes one per split)
 
 struct ActInfo { void* ptr; int H, W, cs, coff, C; };
 
@@ -640,6 +649,10 @@ int prepare(ofs_net* n, int B) {
       return OFS_EINVAL;
     }
     if (L.d.slab) { cg = 2; bn = L.d.block_n; ks = 1; }   // the packed K order is the slab order: tiling is fixed
+    if (L.d.head && ks > kMaxHeadSplits) {
+      set_error("layer %s: split-K %d exceeds the %d planes of fused-head shares", L.name.c_str(), ks, kMaxHeadSplits);
+      return OFS_EINVAL;
+    }
     if (L.d.stack) {   // stacked deconv: only 1 CTA / CTA pair is a choice
       bn = L.d.block_n; ks = 1; if (cg != 1) cg = 2;
       L.d.cta_group = cg;
@@ -722,6 +735,11 @@ int launch_pyr(ofs_net* n, int level, int B, cudaStream_t st) {
   static const int hs[7] = {0, 0, 0, 48, 24, 12, 6}, ws[7] = {0, 0, 0, 64, 32, 16, 8};
   PyrParams p;
   p.hpart = reinterpret_cast<const float2*>(n->hpart[level]);
+  p.nsplit = 1;
+  for (const Layer& L : n->layers)
+    if (L.d.head && L.name == (level == 6 ? "deconv5" : level == 5 ? "deconv4" : level == 4 ? "deconv3" : "deconv2"))
+      p.nsplit = std::max(1, L.plan.p.ksplit);
+  p.split_stride = (long long)B * 4 * hs[level] * ws[level];
   p.hb0 = n->heads[6 - level].bias[0]; p.hb1 = n->heads[6 - level].bias[1];
   p.f_prev = level == 6 ? nullptr : reinterpret_cast<const float2*>(n->f[level + 1]);
   p.f_out = reinterpret_cast<float2*>(n->f[level]);
@@ -934,7 +952,7 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
   static const int hs[7] = {0, 0, 382, 48, 24, 12, 6}, ws[7] = {0, 0, 510, 64, 32, 16, 8};
   for (int l = 2; l <= 6; ++l) {
     rc = dev_alloc(n, (void**)&n->f[l], B * hs[l] * ws[l] * 2 * 4, true);
-    if (rc == OFS_OK && l >= 3) rc = dev_alloc(n, (void**)&n->hpart[l], B * 4 * hs[l] * ws[l] * 2 * 4, true);
+    if (rc == OFS_OK && l >= 3) rc = dev_alloc(n, (void**)&n->hpart[l], kMaxHeadSplits * B * 4 * hs[l] * ws[l] * 2 * 4, true);
     if (rc != OFS_OK) { ofs_net_destroy(n); return rc; }
   }
   rc = dev_alloc(n, (void**)&n->P2, B * 96 * 128 * 18 * 4, true);
@@ -1019,6 +1037,10 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
     // the level's flow head rides in the deconv GEMM (128 / 64-column tiles); CTA pairs halve the B fetch per CTA
     else if (L.d.kind == kDeconvK4S2) {
       L.d.head = 1; L.cta_group = L.name == "deconv5" ? 1 : 2;   // deconv5 (3 M tiles): single CTAs 13.8 vs 14.5 us
+      // deconv4 (M = 1536 rows: 12 M tiles x 4 phases = 48 units of 68 K blocks) keeps a third of the machine busy, but
+      // single CTAs x split-K 3 = 144 units (the head's shares leave per split and are summed by pyr_kernel: built,
+      // tested, OFS_TUNE=deconv4:128:3:1) measured 27.1 us against 24.5 us for the pairs: the fp32 partials and the
+      // reduce launch cost more than the idle SMs (profiles/r02_tuning.md section 7)
       // deconv2 (cout 64): all four sub-pixel phases stacked in one accumulator tile, each input tap fetched once
       // (deconv_stack_kernel); fixes the packed weight layout.  OFS_NOSTACK=1: the per-phase form (A/B).
       if (L.name == "deconv2" && !(getenv("OFS_NOSTACK") && getenv("OFS_NOSTACK")[0] == '1')) { L.d.stack = 1; L.d.cta_group = 2; }

@@ -136,6 +136,11 @@ TILING_CASES = [
     pytest.param(7, 48, 64, 64, 256, 3, 1, False, 256, -1, 2, id="tail_half_pairs_84_pair_tiles"),
     pytest.param(7, 46, 64, 64, 256, 3, 1, False, 256, -1, 2, id="tail_half_pairs_odd_tile_count_161"),
     pytest.param(5, 96, 64, 64, 256, 3, 2, False, 256, -1, 2, id="pairs_n256_k3s2_out16"),
+    # transposed conv with the fused head on single CTAs (cta_group = 34) and split-K: the deconv4 form (the head's
+    # shares leave per split; the network tests check their sum)
+    pytest.param(2, 12, 16, 1026, 256, 4, 2, True, 128, 3, 34, id="deconv4_form_head_splitk3"),
+    pytest.param(3, 6, 8, 200, 128, 4, 2, True, 128, 2, 34, id="deconv_head_splitk2_ragged_batch"),
+    pytest.param(1, 12, 16, 130, 128, 4, 2, True, 64, 4, 34, id="deconv_head_splitk4_two_n_tiles"),
     # cluster split-K (cta_group = 16: the K splits of a tile are one thread-block cluster, reduced through DSMEM)
     pytest.param(3, 6, 8, 512, 512, 3, 1, False, 256, 8, 16, id="kcluster8_whole_image_tiles_ragged_batch"),
     pytest.param(2, 12, 16, 256, 256, 3, 2, False, 256, 4, 16, id="kcluster4_k3s2"),
