@@ -46,7 +46,7 @@ def launch_shares():
             "dense-layer set replayed 2 x 20 times by ofs_net_time_kernels).  ONE step of the hot path (from the input pack",
             "to the fused warp, first complete step in the list):", "", "| kernel | launches | total us | share |", "|---|---:|---:|---:|"]
     names = [short(d["Kernel Name"]) for d in data]
-    start = next(i for i, k in enumerate(names) if k.startswith("pack_act"))
+    start = next(i for i, k in enumerate(names) if k.startswith(("pack_act", "pack27")))
     end = next(i for i in range(start, len(names)) if names[i].startswith("warp5"))
     step, stot = collections.OrderedDict(), 0.0
     for d in data[start:end + 1]:

@@ -93,11 +93,16 @@ def main():
                                         ms=ms, gbs=px * 32 / ms / 1e6))
                 ofs.set_warp_variant(3)
                 del flow
+            # the stand-alone fused op on two flows: white noise per flow pixel (every gather lands in its own sector: the
+            # adversarial case) and a smooth field like the network's (what the in-network roofline line measures)
             f2 = torch.randn((B, 382, 510, 2), generator=gen).to(dev) * 2.0
-            ofs.flow_resize_warp(img, f2)
-            ms = timed(lambda: ofs.flow_resize_warp(img, f2), flush, iters)
-            results.append(dict(op="flow_resize_warp", variant="lean", flow="net-like N(0,2^2)", B=B, H=H, W=W, ms=ms,
-                                gbs=(px * 24 + B * 382 * 510 * 8) / ms / 1e6))
+            low = torch.randn((B, 2, 14, 18), generator=gen) * 3.0
+            f2s = torch.nn.functional.interpolate(low, size=(382, 510), mode="bicubic", align_corners=False).permute(0, 2, 3, 1).contiguous().to(dev)
+            for fl, label in ((f2, "white noise N(0,2^2)"), (f2s, "smooth (network-like)")):
+                ofs.flow_resize_warp(img, fl)
+                ms = timed(lambda: ofs.flow_resize_warp(img, fl), flush, iters)
+                results.append(dict(op="flow_resize_warp", variant="lean", flow=label, B=B, H=H, W=W, ms=ms,
+                                    gbs=(px * 24 + B * 382 * 510 * 8) / ms / 1e6))
             c, s_ = np.cos(np.deg2rad(5)) * 1.02, np.sin(np.deg2rad(5)) * 1.02
             th6 = torch.tensor([[c, -s_, 0.01, s_, c, -0.02]] * B, dtype=torch.float32, device=dev)
             aff = ofs.AffineTransformer((H, W))

@@ -89,6 +89,18 @@ struct FlowResize {
   }
 };
 
+// The four taps of a bilinear sample as two source rows x two source columns -- what every coordinate model here
+// produces -- for the tiled kernel: r0 / r1 are ELEMENT offsets of the rows (y * srcW), c0 / c1 the columns, all clamped
+// into the image so that every tap can be fetched unconditionally; w[] are the weights in the reference's summation
+// order (r0c0, r0c1, r1c0, r1c1), already ZERO for a tap that falls outside the image: the reference multiplies such a
+// tap by a zero pixel, w * 0 = +-0, and a rounded product of +-0 leaves the running sum unchanged, exactly as 0 * pixel does.
+struct RowColTaps {
+  int r0, r1, c0, c1;
+  float w[4];
+};
+// yp in [lo, lo + n) as ONE unsigned compare
+__device__ __forceinline__ bool in_range(int v, int lo, int n) { return (unsigned)(v - lo) < (unsigned)n; }
+
 // ---- spatial_transformer.py:755-779 + 442-451 / 578-602 + 916-961 -------------------------------
 struct GridSampleCoord {
   const float* theta;  // [B,6] or [B,8]
@@ -138,6 +150,42 @@ struct GridSampleCoord {
     put(2, y1, x0, (x1f - x) * (y - y0f));  // w10 I10
     put(3, y1, x1, (x - x0f) * (y - y0f));  // w11 I11
     return tp;
+  }
+  __host__ __device__ __forceinline__ bool flag() const { return projective != 0; }
+  // the same coordinates and weights as taps() (operation for operation), in row / column form; kProj compiles the
+  // projective division in or out
+  template <bool kProj>
+  __device__ __forceinline__ RowColTaps rc(const Ctx& c, int oy, int ox) const {
+    const float xt = (oW == 1) ? -1.0f : __fadd_rn(-1.0f, __fmul_rn(step_x, (float)ox));
+    const float yt = (oH == 1) ? -1.0f : __fadd_rn(-1.0f, __fmul_rn(step_y, (float)oy));
+    float xs = c.t[0] * xt + c.t[1] * yt + c.t[2];
+    float ys = c.t[3] * xt + c.t[4] * yt + c.t[5];
+    if (kProj) {
+      float zs = c.t[6] * xt + c.t[7] * yt + 1.0f;
+      if (zs == 0.0f) zs = zs + 1e-8f;
+      xs = __fdiv_rn(xs, zs);
+      ys = __fdiv_rn(ys, zs);
+    }
+    const float Wf = (float)W, Hf = (float)H;
+    float x = __fmul_rn(__fmul_rn(__fadd_rn(xs, 1.0f), 0.5f), Wf - 1.0f);
+    float y = __fmul_rn(__fmul_rn(__fadd_rn(ys, 1.0f), 0.5f), Hf - 1.0f);
+    x = fminf(fmaxf(x, -1.0f), Wf) + 1.0f;
+    y = fminf(fmaxf(y, -1.0f), Hf) + 1.0f;
+    const float x0f = floorf(x), y0f = floorf(y);
+    const float x1f = x0f + 1.0f, y1f = y0f + 1.0f;
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const int x1 = (int)fminf(x1f, Wf + 1.0f), y1 = (int)fminf(y1f, Hf + 1.0f);
+    // coordinates are on the 1-px zero-padded image: valid rows / columns are 1..H / 1..W
+    const bool vy0 = in_range(y0, 1, H), vy1 = in_range(y1, 1, H), vx0 = in_range(x0, 1, W), vx1 = in_range(x1, 1, W);
+    RowColTaps t;
+    t.r0 = (vy0 ? y0 - 1 : 0) * W; t.r1 = (vy1 ? y1 - 1 : 0) * W;
+    t.c0 = vx0 ? x0 - 1 : 0; t.c1 = vx1 ? x1 - 1 : 0;
+    const float ax = x1f - x, bx = x - x0f, ay = y1f - y, by = y - y0f;
+    t.w[0] = (vy0 && vx0) ? ax * ay : 0.0f;
+    t.w[1] = (vy0 && vx1) ? bx * ay : 0.0f;
+    t.w[2] = (vy1 && vx0) ? ax * by : 0.0f;
+    t.w[3] = (vy1 && vx1) ? bx * by : 0.0f;
+    return t;
   }
 };
 
@@ -191,6 +239,34 @@ struct LieCoord {
     put(3, yci, xci, xr * yr);                    // BR
     return tp;
   }
+  __host__ __device__ __forceinline__ bool flag() const { return false; }
+  template <bool>
+  __device__ __forceinline__ RowColTaps rc(const Ctx& c, int oy, int ox) const {
+    const float* M = c.M;
+    const float X = (oW == 1) ? -1.0f : (ox == oW - 1 ? 1.0f : (float)(-1.0 + (double)ox * c.sx));
+    const float Y = (oH == 1) ? -1.0f : (oy == oH - 1 ? 1.0f : (float)(-1.0 + (double)oy * c.sy));
+    const float h0 = M[0] * X + M[1] * Y + M[2];
+    const float h1 = M[3] * X + M[4] * Y + M[5];
+    const float h2 = M[6] * X + M[7] * Y + M[8];
+    const float Xw = __fdiv_rn(h0, h2 + 1e-8f);
+    const float Yw = __fdiv_rn(h1, h2 + 1e-8f);
+    const float xf = floorf(Xw), xc = ceilf(Xw), yf = floorf(Yw), yc = ceilf(Yw);
+    const float xr = Xw - xf, yr = Yw - yf;
+    const int xfi = (int)fminf(fmaxf(xf, -2.0f), (float)srcW + 1.0f);
+    const int xci = (int)fminf(fmaxf(xc, -2.0f), (float)srcW + 1.0f);
+    const int yfi = (int)fminf(fmaxf(yf, -2.0f), (float)srcH + 1.0f);
+    const int yci = (int)fminf(fmaxf(yc, -2.0f), (float)srcH + 1.0f);
+    const bool vy0 = in_range(yfi, 0, srcH), vy1 = in_range(yci, 0, srcH), vx0 = in_range(xfi, 0, srcW), vx1 = in_range(xci, 0, srcW);
+    RowColTaps t;
+    t.r0 = (vy0 ? yfi : 0) * srcW; t.r1 = (vy1 ? yci : 0) * srcW;
+    t.c0 = vx0 ? xfi : 0; t.c1 = vx1 ? xci : 0;
+    const float ax = 1.0f - xr, ay = 1.0f - yr;
+    t.w[0] = (vy0 && vx0) ? ax * ay : 0.0f;   // UL
+    t.w[1] = (vy0 && vx1) ? xr * ay : 0.0f;   // UR
+    t.w[2] = (vy1 && vx0) ? ax * yr : 0.0f;   // BL
+    t.w[3] = (vy1 && vx1) ? xr * yr : 0.0f;   // BR
+    return t;
+  }
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -221,6 +297,9 @@ struct CoordProvider {
   __device__ __forceinline__ Ctx begin(int b) const { return c.begin(b); }
   __device__ __forceinline__ Taps taps(const Ctx& ctx, int oy, int ox) const { return c.taps(ctx, oy, ox); }
   __device__ __forceinline__ Taps taps(int b, int oy, int ox) const { return c.taps(b, oy, ox); }
+  template <bool kFlag>
+  __device__ __forceinline__ RowColTaps rc(const Ctx& ctx, int oy, int ox) const { return c.template rc<kFlag>(ctx, oy, ox); }
+  bool flag() const { return c.flag(); }
 };
 
 // acc + w*v as two separately rounded fp32 operations (no FMA contraction): the reference sums
@@ -799,9 +878,13 @@ __global__ void __launch_bounds__(256) warp_u8_px_kernel(ResizeWarpProvider prov
   }
 }
 
-// generic 4-tap sampler (grid_sample / Lie warp), lean form of sample3_kernel: one block per 64 x 16 output tile
-// (3-D grid), 32-bit image offsets, predicated loads instead of per-tap branches, 6 resident blocks per SM
-template <class Provider>
+// 4-tap sampler of the coordinate models (grid_sample / Lie warp): one block per 64 x 16 output tile (3-D grid), a thread
+// owns columns lane, lane + 32 of two rows.  The taps arrive as two rows x two columns with the weights of outside taps
+// already zero (RowColTaps), so the 12 loads of a pixel are unconditional, every address is one IMAD.WIDE.U32 off a
+// pinned base, and the sum is the reference's: rounded products added in tap order.  kFlag: the model's compile-time
+// switch (GridSampleCoord: projective division).  [round 1's form built per-tap validity, selects on all 12 loaded values
+// and both the affine and the projective path into one kernel: 250 instructions per pixel, 0.45-0.48 of HBM peak]
+template <class Provider, bool kFlag>
 __global__ void __launch_bounds__(256, 6) sample5_kernel(Provider prov, const float* __restrict__ img,
                                                          float* __restrict__ out, int B, int srcH, int srcW, int oH,
                                                          int oW) {
@@ -822,24 +905,18 @@ __global__ void __launch_bounds__(256, 6) sample5_kernel(Provider prov, const fl
       const int ox = ox0 + lane + 32 * h;
       v[h][0] = v[h][1] = v[h][2] = 0.0f;
       if (ox < oW) {
-        const Taps tp = prov.taps(ctx, oy, ox);
-        float px[4][3];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const bool in = tp.x[k] >= 0;
-          const float* p = tap_ptr<12>(imgb, tp.y[k] * srcW + (in ? tp.x[k] : 0));
-          px[k][0] = in ? __ldg(p) : 0.0f;
-          px[k][1] = in ? __ldg(p + 1) : 0.0f;
-          px[k][2] = in ? __ldg(p + 2) : 0.0f;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {   // rounded products summed in tap order; an outside tap adds exactly +0
-          if (tp.x[k] >= 0) {
-            v[h][0] = mul_add_rn(v[h][0], tp.w[k], px[k][0]);
-            v[h][1] = mul_add_rn(v[h][1], tp.w[k], px[k][1]);
-            v[h][2] = mul_add_rn(v[h][2], tp.w[k], px[k][2]);
-          }
-        }
+        const RowColTaps t = prov.template rc<kFlag>(ctx, oy, ox);
+        const float* pa = tap_ptr<12>(imgb, t.r0 + t.c0);
+        const float* pb = tap_ptr<12>(imgb, t.r0 + t.c1);
+        const float* pc = tap_ptr<12>(imgb, t.r1 + t.c0);
+        const float* pd = tap_ptr<12>(imgb, t.r1 + t.c1);
+        const float a0 = __ldg(pa), a1 = __ldg(pa + 1), a2 = __ldg(pa + 2);
+        const float b0 = __ldg(pb), b1 = __ldg(pb + 1), b2 = __ldg(pb + 2);
+        const float c0 = __ldg(pc), c1 = __ldg(pc + 1), c2 = __ldg(pc + 2);
+        const float d0 = __ldg(pd), d1 = __ldg(pd + 1), d2 = __ldg(pd + 2);
+        v[h][0] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t.w[0], a0), __fmul_rn(t.w[1], b0)), __fmul_rn(t.w[2], c0)), __fmul_rn(t.w[3], d0));
+        v[h][1] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t.w[0], a1), __fmul_rn(t.w[1], b1)), __fmul_rn(t.w[2], c1)), __fmul_rn(t.w[3], d1));
+        v[h][2] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t.w[0], a2), __fmul_rn(t.w[1], b2)), __fmul_rn(t.w[2], c2)), __fmul_rn(t.w[3], d2));
       }
     }
     float* o = out + (((size_t)b * oH + oy) * oW + ox0 + lane) * 3;
@@ -932,7 +1009,8 @@ int launch_sampler(Provider prov, const float* img, float* out, int B, int srcH,
   if (B == 0 || oH == 0 || oW == 0) return OFS_OK;
   if (C == 3 && (oW % 4) == 0 && (((uintptr_t)out) % 16 == 0)) {
     if ((size_t)srcH * srcW * 3 < (1u << 31) && B <= 65535 && (oH + kTileH - 1) / kTileH <= 65535) {
-      sample5_kernel<Provider><<<tile_grid3(B, oH, oW), 256, 0, st>>>(prov, img, out, B, srcH, srcW, oH, oW);
+      if (prov.flag()) sample5_kernel<Provider, true><<<tile_grid3(B, oH, oW), 256, 0, st>>>(prov, img, out, B, srcH, srcW, oH, oW);
+      else sample5_kernel<Provider, false><<<tile_grid3(B, oH, oW), 256, 0, st>>>(prov, img, out, B, srcH, srcW, oH, oW);
     } else {
       const size_t nt = tile_count(B, oH, oW);
       sample3_kernel<Provider><<<tile_grid(nt, 8), 256, 0, st>>>(prov, img, out, B, srcH, srcW, oH, oW);

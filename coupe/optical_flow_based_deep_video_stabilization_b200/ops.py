@@ -86,7 +86,9 @@ def flow_resize_warp(img, flow2, out_h=None, out_w=None):
 
 
 def set_warp_variant(variant):
-    """1 = shared-memory staged tf_warp (default), 0 = direct gathers.  Identical results."""
+    """A/B switch of the tf_warp kernels (identical results): 3 = lean direct gathers (default), 0 = first direct kernel,
+    1 / 2 = shared-memory staged (12-byte / padded 16-byte pixels).  3 + 16 t selects launch shape t of the fused warp
+    (benchmarks/warp_tune.py)."""
     _lib.check(_lib.load().ofs_set_warp_variant(int(variant)))
 
 

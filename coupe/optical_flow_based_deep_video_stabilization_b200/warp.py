@@ -42,9 +42,23 @@ def inverse(config, p):
     return torch.neg(p) if isinstance(p, torch.Tensor) else np.negative(p)
 
 
+_REF_CACHE = {}
+
+
 def _ref_tensor(ref, device):
-    t = ref if isinstance(ref, torch.Tensor) else torch.as_tensor(np.asarray(ref, dtype=np.float32))
-    return t.to(device=device, dtype=torch.float32).contiguous()
+    """config.refMtrx on the device.  The reference keeps it as a numpy constant of the config; uploading it on every
+    call is a synchronous pageable copy (~30 us, the whole cost of a small transformImage), so host matrices are cached
+    by value per device."""
+    if isinstance(ref, torch.Tensor):
+        return ref.to(device=device, dtype=torch.float32).contiguous()
+    arr = np.ascontiguousarray(ref, dtype=np.float32)
+    key = (arr.tobytes(), arr.shape, str(device))
+    t = _REF_CACHE.get(key)
+    if t is None:
+        if len(_REF_CACHE) >= 64:
+            _REF_CACHE.clear()
+        t = _REF_CACHE[key] = torch.as_tensor(arr).to(device=device)
+    return t
 
 
 def vec2mtrx(config, p):

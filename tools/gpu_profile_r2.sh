@@ -10,6 +10,6 @@ timeout 600 python bench.py --streams 1 --no-cpu-baseline --sustained-seconds 0 
 CMD="env OFS_GRAPH=0 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --sustained-seconds 0"
 $CMD > gpurun_out/plain.log 2>&1 && timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 $CMD > gpurun_out/plain2.log 2>&1 && timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"conv_gemm|deconv_stack|splitk_reduce" -s 38 -c 19 -o gpurun_out/prof_conv -f $CMD > gpurun_out/ncu_conv.log 2>&1
-$CMD > gpurun_out/plain3.log 2>&1 && timeout 900 ncu --set full --clock-control none --import-source on -k regex:"warp5|pack_act|predict2_gather|pyr_kernel" -s 14 -c 7 -o gpurun_out/prof_misc -f $CMD > gpurun_out/ncu_misc.log 2>&1
+$CMD > gpurun_out/plain3.log 2>&1 && timeout 900 ncu --set full --clock-control none --import-source on -k regex:"warp5|pack_act|pack27|predict2_gather|pyr_kernel" -s 14 -c 7 -o gpurun_out/prof_misc -f $CMD > gpurun_out/ncu_misc.log 2>&1
 tail -2 gpurun_out/ncu_launches.log gpurun_out/ncu_conv.log gpurun_out/ncu_misc.log
 ls -la gpurun_out | head -40
