@@ -249,6 +249,18 @@ def run_ours(args):
     for i in range(max(args.warmup, 3) * nstreams):
         step(i)
     barrier()
+    # ---- the two roofline kernels timed ALONE and FIRST, on a GPU that has only run the warm-up steps: the tensor
+    # denominator is the BURST bf16 peak (MEASURED_PEAKS: a kernel timed alone from idle), so the numerator is taken in
+    # the same state -- after the K-step region and the sustained block the SM clock sits at the 1 kW power cap
+    # (~1.68 GHz against 1.965) and the same launch set reads ~10 % slower; that second reading is reported beside it,
+    # against the SUSTAINED peak
+    burst = None
+    if rank == 0:
+        time.sleep(0.5)
+        g_ms, g_macs, g_launches = net.time_kernels("dense", BATCH, iters=20)
+        w_ms, _, _ = net.time_kernels("warp", BATCH, frames=sets[0][1], iters=20)
+        burst = (g_ms, g_macs, g_launches, w_ms)
+    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -301,28 +313,37 @@ def run_ours(args):
         step_ms = (single_ms if single_ms else ms_total) / args.steps   # shares refer to one step executed alone
         # dominant kernel = the tcgen05 implicit-GEMM conv: its 14 launches per step (plus split-K reductions) are
         # replayed from one CUDA graph, exactly as the step runs them, between two CUDA events on the net's stream
-        gemm_ms, macs, gemm_launches = net.time_kernels("dense", BATCH, iters=20)
+        # ... and once more now, after the K-step region and the sustained block (hot, at the power cap)
+        hot_ms, macs, gemm_launches = net.time_kernels("dense", BATCH, iters=20)
+        hot_wms, _, _ = net.time_kernels("warp", BATCH, frames=sets[0][1], iters=20)
+        gemm_ms, _, _, wms = burst
         flops = 2.0 * macs
         ach = flops / (gemm_ms * 1e-3) / 1e12
+        hot_ach = flops / (hot_ms * 1e-3) / 1e12
         ncu = load_ncu_traffic()
-        # the launch set is timed alone as a ~10 ms graph replay at boost clocks: the BURST peak is the denominator
         roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": ach / peaks["bf16_tflops"], "traffic": ncu.get("dense_set_bytes") if ncu else None,
                     "traffic_source": (ncu["source"] + " (ncu --set full: DRAM bytes of the launch set)") if ncu else None,
                     "kernel": "conv_gemm*_kernel (the 14 dense conv / transposed-conv layers of one step, incl. split-K reductions)",
-                    "launches_per_step": gemm_launches, "ms_per_step_in_kernel": gemm_ms, "share_of_step": gemm_ms / step_ms,
-                    "algorithmic_gflop_per_launch_set": flops / 1e9, "peak_source": peaks["source"] + " (burst bf16: kernel set timed alone)",
-                    "frac_of_sustained_peak": ach / peaks["bf16_tflops_sustained"], "peak_sustained": peaks["bf16_tflops_sustained"],
+                    "launches_per_step": gemm_launches, "ms_per_step_in_kernel": gemm_ms, "share_of_step": hot_ms / step_ms,
+                    "algorithmic_gflop_per_launch_set": flops / 1e9,
+                    "peak_source": peaks["source"] + " (burst bf16; the launch set timed alone right after the warm-up steps, before any long timed region)",
+                    "after_sustained_load": {"ms_per_step_in_kernel": hot_ms, "achieved": hot_ach, "peak_sustained": peaks["bf16_tflops_sustained"],
+                                             "frac_of_sustained_peak": hot_ach / peaks["bf16_tflops_sustained"],
+                                             "frac_of_burst_peak": hot_ach / peaks["bf16_tflops"],
+                                             "note": "the same launch set timed again after the K-step region and the sustained block (SM clock at the power cap)"},
+                    "frac_of_sustained_peak": hot_ach / peaks["bf16_tflops_sustained"], "peak_sustained": peaks["bf16_tflops_sustained"],
                     "frac_of_nominal_2250": ach / 2250.0,
                     "timing": "20 repetitions of the launch set replayed from one CUDA graph, CUDA events on the launching stream"}
-        wms, _, _ = net.time_kernels("warp", BATCH, frames=sets[0][1], iters=20)
         wbytes = BATCH * (FRAME_H * FRAME_W * WARP_BYTES_PER_PX + FLOW2_BYTES)
         wach = wbytes / (wms * 1e-3) / 1e9
         roofline_warp = {"bound": "hbm", "achieved": wach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": wach / peaks["hbm_gbs"], "traffic": ncu.get("warp_bytes") if ncu else None,
                          "kernel": "warp5_kernel<true> (fused flow-resize + tf_warp)",
                          "ms_per_launch": wms, "algorithmic_bytes_per_launch": wbytes, "frac_of_nominal_7700": wach / 7700.0,
-                         "share_of_step": wms / step_ms, "peak_source": peaks["source"]}
+                         "share_of_step": hot_wms / step_ms, "peak_source": peaks["source"] + " (timed alone right after the warm-up steps)",
+                         "after_sustained_load": {"ms_per_launch": hot_wms, "achieved": wbytes / (hot_wms * 1e-3) / 1e9,
+                                                  "frac": wbytes / (hot_wms * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
         breakdown = [{"kernel": n, "ms": round(ms, 4), "tflops": (2 * m / (ms * 1e-3) / 1e12 if m else None)} for n, ms, m in prof]
 
     # ---- e2e: the C-ABI host-buffer call, pinned host inputs, H2D + compute + D2H every step
