@@ -446,12 +446,17 @@ __device__ __forceinline__ void conv_gemm_body(const ConvGemmParams& p) {
                 const int gi = gi0 + i;
                 const int gn = (int)p.grp_n[gi];
                 for (int t = 0; t < gn; ++t) {
-                  const uint32_t a_lo = da + ((dbg & 128) ? 0u : (uint32_t)p.grp_off[gi][t] * 8u);   // debug 128: timing of aligned windows
+                  const uint32_t code = (uint32_t)(uint16_t)p.grp_off[gi][t];   // row shift | one-pixel code << 8
+                  const uint32_t a_lo = da + ((dbg & 128) ? 0u : (code & 0xffu) * 8u);   // debug 128: timing of aligned windows
                   const uint32_t b_lo = db + (uint32_t)t * (uint32_t)(Cfg::kBBytes >> 4);
-                  lean::mma<kPair>(d_tmem, a_lo, b_lo, kDescHi, idesc, (i > 0 || t > 0) ? 1u : 0u);
-                  lean::mma<kPair>(d_tmem, a_lo + 2, b_lo + 2, kDescHi, idesc, 1u);
-                  lean::mma<kPair>(d_tmem, a_lo + 4, b_lo + 4, kDescHi, idesc, 1u);
-                  lean::mma<kPair>(d_tmem, a_lo + 6, b_lo + 6, kDescHi, idesc, 1u);
+                  // two-pixel form: a tap that feeds one output pixel is a half-width MMA into that pixel's columns
+                  const uint32_t hf = code >> 8;
+                  const uint32_t id_t = hf ? idesc_half : idesc;
+                  const uint32_t d_t = d_tmem + (hf == 2u ? (uint32_t)(BLOCK_N / 2) : 0u);
+                  lean::mma<kPair>(d_t, a_lo, b_lo, kDescHi, id_t, (i > 0 || t > 0) ? 1u : 0u);
+                  lean::mma<kPair>(d_t, a_lo + 2, b_lo + 2, kDescHi, id_t, 1u);
+                  lean::mma<kPair>(d_t, a_lo + 4, b_lo + 4, kDescHi, id_t, 1u);
+                  lean::mma<kPair>(d_t, a_lo + 6, b_lo + 6, kDescHi, id_t, 1u);
                 }
               } else if constexpr (kG > 1) {
                 // chunk group (ksplit == 1): stage i of a tap holds chunks [kG*j, kG*j + gc) of that tap
@@ -1865,14 +1870,17 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
     const int pad = d.k / 2;
     plan.wt_ky.clear(); plan.wt_kx.clear();
     int ng = 0, extra = 0, gmax = 0;
-    auto add_group = [&](int ky, int cbase, const std::vector<int>& xoffs, const std::vector<int>& kxs) {
+    // halves (two-pixel form only): 0 = the tap feeds both output pixels of a GEMM row (a 128-column MMA), 1 / 2 = only
+    // the first / second pixel (a 64-column MMA into accumulator columns [0, 64) / [64, 128)); carried in bits 8+ of grp_off
+    auto add_group = [&](int ky, int cbase, const std::vector<int>& xoffs, const std::vector<int>& kxs,
+                         const std::vector<int>& halves = std::vector<int>()) {
       const int ty = ky - pad;
       int xmin = xoffs[0];
       for (int v : xoffs) xmin = std::min(xmin, v);
       p.tap_c[ng] = (short)cbase; p.tap_x[ng] = (short)xmin; p.tap_p[ng] = (short)(ty & 1); p.tap_y[ng] = (short)(ty >> 1);
       p.grp_n[ng] = (short)xoffs.size();
       for (size_t t = 0; t < xoffs.size(); ++t) {
-        p.grp_off[ng][t] = (short)(xoffs[t] - xmin);
+        p.grp_off[ng][t] = (short)((xoffs[t] - xmin) | ((halves.empty() ? 0 : halves[t]) << 8));
         extra = std::max(extra, xoffs[t] - xmin);
         plan.wt_ky.push_back(ky); plan.wt_kx.push_back(kxs[t]);
       }
@@ -1883,8 +1891,11 @@ int conv_plan_geometry(ConvPlan& plan, const ConvDesc& d) {
       if (d.slab == 2) {
         // input viewed as quads [(x mod 4, c) = 128, x / 4]: GEMM row m (output pixels 2m, 2m+1) reads quads m-1, m, m+1
         // through the first 64 elements (input x = 4q, 4q+1) and quads m-1, m through the last 64 (x = 4q+2, 4q+3)
-        add_group(ky, 0, {-1, 0, 1}, {0, 0, 0});
-        add_group(ky, 64, {-1, 0}, {0, 0});
+        // Of the three quads read through elements 0, 1 the outer two feed ONE pixel each (q = -1: kx = 0 of pixel 2m;
+        // q = +1: kx = 5, 6 of pixel 2m+1): they are issued as 64-column MMAs into that pixel's accumulator half instead of
+        // multiplying 64 zero weight rows.  The full tap goes first: the first MMA of a tile overwrites all 128 columns.
+        add_group(ky, 0, {0, -1, 1}, {0, 0, 0}, {0, 1, 2});
+        add_group(ky, 64, {-1, 0}, {0, 0}, {0, 0});
       } else if (plan.paired) {   // K block j = x-parity pair (kx = 2j-1, 2j): all pairs of a row are x shifts of each other
         std::vector<int> xo, kxs;
         for (int j = 0; j < (d.k + 1) / 2; ++j) { xo.push_back((2 * j - 1 - pad) >> 1); kxs.push_back(2 * j - 1); }
@@ -2035,10 +2046,16 @@ void conv_pack_weights(const ConvPlan& plan, const float* w, const float* bias, 
     // e = 2, 3; element index inside a block = (e & 1) * 32 + ci.  GEMM row m covers input x = 4 (m + q) + e; output pixel
     // 2m reads x = 4m + kx - 3 (kx = 4q + e + 3), pixel 2m+1 reads x = 4m + kx - 1 (kx = 4q + e + 1); taps outside [0,7)
     // are zero rows (they cost MMA columns but no memory traffic worth mentioning).
+    // K blocks follow the group tables above: elements 0, 1 through quads (0, -1, +1), elements 2, 3 through quads (-1, 0).
+    // A tap that feeds one pixel only is read by a 64-column MMA of the CTA pair, which takes rows 0-31 of EACH CTA's
+    // 64-row share of the tap's weight tile: output channel n of that pixel sits at tile row n (n < 32) or 64 + (n - 32).
     size_t blk = 0;
     for (int ky = 0; ky < d.k; ++ky)
-      for (int half = 0; half < 2; ++half)
-        for (int q = -1; q <= (half == 0 ? 1 : 0); ++q, ++blk)
+      for (int half = 0; half < 2; ++half) {
+        static const int q_order[2][3] = {{0, -1, 1}, {-1, 0, 0}};
+        for (int qi = 0; qi < (half == 0 ? 3 : 2); ++qi, ++blk) {
+          const int q = q_order[half][qi];
+          const bool single = half == 0 && q != 0;   // one pixel only: packed for a 64-column MMA
           for (int el = 0; el < 2; ++el) {
             const int e = 2 * half + el;
             for (int pix = 0; pix < 2; ++pix) {
@@ -2047,10 +2064,15 @@ void conv_pack_weights(const ConvPlan& plan, const float* w, const float* bias, 
               for (int ci = 0; ci < d.cin; ++ci) {
                 const float* src = w + (((size_t)ky * d.k + kx) * d.cin + ci) * d.cout;
                 const size_t kidx = blk * kBlockK + (size_t)el * 32 + ci;
-                for (int n = 0; n < d.cout; ++n) out[(size_t)(pix * d.cout + n) * K + kidx] = cvt(src[n]);
+                for (int n = 0; n < d.cout; ++n) {
+                  const size_t row = single ? (size_t)(n < 32 ? n : 64 + (n - 32)) : (size_t)(pix * d.cout + n);
+                  out[row * K + kidx] = cvt(src[n]);
+                }
               }
             }
           }
+        }
+      }
   } else if (d.stack) {
     // rows in accumulator-column order per (tap, entry); K = the chunks of ONE tap.  Phase (py,px) reads tap (dy,dx)
     // with weight (ky,kx) = (py + 1 - 2 dy, px + 1 - 2 dx) when that lies in [0,4); the head reads every tap with

@@ -257,10 +257,22 @@ def emulate_ex(plan, act):
                 p2 = dict(plan, box_y=1, box_b=1)
                 slab = tma_box(flat, p2, plan["tap_c"][ti], ox0 + plan["tap_x"][ti], plan["tap_p"][ti], y, b, slabW)
                 for t in range(plan["grp_n"][ti]):
-                    off = plan["grp_off"][ti][t]
+                    code = int(plan["grp_off"][ti][t])
+                    off, hf = code & 0xff, code >> 8
                     A = slab[off:off + 128]                       # the row-advanced UMMA window of the slab
                     Wt = plan["w"][w_row:w_row + nb, kcol:kcol + 64]
-                    acc += A.astype(np.float64) @ Wt.astype(np.float64).T
+                    if hf == 0:
+                        if tap == 0 and t == 0:
+                            first_full = True
+                        acc += A.astype(np.float64) @ Wt.astype(np.float64).T
+                    else:
+                        # two-pixel form, a tap that feeds one pixel: a 64-column MMA of the CTA pair reads rows 0-31 of
+                        # each CTA's 64-row share of the tap's weight tile and lands in columns [0,64) (1) or [64,128) (2)
+                        assert nb == 128 and not (tap == 0 and t == 0), "the first MMA of a tile must cover every column"
+                        W64 = np.concatenate([Wt[0:32], Wt[64:96]]).astype(np.float64)
+                        c0 = 64 * (hf - 1)
+                        acc[:, c0:c0 + 64] += A.astype(np.float64) @ W64.T
+                        # rows 32-63 / 96-127 of the tile are never read by that MMA: whatever they hold must not matter
                     kcol += 64
             else:
                 for ch in range(plan["nchunks"]):
