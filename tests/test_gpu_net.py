@@ -491,6 +491,26 @@ def test_layer_chain_bit_identical_to_separate_launches(ofs, cuda_dev, monkeypat
         assert torch.equal(res["0"][0][k], res["1"][0][k]), k
 
 
+def test_deconv_splitk_with_fused_head_matches_default(ofs, cuda_dev, monkeypatch, net_case):
+    """A transposed conv with the fused flow head can run split-K (OFS_TUNE=deconv4:128:3:1: single CTAs, three K splits):
+    every split leaves its share of the head in its own plane and pyr_kernel sums the planes in split order.  The flows
+    then differ from the default tiling only by fp32 summation order (and one bf16 rounding of deconv4's output)."""
+    w, x, net, out = net_case
+    monkeypatch.setenv("OFS_TUNE", "deconv4:128:3:1,deconv5:128:2:1")
+    net2 = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=2, precision="bf16")
+    net2.assign_weights(w)
+    o2 = net2.forward(x.to(cuda_dev))
+    assert net2.launches_per_forward == net.launches_per_forward + 2          # two more split-K reductions
+    for lvl in (6, 5, 4, 3, 2):
+        k = f"predict_flow{lvl}"
+        a, b = out[k].cpu(), o2[k].cpu()
+        mag = float(torch.sqrt((a ** 2).sum(-1)).mean())
+        assert F.epe(b, a) <= 2e-3 * max(mag, 0.1) + 1e-4, (k, F.epe(b, a), mag)
+    c4a, c4b = net.activation("concat4", 2).cpu(), net2.activation("concat4", 2).cpu()
+    assert float((c4a - c4b).abs().max()) <= 2e-2 * float(c4a.abs().max())
+    net2.close()
+
+
 def test_input_pack_kernels_agree(ofs, cuda_dev, monkeypatch):
     """The network input [B,384,512,27] float32 is rounded to 16-bit channels-32 pixels by pack27_kernel (a warp streams 32
     pixels through shared memory with 128-bit loads) when the caller's array is 16-byte aligned, and by the generic
