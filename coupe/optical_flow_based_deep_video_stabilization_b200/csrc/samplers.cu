@@ -1052,7 +1052,7 @@ int launch_warp3(Provider prov, const float* img, float* out, int B, int H, int 
       }
     } else {
       Resize2 rz{};
-      OFS_CUDA(launch_pdl(warp5_kernel<false, true>, tile_grid3(B, H, W), dim3(256), 0, st, img,
+      OFS_CUDA(launch_pdl(warp5_kernel<false, true, 2, 8>, tile_grid3(B, H, W), dim3(256), 0, st, img,
                           reinterpret_cast<const float2*>(prov.flow), rz, out, B, H, W));
       OFS_LAUNCH_CHECK();
       return OFS_OK;
