@@ -23,40 +23,42 @@ sys.path.insert(0, ROOT)
 # name: (H, W, cin, in_cs, cout, out_cs, k, stride, transposed, default variant)
 LAYERS = {
     "1": (384, 512, 27, 32, 64, 64, 7, 2, 0),
-    "2": (192, 256, 64, 64, 128, 200, 5, 2, 0),
-    "3": (96, 128, 128, 200, 256, 256, 5, 2, 0),
-    "3_1": (48, 64, 256, 256, 256, 392, 3, 1, 0),
-    "4": (48, 64, 256, 392, 512, 512, 3, 2, 0),
-    "4_1": (24, 32, 512, 512, 512, 776, 3, 1, 0),
-    "5": (24, 32, 512, 776, 512, 512, 3, 2, 0),
-    "5_1": (12, 16, 512, 512, 512, 1032, 3, 1, 0),
-    "6": (12, 16, 512, 1032, 1024, 1024, 3, 2, 0),
+    "2": (192, 256, 64, 64, 128, 256, 5, 2, 0),
+    "3": (96, 128, 128, 256, 256, 256, 5, 2, 0),
+    "3_1": (48, 64, 256, 256, 256, 448, 3, 1, 0),
+    "4": (48, 64, 256, 448, 512, 512, 3, 2, 0),
+    "4_1": (24, 32, 512, 512, 512, 832, 3, 1, 0),
+    "5": (24, 32, 512, 832, 512, 512, 3, 2, 0),
+    "5_1": (12, 16, 512, 512, 512, 1088, 3, 1, 0),
+    "6": (12, 16, 512, 1088, 1024, 1024, 3, 2, 0),
     "6_1": (6, 8, 1024, 1024, 1024, 1024, 3, 1, 0),
-    "deconv5": (6, 8, 1024, 1024, 512, 1032, 4, 2, 1),
-    "deconv4": (12, 16, 1026, 1032, 256, 776, 4, 2, 1),
-    "deconv3": (24, 32, 770, 776, 128, 392, 4, 2, 1),
-    "deconv2": (48, 64, 386, 392, 64, 200, 4, 2, 1),
-    "predict2": (96, 128, 194, 200, 18, 18, 1, 1, 0),
-    # the same layers with every concat buffer padded to a multiple of 64 channels (128-byte aligned pixel rows for TMA)
-    "2a": (192, 256, 64, 64, 128, 256, 5, 2, 0),
-    "3a": (96, 128, 128, 256, 256, 256, 5, 2, 0),
-    "3_1a": (48, 64, 256, 256, 256, 448, 3, 1, 0),
-    "4a": (48, 64, 256, 448, 512, 512, 3, 2, 0),
-    "4_1a": (24, 32, 512, 512, 512, 832, 3, 1, 0),
-    "5a": (24, 32, 512, 832, 512, 512, 3, 2, 0),
-    "5_1a": (12, 16, 512, 512, 512, 1088, 3, 1, 0),
-    "6a": (12, 16, 512, 1088, 1024, 1024, 3, 2, 0),
-    "deconv5a": (6, 8, 1024, 1024, 512, 1088, 4, 2, 1),
-    "deconv4a": (12, 16, 1026, 1088, 256, 832, 4, 2, 1),
-    "deconv3a": (24, 32, 770, 832, 128, 448, 4, 2, 1),
-    "deconv2a": (48, 64, 386, 448, 64, 256, 4, 2, 1),
+    "deconv5": (6, 8, 1024, 1024, 512, 1088, 4, 2, 1),
+    "deconv4": (12, 16, 1026, 1088, 256, 832, 4, 2, 1),
+    "deconv3": (24, 32, 770, 832, 128, 448, 4, 2, 1),
+    "deconv2": (48, 64, 386, 448, 64, 256, 4, 2, 1),
+    "predict2": (96, 128, 194, 256, 18, 18, 1, 1, 0),
+    # the same layers with TIGHT concat strides (200 / 392 / 776 / 1032 channels: pixel rows not 128-byte aligned, a
+    # 64-channel TMA box row straddles two lines) -- what the network used before round 2's alignment change
+    "2t": (192, 256, 64, 64, 128, 200, 5, 2, 0),
+    "3t": (96, 128, 128, 200, 256, 256, 5, 2, 0),
+    "3_1t": (48, 64, 256, 256, 256, 392, 3, 1, 0),
+    "4t": (48, 64, 256, 392, 512, 512, 3, 2, 0),
+    "4_1t": (24, 32, 512, 512, 512, 776, 3, 1, 0),
+    "5t": (24, 32, 512, 776, 512, 512, 3, 2, 0),
+    "5_1t": (12, 16, 512, 512, 512, 1032, 3, 1, 0),
+    "6t": (12, 16, 512, 1032, 1024, 1024, 3, 2, 0),
+    "deconv5t": (6, 8, 1024, 1024, 512, 1032, 4, 2, 1),
+    "deconv4t": (12, 16, 1026, 1032, 256, 776, 4, 2, 1),
+    "deconv3t": (24, 32, 770, 776, 128, 392, 4, 2, 1),
+    "deconv2t": (48, 64, 386, 392, 64, 200, 4, 2, 1),
+    "predict2t": (96, 128, 194, 200, 18, 18, 1, 1, 0),
     # proxy for conv1 in space-to-depth form (25 K blocks of a 128-column 1-CTA tile on the 192 x 128 pair grid; the real thing has 35)
     "s2d_proxy": (192, 128, 64, 64, 128, 128, 5, 1, 0),
 }
 DEFAULTS = {"1": "64:1:1", "2": "128:1:1", "3": "256:1:1", "3_1": "256:1:1", "4": "256:1:1", "4_1": "256:1:1",
             "5": "256:6:1", "5_1": "256:6:1", "6": "256:8:1", "6_1": "256:8:1", "deconv5": "256:4:1",
             "deconv4": "256:3:1", "deconv3": "128:1:1", "deconv2": "64:1:1", "predict2": "32:1:1", "s2d_proxy": "128:1:1"}
-DEFAULTS.update({k + "a": v for k, v in DEFAULTS.items() if k + "a" in LAYERS})
+DEFAULTS.update({k + "t": v for k, v in DEFAULTS.items() if k + "t" in LAYERS})
 
 
 def macs(name, B):

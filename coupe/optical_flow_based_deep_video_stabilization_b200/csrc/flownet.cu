@@ -40,6 +40,12 @@ namespace {
 using namespace ofs;
 
 constexpr int kNetH = 384, kNetW = 512, kNetC = 27;
+// Channel strides of the concat buffers (logical channels 194 / 386 / 770 / 1026): padded to a multiple of 64 channels, so
+// that every pixel row starts on a 128-byte boundary and a 64-channel TMA box row is ONE aligned 128-byte line.  With the
+// tight strides (200 / 392 / 776 / 1032) a box row straddled two lines: conv3 34.3 -> 31.5 us, conv4 17.7 -> 16.0,
+// conv6 11.7 -> 10.0, deconv3 32.2 -> 24.3, deconv2 40.9 -> 38.7 alone at batch 8 (profiles/r02_tuning.md section 11).
+// The pad channels are zero from allocation on and never written; their packed weights are zero.
+constexpr int kCat2 = 256, kCat3 = 448, kCat4 = 832, kCat5 = 1088;
 constexpr float kBnEps = 1e-5f;
 
 __device__ __forceinline__ uint16_t cvt16(float v, int is_bf16) {
@@ -280,7 +286,7 @@ __global__ void __launch_bounds__(256) predict2_gather_kernel(Predict2Params p) 
 // The sum per output pixel has the terms and the order of predict2_gather_kernel (bias, then ky-major taps; a tap on the
 // zero padding adds +0.0f instead of being skipped: the same value).
 struct P2FusedParams {
-  const uint16_t* concat2;  // [B,96,128,200] 16-bit
+  const uint16_t* concat2;  // [B,96,128,kCat2] 16-bit
   const uint16_t* w;        // packed predict2 product weights [32 rows][256] K-major; row (ky*3+kx)*2 + o
   const float2* f3;         // [B,48,64]
   float2* f2;               // [B,382,510]
@@ -338,11 +344,10 @@ __global__ void __launch_bounds__(kP2Threads, 3) predict2_fused_kernel(P2FusedPa
       const int rr = pp / kP2RegionW, cc = pp - rr * kP2RegionW;
       const int sr = r0 + rr, sc = c0 + cc;
       valid[h] = pp < kP2Region && sr < 96 && sc < 128;
-      rowp[h] = reinterpret_cast<const uint4*>(p.concat2 + ((size_t)(b * 96 + min(sr, 95)) * 128 + min(sc, 127)) * 200);
+      rowp[h] = reinterpret_cast<const uint4*>(p.concat2 + ((size_t)(b * 96 + min(sr, 95)) * 128 + min(sc, 127)) * kCat2);
     }
     float acc[3][4] = {};
-    // 16-byte unit 4 kb + t of the 400-byte pixel row; the last block's units past the row (elements >= 200, zero
-    // weights) re-read the row's last unit.  The loads of block kb + 2 are in flight while block kb is multiplied.
+    // 16-byte unit 4 kb + t of the pixel row; the last block's units past element 200 (zero weights) re-read unit 24.  The loads of block kb + 2 are in flight while block kb is multiplied.
     uint4 va[3], vb[3];
     va[0] = __ldg(rowp[0] + t); vb[0] = __ldg(rowp[1] + t);
     va[1] = __ldg(rowp[0] + 4 + t); vb[1] = __ldg(rowp[1] + 4 + t);
@@ -746,10 +751,10 @@ int launch_pyr(ofs_net* n, int level, int B, cudaStream_t st) {
   p.up_w = n->upw + (6 - level) * 66;
   p.B = B; p.h = hs[level]; p.w = ws[level]; p.is_bf16 = n->is_bf16;
   switch (level) {
-    case 6: p.concat = (uint16_t*)n->concat5; p.cstride = 1032; p.coff = 1024; break;
-    case 5: p.concat = (uint16_t*)n->concat4; p.cstride = 776; p.coff = 768; break;
-    case 4: p.concat = (uint16_t*)n->concat3; p.cstride = 392; p.coff = 384; break;
-    default: p.concat = (uint16_t*)n->concat2; p.cstride = 200; p.coff = 192; break;
+    case 6: p.concat = (uint16_t*)n->concat5; p.cstride = kCat5; p.coff = 1024; break;
+    case 5: p.concat = (uint16_t*)n->concat4; p.cstride = kCat4; p.coff = 768; break;
+    case 4: p.concat = (uint16_t*)n->concat3; p.cstride = kCat3; p.coff = 384; break;
+    default: p.concat = (uint16_t*)n->concat2; p.cstride = kCat2; p.coff = 192; break;
   }
   const size_t total = (size_t)B * 4 * p.h * p.w;
   const int blocks = (int)std::min<size_t>((total + 127) / 128, (size_t)sm_count() * 8);
@@ -941,9 +946,9 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
   if (rc != OFS_OK) { ofs_net_destroy(n); return rc; }
   const size_t B = (size_t)max_batch;
   struct { void** p; size_t elems; } bufs[] = {
-      {&n->x0, B * 384 * 512 * 32},    {&n->conv1, B * 192 * 256 * 64}, {&n->concat2, B * 96 * 128 * 200},
-      {&n->conv3, B * 48 * 64 * 256},  {&n->concat3, B * 48 * 64 * 392}, {&n->conv4, B * 24 * 32 * 512},
-      {&n->concat4, B * 24 * 32 * 776}, {&n->conv5, B * 12 * 16 * 512},  {&n->concat5, B * 12 * 16 * 1032},
+      {&n->x0, B * 384 * 512 * 32},    {&n->conv1, B * 192 * 256 * 64}, {&n->concat2, B * 96 * 128 * kCat2},
+      {&n->conv3, B * 48 * 64 * 256},  {&n->concat3, B * 48 * 64 * kCat3}, {&n->conv4, B * 24 * 32 * 512},
+      {&n->concat4, B * 24 * 32 * kCat4}, {&n->conv5, B * 12 * 16 * 512},  {&n->concat5, B * 12 * 16 * kCat5},
       {&n->conv6, B * 6 * 8 * 1024},   {&n->conv6_1, B * 6 * 8 * 1024}};
   for (auto& b : bufs) {
     rc = dev_alloc(n, b.p, b.elems * 2, true);
@@ -993,21 +998,21 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
   // execution order (model.py:807-885).  in_cs / out_cstride are the physical channel strides.
   auto& Ls = n->layers;
   Ls.push_back(make_layer("1", "1", kConv, 384, 512, 27, 32, 64, 7, 2, 64, 0, 1, 64, 0, n->x0, n->conv1));
-  Ls.push_back(make_layer("2", "2", kConv, 192, 256, 64, 64, 128, 5, 2, 128, 0, 1, 200, 0, n->conv1, n->concat2));
-  Ls.push_back(make_layer("3", "3", kConv, 96, 128, 128, 200, 256, 5, 2, 128, 0, 1, 256, 0, n->concat2, n->conv3));
-  Ls.push_back(make_layer("3_1", "3_1", kConv, 48, 64, 256, 256, 256, 3, 1, 128, 0, 1, 392, 0, n->conv3, n->concat3));
-  Ls.push_back(make_layer("4", "4", kConv, 48, 64, 256, 392, 512, 3, 2, 128, 0, 1, 512, 0, n->concat3, n->conv4));
-  Ls.push_back(make_layer("4_1", "4_1", kConv, 24, 32, 512, 512, 512, 3, 1, 128, 0, 1, 776, 0, n->conv4, n->concat4));
-  Ls.push_back(make_layer("5", "5", kConv, 24, 32, 512, 776, 512, 3, 2, 128, 0, 1, 512, 0, n->concat4, n->conv5));
-  Ls.push_back(make_layer("5_1", "5_1", kConv, 12, 16, 512, 512, 512, 3, 1, 128, 0, 1, 1032, 0, n->conv5, n->concat5));
-  Ls.push_back(make_layer("6", "6", kConv, 12, 16, 512, 1032, 1024, 3, 2, 128, 0, 1, 1024, 0, n->concat5, n->conv6));
+  Ls.push_back(make_layer("2", "2", kConv, 192, 256, 64, 64, 128, 5, 2, 128, 0, 1, kCat2, 0, n->conv1, n->concat2));
+  Ls.push_back(make_layer("3", "3", kConv, 96, 128, 128, kCat2, 256, 5, 2, 128, 0, 1, 256, 0, n->concat2, n->conv3));
+  Ls.push_back(make_layer("3_1", "3_1", kConv, 48, 64, 256, 256, 256, 3, 1, 128, 0, 1, kCat3, 0, n->conv3, n->concat3));
+  Ls.push_back(make_layer("4", "4", kConv, 48, 64, 256, kCat3, 512, 3, 2, 128, 0, 1, 512, 0, n->concat3, n->conv4));
+  Ls.push_back(make_layer("4_1", "4_1", kConv, 24, 32, 512, 512, 512, 3, 1, 128, 0, 1, kCat4, 0, n->conv4, n->concat4));
+  Ls.push_back(make_layer("5", "5", kConv, 24, 32, 512, kCat4, 512, 3, 2, 128, 0, 1, 512, 0, n->concat4, n->conv5));
+  Ls.push_back(make_layer("5_1", "5_1", kConv, 12, 16, 512, 512, 512, 3, 1, 128, 0, 1, kCat5, 0, n->conv5, n->concat5));
+  Ls.push_back(make_layer("6", "6", kConv, 12, 16, 512, kCat5, 1024, 3, 2, 128, 0, 1, 1024, 0, n->concat5, n->conv6));
   Ls.push_back(make_layer("6_1", "6_1", kConv, 6, 8, 1024, 1024, 1024, 3, 1, 128, 0, 1, 1024, 0, n->conv6, n->conv6_1));
-  Ls.push_back(make_layer("deconv5", "deconv5_bn", kDeconvK4S2, 6, 8, 1024, 1024, 512, 4, 2, 128, 0, 1, 1032, 512, n->conv6_1, n->concat5));
-  Ls.push_back(make_layer("deconv4", "deconv4_bn", kDeconvK4S2, 12, 16, 1026, 1032, 256, 4, 2, 128, 0, 1, 776, 512, n->concat5, n->concat4));
-  Ls.push_back(make_layer("deconv3", "deconv3_bn", kDeconvK4S2, 24, 32, 770, 776, 128, 4, 2, 128, 0, 1, 392, 256, n->concat4, n->concat3));
-  Ls.push_back(make_layer("deconv2", "deconv2_bn", kDeconvK4S2, 48, 64, 386, 392, 64, 4, 2, 64, 0, 1, 200, 128, n->concat3, n->concat2));
+  Ls.push_back(make_layer("deconv5", "deconv5_bn", kDeconvK4S2, 6, 8, 1024, 1024, 512, 4, 2, 128, 0, 1, kCat5, 512, n->conv6_1, n->concat5));
+  Ls.push_back(make_layer("deconv4", "deconv4_bn", kDeconvK4S2, 12, 16, 1026, kCat5, 256, 4, 2, 128, 0, 1, kCat4, 512, n->concat5, n->concat4));
+  Ls.push_back(make_layer("deconv3", "deconv3_bn", kDeconvK4S2, 24, 32, 770, kCat4, 128, 4, 2, 128, 0, 1, kCat3, 256, n->concat4, n->concat3));
+  Ls.push_back(make_layer("deconv2", "deconv2_bn", kDeconvK4S2, 48, 64, 386, kCat3, 64, 4, 2, 64, 0, 1, kCat2, 128, n->concat3, n->concat2));
   // predict2 as a 1x1 GEMM with 18 columns on the 96x128 grid
-  Ls.push_back(make_layer("predict2", "", kConv, 96, 128, 194, 200, 18, 1, 1, 32, 1, 0, 18, 0, n->concat2, n->P2));
+  Ls.push_back(make_layer("predict2", "", kConv, 96, 128, 194, kCat2, 18, 1, 1, 32, 1, 0, 18, 0, n->concat2, n->P2));
   n->heads = {Head{"predict6", 6, 1024}, Head{"predict5", 5, 1026}, Head{"predict4", 4, 770}, Head{"predict3", 3, 386}};
   // Deep layers have few output tiles (conv6_1 at B=8: 32) but long K loops: their K loop is split over
   // several CTAs (fp32 partials in a workspace, summed in a fixed order).  The factors are constants of the
@@ -1017,10 +1022,9 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
   for (Layer& L : Ls) {
     if ((L.name == "1" || L.name == "2") && !(getenv("OFS_NOSLAB") && getenv("OFS_NOSLAB")[0] == '1')) {
       L.d.slab = 1; L.d.cta_group = 2;   // x-shifted taps share one A slab per stage (CTA pairs); fixes the packed K order
-      // conv1 with two output pixels per GEMM row (quad view, 128-column MMAs over 5 quad taps per kernel row instead of
-      // 64-column MMAs over 2 x 4 pair taps): built and tested, -6 % cycles but the zero-weight halves of the two edge taps
-      // cost power -- under the 1 kW cap the clock drops by as much (79.5 vs 74.6 us alone, profiles/r02_tuning.md).
-      // OFS_CONV1X2=1 selects it.
+      // conv1 with two output pixels per GEMM row (quad view; per kernel row 3 128-column and 2 64-column MMAs over quad
+      // taps instead of 2 x 4 64-column MMAs over pair taps): built and tested, 74.6 vs 76.3 us alone, parity in the
+      // step (profiles/r02_tuning.md sections 4 and 9).  OFS_CONV1X2=1 selects it.
       if (L.name == "1" && getenv("OFS_CONV1X2") && getenv("OFS_CONV1X2")[0] == '1') { L.d.slab = 2; L.d.block_n = 128; }
     } else if (L.name == "3") { L.block_n_run = 256; L.cta_group = 2; }   // CTA pairs: 36.9 vs 40.3 us (conv_bench)
     else if (L.name == "3_1") { L.block_n_run = 256; }
@@ -1058,13 +1062,13 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
     if (rc != OFS_OK) { ofs_net_destroy(n); return rc; }
   }
   n->acts = {
-      {"conv1", {n->conv1, 192, 256, 64, 0, 64}},       {"conv2", {n->concat2, 96, 128, 200, 0, 128}},
-      {"conv3", {n->conv3, 48, 64, 256, 0, 256}},       {"conv3_1", {n->concat3, 48, 64, 392, 0, 256}},
-      {"conv4", {n->conv4, 24, 32, 512, 0, 512}},       {"conv4_1", {n->concat4, 24, 32, 776, 0, 512}},
-      {"conv5", {n->conv5, 12, 16, 512, 0, 512}},       {"conv5_1", {n->concat5, 12, 16, 1032, 0, 512}},
+      {"conv1", {n->conv1, 192, 256, 64, 0, 64}},       {"conv2", {n->concat2, 96, 128, kCat2, 0, 128}},
+      {"conv3", {n->conv3, 48, 64, 256, 0, 256}},       {"conv3_1", {n->concat3, 48, 64, kCat3, 0, 256}},
+      {"conv4", {n->conv4, 24, 32, 512, 0, 512}},       {"conv4_1", {n->concat4, 24, 32, kCat4, 0, 512}},
+      {"conv5", {n->conv5, 12, 16, 512, 0, 512}},       {"conv5_1", {n->concat5, 12, 16, kCat5, 0, 512}},
       {"conv6", {n->conv6, 6, 8, 1024, 0, 1024}},       {"conv6_1", {n->conv6_1, 6, 8, 1024, 0, 1024}},
-      {"concat5", {n->concat5, 12, 16, 1032, 0, 1026}}, {"concat4", {n->concat4, 24, 32, 776, 0, 770}},
-      {"concat3", {n->concat3, 48, 64, 392, 0, 386}},   {"concat2", {n->concat2, 96, 128, 200, 0, 194}},
+      {"concat5", {n->concat5, 12, 16, kCat5, 0, 1026}}, {"concat4", {n->concat4, 24, 32, kCat4, 0, 770}},
+      {"concat3", {n->concat3, 48, 64, kCat3, 0, 386}},   {"concat2", {n->concat2, 96, 128, kCat2, 0, 194}},
       {"input", {n->x0, 384, 512, 32, 0, 27}}};
   *out = n;
   return OFS_OK;
