@@ -1027,27 +1027,30 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
       // step (profiles/r02_tuning.md sections 4 and 9).  OFS_CONV1X2=1 selects it.
       if (L.name == "1" && getenv("OFS_CONV1X2") && getenv("OFS_CONV1X2")[0] == '1') { L.d.slab = 2; L.d.block_n = 128; }
     } else if (L.name == "3") { L.block_n_run = 256; L.cta_group = 2; }   // CTA pairs: 36.9 vs 40.3 us (conv_bench)
-    else if (L.name == "3_1") { L.block_n_run = 256; }
+    // (tilings below re-measured on the 64-channel-aligned concat strides: profiles/r02_sweep_aligned_strides.txt)
+    else if (L.name == "3_1") { L.block_n_run = 256; L.cta_group = 2; }   // pairs 24.4 vs 25.3 us
     // cout 512 on 48 M tiles: 3 N tiles of 192 (the last one a third empty, clipped by the TMA store) = 144 tiles, ONE
     // wave on 148 SMs, instead of 2 x 256 = 96 tiles on 65 % of the SMs (-25 % time, conv_bench A/B)
-    // conv4 on CTA pairs (72 pair tiles on 74 pair slots; 16 KB of A + 12 KB of B per K block and CTA instead of 16 + 24):
-    // 17.8 vs 18.5 us isolated; conv4_1 measured the other way round (24.7 vs 23.7 us) and stays on single CTAs
-    // (profiles/r02_tuning.md)
-    else if (L.name == "4" || L.name == "4_1") { L.d.block_n = 192; if (L.name == "4") L.cta_group = 2; }
+    // single CTAs for both: conv4 15.0 vs 16.1 us on pairs, conv4_1 23.8 vs 24.8 (with the tight strides conv4 was faster
+    // on pairs, 17.8 vs 18.5)
+    else if (L.name == "4" || L.name == "4_1") { L.d.block_n = 192; }
     else if (L.name == "5" || L.name == "5_1") { L.block_n_run = 256; L.ksplit = 6; }
     // conv6 / conv6_1 (M = 384 rows): 128-column tiles x split-K 4 = 128 units move half the fp32 partials of 256 x 8
     // (alone: 11.8 vs 12.2 and 13.1 vs 14.8 us, profiles/r02_sweep_small_layers.txt)
     else if (L.name == "6" || L.name == "6_1") { L.block_n_run = 128; L.ksplit = 4; }
     // the level's flow head rides in the deconv GEMM (128 / 64-column tiles); CTA pairs halve the B fetch per CTA
     else if (L.d.kind == kDeconvK4S2) {
-      L.d.head = 1; L.cta_group = L.name == "deconv5" ? 1 : 2;   // deconv5 (3 M tiles): single CTAs 13.8 vs 14.5 us
+      // single CTAs: deconv5 13.8 vs 14.5 us on pairs, deconv4 22.7 vs 24.4; deconv3 on pairs 24.7 vs 25.4
+      L.d.head = 1; L.cta_group = L.name == "deconv3" ? 2 : 1;
       // deconv4 (M = 1536 rows: 12 M tiles x 4 phases = 48 units of 68 K blocks) keeps a third of the machine busy, but
       // single CTAs x split-K 3 = 144 units (the head's shares leave per split and are summed by pyr_kernel: built,
       // tested, OFS_TUNE=deconv4:128:3:1) measured 27.1 us against 24.5 us for the pairs: the fp32 partials and the
       // reduce launch cost more than the idle SMs (profiles/r02_tuning.md section 7)
-      // deconv2 (cout 64): all four sub-pixel phases stacked in one accumulator tile, each input tap fetched once
-      // (deconv_stack_kernel); fixes the packed weight layout.  OFS_NOSTACK=1: the per-phase form (A/B).
-      if (L.name == "deconv2" && !(getenv("OFS_NOSTACK") && getenv("OFS_NOSTACK")[0] == '1')) { L.d.stack = 1; L.d.cta_group = 2; }
+      // deconv2 (cout 64) has a second form: all four sub-pixel phases stacked in one accumulator tile, each input tap
+      // fetched once (deconv_stack_kernel; fixes the packed weight layout).  It beat the per-phase form while the A boxes
+      // straddled cache lines (40.4 vs 46.4 us); on the aligned strides the per-phase form is the faster one -- 33.4 us on
+      // single CTAs, 33.7 on pairs, against 38.5 / 39.2 stacked -- and is the default.  OFS_STACK=1: the stacked form (A/B).
+      if (L.name == "deconv2" && getenv("OFS_STACK") && getenv("OFS_STACK")[0] == '1') { L.d.stack = 1; L.d.cta_group = 2; }
     }
   }
   for (Layer& L : Ls) {

@@ -513,6 +513,28 @@ def test_deconv_splitk_with_fused_head_matches_default(ofs, cuda_dev, monkeypatc
     net2.close()
 
 
+def test_stacked_deconv2_matches_per_phase_form(ofs, cuda_dev, monkeypatch, net_case):
+    """deconv2 + predict3 in the phase-stacked form (OFS_STACK=1: one 304-column accumulator tile, nine taps fetched once)
+    against the default per-phase form at network level: same products, another fp32 summation order."""
+    w, x, net, _ = net_case
+    out = {k: v.clone() for k, v in net.forward(x.to(cuda_dev)).items()}
+    c2a = net.activation("concat2", 2).cpu()
+    monkeypatch.setenv("OFS_STACK", "1")
+    net2 = ofs.FlowNetSPyramid(device=cuda_dev, max_batch=2, precision="bf16")
+    net2.assign_weights(w)
+    o2 = net2.forward(x.to(cuda_dev))
+    for lvl in (3, 2):
+        k = f"predict_flow{lvl}"
+        a, b = out[k].cpu(), o2[k].cpu()
+        mag = float(torch.sqrt((a ** 2).sum(-1)).mean())
+        assert F.epe(b, a) <= 2e-3 * max(mag, 0.1) + 1e-4, (k, F.epe(b, a), mag)
+    for lvl in (6, 5, 4):
+        assert torch.equal(out[f"predict_flow{lvl}"], o2[f"predict_flow{lvl}"])
+    c2b = net2.activation("concat2", 2).cpu()
+    assert float((c2a - c2b).abs().max()) <= 2e-2 * float(c2a.abs().max())
+    net2.close()
+
+
 def test_input_pack_kernels_agree(ofs, cuda_dev, monkeypatch):
     """The network input [B,384,512,27] float32 is rounded to 16-bit channels-32 pixels by pack27_kernel (a warp streams 32
     pixels through shared memory with 128-bit loads) when the caller's array is 16-byte aligned, and by the generic
