@@ -2496,6 +2496,7 @@ extern "C" int ofs_conv2d_bench(int B, int H, int W, int Cin, int in_cs, int Cou
   d.kcluster = cta_group == 16 ? 1 : 0;
   if (cta_group == 64 || cta_group == 66) { d.stack = 1; d.head = 1; d.cta_group = cta_group == 66 ? 2 : 1; }
   if (cta_group == 34 || cta_group == 36) { d.head = 1; d.cta_group = cta_group == 36 ? 2 : 1; }   // per-phase form with the fused head
+  if (cta_group == 40) { d.head = 1; d.cta_group = 1; d.kgroup = 2; }                              // ... with two K chunks per stage
   const bool out16 = (Cout % block_n) == 0 || (!transposed && block_n >= 64 && Cout % 64 == 0 && ksplit <= 1);
   d.out_mode = out16 ? 0 : 1; d.lrelu = 1; d.is_bf16 = 1; d.out_cstride = out_cs; d.out_coff = 0;
   ConvPlan plan;
