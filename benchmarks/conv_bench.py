@@ -55,9 +55,10 @@ LAYERS = {
     # proxy for conv1 in space-to-depth form (25 K blocks of a 128-column 1-CTA tile on the 192 x 128 pair grid; the real thing has 35)
     "s2d_proxy": (192, 128, 64, 64, 128, 128, 5, 1, 0),
 }
-DEFAULTS = {"1": "64:1:1", "2": "128:1:1", "3": "256:1:1", "3_1": "256:1:1", "4": "256:1:1", "4_1": "256:1:1",
-            "5": "256:6:1", "5_1": "256:6:1", "6": "256:8:1", "6_1": "256:8:1", "deconv5": "256:4:1",
-            "deconv4": "256:3:1", "deconv3": "128:1:1", "deconv2": "64:1:1", "predict2": "32:1:1", "s2d_proxy": "128:1:1"}
+# the network's own tilings (flownet.cu, ofs_net_create): block_n:ksplit:cta_group code
+DEFAULTS = {"1": "64:1:4", "2": "128:1:4", "3": "256:1:2", "3_1": "256:1:2", "4": "192:1:1", "4_1": "192:1:1",
+            "5": "256:6:1", "5_1": "256:6:1", "6": "128:4:1", "6_1": "128:4:1", "deconv5": "64:1:34",
+            "deconv4": "128:1:34", "deconv3": "128:1:36", "deconv2": "64:1:34", "predict2": "32:1:32", "s2d_proxy": "128:1:1"}
 DEFAULTS.update({k + "t": v for k, v in DEFAULTS.items() if k + "t" in LAYERS})
 
 
