@@ -74,10 +74,10 @@ def raw(rep):
 
 
 def full_summary():
-    labels = ["conv1 (slab, pairs)", "conv2 (slab, pairs)", "conv3 (pairs)", "conv3_1", "conv4 (192, pairs)", "conv4_1 (192)",
+    labels = ["conv1 (slab, pairs)", "conv2 (slab, pairs)", "conv3 (pairs)", "conv3_1 (pairs)", "conv4 (192)", "conv4_1 (192)",
               "conv5 (split-K 6)", "conv5 reduce", "conv5_1 (split-K 6)", "conv5_1 reduce", "conv6 (128 cols, split-K 4)", "conv6 reduce",
-              "conv6_1 (128 cols, split-K 4)", "conv6_1 reduce", "deconv5 + predict6 (1 CTA)", "deconv4 + predict5 (pairs)",
-              "deconv3 + predict4 (pairs)", "deconv2 + predict3 (stacked, pairs)", "predict2 1x1 product"]
+              "conv6_1 (128 cols, split-K 4)", "conv6_1 reduce", "deconv5 + predict6 (1 CTA)", "deconv4 + predict5 (1 CTA)",
+              "deconv3 + predict4 (pairs)", "deconv2 + predict3 (per phase, 1 CTA)", "predict2 1x1 product"]
     traffic = {"how": "ncu --set full --clock-control none, one step of `OFS_GRAPH=0 python bench.py --steps 2 --warmup 1 --no-cpu-baseline "
                       "--sustained-seconds 0` in launch order; dram__bytes_read.sum + dram__bytes_write.sum per launch", "per_launch": []}
     out = [f"# ncu --set full summaries ({tag}, B200, `OFS_GRAPH=0 python bench.py --steps 2 --warmup 1 --no-cpu-baseline`)", "",
