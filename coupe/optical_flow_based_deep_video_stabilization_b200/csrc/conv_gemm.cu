@@ -2333,7 +2333,9 @@ int launch_pack_act(const float* in, void* out, size_t npix, int cin, int cs, in
   static const bool generic_only = [] { const char* e = getenv("OFS_PACK27"); return e && e[0] == '0'; }();   // A/B switch
   if (cin == 27 && cs == 32 && !generic_only && ((uintptr_t)in % 16) == 0 && (npix % 32) == 0) {   // the network input
     const size_t nchunks = npix / 32;
-    const size_t blocks = std::min<size_t>((nchunks + kPack27Warps - 1) / kPack27Warps, (size_t)sm_count() * 6);
+    // one 32-pixel chunk per warp, no grid-stride loop: 46.3 us against 50 us with 6 blocks per SM looping (the block
+    // scheduler balances the tail better than a fixed stride does); the cap only bounds the grid for huge inputs
+    const size_t blocks = std::min<size_t>((nchunks + kPack27Warps - 1) / kPack27Warps, (size_t)sm_count() * 64);
     OFS_CUDA(launch_pdl(pack27_kernel, dim3((unsigned)blocks), dim3(32 * kPack27Warps), 0, st, reinterpret_cast<const float4*>(in),
                         reinterpret_cast<uint4*>(out), nchunks, is_bf16));
     OFS_LAUNCH_CHECK();
