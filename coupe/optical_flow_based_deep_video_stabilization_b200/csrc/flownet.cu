@@ -1023,8 +1023,12 @@ int ofs_net_create(ofs_net** out, int device, int max_batch, int precision) {
     if ((L.name == "1" || L.name == "2") && !(getenv("OFS_NOSLAB") && getenv("OFS_NOSLAB")[0] == '1')) {
       L.d.slab = 1; L.d.cta_group = 2;   // x-shifted taps share one A slab per stage (CTA pairs); fixes the packed K order
       // conv1 with two output pixels per GEMM row (quad view; per kernel row 3 128-column and 2 64-column MMAs over quad
-      // taps instead of 2 x 4 64-column MMAs over pair taps): built and tested, 74.6 vs 76.3 us alone, parity in the
-      // step (profiles/r02_tuning.md sections 4 and 9).  OFS_CONV1X2=1 selects it.
+      // taps instead of 2 x 4 64-column MMAs over pair taps): built and tested, 74.6 vs 76.3 us alone, +0.4 % pairs/s one
+      // step at a time and +2 % with two in flight.  Its conv1 output differs from the one-pixel form's in 0.016 % of the
+      // elements by one bf16 ulp (another fp32 summation order), which the network amplifies to 0.009 px of flow: the
+      // EPE against the fp32 oracle lands at 0.0165 / 0.0179 px instead of 0.0153 / 0.0151 on the two test inputs -- inside
+      // the 0.02 px bound, but with less margin, so the one-pixel form stays the default (profiles/r02_tuning.md
+      // sections 4 and 9).  OFS_CONV1X2=1 selects it.
       if (L.name == "1" && getenv("OFS_CONV1X2") && getenv("OFS_CONV1X2")[0] == '1') { L.d.slab = 2; L.d.block_n = 128; }
     } else if (L.name == "3") { L.block_n_run = 256; L.cta_group = 2; }   // CTA pairs: 36.9 vs 40.3 us (conv_bench)
     // (tilings below re-measured on the 64-channel-aligned concat strides: profiles/r02_sweep_aligned_strides.txt)
